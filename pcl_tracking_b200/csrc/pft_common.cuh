@@ -1,0 +1,151 @@
+// pft_common.cuh -- internal helpers shared by the sm_100a kernels of the tracker.
+//
+// Arithmetic contract (DESIGN.md "Arithmetic contract"): this library is compiled with
+// -fmad=false, so every fp32/fp64 add and multiply is rounded on its own exactly as the x86-64
+// default-march build of PCL does it; sin/cos/atan2/asin/exp are evaluated in double and rounded
+// to float where PCL calls the float overloads.  That is what makes nearest-neighbour indices
+// comparable bit-for-bit with the CPU oracle.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <float.h>
+
+namespace pft {
+
+constexpr int kWarp = 32;
+constexpr unsigned kFull = 0xffffffffu;
+
+// ------------------------------------------------------------------ error plumbing (host)
+void set_last_error(const char* fmt, ...);
+extern unsigned long long g_launch_count;
+#define PFT_CUDA_TRY(expr)                                                                         \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess) {                                                                       \
+      ::pft::set_last_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return PFT_ERR_CUDA;                                                                         \
+    }                                                                                              \
+  } while (0)
+#define PFT_LAUNCH_CHECK()                                                                         \
+  do {                                                                                             \
+    ++::pft::g_launch_count;                                                                       \
+    cudaError_t _e = cudaGetLastError();                                                           \
+    if (_e != cudaSuccess) {                                                                       \
+      ::pft::set_last_error("%s:%d: kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+      return PFT_ERR_CUDA;                                                                         \
+    }                                                                                              \
+  } while (0)
+
+// ------------------------------------------------------------------ device structs
+// Device point: float4 {x, y, z, bits}.  bits = rgba for clouds, packed HSV (h | s<<8 | v<<16) for
+// the model and the sorted scene index.
+struct __align__(16) DevParticle { float x, y, z, one, roll, pitch, yaw, weight; };  // = pcl ParticleXYZRPY
+
+// Device-resident cloud header: the point count lives on the device so that no stage needs a host
+// round trip (cloud sizes after K1, particle counts after the KLD resample).
+struct CloudHeader { int n; int pad[3]; };
+
+// Scene index header, recomputed by every weight() call from the crop AABB.
+struct IndexHeader {
+  float aabb[6];      // crop box: minx,miny,minz,maxx,maxy,maxz (inclusive, fp32)
+  int origin[3];      // lattice coordinate (at `level`) of cell (0,0,0)
+  int dim[3];         // cells per axis
+  int level;          // cell edge = leaf * 2^level
+  int wx;             // 32-bit words per x-row
+  int n_words;        // wx * dim[1] * dim[2]
+  int n_cropped;      // scene points inside the crop box
+  int n_occupied;     // occupied cells (= primary slots)
+  int n_overflow;     // points sharing a cell with an earlier one (chained)
+  float cell;         // cell edge in metres
+  float inv_leaf;     // 1 / leaf  (lattice = floor(coord * inv_leaf) >> level)
+  float level_scale;  // 2^-level
+  int valid;          // 0: empty AABB (no model / no particles)
+};
+
+// ------------------------------------------------------------------ device helpers
+__device__ __forceinline__ void atomic_min_float(float* addr, float v) {
+  if (v >= 0.f) atomicMin(reinterpret_cast<int*>(addr), __float_as_int(v));
+  else atomicMax(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+__device__ __forceinline__ void atomic_max_float(float* addr, float v) {
+  if (v >= 0.f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+  else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(kFull, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(kFull, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+
+// Block-wide sum of doubles; result valid in thread 0.  `red` holds >= 32 doubles.
+__device__ __forceinline__ double block_sum(double v, double* red) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  if (wid == 0) {
+    double t = lane < nw ? red[lane] : 0.0;
+    t = warp_sum(t);
+    v = t;
+  }
+  return v;
+}
+
+// Exclusive scan over n values produced by `load(i)`, written through `store(i, exclusive_prefix)`,
+// executed by ONE thread block (any size that is a multiple of 32, <= 1024).  Returns the grand
+// total to every thread.  Integer types only: the result is independent of the association order,
+// which is what makes cumulative tables bit-identical to a sequential CPU loop.
+template <typename T, typename Load, typename Store>
+__device__ T block_exclusive_scan(int n, Load load, Store store, T* smem /* >= 33 entries */) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  constexpr int ITEMS = 4;
+  T carry = 0;
+  const int tile = blockDim.x * ITEMS;
+  for (int base = 0; base < n; base += tile) {
+    T v[ITEMS];
+    T sum = 0;
+    const int i0 = base + threadIdx.x * ITEMS;
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) { v[k] = (i0 + k < n) ? load(i0 + k) : T(0); sum += v[k]; }
+    T inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { T t = __shfl_up_sync(kFull, inc, o); if (lane >= o) inc += t; }
+    __syncthreads();
+    if (lane == 31) smem[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+      T w = lane < nw ? smem[lane] : T(0);
+      T winc = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { T t = __shfl_up_sync(kFull, winc, o); if (lane >= o) winc += t; }
+      smem[lane] = winc - w;            // exclusive prefix of warp totals
+      if (lane == 31) smem[32] = winc;  // tile total
+    }
+    __syncthreads();
+    T ex = carry + smem[wid] + (inc - sum);
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) { if (i0 + k < n) store(i0 + k, ex); ex += v[k]; }
+    carry += smem[32];
+  }
+  __syncthreads();
+  return carry;
+}
+
+}  // namespace pft

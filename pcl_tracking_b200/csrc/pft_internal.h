@@ -1,0 +1,55 @@
+// pft_internal.h -- host-side objects behind the opaque C handles and the kernel launchers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <vector>
+
+#include "../../include/pft/pft.h"
+#include "pft_common.cuh"
+
+namespace pft {
+
+// Grow-only device buffer.
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  int reserve(size_t need);
+  void release();
+  template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+}  // namespace pft
+
+struct pft_context {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  // K1 scratch
+  pft::DevBuf k1_keys, k1_first, k1_vid, k1_slot_of, k1_acc_xyz, k1_acc_rgbc, k1_blk, staging, tmp_cloud_pts, tmp_hdr, tmp_f;
+  void* pinned = nullptr;  // small pinned buffer for scalar read-backs
+  size_t pinned_bytes = 0;
+};
+
+struct pft_cloud {
+  pft_context* ctx = nullptr;
+  pft::DevBuf pts;              // float4[capacity]
+  pft::DevBuf hdr;              // CloudHeader
+  size_t capacity = 0;          // host-known upper bound on n
+  long long host_n = -1;        // exact n if known on the host, else -1
+  float4* d_pts() const { return pts.as<float4>(); }
+  pft::CloudHeader* d_hdr() const { return hdr.as<pft::CloudHeader>(); }
+  int ensure(size_t cap);
+};
+
+namespace pft {
+
+// ---- filters (pft_filters.cu)
+int launch_unpack_pcl32(cudaStream_t s, const void* src32, float4* dst, size_t n);
+int launch_pack_pcl32(cudaStream_t s, const float4* src, void* dst32, size_t n);
+int launch_set_header(cudaStream_t s, CloudHeader* hdr, int n);
+int run_passthrough(pft_context* ctx, const pft_cloud* in, pft_cloud* out, int field, float lo, float hi, int drop_zero);
+int run_voxel_grid(pft_context* ctx, const pft_cloud* in, pft_cloud* out, float leaf, int field, float lo, float hi);
+int run_centre_on_centroid(pft_context* ctx, pft_cloud* cloud, float* d_centroid3);
+
+}  // namespace pft

@@ -1,0 +1,1195 @@
+// pft_tracker.cu -- C ABI of the tracker object (include/pft/pft.h) and the host-side sequencing of
+// kernels K2 (scene index), K3 (weight) and K4 (normalise / resample / update).
+//
+// Replaces pcl::tracking::KLDAdaptiveParticleFilterOMPTracker / ParticleFilterOMPTracker as configured
+// and driven by ref: src/auto_tracking.cpp:198-258 (knobs), :673-676 (reference cloud), :688-697
+// (setInputCloud + compute per frame), :270 / :309-310 (read-out).  Upstream control flow restated in
+// compute() = initCompute (initParticles on first use) + iteration_num x
+// { resample (if changed_) ; weight ; update (if changed_) }.
+//
+// Everything a frame needs lives on the device (particle set, live particle count, crop box, index
+// header, weights, representative state), so one compute() is a fixed kernel sequence without a host
+// round trip; in steady state the sequence is replayed from a CUDA graph.  Multi-GPU: particle i is
+// weighted by rank i % nranks; the crop box is all-reduced and the raw weights all-gathered over NCCL
+// (loaded with dlopen so that the library itself has no link-time NCCL dependency); resample, normalise
+// and update run replicated on every rank from identical draws.
+#include <dlfcn.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "pft_internal.h"
+#include "pft_tracker_kernels.cuh"
+
+using namespace pft;
+
+// ------------------------------------------------------------------ NCCL through dlopen
+namespace {
+
+struct UidByValue { char internal[128]; };  // ncclUniqueId is passed by value
+struct NcclApi {
+  void* lib = nullptr;
+  bool tried = false;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, UidByValue, int) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+constexpr int kNcclFloat = 7;  // ncclFloat32
+constexpr int kNcclMax = 2, kNcclMin = 3;
+
+int load_nccl() {
+  if (g_nccl.lib) return PFT_OK;
+  if (g_nccl.tried) { set_last_error("NCCL is not loadable (libnccl.so.2)"); return PFT_ERR_COMM; }
+  g_nccl.tried = true;
+  const char* names[] = {getenv("PFT_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+  void* h = nullptr;
+  for (const char* n : names) {
+    if (!n) continue;
+    h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (h) break;
+  }
+  if (!h) { set_last_error("NCCL is not loadable: %s", dlerror()); return PFT_ERR_COMM; }
+  auto sym = [&](const char* n) { return dlsym(h, n); };
+  g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))sym("ncclGetUniqueId");
+  g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))sym("ncclCommInitRank");
+  g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))sym("ncclCommDestroy");
+  g_nccl.AllGather = (decltype(g_nccl.AllGather))sym("ncclAllGather");
+  g_nccl.AllReduce = (decltype(g_nccl.AllReduce))sym("ncclAllReduce");
+  g_nccl.GroupStart = (decltype(g_nccl.GroupStart))sym("ncclGroupStart");
+  g_nccl.GroupEnd = (decltype(g_nccl.GroupEnd))sym("ncclGroupEnd");
+  g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))sym("ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllGather || !g_nccl.AllReduce || !g_nccl.GroupStart ||
+      !g_nccl.GroupEnd) {
+    set_last_error("NCCL library lacks a required symbol");
+    return PFT_ERR_COMM;
+  }
+  g_nccl.lib = h;
+  return PFT_OK;
+}
+#define PFT_NCCL_TRY(expr)                                                                                       \
+  do {                                                                                                           \
+    int _r = (expr);                                                                                             \
+    if (_r != 0) {                                                                                               \
+      set_last_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, g_nccl.GetErrorString ? g_nccl.GetErrorString(_r) : "nccl error"); \
+      return PFT_ERR_COMM;                                                                                       \
+    }                                                                                                            \
+  } while (0)
+
+inline int blocks_for(long long n, int block, int cap) {
+  long long g = (n + block - 1) / block;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ the tracker object
+struct pft_tracker {
+  pft_context* ctx = nullptr;
+  bool kld = true;
+  // knobs (defaults = PCL constructor defaults; coherence defaults as the CPU oracle)
+  int threads = 0, particle_num = 0, max_particle_num = 0, iteration_num = 1, min_indices = 1;
+  int nn_mode = PFT_NN_EXACT, use_hsv = 0, use_dist = 1, sampler = PFT_SAMPLER_CDF, quat_sample = 1, debug_nn = 0;
+  double delta = 0.99, epsilon = 0.0, alpha = 15.0, motion_ratio = 0.25, max_dist = 1.79769313486231570815e+308;
+  double dist_w = 1.0, hsv_w = 1.0, h_w = 1.0, s_w = 1.0, v_w = 0.0, search_res = 0.01, resample_thr = 0.0;
+  double step_cov[6] = {0, 0, 0, 0, 0, 0}, init_cov[6] = {0, 0, 0, 0, 0, 0}, init_mean[6] = {0, 0, 0, 0, 0, 0};
+  float bin_size[6] = {0, 0, 0, 0, 0, 0};
+  float trans[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+  unsigned long long seed = 0x5eedull;
+  // host mirror of the control state
+  bool changed = false, has_particles = false;
+  int n_cap = 0;        // allocated particle capacity
+  int M = 0;            // model points
+  const pft_cloud* input = nullptr;
+  size_t scene_cap = 0; // allocated index capacity (scene points)
+  int max_words = 1 << 18;
+  int cur = 0;          // live particle buffer
+  int inj_slots = 0, inj_stride = 0;
+  int draw_cap = 0;
+  bool timing = false;
+  float t_weight_ms = 0.f, t_compute_ms = 0.f;
+  std::vector<cudaEvent_t> ev_w;  // pairs around weight_kernel launches of the last compute
+  cudaEvent_t ev_c0 = nullptr, ev_c1 = nullptr;
+  int n_ev_used = 0;
+  // comm
+  void* comm = nullptr;
+  int nranks = 1, rank = 0;
+  // graph
+  bool graph_enabled = true;
+  cudaGraphExec_t graph_exec = nullptr;
+  const void* graph_scene_pts = nullptr;
+  const void* graph_scene_hdr = nullptr;
+  unsigned long long config_version = 1, graph_version = 0;
+  unsigned long long graph_replays = 0;
+  int graph_nodes = 0;
+  // device buffers
+  DevBuf st, parts[2], mats, slot_aabb, model, model_perm, model_tmp, sort_keys, sort_idx, bbox, raw, partial, cdf, cdf_total, ancestors, bin_keys, tbl_rep,
+      tbl_min, slot_of, klb, d_usel, d_normals, d_umot, idx_hdr, words, rank_buf, ipts, iorig, inext, icount, dbg_idx, dbg_d2, d_trans;
+  int tbl_size = 0;
+  int n_slots = 0;
+  int chunks = 1, chunk_len = 0;
+
+  int slice_cap() const { return (n_cap + nranks - 1) / nranks; }
+};
+
+namespace {
+
+void invalidate_graph(pft_tracker* t) { t->config_version++; }
+
+void release_all(pft_tracker* t) {
+  DevBuf* bufs[] = {&t->st, &t->parts[0], &t->parts[1], &t->mats, &t->slot_aabb, &t->model, &t->model_perm, &t->model_tmp, &t->sort_keys, &t->sort_idx,
+                    &t->bbox, &t->raw, &t->partial, &t->cdf, &t->cdf_total, &t->ancestors, &t->bin_keys, &t->tbl_rep, &t->tbl_min, &t->slot_of, &t->klb,
+                    &t->d_usel, &t->d_normals, &t->d_umot, &t->idx_hdr, &t->words, &t->rank_buf, &t->ipts, &t->iorig, &t->inext, &t->icount, &t->dbg_idx,
+                    &t->dbg_d2, &t->d_trans};
+  for (auto* b : bufs) b->release();
+}
+
+NoiseParams make_noise(const pft_tracker* t, const double* mean, const double* cov) {
+  NoiseParams np;
+  for (int d = 0; d < 6; ++d) { np.mean[d] = mean[d]; np.sigma[d] = sqrt(cov[d]); }
+  const float scale_factor = 0.2862f;
+  for (int d = 0; d < 3; ++d) np.sigma_q[d] = sqrt((double)scale_factor * cov[3 + d]);
+  np.quat_mode = t->quat_sample;
+  return np;
+}
+
+// KLDAdaptiveParticleFilterTracker::calcKLBound / normalQuantile: evaluated on the host in
+// IEEE double once per configuration and tabulated for k = 0..n_max.
+double normal_quantile(double u) {
+  static const double a[9] = {1.24818987e-4, -1.075204047e-3, 5.198775019e-3, -0.019198292004, 0.059054035642,
+                              -0.151968751364, 0.319152932694, -0.5319230073, 0.797884560593};
+  static const double b[15] = {-4.5255659e-5, 1.5252929e-4, -1.9538132e-5, -6.76904986e-4, 1.390604284e-3,
+                               -7.9462082e-4, -2.034254874e-3, 6.549791214e-3, -0.010557625006, 0.011630447319,
+                               -9.279453341e-3, 5.353579108e-3, -2.141268741e-3, 5.35310549e-4, 0.999936657524};
+  if (u == 0.) return 0.5;
+  double y = u / 2.0, z;
+  if (y < -3.) return 0.0;
+  if (y > 3.) return 1.0;
+  if (y < 0.0) y = -y;
+  if (y < 1.0) {
+    const double w = y * y;
+    z = a[0];
+    for (int i = 1; i < 9; i++) z = z * w + a[i];
+    z *= (y * 2.0);
+  } else {
+    y -= 2.0;
+    z = b[0];
+    for (int i = 1; i < 15; i++) z = z * y + b[i];
+  }
+  return u < 0.0 ? (1.0 - z) / 2.0 : (1.0 + z) / 2.0;
+}
+double kl_bound(int k, double delta, double eps) {
+  const double z = normal_quantile(delta);
+  const double chi = 1.0 - 2.0 / (9.0 * (k - 1)) + sqrt(2.0 / (9.0 * (k - 1))) * z;
+  return ((k - 1.0) / (2.0 * eps)) * chi * chi * chi;
+}
+
+int wanted_cap(const pft_tracker* t) { return t->kld ? std::max(t->max_particle_num, t->particle_num) : t->particle_num; }
+
+// (Re)allocate every particle-count dependent buffer.  Existing particles survive a capacity change.
+int ensure_particle_buffers(pft_tracker* t) {
+  const int cap = wanted_cap(t);
+  if (cap <= 0) { set_last_error("particle count is zero: call setParticleNum / setMaximumParticleNum first"); return PFT_ERR_STATE; }
+  cudaStream_t s = t->ctx->stream;
+  int rc;
+  if (!t->st.p) {
+    if ((rc = t->st.reserve(sizeof(TrackerState)))) return rc;
+    PFT_CUDA_TRY(cudaMemsetAsync(t->st.p, 0, sizeof(TrackerState), s));
+    DevParticle one{0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 0.f};
+    PFT_CUDA_TRY(cudaMemcpyAsync(&t->st.as<TrackerState>()->rep, &one, sizeof(one), cudaMemcpyHostToDevice, s));
+    PFT_CUDA_TRY(cudaMemcpyAsync(&t->st.as<TrackerState>()->motion, &one, sizeof(one), cudaMemcpyHostToDevice, s));
+    PFT_CUDA_TRY(cudaStreamSynchronize(s));
+    if ((rc = t->cdf_total.reserve(sizeof(unsigned long long)))) return rc;
+    if ((rc = t->idx_hdr.reserve(sizeof(IndexHeader)))) return rc;
+    if ((rc = t->d_trans.reserve(12 * sizeof(float)))) return rc;
+    if ((rc = t->words.reserve((size_t)t->max_words * sizeof(unsigned int)))) return rc;
+    if ((rc = t->rank_buf.reserve((size_t)t->max_words * sizeof(int)))) return rc;
+  }
+  if (cap == t->n_cap) return PFT_OK;
+  invalidate_graph(t);
+  PFT_CUDA_TRY(cudaStreamSynchronize(s));
+  const int old_cap = t->n_cap;
+  // particles: keep the live set
+  DevBuf np0, np1;
+  if ((rc = np0.reserve((size_t)cap * sizeof(DevParticle)))) return rc;
+  if ((rc = np1.reserve((size_t)cap * sizeof(DevParticle)))) return rc;
+  if (old_cap > 0 && t->has_particles) {
+    PFT_CUDA_TRY(cudaMemcpyAsync(np0.p, t->parts[t->cur].p, (size_t)std::min(cap, old_cap) * sizeof(DevParticle), cudaMemcpyDeviceToDevice, s));
+    PFT_CUDA_TRY(cudaStreamSynchronize(s));
+  }
+  t->parts[0].release(); t->parts[1].release();
+  t->parts[0] = np0; t->parts[1] = np1; t->cur = 0;
+  t->n_cap = cap;
+  t->n_slots = cap;
+  const int slice = t->slice_cap();
+  if ((rc = t->mats.reserve((size_t)cap * 12 * sizeof(float)))) return rc;
+  t->slot_aabb.release();
+  if ((rc = t->slot_aabb.reserve((size_t)cap * 6 * sizeof(float)))) return rc;
+  {
+    std::vector<float> init((size_t)cap * 6);
+    for (int i = 0; i < cap; ++i) { for (int d = 0; d < 3; ++d) { init[6 * i + d] = FLT_MAX; init[6 * i + 3 + d] = -FLT_MAX; } }
+    PFT_CUDA_TRY(cudaMemcpy(t->slot_aabb.p, init.data(), init.size() * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  if ((rc = t->raw.reserve((size_t)slice * t->nranks * sizeof(float)))) return rc;
+  PFT_CUDA_TRY(cudaMemset(t->raw.p, 0, (size_t)slice * t->nranks * sizeof(float)));
+  if ((rc = t->cdf.reserve((size_t)cap * sizeof(unsigned long long)))) return rc;
+  if ((rc = t->ancestors.reserve((size_t)cap * sizeof(int)))) return rc;
+  PFT_CUDA_TRY(cudaMemset(t->ancestors.p, 0xff, (size_t)cap * sizeof(int)));
+  if (t->kld) {
+    if ((rc = t->bin_keys.reserve((size_t)cap * 6 * sizeof(int)))) return rc;
+    int ts = 1024;
+    while (ts < 2 * cap) ts <<= 1;
+    t->tbl_size = ts;
+    if ((rc = t->tbl_rep.reserve((size_t)ts * sizeof(int)))) return rc;
+    if ((rc = t->tbl_min.reserve((size_t)ts * sizeof(int)))) return rc;
+    if ((rc = t->slot_of.reserve((size_t)cap * sizeof(int)))) return rc;
+    if ((rc = t->klb.reserve((size_t)(cap + 2) * sizeof(double)))) return rc;
+  }
+  return PFT_OK;
+}
+
+int upload_kl_table(pft_tracker* t) {
+  if (!t->kld) return PFT_OK;
+  const int n = t->n_cap + 2;
+  std::vector<double> tab(n, 0.0);
+  for (int k = 2; k < n; ++k) tab[k] = kl_bound(k, t->delta, t->epsilon);
+  PFT_CUDA_TRY(cudaMemcpyAsync(t->klb.p, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice, t->ctx->stream));
+  PFT_CUDA_TRY(cudaStreamSynchronize(t->ctx->stream));
+  return PFT_OK;
+}
+
+int ensure_draw_buffers(pft_tracker* t, int slots, int stride) {
+  const size_t n = (size_t)slots * stride;
+  int rc;
+  if ((rc = t->d_usel.reserve(n * sizeof(float)))) return rc;
+  if ((rc = t->d_normals.reserve(n * 6 * sizeof(float)))) return rc;
+  if ((rc = t->d_umot.reserve(n * sizeof(float)))) return rc;
+  return PFT_OK;
+}
+
+// Draw arrays of one resample slot: injected (slot-indexed) or generated on the device into slot 0.
+int prepare_draws(pft_tracker* t, int slot, int count, const float** usel, const float** normals, const float** umot) {
+  cudaStream_t s = t->ctx->stream;
+  if (t->inj_stride > 0) {
+    if (slot >= t->inj_slots || count > t->inj_stride) {
+      set_last_error("injected draws cover %d slots x %d, need slot %d x %d", t->inj_slots, t->inj_stride, slot, count);
+      return PFT_ERR_STATE;
+    }
+    *usel = t->d_usel.as<float>() + (size_t)slot * t->inj_stride;
+    *normals = t->d_normals.as<float>() + (size_t)slot * t->inj_stride * 6;
+    *umot = t->d_umot.as<float>() + (size_t)slot * t->inj_stride;
+    return PFT_OK;
+  }
+  if (t->draw_cap < count) {
+    int rc = ensure_draw_buffers(t, 1, count);
+    if (rc) return rc;
+    t->draw_cap = count;
+    invalidate_graph(t);
+  }
+  draws_kernel<<<blocks_for(count, 256, t->ctx->sm_count * 4), 256, 0, s>>>(t->st.as<TrackerState>(), t->d_usel.as<float>(), t->d_normals.as<float>(),
+                                                                        t->d_umot.as<float>(), count, t->seed);
+  PFT_LAUNCH_CHECK();
+  *usel = t->d_usel.as<float>(); *normals = t->d_normals.as<float>(); *umot = t->d_umot.as<float>();
+  return PFT_OK;
+}
+
+int ensure_index_buffers(pft_tracker* t) {
+  const size_t cap = std::max<size_t>(t->input ? t->input->capacity : 0, 1);
+  if (cap <= t->scene_cap) return PFT_OK;
+  invalidate_graph(t);
+  PFT_CUDA_TRY(cudaStreamSynchronize(t->ctx->stream));
+  int rc;
+  if ((rc = t->ipts.reserve(cap * sizeof(float4)))) return rc;
+  if ((rc = t->iorig.reserve(cap * sizeof(int)))) return rc;
+  if ((rc = t->inext.reserve(cap * sizeof(int)))) return rc;
+  if ((rc = t->icount.reserve(cap * sizeof(int)))) return rc;
+  t->scene_cap = cap;
+  return PFT_OK;
+}
+
+void choose_chunks(pft_tracker* t) {
+  const int n_expected = std::max(1, (t->particle_num > 0 ? t->particle_num : t->n_cap) / t->nranks);
+  const int target_items = t->ctx->sm_count * 8;
+  const int max_chunks = std::max(1, (t->M + 255) / 256);
+  int chunks = (target_items + n_expected - 1) / n_expected;
+  chunks = std::min(std::max(chunks, 1), std::min(max_chunks, 64));
+  int len = (t->M + chunks - 1) / chunks;
+  len = ((len + 31) / 32) * 32;
+  if (len < 32) len = 32;
+  chunks = std::max(1, (t->M + len - 1) / len);
+  if (chunks != t->chunks || len != t->chunk_len) invalidate_graph(t);
+  t->chunks = chunks;
+  t->chunk_len = len;
+}
+
+CoherenceParams make_coherence(const pft_tracker* t) {
+  CoherenceParams c;
+  c.max_d2 = t->max_dist * t->max_dist;
+  c.dist_w = t->dist_w; c.hsv_w = t->hsv_w;
+  c.h_w = (float)t->h_w; c.s_w = (float)t->s_w; c.v_w = (float)t->v_w;
+  c.r_max = (float)std::min(t->max_dist, 1.0e18);
+  c.use_dist = t->use_dist; c.use_hsv = t->use_hsv;
+  return c;
+}
+
+// ---- stages -------------------------------------------------------------------------------------
+int stage_init_particles(pft_tracker* t) {
+  int rc = ensure_particle_buffers(t);
+  if (rc) return rc;
+  if (t->particle_num <= 0) { set_last_error("setParticleNum was not called"); return PFT_ERR_STATE; }
+  if ((rc = upload_kl_table(t))) return rc;
+  cudaStream_t s = t->ctx->stream;
+  PFT_CUDA_TRY(cudaMemcpyAsync(t->d_trans.p, t->trans, sizeof(t->trans), cudaMemcpyHostToDevice, s));
+  const float *usel, *normals, *umot;
+  if ((rc = prepare_draws(t, 0, t->particle_num, &usel, &normals, &umot))) return rc;
+  const NoiseParams np = make_noise(t, t->init_mean, t->init_cov);
+  init_particles_kernel<<<blocks_for(t->particle_num, 128, 1 << 20), 128, 0, s>>>(t->st.as<TrackerState>(), t->parts[t->cur].as<DevParticle>(),
+                                                                                   t->particle_num, t->d_trans.as<float>(), np, normals);
+  PFT_LAUNCH_CHECK();
+  t->has_particles = true;
+  return PFT_OK;
+}
+
+int stage_resample(pft_tracker* t, int slot) {
+  if (!t->has_particles) { set_last_error("resample before particles exist"); return PFT_ERR_STATE; }
+  if (!t->input) { set_last_error("resample needs an input cloud (setInputCloud)"); return PFT_ERR_STATE; }
+  if (t->kld && t->max_particle_num <= 0) { set_last_error("KLD tracker: setMaximumParticleNum was not called"); return PFT_ERR_STATE; }
+  cudaStream_t s = t->ctx->stream;
+  const int count = t->kld ? t->max_particle_num : t->n_cap;
+  const float *usel, *normals, *umot;
+  int rc = prepare_draws(t, slot, count, &usel, &normals, &umot);
+  if (rc) return rc;
+  TrackerState* st = t->st.as<TrackerState>();
+  const DevParticle* old_parts = t->parts[t->cur].as<DevParticle>();
+  DevParticle* new_parts = t->parts[t->cur ^ 1].as<DevParticle>();
+  cdf_kernel<<<1, 1024, 0, s>>>(st, old_parts, t->cdf.as<unsigned long long>(), t->cdf_total.as<unsigned long long>(), t->tbl_rep.as<int>(),
+                                t->tbl_min.as<int>(), t->kld ? t->tbl_size : 0);
+  PFT_LAUNCH_CHECK();
+  ResampleArgs a;
+  a.st = st; a.old_parts = old_parts; a.new_parts = new_parts;
+  a.cdf = t->cdf.as<unsigned long long>(); a.cdf_total = t->cdf_total.as<unsigned long long>();
+  a.u_select = usel; a.normals = normals; a.u_motion = umot;
+  a.scene_hdr = t->input->d_hdr();
+  a.ancestors = t->ancestors.as<int>(); a.bin_keys = t->bin_keys.as<int>();
+  const double zero[6] = {0, 0, 0, 0, 0, 0};
+  a.np = make_noise(t, zero, t->step_cov);
+  a.motion_ratio = t->motion_ratio;
+  for (int d = 0; d < 6; ++d) a.bin_size[d] = t->bin_size[d];
+  a.kld = t->kld ? 1 : 0; a.n_max = t->max_particle_num; a.sampler = t->sampler;
+  resample_kernel<<<blocks_for(count, 128, t->ctx->sm_count * 16), 128, 0, s>>>(a);
+  PFT_LAUNCH_CHECK();
+  if (t->kld) {
+    kld_insert_kernel<<<blocks_for(count, 128, t->ctx->sm_count * 16), 128, 0, s>>>(t->bin_keys.as<int>(), t->max_particle_num, t->tbl_rep.as<int>(),
+                                                                                    t->tbl_min.as<int>(), t->slot_of.as<int>(), (unsigned)(t->tbl_size - 1));
+    PFT_LAUNCH_CHECK();
+    kld_stop_kernel<<<1, 1024, 0, s>>>(st, t->tbl_min.as<int>(), t->slot_of.as<int>(), t->klb.as<double>(), t->max_particle_num, t->input->d_hdr());
+    PFT_LAUNCH_CHECK();
+  }
+  t->cur ^= 1;
+  return PFT_OK;
+}
+
+int check_weight_ready(pft_tracker* t) {
+  if (!t->has_particles) { set_last_error("weight before particles exist"); return PFT_ERR_STATE; }
+  if (!t->input) { set_last_error("weight needs an input cloud (setInputCloud)"); return PFT_ERR_STATE; }
+  if (t->M <= 0) { set_last_error("weight needs a reference cloud (setReferenceCloud)"); return PFT_ERR_STATE; }
+  return ensure_index_buffers(t);
+}
+
+// weight(), part 1: per-particle transforms + this rank's share of the crop box
+// (transformPointCloud per slot + calcBoundingBox)
+int weight_phase_box(pft_tracker* t) {
+  int rc = check_weight_ready(t);
+  if (rc) return rc;
+  cudaStream_t s = t->ctx->stream;
+  const int sm = t->ctx->sm_count;
+  TrackerState* st = t->st.as<TrackerState>();
+  DevParticle* parts = t->parts[t->cur].as<DevParticle>();
+  matrices_kernel<<<blocks_for(t->n_cap, 128, sm * 8), 128, 0, s>>>(st, parts, t->mats.as<float>());
+  PFT_LAUNCH_CHECK();
+  aabb_kernel<<<blocks_for((long long)t->n_slots * 32, 256, sm * 8), 256, 0, s>>>(st, t->model.as<float4>(), t->M, t->mats.as<float>(),
+                                                                               t->slot_aabb.as<float>(), t->n_slots, t->nranks, t->rank);
+  PFT_LAUNCH_CHECK();
+  return PFT_OK;
+}
+
+// crop box exchange: union over ranks
+int weight_comm_box(pft_tracker* t) {
+  if (!t->comm) return PFT_OK;
+  cudaStream_t s = t->ctx->stream;
+  TrackerState* st = t->st.as<TrackerState>();
+  PFT_NCCL_TRY(g_nccl.GroupStart());
+  PFT_NCCL_TRY(g_nccl.AllReduce(st->aabb, st->aabb, 3, kNcclFloat, kNcclMin, t->comm, s));
+  PFT_NCCL_TRY(g_nccl.AllReduce(st->aabb + 3, st->aabb + 3, 3, kNcclFloat, kNcclMax, t->comm, s));
+  PFT_NCCL_TRY(g_nccl.GroupEnd());
+  return PFT_OK;
+}
+
+// weight(), part 2: cropInputPointCloud + search index rebuild (K2), coherence of this rank's particles (K3)
+int weight_phase_eval(pft_tracker* t) {
+  int rc = check_weight_ready(t);
+  if (rc) return rc;
+  cudaStream_t s = t->ctx->stream;
+  const int sm = t->ctx->sm_count;
+  TrackerState* st = t->st.as<TrackerState>();
+  const pft_cloud* in = t->input;
+  const int ncap_scene = (int)std::max<size_t>(in->capacity, 1);
+  IndexHeader* hdr = t->idx_hdr.as<IndexHeader>();
+  const float inv_leaf = 1.0f / (float)t->search_res;
+  const int gscene = blocks_for(ncap_scene, 256, sm * 4);
+  index_begin_kernel<<<gscene, 256, 0, s>>>(st, hdr, t->words.as<unsigned int>(), t->icount.as<int>(), t->inext.as<int>(), in->d_hdr(), inv_leaf,
+                                            t->max_words);
+  PFT_LAUNCH_CHECK();
+  index_bits_kernel<<<gscene, 256, 0, s>>>(in->d_pts(), in->d_hdr(), hdr, t->words.as<unsigned int>());
+  PFT_LAUNCH_CHECK();
+  index_rank_kernel<<<1, 1024, 0, s>>>(hdr, t->words.as<unsigned int>(), t->rank_buf.as<int>());
+  PFT_LAUNCH_CHECK();
+  index_scatter_kernel<<<gscene, 256, 0, s>>>(in->d_pts(), in->d_hdr(), hdr, t->words.as<unsigned int>(), t->rank_buf.as<int>(), t->icount.as<int>(),
+                                              t->ipts.as<float4>(), t->iorig.as<int>(), t->inext.as<int>());
+  PFT_LAUNCH_CHECK();
+  WeightArgs a;
+  a.st = st; a.hdr = hdr;
+  a.g.words = t->words.as<unsigned int>(); a.g.rank = t->rank_buf.as<int>(); a.g.pts = t->ipts.as<float4>(); a.g.orig = t->iorig.as<int>();
+  a.g.next = t->inext.as<int>();
+  a.model = t->model.as<float4>(); a.model_perm = t->model_perm.as<int>(); a.M = t->M;
+  a.mats = t->mats.as<float>();
+  a.partial = t->partial.as<double>(); a.chunks = t->chunks; a.chunk_len = t->chunk_len; a.n_max = t->n_cap;
+  a.nranks = t->nranks; a.rank = t->rank;
+  a.co = make_coherence(t);
+  a.dbg_k = t->debug_nn; a.dbg_idx = t->dbg_idx.as<int>(); a.dbg_d2 = t->dbg_d2.as<float>();
+  const int local_cap = t->slice_cap();
+  const int wgrid = blocks_for((long long)local_cap * t->chunks, 1, sm * 8);
+  if (t->timing) {
+    while ((int)t->ev_w.size() < 2 * (t->n_ev_used + 1)) { cudaEvent_t e; PFT_CUDA_TRY(cudaEventCreate(&e)); t->ev_w.push_back(e); }
+    PFT_CUDA_TRY(cudaEventRecord(t->ev_w[2 * t->n_ev_used], s));
+  }
+  if (t->use_hsv) weight_kernel<true><<<wgrid, 256, 0, s>>>(a);
+  else weight_kernel<false><<<wgrid, 256, 0, s>>>(a);
+  PFT_LAUNCH_CHECK();
+  if (t->timing) { PFT_CUDA_TRY(cudaEventRecord(t->ev_w[2 * t->n_ev_used + 1], s)); t->n_ev_used++; }
+  raw_weights_kernel<<<blocks_for(local_cap, 256, sm * 4), 256, 0, s>>>(st, t->partial.as<double>(), t->chunks, t->n_cap, t->raw.as<float>(), local_cap,
+                                                                       t->nranks, t->rank);
+  PFT_LAUNCH_CHECK();
+  return PFT_OK;
+}
+
+// raw weight exchange: every rank ends up with all raw weights
+int weight_comm_raw(pft_tracker* t) {
+  if (!t->comm) return PFT_OK;
+  const int local_cap = t->slice_cap();
+  PFT_NCCL_TRY(g_nccl.AllGather(t->raw.as<float>() + (size_t)t->rank * local_cap, t->raw.as<float>(), (size_t)local_cap, kNcclFloat, t->comm,
+                                t->ctx->stream));
+  return PFT_OK;
+}
+
+// weight(), part 3: normalizeWeight (replicated)
+int weight_phase_normalize(pft_tracker* t) {
+  int rc = check_weight_ready(t);
+  if (rc) return rc;
+  normalize_kernel<<<1, 1024, 0, t->ctx->stream>>>(t->st.as<TrackerState>(), t->parts[t->cur].as<DevParticle>(), t->raw.as<float>(), t->alpha, t->nranks,
+                                                   t->slice_cap(), t->input->d_hdr());
+  PFT_LAUNCH_CHECK();
+  t->changed = true;  // change detector is off upstream => changed_ = true after every weight()
+  return PFT_OK;
+}
+
+int stage_weight(pft_tracker* t) {
+  int rc;
+  if ((rc = weight_phase_box(t))) return rc;
+  if ((rc = weight_comm_box(t))) return rc;
+  if ((rc = weight_phase_eval(t))) return rc;
+  if ((rc = weight_comm_raw(t))) return rc;
+  return weight_phase_normalize(t);
+}
+
+int stage_update(pft_tracker* t) {
+  if (!t->has_particles || !t->input) { set_last_error("update before weight"); return PFT_ERR_STATE; }
+  update_kernel<<<1, 1024, 0, t->ctx->stream>>>(t->st.as<TrackerState>(), t->parts[t->cur].as<DevParticle>(), t->input->d_hdr());
+  PFT_LAUNCH_CHECK();
+  return PFT_OK;
+}
+
+int enqueue_tracking(pft_tracker* t) {
+  int rc;
+  for (int it = 0; it < t->iteration_num; ++it) {
+    if (t->changed && (rc = stage_resample(t, it))) return rc;
+    if ((rc = stage_weight(t))) return rc;
+    if (t->changed && (rc = stage_update(t))) return rc;
+  }
+  return PFT_OK;
+}
+
+int prepare_compute(pft_tracker* t) {
+  int rc = ensure_particle_buffers(t);
+  if (rc) return rc;
+  if ((rc = ensure_index_buffers(t))) return rc;
+  choose_chunks(t);
+  const size_t need_partial = (size_t)t->chunks * t->n_cap * sizeof(double);
+  if (need_partial > t->partial.bytes) {
+    invalidate_graph(t);
+    PFT_CUDA_TRY(cudaStreamSynchronize(t->ctx->stream));
+    if ((rc = t->partial.reserve(need_partial))) return rc;
+  }
+  if (t->debug_nn > 0) {
+    const size_t need = (size_t)t->debug_nn * t->M;
+    if (need * sizeof(int) > t->dbg_idx.bytes) {
+      invalidate_graph(t);
+      PFT_CUDA_TRY(cudaStreamSynchronize(t->ctx->stream));
+      if ((rc = t->dbg_idx.reserve(need * sizeof(int)))) return rc;
+      if ((rc = t->dbg_d2.reserve(need * sizeof(float)))) return rc;
+    }
+  }
+  return PFT_OK;
+}
+
+bool is_noop(const pft_tracker* t) {
+  // Tracker::initCompute fails silently on an empty input (PCL_ERROR, no exception): compute() does nothing.
+  return !t->input || t->M <= 0 || t->input->host_n == 0 || t->input->capacity == 0;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ C ABI
+extern "C" {
+
+int pft_tracker_create(pft_context* ctx, int kld, pft_tracker** out) {
+  if (!ctx || !out) { set_last_error("pft_tracker_create: null argument"); return PFT_ERR_INVALID; }
+  pft_tracker* t = new pft_tracker();
+  t->ctx = ctx;
+  t->kld = kld != 0;
+  const char* ng = getenv("PFT_NO_GRAPH");
+  t->graph_enabled = !(ng && ng[0] == '1');
+  *out = t;
+  return PFT_OK;
+}
+
+void pft_tracker_destroy(pft_tracker* t) {
+  if (!t) return;
+  cudaSetDevice(t->ctx->device);
+  cudaStreamSynchronize(t->ctx->stream);
+  if (t->graph_exec) cudaGraphExecDestroy(t->graph_exec);
+  for (auto e : t->ev_w) cudaEventDestroy(e);
+  if (t->ev_c0) cudaEventDestroy(t->ev_c0);
+  if (t->ev_c1) cudaEventDestroy(t->ev_c1);
+  if (t->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(t->comm);
+  release_all(t);
+  delete t;
+}
+
+int pft_tracker_set_i(pft_tracker* t, int key, int v) {
+  if (!t) { set_last_error("null tracker"); return PFT_ERR_INVALID; }
+  switch (key) {
+    case PFT_THREADS: t->threads = v; break;  // OpenMP thread count of the CPU tracker: meaningless here
+    case PFT_PARTICLE_NUM:
+      if (v < 0) { set_last_error("particle number must be >= 0"); return PFT_ERR_INVALID; }
+      t->particle_num = v; break;
+    case PFT_MAX_PARTICLE_NUM:
+      if (v < 0) { set_last_error("maximum particle number must be >= 0"); return PFT_ERR_INVALID; }
+      t->max_particle_num = v; break;
+    case PFT_ITERATION_NUM:
+      if (v < 0) { set_last_error("iteration number must be >= 0"); return PFT_ERR_INVALID; }
+      t->iteration_num = v; break;
+    case PFT_NN_MODE:
+      if (v != PFT_NN_EXACT) { set_last_error("only PFT_NN_EXACT is implemented (exact grid search, ties to the lower index)"); return PFT_ERR_INVALID; }
+      t->nn_mode = v; break;
+    case PFT_USE_HSV: t->use_hsv = v != 0; break;
+    case PFT_USE_DISTANCE: t->use_dist = v != 0; break;
+    case PFT_SAMPLER:
+      if (v != PFT_SAMPLER_CDF && v != PFT_SAMPLER_CDF_VDC) { set_last_error("unknown sampler %d", v); return PFT_ERR_INVALID; }
+      t->sampler = v; break;
+    case PFT_QUAT_SAMPLE: t->quat_sample = v != 0; break;
+    case PFT_USE_NORMAL:
+      if (v != 0) { set_last_error("setUseNormal(true) is not supported (the reference runs with false, src/auto_tracking.cpp:233)"); return PFT_ERR_INVALID; }
+      break;
+    case PFT_MIN_INDICES: t->min_indices = v; break;
+    case PFT_DEBUG_NN:
+      if (v < 0) { set_last_error("PFT_DEBUG_NN must be >= 0"); return PFT_ERR_INVALID; }
+      t->debug_nn = v; break;
+    default: set_last_error("unknown int key %d", key); return PFT_ERR_INVALID;
+  }
+  invalidate_graph(t);
+  return PFT_OK;
+}
+
+int pft_tracker_set_d(pft_tracker* t, int key, double v) {
+  if (!t) { set_last_error("null tracker"); return PFT_ERR_INVALID; }
+  switch (key) {
+    case PFT_DELTA: t->delta = v; break;
+    case PFT_EPSILON: t->epsilon = v; break;
+    case PFT_ALPHA: t->alpha = v; break;
+    case PFT_MOTION_RATIO: t->motion_ratio = v; break;
+    case PFT_MAX_DIST: t->max_dist = v; break;
+    case PFT_DIST_WEIGHT: t->dist_w = v; break;
+    case PFT_HSV_WEIGHT: t->hsv_w = v; break;
+    case PFT_H_WEIGHT: t->h_w = v; break;
+    case PFT_S_WEIGHT: t->s_w = v; break;
+    case PFT_V_WEIGHT: t->v_w = v; break;
+    case PFT_SEARCH_RESOLUTION:
+      if (!(v > 0.0)) { set_last_error("search resolution must be positive"); return PFT_ERR_INVALID; }
+      t->search_res = v; break;
+    case PFT_RESAMPLE_LIKELIHOOD_THR: t->resample_thr = v; break;
+    default: set_last_error("unknown double key %d", key); return PFT_ERR_INVALID;
+  }
+  invalidate_graph(t);
+  if ((key == PFT_DELTA || key == PFT_EPSILON) && t->klb.p && t->n_cap > 0) return upload_kl_table(t);
+  return PFT_OK;
+}
+
+int pft_tracker_set_vec6(pft_tracker* t, int key, const double* v) {
+  if (!t || !v) { set_last_error("null argument"); return PFT_ERR_INVALID; }
+  switch (key) {
+    case PFT_STEP_NOISE_COV: memcpy(t->step_cov, v, sizeof(t->step_cov)); break;
+    case PFT_INIT_NOISE_COV: memcpy(t->init_cov, v, sizeof(t->init_cov)); break;
+    case PFT_INIT_NOISE_MEAN: memcpy(t->init_mean, v, sizeof(t->init_mean)); break;
+    case PFT_BIN_SIZE: for (int d = 0; d < 6; ++d) t->bin_size[d] = (float)v[d]; break;
+    default: set_last_error("unknown vec6 key %d", key); return PFT_ERR_INVALID;
+  }
+  invalidate_graph(t);
+  return PFT_OK;
+}
+
+int pft_tracker_set_trans(pft_tracker* t, const float* m12) {
+  if (!t || !m12) { set_last_error("null argument"); return PFT_ERR_INVALID; }
+  memcpy(t->trans, m12, sizeof(t->trans));
+  return PFT_OK;
+}
+
+static int set_reference_device(pft_tracker* t, const float4* d_pts, int n) {
+  pft_context* ctx = t->ctx;
+  cudaStream_t s = ctx->stream;
+  invalidate_graph(t);
+  PFT_CUDA_TRY(cudaStreamSynchronize(s));
+  t->M = n;
+  if (n == 0) return PFT_OK;
+  int n_pad = 1;
+  while (n_pad < n) n_pad <<= 1;
+  int rc;
+  if ((rc = t->model.reserve((size_t)n * sizeof(float4)))) return rc;
+  if ((rc = t->model_perm.reserve((size_t)n * sizeof(int)))) return rc;
+  if ((rc = t->sort_keys.reserve((size_t)n_pad * sizeof(unsigned int)))) return rc;
+  if ((rc = t->sort_idx.reserve((size_t)n_pad * sizeof(int)))) return rc;
+  if ((rc = t->bbox.reserve(6 * sizeof(float)))) return rc;
+  model_bbox_kernel<<<1, 1024, 0, s>>>(d_pts, n, t->bbox.as<float>());
+  PFT_LAUNCH_CHECK();
+  model_keys_kernel<<<blocks_for(n_pad, 256, 1024), 256, 0, s>>>(d_pts, n, t->sort_keys.as<unsigned int>(), t->sort_idx.as<int>(), n_pad, t->bbox.as<float>());
+  PFT_LAUNCH_CHECK();
+  bitonic_sort_kernel<<<1, 1024, 0, s>>>(t->sort_keys.as<unsigned int>(), t->sort_idx.as<int>(), n_pad);
+  PFT_LAUNCH_CHECK();
+  model_gather_kernel<<<blocks_for(n, 256, 1024), 256, 0, s>>>(d_pts, t->sort_idx.as<int>(), n, t->model.as<float4>(), t->model_perm.as<int>());
+  PFT_LAUNCH_CHECK();
+  PFT_CUDA_TRY(cudaStreamSynchronize(s));
+  choose_chunks(t);
+  return PFT_OK;
+}
+
+int pft_tracker_set_reference_cloud(pft_tracker* t, const pft_cloud* cloud) {
+  if (!t || !cloud) { set_last_error("null argument"); return PFT_ERR_INVALID; }
+  if (cloud->ctx != t->ctx) { set_last_error("cloud belongs to another context"); return PFT_ERR_INVALID; }
+  PFT_CUDA_TRY(cudaSetDevice(t->ctx->device));
+  size_t n = 0;
+  int rc = pft_cloud_size(const_cast<pft_cloud*>(cloud), &n);
+  if (rc) return rc;
+  return set_reference_device(t, cloud->d_pts(), (int)n);
+}
+
+int pft_tracker_set_reference_points(pft_tracker* t, const void* host_points, size_t n, int layout) {
+  if (!t || (n && !host_points)) { set_last_error("null argument"); return PFT_ERR_INVALID; }
+  PFT_CUDA_TRY(cudaSetDevice(t->ctx->device));
+  pft_cloud tmp;
+  tmp.ctx = t->ctx;
+  int rc = tmp.ensure(n);
+  if (!rc) rc = pft_cloud_upload(&tmp, host_points, n, layout);
+  if (!rc) rc = set_reference_device(t, tmp.d_pts(), (int)n);
+  cudaStreamSynchronize(t->ctx->stream);
+  tmp.pts.release(); tmp.hdr.release();
+  return rc;
+}
+
+int pft_tracker_set_input_cloud(pft_tracker* t, const pft_cloud* cloud) {
+  if (!t) { set_last_error("null tracker"); return PFT_ERR_INVALID; }
+  if (cloud && cloud->ctx != t->ctx) { set_last_error("cloud belongs to another context"); return PFT_ERR_INVALID; }
+  t->input = cloud;
+  return PFT_OK;
+}
+
+// ------------------------------------------------------------------ execution
+static int compute_one(pft_tracker* t) {
+  if (is_noop(t)) return PFT_OK;
+  PFT_CUDA_TRY(cudaSetDevice(t->ctx->device));
+  cudaStream_t s = t->ctx->stream;
+  int rc = prepare_compute(t);
+  if (rc) return rc;
+  if (!t->has_particles && (rc = stage_init_particles(t))) return rc;
+  if (t->timing) {
+    if (!t->ev_c0) { PFT_CUDA_TRY(cudaEventCreate(&t->ev_c0)); PFT_CUDA_TRY(cudaEventCreate(&t->ev_c1)); }
+    t->n_ev_used = 0;
+    PFT_CUDA_TRY(cudaEventRecord(t->ev_c0, s));
+  }
+  const bool steady = t->changed && t->graph_enabled && !t->timing && t->debug_nn == 0;
+  if (steady) {
+    // The steady-state frame is a fixed launch sequence over fixed buffers: replay it from a graph.
+    // (Particle double-buffering flips `cur` once per resample; a graph is only valid when a whole
+    // compute() returns `cur` to where it started, i.e. for an even number of resamples.)
+    const bool even = (t->iteration_num % 2) == 0;
+    if (even) {
+      const bool valid = t->graph_exec && t->graph_version == t->config_version && t->graph_scene_pts == (const void*)t->input->d_pts() &&
+                         t->graph_scene_hdr == (const void*)t->input->d_hdr();
+      if (!valid) {
+        if (t->graph_exec) { cudaGraphExecDestroy(t->graph_exec); t->graph_exec = nullptr; }
+        // make sure every lazily sized buffer exists before capture (no allocation inside a capture)
+        if (t->inj_stride == 0) {
+          const int count = t->kld ? t->max_particle_num : t->n_cap;
+          if (t->draw_cap < count) { if ((rc = ensure_draw_buffers(t, 1, count))) return rc; t->draw_cap = count; }
+        }
+        const unsigned long long version = t->config_version;
+        cudaGraph_t graph = nullptr;
+        PFT_CUDA_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+        const unsigned long long launches_before = g_launch_count;
+        rc = enqueue_tracking(t);
+        cudaError_t ce = cudaStreamEndCapture(s, &graph);
+        g_launch_count = launches_before;  // captured, not launched
+        if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (ce != cudaSuccess) { set_last_error("graph capture failed: %s", cudaGetErrorString(ce)); cudaGetLastError(); return PFT_ERR_CUDA; }
+        size_t n_nodes = 0;
+        cudaGraphGetNodes(graph, nullptr, &n_nodes);
+        cudaError_t ie = cudaGraphInstantiate(&t->graph_exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ie != cudaSuccess) { set_last_error("graph instantiate failed: %s", cudaGetErrorString(ie)); cudaGetLastError(); t->graph_exec = nullptr; return PFT_ERR_CUDA; }
+        t->graph_version = version;
+        t->config_version = version;  // stages may bump the version while sizing buffers; nothing changed since
+        t->graph_scene_pts = t->input->d_pts();
+        t->graph_scene_hdr = t->input->d_hdr();
+        t->graph_nodes = (int)n_nodes;
+      }
+      PFT_CUDA_TRY(cudaGraphLaunch(t->graph_exec, s));
+      g_launch_count += (unsigned long long)t->graph_nodes;
+      t->graph_replays++;
+      return PFT_OK;
+    }
+  }
+  rc = enqueue_tracking(t);
+  if (rc) return rc;
+  if (t->timing) PFT_CUDA_TRY(cudaEventRecord(t->ev_c1, s));
+  return PFT_OK;
+}
+
+int pft_tracker_compute(pft_tracker* t) {
+  if (!t) { set_last_error("null tracker"); return PFT_ERR_INVALID; }
+  return compute_one(t);
+}
+
+int pft_compute_batch(pft_tracker** ts, int n) {
+  if (n < 0 || (n && !ts)) { set_last_error("pft_compute_batch: bad arguments"); return PFT_ERR_INVALID; }
+  // Independent trackers on one scene (ref: src/auto_tracking.cpp:688-697 loops them serially).  Each
+  // tracker's frame is one graph launch on its context's stream.
+  for (int i = 0; i < n; ++i) {
+    if (!ts[i]) { set_last_error("pft_compute_batch: null tracker %d", i); return PFT_ERR_INVALID; }
+    int rc = compute_one(ts[i]);
+    if (rc) return rc;
+  }
+  return PFT_OK;
+}
+
+static int read_state(pft_tracker* t, TrackerState* host) {
+  if (!t->st.p) { memset(host, 0, sizeof(*host)); host->rep.one = 1.f; host->motion.one = 1.f; return PFT_OK; }
+  PFT_CUDA_TRY(cudaSetDevice(t->ctx->device));
+  cudaStream_t s = t->ctx->stream;
+  PFT_CUDA_TRY(cudaMemcpyAsync(t->ctx->pinned, t->st.p, sizeof(TrackerState), cudaMemcpyDeviceToHost, s));
+  PFT_CUDA_TRY(cudaStreamSynchronize(s));
+  memcpy(host, t->ctx->pinned, sizeof(TrackerState));
+  return PFT_OK;
+}
+
+int pft_tracker_get_result(pft_tracker* t, pft_particle* out) {
+  if (!t || !out) { set_last_error("null argument"); return PFT_ERR_INVALID; }
+  TrackerState h;
+  int rc = read_state(t, &h);
+  if (rc) return rc;
+  memcpy(out, &h.rep, sizeof(pft_particle));
+  return PFT_OK;
+}
+
+int pft_tracker_get_motion(pft_tracker* t, pft_particle* out) {
+  if (!t || !out) { set_last_error("null argument"); return PFT_ERR_INVALID; }
+  TrackerState h;
+  int rc = read_state(t, &h);
+  if (rc) return rc;
+  memcpy(out, &h.motion, sizeof(pft_particle));
+  return PFT_OK;
+}
+
+int pft_tracker_get_fit_ratio(pft_tracker* t, double* out) {
+  if (!t || !out) { set_last_error("null argument"); return PFT_ERR_INVALID; }
+  TrackerState h;
+  int rc = read_state(t, &h);
+  if (rc) return rc;
+  *out = h.fit_ratio;
+  return PFT_OK;
+}
+
+int pft_tracker_get_particles(pft_tracker* t, pft_particle* out, size_t capacity, size_t* n_out) {
+  if (!t) { set_last_error("null tracker"); return PFT_ERR_INVALID; }
+  size_t n = 0;
+  if (t->has_particles) {
+    TrackerState h;
+    int rc = read_state(t, &h);
+    if (rc) return rc;
+    n = (size_t)h.particle_num;
+  }
+  if (n_out) *n_out = n;
+  if (n > capacity) { set_last_error("pft_tracker_get_particles: %zu particles, capacity %zu", n, capacity); return PFT_ERR_CAPACITY; }
+  if (n == 0) return PFT_OK;
+  if (!out) { set_last_error("null buffer"); return PFT_ERR_INVALID; }
+  cudaStream_t s = t->ctx->stream;
+  PFT_CUDA_TRY(cudaMemcpyAsync(out, t->parts[t->cur].p, n * sizeof(pft_particle), cudaMemcpyDeviceToHost, s));
+  PFT_CUDA_TRY(cudaStreamSynchronize(s));
+  return PFT_OK;
+}
+
+int pft_particle_to_matrix(pft_context* ctx, const pft_particle* p, float* m12) {
+  if (!ctx || !p || !m12) { set_last_error("null argument"); return PFT_ERR_INVALID; }
+  PFT_CUDA_TRY(cudaSetDevice(ctx->device));
+  int rc = ctx->tmp_f.reserve(16 * sizeof(float));
+  if (rc) return rc;
+  DevParticle dp;
+  memcpy(&dp, p, sizeof(dp));
+  single_matrix_kernel<<<1, 1, 0, ctx->stream>>>(dp, ctx->tmp_f.as<float>() + 4);
+  PFT_LAUNCH_CHECK();
+  PFT_CUDA_TRY(cudaMemcpyAsync(ctx->pinned, ctx->tmp_f.as<float>() + 4, 12 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  PFT_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  memcpy(m12, ctx->pinned, 12 * sizeof(float));
+  return PFT_OK;
+}
+
+int pft_tracker_reset(pft_tracker* t) {
+  if (!t) { set_last_error("null tracker"); return PFT_ERR_INVALID; }
+  // resetTracking: particles are re-drawn around trans_ on the next compute()
+  t->has_particles = false;
+  t->changed = false;
+  invalidate_graph(t);
+  if (t->st.p) {
+    PFT_CUDA_TRY(cudaSetDevice(t->ctx->device));
+    cudaStream_t s = t->ctx->stream;
+    PFT_CUDA_TRY(cudaMemsetAsync(&t->st.as<TrackerState>()->has_particles, 0, sizeof(int), s));
+    if (t->slot_aabb.p && t->n_cap > 0) {
+      std::vector<float> init((size_t)t->n_cap * 6);
+      for (int i = 0; i < t->n_cap; ++i) { for (int d = 0; d < 3; ++d) { init[6 * i + d] = FLT_MAX; init[6 * i + 3 + d] = -FLT_MAX; } }
+      PFT_CUDA_TRY(cudaStreamSynchronize(s));
+      PFT_CUDA_TRY(cudaMemcpy(t->slot_aabb.p, init.data(), init.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
+  }
+  return PFT_OK;
+}
+
+// ------------------------------------------------------------------ reproducibility / parity hooks
+int pft_tracker_set_particles(pft_tracker* t, const pft_particle* p, size_t n) {
+  if (!t || (n && !p)) { set_last_error("null argument"); return PFT_ERR_INVALID; }
+  if (n == 0 || n > 0x7fffffffull) { set_last_error("bad particle count %zu", n); return PFT_ERR_INVALID; }
+  PFT_CUDA_TRY(cudaSetDevice(t->ctx->device));
+  t->particle_num = (int)n;  // as PCL: particle_num_ follows the particle set
+  int rc = ensure_particle_buffers(t);
+  if (rc) return rc;
+  if ((rc = upload_kl_table(t))) return rc;
+  cudaStream_t s = t->ctx->stream;
+  PFT_CUDA_TRY(cudaMemcpyAsync(t->parts[t->cur].p, p, n * sizeof(pft_particle), cudaMemcpyHostToDevice, s));
+  const int nn = (int)n, one = 1;
+  PFT_CUDA_TRY(cudaMemcpyAsync(&t->st.as<TrackerState>()->particle_num, &nn, sizeof(int), cudaMemcpyHostToDevice, s));
+  PFT_CUDA_TRY(cudaMemcpyAsync(&t->st.as<TrackerState>()->has_particles, &one, sizeof(int), cudaMemcpyHostToDevice, s));
+  PFT_CUDA_TRY(cudaStreamSynchronize(s));
+  t->has_particles = true;
+  invalidate_graph(t);
+  return PFT_OK;
+}
+
+int pft_tracker_set_result(pft_tracker* t, const pft_particle* rep, const pft_particle* motion) {
+  if (!t) { set_last_error("null tracker"); return PFT_ERR_INVALID; }
+  PFT_CUDA_TRY(cudaSetDevice(t->ctx->device));
+  int rc = ensure_particle_buffers(t);
+  if (rc) return rc;
+  cudaStream_t s = t->ctx->stream;
+  if (rep) PFT_CUDA_TRY(cudaMemcpyAsync(&t->st.as<TrackerState>()->rep, rep, sizeof(pft_particle), cudaMemcpyHostToDevice, s));
+  if (motion) PFT_CUDA_TRY(cudaMemcpyAsync(&t->st.as<TrackerState>()->motion, motion, sizeof(pft_particle), cudaMemcpyHostToDevice, s));
+  PFT_CUDA_TRY(cudaStreamSynchronize(s));
+  return PFT_OK;
+}
+
+int pft_tracker_inject_draws(pft_tracker* t, const float* usel, const float* normals6, const float* umot, int slots, int stride) {
+  if (!t) { set_last_error("null tracker"); return PFT_ERR_INVALID; }
+  PFT_CUDA_TRY(cudaSetDevice(t->ctx->device));
+  invalidate_graph(t);
+  PFT_CUDA_TRY(cudaStreamSynchronize(t->ctx->stream));
+  if (!usel || !normals6 || !umot) {
+    t->inj_slots = 0; t->inj_stride = 0; t->draw_cap = 0;
+    return PFT_OK;
+  }
+  if (slots <= 0 || stride <= 0) { set_last_error("bad draw shape %d x %d", slots, stride); return PFT_ERR_INVALID; }
+  int rc = ensure_draw_buffers(t, slots, stride);
+  if (rc) return rc;
+  const size_t n = (size_t)slots * stride;
+  cudaStream_t s = t->ctx->stream;
+  PFT_CUDA_TRY(cudaMemcpyAsync(t->d_usel.p, usel, n * sizeof(float), cudaMemcpyHostToDevice, s));
+  PFT_CUDA_TRY(cudaMemcpyAsync(t->d_normals.p, normals6, n * 6 * sizeof(float), cudaMemcpyHostToDevice, s));
+  PFT_CUDA_TRY(cudaMemcpyAsync(t->d_umot.p, umot, n * sizeof(float), cudaMemcpyHostToDevice, s));
+  PFT_CUDA_TRY(cudaStreamSynchronize(s));
+  t->inj_slots = slots; t->inj_stride = stride; t->draw_cap = 0;
+  return PFT_OK;
+}
+
+int pft_tracker_seed(pft_tracker* t, uint64_t seed) {
+  if (!t) { set_last_error("null tracker"); return PFT_ERR_INVALID; }
+  t->seed = seed;
+  invalidate_graph(t);
+  if (t->st.p) {
+    PFT_CUDA_TRY(cudaSetDevice(t->ctx->device));
+    PFT_CUDA_TRY(cudaMemsetAsync(&t->st.as<TrackerState>()->draw_call, 0, sizeof(unsigned long long), t->ctx->stream));
+  }
+  return PFT_OK;
+}
+
+int pft_tracker_init_particles(pft_tracker* t) {
+  if (!t) { set_last_error("null tracker"); return PFT_ERR_INVALID; }
+  PFT_CUDA_TRY(cudaSetDevice(t->ctx->device));
+  return stage_init_particles(t);
+}
+int pft_tracker_resample(pft_tracker* t, int slot) {
+  if (!t) { set_last_error("null tracker"); return PFT_ERR_INVALID; }
+  PFT_CUDA_TRY(cudaSetDevice(t->ctx->device));
+  int rc = prepare_compute(t);
+  if (rc) return rc;
+  return stage_resample(t, slot);
+}
+int pft_tracker_weight(pft_tracker* t) {
+  if (!t) { set_last_error("null tracker"); return PFT_ERR_INVALID; }
+  PFT_CUDA_TRY(cudaSetDevice(t->ctx->device));
+  int rc = prepare_compute(t);
+  if (rc) return rc;
+  if (t->timing) t->n_ev_used = 0;
+  return stage_weight(t);
+}
+int pft_tracker_update(pft_tracker* t) {
+  if (!t) { set_last_error("null tracker"); return PFT_ERR_INVALID; }
+  PFT_CUDA_TRY(cudaSetDevice(t->ctx->device));
+  return stage_update(t);
+}
+int pft_tracker_set_changed(pft_tracker* t, int changed) {
+  if (!t) { set_last_error("null tracker"); return PFT_ERR_INVALID; }
+  t->changed = changed != 0;
+  return PFT_OK;
+}
+
+int pft_tracker_get_aabb(pft_tracker* t, float* aabb6) {
+  if (!t || !aabb6) { set_last_error("null argument"); return PFT_ERR_INVALID; }
+  if (!t->idx_hdr.p) { set_last_error("no weight() has run"); return PFT_ERR_STATE; }
+  PFT_CUDA_TRY(cudaSetDevice(t->ctx->device));
+  cudaStream_t s = t->ctx->stream;
+  PFT_CUDA_TRY(cudaMemcpyAsync(t->ctx->pinned, t->idx_hdr.p, sizeof(IndexHeader), cudaMemcpyDeviceToHost, s));
+  PFT_CUDA_TRY(cudaStreamSynchronize(s));
+  memcpy(aabb6, reinterpret_cast<IndexHeader*>(t->ctx->pinned)->aabb, 6 * sizeof(float));
+  return PFT_OK;
+}
+
+int pft_tracker_get_cropped_count(pft_tracker* t, size_t* n) {
+  if (!t || !n) { set_last_error("null argument"); return PFT_ERR_INVALID; }
+  if (!t->idx_hdr.p) { set_last_error("no weight() has run"); return PFT_ERR_STATE; }
+  PFT_CUDA_TRY(cudaSetDevice(t->ctx->device));
+  cudaStream_t s = t->ctx->stream;
+  PFT_CUDA_TRY(cudaMemcpyAsync(t->ctx->pinned, t->idx_hdr.p, sizeof(IndexHeader), cudaMemcpyDeviceToHost, s));
+  PFT_CUDA_TRY(cudaStreamSynchronize(s));
+  *n = (size_t)reinterpret_cast<IndexHeader*>(t->ctx->pinned)->n_cropped;
+  return PFT_OK;
+}
+
+int pft_tracker_get_index_info(pft_tracker* t, int* info8) {
+  if (!t || !info8) { set_last_error("null argument"); return PFT_ERR_INVALID; }
+  if (!t->idx_hdr.p) { set_last_error("no weight() has run"); return PFT_ERR_STATE; }
+  PFT_CUDA_TRY(cudaSetDevice(t->ctx->device));
+  cudaStream_t s = t->ctx->stream;
+  PFT_CUDA_TRY(cudaMemcpyAsync(t->ctx->pinned, t->idx_hdr.p, sizeof(IndexHeader), cudaMemcpyDeviceToHost, s));
+  PFT_CUDA_TRY(cudaStreamSynchronize(s));
+  const IndexHeader* h = reinterpret_cast<IndexHeader*>(t->ctx->pinned);
+  info8[0] = h->dim[0]; info8[1] = h->dim[1]; info8[2] = h->dim[2]; info8[3] = h->level;
+  info8[4] = h->n_cropped; info8[5] = h->n_occupied; info8[6] = h->n_overflow; info8[7] = h->n_words;
+  return PFT_OK;
+}
+
+int pft_tracker_get_raw_weights(pft_tracker* t, float* out, size_t capacity, size_t* n_out) {
+  if (!t) { set_last_error("null tracker"); return PFT_ERR_INVALID; }
+  TrackerState h;
+  int rc = read_state(t, &h);
+  if (rc) return rc;
+  const size_t n = t->has_particles ? (size_t)h.particle_num : 0;
+  if (n_out) *n_out = n;
+  if (n > capacity) { set_last_error("capacity %zu < %zu", capacity, n); return PFT_ERR_CAPACITY; }
+  if (n == 0) return PFT_OK;
+  const int slice = t->slice_cap();
+  std::vector<float> all((size_t)slice * t->nranks);
+  PFT_CUDA_TRY(cudaMemcpy(all.data(), t->raw.p, all.size() * sizeof(float), cudaMemcpyDeviceToHost));
+  for (size_t i = 0; i < n; ++i) out[i] = all[(i % t->nranks) * slice + i / t->nranks];
+  return PFT_OK;
+}
+
+int pft_tracker_get_ancestors(pft_tracker* t, int32_t* out, size_t capacity, size_t* n_out) {
+  if (!t) { set_last_error("null tracker"); return PFT_ERR_INVALID; }
+  TrackerState h;
+  int rc = read_state(t, &h);
+  if (rc) return rc;
+  const size_t n = t->has_particles ? (size_t)h.particle_num : 0;
+  if (n_out) *n_out = n;
+  if (n > capacity) { set_last_error("capacity %zu < %zu", capacity, n); return PFT_ERR_CAPACITY; }
+  if (n == 0) return PFT_OK;
+  PFT_CUDA_TRY(cudaMemcpy(out, t->ancestors.p, n * sizeof(int), cudaMemcpyDeviceToHost));
+  return PFT_OK;
+}
+
+int pft_tracker_get_nn(pft_tracker* t, int particle, int32_t* idx, float* d2, size_t capacity) {
+  if (!t || !idx || !d2) { set_last_error("null argument"); return PFT_ERR_INVALID; }
+  if (particle < 0 || particle >= t->debug_nn || !t->dbg_idx.p) { set_last_error("particle %d was not recorded (PFT_DEBUG_NN = %d)", particle, t->debug_nn); return PFT_ERR_STATE; }
+  if ((size_t)t->M > capacity) { set_last_error("capacity %zu < %d", capacity, t->M); return PFT_ERR_CAPACITY; }
+  PFT_CUDA_TRY(cudaSetDevice(t->ctx->device));
+  PFT_CUDA_TRY(cudaStreamSynchronize(t->ctx->stream));
+  PFT_CUDA_TRY(cudaMemcpy(idx, t->dbg_idx.as<int>() + (size_t)particle * t->M, (size_t)t->M * sizeof(int), cudaMemcpyDeviceToHost));
+  PFT_CUDA_TRY(cudaMemcpy(d2, t->dbg_d2.as<float>() + (size_t)particle * t->M, (size_t)t->M * sizeof(float), cudaMemcpyDeviceToHost));
+  return PFT_OK;
+}
+
+int pft_tracker_enable_timing(pft_tracker* t, int on) {
+  if (!t) { set_last_error("null tracker"); return PFT_ERR_INVALID; }
+  t->timing = on != 0;
+  return PFT_OK;
+}
+
+int pft_tracker_get_timing(pft_tracker* t, float* weight_ms, float* compute_ms) {
+  if (!t) { set_last_error("null tracker"); return PFT_ERR_INVALID; }
+  if (!t->timing || !t->ev_c0) { set_last_error("timing is not enabled or no compute() has run"); return PFT_ERR_STATE; }
+  PFT_CUDA_TRY(cudaSetDevice(t->ctx->device));
+  PFT_CUDA_TRY(cudaStreamSynchronize(t->ctx->stream));
+  float w = 0.f;
+  for (int k = 0; k < t->n_ev_used; ++k) {
+    float ms = 0.f;
+    PFT_CUDA_TRY(cudaEventElapsedTime(&ms, t->ev_w[2 * k], t->ev_w[2 * k + 1]));
+    w += ms;
+  }
+  float c = 0.f;
+  if (cudaEventElapsedTime(&c, t->ev_c0, t->ev_c1) != cudaSuccess) { cudaGetLastError(); c = 0.f; }
+  if (weight_ms) *weight_ms = w;
+  if (compute_ms) *compute_ms = c;
+  return PFT_OK;
+}
+
+// weight() in its three parts, with the two exchange points exposed, so that a sharded run can be
+// driven (and tested) without a communicator: 0 = transforms + local crop box, 1 = index + coherence of
+// the local particles, 2 = normalise.
+int pft_tracker_weight_phase(pft_tracker* t, int phase) {
+  if (!t) { set_last_error("null tracker"); return PFT_ERR_INVALID; }
+  PFT_CUDA_TRY(cudaSetDevice(t->ctx->device));
+  int rc = prepare_compute(t);
+  if (rc) return rc;
+  switch (phase) {
+    case 0: return weight_phase_box(t);
+    case 1: if (t->timing) t->n_ev_used = 0; return weight_phase_eval(t);
+    case 2: return weight_phase_normalize(t);
+    default: set_last_error("phase must be 0, 1 or 2"); return PFT_ERR_INVALID;
+  }
+}
+int pft_tracker_get_crop_box(pft_tracker* t, float* aabb6) {
+  if (!t || !aabb6) { set_last_error("null argument"); return PFT_ERR_INVALID; }
+  TrackerState h;
+  int rc = read_state(t, &h);
+  if (rc) return rc;
+  memcpy(aabb6, h.aabb, sizeof(h.aabb));
+  return PFT_OK;
+}
+int pft_tracker_set_crop_box(pft_tracker* t, const float* aabb6) {
+  if (!t || !aabb6 || !t->st.p) { set_last_error("null argument / no state"); return PFT_ERR_INVALID; }
+  PFT_CUDA_TRY(cudaSetDevice(t->ctx->device));
+  PFT_CUDA_TRY(cudaMemcpyAsync(t->st.as<TrackerState>()->aabb, aabb6, 6 * sizeof(float), cudaMemcpyHostToDevice, t->ctx->stream));
+  PFT_CUDA_TRY(cudaStreamSynchronize(t->ctx->stream));
+  return PFT_OK;
+}
+int pft_tracker_get_raw_slice(pft_tracker* t, int rank, float* out, size_t capacity, size_t* n_out) {
+  if (!t || !t->raw.p) { set_last_error("null argument / no state"); return PFT_ERR_INVALID; }
+  if (rank < 0 || rank >= t->nranks) { set_last_error("bad rank"); return PFT_ERR_INVALID; }
+  const size_t n = (size_t)t->slice_cap();
+  if (n_out) *n_out = n;
+  if (n > capacity || !out) { set_last_error("capacity %zu < %zu", capacity, n); return PFT_ERR_CAPACITY; }
+  PFT_CUDA_TRY(cudaSetDevice(t->ctx->device));
+  PFT_CUDA_TRY(cudaStreamSynchronize(t->ctx->stream));
+  PFT_CUDA_TRY(cudaMemcpy(out, t->raw.as<float>() + (size_t)rank * n, n * sizeof(float), cudaMemcpyDeviceToHost));
+  return PFT_OK;
+}
+int pft_tracker_set_raw_slice(pft_tracker* t, int rank, const float* in, size_t n) {
+  if (!t || !in || !t->raw.p) { set_last_error("null argument / no state"); return PFT_ERR_INVALID; }
+  if (rank < 0 || rank >= t->nranks || n != (size_t)t->slice_cap()) { set_last_error("bad rank or slice length"); return PFT_ERR_INVALID; }
+  PFT_CUDA_TRY(cudaSetDevice(t->ctx->device));
+  PFT_CUDA_TRY(cudaMemcpyAsync(t->raw.as<float>() + (size_t)rank * n, in, n * sizeof(float), cudaMemcpyHostToDevice, t->ctx->stream));
+  PFT_CUDA_TRY(cudaStreamSynchronize(t->ctx->stream));
+  return PFT_OK;
+}
+
+// ------------------------------------------------------------------ multi-GPU
+int pft_comm_get_unique_id(void* id128) {
+  if (!id128) { set_last_error("null id"); return PFT_ERR_INVALID; }
+  int rc = load_nccl();
+  if (rc) return rc;
+  PFT_NCCL_TRY(g_nccl.GetUniqueId(id128));
+  return PFT_OK;
+}
+
+int pft_tracker_comm_init(pft_tracker* t, int nranks, int rank, const void* id128) {
+  if (!t || !id128) { set_last_error("null argument"); return PFT_ERR_INVALID; }
+  if (nranks < 1 || rank < 0 || rank >= nranks) { set_last_error("bad rank %d of %d", rank, nranks); return PFT_ERR_INVALID; }
+  if (t->n_cap > 0) { set_last_error("pft_tracker_comm_init must precede the first compute()/set_particles()"); return PFT_ERR_STATE; }
+  PFT_CUDA_TRY(cudaSetDevice(t->ctx->device));
+  t->nranks = nranks; t->rank = rank;
+  invalidate_graph(t);
+  if (nranks == 1) return PFT_OK;
+  int rc = load_nccl();
+  if (rc) return rc;
+  UidByValue uid;
+  memcpy(uid.internal, id128, 128);
+  PFT_NCCL_TRY(g_nccl.CommInitRank(&t->comm, nranks, uid, rank));
+  return PFT_OK;
+}
+
+int pft_tracker_comm_destroy(pft_tracker* t) {
+  if (!t) { set_last_error("null tracker"); return PFT_ERR_INVALID; }
+  if (t->comm) {
+    PFT_CUDA_TRY(cudaSetDevice(t->ctx->device));
+    PFT_CUDA_TRY(cudaStreamSynchronize(t->ctx->stream));
+    g_nccl.CommDestroy(t->comm);
+    t->comm = nullptr;
+    invalidate_graph(t);
+  }
+  return PFT_OK;
+}
+
+// Set the sharding without a communicator: this rank evaluates particles i % nranks == rank only and the
+// caller moves the crop box / raw weights itself.  Used by the world-size-2 CPU (gloo) tests of the host
+// logic and by single-GPU emulation of a sharded run.
+int pft_tracker_set_shard(pft_tracker* t, int nranks, int rank) {
+  if (!t) { set_last_error("null tracker"); return PFT_ERR_INVALID; }
+  if (nranks < 1 || rank < 0 || rank >= nranks) { set_last_error("bad rank %d of %d", rank, nranks); return PFT_ERR_INVALID; }
+  if (t->n_cap > 0) { set_last_error("pft_tracker_set_shard must precede the first compute()/set_particles()"); return PFT_ERR_STATE; }
+  t->nranks = nranks; t->rank = rank;
+  invalidate_graph(t);
+  return PFT_OK;
+}
+
+int pft_tracker_graph_replays(pft_tracker* t, uint64_t* n) {
+  if (!t || !n) { set_last_error("null argument"); return PFT_ERR_INVALID; }
+  *n = t->graph_replays;
+  return PFT_OK;
+}
+
+}  // extern "C"

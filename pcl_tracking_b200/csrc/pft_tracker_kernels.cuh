@@ -1,0 +1,853 @@
+// pft_tracker_kernels.cuh -- device code of kernels K2 (scene index), K3 (weight) and K4
+// (normalise / resample / update).  Included by pft_tracker.cu only.
+//
+// What each kernel replaces (PCL-1.8.0 upstream; call sites in
+// ref: src/auto_tracking.cpp:198-258, :688-697):
+//   matrices_kernel      ParticleXYZRPY::toEigenMatrix = pcl::getTransformation          (A.6)
+//   aabb_kernel          transformPointCloud per particle + calcBoundingBox               (A.3)
+//   index_*_kernel       cropInputPointCloud + search::Octree::setInputCloud              (A.3, A.5)
+//   weight_kernel        NearestPairPointCloudCoherence::computeCoherence + Distance/HSV  (A.4)
+//   normalize_kernel     ParticleFilterTracker::normalizeWeight                           (A.6)
+//   update_kernel        ParticleFilterTracker::update                                    (A.6)
+//   cdf/resample/kld_*   (KLDAdaptive)ParticleFilterTracker::resample                     (A.7)
+//   init_particles_kernel ParticleFilterTracker::initParticles                            (A.8)
+#pragma once
+#include "pft_common.cuh"
+
+namespace pft {
+
+// ------------------------------------------------------------------ device-resident tracker state
+struct TrackerState {
+  int particle_num;       // live particle count (changes on the device in KLD mode)
+  int has_particles;
+  float aabb[6];          // crop box being accumulated by aabb_kernel (atomic min/max)
+  DevParticle rep;        // representative_state_
+  DevParticle motion;     // motion_
+  double fit_ratio;
+  double weight_sum;
+  unsigned long long draw_call;  // Philox stream position (advanced on the device: graph replays stay distinct)
+};
+
+struct NoiseParams {      // host-precomputed square roots (IEEE, identical to the oracle's)
+  double mean[6];
+  double sigma[6];        // sqrt(cov[d])
+  double sigma_q[3];      // sqrt((double)0.2862f * cov[3+d])
+  int quat_mode;
+};
+
+struct CoherenceParams {
+  double max_d2;          // maximum_distance_^2 (double compare, as upstream)
+  double dist_w, hsv_w;
+  float h_w, s_w, v_w;
+  float r_max;            // min(maximum_distance_, 1e18)
+  int use_dist, use_hsv;
+};
+
+struct GridView {
+  const unsigned int* __restrict__ words;  // occupancy bits, x fastest, 32 cells per word
+  const int* __restrict__ rank;            // occupied cells before each word
+  const float4* __restrict__ pts;          // {x,y,z,hsv}: primary slots [0,n_occupied) in cell order, overflow after
+  const int* __restrict__ orig;            // input-cloud index of each slot (tie-break key)
+  const int* __restrict__ next;            // overflow chain per slot (-1 ends)
+};
+
+// ------------------------------------------------------------------ small math (arithmetic contract)
+__device__ __forceinline__ void sincos_c(float a, float& s, float& c) {
+  double ds, dc;
+  sincos((double)a, &ds, &dc);
+  s = (float)ds; c = (float)dc;
+}
+
+// pcl::getTransformation (common/impl/eigen.hpp): row-major 3x4
+__device__ __forceinline__ void particle_to_matrix(float x, float y, float z, float roll, float pitch, float yaw, float* m) {
+  float A, B, C, D, E, F;
+  sincos_c(yaw, B, A); sincos_c(pitch, D, C); sincos_c(roll, F, E);
+  const float DE = D * E, DF = D * F;
+  m[0] = A * C; m[1] = A * DF - B * E; m[2] = B * F + A * DE;  m[3] = x;
+  m[4] = B * C; m[5] = A * E + B * DF; m[6] = B * DE - A * F;  m[7] = y;
+  m[8] = -D;    m[9] = C * F;          m[10] = C * E;          m[11] = z;
+}
+__device__ __forceinline__ void matrix_to_rpy(const float* m, float& roll, float& pitch, float& yaw) {
+  roll = (float)atan2((double)m[9], (double)m[10]);
+  pitch = (float)asin((double)(-m[8]));
+  yaw = (float)atan2((double)m[4], (double)m[0]);
+}
+// pcl::transformPointCloud, dense branch
+__device__ __forceinline__ void xform(const float* m, float x, float y, float z, float& ox, float& oy, float& oz) {
+  ox = ((m[0] * x + m[1] * y) + m[2] * z) + m[3];
+  oy = ((m[4] * x + m[5] * y) + m[6] * z) + m[7];
+  oz = ((m[8] * x + m[9] * y) + m[10] * z) + m[11];
+}
+
+struct Quat { float w, x, y, z; };
+// Eigen::Quaternionf(Matrix3f)
+__device__ inline Quat quat_from_matrix(const float* m) {
+  Quat q;
+  float t = (m[0] + m[5]) + m[10];
+  if (t > 0.f) {
+    t = sqrtf(t + 1.0f);
+    q.w = 0.5f * t;
+    t = 0.5f / t;
+    q.x = (m[9] - m[6]) * t; q.y = (m[2] - m[8]) * t; q.z = (m[4] - m[1]) * t;
+  } else {
+    int i = 0;
+    if (m[5] > m[0]) i = 1;
+    if (m[10] > m[i * 5]) i = 2;
+    const int j = (i + 1) % 3, k = (j + 1) % 3;
+    t = sqrtf(((m[i * 5] - m[j * 5]) - m[k * 5]) + 1.0f);
+    float v[3];
+    v[i] = 0.5f * t;
+    t = 0.5f / t;
+    q.w = (m[k * 4 + j] - m[j * 4 + k]) * t;
+    v[j] = (m[j * 4 + i] + m[i * 4 + j]) * t;
+    v[k] = (m[k * 4 + i] + m[i * 4 + k]) * t;
+    q.x = v[0]; q.y = v[1]; q.z = v[2];
+  }
+  return q;
+}
+__device__ __forceinline__ Quat quat_mul(const Quat& a, const Quat& b) {
+  Quat r;
+  r.w = ((a.w * b.w - a.x * b.x) - a.y * b.y) - a.z * b.z;
+  r.x = ((a.w * b.x + a.x * b.w) + a.y * b.z) - a.z * b.y;
+  r.y = ((a.w * b.y + a.y * b.w) + a.z * b.x) - a.x * b.z;
+  r.z = ((a.w * b.z + a.z * b.w) + a.x * b.y) - a.y * b.x;
+  return r;
+}
+// ParticleXYZRPY::sample with injected standard normals z[6]
+__device__ inline void particle_sample(DevParticle& p, const NoiseParams& np, const float* z) {
+  p.x += (float)(np.mean[0] + np.sigma[0] * (double)z[0]);
+  p.y += (float)(np.mean[1] + np.sigma[1] * (double)z[1]);
+  p.z += (float)(np.mean[2] + np.sigma[2] * (double)z[2]);
+  if (!np.quat_mode) {
+    p.roll += (float)(np.mean[3] + np.sigma[3] * (double)z[3]);
+    p.pitch += (float)(np.mean[4] + np.sigma[4] * (double)z[4]);
+    p.yaw += (float)(np.mean[5] + np.sigma[5] * (double)z[5]);
+    return;
+  }
+  float cur[12], mr[12];
+  particle_to_matrix(p.x, p.y, p.z, p.roll, p.pitch, p.yaw, cur);
+  const Quat q_cur = quat_from_matrix(cur);
+  particle_to_matrix((float)np.mean[0], (float)np.mean[1], (float)np.mean[2], (float)np.mean[3], (float)np.mean[4], (float)np.mean[5], mr);
+  const Quat q_mean = quat_from_matrix(mr);
+  const float a = (float)(np.sigma_q[0] * (double)z[3]);
+  const float b = (float)(np.sigma_q[1] * (double)z[4]);
+  const float c = (float)(np.sigma_q[2] * (double)z[5]);
+  const float n2 = ((a * a + b * b) + c * c) + 1.0f;  // Quaternionf(Vector4f(a,b,c,1)): x,y,z,w
+  const float n = sqrtf(n2);
+  const Quat qs{1.0f / n, a / n, b / n, c / n};
+  const Quat q = quat_mul(quat_mul(qs, q_mean), q_cur);
+  const float tx = 2.f * q.x, ty = 2.f * q.y, tz = 2.f * q.z;
+  const float twx = tx * q.w, twy = ty * q.w, twz = tz * q.w;
+  const float txx = tx * q.x, txy = ty * q.x, txz = tz * q.x;
+  const float tyy = ty * q.y, tyz = tz * q.y, tzz = tz * q.z;
+  float R[12];
+  R[0] = 1.f - (tyy + tzz); R[1] = txy - twz;         R[2] = txz + twy;
+  R[4] = txy + twz;         R[5] = 1.f - (txx + tzz); R[6] = tyz - twx;
+  R[8] = txz - twy;         R[9] = tyz + twx;         R[10] = 1.f - (txx + tyy);
+  matrix_to_rpy(R, p.roll, p.pitch, p.yaw);
+}
+
+// HSVColorCoherence::RGB2HSV (integer, OpenCV style).  Upstream calls it with (Red, Blue, Green).
+__device__ __forceinline__ int div_table(int i) { return i == 0 ? 0 : (2088960 + i) / (2 * i); }  // round(1044480/i)
+__device__ inline unsigned int rgba_to_hsv_packed(unsigned int rgba) {
+  const int B = rgba & 0xff, G = (rgba >> 8) & 0xff, R = (rgba >> 16) & 0xff;
+  const int r = R, g = B, b = G;  // upstream quirk: G and B swapped at the call site
+  const int v = max(r, max(g, b)), vmin = min(r, min(g, b));
+  const int diff = v - vmin;
+  const int vr = (v == r) ? -1 : 0, vg = (v == g) ? -1 : 0;
+  const int s = (diff * div_table(v)) >> 12;
+  int h = (vr & (g - b)) + (~vr & ((vg & (b - r + 2 * diff)) + ((~vg) & (r - g + 4 * diff))));
+  h = (h * div_table(diff) * 15 + (1 << 18)) >> 19;
+  h += h < 0 ? 180 : 0;
+  return (unsigned int)h | ((unsigned int)s << 8) | ((unsigned int)v << 16);
+}
+
+// ------------------------------------------------------------------ K: init / matrices / AABB
+__global__ void init_particles_kernel(TrackerState* st, DevParticle* parts, int n, const float* __restrict__ trans12,
+                                      NoiseParams np, const float* __restrict__ normals /* slot 0: [stride][6] */) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  DevParticle rep{trans12[3], trans12[7], trans12[11], 1.f, 0.f, 0.f, 0.f, 0.f};
+  matrix_to_rpy(trans12, rep.roll, rep.pitch, rep.yaw);
+  rep.weight = 1.0f / (float)n;
+  if (i == 0) {
+    st->rep = rep;
+    st->motion = DevParticle{0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 0.f};
+    st->particle_num = n;
+    st->has_particles = 1;
+    st->draw_call += 1ull;
+  }
+  if (i >= n) return;
+  DevParticle p{0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 0.f};
+  float z[6];
+#pragma unroll
+  for (int d = 0; d < 6; ++d) z[d] = normals[(size_t)i * 6 + d];
+  particle_sample(p, np, z);
+  p.x += rep.x; p.y += rep.y; p.z += rep.z; p.roll += rep.roll; p.pitch += rep.pitch; p.yaw += rep.yaw;
+  p.weight = 1.0f / (float)n;
+  parts[i] = p;
+}
+
+__global__ void matrices_kernel(TrackerState* st, const DevParticle* __restrict__ parts, float* __restrict__ mats) {
+  const int n = st->particle_num;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) {
+    st->aabb[0] = st->aabb[1] = st->aabb[2] = FLT_MAX;
+    st->aabb[3] = st->aabb[4] = st->aabb[5] = -FLT_MAX;
+  }
+  for (int k = i; k < n; k += gridDim.x * blockDim.x) {
+    const DevParticle p = parts[k];
+    float m[12];
+    particle_to_matrix(p.x, p.y, p.z, p.roll, p.pitch, p.yaw, m);
+#pragma unroll
+    for (int d = 0; d < 3; ++d) reinterpret_cast<float4*>(mats)[(size_t)k * 3 + d] = make_float4(m[4 * d], m[4 * d + 1], m[4 * d + 2], m[4 * d + 3]);
+  }
+}
+
+// One warp per slot.  Live slots of this rank's slice are recomputed; slots >= particle_num keep the
+// box of the last particle that occupied them (upstream's stale transed_reference_vector_ entries).
+__global__ void aabb_kernel(TrackerState* st, const float4* __restrict__ model, int M, const float* __restrict__ mats,
+                            float* __restrict__ slot_aabb, int n_slots, int nranks, int rank) {
+  const int n = st->particle_num;
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int s = warp; s < n_slots; s += nwarps) {
+    float mn[3], mx[3];
+    if (s < n) {
+      if (s % nranks != rank) continue;  // another rank's live slot (particle i belongs to rank i % nranks)
+      float m[12];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const float4 r = reinterpret_cast<const float4*>(mats)[(size_t)s * 3 + d];
+        m[4 * d] = r.x; m[4 * d + 1] = r.y; m[4 * d + 2] = r.z; m[4 * d + 3] = r.w;
+      }
+      mn[0] = mn[1] = mn[2] = FLT_MAX; mx[0] = mx[1] = mx[2] = -FLT_MAX;
+      for (int j = lane; j < M; j += 32) {
+        const float4 p = model[j];
+        float x, y, z;
+        xform(m, p.x, p.y, p.z, x, y, z);
+        mn[0] = fminf(mn[0], x); mn[1] = fminf(mn[1], y); mn[2] = fminf(mn[2], z);
+        mx[0] = fmaxf(mx[0], x); mx[1] = fmaxf(mx[1], y); mx[2] = fmaxf(mx[2], z);
+      }
+#pragma unroll
+      for (int d = 0; d < 3; ++d) { mn[d] = warp_min(mn[d]); mx[d] = warp_max(mx[d]); }
+      if (lane < 3) slot_aabb[(size_t)s * 6 + lane] = mn[lane];
+      else if (lane < 6) slot_aabb[(size_t)s * 6 + lane] = mx[lane - 3];
+    } else {
+#pragma unroll
+      for (int d = 0; d < 3; ++d) { mn[d] = slot_aabb[(size_t)s * 6 + d]; mx[d] = slot_aabb[(size_t)s * 6 + 3 + d]; }
+      if (mn[0] > mx[0]) continue;  // never used
+    }
+    if (lane < 3) atomic_min_float(&st->aabb[lane], mn[lane]);
+    else if (lane < 6) atomic_max_float(&st->aabb[lane], mx[lane - 3]);
+  }
+}
+
+// ------------------------------------------------------------------ K2: scene index build
+__device__ inline void compute_index_header(const float* aabb, float inv_leaf, int max_words, IndexHeader& h) {
+#pragma unroll
+  for (int d = 0; d < 6; ++d) h.aabb[d] = aabb[d];
+  h.inv_leaf = inv_leaf;
+  h.n_cropped = 0; h.n_occupied = 0; h.n_overflow = 0;
+  h.valid = (aabb[0] <= aabb[3] && aabb[1] <= aabb[4] && aabb[2] <= aabb[5]) ? 1 : 0;
+  h.level = 0; h.level_scale = 1.0f; h.wx = 0; h.n_words = 0;
+  h.dim[0] = h.dim[1] = h.dim[2] = 0; h.origin[0] = h.origin[1] = h.origin[2] = 0;
+  h.cell = 1.0f / inv_leaf;
+  if (!h.valid) return;
+  float lo[3], hi[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) { lo[d] = aabb[d] * inv_leaf; hi[d] = aabb[3 + d] * inv_leaf; }
+  for (int level = 0; level < 24; ++level) {
+    const float ls = 1.0f / (float)(1 << level);
+    long long words = 1;
+    int dim[3], org[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      org[d] = (int)floorf(lo[d] * ls);
+      dim[d] = (int)floorf(hi[d] * ls) - org[d] + 1;
+    }
+    const int wx = (dim[0] + 31) >> 5;
+    words = (long long)wx * dim[1] * dim[2];
+    if (words <= (long long)max_words || level == 23) {
+      h.level = level; h.level_scale = ls; h.wx = wx; h.n_words = (int)min(words, (long long)max_words);
+#pragma unroll
+      for (int d = 0; d < 3; ++d) { h.dim[d] = dim[d]; h.origin[d] = org[d]; }
+      h.cell = (float)(1 << level) / inv_leaf;
+      break;
+    }
+  }
+}
+
+// Every block derives the header from the crop box (a pure function of it), block 0 publishes it, and
+// all blocks clear the occupancy words and the per-slot chain heads.
+__global__ void index_begin_kernel(const TrackerState* __restrict__ st, IndexHeader* hdr, unsigned int* words, int* cell_count,
+                                   int* next, const CloudHeader* __restrict__ scene_hdr, float inv_leaf, int max_words) {
+  __shared__ IndexHeader h;
+  if (threadIdx.x == 0) {
+    compute_index_header(st->aabb, inv_leaf, max_words, h);
+    if (blockIdx.x == 0) *hdr = h;
+  }
+  __syncthreads();
+  const int nw = h.n_words, ns = scene_hdr->n;
+  const int stride = gridDim.x * blockDim.x;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nw; i += stride) words[i] = 0u;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ns; i += stride) { cell_count[i] = 0; next[i] = -1; }
+}
+
+__device__ __forceinline__ bool in_crop(const float4& p, const IndexHeader& h) {
+  // three inclusive PassThrough passes (x, y, z) on finite points
+  return isfinite(p.x) && isfinite(p.y) && isfinite(p.z) && p.x >= h.aabb[0] && p.x <= h.aabb[3] && p.y >= h.aabb[1] &&
+         p.y <= h.aabb[4] && p.z >= h.aabb[2] && p.z <= h.aabb[5];
+}
+__device__ __forceinline__ void cell_of(const float4& p, const IndexHeader& h, int& cx, int& cy, int& cz) {
+  cx = (int)floorf((p.x * h.inv_leaf) * h.level_scale) - h.origin[0];
+  cy = (int)floorf((p.y * h.inv_leaf) * h.level_scale) - h.origin[1];
+  cz = (int)floorf((p.z * h.inv_leaf) * h.level_scale) - h.origin[2];
+}
+
+__global__ void index_bits_kernel(const float4* __restrict__ scene, const CloudHeader* __restrict__ scene_hdr, IndexHeader* hdr,
+                                  unsigned int* words) {
+  __shared__ IndexHeader h;
+  if (threadIdx.x == 0) h = *hdr;
+  __syncthreads();
+  if (!h.valid) return;
+  const int ns = scene_hdr->n;
+  int local = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ns; i += gridDim.x * blockDim.x) {
+    const float4 p = scene[i];
+    if (!in_crop(p, h)) continue;
+    int cx, cy, cz;
+    cell_of(p, h, cx, cy, cz);
+    const int w = (cz * h.dim[1] + cy) * h.wx + (cx >> 5);
+    atomicOr(&words[w], 1u << (cx & 31));
+    ++local;
+  }
+  local = warp_sum(local);
+  if ((threadIdx.x & 31) == 0 && local) atomicAdd(&hdr->n_cropped, local);
+}
+
+__global__ void __launch_bounds__(1024) index_rank_kernel(IndexHeader* hdr, const unsigned int* __restrict__ words, int* __restrict__ rank) {
+  __shared__ int smem[34];
+  const int nw = hdr->n_words;
+  const int total = block_exclusive_scan<int>(
+      nw, [&](int i) { return __popc(words[i]); }, [&](int i, int ex) { rank[i] = ex; }, smem);
+  if (threadIdx.x == 0) hdr->n_occupied = total;
+}
+
+__global__ void index_scatter_kernel(const float4* __restrict__ scene, const CloudHeader* __restrict__ scene_hdr, IndexHeader* hdr,
+                                     const unsigned int* __restrict__ words, const int* __restrict__ rank, int* cell_count,
+                                     float4* __restrict__ pts, int* __restrict__ orig, int* next) {
+  __shared__ IndexHeader h;
+  if (threadIdx.x == 0) h = *hdr;
+  __syncthreads();
+  if (!h.valid) return;
+  const int ns = scene_hdr->n;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ns; i += gridDim.x * blockDim.x) {
+    const float4 p = scene[i];
+    if (!in_crop(p, h)) continue;
+    int cx, cy, cz;
+    cell_of(p, h, cx, cy, cz);
+    const int w = (cz * h.dim[1] + cy) * h.wx + (cx >> 5);
+    const unsigned int m = words[w];
+    const int slot = rank[w] + __popc(m & ((1u << (cx & 31)) - 1u));
+    const float4 q = make_float4(p.x, p.y, p.z, __uint_as_float(rgba_to_hsv_packed(__float_as_uint(p.w))));
+    const int pos = atomicAdd(&cell_count[slot], 1);
+    if (pos == 0) {
+      pts[slot] = q; orig[slot] = i;
+    } else {
+      // a second point in the same cell: append after the primary slots and link it to the cell
+      const int o = h.n_occupied + atomicAdd(&hdr->n_overflow, 1);
+      pts[o] = q; orig[o] = i;
+      // push-front on the chain of `slot`; chains are only traversed by later kernels
+      int head = atomicExch(&next[slot], o);
+      next[o] = head;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ K3: weight
+// Exact nearest neighbour over the occupancy grid: expanding cube shells around the query cell,
+// candidate rows pruned by the current best distance, termination when the scanned cube provably
+// contains the nearest point (or nothing can be inside r_max).  Ties go to the lower input index.
+struct NNResult { int slot; float d2; };
+
+__device__ __forceinline__ void nn_eval(const GridView& g, int slot, float qx, float qy, float qz, NNResult& best) {
+  const float4 p = g.pts[slot];
+  const float dx = qx - p.x, dy = qy - p.y, dz = qz - p.z;
+  const float d2 = (dx * dx + dy * dy) + dz * dz;
+  if (d2 < best.d2) { best.d2 = d2; best.slot = slot; }
+  else if (d2 == best.d2 && best.slot >= 0 && g.orig[slot] < g.orig[best.slot]) { best.slot = slot; }
+}
+
+__device__ __forceinline__ void nn_scan_row(const GridView& g, const IndexHeader& h, int row, int xa, int xb, float qx, float qy,
+                                            float qz, NNResult& best) {
+  xa = max(xa, 0); xb = min(xb, h.dim[0] - 1);
+  if (xa > xb) return;
+  const int wa = xa >> 5, wb = xb >> 5;
+  for (int w = wa; w <= wb; ++w) {
+    const unsigned int m = g.words[row + w];
+    unsigned int keep = 0xffffffffu;
+    unsigned int below = 0u;
+    if (w == wa) { below = (1u << (xa & 31)) - 1u; keep &= ~below; }
+    if (w == wb) { const int e = xb & 31; keep &= (e == 31) ? 0xffffffffu : ((2u << e) - 1u); }
+    const unsigned int bits = m & keep;
+    if (!bits) continue;
+    const int base = g.rank[row + w] + __popc(m & below);
+    const int cnt = __popc(bits);
+    for (int k = 0; k < cnt; ++k) {
+      nn_eval(g, base + k, qx, qy, qz, best);
+      if (h.n_overflow) for (int o = g.next[base + k]; o >= 0; o = g.next[o]) nn_eval(g, o, qx, qy, qz, best);
+    }
+  }
+}
+
+__device__ __forceinline__ float axis_gap(int d, float t) {  // min distance (cell units) to the cell at offset d
+  return d > 0 ? (float)d - t : (d < 0 ? t - (float)(d + 1) : 0.f);
+}
+
+__device__ inline NNResult nn_search(const GridView& g, const IndexHeader& h, float qx, float qy, float qz, float r_max) {
+  NNResult best{-1, FLT_MAX};
+  if (h.n_occupied == 0) return best;
+  const float sx = (qx * h.inv_leaf) * h.level_scale, sy = (qy * h.inv_leaf) * h.level_scale, sz = (qz * h.inv_leaf) * h.level_scale;
+  const float fx = floorf(sx), fy = floorf(sy), fz = floorf(sz);
+  const int cx = (int)fx - h.origin[0], cy = (int)fy - h.origin[1], cz = (int)fz - h.origin[2];
+  const float tx = sx - fx, ty = sy - fy, tz = sz - fz;
+  const float tmin = fminf(fminf(fminf(tx, 1.f - tx), fminf(ty, 1.f - ty)), fminf(tz, 1.f - tz));
+  const float cell2 = h.cell * h.cell;
+  const int rcap = max(1, (int)ceilf(r_max / h.cell - tmin + 0.002f));
+  int r_prev = -1, r = 1;
+  while (true) {
+    const int z0 = max(cz - r, 0), z1 = min(cz + r, h.dim[2] - 1);
+    const int y0 = max(cy - r, 0), y1 = min(cy + r, h.dim[1] - 1);
+    for (int z = z0; z <= z1; ++z) {
+      const int dz = z - cz;
+      const float az = axis_gap(dz, tz);
+      const float az2 = az * az;
+      for (int y = y0; y <= y1; ++y) {
+        const int dy = y - cy;
+        const float ay = axis_gap(dy, ty);
+        const float row2 = (az2 + ay * ay) * cell2;
+        if (row2 * 0.9999f > best.d2) continue;  // no cell of this row can hold a closer (or tying) point
+        const int row = (z * h.dim[1] + y) * h.wx;
+        const bool inner = max(abs(dy), abs(dz)) <= r_prev;
+        if (!inner) nn_scan_row(g, h, row, cx - r, cx + r, qx, qy, qz, best);
+        else {
+          nn_scan_row(g, h, row, cx - r, cx - r_prev - 1, qx, qy, qz, best);
+          nn_scan_row(g, h, row, cx + r_prev + 1, cx + r, qx, qy, qz, best);
+        }
+      }
+    }
+    // every unscanned point lies outside the cube of half-width (r + tmin) cells around the query
+    const float grad = ((float)r + tmin - 0.002f) * h.cell;
+    const bool covered = (cx - r <= 0) && (cx + r >= h.dim[0] - 1) && (cy - r <= 0) && (cy + r >= h.dim[1] - 1) && (cz - r <= 0) &&
+                         (cz + r >= h.dim[2] - 1);
+    if (covered) break;
+    if (best.slot >= 0 && best.d2 <= grad * grad) break;
+    if (grad >= r_max) break;
+    r_prev = r;
+    int need;
+    if (best.slot >= 0) need = max(r + 1, (int)ceilf(sqrtf(best.d2) / h.cell - tmin + 0.004f));
+    else need = 2 * r + 1;
+    r = min(need, max(rcap, r + 1));
+  }
+  return best;
+}
+
+struct WeightArgs {
+  const TrackerState* st;
+  const IndexHeader* hdr;
+  GridView g;
+  const float4* model;      // {x,y,z,hsv} in tile order
+  const int* model_perm;    // tile order -> order of the reference cloud as given
+  int M;
+  const float* mats;
+  double* partial;          // [chunks][n_max]
+  int chunks, chunk_len, n_max;
+  int nranks, rank;         // particle i is evaluated by rank i % nranks
+  CoherenceParams co;
+  int dbg_k; int* dbg_idx; float* dbg_d2;
+};
+
+template <bool USE_HSV>
+__global__ void __launch_bounds__(256) weight_kernel(const WeightArgs a) {
+  __shared__ IndexHeader h;
+  __shared__ float lut_h[256], lut_s[256];
+  __shared__ double red[32];
+  __shared__ float mat[12];
+  if (threadIdx.x == 0) h = *a.hdr;
+  if (USE_HSV) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) { lut_h[i] = (float)i / 180.0f; lut_s[i] = (float)i / 255.0f; }
+  }
+  __syncthreads();
+  const int n = a.st->particle_num;
+  const int n_local = n > a.rank ? (n - a.rank + a.nranks - 1) / a.nranks : 0;
+  const int items = n_local * a.chunks;
+  for (int item = blockIdx.x; item < items; item += gridDim.x) {
+    const int i = a.rank + (item / a.chunks) * a.nranks, c = item % a.chunks;
+    __syncthreads();
+    if (threadIdx.x < 12) mat[threadIdx.x] = a.mats[(size_t)i * 12 + threadIdx.x];
+    __syncthreads();
+    float m[12];
+#pragma unroll
+    for (int d = 0; d < 12; ++d) m[d] = mat[d];
+    const int j0 = c * a.chunk_len, j1 = min(a.M, j0 + a.chunk_len);
+    double val = 0.0;
+    for (int j = j0 + threadIdx.x; j < j1; j += blockDim.x) {
+      const float4 mp = a.model[j];
+      float qx, qy, qz;
+      xform(m, mp.x, mp.y, mp.z, qx, qy, qz);
+      const NNResult nn = nn_search(a.g, h, qx, qy, qz, a.co.r_max);
+      if (i < a.dbg_k) {
+        const size_t o = (size_t)i * a.M + a.model_perm[j];
+        a.dbg_idx[o] = nn.slot >= 0 ? a.g.orig[nn.slot] : -1;
+        a.dbg_d2[o] = nn.d2;
+      }
+      if (nn.slot >= 0 && (double)nn.d2 < a.co.max_d2) {
+        double cc = 1.0;
+        if (a.co.use_dist) {
+          const double d = (double)sqrtf(nn.d2);
+          cc *= 1.0 / (1.0 + d * d * a.co.dist_w);
+        }
+        if (USE_HSV) {
+          const unsigned int sb = __float_as_uint(mp.w), tb = __float_as_uint(a.g.pts[nn.slot].w);
+          const float sh = lut_h[sb & 0xff], ss = lut_s[(sb >> 8) & 0xff], sv = lut_s[(sb >> 16) & 0xff];
+          const float th = lut_h[tb & 0xff], ts = lut_s[(tb >> 8) & 0xff], tv = lut_s[(tb >> 16) & 0xff];
+          const float hd = fabsf(sh - th);
+          float hd2;
+          if (sh < th) hd2 = fabsf(1.0f + sh - th); else hd2 = fabsf(1.0f + th - sh);
+          float h_diff;
+          if (hd < hd2) h_diff = a.co.h_w * hd * hd; else h_diff = a.co.h_w * hd2 * hd2;
+          const float s_diff = a.co.s_w * (ss - ts) * (ss - ts);
+          const float v_diff = a.co.v_w * (sv - tv) * (sv - tv);
+          const float diff2 = h_diff + s_diff + v_diff;
+          cc *= 1.0 / (1.0 + a.co.hsv_w * (double)diff2);
+        }
+        val += cc;
+      }
+    }
+    val = block_sum(val, red);
+    if (threadIdx.x == 0) a.partial[(size_t)c * a.n_max + i] = val;
+  }
+}
+
+// Where particle i's raw weight lives in the all-gathered buffer [nranks][slice_cap].
+__device__ __forceinline__ int raw_slot(int i, int nranks, int slice_cap) { return (i % nranks) * slice_cap + i / nranks; }
+
+// raw weight = -(float)sum over chunks (fixed order).  Used on its own before the NCCL all-gather.
+__global__ void raw_weights_kernel(const TrackerState* __restrict__ st, const double* __restrict__ partial, int chunks, int n_max,
+                                   float* __restrict__ raw, int slice_cap, int nranks, int rank) {
+  const int n = st->particle_num;
+  for (int l = blockIdx.x * blockDim.x + threadIdx.x; rank + l * nranks < n; l += gridDim.x * blockDim.x) {
+    const int i = rank + l * nranks;
+    double v = 0.0;
+    for (int c = 0; c < chunks; ++c) v += partial[(size_t)c * n_max + i];
+    raw[rank * slice_cap + l] = -(float)v;
+  }
+}
+
+// ------------------------------------------------------------------ K4a: normalizeWeight (one block)
+__global__ void __launch_bounds__(1024) normalize_kernel(TrackerState* st, DevParticle* parts, const float* __restrict__ raw, double alpha,
+                                                         int nranks, int slice_cap, const CloudHeader* __restrict__ scene_hdr) {
+  __shared__ double red[32];
+  __shared__ double s_min, s_max, s_sum;
+  if (scene_hdr->n <= 0) return;  // Tracker::initCompute fails on an empty input cloud: compute() is a no-op
+  const int n = st->particle_num;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  double wmin = DBL_MAX, wmax = -DBL_MAX;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double w = (double)raw[raw_slot(i, nranks, slice_cap)];
+    if (wmin > w) wmin = w;
+    if (w != 0.0 && wmax < w) wmax = w;
+  }
+  for (int o = 16; o > 0; o >>= 1) { wmin = fmin(wmin, __shfl_xor_sync(kFull, wmin, o)); wmax = fmax(wmax, __shfl_xor_sync(kFull, wmax, o)); }
+  if (lane == 0) red[wid] = wmin;
+  __syncthreads();
+  if (threadIdx.x == 0) { double v = DBL_MAX; for (int k = 0; k < nw; ++k) v = fmin(v, red[k]); s_min = v; }
+  __syncthreads();
+  if (lane == 0) red[wid] = wmax;
+  __syncthreads();
+  if (threadIdx.x == 0) { double v = -DBL_MAX; for (int k = 0; k < nw; ++k) v = fmax(v, red[k]); s_max = v; }
+  __syncthreads();
+  wmin = s_min; wmax = s_max;
+  double sum = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    float w = raw[raw_slot(i, nranks, slice_cap)];
+    if (wmax != wmin) {
+      if (w != 0.0f) w = (float)exp(1.0 - alpha * ((double)w - wmin) / (wmax - wmin));
+    } else {
+      w = 1.0f / (float)n;
+    }
+    parts[i].weight = w;
+    sum += (double)w;
+  }
+  sum = block_sum(sum, red);
+  if (threadIdx.x == 0) { s_sum = sum; st->fit_ratio = wmin; st->weight_sum = sum; }
+  __syncthreads();
+  sum = s_sum;
+  const float fs = (float)sum;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    if (sum != 0.0) parts[i].weight = parts[i].weight / fs;
+    else parts[i].weight = 1.0f / (float)n;
+  }
+}
+
+// ------------------------------------------------------------------ K4c: update (one block)
+__global__ void __launch_bounds__(1024) update_kernel(TrackerState* st, const DevParticle* __restrict__ parts,
+                                                      const CloudHeader* __restrict__ scene_hdr) {
+  __shared__ double red[32];
+  if (scene_hdr->n <= 0) return;
+  const int n = st->particle_num;
+  double acc[6] = {0, 0, 0, 0, 0, 0};
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const DevParticle p = parts[i];
+    const double w = (double)p.weight;
+    acc[0] += (double)(float)((double)p.x * w); acc[1] += (double)(float)((double)p.y * w); acc[2] += (double)(float)((double)p.z * w);
+    acc[3] += (double)(float)((double)p.roll * w); acc[4] += (double)(float)((double)p.pitch * w); acc[5] += (double)(float)((double)p.yaw * w);
+  }
+  double tot[6];
+#pragma unroll
+  for (int d = 0; d < 6; ++d) tot[d] = block_sum(acc[d], red);
+  if (threadIdx.x == 0) {
+    const DevParticle o = st->rep;
+    DevParticle r{(float)tot[0], (float)tot[1], (float)tot[2], 1.f, (float)tot[3], (float)tot[4], (float)tot[5], 1.0f / (float)n};
+    st->rep = r;
+    st->motion = DevParticle{r.x - o.x, r.y - o.y, r.z - o.z, 1.f, r.roll - o.roll, r.pitch - o.pitch, r.yaw - o.yaw, 0.f};
+  }
+}
+
+// ------------------------------------------------------------------ K4b: resample
+// Cumulative table in 2^-40 fixed point (order-independent integer prefix sums), one block.
+__global__ void __launch_bounds__(1024) cdf_kernel(TrackerState* st, const DevParticle* __restrict__ parts,
+                                                   unsigned long long* __restrict__ cdf, unsigned long long* total_out,
+                                                   int* __restrict__ tbl_rep, int* __restrict__ tbl_min, int tbl_size) {
+  __shared__ unsigned long long smem[34];
+  const int n = st->particle_num;
+  if (threadIdx.x == 0) st->draw_call += 1ull;  // the draws of this resample were generated by the previous launch
+  for (int i = threadIdx.x; i < tbl_size; i += blockDim.x) { tbl_rep[i] = -1; tbl_min[i] = 0x7fffffff; }
+  auto wq = [&](int i) -> unsigned long long {
+    const double w = (double)parts[i].weight;
+    return (w > 0.0) ? (unsigned long long)(w * 1099511627776.0) : 0ull;
+  };
+  const unsigned long long total = block_exclusive_scan<unsigned long long>(
+      n, wq, [&](int i, unsigned long long ex) { cdf[i] = ex + wq(i); }, smem);
+  if (threadIdx.x == 0) *total_out = total;
+}
+
+struct ResampleArgs {
+  const TrackerState* st;
+  const DevParticle* old_parts;
+  DevParticle* new_parts;
+  const unsigned long long* cdf;
+  const unsigned long long* cdf_total;
+  const float* u_select;   // [stride]
+  const float* normals;    // [stride][6]
+  const float* u_motion;   // [stride]
+  const CloudHeader* scene_hdr;
+  int* ancestors;
+  int* bin_keys;           // [n_max][6] (KLD)
+  NoiseParams np;
+  double motion_ratio;
+  float bin_size[6];
+  int kld, n_max, sampler;
+};
+
+__device__ __forceinline__ int cdf_pick(const unsigned long long* __restrict__ cdf, unsigned long long total, int n, double u) {
+  if (total == 0ull) { const int k = (int)(u * (double)n); return k >= n ? n - 1 : k; }
+  const unsigned long long t = (unsigned long long)(u * (double)total);
+  int lo = 0, hi = n - 1;
+  while (lo < hi) { const int mid = (lo + hi) >> 1; if (cdf[mid] > t) hi = mid; else lo = mid + 1; }
+  return lo;
+}
+
+__global__ void resample_kernel(const ResampleArgs a) {
+  const int n_old = a.st->particle_num;
+  const int n_cand = a.kld ? a.n_max : n_old;
+  const unsigned long long total = *a.cdf_total;
+  const float u0 = a.u_select[0];
+  const bool skip = a.scene_hdr->n <= 0;  // empty input cloud: compute() is a no-op, particles carried over unchanged
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < n_cand; n += gridDim.x * blockDim.x) {
+    if (skip) {
+      if (n < n_old) a.new_parts[n] = a.old_parts[n];
+      if (a.kld) {
+#pragma unroll
+        for (int d = 0; d < 6; ++d) a.bin_keys[(size_t)n * 6 + d] = 0;
+      }
+      continue;
+    }
+    if (!a.kld && n == 0) {  // fixed-N tracker: slot 0 is the representative state
+      a.new_parts[0] = a.st->rep;
+      a.ancestors[0] = -1;
+      continue;
+    }
+    double u;
+    if (a.sampler == PFT_SAMPLER_CDF_VDC) {
+      u = (double)u0 + (double)__brev((unsigned int)n) * (1.0 / 4294967296.0);
+      if (u >= 1.0) u -= 1.0;
+    } else {
+      u = (double)a.u_select[n];
+    }
+    const int j = cdf_pick(a.cdf, total, n_old, u);
+    DevParticle x = a.old_parts[j];
+    float z[6];
+#pragma unroll
+    for (int d = 0; d < 6; ++d) z[d] = a.normals[(size_t)n * 6 + d];
+    particle_sample(x, a.np, z);
+    if (a.kld && (double)a.u_motion[n] < a.motion_ratio) {
+      const DevParticle mo = a.st->motion;
+      x.x += mo.x; x.y += mo.y; x.z += mo.z; x.roll += mo.roll; x.pitch += mo.pitch; x.yaw += mo.yaw;
+    }
+    a.new_parts[n] = x;
+    a.ancestors[n] = j;
+    if (a.kld) {
+      const float xs[6] = {x.x, x.y, x.z, x.roll, x.pitch, x.yaw};
+#pragma unroll
+      for (int d = 0; d < 6; ++d) a.bin_keys[(size_t)n * 6 + d] = (int)(xs[d] / a.bin_size[d]);
+    }
+  }
+}
+
+// KLD: k(n) = number of distinct bins among the first n candidates.  A hash set keyed by the 6-int bin
+// records the lowest candidate index of every bin; candidate m is "new" iff it is that lowest index.
+__global__ void kld_insert_kernel(const int* __restrict__ bin_keys, int n_max, int* tbl_rep, int* tbl_min, int* __restrict__ slot_of,
+                                  unsigned int mask) {
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < n_max; n += gridDim.x * blockDim.x) {
+    int key[6];
+    unsigned int hsh = 2166136261u;
+#pragma unroll
+    for (int d = 0; d < 6; ++d) { key[d] = bin_keys[(size_t)n * 6 + d]; hsh = (hsh ^ (unsigned int)key[d]) * 16777619u; hsh ^= hsh >> 15; }
+    unsigned int s = hsh & mask;
+    while (true) {
+      int cur = tbl_rep[s];
+      if (cur == -1) { const int prev = atomicCAS(&tbl_rep[s], -1, n); cur = (prev == -1) ? n : prev; }
+      bool same = true;
+#pragma unroll
+      for (int d = 0; d < 6; ++d) same = same && (bin_keys[(size_t)cur * 6 + d] == key[d]);
+      if (same) { atomicMin(&tbl_min[s], n); slot_of[n] = (int)s; break; }
+      s = (s + 1) & mask;
+    }
+  }
+}
+// One block: first n >= 1 with !(n < n_max && (k(n) < 2 || n < KLbound(k(n)))) becomes particle_num.
+__global__ void __launch_bounds__(1024) kld_stop_kernel(TrackerState* st, const int* __restrict__ tbl_min, const int* __restrict__ slot_of,
+                                                        const double* __restrict__ kl_bound, int n_max,
+                                                        const CloudHeader* __restrict__ scene_hdr) {
+  __shared__ int smem[34];
+  __shared__ int stop;
+  if (scene_hdr->n <= 0) return;
+  if (threadIdx.x == 0) stop = n_max;
+  __syncthreads();
+  auto is_new = [&](int m) -> int { return tbl_min[slot_of[m]] == m ? 1 : 0; };
+  block_exclusive_scan<int>(
+      n_max, is_new,
+      [&](int m, int ex) {
+        const int n = m + 1, k = ex + is_new(m);
+        const bool go_on = (n < n_max) && (k < 2 || (double)n < kl_bound[k]);
+        if (!go_on) atomicMin(&stop, n);
+      },
+      smem);
+  __syncthreads();
+  if (threadIdx.x == 0) st->particle_num = stop;
+}
+
+// ------------------------------------------------------------------ on-device draws (Philox4x32-10)
+__device__ __forceinline__ void philox_round(unsigned int& c0, unsigned int& c1, unsigned int& c2, unsigned int& c3, unsigned int k0, unsigned int k1) {
+  const unsigned int hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+  const unsigned int hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+  c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
+}
+__device__ inline void philox4(unsigned int c0, unsigned int c1, unsigned int c2, unsigned int c3, unsigned int k0, unsigned int k1, unsigned int* out) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) { philox_round(c0, c1, c2, c3, k0, k1); k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+__global__ void draws_kernel(const TrackerState* __restrict__ st, float* u_select, float* normals, float* u_motion, int count,
+                             unsigned long long seed) {
+  const unsigned long long call = st->draw_call;
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < count; n += gridDim.x * blockDim.x) {
+    unsigned int r[8];
+    philox4((unsigned int)n, (unsigned int)call, (unsigned int)(call >> 32), 0u, (unsigned int)seed, (unsigned int)(seed >> 32), r);
+    philox4((unsigned int)n, (unsigned int)call, (unsigned int)(call >> 32), 1u, (unsigned int)seed, (unsigned int)(seed >> 32), r + 4);
+    const float k = 1.0f / 16777216.0f;
+    u_select[n] = (float)(r[0] >> 8) * k;
+    u_motion[n] = (float)(r[1] >> 8) * k;
+#pragma unroll
+    for (int p = 0; p < 3; ++p) {
+      const float u1 = ((float)(r[2 + 2 * p] >> 8) + 1.0f) * k;  // (0,1]
+      const float u2 = (float)(r[3 + 2 * p] >> 8) * k;
+      const float rad = sqrtf(-2.0f * logf(u1));
+      float s, c;
+      sincosf(6.28318530718f * u2, &s, &c);
+      normals[(size_t)n * 6 + 2 * p] = rad * c;
+      normals[(size_t)n * 6 + 2 * p + 1] = rad * s;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ model preparation
+// HSV packing of the reference cloud + spatial ordering so that a warp's 32 queries are neighbours.
+__global__ void model_keys_kernel(const float4* __restrict__ in, int M, unsigned int* __restrict__ keys, int* __restrict__ idx, int M_pad,
+                                  const float* __restrict__ bbox6) {
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < M_pad; j += gridDim.x * blockDim.x) {
+    unsigned int key = 0xffffffffu;
+    if (j < M) {
+      const float4 p = in[j];
+      const float ext = fmaxf(fmaxf(bbox6[3] - bbox6[0], bbox6[4] - bbox6[1]), fmaxf(bbox6[5] - bbox6[2], 1e-6f));
+      auto q = [&](float v, float lo) -> unsigned int { float t = (v - lo) / ext * 1023.0f; t = fminf(fmaxf(t, 0.f), 1023.f); return (unsigned int)t; };
+      auto spread = [](unsigned int v) -> unsigned int {
+        v = (v | (v << 16)) & 0x030000FFu; v = (v | (v << 8)) & 0x0300F00Fu; v = (v | (v << 4)) & 0x030C30C3u; v = (v | (v << 2)) & 0x09249249u;
+        return v;
+      };
+      key = spread(q(p.x, bbox6[0])) | (spread(q(p.y, bbox6[1])) << 1) | (spread(q(p.z, bbox6[2])) << 2);
+    }
+    keys[j] = key; idx[j] = j;
+  }
+}
+__global__ void __launch_bounds__(1024) model_bbox_kernel(const float4* __restrict__ in, int M, float* bbox6) {
+  __shared__ float red[6][32];
+  float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  for (int j = threadIdx.x; j < M; j += blockDim.x) {
+    const float4 p = in[j];
+    mn[0] = fminf(mn[0], p.x); mn[1] = fminf(mn[1], p.y); mn[2] = fminf(mn[2], p.z);
+    mx[0] = fmaxf(mx[0], p.x); mx[1] = fmaxf(mx[1], p.y); mx[2] = fmaxf(mx[2], p.z);
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) { mn[d] = warp_min(mn[d]); mx[d] = warp_max(mx[d]); }
+  if (lane == 0) { for (int d = 0; d < 3; ++d) { red[d][wid] = mn[d]; red[3 + d][wid] = mx[d]; } }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    float v = red[threadIdx.x][0];
+    for (int k = 1; k < (int)(blockDim.x >> 5); ++k) v = threadIdx.x < 3 ? fminf(v, red[threadIdx.x][k]) : fmaxf(v, red[threadIdx.x][k]);
+    bbox6[threadIdx.x] = v;
+  }
+}
+// Bitonic sort of (key, idx) pairs by (key, idx), one block, data in global memory (init-time only).
+__global__ void __launch_bounds__(1024) bitonic_sort_kernel(unsigned int* keys, int* idx, int n_pad) {
+  for (int k = 2; k <= n_pad; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < n_pad; i += blockDim.x) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const unsigned int ka = keys[i], kb = keys[ixj];
+          const int ia = idx[i], ib = idx[ixj];
+          const bool gt = (ka > kb) || (ka == kb && ia > ib);
+          const bool up = (i & k) == 0;
+          if (gt == up) { keys[i] = kb; keys[ixj] = ka; idx[i] = ib; idx[ixj] = ia; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+__global__ void model_gather_kernel(const float4* __restrict__ in, const int* __restrict__ idx, int M, float4* __restrict__ out, int* __restrict__ perm) {
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < M; j += gridDim.x * blockDim.x) {
+    const int s = idx[j];
+    const float4 p = in[s];
+    out[j] = make_float4(p.x, p.y, p.z, __uint_as_float(rgba_to_hsv_packed(__float_as_uint(p.w))));
+    perm[j] = s;
+  }
+}
+
+__global__ void single_matrix_kernel(DevParticle p, float* m12) { particle_to_matrix(p.x, p.y, p.z, p.roll, p.pitch, p.yaw, m12); }
+
+}  // namespace pft

@@ -1,0 +1,107 @@
+"""Parity of kernel K2+K3 (scene index + weight()) with the CPU oracle, through the C ABI.
+
+north_star bar: nearest-neighbour indices bit-exact against the exact-search coherence configuration
+(ties to the lower index), particle weights within 1e-5 relative."""
+import numpy as np
+import pytest
+
+import oracle
+from pcl_tracking_b200 import pcl
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+W_RTOL = 1e-5
+
+
+def _run_weight(seed, use_hsv, n_scene=4000, n_model=300, n_particles=48, max_dist=0.1, sigma_t=0.015, search_res=0.01, dbg=8):
+    scene, model, centre = util.small_case(seed, n_scene=n_scene, n_model=n_model)
+    g, o = util.make_pair(kld=False, particle_num=n_particles, use_hsv=use_hsv, max_dist=max_dist, search_res=search_res)
+    parts = util.particles_around(centre, n_particles, seed=seed + 100, sigma_t=sigma_t)
+    cloud = pcl.PointCloud(scene)
+    g.setReferenceCloud(model)
+    g.setInputCloud(cloud)
+    g.setParticles(parts)
+    g.setDebugNN(dbg)
+    g.weight()
+    o.set_reference(model)
+    o.set_input(scene)
+    o.set_particles(parts)
+    o.weight(keep_nn=True)
+    return g, o, scene, model
+
+
+@pytest.mark.parametrize("seed,use_hsv", [(0, False), (1, True), (2, True)])
+def test_weight_matches_oracle(seed, use_hsv):
+    g, o, scene, model = _run_weight(seed, use_hsv)
+    # crop box and crop count: bit-exact
+    np.testing.assert_array_equal(g.aabb(), o.aabb())
+    cidx, _ = o.cropped()
+    assert g.croppedCount() == len(cidx)
+    # nearest neighbours of the recorded particles: indices and squared distances bit-exact
+    for p in range(8):
+        gi, gd = g.nn(p, len(model))
+        oi, od = o.nn(p, len(model))
+        oi_scene = np.where(oi >= 0, cidx[np.maximum(oi, 0)], -1)
+        inside = od < np.float32(0.1) ** 2 * 4  # the grid search may stop beyond r_max: compare where a match is possible
+        np.testing.assert_array_equal(gi[inside], oi_scene[inside])
+        np.testing.assert_array_equal(gd[inside], od[inside])
+        matched = od.astype(np.float64) < 0.1 * 0.1
+        assert np.all(gd[~inside].astype(np.float64) >= 0.1 * 0.1)
+        assert matched.sum() > 0
+    np.testing.assert_allclose(g.rawWeights(), o.raw_weights(), rtol=W_RTOL, atol=0)
+    gp, op = g.getParticles(), o.get_particles()
+    np.testing.assert_allclose(gp["weight"], op["weight"], rtol=W_RTOL, atol=1e-12)
+    assert abs(float(gp["weight"].astype(np.float64).sum()) - 1.0) < 1e-4
+    assert abs(g.getFitRatio() - o.fit_ratio()) <= 1e-5 * abs(o.fit_ratio())
+
+
+def test_weight_large_max_distance_all_indices_exact():
+    # maximum distance larger than the scene: every model point has a match; all indices must agree
+    g, o, scene, model = _run_weight(5, True, n_scene=1500, n_model=120, n_particles=16, max_dist=10.0, sigma_t=0.05, dbg=16)
+    cidx, _ = o.cropped()
+    for p in range(16):
+        gi, gd = g.nn(p, len(model))
+        oi, od = o.nn(p, len(model))
+        np.testing.assert_array_equal(gi, cidx[oi])
+        np.testing.assert_array_equal(gd, od)
+    np.testing.assert_allclose(g.rawWeights(), o.raw_weights(), rtol=W_RTOL)
+
+
+def test_weight_ties_go_to_lower_index():
+    # duplicated scene points: the same coordinates at two indices; the lower index must win
+    scene, model, centre = util.small_case(7, n_scene=800, n_model=100)
+    scene = np.concatenate([scene, scene[::-1]])  # every point appears twice
+    g, o = util.make_pair(kld=False, particle_num=8, use_hsv=False)
+    parts = util.particles_around(centre, 8, seed=3)
+    cloud = pcl.PointCloud(scene)
+    g.setReferenceCloud(model); g.setInputCloud(cloud); g.setParticles(parts); g.setDebugNN(8); g.weight()
+    o.set_reference(model); o.set_input(scene); o.set_particles(parts); o.weight(keep_nn=True)
+    cidx, _ = o.cropped()
+    for p in range(8):
+        gi, gd = g.nn(p, len(model))
+        oi, od = o.nn(p, len(model))
+        m = od.astype(np.float64) < 0.01
+        np.testing.assert_array_equal(gi[m], cidx[oi[m]])
+        assert np.all(gi[m] < len(scene) // 2 + len(scene))  # sanity
+    np.testing.assert_allclose(g.rawWeights(), o.raw_weights(), rtol=W_RTOL)
+
+
+def test_weight_coarse_and_fine_cells():
+    for res in (0.005, 0.02, 0.05):
+        g, o, scene, model = _run_weight(11, True, n_scene=2500, n_model=150, n_particles=12, search_res=res, dbg=4)
+        np.testing.assert_allclose(g.rawWeights(), o.raw_weights(), rtol=W_RTOL)
+
+
+def test_weight_no_scene_point_in_crop():
+    # scene far away from every particle: all raw weights 0 -> uniform normalised weights (A.6 fallback)
+    scene, model, centre = util.small_case(3, n_scene=500, n_model=50)
+    scene["x"] += 50.0
+    g, o = util.make_pair(kld=False, particle_num=10, use_hsv=True)
+    parts = util.particles_around(centre, 10)
+    cloud = pcl.PointCloud(scene)
+    g.setReferenceCloud(model); g.setInputCloud(cloud); g.setParticles(parts); g.weight()
+    o.set_reference(model); o.set_input(scene); o.set_particles(parts); o.weight()
+    assert g.croppedCount() == 0
+    np.testing.assert_array_equal(g.rawWeights(), np.zeros(10, dtype=np.float32))
+    np.testing.assert_allclose(g.getParticles()["weight"], o.get_particles()["weight"], rtol=1e-6)

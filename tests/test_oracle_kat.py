@@ -1,0 +1,347 @@
+"""Pins the CPU oracle (oracle/pft_oracle.cpp) against the derived known-answer vectors of SURVEY.md
+Appendix A.10 and against independent numpy restatements of the published formulas.
+
+PARITY UNPINNED at the PCL boundary: the reference ships no golden vectors for the tracking path and
+PCL 1.8.0 is not available; these KATs are the strongest pin that exists (see oracle/pft_oracle.cpp)."""
+import math
+
+import numpy as np
+import pytest
+
+import oracle
+from pcl_tracking_b200 import synth
+
+
+def test_normal_quantile_kat():
+    assert abs(oracle.normal_quantile(0.99) - 0.8389129405830074) < 1e-12
+    assert oracle.normal_quantile(0.0) == 0.5
+    assert oracle.normal_quantile(7.0) == 1.0
+    assert oracle.normal_quantile(-7.0) == 0.0
+    # it is a normal CDF (upstream misnomer): cross-check against erf
+    for u in (-2.5, -1.0, -0.3, 0.2, 0.99, 1.7, 3.3):
+        assert abs(oracle.normal_quantile(u) - 0.5 * (1 + math.erf(u / math.sqrt(2)))) < 2e-6
+
+
+def test_kl_bound_kat():
+    expect = {2: 4.037, 3: 7.978, 5: 14.901, 10: 30.534, 20: 59.675, 50: 142.605, 100: 276.402, 150: 408.116, 200: 538.765}
+    for k, v in expect.items():
+        assert abs(oracle.kl_bound(k, 0.99, 0.2) - v) < 5e-3, (k, oracle.kl_bound(k, 0.99, 0.2))
+
+
+def test_div_table_kat():
+    expect = [1044480, 522240, 348160, 261120, 208896, 174080, 149211, 130560, 116053, 104448, 94953, 87040, 80345, 74606, 69632]
+    assert [oracle.div_table(i) for i in range(1, 16)] == expect
+    assert oracle.div_table(255) == 4096
+    assert oracle.div_table(0) == 0
+
+
+def test_rgb2hsv_kat():
+    cases = {(255, 0, 0): (0, 255, 255), (0, 255, 0): (60, 255, 255), (0, 0, 255): (120, 255, 255), (200, 120, 40): (15, 203, 200),
+             (10, 10, 10): (0, 0, 10), (255, 255, 255): (0, 0, 255), (0, 0, 0): (0, 0, 0)}
+    for rgb, hsv in cases.items():
+        assert oracle.rgb2hsv(*rgb) == hsv, rgb
+
+
+def test_rgb2hsv_against_float_formula():
+    rng = np.random.default_rng(0)
+    for r, g, b in rng.integers(0, 256, (300, 3)):
+        h, s, v = oracle.rgb2hsv(int(r), int(g), int(b))
+        mx, mn = max(r, g, b), min(r, g, b)
+        assert v == mx
+        if mx > 0:
+            assert abs(s - 255.0 * (mx - mn) / mx) <= 1.0
+        if mx - mn > 8:
+            d = float(mx - mn)
+            if mx == r:
+                hf = 60.0 * (float(g) - float(b)) / d
+            elif mx == g:
+                hf = 120.0 + 60.0 * (float(b) - float(r)) / d
+            else:
+                hf = 240.0 + 60.0 * (float(r) - float(g)) / d
+            hf = (hf % 360.0) / 2.0
+            dh = abs(h - hf)
+            assert min(dh, 180 - dh) <= 1.0, (r, g, b, h, hf)
+
+
+def _rot_zyx(roll, pitch, yaw):
+    cr, sr, cp, sp, cy, sy = math.cos(roll), math.sin(roll), math.cos(pitch), math.sin(pitch), math.cos(yaw), math.sin(yaw)
+    Rx = np.array([[1, 0, 0], [0, cr, -sr], [0, sr, cr]])
+    Ry = np.array([[cp, 0, sp], [0, 1, 0], [-sp, 0, cp]])
+    Rz = np.array([[cy, -sy, 0], [sy, cy, 0], [0, 0, 1]])
+    return Rz @ Ry @ Rx
+
+
+def test_particle_to_matrix_is_Rz_Ry_Rx():
+    rng = np.random.default_rng(1)
+    for _ in range(50):
+        s = rng.uniform(-1.2, 1.2, 6)
+        m = oracle.particle_to_matrix(s)
+        np.testing.assert_allclose(m[:, :3], _rot_zyx(s[3], s[4], s[5]), atol=3e-7)
+        np.testing.assert_allclose(m[:, 3], s[:3].astype(np.float32), atol=0)
+        back = oracle.matrix_to_particle(m)
+        np.testing.assert_allclose([back["roll"], back["pitch"], back["yaw"]], s[3:], atol=2e-6)
+
+
+def test_identity_matrix():
+    m = oracle.particle_to_matrix([0, 0, 0, 0, 0, 0])
+    np.testing.assert_array_equal(m, np.eye(4, dtype=np.float32)[:3])
+
+
+def test_distance_and_hsv_coherence_formulas():
+    a, b = (0.1, 0.2, 0.3), (0.13, 0.16, 0.3)
+    d2 = np.float32(np.float32(np.float32(0.1) - np.float32(0.13)) ** 2 + np.float32(np.float32(0.2) - np.float32(0.16)) ** 2)
+    d = float(np.sqrt(np.float32(d2)))
+    assert abs(oracle.distance_coherence(a, b, 1.0) - 1.0 / (1.0 + d * d)) < 1e-12
+    assert abs(oracle.distance_coherence(a, b, 3.0) - 1.0 / (1.0 + 3.0 * d * d)) < 1e-12
+    # identical colours -> 1; G/B swap quirk: (R,G,B)=(255,0,0) vs (255,0,0) trivially 1
+    c = (255 << 24) | (200 << 16) | (120 << 8) | 40
+    assert oracle.hsv_coherence(c, c, 0.1) == 1.0
+    # upstream passes (R, B, G): colour (r=200,g=120,b=40) is converted as RGB2HSV(200, 40, 120)
+    h1, s1, _ = oracle.rgb2hsv(200, 40, 120)
+    c2 = (255 << 24) | (10 << 16) | (200 << 8) | 30
+    h2, s2, _ = oracle.rgb2hsv(10, 30, 200)
+    fh1, fh2, fs1, fs2 = np.float32(h1) / np.float32(180), np.float32(h2) / np.float32(180), np.float32(s1) / np.float32(255), np.float32(s2) / np.float32(255)
+    hd = abs(fh1 - fh2)
+    hd2 = abs(np.float32(1.0) + min(fh1, fh2) - max(fh1, fh2))
+    hdiff = np.float32(min(hd, hd2)) ** 2
+    sdiff = np.float32(fs1 - fs2) ** 2
+    want = 1.0 / (1.0 + 0.1 * float(np.float32(hdiff + sdiff)))
+    assert abs(oracle.hsv_coherence(c, c2, 0.1) - want) < 1e-7
+
+
+def test_passthrough_semantics():
+    pts = oracle.make_points([[0, 0, 0.0], [0, 0, 10.0], [0, 0, 10.0001], [0, 0, -1e-6], [np.nan, 0, 1], [0, np.inf, 1], [1, 2, 3]])
+    out = oracle.passthrough(pts, 2, 0.0, 10.0)
+    assert [tuple(p)[:3] for p in out] == [(0, 0, 0), (0, 0, 10), (1, 2, 3)]  # inclusive limits, order kept, non-finite dropped
+
+
+def test_approx_voxel_grid_pcl_small_case():
+    # two points in voxel (0,0,0), one in voxel (5,0,0); no hash collision -> two centroids, flush order = slot order
+    pts = oracle.make_points([[0.001, 0.002, 0.003], [0.003, 0.004, 0.005], [0.051, 0.001, 0.001]],
+                             rgba=[(10 << 16) | (20 << 8) | 30, (30 << 16) | (40 << 8) | 50, (1 << 16) | (2 << 8) | 3])
+    out = oracle.approx_voxel_grid_pcl(pts, 0.01)
+    assert len(out) == 2
+    # slot of voxel (0,0,0) is 0 -> emitted first
+    np.testing.assert_allclose([out[0]["x"], out[0]["y"], out[0]["z"]], [0.002, 0.003, 0.004], rtol=1e-6)
+    assert out[0]["rgba"] == (20 << 16) | (30 << 8) | 40
+    np.testing.assert_allclose(out[1]["x"], 0.051, rtol=1e-6)
+
+
+def test_approx_voxel_grid_pcl_collision_emits_duplicates():
+    # voxels (0,0,0) and (512,0,0)... hash = ix*7171 & 511: ix=512 -> 0: same slot, different voxel -> eviction
+    pts = oracle.make_points([[0.001, 0.001, 0.001], [5.121, 0.001, 0.001], [0.002, 0.002, 0.002]])
+    out = oracle.approx_voxel_grid_pcl(pts, 0.01)
+    assert len(out) == 3  # voxel (0,0,0) is emitted twice (partial centroids): "approximate"
+
+
+def test_voxel_grid_pcl_order_and_centroids():
+    rng = np.random.default_rng(2)
+    xyz = rng.uniform(-0.05, 0.05, (500, 3))
+    pts = oracle.make_points(xyz, rgba=rng.integers(0, 1 << 24, 500))
+    out = oracle.voxel_grid_pcl(pts, 0.02)
+    ex = oracle.voxel_grid_exact(pts, 0.02, -1, 0, 0)
+    assert len(out) == len(ex)
+    # same voxel set, same centroids (float vs double accumulation: 1e-6), different order
+    key = lambda a: np.lexsort((np.floor(a["z"] * 50), np.floor(a["y"] * 50), np.floor(a["x"] * 50)))
+    a, b = out[key(out)], ex[key(ex)]
+    for k in "xyz":
+        np.testing.assert_allclose(a[k], b[k], atol=1e-6)
+    # PCL order: ascending voxel index, x fastest then y then z
+    ix, iy, iz = (np.floor(out[k] * np.float32(50.0)).astype(int) for k in "xyz")
+    lin = (ix - ix.min()) + (iy - iy.min()) * 100 + (iz - iz.min()) * 10000
+    assert np.all(np.diff(lin) > 0)
+
+
+def test_voxel_grid_exact_first_appearance_order_and_passthrough():
+    pts = oracle.make_points([[0.051, 0, 1.0], [0.001, 0, 1.0], [0.052, 0, 1.0], [0.3, 0, 11.0], [np.nan, 0, 1.0]])
+    out = oracle.voxel_grid_exact(pts, 0.01, 2, 0.0, 10.0)
+    assert len(out) == 2
+    np.testing.assert_allclose(out["x"], [0.0515, 0.001], rtol=1e-6)
+
+
+def test_octree_approx_nearest_properties():
+    rng = np.random.default_rng(3)
+    pts = oracle.make_points(rng.uniform(0, 0.5, (2000, 3)))
+    # querying exactly at data points returns a point at distance 0 in the same leaf
+    idx, d2 = oracle.octree_approx_nearest(pts, 0.01, np.stack([pts["x"], pts["y"], pts["z"]], 1)[:200])
+    assert np.all(d2 == 0)
+    q = rng.uniform(0, 0.5, (500, 3)).astype(np.float32)
+    idx, d2 = oracle.octree_approx_nearest(pts, 0.01, q)
+    assert np.all(idx >= 0)
+    xyz = np.stack([pts["x"], pts["y"], pts["z"]], 1)
+    true_d2 = ((xyz[None, :, :] - q[:, None, :]) ** 2).sum(-1).min(1)
+    got = ((xyz[idx] - q) ** 2).sum(-1)
+    np.testing.assert_allclose(got, d2, rtol=1e-5)
+    assert np.all(got >= true_d2 - 1e-9)        # never better than the true nearest
+    assert np.mean(got <= true_d2 * 1.0001 + 1e-12) > 0.3  # and often equal to it
+
+
+def _tracker(kld=True, **kw):
+    t = oracle.Tracker(kld=kld)
+    oracle.configure_like_reference(t, **kw)
+    return t
+
+
+def test_normalize_weight():
+    t = _tracker()
+    p = oracle.make_particles(np.zeros((5, 6)), [-10.0, -4.0, 0.0, -7.0, -10.0])
+    t.set_particles(p)
+    t.normalize()
+    w = t.get_particles()["weight"].astype(np.float64)
+    assert abs(w.sum() - 1.0) < 1e-6
+    assert w[2] == 0.0                                   # zero raw weight stays zero
+    e = np.exp(1.0 - 15.0 * (np.array([-10.0, -4.0, -7.0, -10.0]) + 10.0) / 6.0)
+    np.testing.assert_allclose(w[[0, 1, 3, 4]], e / e.sum(), rtol=1e-6)
+    assert t.fit_ratio() == -10.0
+    # all equal -> uniform
+    t.set_particles(oracle.make_particles(np.zeros((4, 6)), [-3.0] * 4))
+    t.normalize()
+    np.testing.assert_allclose(t.get_particles()["weight"], 0.25)
+
+
+def test_update_weighted_mean_and_motion():
+    t = _tracker()
+    rng = np.random.default_rng(4)
+    s = rng.normal(0, 1, (50, 6)).astype(np.float32)
+    w = rng.random(50).astype(np.float32)
+    w /= w.sum()
+    t.set_particles(oracle.make_particles(s, w))
+    rep0 = np.zeros(1, dtype=oracle.PARTICLE)
+    rep0["x"], rep0["one"] = 0.5, 1.0
+    t.set_result(rep0[0])
+    t.update()
+    r = t.get_result()
+    want = (s.astype(np.float64) * w[:, None].astype(np.float64)).sum(0)
+    np.testing.assert_allclose([r[k] for k in ("x", "y", "z", "roll", "pitch", "yaw")], want, atol=2e-6)
+    assert abs(r["weight"] - 1 / 50) < 1e-9
+    assert abs(t.get_motion()["x"] - (r["x"] - 0.5)) < 1e-7
+
+
+def test_exact_grid_equals_brute_force():
+    scene, model, centre = synth.uniform_surface_scene(6000, 400, seed=5)
+    ws = []
+    nns = []
+    for mode in (oracle.NN_EXACT_BRUTE, oracle.NN_EXACT_GRID):
+        t = _tracker(kld=False, particle_num=24, nn_mode=mode)
+        rng = np.random.default_rng(6)
+        s = np.zeros((24, 6), dtype=np.float32)
+        s[:, :3] = centre + rng.normal(0, 0.02, (24, 3))
+        s[:, 3:] = rng.normal(0, 0.1, (24, 3))
+        t.set_reference(model); t.set_input(scene); t.set_particles(oracle.make_particles(s, np.full(24, 1 / 24)))
+        t.weight(keep_nn=True)
+        ws.append(t.raw_weights())
+        nns.append([t.nn(p, len(model)) for p in range(24)])
+    np.testing.assert_array_equal(ws[0], ws[1])
+    for (bi, bd), (gi, gd) in zip(*nns):
+        m = bd.astype(np.float64) < 0.1 * 0.1
+        np.testing.assert_array_equal(bi[m], gi[m])
+        np.testing.assert_array_equal(bd[m], gd[m])
+
+
+def test_alias_table_preserves_weights():
+    t = _tracker(kld=False, particle_num=200)
+    t.set_i(oracle.SAMPLER, oracle.SAMPLER_ALIAS_PCL)
+    rng = np.random.default_rng(8)
+    w = rng.random(200).astype(np.float32) ** 3
+    w /= w.sum()
+    s = np.zeros((200, 6), dtype=np.float32)
+    s[:, 0] = np.arange(200)
+    t.set_particles(oracle.make_particles(s, w))
+    t.set_vec6(oracle.STEP_COV, [0] * 6)
+    t.set_i(oracle.QUAT_SAMPLE, 0)
+    n_draw = 200
+    counts = np.zeros(200)
+    for rep in range(60):
+        t.set_particles(oracle.make_particles(s, w))
+        usel, normals, umot = synth.draws(1, n_draw, seed=100 + rep)
+        t.inject_draws(usel, normals, umot)
+        t.resample(0)
+        anc = t.ancestors()
+        a = anc[anc >= 0]
+        np.add.at(counts, a, 1)
+        got = t.get_particles()
+        np.testing.assert_array_equal(got["x"][1:], a.astype(np.float32))  # slot 0 = representative
+    freq = counts / counts.sum()
+    assert np.abs(freq - w).max() < 0.02
+
+
+def test_cdf_sampler_is_inverse_cdf():
+    t = _tracker(kld=False, particle_num=50)
+    t.set_i(oracle.SAMPLER, oracle.SAMPLER_CDF)
+    w = np.zeros(50, dtype=np.float32)
+    w[[3, 10, 40]] = [0.25, 0.5, 0.25]
+    s = np.zeros((50, 6), dtype=np.float32)
+    t.set_particles(oracle.make_particles(s, w))
+    usel = np.array([[0.0, 0.1, 0.2499, 0.2501, 0.5, 0.7499, 0.7501, 0.99] + [0.5] * 42], dtype=np.float32)
+    t.inject_draws(usel, np.zeros((1, 50, 6), np.float32), np.ones((1, 50), np.float32))
+    t.resample(0)
+    assert t.ancestors()[1:8].tolist() == [3, 3, 10, 10, 10, 40, 40]
+
+
+def test_kld_resample_respects_bound():
+    scene, model, centre = synth.uniform_surface_scene(3000, 200, seed=9)
+    for eps, bins in ((0.2, 0.1), (0.05, 0.05), (0.02, 0.02)):
+        t = _tracker(kld=True, particle_num=100, max_particle_num=5000)
+        t.set_d(oracle.EPSILON, eps)
+        t.set_vec6(oracle.BIN_SIZE, [bins] * 6)
+        s = np.zeros((100, 6), dtype=np.float32)
+        s[:, :3] = centre
+        t.set_particles(oracle.make_particles(s, np.full(100, 0.01)))
+        usel, normals, umot = synth.draws(1, 5000, seed=11)
+        t.inject_draws(usel, normals, umot)
+        t.resample(0)
+        p = t.get_particles()
+        n = len(p)
+        st = np.stack([p[k] for k in ("x", "y", "z", "roll", "pitch", "yaw")], 1)
+        k = len({tuple(r) for r in np.trunc(st / np.float32(bins)).astype(np.int64)})
+        assert 1 <= n <= 5000
+        if n < 5000:
+            assert k >= 2 and n >= oracle.kl_bound(k, 0.99, eps)
+            # one particle fewer would not have satisfied the stop rule
+            km = len({tuple(r) for r in np.trunc(st[:-1] / np.float32(bins)).astype(np.int64)})
+            assert km < 2 or (n - 1) < oracle.kl_bound(km, 0.99, eps)
+
+
+def test_compute_first_iteration_skips_resample_and_tracks():
+    scene, model, centre = synth.uniform_surface_scene(60000, 1500, seed=12)
+    t = _tracker(kld=True, particle_num=400, max_particle_num=500, nn_mode=oracle.NN_EXACT_GRID, use_hsv=False)
+    m = np.eye(4, dtype=np.float32)
+    m[:3, 3] = centre + np.array([0.03, -0.02, 0.01], dtype=np.float32)
+    t.set_trans(m[:3])
+    t.set_reference(model)
+    t.set_input(scene)
+    for f in range(4):
+        t.inject_draws(*synth.draws(2, 500, seed=13 + f))
+        t.compute()
+        if f == 0:
+            assert len(t.get_particles()) != 400  # iteration 1 resampled (KLD changes the count), iteration 0 did not
+    r = t.get_result()
+    err = np.linalg.norm([r["x"] - centre[0], r["y"] - centre[1], r["z"] - centre[2]])
+    assert err < 0.01, err  # starts 3.7 cm off, converges to a few mm
+    assert abs(t.get_particles()["weight"].astype(np.float64).sum() - 1.0) < 1e-4
+
+
+def test_empty_input_is_noop():
+    t = _tracker(kld=True, particle_num=10, max_particle_num=20)
+    t.set_reference(oracle.make_points([[0, 0, 0]]))
+    t.set_input(oracle.make_points(np.zeros((0, 3))))
+    t.compute()
+    assert len(t.get_particles()) == 0
+
+
+def test_particle_sample_modes():
+    z = np.array([0.5, -1.0, 2.0, 0.3, -0.2, 0.1], dtype=np.float32)
+    cov = [1e-4] * 3 + [4e-4] * 3
+    p = oracle.particle_sample([1, 2, 3, 0.1, 0.2, 0.3], [0] * 6, cov, z, quat_mode=0)
+    np.testing.assert_allclose([p["x"], p["y"], p["z"]], [1.005, 1.99, 3.02], atol=1e-6)
+    np.testing.assert_allclose([p["roll"], p["pitch"], p["yaw"]], [0.106, 0.196, 0.302], atol=1e-6)
+    q = oracle.particle_sample([1, 2, 3, 0.1, 0.2, 0.3], [0] * 6, cov, z, quat_mode=1)
+    np.testing.assert_allclose([q["x"], q["y"], q["z"]], [1.005, 1.99, 3.02], atol=1e-6)
+    # small-angle: quaternion noise (a,b,c)*sqrt(0.2862*cov) rotates by ~2*(a,b,c) about x,y,z
+    R0 = _rot_zyx(0.1, 0.2, 0.3)
+    ang = 2 * np.sqrt(0.2862 * 4e-4) * z[3:]
+    Rs = _rot_zyx(ang[0], ang[1], ang[2])
+    np.testing.assert_allclose(_rot_zyx(q["roll"], q["pitch"], q["yaw"]), Rs @ R0, atol=2e-4)
+    # zero noise keeps the pose
+    q0 = oracle.particle_sample([1, 2, 3, 0.1, 0.2, 0.3], [0] * 6, [0] * 6, z, quat_mode=1)
+    np.testing.assert_allclose([q0["roll"], q0["pitch"], q0["yaw"]], [0.1, 0.2, 0.3], atol=1e-6)
