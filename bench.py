@@ -1,0 +1,466 @@
+#!/usr/bin/env python
+"""bench.py -- the tracker's headline benchmark (BASELINE.json: "tracker frames/s and particle x
+model-point likelihood evals/s, 217k-pt scene").
+
+A step is one tracked frame of ref: src/auto_tracking.cpp:cloud_cb (:637, :683, :688-697):
+    PassThrough(z in [0,10]) + voxel-grid(1 cm) of the 512x424 scene  ->  setInputCloud  ->  compute()
+with compute() = 2 x { resample, crop + index rebuild, weight, normalise, update }.
+
+Workloads (config.workload):
+  c2   BASELINE.json configs[1]: 217 088-pt Kinect2-shaped synthetic scene, ~2k-pt model, 1000
+       particles PER GPU (fixed-N tracker), Distance+HSV coherence.  With N GPUs it is ONE tracker
+       of 1000*N particles sharded by particle (weak scaling): rank 0 downsamples and broadcasts the
+       scene over NCCL/NVLink, every rank weights its own particles, the crop box is all-reduced and
+       the raw weights all-gathered, resample/normalise/update run replicated.
+  c4   BASELINE.json configs[3]: 100 000 particles in total, sharded over the N GPUs (strong scaling).
+
+`value`   = likelihood evals/s, whole job, inputs resident in HBM (raw frames pre-uploaded).
+`e2e`     = the same through the public API with HOST buffers: every step uploads the raw frame from
+            pinned host memory (3.47 MB) and reads the result pose back (32 B).
+--impl reference times the CPU restatement of the PCL-1.8.0 path (oracle/, "port": PCL itself is not
+buildable here) on the box's host cores.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "likelihood evals/s (particle x model-point), 217k-pt scene tracker frame"
+UNIT = "evals/s"
+N_FRAMES = 6          # pre-rendered frames, played ping-pong so that motion stays continuous
+LEAF = 0.01
+PARTICLES_PER_GPU = 1000
+C4_PARTICLES = 100_000
+ITERATIONS = 2
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+# ------------------------------------------------------------------ workload
+def make_frames(n_frames):
+    from pcl_tracking_b200 import synth
+    objs = synth.default_objects(1)
+    frames = []
+    oid0 = None
+    for f in range(n_frames):
+        pts, oid = synth.render(f, objs)
+        if f == 0:
+            oid0 = oid
+        frames.append(pts)
+    return frames, oid0
+
+
+def frame_order(k, n_frames):
+    """ping-pong 0,1,..,n-1,n-2,..,1,0,1,... (index of the frame shown at step k)"""
+    period = 2 * (n_frames - 1)
+    r = k % period
+    return r if r < n_frames else period - r
+
+
+def raw_model(frames, oid0):
+    from pcl_tracking_b200 import synth
+    return synth.model_points(frames[0], oid0, 0)
+
+
+# ------------------------------------------------------------------ clocks
+class ClockSampler:
+    """Samples SM clock + throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._nv = None
+
+    def sample(self):
+        if not self._nv:
+            return
+        nv = self._nv
+        try:
+            self.samples.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+            try:
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+            except Exception:
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+            names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+                     0x80: "hw_power_brake_slowdown"}
+            for bit, name in names.items():
+                if r & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
+    def _run(self):
+        while not self._stop.is_set():
+            self.sample()
+            self._stop.wait(0.02)
+
+    def start(self):
+        self._stop.clear()
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._thread.start()
+
+    def stop(self):
+        self.sample()
+        self._stop.set()
+        if self._thread:
+            self._thread.join()
+
+    def summary(self):
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------ reference arm / cpu baseline (oracle)
+def oracle_tracker(model, centroid, n_particles, threads):
+    import oracle
+    t = oracle.Tracker(kld=False)
+    oracle.configure_like_reference(t, particle_num=n_particles, max_particle_num=n_particles, use_hsv=True,
+                                    nn_mode=oracle.NN_PCL_APPROX, iteration_num=ITERATIONS, threads=threads)
+    t.set_i(oracle.SAMPLER, oracle.SAMPLER_ALIAS_PCL)
+    m = np.eye(4, dtype=np.float32)
+    m[:3, 3] = centroid
+    t.set_trans(m[:3])
+    t.set_reference(model)
+    return t
+
+
+def cpu_prepare_model(raw):
+    """ref: src/auto_tracking.cpp:656-674 on the CPU (oracle restatement)."""
+    import oracle
+    r = oracle.remove_zero_points(raw)
+    c = oracle.centroid(r)
+    r["x"] -= c[0]
+    r["y"] -= c[1]
+    r["z"] -= c[2]
+    return oracle.voxel_grid_pcl(r, LEAF), c
+
+
+def cpu_frame(t, frame):
+    """One cloud_cb on the CPU: PassThrough + ApproximateVoxelGrid (512-slot, as PCL) + compute()."""
+    import oracle
+    ds = oracle.approx_voxel_grid_pcl(oracle.passthrough(frame, 2, 0.0, 10.0), LEAF)
+    t.set_input(ds)
+    t.compute()
+
+
+def run_cpu(frames, oid0, n_particles, steps, warmup, budget_s):
+    """Times `steps` CPU frames after `warmup`.  The particle count is bounded so that the run fits
+    `budget_s`: throughput in evals/s does not depend on it (weight() is linear in particles)."""
+    import oracle
+    threads = oracle.lib().orc_max_threads()
+    model, centroid = cpu_prepare_model(raw_model(frames, oid0))
+    M = len(model)
+    # calibrate on a small particle set
+    cal = oracle_tracker(model, centroid, 64, threads)
+    cpu_frame(cal, frames[0])
+    t0 = time.perf_counter()
+    cpu_frame(cal, frames[1])
+    dt = time.perf_counter() - t0
+    ds_t0 = time.perf_counter()
+    oracle.approx_voxel_grid_pcl(oracle.passthrough(frames[0], 2, 0.0, 10.0), LEAF)
+    ds_dt = time.perf_counter() - ds_t0
+    per_particle = max((dt - ds_dt) / 64.0, 1e-6)
+    per_step_budget = budget_s / max(steps + warmup, 1)
+    n_fit = int(max(per_step_budget - ds_dt, 0.0) / per_particle)
+    n_used = int(min(n_particles, max(n_fit, 32)))
+    t = oracle_tracker(model, centroid, n_used, threads)
+    for k in range(warmup):
+        cpu_frame(t, frames[frame_order(k, len(frames))])
+    t0 = time.perf_counter()
+    for k in range(steps):
+        cpu_frame(t, frames[frame_order(warmup + k, len(frames))])
+    total = time.perf_counter() - t0
+    evals = float(n_used) * M * ITERATIONS * steps
+    stages = t.stage_seconds()
+    return {
+        "evals_per_s": evals / total, "frames_per_s": steps / total, "ms_per_step": 1e3 * total / steps, "cores": threads,
+        "particles_used": n_used, "model_points": M, "steps": steps,
+        "sample": "%d frames of the c2 workload with %d of %d particles (weight() is linear in particles), %d-pt model, "
+                  "PassThrough + 512-slot ApproximateVoxelGrid + octree approxNearestSearch, %d OpenMP threads"
+                  % (steps, n_used, n_particles, M, threads),
+        "stage_s": {k: round(v, 4) for k, v in stages.items()},
+    }
+
+
+def reference_arm(args):
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return 0
+    frames, oid0 = make_frames(N_FRAMES)
+    n_particles = PARTICLES_PER_GPU * args.gpus if args.workload == "c2" else C4_PARTICLES
+    r = run_cpu(frames, oid0, n_particles, args.steps, args.warmup, budget_s=150.0)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["evals_per_s"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak" if args.workload == "c2" else "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, r["model_points"], n_particles),
+        "frames_per_s": r["frames_per_s"],
+        "cpu_baseline": {"value": r["evals_per_s"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"],
+                         "stage_s": r["stage_s"]},
+        "e2e": {"value": r["evals_per_s"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config(args, M, n_particles):
+    return {
+        "workload": ("c2: BASELINE.json configs[1], 512x424 (217088-pt) Kinect2-shaped synthetic scene, %d-pt model, %d particles"
+                     " per GPU (one tracker sharded by particle), Distance+HSV coherence, 2 iterations/frame" % (M, PARTICLES_PER_GPU))
+        if args.workload == "c2" else
+        ("c4: BASELINE.json configs[3], 100000 particles sharded over the GPUs, 217088-pt scene, %d-pt model, Distance+HSV" % M),
+        "scene_points": 217088, "model_points": M, "particles_total": n_particles, "iterations_per_frame": ITERATIONS,
+        "leaf_m": LEAF, "max_distance_m": 0.1, "l2": "flushed between timed steps (256 MiB write)", "parallelism": "particle-shard x%d" % args.gpus,
+    }
+
+
+# ------------------------------------------------------------------ our arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c4"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-flush", action="store_true", help="debug only: do not flush L2 between steps")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    from pcl_tracking_b200 import build as pft_build
+    rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            print("bench.py: --gpus %d needs torchrun (WORLD_SIZE=%d)" % (args.gpus, world), file=sys.stderr)
+            return 2
+    if not torch.cuda.is_available():
+        print("bench.py: no CUDA device; the tracker has no CPU fallback (use --impl reference for the CPU arm)", file=sys.stderr)
+        return 3
+    if rank == 0:
+        pft_build.build()
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.barrier()
+    from pcl_tracking_b200 import pcl
+
+    ctx = pcl.Context(local_rank)
+    if world > 1:
+        uid = [pcl.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx.commInit(world, rank, uid[0])
+    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
+
+    frames, oid0 = make_frames(N_FRAMES)
+    n_pts = len(frames[0])
+    n_particles = PARTICLES_PER_GPU * world if args.workload == "c2" else C4_PARTICLES
+
+    # model preparation on the GPU (ref :656-674) -- init-time, untimed
+    raw_model_cloud = pcl.PointCloud(raw_model(frames, oid0), ctx=ctx)
+    model_cloud, centroid = pcl.prepare_model(raw_model_cloud, LEAF, ctx=ctx)
+    M = model_cloud.size()
+
+    tracker = pcl.ParticleFilterOMPTracker(16, ctx=ctx)
+    pcl.configure_like_reference(tracker, particle_num=n_particles, use_hsv=True, iteration_num=ITERATIONS)
+    m = np.eye(4, dtype=np.float32)
+    m[:3, 3] = centroid
+    tracker.setTrans(m)
+    tracker.seed(1234)
+    if world > 1:
+        tracker.commInit(world, rank, uid[0])
+    tracker.setReferenceCloud(model_cloud)
+
+    # resident inputs: raw frames in HBM (rank 0 owns the sensor; the other ranks receive the downsampled scene)
+    dev_frames = [pcl.PointCloud(f, ctx=ctx) for f in frames] if rank == 0 else None
+    # host inputs for e2e: pinned frame buffers
+    pinned = []
+    if rank == 0:
+        for f in frames:
+            p = C.c_void_p()
+            pcl.check(pcl.capi.load().pft_host_alloc(C.byref(p), f.nbytes))
+            C.memmove(p, f.ctypes.data, f.nbytes)
+            pinned.append(p)
+    upload_cloud = pcl.PointCloud(ctx=ctx)
+    ds = pcl.PointCloud(ctx=ctx)
+    vg = pcl.ApproximateVoxelGrid(ctx=ctx)
+    vg.setLeafSize(LEAF, LEAF, LEAF)
+    vg.setPassThrough("z", 0.0, 10.0)
+
+    def step_resident(k):
+        if rank == 0:
+            vg.setInputCloud(dev_frames[frame_order(k, N_FRAMES)])
+            vg.filter(ds)
+        if world > 1:
+            ds.broadcast(n_pts, 0)
+        tracker.setInputCloud(ds)
+        tracker.compute()
+
+    def step_e2e(k):
+        if rank == 0:
+            upload_cloud.upload_raw(pinned[frame_order(k, N_FRAMES)].value, n_pts)
+            vg.setInputCloud(upload_cloud)
+            vg.filter(ds)
+        if world > 1:
+            ds.broadcast(n_pts, 0)
+        tracker.setInputCloud(ds)
+        tracker.compute()
+        return tracker.getResult()  # D2H of the pose: synchronises
+
+    flush_buf = None if args.no_flush else torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+
+    def flush_l2():
+        if flush_buf is not None:
+            with torch.cuda.stream(stream):
+                flush_buf.fill_(1)
+
+    def sync_all():
+        ctx.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(step_fn, steps, first_k, sampler=None):
+        """EXACTLY `steps` steps, each bracketed by CUDA events on the library's stream; L2 flushed between
+        steps outside the event pairs.  Returns (sum of step times in ms over steps, max over ranks)."""
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        sync_all()
+        if sampler:
+            sampler.start()
+        wall0 = time.perf_counter()
+        for i in range(steps):
+            flush_l2()
+            ev[i][0].record(stream)
+            step_fn(first_k + i)
+            ev[i][1].record(stream)
+        sync_all()
+        wall = time.perf_counter() - wall0
+        if sampler:
+            sampler.stop()
+        total_ms = float(sum(a.elapsed_time(b) for a, b in ev))
+        if world > 1:
+            tt = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            total_ms = float(tt.item())
+        return total_ms, wall
+
+    if rank == 0:
+        print("bench: model %d pts, centroid %s, particles %d, world %d" % (M, np.round(centroid, 4).tolist(), n_particles, world), file=sys.stderr)
+    # ---- warm-up (also builds the CUDA graph), then the timed region
+    W = max(args.warmup, 3)
+    for k in range(W):
+        step_resident(k)
+    sync_all()
+    sampler = ClockSampler(local_rank)
+    launches0 = pcl.kernel_launch_count()
+    total_ms, wall_s = timed(step_resident, args.steps, W, sampler)
+    launches = pcl.kernel_launch_count() - launches0
+    if rank == 0:
+        print("bench: timed %d steps: %.3f ms/step, ds %d pts, launches %d" % (args.steps, total_ms / args.steps, ds.size(), launches), file=sys.stderr)
+    ms_per_step = total_ms / args.steps
+    evals_per_step = float(n_particles) * M * ITERATIONS
+    value = evals_per_step / (ms_per_step * 1e-3)
+    graph_replays = tracker.graphReplays()
+
+    # ---- e2e: host buffers in, pose out, every step
+    for k in range(3):
+        step_e2e(k)
+    e2e_ms, _ = timed(step_e2e, args.steps, W + args.steps)
+    e2e_ms_per_step = e2e_ms / args.steps
+    e2e_value = evals_per_step / (e2e_ms_per_step * 1e-3)
+
+    # ---- roofline of the dominant kernel (weight_kernel): CUDA events around every launch of it on the
+    # library's stream, over `steps` more frames driven through the same code path without the graph
+    tracker.enableTiming(True)
+    w_ms, n_w = 0.0, 0
+    c_ms = 0.0
+    rsteps = min(args.steps, 100)
+    for k in range(rsteps):
+        flush_l2()
+        step_resident(W + k)
+        a, b = tracker.timing()
+        w_ms += a
+        c_ms += b
+        n_w += ITERATIONS
+    tracker.enableTiming(False)
+    info = tracker.indexInfo()
+    n_local = (n_particles - rank + world - 1) // world
+    bytes_per_launch = 32.0 * n_local * M + 36.0 * n_local + 16.0 * info["n_cropped"]
+    w_ms_per_launch = w_ms / max(n_w, 1)
+    achieved = bytes_per_launch / (w_ms_per_launch * 1e-3) / 1e9
+    peak, peak_src = 6650.0, "fallback"
+    try:
+        mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        peak, peak_src = float(mp["hbm_gbs"]), "measured"
+    except Exception:
+        pass
+    result = tracker.getResult()
+
+    line = None
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak" if args.workload == "c2" else "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(args, M, n_particles),
+            "frames_per_s": 1e3 / ms_per_step,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(frames[0].nbytes), "d2h_bytes_per_step": 32 + 64,
+                    "ms_per_step": e2e_ms_per_step, "frames_per_s": 1e3 / e2e_ms_per_step},
+            "gpu_launches": int(launches),
+            "graph_replays": int(graph_replays),
+            "clocks": sampler.summary(),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "kernel": "weight_kernel<HSV>", "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": bytes_per_launch, "ms_per_launch": w_ms_per_launch,
+                         "evals_per_s_in_kernel": n_local * M / (w_ms_per_launch * 1e-3),
+                         "share_of_compute": w_ms / c_ms if c_ms > 0 else None,
+                         "how": "CUDA events around each weight_kernel launch on the library stream, %d frames, stream-launched (no graph)" % rsteps},
+            "scene_index": info,
+            "result_pose": {k: float(result[k]) for k in ("x", "y", "z", "roll", "pitch", "yaw")},
+            "wall_s_timed_region": wall_s,
+        }
+    if world > 1:
+        dist.barrier()
+    # ---- CPU baseline beside it (rank 0, N=1 only): bounded sample on the box's host cores
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            r = run_cpu(frames, oid0, n_particles, steps=8, warmup=1, budget_s=20.0)
+            line["cpu_baseline"] = {"value": r["evals_per_s"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"],
+                                    "frames_per_s": r["frames_per_s"], "stage_s": r["stage_s"]}
+        except Exception as e:  # the GPU number stands on its own
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -214,6 +214,13 @@ PFT_API int pft_tracker_set_shard(pft_tracker* t, int nranks, int rank);
  * (i % nranks == rank); the crop AABB is all-reduced and the raw weights all-gathered over NCCL/NVLink;
  * resample/normalise/update run replicated from identical draws (same seed or same injected arrays). */
 PFT_API int pft_comm_get_unique_id(void* id128);
+/* one NCCL communicator per context, shared by its clouds and trackers */
+PFT_API int pft_context_comm_init(pft_context* ctx, int nranks, int rank, const void* id128);
+PFT_API int pft_context_comm_destroy(pft_context* ctx);
+/* NVLink broadcast of a (downsampled) scene cloud from `root`: header + `capacity` points; the point
+ * count stays on the device.  Every rank passes the same capacity and root. */
+PFT_API int pft_cloud_broadcast(pft_cloud* cloud, size_t capacity, int root);
+/* attach the tracker to the context communicator (creates it on first use); detach */
 PFT_API int pft_tracker_comm_init(pft_tracker* t, int nranks, int rank, const void* id128);
 PFT_API int pft_tracker_comm_destroy(pft_tracker* t);
 

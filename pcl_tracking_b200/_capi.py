@@ -101,6 +101,9 @@ SIGNATURES = {
     "pft_tracker_set_raw_slice": (_i, [_vp, _i, _vp, _sz]),
     "pft_tracker_set_shard": (_i, [_vp, _i, _i]),
     "pft_comm_get_unique_id": (_i, [_vp]),
+    "pft_context_comm_init": (_i, [_vp, _i, _i, _vp]),
+    "pft_context_comm_destroy": (_i, [_vp]),
+    "pft_cloud_broadcast": (_i, [_vp, _sz, _i]),
     "pft_tracker_comm_init": (_i, [_vp, _i, _i, _vp]),
     "pft_tracker_comm_destroy": (_i, [_vp]),
 }

@@ -29,6 +29,9 @@ struct pft_context {
   pft::DevBuf k1_keys, k1_first, k1_vid, k1_slot_of, k1_acc_xyz, k1_acc_rgbc, k1_blk, staging, tmp_cloud_pts, tmp_hdr, tmp_f;
   void* pinned = nullptr;  // small pinned buffer for scalar read-backs
   size_t pinned_bytes = 0;
+  // NCCL communicator shared by the clouds and trackers of this context (one process per GPU)
+  void* comm = nullptr;
+  int nranks = 1, rank = 0;
 };
 
 struct pft_cloud {

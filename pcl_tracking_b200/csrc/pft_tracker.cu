@@ -38,6 +38,7 @@ struct NcclApi {
   int (*CommInitRank)(void**, int, UidByValue, int) = nullptr;
   int (*CommDestroy)(void*) = nullptr;
   int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+  int (*Broadcast)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
   int (*GroupStart)() = nullptr;
   int (*GroupEnd)() = nullptr;
@@ -45,6 +46,7 @@ struct NcclApi {
 };
 NcclApi g_nccl;
 constexpr int kNcclFloat = 7;  // ncclFloat32
+constexpr int kNcclChar = 0;   // ncclInt8
 constexpr int kNcclMax = 2, kNcclMin = 3;
 
 int load_nccl() {
@@ -65,10 +67,11 @@ int load_nccl() {
   g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))sym("ncclCommDestroy");
   g_nccl.AllGather = (decltype(g_nccl.AllGather))sym("ncclAllGather");
   g_nccl.AllReduce = (decltype(g_nccl.AllReduce))sym("ncclAllReduce");
+  g_nccl.Broadcast = (decltype(g_nccl.Broadcast))sym("ncclBroadcast");
   g_nccl.GroupStart = (decltype(g_nccl.GroupStart))sym("ncclGroupStart");
   g_nccl.GroupEnd = (decltype(g_nccl.GroupEnd))sym("ncclGroupEnd");
   g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))sym("ncclGetErrorString");
-  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllGather || !g_nccl.AllReduce || !g_nccl.GroupStart ||
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllGather || !g_nccl.AllReduce || !g_nccl.Broadcast || !g_nccl.GroupStart ||
       !g_nccl.GroupEnd) {
     set_last_error("NCCL library lacks a required symbol");
     return PFT_ERR_COMM;
@@ -122,7 +125,7 @@ struct pft_tracker {
   std::vector<cudaEvent_t> ev_w;  // pairs around weight_kernel launches of the last compute
   cudaEvent_t ev_c0 = nullptr, ev_c1 = nullptr;
   int n_ev_used = 0;
-  // comm
+  // sharding (comm = the context's communicator when this tracker exchanges over NCCL)
   void* comm = nullptr;
   int nranks = 1, rank = 0;
   // graph
@@ -135,7 +138,8 @@ struct pft_tracker {
   int graph_nodes = 0;
   // device buffers
   DevBuf st, parts[2], mats, slot_aabb, model, model_perm, model_tmp, sort_keys, sort_idx, bbox, raw, partial, cdf, cdf_total, ancestors, bin_keys, tbl_rep,
-      tbl_min, slot_of, klb, d_usel, d_normals, d_umot, idx_hdr, words, rank_buf, ipts, iorig, inext, icount, dbg_idx, dbg_d2, d_trans;
+      tbl_min, slot_of, klb, d_usel, d_normals, d_umot, idx_hdr, words, rank_buf, ipts, ihsv, inext, icount, dbg_idx, dbg_d2, d_trans, row_table;
+  int weight_smem = 0;  // dynamic shared memory of the weight kernel (bytes)
   int tbl_size = 0;
   int n_slots = 0;
   int chunks = 1, chunk_len = 0;
@@ -150,8 +154,8 @@ void invalidate_graph(pft_tracker* t) { t->config_version++; }
 void release_all(pft_tracker* t) {
   DevBuf* bufs[] = {&t->st, &t->parts[0], &t->parts[1], &t->mats, &t->slot_aabb, &t->model, &t->model_perm, &t->model_tmp, &t->sort_keys, &t->sort_idx,
                     &t->bbox, &t->raw, &t->partial, &t->cdf, &t->cdf_total, &t->ancestors, &t->bin_keys, &t->tbl_rep, &t->tbl_min, &t->slot_of, &t->klb,
-                    &t->d_usel, &t->d_normals, &t->d_umot, &t->idx_hdr, &t->words, &t->rank_buf, &t->ipts, &t->iorig, &t->inext, &t->icount, &t->dbg_idx,
-                    &t->dbg_d2, &t->d_trans};
+                    &t->d_usel, &t->d_normals, &t->d_umot, &t->idx_hdr, &t->words, &t->rank_buf, &t->ipts, &t->ihsv, &t->inext, &t->icount, &t->dbg_idx,
+                    &t->dbg_d2, &t->d_trans, &t->row_table};
   for (auto* b : bufs) b->release();
 }
 
@@ -195,6 +199,37 @@ double kl_bound(int k, double delta, double eps) {
   return ((k - 1.0) / (2.0 * eps)) * chi * chi * chi;
 }
 
+// Row table of the nearest-neighbour search: the (dy,dz) offsets within kRT cells sorted by the lower bound
+// gap(dy)^2 + gap(dz)^2 of their distance (gap(d) = max(|d|-1, 0)), nearer rows first.
+int upload_row_table(pft_tracker* t) {
+  std::vector<RowEntry> tab;
+  tab.reserve(kRows);
+  for (int dz = -kRT; dz <= kRT; ++dz)
+    for (int dy = -kRT; dy <= kRT; ++dy) {
+      const int gy = std::max(std::abs(dy) - 1, 0), gz = std::max(std::abs(dz) - 1, 0);
+      tab.push_back(RowEntry{(signed char)dy, (signed char)dz, (unsigned short)(gy * gy + gz * gz)});
+    }
+  std::stable_sort(tab.begin(), tab.end(), [](const RowEntry& a, const RowEntry& b) {
+    if (a.lb2 != b.lb2) return a.lb2 < b.lb2;
+    return (a.dy * a.dy + a.dz * a.dz) < (b.dy * b.dy + b.dz * b.dz);  // among equal bounds: the row through the query cell first
+  });
+  int rc = t->row_table.reserve(tab.size() * sizeof(RowEntry));
+  if (rc) return rc;
+  PFT_CUDA_TRY(cudaMemcpy(t->row_table.p, tab.data(), tab.size() * sizeof(RowEntry), cudaMemcpyHostToDevice));
+  // the weight kernel stages the scene index in shared memory: ask for everything the SM has
+  int dev = t->ctx->device, max_optin = 0;
+  PFT_CUDA_TRY(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  cudaFuncAttributes fa;
+  PFT_CUDA_TRY(cudaFuncGetAttributes(&fa, weight_kernel<true>));
+  int dyn = max_optin - (int)fa.sharedSizeBytes - 1024;
+  if (dyn < 0) dyn = 0;
+  dyn &= ~15;
+  PFT_CUDA_TRY(cudaFuncSetAttribute(weight_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+  PFT_CUDA_TRY(cudaFuncSetAttribute(weight_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+  t->weight_smem = dyn;
+  return PFT_OK;
+}
+
 int wanted_cap(const pft_tracker* t) { return t->kld ? std::max(t->max_particle_num, t->particle_num) : t->particle_num; }
 
 // (Re)allocate every particle-count dependent buffer.  Existing particles survive a capacity change.
@@ -213,8 +248,9 @@ int ensure_particle_buffers(pft_tracker* t) {
     if ((rc = t->cdf_total.reserve(sizeof(unsigned long long)))) return rc;
     if ((rc = t->idx_hdr.reserve(sizeof(IndexHeader)))) return rc;
     if ((rc = t->d_trans.reserve(12 * sizeof(float)))) return rc;
-    if ((rc = t->words.reserve((size_t)t->max_words * sizeof(unsigned int)))) return rc;
-    if ((rc = t->rank_buf.reserve((size_t)t->max_words * sizeof(int)))) return rc;
+    if ((rc = t->words.reserve(((size_t)t->max_words + 16) * sizeof(unsigned int)))) return rc;
+    if ((rc = t->rank_buf.reserve(((size_t)t->max_words + 16) * sizeof(int)))) return rc;
+    if ((rc = upload_row_table(t))) return rc;
   }
   if (cap == t->n_cap) return PFT_OK;
   invalidate_graph(t);
@@ -310,20 +346,23 @@ int ensure_index_buffers(pft_tracker* t) {
   invalidate_graph(t);
   PFT_CUDA_TRY(cudaStreamSynchronize(t->ctx->stream));
   int rc;
-  if ((rc = t->ipts.reserve(cap * sizeof(float4)))) return rc;
-  if ((rc = t->iorig.reserve(cap * sizeof(int)))) return rc;
-  if ((rc = t->inext.reserve(cap * sizeof(int)))) return rc;
+  if ((rc = t->ipts.reserve((cap + 4) * sizeof(float4)))) return rc;
+  if ((rc = t->ihsv.reserve((cap + 4) * sizeof(unsigned int)))) return rc;
+  if ((rc = t->inext.reserve((cap + 4) * sizeof(int)))) return rc;
   if ((rc = t->icount.reserve(cap * sizeof(int)))) return rc;
   t->scene_cap = cap;
   return PFT_OK;
 }
 
+// One work item of the weight kernel = one warp x (particle, chunk of the model).  Enough items for ~6 per
+// warp of the persistent grid keeps the tail short; a chunk is a multiple of 32 points (one per lane).
 void choose_chunks(pft_tracker* t) {
   const int n_expected = std::max(1, (t->particle_num > 0 ? t->particle_num : t->n_cap) / t->nranks);
-  const int target_items = t->ctx->sm_count * 8;
-  const int max_chunks = std::max(1, (t->M + 255) / 256);
+  const int total_warps = t->ctx->sm_count * 32;
+  const int target_items = total_warps * 6;
+  const int max_chunks = std::max(1, (t->M + 63) / 64);
   int chunks = (target_items + n_expected - 1) / n_expected;
-  chunks = std::min(std::max(chunks, 1), std::min(max_chunks, 64));
+  chunks = std::min(std::max(chunks, 1), std::min(max_chunks, 256));
   int len = (t->M + chunks - 1) / chunks;
   len = ((len + 31) / 32) * 32;
   if (len < 32) len = 32;
@@ -456,26 +495,26 @@ int weight_phase_eval(pft_tracker* t) {
   index_rank_kernel<<<1, 1024, 0, s>>>(hdr, t->words.as<unsigned int>(), t->rank_buf.as<int>());
   PFT_LAUNCH_CHECK();
   index_scatter_kernel<<<gscene, 256, 0, s>>>(in->d_pts(), in->d_hdr(), hdr, t->words.as<unsigned int>(), t->rank_buf.as<int>(), t->icount.as<int>(),
-                                              t->ipts.as<float4>(), t->iorig.as<int>(), t->inext.as<int>());
+                                              t->ipts.as<float4>(), t->ihsv.as<unsigned int>(), t->inext.as<int>());
   PFT_LAUNCH_CHECK();
   WeightArgs a;
   a.st = st; a.hdr = hdr;
-  a.g.words = t->words.as<unsigned int>(); a.g.rank = t->rank_buf.as<int>(); a.g.pts = t->ipts.as<float4>(); a.g.orig = t->iorig.as<int>();
-  a.g.next = t->inext.as<int>();
+  a.words = t->words.as<unsigned int>(); a.rank = t->rank_buf.as<int>(); a.pts = t->ipts.as<float4>(); a.next = t->inext.as<int>();
+  a.hsv = t->ihsv.as<unsigned int>(); a.table = t->row_table.as<RowEntry>(); a.smem_bytes = t->weight_smem;
   a.model = t->model.as<float4>(); a.model_perm = t->model_perm.as<int>(); a.M = t->M;
   a.mats = t->mats.as<float>();
   a.partial = t->partial.as<double>(); a.chunks = t->chunks; a.chunk_len = t->chunk_len; a.n_max = t->n_cap;
-  a.nranks = t->nranks; a.rank = t->rank;
+  a.nranks = t->nranks; a.rank_id = t->rank;
   a.co = make_coherence(t);
   a.dbg_k = t->debug_nn; a.dbg_idx = t->dbg_idx.as<int>(); a.dbg_d2 = t->dbg_d2.as<float>();
   const int local_cap = t->slice_cap();
-  const int wgrid = blocks_for((long long)local_cap * t->chunks, 1, sm * 8);
+  const int wgrid = sm;  // persistent: one CTA per SM
   if (t->timing) {
     while ((int)t->ev_w.size() < 2 * (t->n_ev_used + 1)) { cudaEvent_t e; PFT_CUDA_TRY(cudaEventCreate(&e)); t->ev_w.push_back(e); }
     PFT_CUDA_TRY(cudaEventRecord(t->ev_w[2 * t->n_ev_used], s));
   }
-  if (t->use_hsv) weight_kernel<true><<<wgrid, 256, 0, s>>>(a);
-  else weight_kernel<false><<<wgrid, 256, 0, s>>>(a);
+  if (t->use_hsv) weight_kernel<true><<<wgrid, 1024, t->weight_smem, s>>>(a);
+  else weight_kernel<false><<<wgrid, 1024, t->weight_smem, s>>>(a);
   PFT_LAUNCH_CHECK();
   if (t->timing) { PFT_CUDA_TRY(cudaEventRecord(t->ev_w[2 * t->n_ev_used + 1], s)); t->n_ev_used++; }
   raw_weights_kernel<<<blocks_for(local_cap, 256, sm * 4), 256, 0, s>>>(st, t->partial.as<double>(), t->chunks, t->n_cap, t->raw.as<float>(), local_cap,
@@ -582,7 +621,6 @@ void pft_tracker_destroy(pft_tracker* t) {
   for (auto e : t->ev_w) cudaEventDestroy(e);
   if (t->ev_c0) cudaEventDestroy(t->ev_c0);
   if (t->ev_c1) cudaEventDestroy(t->ev_c1);
-  if (t->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(t->comm);
   release_all(t);
   delete t;
 }
@@ -1146,31 +1184,78 @@ int pft_comm_get_unique_id(void* id128) {
   return PFT_OK;
 }
 
-int pft_tracker_comm_init(pft_tracker* t, int nranks, int rank, const void* id128) {
-  if (!t || !id128) { set_last_error("null argument"); return PFT_ERR_INVALID; }
+int pft_context_comm_init(pft_context* ctx, int nranks, int rank, const void* id128) {
+  if (!ctx || !id128) { set_last_error("null argument"); return PFT_ERR_INVALID; }
   if (nranks < 1 || rank < 0 || rank >= nranks) { set_last_error("bad rank %d of %d", rank, nranks); return PFT_ERR_INVALID; }
-  if (t->n_cap > 0) { set_last_error("pft_tracker_comm_init must precede the first compute()/set_particles()"); return PFT_ERR_STATE; }
-  PFT_CUDA_TRY(cudaSetDevice(t->ctx->device));
-  t->nranks = nranks; t->rank = rank;
-  invalidate_graph(t);
+  if (ctx->comm) { set_last_error("context already has a communicator"); return PFT_ERR_STATE; }
+  PFT_CUDA_TRY(cudaSetDevice(ctx->device));
+  ctx->nranks = nranks; ctx->rank = rank;
   if (nranks == 1) return PFT_OK;
   int rc = load_nccl();
   if (rc) return rc;
   UidByValue uid;
   memcpy(uid.internal, id128, 128);
-  PFT_NCCL_TRY(g_nccl.CommInitRank(&t->comm, nranks, uid, rank));
+  PFT_NCCL_TRY(g_nccl.CommInitRank(&ctx->comm, nranks, uid, rank));
+  return PFT_OK;
+}
+
+int pft_context_comm_destroy(pft_context* ctx) {
+  if (!ctx) { set_last_error("null context"); return PFT_ERR_INVALID; }
+  if (ctx->comm) {
+    PFT_CUDA_TRY(cudaSetDevice(ctx->device));
+    PFT_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    g_nccl.CommDestroy(ctx->comm);
+    ctx->comm = nullptr;
+  }
+  ctx->nranks = 1; ctx->rank = 0;
+  return PFT_OK;
+}
+
+// Replicates a cloud (header + `capacity` points) from `root` to every rank of the context's
+// communicator: the NVLink broadcast of the downsampled scene.  The point count stays on the device.
+int pft_cloud_broadcast(pft_cloud* cloud, size_t capacity, int root) {
+  if (!cloud) { set_last_error("null cloud"); return PFT_ERR_INVALID; }
+  pft_context* ctx = cloud->ctx;
+  if (root < 0 || root >= ctx->nranks) { set_last_error("bad root %d", root); return PFT_ERR_INVALID; }
+  if (ctx->nranks == 1) return PFT_OK;
+  if (!ctx->comm) { set_last_error("context has no communicator"); return PFT_ERR_COMM; }
+  PFT_CUDA_TRY(cudaSetDevice(ctx->device));
+  if (ctx->rank == root) {
+    if (cloud->capacity < capacity && cloud->capacity > 0) capacity = cloud->capacity;  // never read past the root's buffer
+  }
+  if (ctx->rank != root || cloud->capacity < capacity) {
+    if (ctx->rank == root) { set_last_error("root cloud holds fewer than %zu points of storage", capacity); return PFT_ERR_CAPACITY; }
+    int rc = cloud->ensure(capacity);
+    if (rc) return rc;
+  }
+  PFT_NCCL_TRY(g_nccl.GroupStart());
+  PFT_NCCL_TRY(g_nccl.Broadcast(cloud->hdr.p, cloud->hdr.p, sizeof(CloudHeader), kNcclChar, root, ctx->comm, ctx->stream));
+  PFT_NCCL_TRY(g_nccl.Broadcast(cloud->pts.p, cloud->pts.p, capacity * sizeof(float4), kNcclChar, root, ctx->comm, ctx->stream));
+  PFT_NCCL_TRY(g_nccl.GroupEnd());
+  if (ctx->rank != root) cloud->host_n = -1;
+  return PFT_OK;
+}
+
+int pft_tracker_comm_init(pft_tracker* t, int nranks, int rank, const void* id128) {
+  if (!t) { set_last_error("null tracker"); return PFT_ERR_INVALID; }
+  if (t->n_cap > 0) { set_last_error("pft_tracker_comm_init must precede the first compute()/set_particles()"); return PFT_ERR_STATE; }
+  pft_context* ctx = t->ctx;
+  if (!ctx->comm && ctx->nranks == 1) {
+    int rc = pft_context_comm_init(ctx, nranks, rank, id128);
+    if (rc) return rc;
+  } else if (ctx->nranks != nranks || ctx->rank != rank) {
+    set_last_error("context communicator is rank %d of %d, asked for %d of %d", ctx->rank, ctx->nranks, rank, nranks);
+    return PFT_ERR_INVALID;
+  }
+  t->nranks = ctx->nranks; t->rank = ctx->rank; t->comm = ctx->comm;
+  invalidate_graph(t);
   return PFT_OK;
 }
 
 int pft_tracker_comm_destroy(pft_tracker* t) {
   if (!t) { set_last_error("null tracker"); return PFT_ERR_INVALID; }
-  if (t->comm) {
-    PFT_CUDA_TRY(cudaSetDevice(t->ctx->device));
-    PFT_CUDA_TRY(cudaStreamSynchronize(t->ctx->stream));
-    g_nccl.CommDestroy(t->comm);
-    t->comm = nullptr;
-    invalidate_graph(t);
-  }
+  t->comm = nullptr;
+  invalidate_graph(t);
   return PFT_OK;
 }
 

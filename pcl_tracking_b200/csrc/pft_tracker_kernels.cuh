@@ -43,13 +43,6 @@ struct CoherenceParams {
   int use_dist, use_hsv;
 };
 
-struct GridView {
-  const unsigned int* __restrict__ words;  // occupancy bits, x fastest, 32 cells per word
-  const int* __restrict__ rank;            // occupied cells before each word
-  const float4* __restrict__ pts;          // {x,y,z,hsv}: primary slots [0,n_occupied) in cell order, overflow after
-  const int* __restrict__ orig;            // input-cloud index of each slot (tie-break key)
-  const int* __restrict__ next;            // overflow chain per slot (-1 ends)
-};
 
 // ------------------------------------------------------------------ small math (arithmetic contract)
 __device__ __forceinline__ void sincos_c(float a, float& s, float& c) {
@@ -290,7 +283,7 @@ __global__ void index_begin_kernel(const TrackerState* __restrict__ st, IndexHea
   __syncthreads();
   const int nw = h.n_words, ns = scene_hdr->n;
   const int stride = gridDim.x * blockDim.x;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nw; i += stride) words[i] = 0u;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nw + 8; i += stride) words[i] = 0u;  // + zero padding read by the row windows
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ns; i += stride) { cell_count[i] = 0; next[i] = -1; }
 }
 
@@ -336,7 +329,7 @@ __global__ void __launch_bounds__(1024) index_rank_kernel(IndexHeader* hdr, cons
 
 __global__ void index_scatter_kernel(const float4* __restrict__ scene, const CloudHeader* __restrict__ scene_hdr, IndexHeader* hdr,
                                      const unsigned int* __restrict__ words, const int* __restrict__ rank, int* cell_count,
-                                     float4* __restrict__ pts, int* __restrict__ orig, int* next) {
+                                     float4* __restrict__ pts, unsigned int* __restrict__ hsv, int* next) {
   __shared__ IndexHeader h;
   if (threadIdx.x == 0) h = *hdr;
   __syncthreads();
@@ -350,14 +343,15 @@ __global__ void index_scatter_kernel(const float4* __restrict__ scene, const Clo
     const int w = (cz * h.dim[1] + cy) * h.wx + (cx >> 5);
     const unsigned int m = words[w];
     const int slot = rank[w] + __popc(m & ((1u << (cx & 31)) - 1u));
-    const float4 q = make_float4(p.x, p.y, p.z, __uint_as_float(rgba_to_hsv_packed(__float_as_uint(p.w))));
+    const float4 q = make_float4(p.x, p.y, p.z, __int_as_float(i));  // .w = index in the input cloud (tie-break key)
+    const unsigned int hq = rgba_to_hsv_packed(__float_as_uint(p.w));
     const int pos = atomicAdd(&cell_count[slot], 1);
     if (pos == 0) {
-      pts[slot] = q; orig[slot] = i;
+      pts[slot] = q; hsv[slot] = hq;
     } else {
       // a second point in the same cell: append after the primary slots and link it to the cell
       const int o = h.n_occupied + atomicAdd(&hdr->n_overflow, 1);
-      pts[o] = q; orig[o] = i;
+      pts[o] = q; hsv[o] = hq;
       // push-front on the chain of `slot`; chains are only traversed by later kernels
       int head = atomicExch(&next[slot], o);
       next[o] = head;
@@ -366,150 +360,242 @@ __global__ void index_scatter_kernel(const float4* __restrict__ scene, const Clo
 }
 
 // ------------------------------------------------------------------ K3: weight
-// Exact nearest neighbour over the occupancy grid: expanding cube shells around the query cell,
-// candidate rows pruned by the current best distance, termination when the scanned cube provably
-// contains the nearest point (or nothing can be inside r_max).  Ties go to the lower input index.
-struct NNResult { int slot; float d2; };
+// Exact nearest neighbour over the occupancy grid.  One lane = one query.  The (dy,dz) rows of the grid
+// around the query cell are visited in order of a precomputed lower bound of their distance (RowTable);
+// a row is skipped when its exact lower bound exceeds the best distance so far, the traversal stops at
+// the first table entry whose bound does, and inside a row only the x-window that can still hold a closer
+// point is extracted from the occupancy words (one funnel shift) and its set bits are evaluated.
+// Ties go to the lower input index.  The radius is capped at maximum_distance_ (points farther than that
+// never contribute to the coherence); beyond the table's reach the search continues shell by shell.
+//
+// The index of a typical crop (a few thousand points, a 60^3 grid: ~140 KB) is staged into shared
+// memory once per CTA by a persistent one-CTA-per-SM launch; larger indices are read from L2.
+constexpr int kRT = 11;                         // table reach in cells (Chebyshev), >= ceil(0.1 m / 1 cm) + 1
+constexpr int kRows = (2 * kRT + 1) * (2 * kRT + 1);
+struct RowEntry { signed char dy, dz; unsigned short lb2; };  // lb2 = gap(dy)^2 + gap(dz)^2, gap(d) = max(|d|-1, 0)
 
-__device__ __forceinline__ void nn_eval(const GridView& g, int slot, float qx, float qy, float qz, NNResult& best) {
+struct NNResult { int slot; int orig; float d2; };
+
+struct IndexPtrs {            // generic pointers: shared memory when the index fits, global otherwise
+  const unsigned int* words;  // occupancy bits, x fastest, 32 cells per word, one zero word of padding at the end
+  const int* rank;            // occupied cells before each word
+  const float4* pts;          // {x, y, z, input index}: primary slots [0,n_occupied) in cell order, overflow after
+  const int* next;            // overflow chain per slot (-1 ends); only read when n_overflow > 0
+};
+
+__device__ __forceinline__ void nn_eval(const IndexPtrs& g, int slot, float qx, float qy, float qz, NNResult& best) {
   const float4 p = g.pts[slot];
   const float dx = qx - p.x, dy = qy - p.y, dz = qz - p.z;
   const float d2 = (dx * dx + dy * dy) + dz * dz;
-  if (d2 < best.d2) { best.d2 = d2; best.slot = slot; }
-  else if (d2 == best.d2 && best.slot >= 0 && g.orig[slot] < g.orig[best.slot]) { best.slot = slot; }
+  const int orig = __float_as_int(p.w);
+  if (d2 < best.d2 || (d2 == best.d2 && orig < best.orig)) { best.d2 = d2; best.slot = slot; best.orig = orig; }
 }
 
-__device__ __forceinline__ void nn_scan_row(const GridView& g, const IndexHeader& h, int row, int xa, int xb, float qx, float qy,
-                                            float qz, NNResult& best) {
-  xa = max(xa, 0); xb = min(xb, h.dim[0] - 1);
-  if (xa > xb) return;
-  const int wa = xa >> 5, wb = xb >> 5;
-  for (int w = wa; w <= wb; ++w) {
-    const unsigned int m = g.words[row + w];
-    unsigned int keep = 0xffffffffu;
-    unsigned int below = 0u;
-    if (w == wa) { below = (1u << (xa & 31)) - 1u; keep &= ~below; }
-    if (w == wb) { const int e = xb & 31; keep &= (e == 31) ? 0xffffffffu : ((2u << e) - 1u); }
-    const unsigned int bits = m & keep;
-    if (!bits) continue;
-    const int base = g.rank[row + w] + __popc(m & below);
-    const int cnt = __popc(bits);
-    for (int k = 0; k < cnt; ++k) {
-      nn_eval(g, base + k, qx, qy, qz, best);
-      if (h.n_overflow) for (int o = g.next[base + k]; o >= 0; o = g.next[o]) nn_eval(g, o, qx, qy, qz, best);
-    }
-  }
+// distance (cell units) from the query at fractional position t of its cell to the cell at offset d, minus a
+// safety margin that covers the fp32 rounding of the lattice coordinates (so it is a true lower bound)
+__device__ __forceinline__ float axis_gap(int d, float t) {
+  const float g = d > 0 ? (float)d - t : (d < 0 ? t - (float)(d + 1) : 0.f);
+  return fmaxf(g - 2.5e-4f, 0.f);
 }
 
-__device__ __forceinline__ float axis_gap(int d, float t) {  // min distance (cell units) to the cell at offset d
-  return d > 0 ? (float)d - t : (d < 0 ? t - (float)(d + 1) : 0.f);
-}
-
-__device__ inline NNResult nn_search(const GridView& g, const IndexHeader& h, float qx, float qy, float qz, float r_max) {
-  NNResult best{-1, FLT_MAX};
-  if (h.n_occupied == 0) return best;
-  const float sx = (qx * h.inv_leaf) * h.level_scale, sy = (qy * h.inv_leaf) * h.level_scale, sz = (qz * h.inv_leaf) * h.level_scale;
-  const float fx = floorf(sx), fy = floorf(sy), fz = floorf(sz);
-  const int cx = (int)fx - h.origin[0], cy = (int)fy - h.origin[1], cz = (int)fz - h.origin[2];
-  const float tx = sx - fx, ty = sy - fy, tz = sz - fz;
+// Shell-by-shell continuation beyond the row table (large maximum distances / very fine cells): rare path.
+__device__ __noinline__ NNResult nn_search_shells(const IndexPtrs g, const IndexHeader& h, float qx, float qy, float qz, int cx, int cy, int cz,
+                                                  float tx, float ty, float tz, float lim2, NNResult best) {
   const float tmin = fminf(fminf(fminf(tx, 1.f - tx), fminf(ty, 1.f - ty)), fminf(tz, 1.f - tz));
   const float cell2 = h.cell * h.cell;
-  const int rcap = max(1, (int)ceilf(r_max / h.cell - tmin + 0.002f));
-  int r_prev = -1, r = 1;
+  int r_prev = kRT, r = kRT + 1;
   while (true) {
+    const float done = ((float)r_prev + tmin - 2.5e-4f) * h.cell;  // everything unscanned is farther than this
+    const bool covered = (cx - r_prev <= 0) && (cx + r_prev >= h.dim[0] - 1) && (cy - r_prev <= 0) && (cy + r_prev >= h.dim[1] - 1) &&
+                         (cz - r_prev <= 0) && (cz + r_prev >= h.dim[2] - 1);
+    if (covered || done * done * 0.9999f > fminf(best.d2, lim2)) return best;
     const int z0 = max(cz - r, 0), z1 = min(cz + r, h.dim[2] - 1);
     const int y0 = max(cy - r, 0), y1 = min(cy + r, h.dim[1] - 1);
     for (int z = z0; z <= z1; ++z) {
       const int dz = z - cz;
       const float az = axis_gap(dz, tz);
-      const float az2 = az * az;
       for (int y = y0; y <= y1; ++y) {
         const int dy = y - cy;
         const float ay = axis_gap(dy, ty);
-        const float row2 = (az2 + ay * ay) * cell2;
-        if (row2 * 0.9999f > best.d2) continue;  // no cell of this row can hold a closer (or tying) point
+        if ((az * az + ay * ay) * cell2 * 0.9999f > best.d2) continue;
         const int row = (z * h.dim[1] + y) * h.wx;
         const bool inner = max(abs(dy), abs(dz)) <= r_prev;
-        if (!inner) nn_scan_row(g, h, row, cx - r, cx + r, qx, qy, qz, best);
-        else {
-          nn_scan_row(g, h, row, cx - r, cx - r_prev - 1, qx, qy, qz, best);
-          nn_scan_row(g, h, row, cx + r_prev + 1, cx + r, qx, qy, qz, best);
+        for (int seg = 0; seg < 2; ++seg) {
+          int xa, xb;
+          if (!inner) { if (seg) break; xa = cx - r; xb = cx + r; }
+          else if (seg == 0) { xa = cx - r; xb = cx - r_prev - 1; }
+          else { xa = cx + r_prev + 1; xb = cx + r; }
+          xa = max(xa, 0); xb = min(xb, h.dim[0] - 1);
+          for (int x = xa; x <= xb; ++x) {
+            const unsigned int m = g.words[row + (x >> 5)];
+            if (!((m >> (x & 31)) & 1u)) { if (!(m >> (x & 31))) x |= 31; continue; }  // nothing left in this word: jump to its end
+            const int slot = g.rank[row + (x >> 5)] + __popc(m & ((1u << (x & 31)) - 1u));
+            nn_eval(g, slot, qx, qy, qz, best);
+            if (h.n_overflow) for (int o = g.next[slot]; o >= 0; o = g.next[o]) nn_eval(g, o, qx, qy, qz, best);
+          }
         }
       }
     }
-    // every unscanned point lies outside the cube of half-width (r + tmin) cells around the query
-    const float grad = ((float)r + tmin - 0.002f) * h.cell;
-    const bool covered = (cx - r <= 0) && (cx + r >= h.dim[0] - 1) && (cy - r <= 0) && (cy + r >= h.dim[1] - 1) && (cz - r <= 0) &&
-                         (cz + r >= h.dim[2] - 1);
-    if (covered) break;
-    if (best.slot >= 0 && best.d2 <= grad * grad) break;
-    if (grad >= r_max) break;
     r_prev = r;
-    int need;
+    int need = 2 * r;
     if (best.slot >= 0) need = max(r + 1, (int)ceilf(sqrtf(best.d2) / h.cell - tmin + 0.004f));
-    else need = 2 * r + 1;
-    r = min(need, max(rcap, r + 1));
+    const int rcap = max(r + 1, (int)ceilf(sqrtf(lim2) / h.cell - tmin + 0.004f));
+    r = min(need, rcap);
   }
+}
+
+__device__ __forceinline__ NNResult nn_search(const IndexPtrs& g, const IndexHeader& h, const RowEntry* __restrict__ table, float qx, float qy,
+                                              float qz, float lim2) {
+  NNResult best{-1, 0x7fffffff, lim2};
+  const float sx = (qx * h.inv_leaf) * h.level_scale, sy = (qy * h.inv_leaf) * h.level_scale, sz = (qz * h.inv_leaf) * h.level_scale;
+  const float fx = floorf(sx), fy = floorf(sy), fz = floorf(sz);
+  // (int) of a huge float is undefined: clamp first; such queries are far outside the grid anyway
+  const float big = 1.0e9f;
+  const int cx = (int)fminf(fmaxf(fx, -big), big) - h.origin[0], cy = (int)fminf(fmaxf(fy, -big), big) - h.origin[1],
+            cz = (int)fminf(fmaxf(fz, -big), big) - h.origin[2];
+  const float tx = sx - fx, ty = sy - fy, tz = sz - fz;
+  const float cell2 = h.cell * h.cell;
+  const float inv_cell = 1.0f / h.cell;
+  const int dimx = h.dim[0], dimy = h.dim[1], dimz = h.dim[2], wx = h.wx;
+  int k = 0;
+  for (; k < kRows; ++k) {
+    const RowEntry e = table[k];
+    if ((float)e.lb2 * cell2 * 0.9999f > best.d2) break;  // every later row is at least this far
+    const int y = cy + e.dy, z = cz + e.dz;
+    if ((unsigned)y >= (unsigned)dimy || (unsigned)z >= (unsigned)dimz) continue;
+    const float ay = axis_gap(e.dy, ty), az = axis_gap(e.dz, tz);
+    const float row2 = (ay * ay + az * az) * cell2 * 0.9999f;
+    if (row2 > best.d2) continue;
+    // cells of this row that can still hold a point at distance <= best: |x gap| <= hw (cell units)
+    const float hw = fminf(sqrtf(best.d2 - row2) * inv_cell + 5.0e-4f, (float)kRT);
+    int xa = cx + (int)ceilf(tx - 1.0f - hw), xb = cx + (int)floorf(tx + hw);
+    xa = max(xa, 0); xb = min(xb, dimx - 1);
+    if (xa > xb) continue;
+    const int w0 = (z * dimy + y) * wx + (xa >> 5);
+    const unsigned int lo = g.words[w0], hi = g.words[w0 + 1];
+    const int sh = xa & 31, width = xb - xa + 1;  // width <= 2*kRT + 2 < 32
+    // bits of the next word only count when the window really crosses into it (the next word may belong to the next row)
+    const unsigned int hi_ok = (sh + width > 32) ? hi : 0u;
+    unsigned int win = __funnelshift_r(lo, hi_ok, sh) & ((1u << width) - 1u);
+    if (!win) continue;
+    int slot = g.rank[w0] + __popc(lo & ((1u << sh) - 1u));  // slots of one row are consecutive in x order
+    do {
+      win &= win - 1u;
+      nn_eval(g, slot, qx, qy, qz, best);
+      if (h.n_overflow) for (int o = g.next[slot]; o >= 0; o = g.next[o]) nn_eval(g, o, qx, qy, qz, best);
+      ++slot;
+    } while (win);
+  }
+  // rows outside the table start at a distance of kRT cells: only then can the search have missed something
+  if (best.d2 > (float)(kRT * kRT) * cell2 * 0.99f) best = nn_search_shells(g, h, qx, qy, qz, cx, cy, cz, tx, ty, tz, lim2, best);
   return best;
 }
 
 struct WeightArgs {
   const TrackerState* st;
   const IndexHeader* hdr;
-  GridView g;
-  const float4* model;      // {x,y,z,hsv} in tile order
-  const int* model_perm;    // tile order -> order of the reference cloud as given
+  const unsigned int* words;  // global copies of the index (see IndexPtrs)
+  const int* rank;
+  const float4* pts;
+  const int* next;
+  const unsigned int* hsv;    // packed HSV of every index slot
+  const RowEntry* table;      // kRows entries sorted by lb2
+  const float4* model;        // {x,y,z,hsv} in tile order
+  const int* model_perm;      // tile order -> order of the reference cloud as given
   int M;
   const float* mats;
-  double* partial;          // [chunks][n_max]
+  double* partial;            // [chunks][n_max]
   int chunks, chunk_len, n_max;
-  int nranks, rank;         // particle i is evaluated by rank i % nranks
+  int nranks, rank_id;        // particle i is evaluated by rank i % nranks
   CoherenceParams co;
   int dbg_k; int* dbg_idx; float* dbg_d2;
+  int smem_bytes;             // dynamic shared memory available for staging the index
 };
 
+__device__ __forceinline__ void stage_copy16(void* dst, const void* src, int bytes16) {
+  uint4* d = reinterpret_cast<uint4*>(dst);
+  const uint4* s = reinterpret_cast<const uint4*>(src);
+  for (int i = threadIdx.x; i < bytes16; i += blockDim.x) d[i] = s[i];
+}
+
+// Persistent launch: one CTA per SM, each warp works through (particle, model chunk) items.
 template <bool USE_HSV>
-__global__ void __launch_bounds__(256) weight_kernel(const WeightArgs a) {
+__global__ void __launch_bounds__(1024, 1) weight_kernel(const WeightArgs a) {
+  extern __shared__ uint4 dyn_smem[];
   __shared__ IndexHeader h;
   __shared__ float lut_h[256], lut_s[256];
-  __shared__ double red[32];
-  __shared__ float mat[12];
+  __shared__ RowEntry s_table[kRows];
   if (threadIdx.x == 0) h = *a.hdr;
+  for (int i = threadIdx.x; i < kRows; i += blockDim.x) s_table[i] = a.table[i];
   if (USE_HSV) {
     for (int i = threadIdx.x; i < 256; i += blockDim.x) { lut_h[i] = (float)i / 180.0f; lut_s[i] = (float)i / 255.0f; }
   }
   __syncthreads();
+  // ---- stage the scene index into shared memory when it fits (all sizes rounded up to 16 bytes)
+  IndexPtrs g{a.words, a.rank, a.pts, a.next};
+  {
+    const int n_pts = h.n_occupied + h.n_overflow;
+    const int words16 = (h.n_words + 1 + 3) >> 2, rank16 = (h.n_words + 3) >> 2, pts16 = n_pts;
+    const int next16 = h.n_overflow ? ((n_pts + 3) >> 2) : 0;
+    const long long need = 16ll * ((long long)words16 + rank16 + pts16 + next16);
+    if (h.valid && need <= (long long)a.smem_bytes) {
+      uint4* s_words = dyn_smem;
+      uint4* s_rank = s_words + words16;
+      uint4* s_pts = s_rank + rank16;
+      uint4* s_next = s_pts + pts16;
+      stage_copy16(s_words, a.words, words16);
+      stage_copy16(s_rank, a.rank, rank16);
+      stage_copy16(s_pts, a.pts, pts16);
+      if (next16) stage_copy16(s_next, a.next, next16);
+      g.words = reinterpret_cast<const unsigned int*>(s_words);
+      g.rank = reinterpret_cast<const int*>(s_rank);
+      g.pts = reinterpret_cast<const float4*>(s_pts);
+      g.next = reinterpret_cast<const int*>(s_next);
+    }
+  }
+  __syncthreads();
   const int n = a.st->particle_num;
-  const int n_local = n > a.rank ? (n - a.rank + a.nranks - 1) / a.nranks : 0;
+  const int n_local = n > a.rank_id ? (n - a.rank_id + a.nranks - 1) / a.nranks : 0;
   const int items = n_local * a.chunks;
-  for (int item = blockIdx.x; item < items; item += gridDim.x) {
-    const int i = a.rank + (item / a.chunks) * a.nranks, c = item % a.chunks;
-    __syncthreads();
-    if (threadIdx.x < 12) mat[threadIdx.x] = a.mats[(size_t)i * 12 + threadIdx.x];
-    __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  const int total_warps = gridDim.x * warps_per_block;
+  // interleave blocks first so that consecutive items spread over the SMs
+  const int warp_id = (threadIdx.x >> 5) * gridDim.x + blockIdx.x;
+  // maximum_distance_^2 as the float just above it: every point with (double)d2 < max_d2 has d2 <= lim2
+  const float lim2 = a.co.max_d2 >= 3.0e38 ? FLT_MAX : __double2float_ru(a.co.max_d2);
+  for (int item = warp_id; item < items; item += total_warps) {
+    const int i = a.rank_id + (item / a.chunks) * a.nranks, c = item % a.chunks;
     float m[12];
-#pragma unroll
-    for (int d = 0; d < 12; ++d) m[d] = mat[d];
+    {
+      const float4* mp = reinterpret_cast<const float4*>(a.mats) + (size_t)i * 3;
+      const float4 r0 = mp[0], r1 = mp[1], r2 = mp[2];
+      m[0] = r0.x; m[1] = r0.y; m[2] = r0.z; m[3] = r0.w; m[4] = r1.x; m[5] = r1.y; m[6] = r1.z; m[7] = r1.w;
+      m[8] = r2.x; m[9] = r2.y; m[10] = r2.z; m[11] = r2.w;
+    }
     const int j0 = c * a.chunk_len, j1 = min(a.M, j0 + a.chunk_len);
     double val = 0.0;
-    for (int j = j0 + threadIdx.x; j < j1; j += blockDim.x) {
+    for (int j = j0 + lane; j < j1; j += 32) {
       const float4 mp = a.model[j];
       float qx, qy, qz;
       xform(m, mp.x, mp.y, mp.z, qx, qy, qz);
-      const NNResult nn = nn_search(a.g, h, qx, qy, qz, a.co.r_max);
+      NNResult nn{-1, 0x7fffffff, lim2};
+      if (h.n_occupied > 0) nn = nn_search(g, h, s_table, qx, qy, qz, lim2);
       if (i < a.dbg_k) {
         const size_t o = (size_t)i * a.M + a.model_perm[j];
-        a.dbg_idx[o] = nn.slot >= 0 ? a.g.orig[nn.slot] : -1;
-        a.dbg_d2[o] = nn.d2;
+        a.dbg_idx[o] = nn.slot >= 0 ? nn.orig : -1;
+        a.dbg_d2[o] = nn.slot >= 0 ? nn.d2 : FLT_MAX;
       }
       if (nn.slot >= 0 && (double)nn.d2 < a.co.max_d2) {
-        double cc = 1.0;
+        // DistanceCoherence x HSVColorCoherence: 1/(1+d^2 w_d) * 1/(1+w_h diff) evaluated as one fp64 reciprocal of
+        // the product of the denominators (differs from the product of reciprocals by ~1 ulp of fp64)
+        double den = 1.0;
         if (a.co.use_dist) {
           const double d = (double)sqrtf(nn.d2);
-          cc *= 1.0 / (1.0 + d * d * a.co.dist_w);
+          den = 1.0 + d * d * a.co.dist_w;
         }
         if (USE_HSV) {
-          const unsigned int sb = __float_as_uint(mp.w), tb = __float_as_uint(a.g.pts[nn.slot].w);
+          const unsigned int sb = __float_as_uint(mp.w), tb = a.hsv[nn.slot];
           const float sh = lut_h[sb & 0xff], ss = lut_s[(sb >> 8) & 0xff], sv = lut_s[(sb >> 16) & 0xff];
           const float th = lut_h[tb & 0xff], ts = lut_s[(tb >> 8) & 0xff], tv = lut_s[(tb >> 16) & 0xff];
           const float hd = fabsf(sh - th);
@@ -520,13 +606,13 @@ __global__ void __launch_bounds__(256) weight_kernel(const WeightArgs a) {
           const float s_diff = a.co.s_w * (ss - ts) * (ss - ts);
           const float v_diff = a.co.v_w * (sv - tv) * (sv - tv);
           const float diff2 = h_diff + s_diff + v_diff;
-          cc *= 1.0 / (1.0 + a.co.hsv_w * (double)diff2);
+          den *= 1.0 + a.co.hsv_w * (double)diff2;
         }
-        val += cc;
+        val += 1.0 / den;
       }
     }
-    val = block_sum(val, red);
-    if (threadIdx.x == 0) a.partial[(size_t)c * a.n_max + i] = val;
+    val = warp_sum(val);
+    if (lane == 0) a.partial[(size_t)c * a.n_max + i] = val;
   }
 }
 

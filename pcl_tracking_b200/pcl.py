@@ -47,6 +47,13 @@ class Context:
     def stream(self):
         return capi.load().pft_context_stream(self._h)
 
+    def commInit(self, nranks, rank, unique_id):
+        buf = (C.c_char * 128).from_buffer_copy(bytes(unique_id))
+        check(capi.load().pft_context_comm_init(self._h, int(nranks), int(rank), buf))
+
+    def commDestroy(self):
+        check(capi.load().pft_context_comm_destroy(self._h))
+
     def close(self):
         if self._h:
             capi.load().pft_context_destroy(self._h)
@@ -78,6 +85,11 @@ class PointCloud:
     def upload_raw(self, host_ptr, n, layout=capi.LAYOUT_PACKED16):
         """Upload from a raw host pointer (e.g. pinned memory from host_alloc)."""
         check(capi.load().pft_cloud_upload(self._h, C.c_void_p(host_ptr), n, layout))
+        return self
+
+    def broadcast(self, capacity, root=0):
+        """NVLink broadcast of this cloud from `root` over the context communicator."""
+        check(capi.load().pft_cloud_broadcast(self._h, int(capacity), int(root)))
         return self
 
     def size(self):
@@ -129,7 +141,7 @@ class PassThrough:
         self._in = cloud
 
     def filter(self, out=None):
-        out = out or PointCloud(ctx=self.ctx)
+        out = PointCloud(ctx=self.ctx) if out is None else out
         check(capi.load().pft_passthrough(self.ctx._h, self._in._h, out._h, self._field, self._lo, self._hi))
         return out
 
@@ -159,7 +171,7 @@ class VoxelGrid:
         self._in = cloud
 
     def filter(self, out=None):
-        out = out or PointCloud(ctx=self.ctx)
+        out = PointCloud(ctx=self.ctx) if out is None else out
         check(capi.load().pft_passthrough_voxel_grid(self.ctx._h, self._in._h, out._h, self._leaf, self._field, self._lo, self._hi))
         return out
 

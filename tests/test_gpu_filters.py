@@ -1,0 +1,147 @@
+"""Parity of kernel K1 (PassThrough / voxel-grid downsampling / model preparation) with the CPU oracle,
+through the C ABI.  Integer/byte results (order, counts, colours) are bit-exact; centroids are
+bit-exact too because both sides accumulate fp32 coordinates in fp64 (exact, order independent)."""
+import numpy as np
+import pytest
+
+import oracle
+from pcl_tracking_b200 import pcl, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _random_cloud(n, seed, nan_frac=0.05, span=2.0):
+    rng = np.random.default_rng(seed)
+    xyz = rng.uniform(-span, span, (n, 3)).astype(np.float32)
+    xyz[:, 2] = rng.uniform(-1.0, 11.0, n)
+    bad = rng.random(n) < nan_frac
+    xyz[bad, rng.integers(0, 3, bad.sum())] = np.nan
+    xyz[rng.random(n) < 0.01, 1] = np.inf
+    return oracle.make_points(xyz, rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32))
+
+
+def _bits(a):
+    return np.ascontiguousarray(a).view(np.uint32).reshape(len(a), 4)
+
+
+@pytest.mark.parametrize("n,seed", [(0, 0), (1, 1), (37, 2), (5000, 3), (70001, 4)])
+def test_passthrough_bit_exact(n, seed):
+    pts = _random_cloud(n, seed)
+    for field, lo, hi in ((2, 0.0, 10.0), (0, -0.5, 0.25), (1, -1e9, 1e9)):
+        pt = pcl.PassThrough()
+        pt.setFilterFieldName("xyz"[field])
+        pt.setFilterLimits(lo, hi)
+        pt.setKeepOrganized(False)
+        pt.setInputCloud(pcl.PointCloud(pts))
+        got = pt.filter().to_numpy()
+        want = oracle.passthrough(pts, field, lo, hi)
+        assert len(got) == len(want)
+        assert np.array_equal(_bits(got), _bits(want))
+
+
+def test_passthrough_inclusive_limits():
+    pts = oracle.make_points([[0, 0, 0.0], [0, 0, 10.0], [0, 0, np.nextafter(np.float32(10.0), np.float32(11.0))], [0, 0, -1e-30]])
+    pt = pcl.PassThrough()
+    pt.setFilterFieldName("z")
+    pt.setFilterLimits(0.0, 10.0)
+    pt.setInputCloud(pcl.PointCloud(pts))
+    assert len(pt.filter()) == 2
+
+
+@pytest.mark.parametrize("n,seed,leaf", [(0, 0, 0.01), (1, 1, 0.01), (500, 2, 0.05), (20000, 3, 0.01), (60000, 4, 0.1)])
+def test_voxel_grid_bit_exact(n, seed, leaf):
+    pts = _random_cloud(n, seed, span=0.6 if leaf < 0.05 else 2.0)
+    vg = pcl.ApproximateVoxelGrid()
+    vg.setLeafSize(leaf, leaf, leaf)
+    vg.setPassThrough("z", 0.0, 10.0)
+    vg.setInputCloud(pcl.PointCloud(pts))
+    got = vg.filter().to_numpy()
+    want = oracle.voxel_grid_exact(pts, leaf, 2, 0.0, 10.0)
+    assert len(got) == len(want)
+    assert np.array_equal(_bits(got), _bits(want))  # same voxels, same order (first appearance), same centroids, same colours
+
+
+def test_voxel_grid_without_passthrough_and_dense_voxels():
+    rng = np.random.default_rng(9)
+    xyz = rng.uniform(0, 0.03, (30000, 3)).astype(np.float32)  # 27 voxels, ~1100 points each
+    pts = oracle.make_points(xyz, rng.integers(0, 1 << 24, 30000).astype(np.uint32))
+    vg = pcl.VoxelGrid()
+    vg.setLeafSize(0.01)
+    vg.setInputCloud(pcl.PointCloud(pts))
+    got = vg.filter().to_numpy()
+    want = oracle.voxel_grid_exact(pts, 0.01, -1, 0, 0)
+    assert len(got) == 27 == len(want)
+    assert np.array_equal(_bits(got), _bits(want))
+
+
+def test_voxel_grid_kinect_frame_full_size_properties():
+    """BASELINE size (217 088 points): bit-exact against the oracle, plus size-independent properties."""
+    pts, _ = synth.render(0)
+    vg = pcl.ApproximateVoxelGrid()
+    vg.setLeafSize(0.01, 0.01, 0.01)
+    vg.setPassThrough("z", 0.0, 10.0)
+    cloud = pcl.PointCloud(pts)
+    vg.setInputCloud(cloud)
+    ds = vg.filter()
+    got = ds.to_numpy()
+    want = oracle.voxel_grid_exact(pts, 0.01, 2, 0.0, 10.0)
+    assert np.array_equal(_bits(got), _bits(want))
+    # one output per occupied voxel
+    inv = np.float32(1.0) / np.float32(0.01)
+    ok = np.isfinite(pts["x"]) & np.isfinite(pts["y"]) & np.isfinite(pts["z"]) & (pts["z"] >= 0) & (pts["z"] <= 10)
+    keys = np.stack([np.floor(pts[k][ok] * inv).astype(np.int64) for k in "xyz"], 1)
+    assert len(got) == len(np.unique(keys, axis=0))
+    # idempotence: a centroid stays in its voxel, so downsampling the downsampled cloud is the identity
+    vg2 = pcl.ApproximateVoxelGrid()
+    vg2.setLeafSize(0.01)
+    vg2.setInputCloud(ds)
+    again = vg2.filter().to_numpy()
+    gk = np.stack([np.floor(got[k] * inv).astype(np.int64) for k in "xyz"], 1)
+    if len(np.unique(gk, axis=0)) == len(got):  # (a centroid can round onto a voxel face; then two merge)
+        assert np.array_equal(_bits(again)[:, :3], _bits(got)[:, :3])
+    # against PCL's own 512-slot ApproximateVoxelGrid (restated): same voxel set, PCL emits duplicates
+    approx = oracle.approx_voxel_grid_pcl(oracle.passthrough(pts, 2, 0.0, 10.0), 0.01)
+    assert len(approx) >= len(got)
+    ak = np.unique(np.stack([np.floor(approx[k] * inv).astype(np.int64) for k in "xyz"], 1), axis=0)
+    assert abs(len(ak) - len(got)) <= 0.001 * len(got)
+
+
+def test_pcl32_layout_roundtrip():
+    pts = _random_cloud(1000, 5, nan_frac=0)
+    p32 = synth.to_pcl32(pts)
+    cloud = pcl.PointCloud(np.ascontiguousarray(p32).view(pcl.POINT_PCL32).reshape(-1))
+    back16 = cloud.to_numpy()
+    assert np.array_equal(_bits(back16), _bits(pts))
+    back32 = cloud.to_numpy(pcl32=True)
+    assert np.array_equal(back32["x"], pts["x"]) and np.array_equal(back32["rgba"], pts["rgba"]) and np.all(back32["w"] == 1.0)
+
+
+def test_prepare_model_matches_reference_flow():
+    """removeZeroPoints -> centroid -> translate -> VoxelGrid (ref: src/auto_tracking.cpp:656-674)."""
+    pts, oid = synth.render(0)
+    raw = synth.model_points(pts, oid, 0)
+    raw = np.concatenate([raw, oracle.make_points([[0.001, -0.002, 0.003], [0, 0, 0]])])  # "zero points" to be removed
+    model, c = pcl.prepare_model(pcl.PointCloud(raw), 0.01)
+    got = model.to_numpy()
+    r = oracle.remove_zero_points(raw)
+    assert len(r) == len(raw) - 2
+    c_ref = oracle.centroid(r)  # PCL accumulates the centroid in fp32; the GPU in fp64
+    np.testing.assert_allclose(c, c_ref, atol=2e-5)
+    r["x"] -= c[0]; r["y"] -= c[1]; r["z"] -= c[2]  # same translation as the GPU used
+    want = oracle.voxel_grid_exact(r, 0.01, -1, 0, 0)
+    assert len(got) == len(want)
+    assert np.array_equal(_bits(got), _bits(want))
+    # and against PCL's exact VoxelGrid (sorted output order, fp32 sums): same set within float tolerance
+    pclvg = oracle.voxel_grid_pcl(r, 0.01)
+    assert len(pclvg) == len(got)
+    key = lambda a: np.lexsort((np.floor(a["z"] * 100), np.floor(a["y"] * 100), np.floor(a["x"] * 100)))
+    a, b = got[key(got)], pclvg[key(pclvg)]
+    for k in "xyz":
+        np.testing.assert_allclose(a[k], b[k], atol=1e-6)
+
+
+def test_all_points_rejected():
+    pts = oracle.make_points(np.full((100, 3), np.nan))
+    vg = pcl.ApproximateVoxelGrid()
+    vg.setInputCloud(pcl.PointCloud(pts))
+    assert len(vg.filter()) == 0

@@ -43,11 +43,10 @@ def test_weight_matches_oracle(seed, use_hsv):
         gi, gd = g.nn(p, len(model))
         oi, od = o.nn(p, len(model))
         oi_scene = np.where(oi >= 0, cidx[np.maximum(oi, 0)], -1)
-        inside = od < np.float32(0.1) ** 2 * 4  # the grid search may stop beyond r_max: compare where a match is possible
-        np.testing.assert_array_equal(gi[inside], oi_scene[inside])
-        np.testing.assert_array_equal(gd[inside], od[inside])
-        matched = od.astype(np.float64) < 0.1 * 0.1
-        assert np.all(gd[~inside].astype(np.float64) >= 0.1 * 0.1)
+        matched = od.astype(np.float64) < 0.1 * 0.1   # the coherence only counts pairs closer than maximum_distance_
+        np.testing.assert_array_equal(gi[matched], oi_scene[matched])
+        np.testing.assert_array_equal(gd[matched], od[matched])
+        assert np.all(gi[~matched] == -1)              # the GPU search stops at maximum_distance_
         assert matched.sum() > 0
     np.testing.assert_allclose(g.rawWeights(), o.raw_weights(), rtol=W_RTOL, atol=0)
     gp, op = g.getParticles(), o.get_particles()
