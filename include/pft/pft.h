@@ -189,7 +189,7 @@ PFT_API int pft_tracker_get_nn(pft_tracker* t, int particle, int32_t* idx, float
 PFT_API int pft_tracker_get_timing(pft_tracker* t, float* weight_kernel_ms, float* compute_ms);
 PFT_API int pft_tracker_enable_timing(pft_tracker* t, int on);
 
-/* dims[3], level, n_cropped, n_occupied, n_overflow, n_words of the scene index built by the last weight() */
+/* dims[3], level (cell edge = resolution x 2^level), n_cropped, n_cells, 0, 0 of the scene index built by the last weight() */
 PFT_API int pft_tracker_get_index_info(pft_tracker* t, int* info8);
 /* number of compute() calls served by replaying the captured CUDA graph */
 PFT_API int pft_tracker_graph_replays(pft_tracker* t, uint64_t* n);

@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libpft.so")
+LIB_PATH = os.environ.get("PFT_LIB") or os.path.join(_HERE, "lib", "libpft.so")  # PFT_LIB: kernel-tuning builds only
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "pft", "pft.h")
 
 POINT = np.dtype([("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("rgba", "<u4")])

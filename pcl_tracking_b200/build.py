@@ -28,12 +28,23 @@ def _stale():
 
 def build(force=False, verbose=False):
     """Compile libpft.so if it is missing or older than its sources.  Returns its path."""
+    if os.environ.get("PFT_LIB"):
+        return os.environ["PFT_LIB"]  # a tuning build chosen explicitly: never rebuilt behind the caller's back
     if not (force or _stale()):
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
     cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + SOURCES + ["-ldl"]
     subprocess.check_call(cmd, cwd=CSRC)
     return LIB_PATH
+
+
+def build_variant(threads, extra=(), name=None):
+    """Kernel-tuning build: weight kernel with `threads` per CTA (plus extra -D flags)."""
+    os.makedirs(LIB_DIR, exist_ok=True)
+    out = os.path.join(LIB_DIR, name or "libpft_t%d.so" % threads)
+    cmd = [NVCC] + FLAGS + ["-DPFT_WEIGHT_THREADS=%d" % threads] + list(extra) + ["-o", out] + SOURCES + ["-ldl"]
+    subprocess.check_call(cmd, cwd=CSRC)
+    return out
 
 
 if __name__ == "__main__":

@@ -50,14 +50,11 @@ struct IndexHeader {
   float aabb[6];      // crop box: minx,miny,minz,maxx,maxy,maxz (inclusive, fp32)
   int origin[3];      // lattice coordinate (at `level`) of cell (0,0,0)
   int dim[3];         // cells per axis
-  int level;          // cell edge = leaf * 2^level
-  int wx;             // 32-bit words per x-row
-  int n_words;        // wx * dim[1] * dim[2]
-  int n_cropped;      // scene points inside the crop box
-  int n_occupied;     // occupied cells (= primary slots)
-  int n_overflow;     // points sharing a cell with an earlier one (chained)
+  int level;          // cell edge = resolution * 2^level
+  int n_cells;        // dim[0] * dim[1] * dim[2]
+  int n_cropped;      // scene points inside the crop box (= indexed points)
   float cell;         // cell edge in metres
-  float inv_leaf;     // 1 / leaf  (lattice = floor(coord * inv_leaf) >> level)
+  float inv_leaf;     // 1 / resolution  (lattice = floor((coord * inv_leaf) * 2^-level))
   float level_scale;  // 2^-level
   int valid;          // 0: empty AABB (no model / no particles)
 };

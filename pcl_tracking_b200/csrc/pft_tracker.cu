@@ -23,6 +23,9 @@
 #include <vector>
 
 #include "pft_internal.h"
+#ifndef PFT_WEIGHT_THREADS
+#define PFT_WEIGHT_THREADS 1024
+#endif
 #include "pft_tracker_kernels.cuh"
 
 using namespace pft;
@@ -116,7 +119,8 @@ struct pft_tracker {
   int M = 0;            // model points
   const pft_cloud* input = nullptr;
   size_t scene_cap = 0; // allocated index capacity (scene points)
-  int max_words = 1 << 18;
+  int max_cells = 1 << 20;  // cap of the index grid; a larger crop box gets coarser cells
+  int index_level = 1;      // cell edge of the index = search resolution x 2^level (internal; results do not depend on it)
   int cur = 0;          // live particle buffer
   int inj_slots = 0, inj_stride = 0;
   int draw_cap = 0;
@@ -138,7 +142,7 @@ struct pft_tracker {
   int graph_nodes = 0;
   // device buffers
   DevBuf st, parts[2], mats, slot_aabb, model, model_perm, model_tmp, sort_keys, sort_idx, bbox, raw, partial, cdf, cdf_total, ancestors, bin_keys, tbl_rep,
-      tbl_min, slot_of, klb, d_usel, d_normals, d_umot, idx_hdr, words, rank_buf, ipts, ihsv, inext, icount, dbg_idx, dbg_d2, d_trans, row_table;
+      tbl_min, slot_of, klb, d_usel, d_normals, d_umot, idx_hdr, cell_start, ipts, ihsv, icount, dbg_idx, dbg_d2, d_trans, row_table;
   int weight_smem = 0;  // dynamic shared memory of the weight kernel (bytes)
   int tbl_size = 0;
   int n_slots = 0;
@@ -154,7 +158,7 @@ void invalidate_graph(pft_tracker* t) { t->config_version++; }
 void release_all(pft_tracker* t) {
   DevBuf* bufs[] = {&t->st, &t->parts[0], &t->parts[1], &t->mats, &t->slot_aabb, &t->model, &t->model_perm, &t->model_tmp, &t->sort_keys, &t->sort_idx,
                     &t->bbox, &t->raw, &t->partial, &t->cdf, &t->cdf_total, &t->ancestors, &t->bin_keys, &t->tbl_rep, &t->tbl_min, &t->slot_of, &t->klb,
-                    &t->d_usel, &t->d_normals, &t->d_umot, &t->idx_hdr, &t->words, &t->rank_buf, &t->ipts, &t->ihsv, &t->inext, &t->icount, &t->dbg_idx,
+                    &t->d_usel, &t->d_normals, &t->d_umot, &t->idx_hdr, &t->cell_start, &t->ipts, &t->ihsv, &t->icount, &t->dbg_idx,
                     &t->dbg_d2, &t->d_trans, &t->row_table};
   for (auto* b : bufs) b->release();
 }
@@ -199,6 +203,8 @@ double kl_bound(int k, double delta, double eps) {
   return ((k - 1.0) / (2.0 * eps)) * chi * chi * chi;
 }
 
+constexpr int kWeightThreads = PFT_WEIGHT_THREADS;  // CTA size of the persistent weight kernel (one CTA per SM)
+
 // Row table of the nearest-neighbour search: the (dy,dz) offsets within kRT cells sorted by the lower bound
 // gap(dy)^2 + gap(dz)^2 of their distance (gap(d) = max(|d|-1, 0)), nearer rows first.
 int upload_row_table(pft_tracker* t) {
@@ -220,12 +226,12 @@ int upload_row_table(pft_tracker* t) {
   int dev = t->ctx->device, max_optin = 0;
   PFT_CUDA_TRY(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   cudaFuncAttributes fa;
-  PFT_CUDA_TRY(cudaFuncGetAttributes(&fa, weight_kernel<true>));
+  PFT_CUDA_TRY(cudaFuncGetAttributes(&fa, weight_kernel<true, kWeightThreads>));
   int dyn = max_optin - (int)fa.sharedSizeBytes - 1024;
   if (dyn < 0) dyn = 0;
   dyn &= ~15;
-  PFT_CUDA_TRY(cudaFuncSetAttribute(weight_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
-  PFT_CUDA_TRY(cudaFuncSetAttribute(weight_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+  PFT_CUDA_TRY(cudaFuncSetAttribute(weight_kernel<true, kWeightThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+  PFT_CUDA_TRY(cudaFuncSetAttribute(weight_kernel<false, kWeightThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
   t->weight_smem = dyn;
   return PFT_OK;
 }
@@ -248,8 +254,8 @@ int ensure_particle_buffers(pft_tracker* t) {
     if ((rc = t->cdf_total.reserve(sizeof(unsigned long long)))) return rc;
     if ((rc = t->idx_hdr.reserve(sizeof(IndexHeader)))) return rc;
     if ((rc = t->d_trans.reserve(12 * sizeof(float)))) return rc;
-    if ((rc = t->words.reserve(((size_t)t->max_words + 16) * sizeof(unsigned int)))) return rc;
-    if ((rc = t->rank_buf.reserve(((size_t)t->max_words + 16) * sizeof(int)))) return rc;
+    if ((rc = t->cell_start.reserve(((size_t)t->max_cells + 16) * sizeof(int)))) return rc;
+    if ((rc = t->icount.reserve(((size_t)t->max_cells + 16) * sizeof(int)))) return rc;
     if ((rc = upload_row_table(t))) return rc;
   }
   if (cap == t->n_cap) return PFT_OK;
@@ -348,8 +354,6 @@ int ensure_index_buffers(pft_tracker* t) {
   int rc;
   if ((rc = t->ipts.reserve((cap + 4) * sizeof(float4)))) return rc;
   if ((rc = t->ihsv.reserve((cap + 4) * sizeof(unsigned int)))) return rc;
-  if ((rc = t->inext.reserve((cap + 4) * sizeof(int)))) return rc;
-  if ((rc = t->icount.reserve(cap * sizeof(int)))) return rc;
   t->scene_cap = cap;
   return PFT_OK;
 }
@@ -358,7 +362,7 @@ int ensure_index_buffers(pft_tracker* t) {
 // warp of the persistent grid keeps the tail short; a chunk is a multiple of 32 points (one per lane).
 void choose_chunks(pft_tracker* t) {
   const int n_expected = std::max(1, (t->particle_num > 0 ? t->particle_num : t->n_cap) / t->nranks);
-  const int total_warps = t->ctx->sm_count * 32;
+  const int total_warps = t->ctx->sm_count * (kWeightThreads / 32);
   const int target_items = total_warps * 6;
   const int max_chunks = std::max(1, (t->M + 63) / 64);
   int chunks = (target_items + n_expected - 1) / n_expected;
@@ -487,19 +491,18 @@ int weight_phase_eval(pft_tracker* t) {
   IndexHeader* hdr = t->idx_hdr.as<IndexHeader>();
   const float inv_leaf = 1.0f / (float)t->search_res;
   const int gscene = blocks_for(ncap_scene, 256, sm * 4);
-  index_begin_kernel<<<gscene, 256, 0, s>>>(st, hdr, t->words.as<unsigned int>(), t->icount.as<int>(), t->inext.as<int>(), in->d_hdr(), inv_leaf,
-                                            t->max_words);
+  index_begin_kernel<<<sm, 256, 0, s>>>(st, hdr, t->icount.as<int>(), inv_leaf, t->index_level, t->max_cells);
   PFT_LAUNCH_CHECK();
-  index_bits_kernel<<<gscene, 256, 0, s>>>(in->d_pts(), in->d_hdr(), hdr, t->words.as<unsigned int>());
+  index_count_kernel<<<gscene, 256, 0, s>>>(in->d_pts(), in->d_hdr(), hdr, t->icount.as<int>());
   PFT_LAUNCH_CHECK();
-  index_rank_kernel<<<1, 1024, 0, s>>>(hdr, t->words.as<unsigned int>(), t->rank_buf.as<int>());
+  index_scan_kernel<<<1, 1024, 0, s>>>(hdr, t->icount.as<int>(), t->cell_start.as<int>());
   PFT_LAUNCH_CHECK();
-  index_scatter_kernel<<<gscene, 256, 0, s>>>(in->d_pts(), in->d_hdr(), hdr, t->words.as<unsigned int>(), t->rank_buf.as<int>(), t->icount.as<int>(),
-                                              t->ipts.as<float4>(), t->ihsv.as<unsigned int>(), t->inext.as<int>());
+  index_scatter_kernel<<<gscene, 256, 0, s>>>(in->d_pts(), in->d_hdr(), hdr, t->cell_start.as<int>(), t->icount.as<int>(), t->ipts.as<float4>(),
+                                              t->ihsv.as<unsigned int>());
   PFT_LAUNCH_CHECK();
   WeightArgs a;
   a.st = st; a.hdr = hdr;
-  a.words = t->words.as<unsigned int>(); a.rank = t->rank_buf.as<int>(); a.pts = t->ipts.as<float4>(); a.next = t->inext.as<int>();
+  a.cell_start = t->cell_start.as<int>(); a.pts = t->ipts.as<float4>();
   a.hsv = t->ihsv.as<unsigned int>(); a.table = t->row_table.as<RowEntry>(); a.smem_bytes = t->weight_smem;
   a.model = t->model.as<float4>(); a.model_perm = t->model_perm.as<int>(); a.M = t->M;
   a.mats = t->mats.as<float>();
@@ -513,8 +516,8 @@ int weight_phase_eval(pft_tracker* t) {
     while ((int)t->ev_w.size() < 2 * (t->n_ev_used + 1)) { cudaEvent_t e; PFT_CUDA_TRY(cudaEventCreate(&e)); t->ev_w.push_back(e); }
     PFT_CUDA_TRY(cudaEventRecord(t->ev_w[2 * t->n_ev_used], s));
   }
-  if (t->use_hsv) weight_kernel<true><<<wgrid, 1024, t->weight_smem, s>>>(a);
-  else weight_kernel<false><<<wgrid, 1024, t->weight_smem, s>>>(a);
+  if (t->use_hsv) weight_kernel<true, kWeightThreads><<<wgrid, kWeightThreads, t->weight_smem, s>>>(a);
+  else weight_kernel<false, kWeightThreads><<<wgrid, kWeightThreads, t->weight_smem, s>>>(a);
   PFT_LAUNCH_CHECK();
   if (t->timing) { PFT_CUDA_TRY(cudaEventRecord(t->ev_w[2 * t->n_ev_used + 1], s)); t->n_ev_used++; }
   raw_weights_kernel<<<blocks_for(local_cap, 256, sm * 4), 256, 0, s>>>(st, t->partial.as<double>(), t->chunks, t->n_cap, t->raw.as<float>(), local_cap,
@@ -609,6 +612,8 @@ int pft_tracker_create(pft_context* ctx, int kld, pft_tracker** out) {
   t->kld = kld != 0;
   const char* ng = getenv("PFT_NO_GRAPH");
   t->graph_enabled = !(ng && ng[0] == '1');
+  const char* il = getenv("PFT_INDEX_LEVEL");  // tuning: cell edge of the index = resolution x 2^level
+  if (il && il[0] >= '0' && il[0] <= '9') t->index_level = il[0] - '0';
   *out = t;
   return PFT_OK;
 }
@@ -1057,7 +1062,7 @@ int pft_tracker_get_index_info(pft_tracker* t, int* info8) {
   PFT_CUDA_TRY(cudaStreamSynchronize(s));
   const IndexHeader* h = reinterpret_cast<IndexHeader*>(t->ctx->pinned);
   info8[0] = h->dim[0]; info8[1] = h->dim[1]; info8[2] = h->dim[2]; info8[3] = h->level;
-  info8[4] = h->n_cropped; info8[5] = h->n_occupied; info8[6] = h->n_overflow; info8[7] = h->n_words;
+  info8[4] = h->n_cropped; info8[5] = h->n_cells; info8[6] = 0; info8[7] = 0;
   return PFT_OK;
 }
 
@@ -1270,6 +1275,17 @@ int pft_tracker_set_shard(pft_tracker* t, int nranks, int rank) {
   invalidate_graph(t);
   return PFT_OK;
 }
+
+#ifdef PFT_STATS
+// tuning builds only (not declared in pft.h): read and clear the search statistics
+__attribute__((visibility("default"))) int pft_debug_stats(unsigned long long* out16) {
+  cudaDeviceSynchronize();
+  if (cudaMemcpyFromSymbol(out16, g_stats, sizeof(unsigned long long) * 16) != cudaSuccess) return -1;
+  unsigned long long z[16] = {0};
+  cudaMemcpyToSymbol(g_stats, z, sizeof(z));
+  return 0;
+}
+#endif
 
 int pft_tracker_graph_replays(pft_tracker* t, uint64_t* n) {
   if (!t || !n) { set_last_error("null argument"); return PFT_ERR_INVALID; }

@@ -237,32 +237,34 @@ __global__ void aabb_kernel(TrackerState* st, const float4* __restrict__ model, 
 }
 
 // ------------------------------------------------------------------ K2: scene index build
-__device__ inline void compute_index_header(const float* aabb, float inv_leaf, int max_words, IndexHeader& h) {
+// The index is a dense uniform grid over the crop box in CSR form: cell_start[c] .. cell_start[c+1] are the slots
+// of the points of cell c (cells x-fastest, so the points of any x-window of a row are ONE contiguous slot range).
+// It replaces pcl::search::Octree::setInputCloud (a pointer octree rebuilt by every weight()); the cell
+// edge is an internal choice (base resolution x 2^level) that never changes results: the search below is exact.
+__device__ inline void compute_index_header(const float* aabb, float inv_leaf, int base_level, int max_cells, IndexHeader& h) {
 #pragma unroll
   for (int d = 0; d < 6; ++d) h.aabb[d] = aabb[d];
   h.inv_leaf = inv_leaf;
-  h.n_cropped = 0; h.n_occupied = 0; h.n_overflow = 0;
+  h.n_cropped = 0;
   h.valid = (aabb[0] <= aabb[3] && aabb[1] <= aabb[4] && aabb[2] <= aabb[5]) ? 1 : 0;
-  h.level = 0; h.level_scale = 1.0f; h.wx = 0; h.n_words = 0;
+  h.level = base_level; h.level_scale = 1.0f; h.n_cells = 0;
   h.dim[0] = h.dim[1] = h.dim[2] = 0; h.origin[0] = h.origin[1] = h.origin[2] = 0;
   h.cell = 1.0f / inv_leaf;
   if (!h.valid) return;
   float lo[3], hi[3];
 #pragma unroll
   for (int d = 0; d < 3; ++d) { lo[d] = aabb[d] * inv_leaf; hi[d] = aabb[3 + d] * inv_leaf; }
-  for (int level = 0; level < 24; ++level) {
+  for (int level = base_level; level < 24; ++level) {
     const float ls = 1.0f / (float)(1 << level);
-    long long words = 1;
     int dim[3], org[3];
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
       org[d] = (int)floorf(lo[d] * ls);
       dim[d] = (int)floorf(hi[d] * ls) - org[d] + 1;
     }
-    const int wx = (dim[0] + 31) >> 5;
-    words = (long long)wx * dim[1] * dim[2];
-    if (words <= (long long)max_words || level == 23) {
-      h.level = level; h.level_scale = ls; h.wx = wx; h.n_words = (int)min(words, (long long)max_words);
+    const long long cells = (long long)dim[0] * dim[1] * dim[2];
+    if (cells <= (long long)max_cells || level == 23) {
+      h.level = level; h.level_scale = ls; h.n_cells = (int)min(cells, (long long)max_cells);
 #pragma unroll
       for (int d = 0; d < 3; ++d) { h.dim[d] = dim[d]; h.origin[d] = org[d]; }
       h.cell = (float)(1 << level) / inv_leaf;
@@ -271,20 +273,18 @@ __device__ inline void compute_index_header(const float* aabb, float inv_leaf, i
   }
 }
 
-// Every block derives the header from the crop box (a pure function of it), block 0 publishes it, and
-// all blocks clear the occupancy words and the per-slot chain heads.
-__global__ void index_begin_kernel(const TrackerState* __restrict__ st, IndexHeader* hdr, unsigned int* words, int* cell_count,
-                                   int* next, const CloudHeader* __restrict__ scene_hdr, float inv_leaf, int max_words) {
+// Every block derives the header from the crop box (a pure function of it), block 0 publishes it, and all
+// blocks clear the per-cell counters.
+__global__ void index_begin_kernel(const TrackerState* __restrict__ st, IndexHeader* hdr, int* cell_count, float inv_leaf, int base_level,
+                                   int max_cells) {
   __shared__ IndexHeader h;
   if (threadIdx.x == 0) {
-    compute_index_header(st->aabb, inv_leaf, max_words, h);
+    compute_index_header(st->aabb, inv_leaf, base_level, max_cells, h);
     if (blockIdx.x == 0) *hdr = h;
   }
   __syncthreads();
-  const int nw = h.n_words, ns = scene_hdr->n;
-  const int stride = gridDim.x * blockDim.x;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nw + 8; i += stride) words[i] = 0u;  // + zero padding read by the row windows
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ns; i += stride) { cell_count[i] = 0; next[i] = -1; }
+  const int nc = h.n_cells + 1;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nc; i += gridDim.x * blockDim.x) cell_count[i] = 0;
 }
 
 __device__ __forceinline__ bool in_crop(const float4& p, const IndexHeader& h) {
@@ -292,14 +292,14 @@ __device__ __forceinline__ bool in_crop(const float4& p, const IndexHeader& h) {
   return isfinite(p.x) && isfinite(p.y) && isfinite(p.z) && p.x >= h.aabb[0] && p.x <= h.aabb[3] && p.y >= h.aabb[1] &&
          p.y <= h.aabb[4] && p.z >= h.aabb[2] && p.z <= h.aabb[5];
 }
-__device__ __forceinline__ void cell_of(const float4& p, const IndexHeader& h, int& cx, int& cy, int& cz) {
-  cx = (int)floorf((p.x * h.inv_leaf) * h.level_scale) - h.origin[0];
-  cy = (int)floorf((p.y * h.inv_leaf) * h.level_scale) - h.origin[1];
-  cz = (int)floorf((p.z * h.inv_leaf) * h.level_scale) - h.origin[2];
+__device__ __forceinline__ int cell_of(const float4& p, const IndexHeader& h) {
+  const int cx = (int)floorf((p.x * h.inv_leaf) * h.level_scale) - h.origin[0];
+  const int cy = (int)floorf((p.y * h.inv_leaf) * h.level_scale) - h.origin[1];
+  const int cz = (int)floorf((p.z * h.inv_leaf) * h.level_scale) - h.origin[2];
+  return (cz * h.dim[1] + cy) * h.dim[0] + cx;
 }
 
-__global__ void index_bits_kernel(const float4* __restrict__ scene, const CloudHeader* __restrict__ scene_hdr, IndexHeader* hdr,
-                                  unsigned int* words) {
+__global__ void index_count_kernel(const float4* __restrict__ scene, const CloudHeader* __restrict__ scene_hdr, IndexHeader* hdr, int* cell_count) {
   __shared__ IndexHeader h;
   if (threadIdx.x == 0) h = *hdr;
   __syncthreads();
@@ -309,27 +309,24 @@ __global__ void index_bits_kernel(const float4* __restrict__ scene, const CloudH
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ns; i += gridDim.x * blockDim.x) {
     const float4 p = scene[i];
     if (!in_crop(p, h)) continue;
-    int cx, cy, cz;
-    cell_of(p, h, cx, cy, cz);
-    const int w = (cz * h.dim[1] + cy) * h.wx + (cx >> 5);
-    atomicOr(&words[w], 1u << (cx & 31));
+    atomicAdd(&cell_count[cell_of(p, h)], 1);
     ++local;
   }
   local = warp_sum(local);
   if ((threadIdx.x & 31) == 0 && local) atomicAdd(&hdr->n_cropped, local);
 }
 
-__global__ void __launch_bounds__(1024) index_rank_kernel(IndexHeader* hdr, const unsigned int* __restrict__ words, int* __restrict__ rank) {
+// exclusive prefix of the cell counts -> cell_start; the counters are cleared again (they become the fill cursors)
+__global__ void __launch_bounds__(1024) index_scan_kernel(const IndexHeader* __restrict__ hdr, int* cell_count, int* __restrict__ cell_start) {
   __shared__ int smem[34];
-  const int nw = hdr->n_words;
+  const int nc = hdr->n_cells;
   const int total = block_exclusive_scan<int>(
-      nw, [&](int i) { return __popc(words[i]); }, [&](int i, int ex) { rank[i] = ex; }, smem);
-  if (threadIdx.x == 0) hdr->n_occupied = total;
+      nc, [&](int i) { return cell_count[i]; }, [&](int i, int ex) { cell_start[i] = ex; cell_count[i] = 0; }, smem);
+  if (threadIdx.x == 0) cell_start[nc] = total;
 }
 
-__global__ void index_scatter_kernel(const float4* __restrict__ scene, const CloudHeader* __restrict__ scene_hdr, IndexHeader* hdr,
-                                     const unsigned int* __restrict__ words, const int* __restrict__ rank, int* cell_count,
-                                     float4* __restrict__ pts, unsigned int* __restrict__ hsv, int* next) {
+__global__ void index_scatter_kernel(const float4* __restrict__ scene, const CloudHeader* __restrict__ scene_hdr, const IndexHeader* __restrict__ hdr,
+                                     const int* __restrict__ cell_start, int* cell_count, float4* __restrict__ pts, unsigned int* __restrict__ hsv) {
   __shared__ IndexHeader h;
   if (threadIdx.x == 0) h = *hdr;
   __syncthreads();
@@ -338,53 +335,37 @@ __global__ void index_scatter_kernel(const float4* __restrict__ scene, const Clo
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ns; i += gridDim.x * blockDim.x) {
     const float4 p = scene[i];
     if (!in_crop(p, h)) continue;
-    int cx, cy, cz;
-    cell_of(p, h, cx, cy, cz);
-    const int w = (cz * h.dim[1] + cy) * h.wx + (cx >> 5);
-    const unsigned int m = words[w];
-    const int slot = rank[w] + __popc(m & ((1u << (cx & 31)) - 1u));
-    const float4 q = make_float4(p.x, p.y, p.z, __int_as_float(i));  // .w = index in the input cloud (tie-break key)
-    const unsigned int hq = rgba_to_hsv_packed(__float_as_uint(p.w));
-    const int pos = atomicAdd(&cell_count[slot], 1);
-    if (pos == 0) {
-      pts[slot] = q; hsv[slot] = hq;
-    } else {
-      // a second point in the same cell: append after the primary slots and link it to the cell
-      const int o = h.n_occupied + atomicAdd(&hdr->n_overflow, 1);
-      pts[o] = q; hsv[o] = hq;
-      // push-front on the chain of `slot`; chains are only traversed by later kernels
-      int head = atomicExch(&next[slot], o);
-      next[o] = head;
-    }
+    const int c = cell_of(p, h);
+    const int pos = cell_start[c] + atomicAdd(&cell_count[c], 1);
+    pts[pos] = make_float4(p.x, p.y, p.z, __int_as_float(i));  // .w = index in the input cloud (tie-break key)
+    hsv[pos] = rgba_to_hsv_packed(__float_as_uint(p.w));
   }
 }
 
 // ------------------------------------------------------------------ K3: weight
-// Exact nearest neighbour over the occupancy grid.  One lane = one query.  The (dy,dz) rows of the grid
-// around the query cell are visited in order of a precomputed lower bound of their distance (RowTable);
-// a row is skipped when its exact lower bound exceeds the best distance so far, the traversal stops at
-// the first table entry whose bound does, and inside a row only the x-window that can still hold a closer
-// point is extracted from the occupancy words (one funnel shift) and its set bits are evaluated.
-// Ties go to the lower input index.  The radius is capped at maximum_distance_ (points farther than that
-// never contribute to the coherence); beyond the table's reach the search continues shell by shell.
+// Exact nearest neighbour over the CSR grid.  One lane = one query.  The (dy,dz) rows of cells around the query cell
+// are visited in order of a precomputed lower bound of their distance (RowTable); a row is skipped when its exact
+// lower bound exceeds the best distance so far, the traversal stops at the first table entry whose bound does, and
+// inside a row only the x-window that can still hold a closer point is read: one contiguous slot range.
+// Ties go to the lower input index.  The radius is capped at maximum_distance_ (points farther than that never
+// contribute to the coherence); beyond the table's reach the search continues shell by shell.
 //
-// The index of a typical crop (a few thousand points, a 60^3 grid: ~140 KB) is staged into shared
-// memory once per CTA by a persistent one-CTA-per-SM launch; larger indices are read from L2.
-constexpr int kRT = 11;                         // table reach in cells (Chebyshev), >= ceil(0.1 m / 1 cm) + 1
+// The index of a typical crop (a few thousand points: ~100 KB of points + ~50 KB of cell starts) is staged into
+// shared memory once per CTA by a persistent one-CTA-per-SM launch; larger indices are read through L1/L2.
+#ifdef PFT_STATS
+__device__ unsigned long long g_stats[16];
+#define PFT_STAT(i, v) atomicAdd(&g_stats[i], (unsigned long long)(v))
+#else
+#define PFT_STAT(i, v)
+#endif
+constexpr int kRT = 11;                         // table reach in cells (Chebyshev)
 constexpr int kRows = (2 * kRT + 1) * (2 * kRT + 1);
 struct RowEntry { signed char dy, dz; unsigned short lb2; };  // lb2 = gap(dy)^2 + gap(dz)^2, gap(d) = max(|d|-1, 0)
 
 struct NNResult { int slot; int orig; float d2; };
 
-struct IndexPtrs {            // generic pointers: shared memory when the index fits, global otherwise
-  const unsigned int* words;  // occupancy bits, x fastest, 32 cells per word, one zero word of padding at the end
-  const int* rank;            // occupied cells before each word
-  const float4* pts;          // {x, y, z, input index}: primary slots [0,n_occupied) in cell order, overflow after
-  const int* next;            // overflow chain per slot (-1 ends); only read when n_overflow > 0
-};
-
-__device__ __forceinline__ void nn_eval(const IndexPtrs& g, int slot, float qx, float qy, float qz, NNResult& best) {
-  const float4 p = g.pts[slot];
+__device__ __forceinline__ void nn_eval(const float4* __restrict__ pts, int slot, float qx, float qy, float qz, NNResult& best) {
+  const float4 p = pts[slot];
   const float dx = qx - p.x, dy = qy - p.y, dz = qz - p.z;
   const float d2 = (dx * dx + dy * dy) + dz * dz;
   const int orig = __float_as_int(p.w);
@@ -399,8 +380,9 @@ __device__ __forceinline__ float axis_gap(int d, float t) {
 }
 
 // Shell-by-shell continuation beyond the row table (large maximum distances / very fine cells): rare path.
-__device__ __noinline__ NNResult nn_search_shells(const IndexPtrs g, const IndexHeader& h, float qx, float qy, float qz, int cx, int cy, int cz,
-                                                  float tx, float ty, float tz, float lim2, NNResult best) {
+template <typename CS>
+__device__ __noinline__ NNResult nn_search_shells(const CS* __restrict__ cs, const float4* __restrict__ pts, const IndexHeader& h, float qx, float qy,
+                                                  float qz, int cx, int cy, int cz, float tx, float ty, float tz, float lim2, NNResult best) {
   const float tmin = fminf(fminf(fminf(tx, 1.f - tx), fminf(ty, 1.f - ty)), fminf(tz, 1.f - tz));
   const float cell2 = h.cell * h.cell;
   int r_prev = kRT, r = kRT + 1;
@@ -418,7 +400,7 @@ __device__ __noinline__ NNResult nn_search_shells(const IndexPtrs g, const Index
         const int dy = y - cy;
         const float ay = axis_gap(dy, ty);
         if ((az * az + ay * ay) * cell2 * 0.9999f > best.d2) continue;
-        const int row = (z * h.dim[1] + y) * h.wx;
+        const int base = (z * h.dim[1] + y) * h.dim[0];
         const bool inner = max(abs(dy), abs(dz)) <= r_prev;
         for (int seg = 0; seg < 2; ++seg) {
           int xa, xb;
@@ -426,13 +408,9 @@ __device__ __noinline__ NNResult nn_search_shells(const IndexPtrs g, const Index
           else if (seg == 0) { xa = cx - r; xb = cx - r_prev - 1; }
           else { xa = cx + r_prev + 1; xb = cx + r; }
           xa = max(xa, 0); xb = min(xb, h.dim[0] - 1);
-          for (int x = xa; x <= xb; ++x) {
-            const unsigned int m = g.words[row + (x >> 5)];
-            if (!((m >> (x & 31)) & 1u)) { if (!(m >> (x & 31))) x |= 31; continue; }  // nothing left in this word: jump to its end
-            const int slot = g.rank[row + (x >> 5)] + __popc(m & ((1u << (x & 31)) - 1u));
-            nn_eval(g, slot, qx, qy, qz, best);
-            if (h.n_overflow) for (int o = g.next[slot]; o >= 0; o = g.next[o]) nn_eval(g, o, qx, qy, qz, best);
-          }
+          if (xa > xb) continue;
+          const int s1 = (int)cs[base + xb + 1];
+          for (int s = (int)cs[base + xa]; s < s1; ++s) nn_eval(pts, s, qx, qy, qz, best);
         }
       }
     }
@@ -444,8 +422,9 @@ __device__ __noinline__ NNResult nn_search_shells(const IndexPtrs g, const Index
   }
 }
 
-__device__ __forceinline__ NNResult nn_search(const IndexPtrs& g, const IndexHeader& h, const RowEntry* __restrict__ table, float qx, float qy,
-                                              float qz, float lim2) {
+template <typename CS>
+__device__ __forceinline__ NNResult nn_search(const CS* __restrict__ cs, const float4* __restrict__ pts, const IndexHeader& h,
+                                              const RowEntry* __restrict__ table, float qx, float qy, float qz, float lim2) {
   NNResult best{-1, 0x7fffffff, lim2};
   const float sx = (qx * h.inv_leaf) * h.level_scale, sy = (qy * h.inv_leaf) * h.level_scale, sz = (qz * h.inv_leaf) * h.level_scale;
   const float fx = floorf(sx), fy = floorf(sy), fz = floorf(sz);
@@ -456,11 +435,12 @@ __device__ __forceinline__ NNResult nn_search(const IndexPtrs& g, const IndexHea
   const float tx = sx - fx, ty = sy - fy, tz = sz - fz;
   const float cell2 = h.cell * h.cell;
   const float inv_cell = 1.0f / h.cell;
-  const int dimx = h.dim[0], dimy = h.dim[1], dimz = h.dim[2], wx = h.wx;
-  int k = 0;
-  for (; k < kRows; ++k) {
+  const int dimx = h.dim[0], dimy = h.dim[1], dimz = h.dim[2];
+  PFT_STAT(6, 1);
+  for (int k = 0; k < kRows; ++k) {
     const RowEntry e = table[k];
     if ((float)e.lb2 * cell2 * 0.9999f > best.d2) break;  // every later row is at least this far
+    PFT_STAT(7, 1);
     const int y = cy + e.dy, z = cz + e.dz;
     if ((unsigned)y >= (unsigned)dimy || (unsigned)z >= (unsigned)dimz) continue;
     const float ay = axis_gap(e.dy, ty), az = axis_gap(e.dz, tz);
@@ -471,34 +451,22 @@ __device__ __forceinline__ NNResult nn_search(const IndexPtrs& g, const IndexHea
     int xa = cx + (int)ceilf(tx - 1.0f - hw), xb = cx + (int)floorf(tx + hw);
     xa = max(xa, 0); xb = min(xb, dimx - 1);
     if (xa > xb) continue;
-    const int w0 = (z * dimy + y) * wx + (xa >> 5);
-    const unsigned int lo = g.words[w0], hi = g.words[w0 + 1];
-    const int sh = xa & 31, width = xb - xa + 1;  // width <= 2*kRT + 2 < 32
-    // bits of the next word only count when the window really crosses into it (the next word may belong to the next row)
-    const unsigned int hi_ok = (sh + width > 32) ? hi : 0u;
-    unsigned int win = __funnelshift_r(lo, hi_ok, sh) & ((1u << width) - 1u);
-    if (!win) continue;
-    int slot = g.rank[w0] + __popc(lo & ((1u << sh) - 1u));  // slots of one row are consecutive in x order
-    do {
-      win &= win - 1u;
-      nn_eval(g, slot, qx, qy, qz, best);
-      if (h.n_overflow) for (int o = g.next[slot]; o >= 0; o = g.next[o]) nn_eval(g, o, qx, qy, qz, best);
-      ++slot;
-    } while (win);
+    PFT_STAT(8, 1);
+    const int base = (z * dimy + y) * dimx;
+    const int s1 = (int)cs[base + xb + 1];
+    for (int s = (int)cs[base + xa]; s < s1; ++s) { PFT_STAT(9, 1); nn_eval(pts, s, qx, qy, qz, best); }
   }
   // rows outside the table start at a distance of kRT cells: only then can the search have missed something
-  if (best.d2 > (float)(kRT * kRT) * cell2 * 0.99f) best = nn_search_shells(g, h, qx, qy, qz, cx, cy, cz, tx, ty, tz, lim2, best);
+  if (best.d2 > (float)(kRT * kRT) * cell2 * 0.99f) best = nn_search_shells<CS>(cs, pts, h, qx, qy, qz, cx, cy, cz, tx, ty, tz, lim2, best);
   return best;
 }
 
 struct WeightArgs {
   const TrackerState* st;
   const IndexHeader* hdr;
-  const unsigned int* words;  // global copies of the index (see IndexPtrs)
-  const int* rank;
-  const float4* pts;
-  const int* next;
-  const unsigned int* hsv;    // packed HSV of every index slot
+  const int* cell_start;      // [n_cells + 1]
+  const float4* pts;          // {x, y, z, input index} in cell order
+  const unsigned int* hsv;    // packed HSV of every slot
   const RowEntry* table;      // kRows entries sorted by lb2
   const float4* model;        // {x,y,z,hsv} in tile order
   const int* model_perm;      // tile order -> order of the reference cloud as given
@@ -512,54 +480,15 @@ struct WeightArgs {
   int smem_bytes;             // dynamic shared memory available for staging the index
 };
 
-__device__ __forceinline__ void stage_copy16(void* dst, const void* src, int bytes16) {
-  uint4* d = reinterpret_cast<uint4*>(dst);
-  const uint4* s = reinterpret_cast<const uint4*>(src);
-  for (int i = threadIdx.x; i < bytes16; i += blockDim.x) d[i] = s[i];
-}
-
-// Persistent launch: one CTA per SM, each warp works through (particle, model chunk) items.
-template <bool USE_HSV>
-__global__ void __launch_bounds__(1024, 1) weight_kernel(const WeightArgs a) {
-  extern __shared__ uint4 dyn_smem[];
-  __shared__ IndexHeader h;
-  __shared__ float lut_h[256], lut_s[256];
-  __shared__ RowEntry s_table[kRows];
-  if (threadIdx.x == 0) h = *a.hdr;
-  for (int i = threadIdx.x; i < kRows; i += blockDim.x) s_table[i] = a.table[i];
-  if (USE_HSV) {
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) { lut_h[i] = (float)i / 180.0f; lut_s[i] = (float)i / 255.0f; }
-  }
-  __syncthreads();
-  // ---- stage the scene index into shared memory when it fits (all sizes rounded up to 16 bytes)
-  IndexPtrs g{a.words, a.rank, a.pts, a.next};
-  {
-    const int n_pts = h.n_occupied + h.n_overflow;
-    const int words16 = (h.n_words + 1 + 3) >> 2, rank16 = (h.n_words + 3) >> 2, pts16 = n_pts;
-    const int next16 = h.n_overflow ? ((n_pts + 3) >> 2) : 0;
-    const long long need = 16ll * ((long long)words16 + rank16 + pts16 + next16);
-    if (h.valid && need <= (long long)a.smem_bytes) {
-      uint4* s_words = dyn_smem;
-      uint4* s_rank = s_words + words16;
-      uint4* s_pts = s_rank + rank16;
-      uint4* s_next = s_pts + pts16;
-      stage_copy16(s_words, a.words, words16);
-      stage_copy16(s_rank, a.rank, rank16);
-      stage_copy16(s_pts, a.pts, pts16);
-      if (next16) stage_copy16(s_next, a.next, next16);
-      g.words = reinterpret_cast<const unsigned int*>(s_words);
-      g.rank = reinterpret_cast<const int*>(s_rank);
-      g.pts = reinterpret_cast<const float4*>(s_pts);
-      g.next = reinterpret_cast<const int*>(s_next);
-    }
-  }
-  __syncthreads();
+// One (particle, model chunk) item by one warp: transform, nearest neighbour, coherence, warp reduction.
+template <bool USE_HSV, typename CS>
+__device__ __forceinline__ void weight_items(const WeightArgs& a, const IndexHeader& h, const CS* __restrict__ cs, const float4* __restrict__ pts,
+                                             const RowEntry* __restrict__ table, const float* __restrict__ lut_h, const float* __restrict__ lut_s) {
   const int n = a.st->particle_num;
   const int n_local = n > a.rank_id ? (n - a.rank_id + a.nranks - 1) / a.nranks : 0;
   const int items = n_local * a.chunks;
   const int lane = threadIdx.x & 31;
-  const int warps_per_block = blockDim.x >> 5;
-  const int total_warps = gridDim.x * warps_per_block;
+  const int total_warps = gridDim.x * (blockDim.x >> 5);
   // interleave blocks first so that consecutive items spread over the SMs
   const int warp_id = (threadIdx.x >> 5) * gridDim.x + blockIdx.x;
   // maximum_distance_^2 as the float just above it: every point with (double)d2 < max_d2 has d2 <= lim2
@@ -580,7 +509,7 @@ __global__ void __launch_bounds__(1024, 1) weight_kernel(const WeightArgs a) {
       float qx, qy, qz;
       xform(m, mp.x, mp.y, mp.z, qx, qy, qz);
       NNResult nn{-1, 0x7fffffff, lim2};
-      if (h.n_occupied > 0) nn = nn_search(g, h, s_table, qx, qy, qz, lim2);
+      if (h.n_cropped > 0) nn = nn_search<CS>(cs, pts, h, table, qx, qy, qz, lim2);
       if (i < a.dbg_k) {
         const size_t o = (size_t)i * a.M + a.model_perm[j];
         a.dbg_idx[o] = nn.slot >= 0 ? nn.orig : -1;
@@ -613,6 +542,36 @@ __global__ void __launch_bounds__(1024, 1) weight_kernel(const WeightArgs a) {
     }
     val = warp_sum(val);
     if (lane == 0) a.partial[(size_t)c * a.n_max + i] = val;
+  }
+}
+
+// Persistent launch: one CTA per SM, each warp works through (particle, model chunk) items.
+template <bool USE_HSV, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) weight_kernel(const WeightArgs a) {
+  extern __shared__ uint4 dyn_smem[];
+  __shared__ IndexHeader h;
+  __shared__ float lut_h[256], lut_s[256];
+  __shared__ RowEntry s_table[kRows];
+  if (threadIdx.x == 0) h = *a.hdr;
+  for (int i = threadIdx.x; i < kRows; i += blockDim.x) s_table[i] = a.table[i];
+  if (USE_HSV) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) { lut_h[i] = (float)i / 180.0f; lut_s[i] = (float)i / 255.0f; }
+  }
+  __syncthreads();
+  // ---- stage the scene index into shared memory when it fits: points as float4, cell starts as 16-bit
+  const int n_pts = h.n_cropped;
+  const long long need = 16ll * n_pts + 2ll * (((long long)h.n_cells + 1 + 7) & ~7ll);
+  const bool staged = h.valid && n_pts < 65536 && need <= (long long)a.smem_bytes;
+  if (staged) {
+    uint4* s_pts = dyn_smem;
+    unsigned short* s_cs = reinterpret_cast<unsigned short*>(dyn_smem + n_pts);
+    const uint4* gp = reinterpret_cast<const uint4*>(a.pts);
+    for (int i = threadIdx.x; i < n_pts; i += blockDim.x) s_pts[i] = gp[i];
+    for (int i = threadIdx.x; i <= h.n_cells; i += blockDim.x) s_cs[i] = (unsigned short)a.cell_start[i];
+    __syncthreads();
+    weight_items<USE_HSV, unsigned short>(a, h, s_cs, reinterpret_cast<const float4*>(s_pts), s_table, lut_h, lut_s);
+  } else {
+    weight_items<USE_HSV, int>(a, h, a.cell_start, a.pts, s_table, lut_h, lut_s);
   }
 }
 

@@ -479,7 +479,7 @@ class ParticleFilterOMPTracker:
     def indexInfo(self):
         a = np.zeros(8, dtype=np.int32)
         check(capi.load().pft_tracker_get_index_info(self._h, ptr(a)))
-        return dict(zip(("dim_x", "dim_y", "dim_z", "level", "n_cropped", "n_occupied", "n_overflow", "n_words"), a.tolist()))
+        return dict(zip(("dim_x", "dim_y", "dim_z", "level", "n_cropped", "n_cells"), a.tolist()[:6]))
 
     def rawWeights(self):
         n = C.c_size_t()
