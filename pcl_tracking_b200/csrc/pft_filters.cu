@@ -95,24 +95,71 @@ __global__ void k1_insert_kernel(const float4* __restrict__ in, const CloudHeade
     slot_of[i] = slot;
   }
 }
-// ---- K1b: one block: voxel id = rank of the voxel's first point among all first points.
-__global__ void __launch_bounds__(1024) k1_rank_kernel(const CloudHeader* __restrict__ in_hdr, const int* __restrict__ slot_of,
-                                                       const int* __restrict__ first, int* __restrict__ vid, double* acc_xyz,
-                                                       unsigned int* acc_rgbc, CloudHeader* out_hdr) {
-  __shared__ int smem[34];
+// ---- K1b: voxel id = rank of the voxel's first point among all first points (output order = order of first
+// appearance).  Three small kernels: per-tile counts, one-block scan of the tile counts, per-tile assignment.
+constexpr int kTile = 4096;  // points per block (1024 threads x 4)
+
+__device__ __forceinline__ int k1_is_first(int i, int n, const int* __restrict__ slot_of, const int* __restrict__ first) {
+  if (i >= n) return 0;
+  const int s = slot_of[i];
+  return (s >= 0 && first[s] == i) ? 1 : 0;
+}
+__global__ void __launch_bounds__(1024) k1_tile_count_kernel(const CloudHeader* __restrict__ in_hdr, const int* __restrict__ slot_of,
+                                                             const int* __restrict__ first, int* __restrict__ tile_count) {
+  __shared__ int red[32];
   const int n = in_hdr->n;
-  auto is_first = [&](int i) -> int { const int s = slot_of[i]; return (s >= 0 && first[s] == i) ? 1 : 0; };
+  const int base = blockIdx.x * kTile + threadIdx.x * 4;
+  int c = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) c += k1_is_first(base + k, n, slot_of, first);
+  c = warp_sum(c);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    int v = red[threadIdx.x];
+    v = warp_sum(v);
+    if (threadIdx.x == 0) tile_count[blockIdx.x] = v;
+  }
+}
+__global__ void __launch_bounds__(1024) k1_tile_scan_kernel(int n_tiles, int* tile_count, CloudHeader* out_hdr) {
+  __shared__ int smem[34];
   const int total = block_exclusive_scan<int>(
-      n, is_first,
-      [&](int i, int ex) {
-        if (is_first(i)) {
-          vid[slot_of[i]] = ex;
-          acc_xyz[3 * ex] = 0.0; acc_xyz[3 * ex + 1] = 0.0; acc_xyz[3 * ex + 2] = 0.0;
-          reinterpret_cast<uint4*>(acc_rgbc)[ex] = make_uint4(0u, 0u, 0u, 0u);
-        }
-      },
-      smem);
+      n_tiles, [&](int i) { return tile_count[i]; }, [&](int i, int ex) { tile_count[i] = ex; }, smem);
   if (threadIdx.x == 0) out_hdr->n = total;
+}
+__global__ void __launch_bounds__(1024) k1_tile_assign_kernel(const CloudHeader* __restrict__ in_hdr, const int* __restrict__ slot_of,
+                                                              const int* __restrict__ first, const int* __restrict__ tile_offset,
+                                                              int* __restrict__ vid, double* acc_xyz, unsigned int* acc_rgbc) {
+  __shared__ int wsum[32];
+  const int n = in_hdr->n;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int base = blockIdx.x * kTile + threadIdx.x * 4;
+  int f[4], sum = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { f[k] = k1_is_first(base + k, n, slot_of, first); sum += f[k]; }
+  int inc = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(kFull, inc, o); if (lane >= o) inc += t; }
+  if (lane == 31) wsum[wid] = inc;
+  __syncthreads();
+  if (wid == 0) {
+    const int w = wsum[lane];
+    int winc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(kFull, winc, o); if (lane >= o) winc += t; }
+    wsum[lane] = winc - w;
+  }
+  __syncthreads();
+  int ex = tile_offset[blockIdx.x] + wsum[wid] + (inc - sum);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (f[k]) {
+      vid[slot_of[base + k]] = ex;
+      acc_xyz[3 * ex] = 0.0; acc_xyz[3 * ex + 1] = 0.0; acc_xyz[3 * ex + 2] = 0.0;
+      reinterpret_cast<uint4*>(acc_rgbc)[ex] = make_uint4(0u, 0u, 0u, 0u);
+      ++ex;
+    }
+  }
 }
 // ---- K1c: accumulate.  fp64 sums of fp32 sensor coordinates are exact => order independent.
 __global__ void k1_accum_kernel(const float4* __restrict__ in, const CloudHeader* __restrict__ in_hdr, const int* __restrict__ slot_of,
@@ -223,8 +270,14 @@ int run_voxel_grid(pft_context* ctx, const pft_cloud* in, pft_cloud* out, float 
   k1_insert_kernel<<<grid, 256, 0, s>>>(in->d_pts(), in->d_hdr(), ctx->k1_keys.as<unsigned long long>(), ctx->k1_first.as<int>(),
                                         ctx->k1_slot_of.as<int>(), (unsigned int)(H - 1), inv, field, lo, hi);
   PFT_LAUNCH_CHECK();
-  k1_rank_kernel<<<1, 1024, 0, s>>>(in->d_hdr(), ctx->k1_slot_of.as<int>(), ctx->k1_first.as<int>(), ctx->k1_vid.as<int>(),
-                                    ctx->k1_acc_xyz.as<double>(), ctx->k1_acc_rgbc.as<unsigned int>(), out->d_hdr());
+  const int n_tiles = (int)((cap + kTile - 1) / kTile);
+  if ((rc = ctx->k1_blk.reserve((size_t)n_tiles * sizeof(int)))) return rc;
+  k1_tile_count_kernel<<<n_tiles, 1024, 0, s>>>(in->d_hdr(), ctx->k1_slot_of.as<int>(), ctx->k1_first.as<int>(), ctx->k1_blk.as<int>());
+  PFT_LAUNCH_CHECK();
+  k1_tile_scan_kernel<<<1, 1024, 0, s>>>(n_tiles, ctx->k1_blk.as<int>(), out->d_hdr());
+  PFT_LAUNCH_CHECK();
+  k1_tile_assign_kernel<<<n_tiles, 1024, 0, s>>>(in->d_hdr(), ctx->k1_slot_of.as<int>(), ctx->k1_first.as<int>(), ctx->k1_blk.as<int>(),
+                                                 ctx->k1_vid.as<int>(), ctx->k1_acc_xyz.as<double>(), ctx->k1_acc_rgbc.as<unsigned int>());
   PFT_LAUNCH_CHECK();
   k1_accum_kernel<<<grid, 256, 0, s>>>(in->d_pts(), in->d_hdr(), ctx->k1_slot_of.as<int>(), ctx->k1_vid.as<int>(),
                                        ctx->k1_acc_xyz.as<double>(), ctx->k1_acc_rgbc.as<unsigned int>());
