@@ -1,0 +1,316 @@
+// pcl_shim.hpp -- header-only C++ classes with PCL's names over the C ABI of libpft.so.
+//
+// What a maintainer of cmaestre/pcl_tracking includes INSTEAD of the PCL tracking/filter headers
+// (ref: src/auto_tracking.cpp:38-109) so that initialize_trackers() (ref :181-259) and cloud_cb()
+// (ref :597-727) compile unchanged against the B200 tracker.  Only the surface that file drives is
+// provided; every method cites the reference line that calls it.
+//
+// The shim defines its own minimal pcl::PointXYZRGBA / pcl::PointCloud / ParticleXYZRPY when the PCL
+// headers are absent (as in this repository's build image).  With PCL present, define
+// PFT_SHIM_USE_PCL_TYPES before including it: the classes then live in namespace pft_pcl and take the
+// real PCL point/cloud types (both are the same 32-byte records).
+//
+// Errors: PCL's compute()/filter() return void and log with PCL_ERROR; here a failing C-ABI call
+// throws pft::Error (std::runtime_error) carrying pft_last_error().
+#ifndef PFT_PCL_SHIM_HPP_
+#define PFT_PCL_SHIM_HPP_
+
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "pft.h"
+
+namespace pft {
+
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const char* m) : std::runtime_error(std::string("pft error ") + std::to_string(c) + ": " + m), code(c) {}
+};
+inline void check(int rc) { if (rc != PFT_OK) throw Error(rc, pft_last_error()); }
+
+// Stand-in for Eigen::Affine3f where Eigen is not available: column-major 4x4, like Eigen's storage.
+struct Affine3f {
+  float m[16];
+  Affine3f() { setIdentity(); }
+  void setIdentity() { std::memset(m, 0, sizeof(m)); m[0] = m[5] = m[10] = m[15] = 1.f; }
+  static Affine3f Identity() { return Affine3f(); }
+  float& operator()(int r, int c) { return m[c * 4 + r]; }
+  float operator()(int r, int c) const { return m[c * 4 + r]; }
+  void translation(float x, float y, float z) { m[12] = x; m[13] = y; m[14] = z; }
+  const float* data() const { return m; }
+  float* data() { return m; }
+};
+
+// One context (device + stream) per process by default, like the implicit global state of a CPU library.
+class Context {
+ public:
+  explicit Context(int device = 0) { check(pft_context_create(device, &h_)); }
+  ~Context() { pft_context_destroy(h_); }
+  Context(const Context&) = delete;
+  Context& operator=(const Context&) = delete;
+  pft_context* get() const { return h_; }
+  void synchronize() { check(pft_context_synchronize(h_)); }
+  static std::shared_ptr<Context>& Default() {
+    static std::shared_ptr<Context> c;
+    if (!c) c = std::make_shared<Context>(0);
+    return c;
+  }
+ private:
+  pft_context* h_ = nullptr;
+};
+
+}  // namespace pft
+
+#ifndef PFT_SHIM_USE_PCL_TYPES
+namespace pcl {
+
+// the 32-byte pcl::PointXYZRGBA record (ref: src/auto_tracking.cpp:139-140)
+struct alignas(16) PointXYZRGBA {
+  float x = 0.f, y = 0.f, z = 0.f, data3 = 1.f;
+  union { struct { uint8_t b, g, r, a; }; uint32_t rgba; };
+  uint32_t pad_[3] = {0, 0, 0};
+  PointXYZRGBA() : rgba(0) {}
+};
+static_assert(sizeof(PointXYZRGBA) == 32, "PointXYZRGBA must be the 32-byte PCL record");
+
+// pcl::PointCloud<PointT>: host vector + a lazily synchronised device mirror
+template <typename PointT>
+class PointCloud {
+ public:
+  typedef std::shared_ptr<PointCloud<PointT>> Ptr;
+  typedef std::shared_ptr<const PointCloud<PointT>> ConstPtr;
+  std::vector<PointT> points;
+  uint32_t width = 0, height = 1;
+  bool is_dense = true;
+  size_t size() const { return device_only_ ? device_size() : points.size(); }
+  bool empty() const { return size() == 0; }
+  void push_back(const PointT& p) { points.push_back(p); host_dirty_ = true; device_only_ = false; }
+  void clear() { points.clear(); host_dirty_ = true; device_only_ = false; }
+  void touch() { host_dirty_ = true; device_only_ = false; }  // call after editing `points` in place
+
+  // ---- device side (used by the shim's filters/trackers)
+  pft_cloud* device(const std::shared_ptr<pft::Context>& ctx = pft::Context::Default()) const {
+    if (!dev_) { ctx_ = ctx; pft::check(pft_cloud_create(ctx_->get(), &dev_)); host_dirty_ = true; }
+    if (host_dirty_ && !device_only_) {
+      pft::check(pft_cloud_upload(dev_, points.data(), points.size(), PFT_LAYOUT_PCL32));
+      host_dirty_ = false;
+    }
+    return dev_;
+  }
+  // a filter wrote the device mirror: the host vector is stale until download()
+  void mark_device_written() { device_only_ = true; host_dirty_ = false; }
+  void download() {
+    if (!device_only_) return;
+    size_t n = device_size();
+    points.resize(n);
+    if (n) pft::check(pft_cloud_download(dev_, points.data(), n, PFT_LAYOUT_PCL32, &n));
+    width = (uint32_t)n; height = 1;
+    device_only_ = false; host_dirty_ = false;
+  }
+  ~PointCloud() { if (dev_) pft_cloud_destroy(dev_); }
+  PointCloud() = default;
+  PointCloud(const PointCloud& o) : points(o.host_points()), width(o.width), height(o.height), is_dense(o.is_dense) {}
+  PointCloud& operator=(const PointCloud& o) { points = o.host_points(); width = o.width; height = o.height; host_dirty_ = true; device_only_ = false; return *this; }
+
+ private:
+  size_t device_size() const { size_t n = 0; pft::check(pft_cloud_size(dev_, &n)); return n; }
+  const std::vector<PointT>& host_points() const { const_cast<PointCloud*>(this)->download(); return points; }
+  mutable pft_cloud* dev_ = nullptr;
+  mutable std::shared_ptr<pft::Context> ctx_;
+  mutable bool host_dirty_ = true;
+  mutable bool device_only_ = false;
+};
+
+// pcl::PassThrough (ref: src/auto_tracking.cpp:539-545)
+template <typename PointT>
+class PassThrough {
+ public:
+  void setFilterFieldName(const std::string& f) {
+    if (f == "x") field_ = 0; else if (f == "y") field_ = 1; else if (f == "z") field_ = 2;
+    else throw pft::Error(PFT_ERR_INVALID, "PassThrough: field must be x, y or z");
+  }
+  void setFilterLimits(float lo, float hi) { lo_ = lo; hi_ = hi; }
+  void setKeepOrganized(bool keep) { if (keep) throw pft::Error(PFT_ERR_INVALID, "setKeepOrganized(true) is not supported (ref :542 passes false)"); }
+  void setInputCloud(const typename PointCloud<PointT>::ConstPtr& c) { in_ = c; }
+  void filter(PointCloud<PointT>& out) {
+    auto& ctx = pft::Context::Default();
+    pft::check(pft_passthrough(ctx->get(), in_->device(ctx), out.device(ctx), field_, lo_, hi_));
+    out.mark_device_written();
+  }
+ private:
+  typename PointCloud<PointT>::ConstPtr in_;
+  int field_ = 2;
+  float lo_ = -3.4028235e38f, hi_ = 3.4028235e38f;
+};
+
+// pcl::VoxelGrid / pcl::ApproximateVoxelGrid (ref: src/auto_tracking.cpp:553-557, :568-571)
+template <typename PointT>
+class VoxelGrid {
+ public:
+  void setLeafSize(float lx, float ly, float lz) {
+    if (lx != ly || lx != lz) throw pft::Error(PFT_ERR_INVALID, "anisotropic leaf sizes are not supported (ref :555, :569 pass one size)");
+    leaf_ = lx;
+  }
+  void setInputCloud(const typename PointCloud<PointT>::ConstPtr& c) { in_ = c; }
+  void filter(PointCloud<PointT>& out) {
+    auto& ctx = pft::Context::Default();
+    pft::check(pft_passthrough_voxel_grid(ctx->get(), in_->device(ctx), out.device(ctx), leaf_, -1, 0.f, 0.f));
+    out.mark_device_written();
+  }
+ private:
+  typename PointCloud<PointT>::ConstPtr in_;
+  float leaf_ = 0.01f;
+};
+template <typename PointT> using ApproximateVoxelGrid = VoxelGrid<PointT>;
+
+namespace search {
+// pcl::search::Octree(resolution) (ref :250): the cell size of the uniform-grid index
+template <typename PointT> struct Octree { explicit Octree(double r) : resolution(r) {} double resolution; };
+}  // namespace search
+
+namespace tracking {
+
+// pcl::tracking::ParticleXYZRPY (ref :142): same 32-byte record as pft_particle
+struct ParticleXYZRPY {
+  float x = 0.f, y = 0.f, z = 0.f, one = 1.f, roll = 0.f, pitch = 0.f, yaw = 0.f, weight = 0.f;
+  // ParticleXYZRPY::toEigenMatrix (ref :310), evaluated by the same device routine weight() uses
+  pft::Affine3f toEigenMatrix() const {
+    float m12[12];
+    pft::check(pft_particle_to_matrix(pft::Context::Default()->get(), reinterpret_cast<const pft_particle*>(this), m12));
+    pft::Affine3f a;
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 4; ++c) a(r, c) = m12[r * 4 + c];
+    return a;
+  }
+};
+static_assert(sizeof(ParticleXYZRPY) == sizeof(pft_particle), "particle layout");
+
+template <typename PointT> struct PointCoherence { virtual ~PointCoherence() {} };
+// pcl::tracking::DistanceCoherence (ref :240-242)
+template <typename PointT> struct DistanceCoherence : PointCoherence<PointT> {
+  void setWeight(double w) { weight = w; }
+  double weight = 1.0;
+};
+// pcl::tracking::HSVColorCoherence (ref :244-247)
+template <typename PointT> struct HSVColorCoherence : PointCoherence<PointT> {
+  void setWeight(double w) { weight = w; }
+  void setHWeight(double w) { h_weight = w; }
+  void setSWeight(double w) { s_weight = w; }
+  void setVWeight(double w) { v_weight = w; }
+  double weight = 1.0, h_weight = 1.0, s_weight = 1.0, v_weight = 0.0;
+};
+// pcl::tracking::NearestPairPointCloudCoherence / ApproxNearestPairPointCloudCoherence (ref :235-238)
+template <typename PointT> struct NearestPairPointCloudCoherence {
+  typedef std::shared_ptr<NearestPairPointCloudCoherence<PointT>> Ptr;
+  void addPointCoherence(const std::shared_ptr<PointCoherence<PointT>>& c) { point_coherences.push_back(c); }
+  void setSearchMethod(const std::shared_ptr<pcl::search::Octree<PointT>>& s) { resolution = s->resolution; }
+  void setMaximumDistance(double d) { maximum_distance = d; }
+  std::vector<std::shared_ptr<PointCoherence<PointT>>> point_coherences;
+  double resolution = 0.01, maximum_distance = 1.79769313486231570815e308;
+};
+template <typename PointT> struct ApproxNearestPairPointCloudCoherence : NearestPairPointCloudCoherence<PointT> {};
+
+// pcl::tracking::ParticleFilterOMPTracker (ref :201-206)
+template <typename PointT, typename StateT>
+class ParticleFilterOMPTracker {
+ public:
+  typedef std::shared_ptr<PointCloud<StateT>> PointCloudStatePtr;
+  explicit ParticleFilterOMPTracker(unsigned int nr_threads = 0) : ParticleFilterOMPTracker(nr_threads, 0) {}
+  virtual ~ParticleFilterOMPTracker() { pft_tracker_destroy(h_); }
+  void setNumberOfThreads(unsigned int n) { si(PFT_THREADS, (int)n); }
+  void setTrans(const pft::Affine3f& t) {  // ref :225, :674
+    float m12[12];
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 4; ++c) m12[r * 4 + c] = t(r, c);
+    pft::check(pft_tracker_set_trans(h_, m12));
+  }
+  void setStepNoiseCovariance(const std::vector<double>& v) { sv(PFT_STEP_NOISE_COV, v); }        // ref :226
+  void setInitialNoiseCovariance(const std::vector<double>& v) { sv(PFT_INIT_NOISE_COV, v); }     // ref :227
+  void setInitialNoiseMean(const std::vector<double>& v) { sv(PFT_INIT_NOISE_MEAN, v); }          // ref :228
+  void setIterationNum(int n) { si(PFT_ITERATION_NUM, n); }                                       // ref :229
+  void setParticleNum(int n) { si(PFT_PARTICLE_NUM, n); }                                         // ref :231
+  void setResampleLikelihoodThr(double v) { sd(PFT_RESAMPLE_LIKELIHOOD_THR, v); }                 // ref :232
+  void setUseNormal(bool u) { si(PFT_USE_NORMAL, u ? 1 : 0); }                                    // ref :233
+  void setMinIndices(int n) { si(PFT_MIN_INDICES, n); }                                           // ref :676
+  void setAlpha(double a) { sd(PFT_ALPHA, a); }
+  void setMotionRatio(double r) { sd(PFT_MOTION_RATIO, r); }
+  void setCloudCoherence(const typename NearestPairPointCloudCoherence<PointT>::Ptr& c) {         // ref :254
+    int use_d = 0, use_h = 0;
+    for (auto& pc : c->point_coherences) {
+      if (auto* d = dynamic_cast<DistanceCoherence<PointT>*>(pc.get())) { use_d = 1; sd(PFT_DIST_WEIGHT, d->weight); }
+      else if (auto* hsv = dynamic_cast<HSVColorCoherence<PointT>*>(pc.get())) {
+        use_h = 1; sd(PFT_HSV_WEIGHT, hsv->weight); sd(PFT_H_WEIGHT, hsv->h_weight); sd(PFT_S_WEIGHT, hsv->s_weight); sd(PFT_V_WEIGHT, hsv->v_weight);
+      } else throw pft::Error(PFT_ERR_INVALID, "unsupported point coherence");
+    }
+    si(PFT_USE_DISTANCE, use_d); si(PFT_USE_HSV, use_h); si(PFT_NN_MODE, PFT_NN_EXACT);
+    sd(PFT_MAX_DIST, c->maximum_distance); sd(PFT_SEARCH_RESOLUTION, c->resolution);
+    coherence_ = c;
+  }
+  template <typename CoherenceT> void setCloudCoherence(const std::shared_ptr<CoherenceT>& c) {
+    setCloudCoherence(std::static_pointer_cast<NearestPairPointCloudCoherence<PointT>>(c));
+  }
+  void setReferenceCloud(const typename PointCloud<PointT>::ConstPtr& c) {                        // ref :673
+    ref_ = c;
+    pft::check(pft_tracker_set_reference_cloud(h_, c->device()));
+  }
+  typename PointCloud<PointT>::ConstPtr getReferenceCloud() const { return ref_; }
+  void setInputCloud(const typename PointCloud<PointT>::ConstPtr& c) {                            // ref :691
+    input_ = c;
+    pft::check(pft_tracker_set_input_cloud(h_, c ? c->device() : nullptr));
+  }
+  void compute() { pft::check(pft_tracker_compute(h_)); }                                        // ref :693
+  StateT getResult() const {                                                                      // ref :309
+    StateT s;
+    pft::check(pft_tracker_get_result(h_, reinterpret_cast<pft_particle*>(&s)));
+    return s;
+  }
+  PointCloudStatePtr getParticles() const {                                                       // ref :270
+    auto out = std::make_shared<PointCloud<StateT>>();
+    size_t n = 0;
+    int rc = pft_tracker_get_particles(h_, nullptr, 0, &n);
+    if (rc != PFT_OK && rc != PFT_ERR_CAPACITY) pft::check(rc);
+    out->points.resize(n);
+    if (n) pft::check(pft_tracker_get_particles(h_, reinterpret_cast<pft_particle*>(out->points.data()), n, &n));
+    return out;
+  }
+  void resetTracking() { pft::check(pft_tracker_reset(h_)); }
+  double getFitRatio() const { double v = 0; pft::check(pft_tracker_get_fit_ratio(h_, &v)); return v; }
+  pft_tracker* handle() const { return h_; }
+
+ protected:
+  ParticleFilterOMPTracker(unsigned int nr_threads, int kld) {
+    pft::check(pft_tracker_create(pft::Context::Default()->get(), kld, &h_));
+    si(PFT_THREADS, (int)nr_threads);
+  }
+  void si(int k, int v) { pft::check(pft_tracker_set_i(h_, k, v)); }
+  void sd(int k, double v) { pft::check(pft_tracker_set_d(h_, k, v)); }
+  void sv(int k, const std::vector<double>& v) {
+    if (v.size() != 6) throw pft::Error(PFT_ERR_INVALID, "expected 6 values");
+    pft::check(pft_tracker_set_vec6(h_, k, v.data()));
+  }
+  pft_tracker* h_ = nullptr;
+  typename PointCloud<PointT>::ConstPtr ref_, input_;
+  typename NearestPairPointCloudCoherence<PointT>::Ptr coherence_;
+};
+
+// pcl::tracking::KLDAdaptiveParticleFilterOMPTracker (ref :209-222)
+template <typename PointT, typename StateT>
+class KLDAdaptiveParticleFilterOMPTracker : public ParticleFilterOMPTracker<PointT, StateT> {
+ public:
+  explicit KLDAdaptiveParticleFilterOMPTracker(unsigned int nr_threads = 0) : ParticleFilterOMPTracker<PointT, StateT>(nr_threads, 1) {}
+  void setMaximumParticleNum(unsigned int n) { this->si(PFT_MAX_PARTICLE_NUM, (int)n); }          // ref :211
+  void setDelta(double d) { this->sd(PFT_DELTA, d); }                                            // ref :212
+  void setEpsilon(double e) { this->sd(PFT_EPSILON, e); }                                        // ref :213
+  void setBinSize(const StateT& b) {                                                              // ref :214-221
+    this->sv(PFT_BIN_SIZE, {b.x, b.y, b.z, b.roll, b.pitch, b.yaw});
+  }
+};
+
+}  // namespace tracking
+}  // namespace pcl
+#endif  // PFT_SHIM_USE_PCL_TYPES
+
+#endif  // PFT_PCL_SHIM_HPP_

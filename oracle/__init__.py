@@ -83,6 +83,8 @@ def lib():
             "orc_update": (None, [vp]),
             "orc_compute": (None, [vp]),
             "orc_get_aabb": (None, [vp, vp]),
+            "orc_get_local_aabb": (None, [vp, vp]),
+            "orc_set_crop_box": (None, [vp, vp]),
             "orc_get_cropped": (i, [vp, vp, vp, i]),
             "orc_get_nn": (i, [vp, i, vp, vp, i]),
             "orc_get_raw_weights": (i, [vp, vp, i]),
@@ -326,6 +328,18 @@ class Tracker:
         a = np.zeros(6, dtype=np.float32)
         lib().orc_get_aabb(self._h, _p(a))
         return a
+
+    def local_aabb(self):
+        a = np.zeros(6, dtype=np.float32)
+        lib().orc_get_local_aabb(self._h, _p(a))
+        return a
+
+    def set_crop_box(self, box6):
+        if box6 is None:
+            lib().orc_set_crop_box(self._h, None)
+        else:
+            a = np.ascontiguousarray(box6, dtype=np.float32)
+            lib().orc_set_crop_box(self._h, _p(a))
 
     def cropped(self):
         n = lib().orc_get_cropped(self._h, None, None, 0)

@@ -663,6 +663,9 @@ struct Tracker {
   std::vector<std::vector<Pt>> transed;
   std::vector<std::array<float, 6>> slot_aabb;  // minx,miny,minz,maxx,maxy,maxz; empty slot = (+FLT_MAX, -FLT_MAX)
   float aabb[6] = {0, 0, 0, 0, 0, 0};
+  float local_aabb[6] = {0, 0, 0, 0, 0, 0};  // union box of this tracker's own slots (before any override)
+  bool crop_override = false;       // multi-rank emulation: the crop box is the union over ranks, supplied from outside
+  float crop_override_box[6] = {0, 0, 0, 0, 0, 0};
   std::vector<Pt> cropped; std::vector<int> cropped_idx;
   std::vector<float> raw_weights;
   std::vector<int> last_ancestors;
@@ -912,6 +915,8 @@ void weight(Tracker& T, std::vector<int>* nn_out /*optional: [N*M] NN index into
     for (int d = 0; d < 3; ++d) { if (bb[d] > a[d]) bb[d] = a[d]; if (bb[3 + d] < a[3 + d]) bb[3 + d] = a[3 + d]; }
   }
   for (int d = 0; d < 6; ++d) T.aabb[d] = (float)bb[d];
+  for (int d = 0; d < 6; ++d) T.local_aabb[d] = T.aabb[d];
+  if (T.crop_override) for (int d = 0; d < 6; ++d) T.aabb[d] = T.crop_override_box[d];
   {
     // three PassThrough passes x -> y -> z, inclusive limits, order preserving
     std::vector<Pt> a(T.input.size()), b(T.input.size());
@@ -1137,6 +1142,12 @@ void orc_compute(orc_tracker* t) {
   compute(t->T);
 }
 void orc_get_aabb(orc_tracker* t, float* a6) { std::memcpy(a6, t->T.aabb, sizeof(float) * 6); }
+void orc_get_local_aabb(orc_tracker* t, float* a6) { std::memcpy(a6, t->T.local_aabb, sizeof(float) * 6); }
+// multi-rank emulation (tests): weight() crops with this box instead of the union of its own slots; NULL switches it off
+void orc_set_crop_box(orc_tracker* t, const float* a6) {
+  t->T.crop_override = a6 != nullptr;
+  if (a6) std::memcpy(t->T.crop_override_box, a6, sizeof(float) * 6);
+}
 int orc_get_cropped(orc_tracker* t, int* idx, orc_point* pts, int cap) {
   int n = std::min<int>(cap, (int)t->T.cropped.size());
   for (int i = 0; i < n; ++i) { if (idx) idx[i] = t->T.cropped_idx[i]; if (pts) pts[i] = t->T.cropped[i]; }
