@@ -120,7 +120,8 @@ struct pft_tracker {
   const pft_cloud* input = nullptr;
   size_t scene_cap = 0; // allocated index capacity (scene points)
   int max_cells = 1 << 20;  // cap of the index grid; a larger crop box gets coarser cells
-  int index_level = 1;      // cell edge of the index = search resolution x 2^level (internal; results do not depend on it)
+  int index_level = -1;     // cell edge of the index = search resolution x 2^level (internal; results do not depend on it);
+                            // -1: chosen per weight() from the nearest-neighbour distances of the previous one
   int cur = 0;          // live particle buffer
   int inj_slots = 0, inj_stride = 0;
   int draw_cap = 0;
@@ -495,7 +496,7 @@ int weight_phase_eval(pft_tracker* t) {
   PFT_LAUNCH_CHECK();
   index_count_kernel<<<gscene, 256, 0, s>>>(in->d_pts(), in->d_hdr(), hdr, t->icount.as<int>());
   PFT_LAUNCH_CHECK();
-  index_scan_kernel<<<1, 1024, 0, s>>>(hdr, t->icount.as<int>(), t->cell_start.as<int>());
+  index_scan_kernel<<<1, 1024, 0, s>>>(hdr, t->icount.as<int>(), t->cell_start.as<int>(), st);
   PFT_LAUNCH_CHECK();
   index_scatter_kernel<<<gscene, 256, 0, s>>>(in->d_pts(), in->d_hdr(), hdr, t->cell_start.as<int>(), t->icount.as<int>(), t->ipts.as<float4>(),
                                               t->ihsv.as<unsigned int>());

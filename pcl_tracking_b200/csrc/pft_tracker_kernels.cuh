@@ -26,6 +26,9 @@ struct TrackerState {
   double fit_ratio;
   double weight_sum;
   unsigned long long draw_call;  // Philox stream position (advanced on the device: graph replays stay distinct)
+  // nearest-neighbour distance statistics of the last weight() (micrometres, matched pairs only): they steer the
+  // cell size of the next index build.  Integer sums: independent of the order the atomics land in.
+  unsigned long long nn_sum_um, nn_count;
 };
 
 struct NoiseParams {      // host-precomputed square roots (IEEE, identical to the oracle's)
@@ -275,10 +278,20 @@ __device__ inline void compute_index_header(const float* aabb, float inv_leaf, i
 
 // Every block derives the header from the crop box (a pure function of it), block 0 publishes it, and all
 // blocks clear the per-cell counters.
+// base_level < 0: choose the cell edge from the mean nearest-neighbour distance of the previous weight() (a query
+// that is d away from the surface walks ~pi (d/cell + 1)^2 rows and ~(d + cell)^2 candidates: cell ~ d balances them)
 __global__ void index_begin_kernel(const TrackerState* __restrict__ st, IndexHeader* hdr, int* cell_count, float inv_leaf, int base_level,
                                    int max_cells) {
   __shared__ IndexHeader h;
   if (threadIdx.x == 0) {
+    if (base_level < 0) {
+      base_level = 1;
+      if (st->nn_count > 0) {
+        const float mean_d = (float)((double)st->nn_sum_um / (double)st->nn_count) * 1.0e-6f;
+        const float want = mean_d * 1.15f * inv_leaf;  // cell edge in units of the resolution
+        base_level = want <= 1.5f ? 1 : (want <= 3.0f ? 1 : (want <= 6.0f ? 2 : (want <= 12.0f ? 3 : 4)));
+      }
+    }
     compute_index_header(st->aabb, inv_leaf, base_level, max_cells, h);
     if (blockIdx.x == 0) *hdr = h;
   }
@@ -317,9 +330,11 @@ __global__ void index_count_kernel(const float4* __restrict__ scene, const Cloud
 }
 
 // exclusive prefix of the cell counts -> cell_start; the counters are cleared again (they become the fill cursors)
-__global__ void __launch_bounds__(1024) index_scan_kernel(const IndexHeader* __restrict__ hdr, int* cell_count, int* __restrict__ cell_start) {
+__global__ void __launch_bounds__(1024) index_scan_kernel(const IndexHeader* __restrict__ hdr, int* cell_count, int* __restrict__ cell_start,
+                                                          TrackerState* st) {
   __shared__ int smem[34];
   const int nc = hdr->n_cells;
+  if (threadIdx.x == 0) { st->nn_sum_um = 0ull; st->nn_count = 0ull; }  // consumed by index_begin; refilled by the weight kernel
   const int total = block_exclusive_scan<int>(
       nc, [&](int i) { return cell_count[i]; }, [&](int i, int ex) { cell_start[i] = ex; cell_count[i] = 0; }, smem);
   if (threadIdx.x == 0) cell_start[nc] = total;
@@ -362,14 +377,26 @@ constexpr int kRT = 11;                         // table reach in cells (Chebysh
 constexpr int kRows = (2 * kRT + 1) * (2 * kRT + 1);
 struct RowEntry { signed char dy, dz; unsigned short lb2; };  // lb2 = gap(dy)^2 + gap(dz)^2, gap(d) = max(|d|-1, 0)
 
-struct NNResult { int slot; int orig; float d2; };
+// Best candidate so far: (bits of d2) << 32 | input index packed in one 64-bit word (two registers), plus its slot.
+struct NNResult {
+  unsigned long long key;
+  int slot;
+  __device__ __forceinline__ float d2() const { return __uint_as_float((unsigned int)(key >> 32)); }
+  __device__ __forceinline__ int orig() const { return (int)(unsigned int)key; }
+};
+__device__ __forceinline__ NNResult nn_none(float lim2) {
+  return NNResult{(unsigned long long)__float_as_uint(lim2) << 32, -1};  // only d2 < lim2 can beat it
+}
 
 __device__ __forceinline__ void nn_eval(const float4* __restrict__ pts, int slot, float qx, float qy, float qz, NNResult& best) {
   const float4 p = pts[slot];
   const float dx = qx - p.x, dy = qy - p.y, dz = qz - p.z;
   const float d2 = (dx * dx + dy * dy) + dz * dz;
-  const int orig = __float_as_int(p.w);
-  if (d2 < best.d2 || (d2 == best.d2 && orig < best.orig)) { best.d2 = d2; best.slot = slot; best.orig = orig; }
+  const float bd = best.d2();
+  if (d2 < bd || (d2 == bd && __float_as_int(p.w) < best.orig())) {
+    best.key = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned long long)__float_as_uint(p.w);
+    best.slot = slot;
+  }
 }
 
 // distance (cell units) from the query at fractional position t of its cell to the cell at offset d, minus a
@@ -390,7 +417,7 @@ __device__ __noinline__ NNResult nn_search_shells(const CS* __restrict__ cs, con
     const float done = ((float)r_prev + tmin - 2.5e-4f) * h.cell;  // everything unscanned is farther than this
     const bool covered = (cx - r_prev <= 0) && (cx + r_prev >= h.dim[0] - 1) && (cy - r_prev <= 0) && (cy + r_prev >= h.dim[1] - 1) &&
                          (cz - r_prev <= 0) && (cz + r_prev >= h.dim[2] - 1);
-    if (covered || done * done * 0.9999f > fminf(best.d2, lim2)) return best;
+    if (covered || done * done * 0.9999f > fminf(best.d2(), lim2)) return best;
     const int z0 = max(cz - r, 0), z1 = min(cz + r, h.dim[2] - 1);
     const int y0 = max(cy - r, 0), y1 = min(cy + r, h.dim[1] - 1);
     for (int z = z0; z <= z1; ++z) {
@@ -399,7 +426,7 @@ __device__ __noinline__ NNResult nn_search_shells(const CS* __restrict__ cs, con
       for (int y = y0; y <= y1; ++y) {
         const int dy = y - cy;
         const float ay = axis_gap(dy, ty);
-        if ((az * az + ay * ay) * cell2 * 0.9999f > best.d2) continue;
+        if ((az * az + ay * ay) * cell2 * 0.9999f > best.d2()) continue;
         const int base = (z * h.dim[1] + y) * h.dim[0];
         const bool inner = max(abs(dy), abs(dz)) <= r_prev;
         for (int seg = 0; seg < 2; ++seg) {
@@ -416,7 +443,7 @@ __device__ __noinline__ NNResult nn_search_shells(const CS* __restrict__ cs, con
     }
     r_prev = r;
     int need = 2 * r;
-    if (best.slot >= 0) need = max(r + 1, (int)ceilf(sqrtf(best.d2) / h.cell - tmin + 0.004f));
+    if (best.slot >= 0) need = max(r + 1, (int)ceilf(sqrtf(best.d2()) / h.cell - tmin + 0.004f));
     const int rcap = max(r + 1, (int)ceilf(sqrtf(lim2) / h.cell - tmin + 0.004f));
     r = min(need, rcap);
   }
@@ -425,7 +452,7 @@ __device__ __noinline__ NNResult nn_search_shells(const CS* __restrict__ cs, con
 template <typename CS>
 __device__ __forceinline__ NNResult nn_search(const CS* __restrict__ cs, const float4* __restrict__ pts, const IndexHeader& h,
                                               const RowEntry* __restrict__ table, float qx, float qy, float qz, float lim2) {
-  NNResult best{-1, 0x7fffffff, lim2};
+  NNResult best = nn_none(lim2);
   const float sx = (qx * h.inv_leaf) * h.level_scale, sy = (qy * h.inv_leaf) * h.level_scale, sz = (qz * h.inv_leaf) * h.level_scale;
   const float fx = floorf(sx), fy = floorf(sy), fz = floorf(sz);
   // (int) of a huge float is undefined: clamp first; such queries are far outside the grid anyway
@@ -439,15 +466,15 @@ __device__ __forceinline__ NNResult nn_search(const CS* __restrict__ cs, const f
   PFT_STAT(6, 1);
   for (int k = 0; k < kRows; ++k) {
     const RowEntry e = table[k];
-    if ((float)e.lb2 * cell2 * 0.9999f > best.d2) break;  // every later row is at least this far
+    if ((float)e.lb2 * cell2 * 0.9999f > best.d2()) break;  // every later row is at least this far
     PFT_STAT(7, 1);
     const int y = cy + e.dy, z = cz + e.dz;
     if ((unsigned)y >= (unsigned)dimy || (unsigned)z >= (unsigned)dimz) continue;
     const float ay = axis_gap(e.dy, ty), az = axis_gap(e.dz, tz);
     const float row2 = (ay * ay + az * az) * cell2 * 0.9999f;
-    if (row2 > best.d2) continue;
+    if (row2 > best.d2()) continue;
     // cells of this row that can still hold a point at distance <= best: |x gap| <= hw (cell units)
-    const float hw = fminf(sqrtf(best.d2 - row2) * inv_cell + 5.0e-4f, (float)kRT);
+    const float hw = fminf(sqrtf(best.d2() - row2) * inv_cell + 5.0e-4f, (float)kRT);
     int xa = cx + (int)ceilf(tx - 1.0f - hw), xb = cx + (int)floorf(tx + hw);
     xa = max(xa, 0); xb = min(xb, dimx - 1);
     if (xa > xb) continue;
@@ -457,12 +484,12 @@ __device__ __forceinline__ NNResult nn_search(const CS* __restrict__ cs, const f
     for (int s = (int)cs[base + xa]; s < s1; ++s) { PFT_STAT(9, 1); nn_eval(pts, s, qx, qy, qz, best); }
   }
   // rows outside the table start at a distance of kRT cells: only then can the search have missed something
-  if (best.d2 > (float)(kRT * kRT) * cell2 * 0.99f) best = nn_search_shells<CS>(cs, pts, h, qx, qy, qz, cx, cy, cz, tx, ty, tz, lim2, best);
+  if (best.d2() > (float)(kRT * kRT) * cell2 * 0.99f) best = nn_search_shells<CS>(cs, pts, h, qx, qy, qz, cx, cy, cz, tx, ty, tz, lim2, best);
   return best;
 }
 
 struct WeightArgs {
-  const TrackerState* st;
+  TrackerState* st;
   const IndexHeader* hdr;
   const int* cell_start;      // [n_cells + 1]
   const float4* pts;          // {x, y, z, input index} in cell order
@@ -504,23 +531,27 @@ __device__ __forceinline__ void weight_items(const WeightArgs& a, const IndexHea
     }
     const int j0 = c * a.chunk_len, j1 = min(a.M, j0 + a.chunk_len);
     double val = 0.0;
+    unsigned int sum_um = 0, matched = 0;
     for (int j = j0 + lane; j < j1; j += 32) {
       const float4 mp = a.model[j];
       float qx, qy, qz;
       xform(m, mp.x, mp.y, mp.z, qx, qy, qz);
-      NNResult nn{-1, 0x7fffffff, lim2};
+      NNResult nn = nn_none(lim2);
       if (h.n_cropped > 0) nn = nn_search<CS>(cs, pts, h, table, qx, qy, qz, lim2);
       if (i < a.dbg_k) {
         const size_t o = (size_t)i * a.M + a.model_perm[j];
-        a.dbg_idx[o] = nn.slot >= 0 ? nn.orig : -1;
-        a.dbg_d2[o] = nn.slot >= 0 ? nn.d2 : FLT_MAX;
+        a.dbg_idx[o] = nn.slot >= 0 ? nn.orig() : -1;
+        a.dbg_d2[o] = nn.slot >= 0 ? nn.d2() : FLT_MAX;
       }
-      if (nn.slot >= 0 && (double)nn.d2 < a.co.max_d2) {
+      if (nn.slot >= 0 && (double)nn.d2() < a.co.max_d2) {
         // DistanceCoherence x HSVColorCoherence: 1/(1+d^2 w_d) * 1/(1+w_h diff) evaluated as one fp64 reciprocal of
         // the product of the denominators (differs from the product of reciprocals by ~1 ulp of fp64)
         double den = 1.0;
+        const float df = sqrtf(nn.d2());
+        sum_um += (unsigned int)fminf(df * 1.0e6f, 1.0e8f);
+        ++matched;
         if (a.co.use_dist) {
-          const double d = (double)sqrtf(nn.d2);
+          const double d = (double)df;
           den = 1.0 + d * d * a.co.dist_w;
         }
         if (USE_HSV) {
@@ -541,7 +572,12 @@ __device__ __forceinline__ void weight_items(const WeightArgs& a, const IndexHea
       }
     }
     val = warp_sum(val);
-    if (lane == 0) a.partial[(size_t)c * a.n_max + i] = val;
+    sum_um = (unsigned int)warp_sum((int)sum_um);  // <= 32 x chunk_len/32 x 1e8 um would overflow: chunk sums stay far below (d <= maximum distance)
+    matched = (unsigned int)warp_sum((int)matched);
+    if (lane == 0) {
+      a.partial[(size_t)c * a.n_max + i] = val;
+      if (matched) { atomicAdd(&a.st->nn_sum_um, (unsigned long long)sum_um); atomicAdd(&a.st->nn_count, (unsigned long long)matched); }
+    }
   }
 }
 
