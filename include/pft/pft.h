@@ -106,6 +106,8 @@ typedef enum {
   PFT_USE_NORMAL = 9,         /* setUseNormal: only 0 is supported (ref :233) */
   PFT_MIN_INDICES = 10,       /* setMinIndices: accepted, inert without normals (ref :676) */
   PFT_DEBUG_NN = 11,          /* record per-point NN indices for the first K particles of weight() */
+  PFT_CANDIDATE_LISTS = 12,   /* exact-NN lookup tables per weight(): 0 never, 1 when they pay off (default), 2 always.
+                                 Internal to the search: results are identical in all three modes. */
   /* double keys */
   PFT_DELTA = 20,             /* setDelta                 (ref :212) */
   PFT_EPSILON = 21,           /* setEpsilon               (ref :213) */
@@ -189,7 +191,7 @@ PFT_API int pft_tracker_get_nn(pft_tracker* t, int particle, int32_t* idx, float
 PFT_API int pft_tracker_get_timing(pft_tracker* t, float* weight_kernel_ms, float* compute_ms);
 PFT_API int pft_tracker_enable_timing(pft_tracker* t, int on);
 
-/* dims[3], level (cell edge = resolution x 2^level), n_cropped, n_cells, 0, 0 of the scene index built by the last weight() */
+/* dims[3], level (cell edge = resolution x 2^level), n_cropped, n_cells, use_lists, list_cells of the scene index built by the last weight() */
 PFT_API int pft_tracker_get_index_info(pft_tracker* t, int* info8);
 /* number of compute() calls served by replaying the captured CUDA graph */
 PFT_API int pft_tracker_graph_replays(pft_tracker* t, uint64_t* n);

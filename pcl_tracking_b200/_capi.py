@@ -21,7 +21,7 @@ LAYOUT_PACKED16, LAYOUT_PCL32 = 0, 1
 OK, ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_CAPACITY, ERR_COMM = 0, -1, -2, -3, -4, -5
 
 # pft_key
-THREADS, PARTICLE_NUM, MAX_PARTICLE_NUM, ITERATION_NUM, NN_MODE, USE_HSV, USE_DISTANCE, SAMPLER, QUAT_SAMPLE, USE_NORMAL, MIN_INDICES, DEBUG_NN = range(12)
+THREADS, PARTICLE_NUM, MAX_PARTICLE_NUM, ITERATION_NUM, NN_MODE, USE_HSV, USE_DISTANCE, SAMPLER, QUAT_SAMPLE, USE_NORMAL, MIN_INDICES, DEBUG_NN, CANDIDATE_LISTS = range(13)
 (DELTA, EPSILON, ALPHA, MOTION_RATIO, MAX_DIST, DIST_WEIGHT, HSV_WEIGHT, H_WEIGHT, S_WEIGHT, V_WEIGHT, SEARCH_RESOLUTION,
  RESAMPLE_LIKELIHOOD_THR) = range(20, 32)
 STEP_NOISE_COV, INIT_NOISE_COV, INIT_NOISE_MEAN, BIN_SIZE = range(40, 44)

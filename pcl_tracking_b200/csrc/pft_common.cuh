@@ -57,6 +57,11 @@ struct IndexHeader {
   float inv_leaf;     // 1 / resolution  (lattice = floor((coord * inv_leaf) * 2^-level))
   float level_scale;  // 2^-level
   int valid;          // 0: empty AABB (no model / no particles)
+  // candidate lists: one list of index slots per cell of the FINE lattice (edge = resolution) over the crop box
+  int f_origin[3];    // fine lattice coordinate of fine cell (0,0,0)
+  int f_dim[3];
+  int f_cells;        // f_dim[0] * f_dim[1] * f_dim[2]
+  int use_lists;      // lists are built and used by this weight() (enough queries to amortise the build)
 };
 
 // ------------------------------------------------------------------ device helpers

@@ -120,6 +120,8 @@ struct pft_tracker {
   const pft_cloud* input = nullptr;
   size_t scene_cap = 0; // allocated index capacity (scene points)
   int max_cells = 1 << 20;  // cap of the index grid; a larger crop box gets coarser cells
+  int list_mode = 1;             // PFT_CANDIDATE_LISTS
+  int list_max_cells = 1 << 19;  // fine cells the candidate lists are sized for (kListK x 2 B each); 0 disables the lists
   int index_level = -1;     // cell edge of the index = search resolution x 2^level (internal; results do not depend on it);
                             // -1: chosen per weight() from the nearest-neighbour distances of the previous one
   int cur = 0;          // live particle buffer
@@ -143,7 +145,7 @@ struct pft_tracker {
   int graph_nodes = 0;
   // device buffers
   DevBuf st, parts[2], mats, slot_aabb, model, model_perm, model_tmp, sort_keys, sort_idx, bbox, raw, partial, cdf, cdf_total, ancestors, bin_keys, tbl_rep,
-      tbl_min, slot_of, klb, d_usel, d_normals, d_umot, idx_hdr, cell_start, ipts, ihsv, icount, dbg_idx, dbg_d2, d_trans, row_table;
+      tbl_min, slot_of, klb, d_usel, d_normals, d_umot, idx_hdr, cell_start, ipts, ihsv, icount, dbg_idx, dbg_d2, d_trans, row_table, fcount, flists, fneeded, fneeded_list, xlists, xcount;
   int weight_smem = 0;  // dynamic shared memory of the weight kernel (bytes)
   int tbl_size = 0;
   int n_slots = 0;
@@ -160,7 +162,7 @@ void release_all(pft_tracker* t) {
   DevBuf* bufs[] = {&t->st, &t->parts[0], &t->parts[1], &t->mats, &t->slot_aabb, &t->model, &t->model_perm, &t->model_tmp, &t->sort_keys, &t->sort_idx,
                     &t->bbox, &t->raw, &t->partial, &t->cdf, &t->cdf_total, &t->ancestors, &t->bin_keys, &t->tbl_rep, &t->tbl_min, &t->slot_of, &t->klb,
                     &t->d_usel, &t->d_normals, &t->d_umot, &t->idx_hdr, &t->cell_start, &t->ipts, &t->ihsv, &t->icount, &t->dbg_idx,
-                    &t->dbg_d2, &t->d_trans, &t->row_table};
+                    &t->dbg_d2, &t->d_trans, &t->row_table, &t->fcount, &t->flists, &t->fneeded, &t->fneeded_list, &t->xlists, &t->xcount};
   for (auto* b : bufs) b->release();
 }
 
@@ -258,6 +260,14 @@ int ensure_particle_buffers(pft_tracker* t) {
     if ((rc = t->cell_start.reserve(((size_t)t->max_cells + 16) * sizeof(int)))) return rc;
     if ((rc = t->icount.reserve(((size_t)t->max_cells + 16) * sizeof(int)))) return rc;
     if ((rc = upload_row_table(t))) return rc;
+    if (t->list_max_cells > 0) {
+      if ((rc = t->fcount.reserve(((size_t)t->list_max_cells + 16) * sizeof(unsigned short)))) return rc;
+      if ((rc = t->flists.reserve(((size_t)t->list_max_cells + 1) * kListK * sizeof(unsigned short)))) return rc;
+      if ((rc = t->fneeded.reserve(((size_t)t->list_max_cells + 16) * sizeof(unsigned int)))) return rc;
+      if ((rc = t->fneeded_list.reserve(((size_t)t->list_max_cells + 16) * sizeof(int)))) return rc;
+      if ((rc = t->xlists.reserve((size_t)kListXCells * kListKX * sizeof(unsigned short)))) return rc;
+      if ((rc = t->xcount.reserve(64))) return rc;
+    }
   }
   if (cap == t->n_cap) return PFT_OK;
   invalidate_graph(t);
@@ -492,7 +502,8 @@ int weight_phase_eval(pft_tracker* t) {
   IndexHeader* hdr = t->idx_hdr.as<IndexHeader>();
   const float inv_leaf = 1.0f / (float)t->search_res;
   const int gscene = blocks_for(ncap_scene, 256, sm * 4);
-  index_begin_kernel<<<sm, 256, 0, s>>>(st, hdr, t->icount.as<int>(), inv_leaf, t->index_level, t->max_cells);
+  index_begin_kernel<<<sm, 256, 0, s>>>(st, hdr, t->icount.as<int>(), inv_leaf, t->index_level, t->max_cells, t->list_mode ? t->list_max_cells : 0,
+                                        t->list_mode == 2 ? 0 : t->M, t->nranks, t->rank, t->fneeded.as<unsigned int>(), t->xcount.as<int>());
   PFT_LAUNCH_CHECK();
   index_count_kernel<<<gscene, 256, 0, s>>>(in->d_pts(), in->d_hdr(), hdr, t->icount.as<int>());
   PFT_LAUNCH_CHECK();
@@ -501,8 +512,17 @@ int weight_phase_eval(pft_tracker* t) {
   index_scatter_kernel<<<gscene, 256, 0, s>>>(in->d_pts(), in->d_hdr(), hdr, t->cell_start.as<int>(), t->icount.as<int>(), t->ipts.as<float4>(),
                                               t->ihsv.as<unsigned int>());
   PFT_LAUNCH_CHECK();
+  if (t->list_max_cells > 0 && t->list_mode) {
+    cand_mark_kernel<<<sm * 4, 256, 0, s>>>(st, hdr, t->model.as<float4>(), t->M, t->mats.as<float>(), t->fneeded.as<unsigned int>(),
+                                           t->fneeded_list.as<int>(), t->xcount.as<int>(), t->nranks, t->rank);
+    PFT_LAUNCH_CHECK();
+    cand_build_kernel<<<sm * 8, 256, 0, s>>>(hdr, t->cell_start.as<int>(), t->ipts.as<float4>(), t->max_dist * t->max_dist, t->fcount.as<unsigned short>(), t->flists.as<unsigned short>(),
+                                            t->fneeded_list.as<int>(), t->xlists.as<unsigned short>(), t->xcount.as<int>());
+    PFT_LAUNCH_CHECK();
+  }
   WeightArgs a;
   a.st = st; a.hdr = hdr;
+  a.fcount = t->fcount.as<unsigned short>(); a.flists = t->flists.as<unsigned short>(); a.xlists = t->xlists.as<unsigned short>();
   a.cell_start = t->cell_start.as<int>(); a.pts = t->ipts.as<float4>();
   a.hsv = t->ihsv.as<unsigned int>(); a.table = t->row_table.as<RowEntry>(); a.smem_bytes = t->weight_smem;
   a.model = t->model.as<float4>(); a.model_perm = t->model_perm.as<int>(); a.M = t->M;
@@ -615,6 +635,8 @@ int pft_tracker_create(pft_context* ctx, int kld, pft_tracker** out) {
   t->graph_enabled = !(ng && ng[0] == '1');
   const char* il = getenv("PFT_INDEX_LEVEL");  // tuning: cell edge of the index = resolution x 2^level
   if (il && il[0] >= '0' && il[0] <= '9') t->index_level = il[0] - '0';
+  const char* nl = getenv("PFT_NO_LISTS");  // tuning: row-table search only
+  if (nl && nl[0] == '1') t->list_mode = 0;
   *out = t;
   return PFT_OK;
 }
@@ -657,6 +679,9 @@ int pft_tracker_set_i(pft_tracker* t, int key, int v) {
       if (v != 0) { set_last_error("setUseNormal(true) is not supported (the reference runs with false, src/auto_tracking.cpp:233)"); return PFT_ERR_INVALID; }
       break;
     case PFT_MIN_INDICES: t->min_indices = v; break;
+    case PFT_CANDIDATE_LISTS:
+      if (v < 0 || v > 2) { set_last_error("PFT_CANDIDATE_LISTS must be 0, 1 or 2"); return PFT_ERR_INVALID; }
+      t->list_mode = v; break;
     case PFT_DEBUG_NN:
       if (v < 0) { set_last_error("PFT_DEBUG_NN must be >= 0"); return PFT_ERR_INVALID; }
       t->debug_nn = v; break;
@@ -1063,7 +1088,7 @@ int pft_tracker_get_index_info(pft_tracker* t, int* info8) {
   PFT_CUDA_TRY(cudaStreamSynchronize(s));
   const IndexHeader* h = reinterpret_cast<IndexHeader*>(t->ctx->pinned);
   info8[0] = h->dim[0]; info8[1] = h->dim[1]; info8[2] = h->dim[2]; info8[3] = h->level;
-  info8[4] = h->n_cropped; info8[5] = h->n_cells; info8[6] = 0; info8[7] = 0;
+  info8[4] = h->n_cropped; info8[5] = h->n_cells; info8[6] = h->use_lists; info8[7] = h->f_cells;
   return PFT_OK;
 }
 

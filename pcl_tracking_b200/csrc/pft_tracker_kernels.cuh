@@ -253,10 +253,23 @@ __device__ inline void compute_index_header(const float* aabb, float inv_leaf, i
   h.level = base_level; h.level_scale = 1.0f; h.n_cells = 0;
   h.dim[0] = h.dim[1] = h.dim[2] = 0; h.origin[0] = h.origin[1] = h.origin[2] = 0;
   h.cell = 1.0f / inv_leaf;
+  h.f_cells = 0; h.use_lists = 0;
+  h.f_origin[0] = h.f_origin[1] = h.f_origin[2] = 0; h.f_dim[0] = h.f_dim[1] = h.f_dim[2] = 0;
   if (!h.valid) return;
   float lo[3], hi[3];
 #pragma unroll
   for (int d = 0; d < 3; ++d) { lo[d] = aabb[d] * inv_leaf; hi[d] = aabb[3 + d] * inv_leaf; }
+  {
+    long long fc = 1;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      h.f_origin[d] = (int)floorf(lo[d]);
+      h.f_dim[d] = (int)floorf(hi[d]) - h.f_origin[d] + 1;
+      fc *= (long long)h.f_dim[d];
+      if (fc > (1ll << 30)) fc = 1ll << 30;
+    }
+    h.f_cells = (int)fc;
+  }
   for (int level = base_level; level < 24; ++level) {
     const float ls = 1.0f / (float)(1 << level);
     int dim[3], org[3];
@@ -281,7 +294,8 @@ __device__ inline void compute_index_header(const float* aabb, float inv_leaf, i
 // base_level < 0: choose the cell edge from the mean nearest-neighbour distance of the previous weight() (a query
 // that is d away from the surface walks ~pi (d/cell + 1)^2 rows and ~(d + cell)^2 candidates: cell ~ d balances them)
 __global__ void index_begin_kernel(const TrackerState* __restrict__ st, IndexHeader* hdr, int* cell_count, float inv_leaf, int base_level,
-                                   int max_cells) {
+                                   int max_cells, int list_max_cells, int M, int nranks, int rank, unsigned int* needed_words,
+                                   int* list_counters /* [0] extended lists handed out, [1] needed cells */) {
   __shared__ IndexHeader h;
   if (threadIdx.x == 0) {
     if (base_level < 0) {
@@ -293,11 +307,20 @@ __global__ void index_begin_kernel(const TrackerState* __restrict__ st, IndexHea
       }
     }
     compute_index_header(st->aabb, inv_leaf, base_level, max_cells, h);
+    // candidate lists pay off when this rank's queries outnumber the fine cells they are built for
+    const int n = st->particle_num;
+    const long long n_local = n > rank ? (n - rank + nranks - 1) / nranks : 0;
+    // (M == 0: the caller forces the lists on)
+    h.use_lists = (h.valid && h.f_cells > 0 && h.f_cells <= list_max_cells && (M == 0 || n_local * (long long)M >= 2ll * h.f_cells)) ? 1 : 0;
     if (blockIdx.x == 0) *hdr = h;
   }
   __syncthreads();
   const int nc = h.n_cells + 1;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nc; i += gridDim.x * blockDim.x) cell_count[i] = 0;
+  if (h.use_lists) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < h.f_cells; i += gridDim.x * blockDim.x) needed_words[i] = 0u;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) { list_counters[0] = 0; list_counters[1] = 0; }
 }
 
 __device__ __forceinline__ bool in_crop(const float4& p, const IndexHeader& h) {
@@ -488,6 +511,256 @@ __device__ __forceinline__ NNResult nn_search(const CS* __restrict__ cs, const f
   return best;
 }
 
+// ---- candidate lists: the exact nearest neighbour as a table lookup.
+// For every cell c of the fine lattice (edge = resolution) the build stores the slots of ALL points that can be the
+// nearest neighbour of SOME query inside c: with p0 the point nearest to the centre of c and U = maxdist(c, p0), any
+// query q in c has |q - NN(q)| <= |q - p0| <= U, hence mindist(c, NN(q)) <= U; the list is {p : mindist(c, p) <= U}
+// (ties included), cut at maximum_distance_.  A query then scans one short list instead of walking the grid.  Cells
+// whose list would not fit kListK entries are marked and their queries use the row-table search.
+constexpr int kListK = 128;                        // entries of a regular list
+constexpr int kListKX = 1024;                      // entries of an extended list (cells far from the surface)
+constexpr int kListXCells = 8192;                  // extended lists available per build
+constexpr unsigned short kListOverflow = 0xffffu;  // no list: use the row-table search
+constexpr unsigned short kListExtended = 0xfffeu;  // list[0..1] = index of the extended list, list[2] = its length
+
+__device__ __forceinline__ float box_mindist2(const float* lo, const float* hi, const float4& p) {
+  const float dx = fmaxf(fmaxf(lo[0] - p.x, p.x - hi[0]), 0.f), dy = fmaxf(fmaxf(lo[1] - p.y, p.y - hi[1]), 0.f),
+              dz = fmaxf(fmaxf(lo[2] - p.z, p.z - hi[2]), 0.f);
+  return (dx * dx + dy * dy) + dz * dz;
+}
+__device__ __forceinline__ float box_maxdist2(const float* lo, const float* hi, const float4& p) {
+  const float dx = fmaxf(fabsf(p.x - lo[0]), fabsf(p.x - hi[0])), dy = fmaxf(fabsf(p.y - lo[1]), fabsf(p.y - hi[1])),
+              dz = fmaxf(fabsf(p.z - lo[2]), fabsf(p.z - hi[2]));
+  return (dx * dx + dy * dy) + dz * dz;
+}
+
+// collects the fine cells that this rank's queries fall into (the lists of the others are never read)
+__global__ void cand_mark_kernel(const TrackerState* __restrict__ st, const IndexHeader* __restrict__ hdr, const float4* __restrict__ model, int M,
+                                 const float* __restrict__ mats, unsigned int* __restrict__ needed, int* __restrict__ needed_list,
+                                 int* __restrict__ list_counters, int nranks, int rank) {
+  __shared__ IndexHeader h;
+  if (threadIdx.x == 0) h = *hdr;
+  __syncthreads();
+  if (!h.valid || !h.use_lists) return;
+  const int n = st->particle_num;
+  const int n_local = n > rank ? (n - rank + nranks - 1) / nranks : 0;
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int l = warp; l < n_local; l += nwarps) {
+    const int i = rank + l * nranks;
+    float m[12];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const float4 r = reinterpret_cast<const float4*>(mats)[(size_t)i * 3 + d];
+      m[4 * d] = r.x; m[4 * d + 1] = r.y; m[4 * d + 2] = r.z; m[4 * d + 3] = r.w;
+    }
+    for (int j = lane; j < M; j += 32) {
+      const float4 p = model[j];
+      float qx, qy, qz;
+      xform(m, p.x, p.y, p.z, qx, qy, qz);
+      const float big = 1.0e9f;
+      const int ix = (int)fminf(fmaxf(floorf(qx * h.inv_leaf), -big), big) - h.f_origin[0], iy = (int)fminf(fmaxf(floorf(qy * h.inv_leaf), -big), big) - h.f_origin[1],
+                iz = (int)fminf(fmaxf(floorf(qz * h.inv_leaf), -big), big) - h.f_origin[2];
+      if ((unsigned)ix < (unsigned)h.f_dim[0] && (unsigned)iy < (unsigned)h.f_dim[1] && (unsigned)iz < (unsigned)h.f_dim[2]) {
+        const int cell = (iz * h.f_dim[1] + iy) * h.f_dim[0] + ix;
+        if (needed[cell] == 0u && atomicExch(&needed[cell], 1u) == 0u) needed_list[atomicAdd(&list_counters[1], 1)] = cell;
+      }
+    }
+  }
+}
+
+// One warp builds the list of one needed cell.
+// (1) U = min over nearby points p of maxdist(cell, p): an upper bound of the nearest-neighbour distance of every
+//     query of the cell (the tightest one when the minimiser lies in the probed block, a valid one always).
+// (2) every point whose distance to the cell does not exceed U is appended (the ball is walked row by row).
+// Both steps run over "the points of a set of rows" flattened across the warp: each lane fetches the slot range of
+// one row, a warp scan turns the counts into offsets, and the 32 lanes then take consecutive points of the
+// concatenation (binary search of the offsets in shared memory), so every lane is busy whatever the row lengths.
+struct RowSpan { int s0, cnt; };
+
+template <typename RowFn, typename PointFn>
+__device__ __forceinline__ void warp_points_of_rows(int nrows, int* __restrict__ s_pref, int* __restrict__ s_start, RowFn row_span, PointFn fn) {
+  const int lane = threadIdx.x & 31;
+  for (int rbase = 0; rbase < nrows; rbase += 32) {
+    RowSpan sp{0, 0};
+    if (rbase + lane < nrows) sp = row_span(rbase + lane);
+    int inc = sp.cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(kFull, inc, o); if (lane >= o) inc += t; }
+    const int total = __shfl_sync(kFull, inc, 31);
+    s_pref[lane] = inc - sp.cnt;
+    s_start[lane] = sp.s0;
+    __syncwarp();
+    for (int t = lane; t < total; t += 32) {
+      int r = 0;
+#pragma unroll
+      for (int step = 16; step > 0; step >>= 1) if (s_pref[r + step] <= t) r += step;  // last row whose offset is <= t
+      fn(s_start[r] + (t - s_pref[r]));
+    }
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(256) cand_build_kernel(const IndexHeader* __restrict__ hdr, const int* __restrict__ cs,
+                                                         const float4* __restrict__ pts, double max_d2,
+                                                         unsigned short* __restrict__ fcount, unsigned short* __restrict__ flists,
+                                                         const int* __restrict__ needed_list, unsigned short* __restrict__ xlists,
+                                                         int* __restrict__ list_counters) {
+  __shared__ IndexHeader h;
+  __shared__ int s_cnt[8];
+  __shared__ int s_pref[8][33], s_start[8][32];
+  if (threadIdx.x == 0) h = *hdr;
+  __syncthreads();
+  if (!h.valid || !h.use_lists) return;
+  const int n_needed = list_counters[1];
+  const float leaf = 1.0f / h.inv_leaf;
+  const float margin = 1.0e-5f + 4.0e-6f * leaf * (float)(abs(h.f_origin[0]) + abs(h.f_origin[1]) + abs(h.f_origin[2]) + h.f_dim[0] + h.f_dim[1] + h.f_dim[2]);
+  const float r_max = max_d2 >= 1.0e30 ? 1.0e15f : (float)sqrt(max_d2) * 1.00001f;
+  const int fdx = h.f_dim[0], fdy = h.f_dim[1];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  const float cell_m = h.cell;
+  const int dimx = h.dim[0], dimy = h.dim[1], dimz = h.dim[2];
+  int* pref = s_pref[wib];
+  int* start = s_start[wib];
+  if (lane == 0) pref[32] = 0x7fffffff;  // sentinel for the binary search
+  for (int idx = warp; idx < n_needed; idx += nwarps) {
+    const int cell = needed_list[idx];
+    const int fz = cell / (fdx * fdy), r2 = cell - fz * fdx * fdy, fy = r2 / fdx, fx = r2 - fy * fdx;
+    // the cell in metric space, widened by the rounding of q * inv_leaf near its faces
+    float lo[3], hi[3];
+    lo[0] = (float)(h.f_origin[0] + fx) * leaf - margin; hi[0] = (float)(h.f_origin[0] + fx + 1) * leaf + margin;
+    lo[1] = (float)(h.f_origin[1] + fy) * leaf - margin; hi[1] = (float)(h.f_origin[1] + fy + 1) * leaf + margin;
+    lo[2] = (float)(h.f_origin[2] + fz) * leaf - margin; hi[2] = (float)(h.f_origin[2] + fz + 1) * leaf + margin;
+    // coarse cell of the centre of the box
+    int cc[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) cc[d] = (int)floorf(((0.5f * (lo[d] + hi[d])) * h.inv_leaf) * h.level_scale) - h.origin[d];
+    // ---- (1) U: probe growing blocks of coarse cells around the cell until one holds a point.  The fine cell lies
+    // inside coarse cell cc, so a block of radius rad without any point means: no point within rad coarse cells.
+    float U2 = 3.0e38f;
+    bool no_match = false;
+    for (int rad = 1; rad <= 8; rad = rad < 2 ? 2 : rad + 2) {
+      const int x0 = max(cc[0] - rad, 0), x1 = min(cc[0] + rad, dimx - 1);
+      const int y0 = max(cc[1] - rad, 0), y1 = min(cc[1] + rad, dimy - 1);
+      const int z0 = max(cc[2] - rad, 0), z1 = min(cc[2] + rad, dimz - 1);
+      float m2 = 3.0e38f;
+      if (x0 <= x1 && y0 <= y1 && z0 <= z1) {
+        const int ny = y1 - y0 + 1;
+        warp_points_of_rows(
+            ny * (z1 - z0 + 1), pref, start,
+            [&](int r) { const int zz = r / ny; const int base = ((z0 + zz) * dimy + (y0 + r - zz * ny)) * dimx; const int a = cs[base + x0]; return RowSpan{a, cs[base + x1 + 1] - a}; },
+            [&](int s) { m2 = fminf(m2, box_maxdist2(lo, hi, pts[s])); });
+        m2 = warp_min(m2);
+      }
+      if (m2 < 3.0e38f) { U2 = m2 * 1.00002f; break; }
+      if ((float)rad * cell_m * 0.999f - 4.0f * margin > r_max) { no_match = true; break; }  // farther than maximum_distance_ from everything
+    }
+    if (U2 >= 3.0e38f) {
+      // provably no point within maximum_distance_ of any query of the cell (empty list), or the probe gave up (the
+      // queries of this cell use the row-table search)
+      if (lane == 0) fcount[cell] = no_match ? (unsigned short)0 : kListOverflow;
+      continue;
+    }
+    U2 = fminf(U2, r_max * r_max);
+    const float reach = sqrtf(U2) * 1.00001f;
+    // ---- (2) gather: rows of coarse cells that intersect the ball-dilated box
+    int c0[3], c1[3];
+#pragma unroll
+    for (int d = 1; d < 3; ++d) {
+      c0[d] = max((int)floorf(((lo[d] - reach) * h.inv_leaf) * h.level_scale) - 1 - h.origin[d], 0);
+      c1[d] = min((int)floorf(((hi[d] + reach) * h.inv_leaf) * h.level_scale) + 1 - h.origin[d], h.dim[d] - 1);
+    }
+    const int ny = c1[1] - c0[1] + 1, nrows = max(ny, 0) * max(c1[2] - c0[2] + 1, 0);
+    unsigned short* list = flists + (size_t)cell * kListK;
+    unsigned short* xl = nullptr;
+    int cap = kListK;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+      if (lane == 0) s_cnt[wib] = 0;
+      __syncwarp();
+      unsigned short* dst = attempt ? xl : list;
+      warp_points_of_rows(
+          nrows, pref, start,
+          [&](int r) {
+            const int zz = r / ny, y = c0[1] + (r - zz * ny), z = c0[2] + zz;
+            const float zlo = (float)(z + h.origin[2]) * cell_m - 2.0f * margin, zhi = (float)(z + 1 + h.origin[2]) * cell_m + 2.0f * margin;
+            const float gz = fmaxf(fmaxf(lo[2] - zhi, zlo - hi[2]), 0.f);
+            const float ylo = (float)(y + h.origin[1]) * cell_m - 2.0f * margin, yhi = (float)(y + 1 + h.origin[1]) * cell_m + 2.0f * margin;
+            const float gy = fmaxf(fmaxf(lo[1] - yhi, ylo - hi[1]), 0.f);
+            const float rem = U2 - (gy * gy + gz * gz) * 0.9999f;
+            if (rem < 0.f) return RowSpan{0, 0};
+            const float xr = sqrtf(rem) * 1.00001f + 2.0f * margin;
+            const int xa = max((int)floorf(((lo[0] - xr) * h.inv_leaf) * h.level_scale) - 1 - h.origin[0], 0);
+            const int xb = min((int)floorf(((hi[0] + xr) * h.inv_leaf) * h.level_scale) + 1 - h.origin[0], dimx - 1);
+            if (xa > xb) return RowSpan{0, 0};
+            const int base = (z * dimy + y) * dimx;
+            const int a = cs[base + xa];
+            return RowSpan{a, cs[base + xb + 1] - a};
+          },
+          [&](int s) {
+            if (box_mindist2(lo, hi, pts[s]) <= U2) {
+              const int pos = atomicAdd(&s_cnt[wib], 1);
+              if (pos < cap) dst[pos] = (unsigned short)s;
+            }
+          });
+      __syncwarp();
+      const int n = s_cnt[wib];
+      __syncwarp();
+      if (n <= cap) {
+        if (lane == 0) {
+          if (!attempt) fcount[cell] = (unsigned short)n;
+          else { list[2] = (unsigned short)n; fcount[cell] = kListExtended; }
+        }
+        break;
+      }
+      // does not fit: take an extended list and gather again into it (rare: cells far from the surface)
+      int xi = -1;
+      if (!attempt && n <= kListKX) {
+        if (lane == 0) xi = atomicAdd(&list_counters[0], 1);
+        xi = __shfl_sync(kFull, xi, 0);
+      }
+      if (xi < 0 || xi >= kListXCells) { if (lane == 0) fcount[cell] = kListOverflow; break; }
+      xl = xlists + (size_t)xi * kListKX;
+      cap = kListKX;
+      if (lane == 0) { list[0] = (unsigned short)(xi & 0xffff); list[1] = (unsigned short)(xi >> 16); }
+    }
+    PFT_STAT(15, lane == 0 ? 1 : 0);
+  }
+}
+
+// Query through the candidate lists; returns false when the row-table search has to be used instead.
+__device__ __forceinline__ bool nn_lookup(const IndexHeader& h, const unsigned short* __restrict__ fcount, const unsigned short* __restrict__ flists,
+                                          const unsigned short* __restrict__ xlists, const float4* __restrict__ pts, float qx, float qy, float qz,
+                                          float lim2, NNResult& best) {
+  const float fx = floorf(qx * h.inv_leaf), fy = floorf(qy * h.inv_leaf), fz = floorf(qz * h.inv_leaf);
+  const float big = 1.0e9f;
+  const int ix = (int)fminf(fmaxf(fx, -big), big) - h.f_origin[0], iy = (int)fminf(fmaxf(fy, -big), big) - h.f_origin[1],
+            iz = (int)fminf(fmaxf(fz, -big), big) - h.f_origin[2];
+  if ((unsigned)ix >= (unsigned)h.f_dim[0] || (unsigned)iy >= (unsigned)h.f_dim[1] || (unsigned)iz >= (unsigned)h.f_dim[2]) return false;
+  const int cell = (iz * h.f_dim[1] + iy) * h.f_dim[0] + ix;
+  int cnt = fcount[cell];
+  PFT_STAT(12, 1);
+  if (cnt == kListOverflow) { PFT_STAT(13, 1); return false; }
+  const unsigned short* lst = flists + (size_t)cell * kListK;
+  if (cnt == kListExtended) {
+    const int xi = (int)lst[0] | ((int)lst[1] << 16);
+    cnt = lst[2];
+    lst = xlists + (size_t)xi * kListKX;
+  }
+  PFT_STAT(14, cnt);
+  best = nn_none(lim2);
+  const uint4* l4 = reinterpret_cast<const uint4*>(lst);
+  for (int b = 0; b < cnt; b += 8) {
+    const uint4 v = l4[b >> 3];
+    const unsigned int w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (b + k < cnt) nn_eval(pts, (int)((w[k >> 1] >> ((k & 1) * 16)) & 0xffffu), qx, qy, qz, best);
+    }
+  }
+  return true;
+}
+
 struct WeightArgs {
   TrackerState* st;
   const IndexHeader* hdr;
@@ -495,6 +768,9 @@ struct WeightArgs {
   const float4* pts;          // {x, y, z, input index} in cell order
   const unsigned int* hsv;    // packed HSV of every slot
   const RowEntry* table;      // kRows entries sorted by lb2
+  const unsigned short* fcount;  // candidate lists (see cand_build_kernel): per fine cell count and kListK slots
+  const unsigned short* flists;
+  const unsigned short* xlists;  // extended lists
   const float4* model;        // {x,y,z,hsv} in tile order
   const int* model_perm;      // tile order -> order of the reference cloud as given
   int M;
@@ -537,7 +813,9 @@ __device__ __forceinline__ void weight_items(const WeightArgs& a, const IndexHea
       float qx, qy, qz;
       xform(m, mp.x, mp.y, mp.z, qx, qy, qz);
       NNResult nn = nn_none(lim2);
-      if (h.n_cropped > 0) nn = nn_search<CS>(cs, pts, h, table, qx, qy, qz, lim2);
+      if (h.n_cropped > 0) {
+        if (!(h.use_lists && nn_lookup(h, a.fcount, a.flists, a.xlists, pts, qx, qy, qz, lim2, nn))) nn = nn_search<CS>(cs, pts, h, table, qx, qy, qz, lim2);
+      }
       if (i < a.dbg_k) {
         const size_t o = (size_t)i * a.M + a.model_perm[j];
         a.dbg_idx[o] = nn.slot >= 0 ? nn.orig() : -1;

@@ -422,6 +422,10 @@ class ParticleFilterOMPTracker:
     def setQuaternionSampling(self, on):
         self._si(capi.QUAT_SAMPLE, 1 if on else 0)
 
+    def setCandidateLists(self, mode):
+        """0 never, 1 automatic, 2 always (internal to the search; results do not depend on it)."""
+        self._si(capi.CANDIDATE_LISTS, mode)
+
     def setDebugNN(self, k):
         self._si(capi.DEBUG_NN, k)
 
@@ -479,7 +483,7 @@ class ParticleFilterOMPTracker:
     def indexInfo(self):
         a = np.zeros(8, dtype=np.int32)
         check(capi.load().pft_tracker_get_index_info(self._h, ptr(a)))
-        return dict(zip(("dim_x", "dim_y", "dim_z", "level", "n_cropped", "n_cells"), a.tolist()[:6]))
+        return dict(zip(("dim_x", "dim_y", "dim_z", "level", "n_cropped", "n_cells", "use_lists", "list_cells"), a.tolist()))
 
     def rawWeights(self):
         n = C.c_size_t()

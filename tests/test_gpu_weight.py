@@ -14,7 +14,10 @@ pytestmark = pytest.mark.gpu
 W_RTOL = 1e-5
 
 
-def _run_weight(seed, use_hsv, n_scene=4000, n_model=300, n_particles=48, max_dist=0.1, sigma_t=0.015, search_res=0.01, dbg=8):
+LIST_MODES = [0, 2]  # exact-NN candidate lists: never / always -- results must not depend on it
+
+
+def _run_weight(seed, use_hsv, n_scene=4000, n_model=300, n_particles=48, max_dist=0.1, sigma_t=0.015, search_res=0.01, dbg=8, lists=1):
     scene, model, centre = util.small_case(seed, n_scene=n_scene, n_model=n_model)
     g, o = util.make_pair(kld=False, particle_num=n_particles, use_hsv=use_hsv, max_dist=max_dist, search_res=search_res)
     parts = util.particles_around(centre, n_particles, seed=seed + 100, sigma_t=sigma_t)
@@ -23,7 +26,9 @@ def _run_weight(seed, use_hsv, n_scene=4000, n_model=300, n_particles=48, max_di
     g.setInputCloud(cloud)
     g.setParticles(parts)
     g.setDebugNN(dbg)
+    g.setCandidateLists(lists)
     g.weight()
+    assert g.indexInfo()["use_lists"] == (1 if lists == 2 else 0)
     o.set_reference(model)
     o.set_input(scene)
     o.set_particles(parts)
@@ -31,9 +36,10 @@ def _run_weight(seed, use_hsv, n_scene=4000, n_model=300, n_particles=48, max_di
     return g, o, scene, model
 
 
+@pytest.mark.parametrize("lists", LIST_MODES)
 @pytest.mark.parametrize("seed,use_hsv", [(0, False), (1, True), (2, True)])
-def test_weight_matches_oracle(seed, use_hsv):
-    g, o, scene, model = _run_weight(seed, use_hsv)
+def test_weight_matches_oracle(seed, use_hsv, lists):
+    g, o, scene, model = _run_weight(seed, use_hsv, lists=lists)
     # crop box and crop count: bit-exact
     np.testing.assert_array_equal(g.aabb(), o.aabb())
     cidx, _ = o.cropped()
@@ -55,9 +61,10 @@ def test_weight_matches_oracle(seed, use_hsv):
     assert abs(g.getFitRatio() - o.fit_ratio()) <= 1e-5 * abs(o.fit_ratio())
 
 
-def test_weight_large_max_distance_all_indices_exact():
+@pytest.mark.parametrize("lists", LIST_MODES)
+def test_weight_large_max_distance_all_indices_exact(lists):
     # maximum distance larger than the scene: every model point has a match; all indices must agree
-    g, o, scene, model = _run_weight(5, True, n_scene=1500, n_model=120, n_particles=16, max_dist=10.0, sigma_t=0.05, dbg=16)
+    g, o, scene, model = _run_weight(5, True, n_scene=1500, n_model=120, n_particles=16, max_dist=10.0, sigma_t=0.05, dbg=16, lists=lists)
     cidx, _ = o.cropped()
     for p in range(16):
         gi, gd = g.nn(p, len(model))
@@ -67,11 +74,13 @@ def test_weight_large_max_distance_all_indices_exact():
     np.testing.assert_allclose(g.rawWeights(), o.raw_weights(), rtol=W_RTOL)
 
 
-def test_weight_ties_go_to_lower_index():
+@pytest.mark.parametrize("lists", LIST_MODES)
+def test_weight_ties_go_to_lower_index(lists):
     # duplicated scene points: the same coordinates at two indices; the lower index must win
     scene, model, centre = util.small_case(7, n_scene=800, n_model=100)
     scene = np.concatenate([scene, scene[::-1]])  # every point appears twice
     g, o = util.make_pair(kld=False, particle_num=8, use_hsv=False)
+    g.setCandidateLists(lists)
     parts = util.particles_around(centre, 8, seed=3)
     cloud = pcl.PointCloud(scene)
     g.setReferenceCloud(model); g.setInputCloud(cloud); g.setParticles(parts); g.setDebugNN(8); g.weight()
@@ -86,9 +95,10 @@ def test_weight_ties_go_to_lower_index():
     np.testing.assert_allclose(g.rawWeights(), o.raw_weights(), rtol=W_RTOL)
 
 
-def test_weight_coarse_and_fine_cells():
+@pytest.mark.parametrize("lists", LIST_MODES)
+def test_weight_coarse_and_fine_cells(lists):
     for res in (0.005, 0.02, 0.05):
-        g, o, scene, model = _run_weight(11, True, n_scene=2500, n_model=150, n_particles=12, search_res=res, dbg=4)
+        g, o, scene, model = _run_weight(11, True, n_scene=2500, n_model=150, n_particles=12, search_res=res, dbg=4, lists=lists)
         np.testing.assert_allclose(g.rawWeights(), o.raw_weights(), rtol=W_RTOL)
 
 
