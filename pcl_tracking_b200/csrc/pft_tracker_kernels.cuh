@@ -354,13 +354,17 @@ __global__ void index_count_kernel(const float4* __restrict__ scene, const Cloud
 
 // exclusive prefix of the cell counts -> cell_start; the counters are cleared again (they become the fill cursors)
 __global__ void __launch_bounds__(1024) index_scan_kernel(const IndexHeader* __restrict__ hdr, int* cell_count, int* __restrict__ cell_start,
-                                                          TrackerState* st) {
+                                                          TrackerState* st, float4* __restrict__ pts) {
   __shared__ int smem[34];
   const int nc = hdr->n_cells;
   if (threadIdx.x == 0) { st->nn_sum_um = 0ull; st->nn_count = 0ull; }  // consumed by index_begin; refilled by the weight kernel
   const int total = block_exclusive_scan<int>(
       nc, [&](int i) { return cell_count[i]; }, [&](int i, int ex) { cell_start[i] = ex; cell_count[i] = 0; }, smem);
-  if (threadIdx.x == 0) cell_start[nc] = total;
+  if (threadIdx.x == 0) {
+    cell_start[nc] = total;
+    // slot `total` is a dummy point infinitely far away: candidate lists are padded with it to a multiple of 8 entries
+    pts[total] = make_float4(3.0e38f, 3.0e38f, 3.0e38f, __int_as_float(0x7fffffff));
+  }
 }
 
 __global__ void index_scatter_kernel(const float4* __restrict__ scene, const CloudHeader* __restrict__ scene_hdr, const IndexHeader* __restrict__ hdr,
@@ -400,26 +404,22 @@ constexpr int kRT = 11;                         // table reach in cells (Chebysh
 constexpr int kRows = (2 * kRT + 1) * (2 * kRT + 1);
 struct RowEntry { signed char dy, dz; unsigned short lb2; };  // lb2 = gap(dy)^2 + gap(dz)^2, gap(d) = max(|d|-1, 0)
 
-// Best candidate so far: (bits of d2) << 32 | input index packed in one 64-bit word (two registers), plus its slot.
+// Best candidate so far.  Ties in distance go to the lower input index.
 struct NNResult {
-  unsigned long long key;
+  float dist2;
+  int orig_idx;
   int slot;
-  __device__ __forceinline__ float d2() const { return __uint_as_float((unsigned int)(key >> 32)); }
-  __device__ __forceinline__ int orig() const { return (int)(unsigned int)key; }
+  __device__ __forceinline__ float d2() const { return dist2; }
+  __device__ __forceinline__ int orig() const { return orig_idx; }
 };
-__device__ __forceinline__ NNResult nn_none(float lim2) {
-  return NNResult{(unsigned long long)__float_as_uint(lim2) << 32, -1};  // only d2 < lim2 can beat it
-}
+__device__ __forceinline__ NNResult nn_none(float lim2) { return NNResult{lim2, (int)0x80000000, -1}; }  // only d2 < lim2 can beat it
 
 __device__ __forceinline__ void nn_eval(const float4* __restrict__ pts, int slot, float qx, float qy, float qz, NNResult& best) {
   const float4 p = pts[slot];
   const float dx = qx - p.x, dy = qy - p.y, dz = qz - p.z;
   const float d2 = (dx * dx + dy * dy) + dz * dz;
-  const float bd = best.d2();
-  if (d2 < bd || (d2 == bd && __float_as_int(p.w) < best.orig())) {
-    best.key = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned long long)__float_as_uint(p.w);
-    best.slot = slot;
-  }
+  const int orig = __float_as_int(p.w);
+  if (d2 < best.dist2 || (d2 == best.dist2 && orig < best.orig_idx)) { best.dist2 = d2; best.orig_idx = orig; best.slot = slot; }
 }
 
 // distance (cell units) from the query at fractional position t of its cell to the cell at offset d, minus a
@@ -522,6 +522,8 @@ constexpr int kListKX = 1024;                      // entries of an extended lis
 constexpr int kListXCells = 8192;                  // extended lists available per build
 constexpr unsigned short kListOverflow = 0xffffu;  // no list: use the row-table search
 constexpr unsigned short kListExtended = 0xfffeu;  // list[0..1] = index of the extended list, list[2] = its length
+// list entries are 16-bit slots (+ the dummy slot n_cropped): larger crops use the row-table search only
+__device__ __forceinline__ bool lists_on(const IndexHeader& h) { return h.use_lists && h.n_cropped < 65535; }
 
 __device__ __forceinline__ float box_mindist2(const float* lo, const float* hi, const float4& p) {
   const float dx = fmaxf(fmaxf(lo[0] - p.x, p.x - hi[0]), 0.f), dy = fmaxf(fmaxf(lo[1] - p.y, p.y - hi[1]), 0.f),
@@ -541,12 +543,15 @@ __global__ void cand_mark_kernel(const TrackerState* __restrict__ st, const Inde
   __shared__ IndexHeader h;
   if (threadIdx.x == 0) h = *hdr;
   __syncthreads();
-  if (!h.valid || !h.use_lists) return;
+  if (!h.valid || !lists_on(h)) return;
   const int n = st->particle_num;
   const int n_local = n > rank ? (n - rank + nranks - 1) / nranks : 0;
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-  for (int l = warp; l < n_local; l += nwarps) {
+  const int jchunks = (M + 31) >> 5;
+  const long long items = (long long)n_local * jchunks;  // one warp-item = 32 consecutive model points of one particle
+  for (long long it = warp; it < items; it += nwarps) {
+    const int l = (int)(it / jchunks), j = (int)(it - (long long)l * jchunks) * 32 + lane;
     const int i = rank + l * nranks;
     float m[12];
 #pragma unroll
@@ -554,7 +559,7 @@ __global__ void cand_mark_kernel(const TrackerState* __restrict__ st, const Inde
       const float4 r = reinterpret_cast<const float4*>(mats)[(size_t)i * 3 + d];
       m[4 * d] = r.x; m[4 * d + 1] = r.y; m[4 * d + 2] = r.z; m[4 * d + 3] = r.w;
     }
-    for (int j = lane; j < M; j += 32) {
+    if (j < M) {
       const float4 p = model[j];
       float qx, qy, qz;
       xform(m, p.x, p.y, p.z, qx, qy, qz);
@@ -611,7 +616,7 @@ __global__ void __launch_bounds__(256) cand_build_kernel(const IndexHeader* __re
   __shared__ int s_pref[8][33], s_start[8][32];
   if (threadIdx.x == 0) h = *hdr;
   __syncthreads();
-  if (!h.valid || !h.use_lists) return;
+  if (!h.valid || !lists_on(h)) return;
   const int n_needed = list_counters[1];
   const float leaf = 1.0f / h.inv_leaf;
   const float margin = 1.0e-5f + 4.0e-6f * leaf * (float)(abs(h.f_origin[0]) + abs(h.f_origin[1]) + abs(h.f_origin[2]) + h.f_dim[0] + h.f_dim[1] + h.f_dim[2]);
@@ -632,18 +637,19 @@ __global__ void __launch_bounds__(256) cand_build_kernel(const IndexHeader* __re
     lo[0] = (float)(h.f_origin[0] + fx) * leaf - margin; hi[0] = (float)(h.f_origin[0] + fx + 1) * leaf + margin;
     lo[1] = (float)(h.f_origin[1] + fy) * leaf - margin; hi[1] = (float)(h.f_origin[1] + fy + 1) * leaf + margin;
     lo[2] = (float)(h.f_origin[2] + fz) * leaf - margin; hi[2] = (float)(h.f_origin[2] + fz + 1) * leaf + margin;
-    // coarse cell of the centre of the box
-    int cc[3];
-#pragma unroll
-    for (int d = 0; d < 3; ++d) cc[d] = (int)floorf(((0.5f * (lo[d] + hi[d])) * h.inv_leaf) * h.level_scale) - h.origin[d];
-    // ---- (1) U: probe growing blocks of coarse cells around the cell until one holds a point.  The fine cell lies
-    // inside coarse cell cc, so a block of radius rad without any point means: no point within rad coarse cells.
+    // coarse cells overlapping the box dilated by r.  floor((p * inv_leaf) * 2^-level) is monotone in p, so every point
+    // with lo - r <= p <= hi + r (per axis) lies in cells [c0, c1]: no padding is needed.
+    auto coarse_range = [&](int d, float r, int& a, int& b) {
+      a = max((int)floorf(((lo[d] - r) * h.inv_leaf) * h.level_scale) - h.origin[d], 0);
+      b = min((int)floorf(((hi[d] + r) * h.inv_leaf) * h.level_scale) - h.origin[d], h.dim[d] - 1);
+    };
+    // ---- (1) U: probe the box dilated by a growing radius until it holds a point
     float U2 = 3.0e38f;
     bool no_match = false;
-    for (int rad = 1; rad <= 8; rad = rad < 2 ? 2 : rad + 2) {
-      const int x0 = max(cc[0] - rad, 0), x1 = min(cc[0] + rad, dimx - 1);
-      const int y0 = max(cc[1] - rad, 0), y1 = min(cc[1] + rad, dimy - 1);
-      const int z0 = max(cc[2] - rad, 0), z1 = min(cc[2] + rad, dimz - 1);
+    float pr = fmaxf(2.0f * leaf, 0.5f * cell_m);
+    for (int round = 0; round < 8; ++round, pr *= 2.0f) {
+      int x0, x1, y0, y1, z0, z1;
+      coarse_range(0, pr, x0, x1); coarse_range(1, pr, y0, y1); coarse_range(2, pr, z0, z1);
       float m2 = 3.0e38f;
       if (x0 <= x1 && y0 <= y1 && z0 <= z1) {
         const int ny = y1 - y0 + 1;
@@ -654,7 +660,7 @@ __global__ void __launch_bounds__(256) cand_build_kernel(const IndexHeader* __re
         m2 = warp_min(m2);
       }
       if (m2 < 3.0e38f) { U2 = m2 * 1.00002f; break; }
-      if ((float)rad * cell_m * 0.999f - 4.0f * margin > r_max) { no_match = true; break; }  // farther than maximum_distance_ from everything
+      if (pr > r_max) { no_match = true; break; }  // nothing within pr (> maximum_distance_) of the box: no query of the cell can match
     }
     if (U2 >= 3.0e38f) {
       // provably no point within maximum_distance_ of any query of the cell (empty list), or the probe gave up (the
@@ -666,11 +672,7 @@ __global__ void __launch_bounds__(256) cand_build_kernel(const IndexHeader* __re
     const float reach = sqrtf(U2) * 1.00001f;
     // ---- (2) gather: rows of coarse cells that intersect the ball-dilated box
     int c0[3], c1[3];
-#pragma unroll
-    for (int d = 1; d < 3; ++d) {
-      c0[d] = max((int)floorf(((lo[d] - reach) * h.inv_leaf) * h.level_scale) - 1 - h.origin[d], 0);
-      c1[d] = min((int)floorf(((hi[d] + reach) * h.inv_leaf) * h.level_scale) + 1 - h.origin[d], h.dim[d] - 1);
-    }
+    coarse_range(1, reach, c0[1], c1[1]); coarse_range(2, reach, c0[2], c1[2]);
     const int ny = c1[1] - c0[1] + 1, nrows = max(ny, 0) * max(c1[2] - c0[2] + 1, 0);
     unsigned short* list = flists + (size_t)cell * kListK;
     unsigned short* xl = nullptr;
@@ -690,8 +692,8 @@ __global__ void __launch_bounds__(256) cand_build_kernel(const IndexHeader* __re
             const float rem = U2 - (gy * gy + gz * gz) * 0.9999f;
             if (rem < 0.f) return RowSpan{0, 0};
             const float xr = sqrtf(rem) * 1.00001f + 2.0f * margin;
-            const int xa = max((int)floorf(((lo[0] - xr) * h.inv_leaf) * h.level_scale) - 1 - h.origin[0], 0);
-            const int xb = min((int)floorf(((hi[0] + xr) * h.inv_leaf) * h.level_scale) + 1 - h.origin[0], dimx - 1);
+            const int xa = max((int)floorf(((lo[0] - xr) * h.inv_leaf) * h.level_scale) - h.origin[0], 0);
+            const int xb = min((int)floorf(((hi[0] + xr) * h.inv_leaf) * h.level_scale) - h.origin[0], dimx - 1);
             if (xa > xb) return RowSpan{0, 0};
             const int base = (z * dimy + y) * dimx;
             const int a = cs[base + xa];
@@ -707,6 +709,9 @@ __global__ void __launch_bounds__(256) cand_build_kernel(const IndexHeader* __re
       const int n = s_cnt[wib];
       __syncwarp();
       if (n <= cap) {
+        // pad to a multiple of 8 entries with the dummy slot (the lookup reads whole 16-byte groups unconditionally)
+        const int n8 = (n + 7) & ~7;
+        if (n + lane < n8) dst[n + lane] = (unsigned short)h.n_cropped;
         if (lane == 0) {
           if (!attempt) fcount[cell] = (unsigned short)n;
           else { list[2] = (unsigned short)n; fcount[cell] = kListExtended; }
@@ -750,13 +755,16 @@ __device__ __forceinline__ bool nn_lookup(const IndexHeader& h, const unsigned s
   PFT_STAT(14, cnt);
   best = nn_none(lim2);
   const uint4* l4 = reinterpret_cast<const uint4*>(lst);
-  for (int b = 0; b < cnt; b += 8) {
-    const uint4 v = l4[b >> 3];
-    const unsigned int w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      if (b + k < cnt) nn_eval(pts, (int)((w[k >> 1] >> ((k & 1) * 16)) & 0xffffu), qx, qy, qz, best);
-    }
+  const int groups = (cnt + 7) >> 3;  // lists are padded with the dummy slot to whole groups of 8
+  if (groups == 0) return true;
+  uint4 v = l4[0];
+  for (int g = 0; g < groups; ++g) {
+    const uint4 cur = v;
+    if (g + 1 < groups) v = l4[g + 1];  // next group in flight while this one is evaluated
+    nn_eval(pts, (int)(cur.x & 0xffffu), qx, qy, qz, best); nn_eval(pts, (int)(cur.x >> 16), qx, qy, qz, best);
+    nn_eval(pts, (int)(cur.y & 0xffffu), qx, qy, qz, best); nn_eval(pts, (int)(cur.y >> 16), qx, qy, qz, best);
+    nn_eval(pts, (int)(cur.z & 0xffffu), qx, qy, qz, best); nn_eval(pts, (int)(cur.z >> 16), qx, qy, qz, best);
+    nn_eval(pts, (int)(cur.w & 0xffffu), qx, qy, qz, best); nn_eval(pts, (int)(cur.w >> 16), qx, qy, qz, best);
   }
   return true;
 }
@@ -814,7 +822,7 @@ __device__ __forceinline__ void weight_items(const WeightArgs& a, const IndexHea
       xform(m, mp.x, mp.y, mp.z, qx, qy, qz);
       NNResult nn = nn_none(lim2);
       if (h.n_cropped > 0) {
-        if (!(h.use_lists && nn_lookup(h, a.fcount, a.flists, a.xlists, pts, qx, qy, qz, lim2, nn))) nn = nn_search<CS>(cs, pts, h, table, qx, qy, qz, lim2);
+        if (!(lists_on(h) && nn_lookup(h, a.fcount, a.flists, a.xlists, pts, qx, qy, qz, lim2, nn))) nn = nn_search<CS>(cs, pts, h, table, qx, qy, qz, lim2);
       }
       if (i < a.dbg_k) {
         const size_t o = (size_t)i * a.M + a.model_perm[j];
@@ -873,7 +881,7 @@ __global__ void __launch_bounds__(THREADS, 1) weight_kernel(const WeightArgs a) 
   }
   __syncthreads();
   // ---- stage the scene index into shared memory when it fits: points as float4, cell starts as 16-bit
-  const int n_pts = h.n_cropped;
+  const int n_pts = h.n_cropped + 1;  // + the dummy point that pads the candidate lists
   const long long need = 16ll * n_pts + 2ll * (((long long)h.n_cells + 1 + 7) & ~7ll);
   const bool staged = h.valid && n_pts < 65536 && need <= (long long)a.smem_bytes;
   if (staged) {
