@@ -625,7 +625,7 @@ __global__ void __launch_bounds__(256) cand_build_kernel(const IndexHeader* __re
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
   const float cell_m = h.cell;
-  const int dimx = h.dim[0], dimy = h.dim[1], dimz = h.dim[2];
+  const int dimx = h.dim[0], dimy = h.dim[1];
   int* pref = s_pref[wib];
   int* start = s_start[wib];
   if (lane == 0) pref[32] = 0x7fffffff;  // sentinel for the binary search
@@ -645,21 +645,28 @@ __global__ void __launch_bounds__(256) cand_build_kernel(const IndexHeader* __re
     };
     // ---- (1) U: probe the box dilated by a growing radius until it holds a point
     float U2 = 3.0e38f;
+    int p0_slot = -1;
     bool no_match = false;
     float pr = fmaxf(2.0f * leaf, 0.5f * cell_m);
     for (int round = 0; round < 8; ++round, pr *= 2.0f) {
       int x0, x1, y0, y1, z0, z1;
       coarse_range(0, pr, x0, x1); coarse_range(1, pr, y0, y1); coarse_range(2, pr, z0, z1);
       float m2 = 3.0e38f;
+      int ms = -1;
       if (x0 <= x1 && y0 <= y1 && z0 <= z1) {
         const int ny = y1 - y0 + 1;
         warp_points_of_rows(
             ny * (z1 - z0 + 1), pref, start,
             [&](int r) { const int zz = r / ny; const int base = ((z0 + zz) * dimy + (y0 + r - zz * ny)) * dimx; const int a = cs[base + x0]; return RowSpan{a, cs[base + x1 + 1] - a}; },
-            [&](int s) { m2 = fminf(m2, box_maxdist2(lo, hi, pts[s])); });
-        m2 = warp_min(m2);
+            [&](int s) { const float v = box_maxdist2(lo, hi, pts[s]); if (v < m2) { m2 = v; ms = s; } });
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float om = __shfl_xor_sync(kFull, m2, o);
+          const int os = __shfl_xor_sync(kFull, ms, o);
+          if (om < m2 || (om == m2 && os > ms)) { m2 = om; ms = os; }  // any deterministic choice among equals
+        }
       }
-      if (m2 < 3.0e38f) { U2 = m2 * 1.00002f; break; }
+      if (m2 < 3.0e38f) { U2 = m2 * 1.00002f; p0_slot = ms; break; }
       if (pr > r_max) { no_match = true; break; }  // nothing within pr (> maximum_distance_) of the box: no query of the cell can match
     }
     if (U2 >= 3.0e38f) {
@@ -670,6 +677,23 @@ __global__ void __launch_bounds__(256) cand_build_kernel(const IndexHeader* __re
     }
     U2 = fminf(U2, r_max * r_max);
     const float reach = sqrtf(U2) * 1.00001f;
+    // Second, sharper filter: the nearest neighbour p* of a query q of the cell satisfies |q - p*| <= |q - p0| for the
+    // reference point p0 found above, i.e. q lies on p*'s side of the bisector plane of (p*, p0).  A point p whose side
+    // of that plane misses the box can therefore never be the answer: min over the box of |q-p|^2 - |q-p0|^2 is linear
+    // in q and attained at a corner.  Coordinates are taken relative to the box centre to keep the fp32 error ~1e-9.
+    const float bcx = 0.5f * (lo[0] + hi[0]), bcy = 0.5f * (lo[1] + hi[1]), bcz = 0.5f * (lo[2] + hi[2]);
+    const float bhx = 0.5f * (hi[0] - lo[0]), bhy = 0.5f * (hi[1] - lo[1]), bhz = 0.5f * (hi[2] - lo[2]);
+    const float4 p0 = pts[p0_slot];
+    const float p0x = p0.x - bcx, p0y = p0.y - bcy, p0z = p0.z - bcz;
+    const float p0n = (p0x * p0x + p0y * p0y) + p0z * p0z;
+    auto can_win = [&](const float4& p) -> bool {
+      const float px = p.x - bcx, py = p.y - bcy, pz = p.z - bcz;
+      const float pn = (px * px + py * py) + pz * pz;
+      const float ex = px - p0x, ey = py - p0y, ez = pz - p0z;
+      // min over q in [-bh, bh]^3 of (pn - p0n) - 2 q.e  =  (pn - p0n) - 2 (bhx|ex| + bhy|ey| + bhz|ez|)
+      const float fmin = (pn - p0n) - 2.0f * ((bhx * fabsf(ex) + bhy * fabsf(ey)) + bhz * fabsf(ez));
+      return fmin <= 1.0e-6f * (pn + p0n) + 1.0e-9f;
+    };
     // ---- (2) gather: rows of coarse cells that intersect the ball-dilated box
     int c0[3], c1[3];
     coarse_range(1, reach, c0[1], c1[1]); coarse_range(2, reach, c0[2], c1[2]);
@@ -700,7 +724,8 @@ __global__ void __launch_bounds__(256) cand_build_kernel(const IndexHeader* __re
             return RowSpan{a, cs[base + xb + 1] - a};
           },
           [&](int s) {
-            if (box_mindist2(lo, hi, pts[s]) <= U2) {
+            const float4 p = pts[s];
+            if (box_mindist2(lo, hi, p) <= U2 && can_win(p)) {
               const int pos = atomicAdd(&s_cnt[wib], 1);
               if (pos < cap) dst[pos] = (unsigned short)s;
             }
@@ -880,18 +905,27 @@ __global__ void __launch_bounds__(THREADS, 1) weight_kernel(const WeightArgs a) 
     for (int i = threadIdx.x; i < 256; i += blockDim.x) { lut_h[i] = (float)i / 180.0f; lut_s[i] = (float)i / 255.0f; }
   }
   __syncthreads();
-  // ---- stage the scene index into shared memory when it fits: points as float4, cell starts as 16-bit
+  // ---- stage the scene index into shared memory: the points (float4) whenever they fit, the cell starts (as 16-bit,
+  // only the row-table search reads them) when there is room left
   const int n_pts = h.n_cropped + 1;  // + the dummy point that pads the candidate lists
-  const long long need = 16ll * n_pts + 2ll * (((long long)h.n_cells + 1 + 7) & ~7ll);
-  const bool staged = h.valid && n_pts < 65536 && need <= (long long)a.smem_bytes;
-  if (staged) {
-    uint4* s_pts = dyn_smem;
-    unsigned short* s_cs = reinterpret_cast<unsigned short*>(dyn_smem + n_pts);
+  const long long need_pts = 16ll * n_pts;
+  const long long need_cs = 2ll * (((long long)h.n_cells + 1 + 7) & ~7ll);
+  const bool pts_staged = h.valid && need_pts <= (long long)a.smem_bytes;
+  const bool cs_staged = pts_staged && n_pts < 65536 && need_pts + need_cs <= (long long)a.smem_bytes;
+  uint4* s_pts = dyn_smem;
+  if (pts_staged) {
     const uint4* gp = reinterpret_cast<const uint4*>(a.pts);
     for (int i = threadIdx.x; i < n_pts; i += blockDim.x) s_pts[i] = gp[i];
+  }
+  // (three call sites so that the compiler sees which pointers are shared memory: LDS instead of generic loads)
+  if (cs_staged) {
+    unsigned short* s_cs = reinterpret_cast<unsigned short*>(dyn_smem + n_pts);
     for (int i = threadIdx.x; i <= h.n_cells; i += blockDim.x) s_cs[i] = (unsigned short)a.cell_start[i];
     __syncthreads();
     weight_items<USE_HSV, unsigned short>(a, h, s_cs, reinterpret_cast<const float4*>(s_pts), s_table, lut_h, lut_s);
+  } else if (pts_staged) {
+    __syncthreads();
+    weight_items<USE_HSV, int>(a, h, a.cell_start, reinterpret_cast<const float4*>(s_pts), s_table, lut_h, lut_s);
   } else {
     weight_items<USE_HSV, int>(a, h, a.cell_start, a.pts, s_table, lut_h, lut_s);
   }
