@@ -145,7 +145,7 @@ struct pft_tracker {
   int graph_nodes = 0;
   // device buffers
   DevBuf st, parts[2], mats, slot_aabb, model, model_perm, model_tmp, sort_keys, sort_idx, bbox, raw, partial, cdf, cdf_total, ancestors, bin_keys, tbl_rep,
-      tbl_min, slot_of, klb, d_usel, d_normals, d_umot, idx_hdr, cell_start, ipts, ihsv, icount, dbg_idx, dbg_d2, d_trans, row_table, fcount, flists, fneeded, fneeded_list, xlists, xcount;
+      tbl_min, slot_of, klb, d_usel, d_normals, d_umot, idx_hdr, cell_start, ipts, ihsv, icount, dbg_idx, dbg_d2, d_trans, row_table, fcount, flists, fneeded, fneeded_blocks, fneeded_list, ffar_list, xlists, xcount;
   int weight_smem = 0;  // dynamic shared memory of the weight kernel (bytes)
   int tbl_size = 0;
   int n_slots = 0;
@@ -162,7 +162,7 @@ void release_all(pft_tracker* t) {
   DevBuf* bufs[] = {&t->st, &t->parts[0], &t->parts[1], &t->mats, &t->slot_aabb, &t->model, &t->model_perm, &t->model_tmp, &t->sort_keys, &t->sort_idx,
                     &t->bbox, &t->raw, &t->partial, &t->cdf, &t->cdf_total, &t->ancestors, &t->bin_keys, &t->tbl_rep, &t->tbl_min, &t->slot_of, &t->klb,
                     &t->d_usel, &t->d_normals, &t->d_umot, &t->idx_hdr, &t->cell_start, &t->ipts, &t->ihsv, &t->icount, &t->dbg_idx,
-                    &t->dbg_d2, &t->d_trans, &t->row_table, &t->fcount, &t->flists, &t->fneeded, &t->fneeded_list, &t->xlists, &t->xcount};
+                    &t->dbg_d2, &t->d_trans, &t->row_table, &t->fcount, &t->flists, &t->fneeded, &t->fneeded_blocks, &t->fneeded_list, &t->ffar_list, &t->xlists, &t->xcount};
   for (auto* b : bufs) b->release();
 }
 
@@ -264,7 +264,10 @@ int ensure_particle_buffers(pft_tracker* t) {
       if ((rc = t->fcount.reserve(((size_t)t->list_max_cells + 16) * sizeof(unsigned short)))) return rc;
       if ((rc = t->flists.reserve(((size_t)t->list_max_cells + 1) * kListK * sizeof(unsigned short)))) return rc;
       if ((rc = t->fneeded.reserve(((size_t)t->list_max_cells + 16) * sizeof(unsigned int)))) return rc;
-      if ((rc = t->fneeded_list.reserve(((size_t)t->list_max_cells + 16) * sizeof(int)))) return rc;
+      // blocks of 2x2x2 fine cells: at most ceil(d/2)^3 <= (d+1)^3/8, bounded generously by cells/2 + 4096
+      if ((rc = t->fneeded_blocks.reserve(((size_t)t->list_max_cells / 2 + 4096) * sizeof(unsigned int)))) return rc;
+      if ((rc = t->fneeded_list.reserve(((size_t)t->list_max_cells / 2 + 4096) * sizeof(int)))) return rc;
+      if ((rc = t->ffar_list.reserve(((size_t)t->list_max_cells + 16) * sizeof(int)))) return rc;
       if ((rc = t->xlists.reserve((size_t)kListXCells * kListKX * sizeof(unsigned short)))) return rc;
       if ((rc = t->xcount.reserve(64))) return rc;
     }
@@ -503,7 +506,7 @@ int weight_phase_eval(pft_tracker* t) {
   const float inv_leaf = 1.0f / (float)t->search_res;
   const int gscene = blocks_for(ncap_scene, 256, sm * 4);
   index_begin_kernel<<<sm, 256, 0, s>>>(st, hdr, t->icount.as<int>(), inv_leaf, t->index_level, t->max_cells, t->list_mode ? t->list_max_cells : 0,
-                                        t->list_mode == 2 ? 0 : t->M, t->nranks, t->rank, t->fneeded.as<unsigned int>(), t->xcount.as<int>());
+                                        t->list_mode == 2 ? 0 : t->M, t->nranks, t->rank, t->fneeded.as<unsigned int>(), t->fneeded_blocks.as<unsigned int>(), t->xcount.as<int>());
   PFT_LAUNCH_CHECK();
   index_count_kernel<<<gscene, 256, 0, s>>>(in->d_pts(), in->d_hdr(), hdr, t->icount.as<int>());
   PFT_LAUNCH_CHECK();
@@ -514,10 +517,15 @@ int weight_phase_eval(pft_tracker* t) {
   PFT_LAUNCH_CHECK();
   if (t->list_max_cells > 0 && t->list_mode) {
     cand_mark_kernel<<<sm * 4, 256, 0, s>>>(st, hdr, t->model.as<float4>(), t->M, t->mats.as<float>(), t->fneeded.as<unsigned int>(),
-                                           t->fneeded_list.as<int>(), t->xcount.as<int>(), t->nranks, t->rank);
+                                           t->fneeded_blocks.as<unsigned int>(), t->fneeded_list.as<int>(), t->xcount.as<int>(), t->nranks, t->rank);
     PFT_LAUNCH_CHECK();
     cand_build_kernel<<<sm * 8, 256, 0, s>>>(hdr, t->cell_start.as<int>(), t->ipts.as<float4>(), t->max_dist * t->max_dist, t->fcount.as<unsigned short>(), t->flists.as<unsigned short>(),
-                                            t->fneeded_list.as<int>(), t->xlists.as<unsigned short>(), t->xcount.as<int>());
+                                            t->fneeded.as<unsigned int>(), t->fneeded_list.as<int>(), t->xlists.as<unsigned short>(),
+                                            t->xcount.as<int>(), t->ffar_list.as<int>());
+    PFT_LAUNCH_CHECK();
+    cand_build_far_kernel<<<sm * 8, 256, 0, s>>>(hdr, t->cell_start.as<int>(), t->ipts.as<float4>(), t->max_dist * t->max_dist,
+                                                t->fcount.as<unsigned short>(), t->flists.as<unsigned short>(), t->xlists.as<unsigned short>(),
+                                                t->xcount.as<int>(), t->ffar_list.as<int>());
     PFT_LAUNCH_CHECK();
   }
   WeightArgs a;

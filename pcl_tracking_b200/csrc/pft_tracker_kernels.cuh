@@ -295,7 +295,7 @@ __device__ inline void compute_index_header(const float* aabb, float inv_leaf, i
 // that is d away from the surface walks ~pi (d/cell + 1)^2 rows and ~(d + cell)^2 candidates: cell ~ d balances them)
 __global__ void index_begin_kernel(const TrackerState* __restrict__ st, IndexHeader* hdr, int* cell_count, float inv_leaf, int base_level,
                                    int max_cells, int list_max_cells, int M, int nranks, int rank, unsigned int* needed_words,
-                                   int* list_counters /* [0] extended lists handed out, [1] needed cells */) {
+                                   unsigned int* needed_blocks, int* list_counters /* [0] extended lists handed out, [1] needed blocks, [2] cells queued for the far pass */) {
   __shared__ IndexHeader h;
   if (threadIdx.x == 0) {
     if (base_level < 0) {
@@ -318,9 +318,11 @@ __global__ void index_begin_kernel(const TrackerState* __restrict__ st, IndexHea
   const int nc = h.n_cells + 1;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nc; i += gridDim.x * blockDim.x) cell_count[i] = 0;
   if (h.use_lists) {
+    const int nb = ((h.f_dim[0] + 1) >> 1) * ((h.f_dim[1] + 1) >> 1) * ((h.f_dim[2] + 1) >> 1);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < h.f_cells; i += gridDim.x * blockDim.x) needed_words[i] = 0u;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nb; i += gridDim.x * blockDim.x) needed_blocks[i] = 0u;
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) { list_counters[0] = 0; list_counters[1] = 0; }
+  if (blockIdx.x == 0 && threadIdx.x == 0) { list_counters[0] = 0; list_counters[1] = 0; list_counters[2] = 0; }
 }
 
 __device__ __forceinline__ bool in_crop(const float4& p, const IndexHeader& h) {
@@ -538,8 +540,8 @@ __device__ __forceinline__ float box_maxdist2(const float* lo, const float* hi, 
 
 // collects the fine cells that this rank's queries fall into (the lists of the others are never read)
 __global__ void cand_mark_kernel(const TrackerState* __restrict__ st, const IndexHeader* __restrict__ hdr, const float4* __restrict__ model, int M,
-                                 const float* __restrict__ mats, unsigned int* __restrict__ needed, int* __restrict__ needed_list,
-                                 int* __restrict__ list_counters, int nranks, int rank) {
+                                 const float* __restrict__ mats, unsigned int* __restrict__ needed, unsigned int* __restrict__ needed_blocks,
+                                 int* __restrict__ needed_list, int* __restrict__ list_counters, int nranks, int rank) {
   __shared__ IndexHeader h;
   if (threadIdx.x == 0) h = *hdr;
   __syncthreads();
@@ -568,7 +570,13 @@ __global__ void cand_mark_kernel(const TrackerState* __restrict__ st, const Inde
                 iz = (int)fminf(fmaxf(floorf(qz * h.inv_leaf), -big), big) - h.f_origin[2];
       if ((unsigned)ix < (unsigned)h.f_dim[0] && (unsigned)iy < (unsigned)h.f_dim[1] && (unsigned)iz < (unsigned)h.f_dim[2]) {
         const int cell = (iz * h.f_dim[1] + iy) * h.f_dim[0] + ix;
-        if (needed[cell] == 0u && atomicExch(&needed[cell], 1u) == 0u) needed_list[atomicAdd(&list_counters[1], 1)] = cell;
+        if (needed[cell] == 0u) {  // (a cell that is already marked has its block queued)
+          needed[cell] = 1u;
+          // lists are built per block of 2x2x2 fine cells: append the block once
+          const int bdx = (h.f_dim[0] + 1) >> 1, bdy = (h.f_dim[1] + 1) >> 1;
+          const int blk = ((iz >> 1) * bdy + (iy >> 1)) * bdx + (ix >> 1);
+          if (atomicExch(&needed_blocks[blk], 1u) == 0u) needed_list[atomicAdd(&list_counters[1], 1)] = blk;
+        }
       }
     }
   }
@@ -606,31 +614,29 @@ __device__ __forceinline__ void warp_points_of_rows(int nrows, int* __restrict__
   }
 }
 
-__global__ void __launch_bounds__(256) cand_build_kernel(const IndexHeader* __restrict__ hdr, const int* __restrict__ cs,
-                                                         const float4* __restrict__ pts, double max_d2,
-                                                         unsigned short* __restrict__ fcount, unsigned short* __restrict__ flists,
-                                                         const int* __restrict__ needed_list, unsigned short* __restrict__ xlists,
-                                                         int* __restrict__ list_counters) {
-  __shared__ IndexHeader h;
-  __shared__ int s_cnt[8];
-  __shared__ int s_pref[8][33], s_start[8][32];
-  if (threadIdx.x == 0) h = *hdr;
-  __syncthreads();
-  if (!h.valid || !lists_on(h)) return;
-  const int n_needed = list_counters[1];
-  const float leaf = 1.0f / h.inv_leaf;
-  const float margin = 1.0e-5f + 4.0e-6f * leaf * (float)(abs(h.f_origin[0]) + abs(h.f_origin[1]) + abs(h.f_origin[2]) + h.f_dim[0] + h.f_dim[1] + h.f_dim[2]);
-  const float r_max = max_d2 >= 1.0e30 ? 1.0e15f : (float)sqrt(max_d2) * 1.00001f;
+constexpr int kSuperCap = 256;  // points a block's superset can hold in shared memory
+
+// bisector test: can p be at least as near as p0 for SOME q of the box (centre bc, half extents bh)?
+// min over the box of |q-p|^2 - |q-p0|^2 is linear in q and attained at a corner; coordinates relative to the box
+// centre keep the fp32 error ~1e-9.
+__device__ __forceinline__ bool can_win(const float4& p, const float4& p0, const float* bc, const float* bh) {
+  const float px = p.x - bc[0], py = p.y - bc[1], pz = p.z - bc[2];
+  const float qx = p0.x - bc[0], qy = p0.y - bc[1], qz = p0.z - bc[2];
+  const float pn = (px * px + py * py) + pz * pz, p0n = (qx * qx + qy * qy) + qz * qz;
+  const float fmin = (pn - p0n) - 2.0f * ((bh[0] * fabsf(px - qx) + bh[1] * fabsf(py - qy)) + bh[2] * fabsf(pz - qz));
+  return fmin <= 1.0e-6f * (pn + p0n) + 1.0e-9f;
+}
+
+// One warp builds the list of ONE fine cell straight from the grid (no shared-memory superset): used for the cells of
+// blocks whose superset does not fit, i.e. far from the surface, where lists are long (extended lists up to kListKX).
+__device__ __noinline__ void build_cell_direct(const IndexHeader& h, const int* __restrict__ cs, const float4* __restrict__ pts, int cell,
+                                               float leaf, float margin, float r_max, unsigned short* __restrict__ fcount,
+                                               unsigned short* __restrict__ flists, unsigned short* __restrict__ xlists,
+                                               int* __restrict__ list_counters, int* pref, int* start, int* s_cnt_w) {
+  const int lane = threadIdx.x & 31;
   const int fdx = h.f_dim[0], fdy = h.f_dim[1];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
   const float cell_m = h.cell;
   const int dimx = h.dim[0], dimy = h.dim[1];
-  int* pref = s_pref[wib];
-  int* start = s_start[wib];
-  if (lane == 0) pref[32] = 0x7fffffff;  // sentinel for the binary search
-  for (int idx = warp; idx < n_needed; idx += nwarps) {
-    const int cell = needed_list[idx];
     const int fz = cell / (fdx * fdy), r2 = cell - fz * fdx * fdy, fy = r2 / fdx, fx = r2 - fy * fdx;
     // the cell in metric space, widened by the rounding of q * inv_leaf near its faces
     float lo[3], hi[3];
@@ -673,7 +679,7 @@ __global__ void __launch_bounds__(256) cand_build_kernel(const IndexHeader* __re
       // provably no point within maximum_distance_ of any query of the cell (empty list), or the probe gave up (the
       // queries of this cell use the row-table search)
       if (lane == 0) fcount[cell] = no_match ? (unsigned short)0 : kListOverflow;
-      continue;
+      return;
     }
     U2 = fminf(U2, r_max * r_max);
     const float reach = sqrtf(U2) * 1.00001f;
@@ -702,7 +708,7 @@ __global__ void __launch_bounds__(256) cand_build_kernel(const IndexHeader* __re
     unsigned short* xl = nullptr;
     int cap = kListK;
     for (int attempt = 0; attempt < 2; ++attempt) {
-      if (lane == 0) s_cnt[wib] = 0;
+      if (lane == 0) (*s_cnt_w) = 0;
       __syncwarp();
       unsigned short* dst = attempt ? xl : list;
       warp_points_of_rows(
@@ -726,12 +732,12 @@ __global__ void __launch_bounds__(256) cand_build_kernel(const IndexHeader* __re
           [&](int s) {
             const float4 p = pts[s];
             if (box_mindist2(lo, hi, p) <= U2 && can_win(p)) {
-              const int pos = atomicAdd(&s_cnt[wib], 1);
+              const int pos = atomicAdd(&(*s_cnt_w), 1);
               if (pos < cap) dst[pos] = (unsigned short)s;
             }
           });
       __syncwarp();
-      const int n = s_cnt[wib];
+      const int n = (*s_cnt_w);
       __syncwarp();
       if (n <= cap) {
         // pad to a multiple of 8 entries with the dummy slot (the lookup reads whole 16-byte groups unconditionally)
@@ -755,7 +761,225 @@ __global__ void __launch_bounds__(256) cand_build_kernel(const IndexHeader* __re
       if (lane == 0) { list[0] = (unsigned short)(xi & 0xffff); list[1] = (unsigned short)(xi >> 16); }
     }
     PFT_STAT(15, lane == 0 ? 1 : 0);
+}
+
+// One warp builds the lists of one block of 2x2x2 fine cells: the points that can be the nearest neighbour of some
+// query of the BLOCK are gathered once into shared memory (a superset of every cell's list), then each needed cell
+// of the block filters that superset with its own bound and bisector test.
+__global__ void __launch_bounds__(256) cand_build_kernel(const IndexHeader* __restrict__ hdr, const int* __restrict__ cs,
+                                                         const float4* __restrict__ pts, double max_d2,
+                                                         unsigned short* __restrict__ fcount, unsigned short* __restrict__ flists,
+                                                         const unsigned int* __restrict__ needed, const int* __restrict__ needed_list,
+                                                         unsigned short* __restrict__ xlists, int* __restrict__ list_counters,
+                                                         int* __restrict__ far_list) {
+  __shared__ IndexHeader h;
+  __shared__ int s_cnt[8];
+  __shared__ int s_pref[8][33], s_start[8][32];
+  __shared__ float4 s_pt[8][kSuperCap];
+  __shared__ unsigned short s_slot[8][kSuperCap];
+  if (threadIdx.x == 0) h = *hdr;
+  __syncthreads();
+  if (!h.valid || !lists_on(h)) return;
+  const int n_needed = list_counters[1];
+  const float leaf = 1.0f / h.inv_leaf;
+  const float margin = 1.0e-5f + 4.0e-6f * leaf * (float)(abs(h.f_origin[0]) + abs(h.f_origin[1]) + abs(h.f_origin[2]) + h.f_dim[0] + h.f_dim[1] + h.f_dim[2]);
+  const float r_max = max_d2 >= 1.0e30 ? 1.0e15f : (float)sqrt(max_d2) * 1.00001f;
+  const int fdx = h.f_dim[0], fdy = h.f_dim[1], fdz = h.f_dim[2];
+  const int bdx = (fdx + 1) >> 1, bdy = (fdy + 1) >> 1;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  const float cell_m = h.cell;
+  const int dimx = h.dim[0], dimy = h.dim[1];
+  int* pref = s_pref[wib];
+  int* start = s_start[wib];
+  float4* spt = s_pt[wib];
+  unsigned short* sslot = s_slot[wib];
+  if (lane == 0) pref[32] = 0x7fffffff;  // sentinel for the binary search
+  for (int idx = warp; idx < n_needed; idx += nwarps) {
+    const int blk = needed_list[idx];
+    const int bz = blk / (bdx * bdy), br = blk - bz * bdx * bdy, by = br / bdx, bx = br - by * bdx;
+    // the block (2x2x2 fine cells) in metric space, widened by the rounding of q * inv_leaf near its faces
+    float lo[3], hi[3];
+    lo[0] = (float)(h.f_origin[0] + 2 * bx) * leaf - margin; hi[0] = (float)(h.f_origin[0] + 2 * bx + 2) * leaf + margin;
+    lo[1] = (float)(h.f_origin[1] + 2 * by) * leaf - margin; hi[1] = (float)(h.f_origin[1] + 2 * by + 2) * leaf + margin;
+    lo[2] = (float)(h.f_origin[2] + 2 * bz) * leaf - margin; hi[2] = (float)(h.f_origin[2] + 2 * bz + 2) * leaf + margin;
+    // every fine cell of the block gets `value` (used when the whole block is decided at once)
+    auto set_all = [&](unsigned short value) {
+      if (lane < 8) {
+        const int fx = 2 * bx + (lane & 1), fy = 2 * by + ((lane >> 1) & 1), fz = 2 * bz + (lane >> 2);
+        if (fx < fdx && fy < fdy && fz < fdz) { const int c = (fz * fdy + fy) * fdx + fx; if (needed[c]) fcount[c] = value; }
+      }
+    };
+    // coarse cells overlapping the box dilated by r.  floor((p * inv_leaf) * 2^-level) is monotone in p, so every point
+    // with lo - r <= p <= hi + r (per axis) lies in cells [c0, c1]: no padding is needed.
+    auto coarse_range = [&](int d, float r, int& a, int& b) {
+      a = max((int)floorf(((lo[d] - r) * h.inv_leaf) * h.level_scale) - h.origin[d], 0);
+      b = min((int)floorf(((hi[d] + r) * h.inv_leaf) * h.level_scale) - h.origin[d], h.dim[d] - 1);
+    };
+    // ---- (1) U_B = min over points of maxdist(block, p): probe the block dilated by a growing radius until it holds a point
+    float U2 = 3.0e38f;
+    int p0_slot = -1;
+    bool no_match = false;
+    float pr = fmaxf(2.0f * leaf, 0.5f * cell_m);
+    for (int round = 0; round < 8; ++round, pr *= 2.0f) {
+      int x0, x1, y0, y1, z0, z1;
+      coarse_range(0, pr, x0, x1); coarse_range(1, pr, y0, y1); coarse_range(2, pr, z0, z1);
+      float m2 = 3.0e38f;
+      int ms = -1;
+      if (x0 <= x1 && y0 <= y1 && z0 <= z1) {
+        const int ny = y1 - y0 + 1;
+        warp_points_of_rows(
+            ny * (z1 - z0 + 1), pref, start,
+            [&](int r) { const int zz = r / ny; const int base = ((z0 + zz) * dimy + (y0 + r - zz * ny)) * dimx; const int a = cs[base + x0]; return RowSpan{a, cs[base + x1 + 1] - a}; },
+            [&](int s) { const float v = box_maxdist2(lo, hi, pts[s]); if (v < m2) { m2 = v; ms = s; } });
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float om = __shfl_xor_sync(kFull, m2, o);
+          const int os = __shfl_xor_sync(kFull, ms, o);
+          if (om < m2 || (om == m2 && os > ms)) { m2 = om; ms = os; }  // any deterministic choice among equals
+        }
+      }
+      if (m2 < 3.0e38f) { U2 = m2 * 1.00002f; p0_slot = ms; break; }
+      if (pr > r_max) { no_match = true; break; }  // nothing within pr (> maximum_distance_) of the block: none of its queries can match
+    }
+    if (U2 >= 3.0e38f) {
+      // provably no point within maximum_distance_ of any query of the block (empty lists), or the probe gave up
+      // (the queries of the block use the row-table search)
+      set_all(no_match ? (unsigned short)0 : kListOverflow);
+      continue;
+    }
+    U2 = fminf(U2, r_max * r_max);
+    const float reach = sqrtf(U2) * 1.00001f;
+    float bc[3], bh[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) { bc[d] = 0.5f * (lo[d] + hi[d]); bh[d] = 0.5f * (hi[d] - lo[d]); }
+    const float4 p0 = pts[p0_slot];
+    // ---- (2) superset of the block: { p : mindist(block, p) <= U_B and p can beat p0 somewhere in the block }
+    int c0[3], c1[3];
+    coarse_range(1, reach, c0[1], c1[1]); coarse_range(2, reach, c0[2], c1[2]);
+    const int ny = c1[1] - c0[1] + 1, nrows = max(ny, 0) * max(c1[2] - c0[2] + 1, 0);
+    if (lane == 0) s_cnt[wib] = 0;
+    __syncwarp();
+    warp_points_of_rows(
+        nrows, pref, start,
+        [&](int r) {
+          const int zz = r / ny, y = c0[1] + (r - zz * ny), z = c0[2] + zz;
+          const float zlo = (float)(z + h.origin[2]) * cell_m - 2.0f * margin, zhi = (float)(z + 1 + h.origin[2]) * cell_m + 2.0f * margin;
+          const float gz = fmaxf(fmaxf(lo[2] - zhi, zlo - hi[2]), 0.f);
+          const float ylo = (float)(y + h.origin[1]) * cell_m - 2.0f * margin, yhi = (float)(y + 1 + h.origin[1]) * cell_m + 2.0f * margin;
+          const float gy = fmaxf(fmaxf(lo[1] - yhi, ylo - hi[1]), 0.f);
+          const float rem = U2 - (gy * gy + gz * gz) * 0.9999f;
+          if (rem < 0.f) return RowSpan{0, 0};
+          const float xr = sqrtf(rem) * 1.00001f + 2.0f * margin;
+          const int xa = max((int)floorf(((lo[0] - xr) * h.inv_leaf) * h.level_scale) - h.origin[0], 0);
+          const int xb = min((int)floorf(((hi[0] + xr) * h.inv_leaf) * h.level_scale) - h.origin[0], dimx - 1);
+          if (xa > xb) return RowSpan{0, 0};
+          const int base = (z * dimy + y) * dimx;
+          const int a = cs[base + xa];
+          return RowSpan{a, cs[base + xb + 1] - a};
+        },
+        [&](int s) {
+          const float4 p = pts[s];
+          if (box_mindist2(lo, hi, p) <= U2 && can_win(p, p0, bc, bh)) {
+            const int pos = atomicAdd(&s_cnt[wib], 1);
+            if (pos < kSuperCap) { spt[pos] = p; sslot[pos] = (unsigned short)s; }
+          }
+        });
+    __syncwarp();
+    const int ns = s_cnt[wib];
+    __syncwarp();
+    if (ns > kSuperCap) {
+      // far from the surface: long lists.  Their cells are queued for cand_build_far_kernel (one warp per cell, straight
+      // from the grid) instead of being built one after the other by this warp.
+      if (lane < 8) {
+        const int fx = 2 * bx + (lane & 1), fy = 2 * by + ((lane >> 1) & 1), fz = 2 * bz + (lane >> 2);
+        if (fx < fdx && fy < fdy && fz < fdz) {
+          const int c = (fz * fdy + fy) * fdx + fx;
+          if (needed[c]) far_list[atomicAdd(&list_counters[2], 1)] = c;
+        }
+      }
+      continue;
+    }
+    // ---- (3) each needed fine cell filters the superset with its own bound and bisector test
+    for (int sub = 0; sub < 8; ++sub) {
+      const int fx = 2 * bx + (sub & 1), fy = 2 * by + ((sub >> 1) & 1), fz = 2 * bz + (sub >> 2);
+      if (fx >= fdx || fy >= fdy || fz >= fdz) continue;
+      const int cell = (fz * fdy + fy) * fdx + fx;
+      if (!needed[cell]) continue;
+      float flo[3], fhi[3], fc[3], fh[3];
+      flo[0] = (float)(h.f_origin[0] + fx) * leaf - margin; fhi[0] = (float)(h.f_origin[0] + fx + 1) * leaf + margin;
+      flo[1] = (float)(h.f_origin[1] + fy) * leaf - margin; fhi[1] = (float)(h.f_origin[1] + fy + 1) * leaf + margin;
+      flo[2] = (float)(h.f_origin[2] + fz) * leaf - margin; fhi[2] = (float)(h.f_origin[2] + fz + 1) * leaf + margin;
+#pragma unroll
+      for (int d = 0; d < 3; ++d) { fc[d] = 0.5f * (flo[d] + fhi[d]); fh[d] = 0.5f * (fhi[d] - flo[d]); }
+      // U_f and its reference point: the minimiser of maxdist(cell, .) over all points lies in the superset
+      float m2 = 3.0e38f;
+      int mi = -1;
+      for (int t = lane; t < ns; t += 32) { const float v = box_maxdist2(flo, fhi, spt[t]); if (v < m2) { m2 = v; mi = t; } }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float om = __shfl_xor_sync(kFull, m2, o);
+        const int oi = __shfl_xor_sync(kFull, mi, o);
+        if (om < m2 || (om == m2 && oi > mi)) { m2 = om; mi = oi; }
+      }
+      const float Uf2 = fminf(m2 * 1.00002f, r_max * r_max);
+      const float4 pf = spt[mi];
+      // count, choose the destination, write (ballot compaction: the order of a list is the order of the superset)
+      int n = 0;
+      for (int t0 = 0; t0 < ns; t0 += 32) {
+        const int t = t0 + lane;
+        const bool keep = t < ns && box_mindist2(flo, fhi, spt[t]) <= Uf2 && can_win(spt[t], pf, fc, fh);
+        n += __popc(__ballot_sync(kFull, keep));
+      }
+      unsigned short* list = flists + (size_t)cell * kListK;
+      unsigned short* dst = list;
+      if (n > kListK) {
+        int xi = -1;
+        if (n <= kListKX) {
+          if (lane == 0) xi = atomicAdd(&list_counters[0], 1);
+          xi = __shfl_sync(kFull, xi, 0);
+        }
+        if (xi < 0 || xi >= kListXCells) { if (lane == 0) fcount[cell] = kListOverflow; continue; }
+        dst = xlists + (size_t)xi * kListKX;
+        if (lane == 0) { list[0] = (unsigned short)(xi & 0xffff); list[1] = (unsigned short)(xi >> 16); list[2] = (unsigned short)n; }
+      }
+      int w = 0;
+      for (int t0 = 0; t0 < ns; t0 += 32) {
+        const int t = t0 + lane;
+        const bool keep = t < ns && box_mindist2(flo, fhi, spt[t]) <= Uf2 && can_win(spt[t], pf, fc, fh);
+        const unsigned int bal = __ballot_sync(kFull, keep);
+        if (keep) dst[w + __popc(bal & ((1u << lane) - 1u))] = sslot[t];
+        w += __popc(bal);
+      }
+      // pad to a multiple of 8 entries with the dummy slot (the lookup reads whole 16-byte groups unconditionally)
+      const int n8 = (n + 7) & ~7;
+      if (n + lane < n8) dst[n + lane] = (unsigned short)h.n_cropped;
+      if (lane == 0) fcount[cell] = n > kListK ? kListExtended : (unsigned short)n;
+      PFT_STAT(15, lane == 0 ? 1 : 0);
+    }
   }
+}
+
+// second pass of the build: the cells queued by cand_build_kernel, one warp each
+__global__ void __launch_bounds__(256) cand_build_far_kernel(const IndexHeader* __restrict__ hdr, const int* __restrict__ cs,
+                                                             const float4* __restrict__ pts, double max_d2, unsigned short* __restrict__ fcount,
+                                                             unsigned short* __restrict__ flists, unsigned short* __restrict__ xlists,
+                                                             int* __restrict__ list_counters, const int* __restrict__ far_list) {
+  __shared__ IndexHeader h;
+  __shared__ int s_cnt[8];
+  __shared__ int s_pref[8][33], s_start[8][32];
+  if (threadIdx.x == 0) h = *hdr;
+  __syncthreads();
+  if (!h.valid || !lists_on(h)) return;
+  const int n_far = list_counters[2];
+  const float leaf = 1.0f / h.inv_leaf;
+  const float margin = 1.0e-5f + 4.0e-6f * leaf * (float)(abs(h.f_origin[0]) + abs(h.f_origin[1]) + abs(h.f_origin[2]) + h.f_dim[0] + h.f_dim[1] + h.f_dim[2]);
+  const float r_max = max_d2 >= 1.0e30 ? 1.0e15f : (float)sqrt(max_d2) * 1.00001f;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  if (lane == 0) s_pref[wib][32] = 0x7fffffff;
+  for (int idx = warp; idx < n_far; idx += nwarps)
+    build_cell_direct(h, cs, pts, far_list[idx], leaf, margin, r_max, fcount, flists, xlists, list_counters, s_pref[wib], s_start[wib], &s_cnt[wib]);
 }
 
 // Query through the candidate lists; returns false when the row-table search has to be used instead.
@@ -778,6 +1002,8 @@ __device__ __forceinline__ bool nn_lookup(const IndexHeader& h, const unsigned s
     lst = xlists + (size_t)xi * kListKX;
   }
   PFT_STAT(14, cnt);
+  PFT_STAT(0, cnt > 16 ? 1 : 0); PFT_STAT(1, cnt > 32 ? 1 : 0); PFT_STAT(2, cnt > 64 ? 1 : 0); PFT_STAT(3, cnt > 128 ? 1 : 0); PFT_STAT(4, cnt > 512 ? 1 : 0);
+  PFT_STAT(5, cnt == 0 ? 1 : 0);
   best = nn_none(lim2);
   const uint4* l4 = reinterpret_cast<const uint4*>(lst);
   const int groups = (cnt + 7) >> 3;  // lists are padded with the dummy slot to whole groups of 8
