@@ -421,6 +421,20 @@ def main():
     except Exception:
         pass
     result = tracker.getResult()
+    # DRAM traffic of the dominant kernel per launch, from the committed `ncu --set full` capture of this workload
+    traffic, traffic_src = None, None
+    try:
+        km = json.load(open(os.path.join(ROOT, "profiles", "r01_final_kernel_metrics.json")))
+        wk = [v for k, v in km.items() if k.startswith("weight_kernel")][0]
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        tot = 0.0
+        for key, val in wk.items():
+            if key.startswith("dram__bytes_read.sum") or key.startswith("dram__bytes_write.sum"):
+                tot += float(val) * scale[key.split("[")[1].rstrip("]")]
+        if args.workload == "c2" and world == 1:
+            traffic, traffic_src = tot, "profiles/r01_weight_and_build_final.ncu-rep (dram__bytes_read.sum + dram__bytes_write.sum, one launch)"
+    except Exception:
+        pass
 
     line = None
     if rank == 0:
@@ -434,7 +448,7 @@ def main():
             "gpu_launches": int(launches),
             "graph_replays": int(graph_replays),
             "clocks": sampler.summary(),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                          "kernel": "weight_kernel<HSV>", "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": bytes_per_launch, "ms_per_launch": w_ms_per_launch,
                          "evals_per_s_in_kernel": n_local * M / (w_ms_per_launch * 1e-3),
