@@ -9,9 +9,11 @@ with compute() = 2 x { resample, crop + index rebuild, weight, normalise, update
 Workloads (config.workload):
   c2   BASELINE.json configs[1]: 217 088-pt Kinect2-shaped synthetic scene, ~2k-pt model, 1000
        particles PER GPU (fixed-N tracker), Distance+HSV coherence.  With N GPUs it is ONE tracker
-       of 1000*N particles sharded by particle (weak scaling): rank 0 downsamples and broadcasts the
-       scene over NCCL/NVLink, every rank weights its own particles, the crop box is all-reduced and
-       the raw weights all-gathered, resample/normalise/update run replicated.
+       of 1000*N particles sharded by particle (weak scaling): every rank downsamples the frame and
+       weights its own particles; the crop box and the raw weights travel between the GPUs as peer
+       stores over NVLink issued by the producing kernels (--exchange peer, default) or through
+       ncclAllReduce / ncclAllGather (--exchange nccl, with rank 0 downsampling and broadcasting the
+       scene); resample/normalise/update run replicated.
   c4   BASELINE.json configs[3]: 100 000 particles in total, sharded over the N GPUs (strong scaling).
 
 `value`   = likelihood evals/s, whole job, inputs resident in HBM (raw frames pre-uploaded).
@@ -233,7 +235,8 @@ def workload_config(args, M, n_particles):
         if args.workload == "c2" else
         ("c4: BASELINE.json configs[3], 100000 particles sharded over the GPUs, 217088-pt scene, %d-pt model, Distance+HSV" % M),
         "scene_points": 217088, "model_points": M, "particles_total": n_particles, "iterations_per_frame": ITERATIONS,
-        "leaf_m": LEAF, "max_distance_m": 0.1, "l2": "flushed between timed steps (256 MiB write)", "parallelism": "particle-shard x%d" % args.gpus,
+        "leaf_m": LEAF, "max_distance_m": 0.1, "l2": "flushed between timed steps (256 MiB write)", "parallelism": "particle-shard x%d" % args.gpus + ("" if args.gpus == 1 else
+                                                                 ", %s exchange, scene %s" % (args.exchange, args.scene or ("replicate" if args.exchange == "peer" else "broadcast"))),
     }
 
 
@@ -247,6 +250,12 @@ def main():
     ap.add_argument("--workload", default="c2", choices=["c2", "c4"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true", help="debug only: do not flush L2 between steps")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N>1: how the crop box and the raw weights travel between the GPUs: 'peer' = stores over NVLink from the "
+                         "producing kernels into CUDA-IPC windows (no collective call per frame), 'nccl' = ncclAllReduce/ncclAllGather")
+    ap.add_argument("--scene", default=None, choices=["replicate", "broadcast"],
+                    help="N>1: every rank downsamples the frame itself (default with --exchange peer) or rank 0 does and "
+                         "broadcasts the result over NCCL (default with --exchange nccl)")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -271,10 +280,13 @@ def main():
     from pcl_tracking_b200 import pcl
 
     ctx = pcl.Context(local_rank)
-    if world > 1:
+    scene_mode = args.scene or ("replicate" if args.exchange == "peer" else "broadcast")
+    use_nccl = world > 1 and (args.exchange == "nccl" or scene_mode == "broadcast")
+    if use_nccl:
         uid = [pcl.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         ctx.commInit(world, rank, uid[0])
+    owns_frames = rank == 0 or scene_mode == "replicate"
     stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
 
     frames, oid0 = make_frames(N_FRAMES)
@@ -292,15 +304,22 @@ def main():
     m[:3, 3] = centroid
     tracker.setTrans(m)
     tracker.seed(1234)
-    if world > 1:
+    if world > 1 and args.exchange == "nccl":
         tracker.commInit(world, rank, uid[0])
+    elif world > 1:
+        # NVLink peer exchange: windows mapped with CUDA IPC, handles shipped by torch.distributed
+        tracker.setShard(world, rank)
+        handles = [None] * world
+        dist.all_gather_object(handles, tracker.peerExport())
+        tracker.peerAttach(handles)
+        dist.barrier()
     tracker.setReferenceCloud(model_cloud)
 
     # resident inputs: raw frames in HBM (rank 0 owns the sensor; the other ranks receive the downsampled scene)
-    dev_frames = [pcl.PointCloud(f, ctx=ctx) for f in frames] if rank == 0 else None
+    dev_frames = [pcl.PointCloud(f, ctx=ctx) for f in frames] if owns_frames else None
     # host inputs for e2e: pinned frame buffers
     pinned = []
-    if rank == 0:
+    if owns_frames:
         for f in frames:
             p = C.c_void_p()
             pcl.check(pcl.capi.load().pft_host_alloc(C.byref(p), f.nbytes))
@@ -313,20 +332,20 @@ def main():
     vg.setPassThrough("z", 0.0, 10.0)
 
     def step_resident(k):
-        if rank == 0:
+        if owns_frames:
             vg.setInputCloud(dev_frames[frame_order(k, N_FRAMES)])
             vg.filter(ds)
-        if world > 1:
+        if world > 1 and scene_mode == "broadcast":
             ds.broadcast(n_pts, 0)
         tracker.setInputCloud(ds)
         tracker.compute()
 
     def step_e2e(k):
-        if rank == 0:
+        if owns_frames:
             upload_cloud.upload_raw(pinned[frame_order(k, N_FRAMES)].value, n_pts)
             vg.setInputCloud(upload_cloud)
             vg.filter(ds)
-        if world > 1:
+        if world > 1 and scene_mode == "broadcast":
             ds.broadcast(n_pts, 0)
         tracker.setInputCloud(ds)
         tracker.compute()
@@ -443,7 +462,7 @@ def main():
             "higher_is_better": True, "scaling": "weak" if args.workload == "c2" else "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": workload_config(args, M, n_particles),
             "frames_per_s": 1e3 / ms_per_step,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(frames[0].nbytes), "d2h_bytes_per_step": 32 + 64,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(frames[0].nbytes) * (world if scene_mode == "replicate" else 1), "d2h_bytes_per_step": 32 + 64,
                     "ms_per_step": e2e_ms_per_step, "frames_per_s": 1e3 / e2e_ms_per_step},
             "gpu_launches": int(launches),
             "graph_replays": int(graph_replays),

@@ -226,6 +226,21 @@ PFT_API int pft_cloud_broadcast(pft_cloud* cloud, size_t capacity, int root);
 PFT_API int pft_tracker_comm_init(pft_tracker* t, int nranks, int rank, const void* id128);
 PFT_API int pft_tracker_comm_destroy(pft_tracker* t);
 
+
+/* ---------------------------------------------------------------- multi-GPU: NVLink peer exchange */
+/* The exchange steps of weight() fused into the producing kernels: every rank owns a window in its HBM
+ * that all peers map with CUDA IPC; aabb -> peer stores of the crop box + flag barrier, and the kernel
+ * that finishes the raw weights stores them straight into every rank's window (it IS the all-gather);
+ * normalizeWeight waits on the flag.  No NCCL call is made per frame.  Call order on every rank (one
+ * process per GPU, same node): pft_tracker_set_shard (or _comm_init) -> particle numbers ->
+ * pft_tracker_peer_export -> the host framework all-gathers the PFT_PEER_HANDLE_BYTES handles in rank
+ * order -> pft_tracker_peer_attach -> compute().  Results are bit-identical to the NCCL path and to the
+ * unsharded run. */
+#define PFT_PEER_HANDLE_BYTES 64
+PFT_API int pft_tracker_peer_export(pft_tracker* t, void* handle64);
+PFT_API int pft_tracker_peer_attach(pft_tracker* t, const void* handles /* nranks x PFT_PEER_HANDLE_BYTES */);
+PFT_API int pft_tracker_peer_detach(pft_tracker* t);
+
 #ifdef __cplusplus
 }
 #endif

@@ -26,6 +26,7 @@ THREADS, PARTICLE_NUM, MAX_PARTICLE_NUM, ITERATION_NUM, NN_MODE, USE_HSV, USE_DI
  RESAMPLE_LIKELIHOOD_THR) = range(20, 32)
 STEP_NOISE_COV, INIT_NOISE_COV, INIT_NOISE_MEAN, BIN_SIZE = range(40, 44)
 NN_EXACT = 0
+PEER_HANDLE_BYTES = 64
 SAMPLER_CDF, SAMPLER_CDF_VDC = 1, 2
 
 
@@ -106,6 +107,9 @@ SIGNATURES = {
     "pft_cloud_broadcast": (_i, [_vp, _sz, _i]),
     "pft_tracker_comm_init": (_i, [_vp, _i, _i, _vp]),
     "pft_tracker_comm_destroy": (_i, [_vp]),
+    "pft_tracker_peer_export": (_i, [_vp, _vp]),
+    "pft_tracker_peer_attach": (_i, [_vp, _vp]),
+    "pft_tracker_peer_detach": (_i, [_vp]),
 }
 
 _lib = None

@@ -135,6 +135,11 @@ struct pft_tracker {
   // sharding (comm = the context's communicator when this tracker exchanges over NCCL)
   void* comm = nullptr;
   int nranks = 1, rank = 0;
+  // NVLink peer exchange (pft_tracker_peer_*): the local window + the peers' windows mapped with CUDA IPC
+  bool peer_mode = false;
+  void* peer_local = nullptr;
+  size_t peer_bytes = 0;
+  PeerSet peers{};
   // graph
   bool graph_enabled = true;
   cudaGraphExec_t graph_exec = nullptr;
@@ -273,6 +278,10 @@ int ensure_particle_buffers(pft_tracker* t) {
     }
   }
   if (cap == t->n_cap) return PFT_OK;
+  if (t->peer_local) {
+    set_last_error("the particle capacity (%d -> %d) cannot change once the peer window is exported", t->n_cap, cap);
+    return PFT_ERR_STATE;
+  }
   invalidate_graph(t);
   PFT_CUDA_TRY(cudaStreamSynchronize(s));
   const int old_cap = t->n_cap;
@@ -483,9 +492,14 @@ int weight_phase_box(pft_tracker* t) {
 
 // crop box exchange: union over ranks
 int weight_comm_box(pft_tracker* t) {
-  if (!t->comm) return PFT_OK;
   cudaStream_t s = t->ctx->stream;
   TrackerState* st = t->st.as<TrackerState>();
+  if (t->peer_mode) {
+    peer_box_exchange_kernel<<<1, 32, 0, s>>>(st, t->peers);
+    PFT_LAUNCH_CHECK();
+    return PFT_OK;
+  }
+  if (!t->comm) return PFT_OK;
   PFT_NCCL_TRY(g_nccl.GroupStart());
   PFT_NCCL_TRY(g_nccl.AllReduce(st->aabb, st->aabb, 3, kNcclFloat, kNcclMin, t->comm, s));
   PFT_NCCL_TRY(g_nccl.AllReduce(st->aabb + 3, st->aabb + 3, 3, kNcclFloat, kNcclMax, t->comm, s));
@@ -550,14 +564,14 @@ int weight_phase_eval(pft_tracker* t) {
   PFT_LAUNCH_CHECK();
   if (t->timing) { PFT_CUDA_TRY(cudaEventRecord(t->ev_w[2 * t->n_ev_used + 1], s)); t->n_ev_used++; }
   raw_weights_kernel<<<blocks_for(local_cap, 256, sm * 4), 256, 0, s>>>(st, t->partial.as<double>(), t->chunks, t->n_cap, t->raw.as<float>(), local_cap,
-                                                                       t->nranks, t->rank);
+                                                                       t->nranks, t->rank, t->peers, t->peer_mode ? 1 : 0);
   PFT_LAUNCH_CHECK();
   return PFT_OK;
 }
 
 // raw weight exchange: every rank ends up with all raw weights
 int weight_comm_raw(pft_tracker* t) {
-  if (!t->comm) return PFT_OK;
+  if (t->peer_mode || !t->comm) return PFT_OK;  // peer mode: raw_weights_kernel has already pushed the values
   const int local_cap = t->slice_cap();
   PFT_NCCL_TRY(g_nccl.AllGather(t->raw.as<float>() + (size_t)t->rank * local_cap, t->raw.as<float>(), (size_t)local_cap, kNcclFloat, t->comm,
                                 t->ctx->stream));
@@ -569,7 +583,7 @@ int weight_phase_normalize(pft_tracker* t) {
   int rc = check_weight_ready(t);
   if (rc) return rc;
   normalize_kernel<<<1, 1024, 0, t->ctx->stream>>>(t->st.as<TrackerState>(), t->parts[t->cur].as<DevParticle>(), t->raw.as<float>(), t->alpha, t->nranks,
-                                                   t->slice_cap(), t->input->d_hdr());
+                                                   t->slice_cap(), t->input->d_hdr(), t->peer_mode ? reinterpret_cast<PeerWindow*>(t->peer_local) : nullptr);
   PFT_LAUNCH_CHECK();
   t->changed = true;  // change detector is off upstream => changed_ = true after every weight()
   return PFT_OK;
@@ -657,6 +671,7 @@ void pft_tracker_destroy(pft_tracker* t) {
   for (auto e : t->ev_w) cudaEventDestroy(e);
   if (t->ev_c0) cudaEventDestroy(t->ev_c0);
   if (t->ev_c1) cudaEventDestroy(t->ev_c1);
+  pft_tracker_peer_detach(t);
   release_all(t);
   delete t;
 }
@@ -885,6 +900,7 @@ static int read_state(pft_tracker* t, TrackerState* host) {
   PFT_CUDA_TRY(cudaMemcpyAsync(t->ctx->pinned, t->st.p, sizeof(TrackerState), cudaMemcpyDeviceToHost, s));
   PFT_CUDA_TRY(cudaStreamSynchronize(s));
   memcpy(host, t->ctx->pinned, sizeof(TrackerState));
+  if (host->peer_error) { set_last_error("NVLink peer exchange timed out: a peer rank did not reach the same weight()"); return PFT_ERR_COMM; }
   return PFT_OK;
 }
 
@@ -1111,7 +1127,8 @@ int pft_tracker_get_raw_weights(pft_tracker* t, float* out, size_t capacity, siz
   if (n == 0) return PFT_OK;
   const int slice = t->slice_cap();
   std::vector<float> all((size_t)slice * t->nranks);
-  PFT_CUDA_TRY(cudaMemcpy(all.data(), t->raw.p, all.size() * sizeof(float), cudaMemcpyDeviceToHost));
+  const void* src = t->peer_mode ? (const void*)reinterpret_cast<PeerWindow*>(t->peer_local)->raw : (const void*)t->raw.p;
+  PFT_CUDA_TRY(cudaMemcpy(all.data(), src, all.size() * sizeof(float), cudaMemcpyDeviceToHost));
   for (size_t i = 0; i < n; ++i) out[i] = all[(i % t->nranks) * slice + i / t->nranks];
   return PFT_OK;
 }
@@ -1306,6 +1323,74 @@ int pft_tracker_set_shard(pft_tracker* t, int nranks, int rank) {
   if (nranks < 1 || rank < 0 || rank >= nranks) { set_last_error("bad rank %d of %d", rank, nranks); return PFT_ERR_INVALID; }
   if (t->n_cap > 0) { set_last_error("pft_tracker_set_shard must precede the first compute()/set_particles()"); return PFT_ERR_STATE; }
   t->nranks = nranks; t->rank = rank;
+  invalidate_graph(t);
+  return PFT_OK;
+}
+
+// ------------------------------------------------------------------ NVLink peer exchange (replaces the NCCL collectives)
+// The two exchange steps of weight() become peer stores issued by the producing kernels over NVLink into windows
+// that every rank maps with CUDA IPC (see PeerWindow in pft_tracker_kernels.cuh).  Call order on every rank:
+//   set_shard / comm_init (rank layout) -> particle numbers -> peer_export -> [host framework all-gathers the
+//   64-byte handles] -> peer_attach -> compute ...
+int pft_tracker_peer_export(pft_tracker* t, void* handle64) {
+  if (!t || !handle64) { set_last_error("null argument"); return PFT_ERR_INVALID; }
+  if (t->nranks < 2) { set_last_error("peer exchange needs a rank layout: call pft_tracker_set_shard / pft_tracker_comm_init first"); return PFT_ERR_STATE; }
+  if (t->nranks > kMaxPeers) { set_last_error("peer exchange supports up to %d ranks", kMaxPeers); return PFT_ERR_INVALID; }
+  static_assert(sizeof(cudaIpcMemHandle_t) == PFT_PEER_HANDLE_BYTES, "handle size");
+  PFT_CUDA_TRY(cudaSetDevice(t->ctx->device));
+  int rc = ensure_particle_buffers(t);
+  if (rc) return rc;
+  if (!t->peer_local) {
+    const size_t bytes = sizeof(PeerWindow) + (size_t)t->slice_cap() * t->nranks * sizeof(float);
+    PFT_CUDA_TRY(cudaMalloc(&t->peer_local, bytes));
+    PFT_CUDA_TRY(cudaMemset(t->peer_local, 0, bytes));
+    PFT_CUDA_TRY(cudaDeviceSynchronize());
+    t->peer_bytes = bytes;
+  }
+  cudaIpcMemHandle_t h;
+  PFT_CUDA_TRY(cudaIpcGetMemHandle(&h, t->peer_local));
+  memcpy(handle64, &h, sizeof(h));
+  return PFT_OK;
+}
+
+int pft_tracker_peer_attach(pft_tracker* t, const void* handles) {
+  if (!t || !handles) { set_last_error("null argument"); return PFT_ERR_INVALID; }
+  if (!t->peer_local) { set_last_error("pft_tracker_peer_export must precede pft_tracker_peer_attach"); return PFT_ERR_STATE; }
+  if (t->peer_mode) { set_last_error("peer windows are already attached"); return PFT_ERR_STATE; }
+  PFT_CUDA_TRY(cudaSetDevice(t->ctx->device));
+  PeerSet ps{};
+  ps.nranks = t->nranks; ps.rank = t->rank;
+  for (int r = 0; r < t->nranks; ++r) {
+    if (r == t->rank) { ps.win[r] = reinterpret_cast<PeerWindow*>(t->peer_local); continue; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char*)handles + (size_t)r * PFT_PEER_HANDLE_BYTES, sizeof(h));
+    void* p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      set_last_error("cudaIpcOpenMemHandle(rank %d) -> %s (peer exchange needs NVLink/P2P between the GPUs of one node)", r, cudaGetErrorString(e));
+      cudaGetLastError();
+      for (int q = 0; q < r; ++q) if (q != t->rank && ps.win[q]) cudaIpcCloseMemHandle(ps.win[q]);
+      return PFT_ERR_COMM;
+    }
+    ps.win[r] = reinterpret_cast<PeerWindow*>(p);
+  }
+  t->peers = ps;
+  t->peer_mode = true;
+  invalidate_graph(t);
+  return PFT_OK;
+}
+
+int pft_tracker_peer_detach(pft_tracker* t) {
+  if (!t) { set_last_error("null tracker"); return PFT_ERR_INVALID; }
+  if (!t->peer_local && !t->peer_mode) return PFT_OK;
+  cudaSetDevice(t->ctx->device);
+  cudaStreamSynchronize(t->ctx->stream);
+  if (t->peer_mode) {
+    for (int r = 0; r < t->peers.nranks; ++r) if (r != t->peers.rank && t->peers.win[r]) cudaIpcCloseMemHandle(t->peers.win[r]);
+  }
+  if (t->peer_local) cudaFree(t->peer_local);
+  t->peer_local = nullptr; t->peer_bytes = 0; t->peer_mode = false;
+  t->peers = PeerSet{};
   invalidate_graph(t);
   return PFT_OK;
 }

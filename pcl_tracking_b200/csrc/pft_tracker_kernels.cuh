@@ -29,7 +29,71 @@ struct TrackerState {
   // nearest-neighbour distance statistics of the last weight() (micrometres, matched pairs only): they steer the
   // cell size of the next index build.  Integer sums: independent of the order the atomics land in.
   unsigned long long nn_sum_um, nn_count;
+  unsigned int peer_epoch;       // weight() calls so far in peer (NVLink P2P) exchange mode
+  unsigned int peer_blocks_done; // raw_weights_kernel blocks that have pushed their slice this epoch
+  unsigned int peer_error;       // a wait on a peer's flag timed out (sticky)
 };
+
+// ------------------------------------------------------------------ NVLink peer exchange (one process per GPU)
+// Every rank owns one PeerWindow in its HBM, mapped into all peers with CUDA IPC.  The two exchange steps of weight()
+// are plain peer stores issued by the producing kernels themselves, followed by a flag barrier:
+//   crop box    every rank stores its six values into slot [rank] of every window, signals, waits, reduces locally;
+//   raw weights raw_weights_kernel stores every value into every window; its last block signals; normalize_kernel waits.
+// Flags only ever grow (epoch numbered), so nothing has to be reset between frames or graph replays.  The box slots
+// are double-buffered by epoch parity; the raw-weight area needs no second buffer: a rank can only push the weights of
+// epoch e+1 after it has passed the box barrier of e+1, which every rank enters after its normalize of epoch e.
+constexpr int kMaxPeers = 16;
+struct PeerWindow {
+  float box[2][kMaxPeers][8];  // [epoch parity][source rank][minx,miny,minz,maxx,maxy,maxz,-,-]
+  unsigned int flag_box;       // += 1 by every rank per epoch
+  unsigned int flag_raw;       // += 1 by every rank per epoch
+  unsigned int pad[30];
+  float raw[1];                // [nranks][slice_cap] gathered raw weights (the allocation is larger)
+};
+struct PeerSet {
+  PeerWindow* win[kMaxPeers];  // win[r] = rank r's window as mapped here (win[rank] = the local one)
+  int nranks, rank;
+};
+
+__device__ __forceinline__ bool peer_wait(volatile unsigned int* flag, unsigned int target, unsigned int* error) {
+  const long long t0 = clock64();
+  while ((int)(*flag - target) < 0) {
+    if (clock64() - t0 > 8000000000ll) { *error = 1u; return false; }  // ~4 s: a peer is gone; give up instead of hanging the GPU
+    __nanosleep(64);
+  }
+  __threadfence_system();
+  return true;
+}
+
+// crop box all-reduce over NVLink: one warp.  Runs right after aabb_kernel.
+__global__ void peer_box_exchange_kernel(TrackerState* st, PeerSet ps) {
+  const int lane = threadIdx.x;
+  PeerWindow* me = ps.win[ps.rank];
+  unsigned int e = 0;
+  if (lane == 0) { e = st->peer_epoch + 1u; st->peer_epoch = e; st->peer_blocks_done = 0u; }
+  e = __shfl_sync(kFull, e, 0);
+  const int cur = e & 1u;
+  // lane = (destination rank, component): 8 floats to each of up to 4 ranks per pass
+  for (int r0 = 0; r0 < ps.nranks; r0 += 4) {
+    const int r = r0 + (lane >> 3), d = lane & 7;
+    if (r < ps.nranks && d < 6) ps.win[r]->box[cur][ps.rank][d] = st->aabb[d];
+  }
+  __threadfence_system();
+  __syncwarp();
+  if (lane < ps.nranks) atomicAdd_system(&ps.win[lane]->flag_box, 1u);
+  bool ok = true;
+  if (lane == 0) ok = peer_wait(&me->flag_box, e * (unsigned int)ps.nranks, &st->peer_error);
+  ok = __shfl_sync(kFull, ok, 0);
+  if (!ok) return;
+  if (lane < 6) {
+    float v = __ldcg(&me->box[cur][0][lane]);
+    for (int r = 1; r < ps.nranks; ++r) {
+      const float o = __ldcg(&me->box[cur][r][lane]);
+      v = lane < 3 ? fminf(v, o) : fmaxf(v, o);
+    }
+    st->aabb[lane] = v;
+  }
+}
 
 struct NoiseParams {      // host-precomputed square roots (IEEE, identical to the oracle's)
   double mean[6];
@@ -1160,29 +1224,52 @@ __global__ void __launch_bounds__(THREADS, 1) weight_kernel(const WeightArgs a) 
 // Where particle i's raw weight lives in the all-gathered buffer [nranks][slice_cap].
 __device__ __forceinline__ int raw_slot(int i, int nranks, int slice_cap) { return (i % nranks) * slice_cap + i / nranks; }
 
-// raw weight = -(float)sum over chunks (fixed order).  Used on its own before the NCCL all-gather.
-__global__ void raw_weights_kernel(const TrackerState* __restrict__ st, const double* __restrict__ partial, int chunks, int n_max,
-                                   float* __restrict__ raw, int slice_cap, int nranks, int rank) {
+// raw weight = -(float)sum over chunks (fixed order).  In peer mode the kernel IS the all-gather: every value is
+// stored into every rank's window over NVLink and the last block to finish raises the peers' flags.
+__global__ void raw_weights_kernel(TrackerState* st, const double* __restrict__ partial, int chunks, int n_max,
+                                   float* __restrict__ raw, int slice_cap, int nranks, int rank, PeerSet ps, int peer_mode) {
   const int n = st->particle_num;
   for (int l = blockIdx.x * blockDim.x + threadIdx.x; rank + l * nranks < n; l += gridDim.x * blockDim.x) {
     const int i = rank + l * nranks;
     double v = 0.0;
     for (int c = 0; c < chunks; ++c) v += partial[(size_t)c * n_max + i];
-    raw[rank * slice_cap + l] = -(float)v;
+    const float w = -(float)v;
+    if (peer_mode) {
+      for (int r = 0; r < nranks; ++r) ps.win[r]->raw[rank * slice_cap + l] = w;
+    } else {
+      raw[rank * slice_cap + l] = w;
+    }
+  }
+  if (peer_mode) {
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned int done = atomicAdd(&st->peer_blocks_done, 1u) + 1u;
+      if (done == gridDim.x) {  // every block of this rank has pushed its values
+        __threadfence_system();
+        for (int r = 0; r < nranks; ++r) atomicAdd_system(&ps.win[r]->flag_raw, 1u);
+      }
+    }
   }
 }
 
 // ------------------------------------------------------------------ K4a: normalizeWeight (one block)
-__global__ void __launch_bounds__(1024) normalize_kernel(TrackerState* st, DevParticle* parts, const float* __restrict__ raw, double alpha,
-                                                         int nranks, int slice_cap, const CloudHeader* __restrict__ scene_hdr) {
+__global__ void __launch_bounds__(1024) normalize_kernel(TrackerState* st, DevParticle* parts, const float* raw, double alpha,
+                                                         int nranks, int slice_cap, const CloudHeader* __restrict__ scene_hdr,
+                                                         PeerWindow* peer_window /* non-null: wait for the peers' raw weights */) {
   __shared__ double red[32];
   __shared__ double s_min, s_max, s_sum;
+  if (peer_window) {
+    if (threadIdx.x == 0) peer_wait(&peer_window->flag_raw, st->peer_epoch * (unsigned int)nranks, &st->peer_error);
+    __syncthreads();
+    raw = peer_window->raw;
+  }
   if (scene_hdr->n <= 0) return;  // Tracker::initCompute fails on an empty input cloud: compute() is a no-op
   const int n = st->particle_num;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   double wmin = DBL_MAX, wmax = -DBL_MAX;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const double w = (double)raw[raw_slot(i, nranks, slice_cap)];
+    const double w = (double)__ldcg(&raw[raw_slot(i, nranks, slice_cap)]);
     if (wmin > w) wmin = w;
     if (w != 0.0 && wmax < w) wmax = w;
   }
@@ -1198,7 +1285,7 @@ __global__ void __launch_bounds__(1024) normalize_kernel(TrackerState* st, DevPa
   wmin = s_min; wmax = s_max;
   double sum = 0.0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    float w = raw[raw_slot(i, nranks, slice_cap)];
+    float w = __ldcg(&raw[raw_slot(i, nranks, slice_cap)]);
     if (wmax != wmin) {
       if (w != 0.0f) w = (float)exp(1.0 - alpha * ((double)w - wmin) / (wmax - wmin));
     } else {

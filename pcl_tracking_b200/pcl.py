@@ -531,6 +531,23 @@ class ParticleFilterOMPTracker:
     def commDestroy(self):
         check(capi.load().pft_tracker_comm_destroy(self._h))
 
+    # NVLink peer exchange: the collectives of weight() as peer stores from the producing kernels
+    def peerExport(self):
+        """Allocates this rank's exchange window and returns its CUDA IPC handle (bytes).  Needs the rank
+        layout (setShard / commInit) and the particle numbers to be set."""
+        buf = C.create_string_buffer(capi.PEER_HANDLE_BYTES)
+        check(capi.load().pft_tracker_peer_export(self._h, buf))
+        return bytes(buf.raw)
+
+    def peerAttach(self, handles):
+        """`handles`: the peerExport() results of all ranks in rank order (e.g. dist.all_gather_object)."""
+        blob = b"".join(bytes(h) for h in handles)
+        buf = C.create_string_buffer(blob, len(blob))
+        check(capi.load().pft_tracker_peer_attach(self._h, buf))
+
+    def peerDetach(self):
+        check(capi.load().pft_tracker_peer_detach(self._h))
+
     def __del__(self):
         try:
             if self._h:
