@@ -190,6 +190,8 @@ PFT_API int pft_tracker_get_nn(pft_tracker* t, int particle, int32_t* idx, float
 /* Device time in ms of the stages of the last compute(): weight kernel only, whole compute. */
 PFT_API int pft_tracker_get_timing(pft_tracker* t, float* weight_kernel_ms, float* compute_ms);
 PFT_API int pft_tracker_enable_timing(pft_tracker* t, int on);
+/* timing mode: device time in ms of every kernel of the last compute(), in launch order (static name strings) */
+PFT_API int pft_tracker_get_kernel_times(pft_tracker* t, const char** names, float* ms, int capacity, int* n);
 
 /* dims[3], level (cell edge = resolution x 2^level), n_cropped, n_cells, use_lists, list_cells of the scene index built by the last weight() */
 PFT_API int pft_tracker_get_index_info(pft_tracker* t, int* info8);

@@ -93,6 +93,7 @@ SIGNATURES = {
     "pft_tracker_get_nn": (_i, [_vp, _i, _vp, _vp, _sz]),
     "pft_tracker_get_timing": (_i, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "pft_tracker_enable_timing": (_i, [_vp, _i]),
+    "pft_tracker_get_kernel_times": (_i, [_vp, _vp, _vp, _i, C.POINTER(C.c_int)]),
     "pft_tracker_get_index_info": (_i, [_vp, _vp]),
     "pft_tracker_graph_replays": (_i, [_vp, C.POINTER(C.c_uint64)]),
     "pft_tracker_weight_phase": (_i, [_vp, _i]),

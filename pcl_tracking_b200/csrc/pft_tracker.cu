@@ -132,6 +132,10 @@ struct pft_tracker {
   std::vector<cudaEvent_t> ev_w;  // pairs around weight_kernel launches of the last compute
   cudaEvent_t ev_c0 = nullptr, ev_c1 = nullptr;
   int n_ev_used = 0;
+  // timing mode: one event after every kernel of the last compute(), for the per-kernel breakdown
+  std::vector<cudaEvent_t> ev_k;
+  std::vector<const char*> ev_k_name;
+  int n_ev_k = 0;
   // sharding (comm = the context's communicator when this tracker exchanges over NCCL)
   void* comm = nullptr;
   int nranks = 1, rank = 0;
@@ -150,7 +154,7 @@ struct pft_tracker {
   int graph_nodes = 0;
   // device buffers
   DevBuf st, parts[2], mats, slot_aabb, model, model_perm, model_tmp, sort_keys, sort_idx, bbox, raw, partial, cdf, cdf_total, ancestors, bin_keys, tbl_rep,
-      tbl_min, slot_of, klb, d_usel, d_normals, d_umot, idx_hdr, cell_start, ipts, ihsv, icount, dbg_idx, dbg_d2, d_trans, row_table, fcount, flists, fneeded, fneeded_blocks, fneeded_list, ffar_list, xlists, xcount;
+      tbl_min, slot_of, klb, d_usel, d_normals, d_umot, idx_hdr, cell_start, ipts, ihsv, icount, dbg_idx, dbg_d2, d_trans, row_table, fcount, flists, fneeded, fneeded_list, ffar_list, xlists, xcount;
   int weight_smem = 0;  // dynamic shared memory of the weight kernel (bytes)
   int tbl_size = 0;
   int n_slots = 0;
@@ -163,11 +167,24 @@ namespace {
 
 void invalidate_graph(pft_tracker* t) { t->config_version++; }
 
+// timing mode only: an event on the stream after the kernel just launched
+void stage_mark(pft_tracker* t, const char* name) {
+  if (!t->timing) return;
+  if ((int)t->ev_k.size() <= t->n_ev_k) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    t->ev_k.push_back(e);
+    t->ev_k_name.push_back(name);
+  }
+  t->ev_k_name[t->n_ev_k] = name;
+  cudaEventRecord(t->ev_k[t->n_ev_k++], t->ctx->stream);
+}
+
 void release_all(pft_tracker* t) {
   DevBuf* bufs[] = {&t->st, &t->parts[0], &t->parts[1], &t->mats, &t->slot_aabb, &t->model, &t->model_perm, &t->model_tmp, &t->sort_keys, &t->sort_idx,
                     &t->bbox, &t->raw, &t->partial, &t->cdf, &t->cdf_total, &t->ancestors, &t->bin_keys, &t->tbl_rep, &t->tbl_min, &t->slot_of, &t->klb,
                     &t->d_usel, &t->d_normals, &t->d_umot, &t->idx_hdr, &t->cell_start, &t->ipts, &t->ihsv, &t->icount, &t->dbg_idx,
-                    &t->dbg_d2, &t->d_trans, &t->row_table, &t->fcount, &t->flists, &t->fneeded, &t->fneeded_blocks, &t->fneeded_list, &t->ffar_list, &t->xlists, &t->xcount};
+                    &t->dbg_d2, &t->d_trans, &t->row_table, &t->fcount, &t->flists, &t->fneeded, &t->fneeded_list, &t->ffar_list, &t->xlists, &t->xcount};
   for (auto* b : bufs) b->release();
 }
 
@@ -241,6 +258,8 @@ int upload_row_table(pft_tracker* t) {
   PFT_CUDA_TRY(cudaFuncSetAttribute(weight_kernel<true, kWeightThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
   PFT_CUDA_TRY(cudaFuncSetAttribute(weight_kernel<false, kWeightThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
   t->weight_smem = dyn;
+  if (t->list_max_cells / 8 + 64 > max_optin - 2048) t->list_max_cells = (max_optin - 4096) * 8;  // the mark kernel keeps one bit per fine cell in shared memory
+  PFT_CUDA_TRY(cudaFuncSetAttribute(cand_mark_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, t->list_max_cells / 8 + 64));
   return PFT_OK;
 }
 
@@ -270,7 +289,6 @@ int ensure_particle_buffers(pft_tracker* t) {
       if ((rc = t->flists.reserve(((size_t)t->list_max_cells + 1) * kListK * sizeof(unsigned short)))) return rc;
       if ((rc = t->fneeded.reserve(((size_t)t->list_max_cells + 16) * sizeof(unsigned int)))) return rc;
       // blocks of 2x2x2 fine cells: at most ceil(d/2)^3 <= (d+1)^3/8, bounded generously by cells/2 + 4096
-      if ((rc = t->fneeded_blocks.reserve(((size_t)t->list_max_cells / 2 + 4096) * sizeof(unsigned int)))) return rc;
       if ((rc = t->fneeded_list.reserve(((size_t)t->list_max_cells / 2 + 4096) * sizeof(int)))) return rc;
       if ((rc = t->ffar_list.reserve(((size_t)t->list_max_cells + 16) * sizeof(int)))) return rc;
       if ((rc = t->xlists.reserve((size_t)kListXCells * kListKX * sizeof(unsigned short)))) return rc;
@@ -365,6 +383,7 @@ int prepare_draws(pft_tracker* t, int slot, int count, const float** usel, const
   draws_kernel<<<blocks_for(count, 256, t->ctx->sm_count * 4), 256, 0, s>>>(t->st.as<TrackerState>(), t->d_usel.as<float>(), t->d_normals.as<float>(),
                                                                         t->d_umot.as<float>(), count, t->seed);
   PFT_LAUNCH_CHECK();
+  stage_mark(t, "draws_kernel");
   *usel = t->d_usel.as<float>(); *normals = t->d_normals.as<float>(); *umot = t->d_umot.as<float>();
   return PFT_OK;
 }
@@ -423,6 +442,7 @@ int stage_init_particles(pft_tracker* t) {
   init_particles_kernel<<<blocks_for(t->particle_num, 128, 1 << 20), 128, 0, s>>>(t->st.as<TrackerState>(), t->parts[t->cur].as<DevParticle>(),
                                                                                    t->particle_num, t->d_trans.as<float>(), np, normals);
   PFT_LAUNCH_CHECK();
+  stage_mark(t, "init_particles_kernel");
   t->has_particles = true;
   return PFT_OK;
 }
@@ -442,6 +462,7 @@ int stage_resample(pft_tracker* t, int slot) {
   cdf_kernel<<<1, 1024, 0, s>>>(st, old_parts, t->cdf.as<unsigned long long>(), t->cdf_total.as<unsigned long long>(), t->tbl_rep.as<int>(),
                                 t->tbl_min.as<int>(), t->kld ? t->tbl_size : 0);
   PFT_LAUNCH_CHECK();
+  stage_mark(t, "cdf_kernel");
   ResampleArgs a;
   a.st = st; a.old_parts = old_parts; a.new_parts = new_parts;
   a.cdf = t->cdf.as<unsigned long long>(); a.cdf_total = t->cdf_total.as<unsigned long long>();
@@ -455,12 +476,15 @@ int stage_resample(pft_tracker* t, int slot) {
   a.kld = t->kld ? 1 : 0; a.n_max = t->max_particle_num; a.sampler = t->sampler;
   resample_kernel<<<blocks_for(count, 128, t->ctx->sm_count * 16), 128, 0, s>>>(a);
   PFT_LAUNCH_CHECK();
+  stage_mark(t, "resample_kernel");
   if (t->kld) {
     kld_insert_kernel<<<blocks_for(count, 128, t->ctx->sm_count * 16), 128, 0, s>>>(t->bin_keys.as<int>(), t->max_particle_num, t->tbl_rep.as<int>(),
                                                                                     t->tbl_min.as<int>(), t->slot_of.as<int>(), (unsigned)(t->tbl_size - 1));
     PFT_LAUNCH_CHECK();
+    stage_mark(t, "kld_insert_kernel");
     kld_stop_kernel<<<1, 1024, 0, s>>>(st, t->tbl_min.as<int>(), t->slot_of.as<int>(), t->klb.as<double>(), t->max_particle_num, t->input->d_hdr());
     PFT_LAUNCH_CHECK();
+    stage_mark(t, "kld_stop_kernel");
   }
   t->cur ^= 1;
   return PFT_OK;
@@ -484,9 +508,16 @@ int weight_phase_box(pft_tracker* t) {
   DevParticle* parts = t->parts[t->cur].as<DevParticle>();
   matrices_kernel<<<blocks_for(t->n_cap, 128, sm * 8), 128, 0, s>>>(st, parts, t->mats.as<float>());
   PFT_LAUNCH_CHECK();
-  aabb_kernel<<<blocks_for((long long)t->n_slots * 32, 256, sm * 8), 256, 0, s>>>(st, t->model.as<float4>(), t->M, t->mats.as<float>(),
-                                                                               t->slot_aabb.as<float>(), t->n_slots, t->nranks, t->rank);
+  stage_mark(t, "matrices_kernel");
+  if (t->n_slots <= sm * 32) {
+    aabb_kernel<4><<<std::min(t->n_slots, sm * 16), 128, 0, s>>>(st, t->model.as<float4>(), t->M, t->mats.as<float>(), t->slot_aabb.as<float>(), t->n_slots,
+                                                                t->nranks, t->rank);
+  } else {
+    aabb_kernel<1><<<std::min(t->n_slots, sm * 64), 32, 0, s>>>(st, t->model.as<float4>(), t->M, t->mats.as<float>(), t->slot_aabb.as<float>(), t->n_slots,
+                                                               t->nranks, t->rank);
+  }
   PFT_LAUNCH_CHECK();
+  stage_mark(t, "aabb_kernel");
   return PFT_OK;
 }
 
@@ -497,6 +528,7 @@ int weight_comm_box(pft_tracker* t) {
   if (t->peer_mode) {
     peer_box_exchange_kernel<<<1, 32, 0, s>>>(st, t->peers);
     PFT_LAUNCH_CHECK();
+    stage_mark(t, "peer_box_exchange_kernel");
     return PFT_OK;
   }
   if (!t->comm) return PFT_OK;
@@ -520,27 +552,37 @@ int weight_phase_eval(pft_tracker* t) {
   const float inv_leaf = 1.0f / (float)t->search_res;
   const int gscene = blocks_for(ncap_scene, 256, sm * 4);
   index_begin_kernel<<<sm, 256, 0, s>>>(st, hdr, t->icount.as<int>(), inv_leaf, t->index_level, t->max_cells, t->list_mode ? t->list_max_cells : 0,
-                                        t->list_mode == 2 ? 0 : t->M, t->nranks, t->rank, t->fneeded.as<unsigned int>(), t->fneeded_blocks.as<unsigned int>(), t->xcount.as<int>());
+                                        t->list_mode == 2 ? 0 : t->M, t->nranks, t->rank, t->fneeded.as<unsigned int>(), t->xcount.as<int>());
   PFT_LAUNCH_CHECK();
+  stage_mark(t, "index_begin_kernel");
   index_count_kernel<<<gscene, 256, 0, s>>>(in->d_pts(), in->d_hdr(), hdr, t->icount.as<int>());
   PFT_LAUNCH_CHECK();
+  stage_mark(t, "index_count_kernel");
   index_scan_kernel<<<1, 1024, 0, s>>>(hdr, t->icount.as<int>(), t->cell_start.as<int>(), st, t->ipts.as<float4>());
   PFT_LAUNCH_CHECK();
+  stage_mark(t, "index_scan_kernel");
   index_scatter_kernel<<<gscene, 256, 0, s>>>(in->d_pts(), in->d_hdr(), hdr, t->cell_start.as<int>(), t->icount.as<int>(), t->ipts.as<float4>(),
                                               t->ihsv.as<unsigned int>());
   PFT_LAUNCH_CHECK();
+  stage_mark(t, "index_scatter_kernel");
   if (t->list_max_cells > 0 && t->list_mode) {
-    cand_mark_kernel<<<sm * 4, 256, 0, s>>>(st, hdr, t->model.as<float4>(), t->M, t->mats.as<float>(), t->fneeded.as<unsigned int>(),
-                                           t->fneeded_blocks.as<unsigned int>(), t->fneeded_list.as<int>(), t->xcount.as<int>(), t->nranks, t->rank);
+    // dynamic shared memory: one bit per fine cell the lists are sized for
+    cand_mark_kernel<<<sm * 3, 256, (size_t)(t->list_max_cells / 8 + 64), s>>>(st, hdr, t->model.as<float4>(), t->M, t->mats.as<float>(), t->fneeded.as<unsigned int>(), t->nranks, t->rank);
     PFT_LAUNCH_CHECK();
+    stage_mark(t, "cand_mark_kernel");
+    cand_collect_kernel<<<sm * 2, 256, 0, s>>>(hdr, t->fneeded.as<unsigned int>(), t->fneeded_list.as<int>(), t->xcount.as<int>());
+    PFT_LAUNCH_CHECK();
+    stage_mark(t, "cand_collect_kernel");
     cand_build_kernel<<<sm * 8, 256, 0, s>>>(hdr, t->cell_start.as<int>(), t->ipts.as<float4>(), t->max_dist * t->max_dist, t->fcount.as<unsigned short>(), t->flists.as<unsigned short>(),
                                             t->fneeded.as<unsigned int>(), t->fneeded_list.as<int>(), t->xlists.as<unsigned short>(),
                                             t->xcount.as<int>(), t->ffar_list.as<int>());
     PFT_LAUNCH_CHECK();
+    stage_mark(t, "cand_build_kernel");
     cand_build_far_kernel<<<sm * 8, 256, 0, s>>>(hdr, t->cell_start.as<int>(), t->ipts.as<float4>(), t->max_dist * t->max_dist,
                                                 t->fcount.as<unsigned short>(), t->flists.as<unsigned short>(), t->xlists.as<unsigned short>(),
                                                 t->xcount.as<int>(), t->ffar_list.as<int>());
     PFT_LAUNCH_CHECK();
+    stage_mark(t, "cand_build_far_kernel");
   }
   WeightArgs a;
   a.st = st; a.hdr = hdr;
@@ -562,10 +604,12 @@ int weight_phase_eval(pft_tracker* t) {
   if (t->use_hsv) weight_kernel<true, kWeightThreads><<<wgrid, kWeightThreads, t->weight_smem, s>>>(a);
   else weight_kernel<false, kWeightThreads><<<wgrid, kWeightThreads, t->weight_smem, s>>>(a);
   PFT_LAUNCH_CHECK();
+  stage_mark(t, "weight_kernel");
   if (t->timing) { PFT_CUDA_TRY(cudaEventRecord(t->ev_w[2 * t->n_ev_used + 1], s)); t->n_ev_used++; }
   raw_weights_kernel<<<blocks_for(local_cap, 256, sm * 4), 256, 0, s>>>(st, t->partial.as<double>(), t->chunks, t->n_cap, t->raw.as<float>(), local_cap,
                                                                        t->nranks, t->rank, t->peers, t->peer_mode ? 1 : 0);
   PFT_LAUNCH_CHECK();
+  stage_mark(t, "raw_weights_kernel");
   return PFT_OK;
 }
 
@@ -585,6 +629,7 @@ int weight_phase_normalize(pft_tracker* t) {
   normalize_kernel<<<1, 1024, 0, t->ctx->stream>>>(t->st.as<TrackerState>(), t->parts[t->cur].as<DevParticle>(), t->raw.as<float>(), t->alpha, t->nranks,
                                                    t->slice_cap(), t->input->d_hdr(), t->peer_mode ? reinterpret_cast<PeerWindow*>(t->peer_local) : nullptr);
   PFT_LAUNCH_CHECK();
+  stage_mark(t, "normalize_kernel");
   t->changed = true;  // change detector is off upstream => changed_ = true after every weight()
   return PFT_OK;
 }
@@ -602,6 +647,7 @@ int stage_update(pft_tracker* t) {
   if (!t->has_particles || !t->input) { set_last_error("update before weight"); return PFT_ERR_STATE; }
   update_kernel<<<1, 1024, 0, t->ctx->stream>>>(t->st.as<TrackerState>(), t->parts[t->cur].as<DevParticle>(), t->input->d_hdr());
   PFT_LAUNCH_CHECK();
+  stage_mark(t, "update_kernel");
   return PFT_OK;
 }
 
@@ -669,6 +715,7 @@ void pft_tracker_destroy(pft_tracker* t) {
   cudaStreamSynchronize(t->ctx->stream);
   if (t->graph_exec) cudaGraphExecDestroy(t->graph_exec);
   for (auto e : t->ev_w) cudaEventDestroy(e);
+  for (auto e : t->ev_k) cudaEventDestroy(e);
   if (t->ev_c0) cudaEventDestroy(t->ev_c0);
   if (t->ev_c1) cudaEventDestroy(t->ev_c1);
   pft_tracker_peer_detach(t);
@@ -826,6 +873,7 @@ static int compute_one(pft_tracker* t) {
   if (t->timing) {
     if (!t->ev_c0) { PFT_CUDA_TRY(cudaEventCreate(&t->ev_c0)); PFT_CUDA_TRY(cudaEventCreate(&t->ev_c1)); }
     t->n_ev_used = 0;
+    t->n_ev_k = 0;
     PFT_CUDA_TRY(cudaEventRecord(t->ev_c0, s));
   }
   const bool steady = t->changed && t->graph_enabled && !t->timing && t->debug_nn == 0;
@@ -1178,6 +1226,24 @@ int pft_tracker_get_timing(pft_tracker* t, float* weight_ms, float* compute_ms) 
   if (cudaEventElapsedTime(&c, t->ev_c0, t->ev_c1) != cudaSuccess) { cudaGetLastError(); c = 0.f; }
   if (weight_ms) *weight_ms = w;
   if (compute_ms) *compute_ms = c;
+  return PFT_OK;
+}
+
+// timing mode: device time of every kernel of the last compute(), in launch order (the time between the event after
+// the previous kernel and the event after this one)
+int pft_tracker_get_kernel_times(pft_tracker* t, const char** names, float* ms, int capacity, int* n_out) {
+  if (!t) { set_last_error("null tracker"); return PFT_ERR_INVALID; }
+  if (!t->timing || !t->ev_c0) { set_last_error("timing is not enabled or no compute() has run"); return PFT_ERR_STATE; }
+  PFT_CUDA_TRY(cudaSetDevice(t->ctx->device));
+  PFT_CUDA_TRY(cudaStreamSynchronize(t->ctx->stream));
+  if (n_out) *n_out = t->n_ev_k;
+  if (t->n_ev_k > capacity) { set_last_error("capacity %d < %d", capacity, t->n_ev_k); return PFT_ERR_CAPACITY; }
+  for (int k = 0; k < t->n_ev_k; ++k) {
+    float v = 0.f;
+    if (cudaEventElapsedTime(&v, k ? t->ev_k[k - 1] : t->ev_c0, t->ev_k[k]) != cudaSuccess) { cudaGetLastError(); v = 0.f; }
+    if (names) names[k] = t->ev_k_name[k];
+    if (ms) ms[k] = v;
+  }
   return PFT_OK;
 }
 

@@ -263,17 +263,26 @@ __global__ void matrices_kernel(TrackerState* st, const DevParticle* __restrict_
   }
 }
 
-// One warp per slot.  Live slots of this rank's slice are recomputed; slots >= particle_num keep the
-// box of the last particle that occupied them (upstream's stale transed_reference_vector_ entries).
-__global__ void aabb_kernel(TrackerState* st, const float4* __restrict__ model, int M, const float* __restrict__ mats,
-                            float* __restrict__ slot_aabb, int n_slots, int nranks, int rank) {
+// Per-slot boxes + their union.  Live slots of this rank's slice are recomputed; slots >= particle_num keep the box
+// of the last particle that occupied them (upstream's stale transed_reference_vector_ entries).  A group of
+// WARPS warps (= one block) works on one slot at a time; the union is accumulated per block in registers and
+// reaches st->aabb through six atomics per block.  WARPS = 4 for small particle sets (more parallelism per slot),
+// 1 for large ones (no block barrier).
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) aabb_kernel(TrackerState* st, const float4* __restrict__ model, int M, const float* __restrict__ mats,
+                                                          float* __restrict__ slot_aabb, int n_slots, int nranks, int rank) {
+  __shared__ float s_red[WARPS][6];
   const int n = st->particle_num;
-  const int lane = threadIdx.x & 31;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  for (int s = warp; s < n_slots; s += nwarps) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  float un[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, ux[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};  // union over this block's slots (valid in every lane of warp 0)
+  for (int s = blockIdx.x; s < n_slots; s += gridDim.x) {
     float mn[3], mx[3];
-    if (s < n) {
+    if (s >= n) {
+      // stale slot: its stored box still takes part in the union (never used slots hold an inverted box)
+#pragma unroll
+      for (int d = 0; d < 3; ++d) { mn[d] = slot_aabb[(size_t)s * 6 + d]; mx[d] = slot_aabb[(size_t)s * 6 + 3 + d]; }
+      if (mn[0] > mx[0]) continue;
+    } else {
       if (s % nranks != rank) continue;  // another rank's live slot (particle i belongs to rank i % nranks)
       float m[12];
 #pragma unroll
@@ -282,7 +291,7 @@ __global__ void aabb_kernel(TrackerState* st, const float4* __restrict__ model, 
         m[4 * d] = r.x; m[4 * d + 1] = r.y; m[4 * d + 2] = r.z; m[4 * d + 3] = r.w;
       }
       mn[0] = mn[1] = mn[2] = FLT_MAX; mx[0] = mx[1] = mx[2] = -FLT_MAX;
-      for (int j = lane; j < M; j += 32) {
+      for (int j = threadIdx.x; j < M; j += WARPS * 32) {
         const float4 p = model[j];
         float x, y, z;
         xform(m, p.x, p.y, p.z, x, y, z);
@@ -291,15 +300,30 @@ __global__ void aabb_kernel(TrackerState* st, const float4* __restrict__ model, 
       }
 #pragma unroll
       for (int d = 0; d < 3; ++d) { mn[d] = warp_min(mn[d]); mx[d] = warp_max(mx[d]); }
-      if (lane < 3) slot_aabb[(size_t)s * 6 + lane] = mn[lane];
-      else if (lane < 6) slot_aabb[(size_t)s * 6 + lane] = mx[lane - 3];
-    } else {
+      if (WARPS > 1) {
+        __syncthreads();  // (s_red of the previous slot has been consumed)
+        if (lane == 0) {
 #pragma unroll
-      for (int d = 0; d < 3; ++d) { mn[d] = slot_aabb[(size_t)s * 6 + d]; mx[d] = slot_aabb[(size_t)s * 6 + 3 + d]; }
-      if (mn[0] > mx[0]) continue;  // never used
+          for (int d = 0; d < 3; ++d) { s_red[wid][d] = mn[d]; s_red[wid][3 + d] = mx[d]; }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) {
+#pragma unroll
+          for (int d = 0; d < 3; ++d) { mn[d] = fminf(mn[d], s_red[w][d]); mx[d] = fmaxf(mx[d], s_red[w][3 + d]); }
+        }
+      }
+      if (wid == 0) {
+        if (lane < 3) slot_aabb[(size_t)s * 6 + lane] = mn[lane];
+        else if (lane < 6) slot_aabb[(size_t)s * 6 + lane] = mx[lane - 3];
+      }
     }
-    if (lane < 3) atomic_min_float(&st->aabb[lane], mn[lane]);
-    else if (lane < 6) atomic_max_float(&st->aabb[lane], mx[lane - 3]);
+#pragma unroll
+    for (int d = 0; d < 3; ++d) { un[d] = fminf(un[d], mn[d]); ux[d] = fmaxf(ux[d], mx[d]); }
+  }
+  if (wid == 0 && un[0] <= ux[0]) {
+    if (lane < 3) atomic_min_float(&st->aabb[lane], un[lane]);
+    else if (lane < 6) atomic_max_float(&st->aabb[lane], ux[lane - 3]);
   }
 }
 
@@ -359,7 +383,7 @@ __device__ inline void compute_index_header(const float* aabb, float inv_leaf, i
 // that is d away from the surface walks ~pi (d/cell + 1)^2 rows and ~(d + cell)^2 candidates: cell ~ d balances them)
 __global__ void index_begin_kernel(const TrackerState* __restrict__ st, IndexHeader* hdr, int* cell_count, float inv_leaf, int base_level,
                                    int max_cells, int list_max_cells, int M, int nranks, int rank, unsigned int* needed_words,
-                                   unsigned int* needed_blocks, int* list_counters /* [0] extended lists handed out, [1] needed blocks, [2] cells queued for the far pass */) {
+                                   int* list_counters /* [0] extended lists handed out, [1] needed blocks, [2] cells queued for the far pass */) {
   __shared__ IndexHeader h;
   if (threadIdx.x == 0) {
     if (base_level < 0) {
@@ -382,9 +406,7 @@ __global__ void index_begin_kernel(const TrackerState* __restrict__ st, IndexHea
   const int nc = h.n_cells + 1;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nc; i += gridDim.x * blockDim.x) cell_count[i] = 0;
   if (h.use_lists) {
-    const int nb = ((h.f_dim[0] + 1) >> 1) * ((h.f_dim[1] + 1) >> 1) * ((h.f_dim[2] + 1) >> 1);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < h.f_cells; i += gridDim.x * blockDim.x) needed_words[i] = 0u;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nb; i += gridDim.x * blockDim.x) needed_blocks[i] = 0u;
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) { list_counters[0] = 0; list_counters[1] = 0; list_counters[2] = 0; }
 }
@@ -602,46 +624,94 @@ __device__ __forceinline__ float box_maxdist2(const float* lo, const float* hi, 
   return (dx * dx + dy * dy) + dz * dz;
 }
 
-// collects the fine cells that this rank's queries fall into (the lists of the others are never read)
-__global__ void cand_mark_kernel(const TrackerState* __restrict__ st, const IndexHeader* __restrict__ hdr, const float4* __restrict__ model, int M,
-                                 const float* __restrict__ mats, unsigned int* __restrict__ needed, unsigned int* __restrict__ needed_blocks,
-                                 int* __restrict__ needed_list, int* __restrict__ list_counters, int nranks, int rank) {
+// marks the fine cells that this rank's queries fall into (the lists of the others are never read).  No global
+// atomics and no global loads: a cell is flagged with a plain store (duplicates are harmless); cand_collect_kernel
+// then queues the blocks.  (Reading a flag back here costs a round trip between the two L2 partitions whenever
+// another SM has just stored to the line: measured 2.5x slower.)
+// The particle set is concentrated, so the same model points of different particles fall into the same cells: a
+// thread block therefore handles ONE group of kMarkUnroll x 32 consecutive model points for many particles and
+// remembers the cells it has flagged in a bitmap of the fine grid in shared memory (f_cells bits, dynamic): every
+// block stores every cell at most once.
+constexpr int kMarkUnroll = 4;
+__global__ void __launch_bounds__(256) cand_mark_kernel(const TrackerState* __restrict__ st, const IndexHeader* __restrict__ hdr, const float4* __restrict__ model, int M,
+                                                        const float* __restrict__ mats, unsigned int* __restrict__ needed, int nranks, int rank) {
+  extern __shared__ unsigned int s_bits[];  // (f_cells + 31) / 32 words
   __shared__ IndexHeader h;
   if (threadIdx.x == 0) h = *hdr;
   __syncthreads();
   if (!h.valid || !lists_on(h)) return;
+  const int words = (h.f_cells + 31) >> 5;
+  for (int i = threadIdx.x; i < words; i += blockDim.x) s_bits[i] = 0u;
+  __syncthreads();
   const int n = st->particle_num;
   const int n_local = n > rank ? (n - rank + nranks - 1) / nranks : 0;
-  const int lane = threadIdx.x & 31;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-  const int jchunks = (M + 31) >> 5;
-  const long long items = (long long)n_local * jchunks;  // one warp-item = 32 consecutive model points of one particle
-  for (long long it = warp; it < items; it += nwarps) {
-    const int l = (int)(it / jchunks), j = (int)(it - (long long)l * jchunks) * 32 + lane;
-    const int i = rank + l * nranks;
-    float m[12];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const int groups = (M + 32 * kMarkUnroll - 1) / (32 * kMarkUnroll);
+  const int per_group = max(1, (int)gridDim.x / groups);  // blocks that share one group of model points
+  const float inv_leaf = h.inv_leaf;
+  const int ox = h.f_origin[0], oy = h.f_origin[1], oz = h.f_origin[2];
+  const int fdx = h.f_dim[0], fdy = h.f_dim[1], fdz = h.f_dim[2];
+  for (int vb = blockIdx.x; vb < groups * per_group; vb += gridDim.x) {
+    const int g = vb % groups, pb = vb / groups;
+    const int j0 = g * (32 * kMarkUnroll) + lane;
+    float4 mp[kMarkUnroll];
 #pragma unroll
-    for (int d = 0; d < 3; ++d) {
-      const float4 r = reinterpret_cast<const float4*>(mats)[(size_t)i * 3 + d];
-      m[4 * d] = r.x; m[4 * d + 1] = r.y; m[4 * d + 2] = r.z; m[4 * d + 3] = r.w;
-    }
-    if (j < M) {
-      const float4 p = model[j];
-      float qx, qy, qz;
-      xform(m, p.x, p.y, p.z, qx, qy, qz);
-      const float big = 1.0e9f;
-      const int ix = (int)fminf(fmaxf(floorf(qx * h.inv_leaf), -big), big) - h.f_origin[0], iy = (int)fminf(fmaxf(floorf(qy * h.inv_leaf), -big), big) - h.f_origin[1],
-                iz = (int)fminf(fmaxf(floorf(qz * h.inv_leaf), -big), big) - h.f_origin[2];
-      if ((unsigned)ix < (unsigned)h.f_dim[0] && (unsigned)iy < (unsigned)h.f_dim[1] && (unsigned)iz < (unsigned)h.f_dim[2]) {
-        const int cell = (iz * h.f_dim[1] + iy) * h.f_dim[0] + ix;
-        if (needed[cell] == 0u) {  // (a cell that is already marked has its block queued)
-          needed[cell] = 1u;
-          // lists are built per block of 2x2x2 fine cells: append the block once
-          const int bdx = (h.f_dim[0] + 1) >> 1, bdy = (h.f_dim[1] + 1) >> 1;
-          const int blk = ((iz >> 1) * bdy + (iy >> 1)) * bdx + (ix >> 1);
-          if (atomicExch(&needed_blocks[blk], 1u) == 0u) needed_list[atomicAdd(&list_counters[1], 1)] = blk;
+    for (int u = 0; u < kMarkUnroll; ++u) mp[u] = (j0 + 32 * u < M) ? model[j0 + 32 * u] : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int l = pb * wpb + wid; l < n_local; l += per_group * wpb) {
+      const int i = rank + l * nranks;
+      const float4* mr = reinterpret_cast<const float4*>(mats) + (size_t)i * 3;
+      const float4 r0 = mr[0], r1 = mr[1], r2 = mr[2];
+      const float m[12] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w};
+#pragma unroll
+      for (int u = 0; u < kMarkUnroll; ++u) {
+        if (j0 + 32 * u < M) {
+          float qx, qy, qz;
+          xform(m, mp[u].x, mp[u].y, mp[u].z, qx, qy, qz);
+          const float big = 1.0e9f;
+          const int ix = (int)fminf(fmaxf(floorf(qx * inv_leaf), -big), big) - ox, iy = (int)fminf(fmaxf(floorf(qy * inv_leaf), -big), big) - oy,
+                    iz = (int)fminf(fmaxf(floorf(qz * inv_leaf), -big), big) - oz;
+          if ((unsigned)ix < (unsigned)fdx && (unsigned)iy < (unsigned)fdy && (unsigned)iz < (unsigned)fdz) {
+            const int c = (iz * fdy + iy) * fdx + ix;
+            const unsigned int bit = 1u << (c & 31);
+            if (!(s_bits[c >> 5] & bit)) {  // (cheap pre-test; the atomic decides)
+              if (!(atomicOr(&s_bits[c >> 5], bit) & bit)) needed[c] = 1u;
+            }
+          }
         }
       }
+    }
+    // (the bitmap stays valid across the groups of one block: it only records which flags this block has stored)
+  }
+}
+
+// queues every block of 2x2x2 fine cells that holds a marked cell (one thread per block, warp-aggregated append)
+__global__ void __launch_bounds__(256) cand_collect_kernel(const IndexHeader* __restrict__ hdr, const unsigned int* __restrict__ needed,
+                                                           int* __restrict__ needed_list, int* __restrict__ list_counters) {
+  __shared__ IndexHeader h;
+  if (threadIdx.x == 0) h = *hdr;
+  __syncthreads();
+  if (!h.valid || !lists_on(h)) return;
+  const int fdx = h.f_dim[0], fdy = h.f_dim[1], fdz = h.f_dim[2];
+  const int bdx = (fdx + 1) >> 1, bdy = (fdy + 1) >> 1, bdz = (fdz + 1) >> 1;
+  const int nb = bdx * bdy * bdz;
+  const int lane = threadIdx.x & 31;
+  for (int b0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31; b0 < nb; b0 += gridDim.x * blockDim.x) {
+    const int blk = b0 + lane;
+    bool any = false;
+    if (blk < nb) {
+      const int bz = blk / (bdx * bdy), br = blk - bz * bdx * bdy, by = br / bdx, bx = br - by * bdx;
+#pragma unroll
+      for (int sub = 0; sub < 8; ++sub) {
+        const int fx = 2 * bx + (sub & 1), fy = 2 * by + ((sub >> 1) & 1), fz = 2 * bz + (sub >> 2);
+        if (fx < fdx && fy < fdy && fz < fdz && needed[(fz * fdy + fy) * fdx + fx] != 0u) any = true;
+      }
+    }
+    const unsigned int bal = __ballot_sync(kFull, any);
+    if (bal) {
+      int base = 0;
+      if (lane == 0) base = atomicAdd(&list_counters[1], __popc(bal));
+      base = __shfl_sync(kFull, base, 0);
+      if (any) needed_list[base + __popc(bal & ((1u << lane) - 1u))] = blk;
     }
   }
 }
@@ -822,6 +892,7 @@ __device__ __noinline__ void build_cell_direct(const IndexHeader& h, const int* 
       if (xi < 0 || xi >= kListXCells) { if (lane == 0) fcount[cell] = kListOverflow; break; }
       xl = xlists + (size_t)xi * kListKX;
       cap = kListKX;
+      PFT_STAT(11, lane == 0 ? 1 : 0);
       if (lane == 0) { list[0] = (unsigned short)(xi & 0xffff); list[1] = (unsigned short)(xi >> 16); }
     }
     PFT_STAT(15, lane == 0 ? 1 : 0);
@@ -959,7 +1030,7 @@ __global__ void __launch_bounds__(256) cand_build_kernel(const IndexHeader* __re
         const int fx = 2 * bx + (lane & 1), fy = 2 * by + ((lane >> 1) & 1), fz = 2 * bz + (lane >> 2);
         if (fx < fdx && fy < fdy && fz < fdz) {
           const int c = (fz * fdy + fy) * fdx + fx;
-          if (needed[c]) far_list[atomicAdd(&list_counters[2], 1)] = c;
+          if (needed[c]) { far_list[atomicAdd(&list_counters[2], 1)] = c; PFT_STAT(10, 1); }
         }
       }
       continue;

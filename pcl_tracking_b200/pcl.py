@@ -519,6 +519,15 @@ class ParticleFilterOMPTracker:
         check(capi.load().pft_tracker_get_timing(self._h, C.byref(w), C.byref(c)))
         return w.value, c.value
 
+    def kernelTimes(self):
+        """[(kernel name, ms)] of the last compute() in launch order (timing mode)."""
+        cap = 256
+        names = (C.c_char_p * cap)()
+        ms = (C.c_float * cap)()
+        n = C.c_int()
+        check(capi.load().pft_tracker_get_kernel_times(self._h, names, ms, cap, C.byref(n)))
+        return [(names[i].decode(), float(ms[i])) for i in range(n.value)]
+
     def graphReplays(self):
         n = C.c_uint64()
         check(capi.load().pft_tracker_graph_replays(self._h, C.byref(n)))

@@ -1,0 +1,90 @@
+"""Per-kernel device times of one tracked frame (bench.py's c2 / c4 workload), from CUDA events recorded after
+every kernel of compute() on the library's stream (stream-launched, no graph, warm caches).  Complements the
+ncu launch list (cold caches, serialised): usage  python scripts/frame_breakdown.py [c2|c4] [frames] [particles]"""
+import collections
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+import torch  # noqa: E402
+from pcl_tracking_b200 import pcl  # noqa: E402
+
+
+def main():
+    workload = sys.argv[1] if len(sys.argv) > 1 else "c2"
+    n_frames = int(sys.argv[2]) if len(sys.argv) > 2 else 50
+    n_particles = int(sys.argv[3]) if len(sys.argv) > 3 else (1000 if workload == "c2" else 100000)
+    ctx = pcl.Context(0)
+    stream = torch.cuda.ExternalStream(ctx.stream)
+    frames, oid0 = bench.make_frames(bench.N_FRAMES)
+    model_cloud, centroid = pcl.prepare_model(pcl.PointCloud(bench.raw_model(frames, oid0), ctx=ctx), bench.LEAF, ctx=ctx)
+    M = model_cloud.size()
+    tracker = pcl.ParticleFilterOMPTracker(16, ctx=ctx)
+    pcl.configure_like_reference(tracker, particle_num=n_particles, use_hsv=True, iteration_num=bench.ITERATIONS)
+    m = np.eye(4, dtype=np.float32)
+    m[:3, 3] = centroid
+    tracker.setTrans(m)
+    tracker.seed(1234)
+    tracker.setReferenceCloud(model_cloud)
+    dev_frames = [pcl.PointCloud(f, ctx=ctx) for f in frames]
+    ds = pcl.PointCloud(ctx=ctx)
+    vg = pcl.ApproximateVoxelGrid(ctx=ctx)
+    vg.setLeafSize(bench.LEAF, bench.LEAF, bench.LEAF)
+    vg.setPassThrough("z", 0.0, 10.0)
+
+    def step(k):
+        vg.setInputCloud(dev_frames[bench.frame_order(k, bench.N_FRAMES)])
+        vg.filter(ds)
+        tracker.setInputCloud(ds)
+        tracker.compute()
+
+    for k in range(5):
+        step(k)
+    ctx.synchronize()
+    # graph-replayed frame time for reference
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for k in range(n_frames):
+        step(5 + k)
+    e1.record(stream)
+    ctx.synchronize()
+    graph_ms = e0.elapsed_time(e1) / n_frames
+    tracker.enableTiming(True)
+    agg = collections.OrderedDict()
+    k1_ms = 0.0
+    total = 0.0
+    for k in range(n_frames):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        vg.setInputCloud(dev_frames[bench.frame_order(k, bench.N_FRAMES)])
+        vg.filter(ds)
+        b.record(stream)
+        tracker.setInputCloud(ds)
+        tracker.compute()
+        times = tracker.kernelTimes()
+        k1_ms += a.elapsed_time(b)
+        occ = collections.Counter()
+        for name, ms in times:
+            e = agg.setdefault(name, [0, 0.0])
+            e[0] += 1
+            e[1] += ms
+            total += ms
+    out = {"workload": workload, "particles": n_particles, "model_points": M, "frames": n_frames,
+           "frame_ms_graph_replay": graph_ms, "frame_ms_stream_launched_sum": (total + k1_ms) / n_frames,
+           "k1_downsample_ms_per_frame": k1_ms / n_frames, "index": tracker.indexInfo(), "kernels": {}}
+    print("%s: %d particles x %d pts; frame %.3f ms (graph replay), %.3f ms (sum of stream-launched kernels incl. K1 %.3f ms)"
+          % (workload, n_particles, M, graph_ms, (total + k1_ms) / n_frames, k1_ms / n_frames))
+    for name, (cnt, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        print("  %-28s %5.1f launches/frame  %8.2f us/launch  %8.2f us/frame  %5.1f%%"
+              % (name, cnt / n_frames, 1e3 * ms / cnt, 1e3 * ms / n_frames, 100.0 * ms / (total + k1_ms)))
+        out["kernels"][name] = {"launches_per_frame": cnt / n_frames, "us_per_launch": 1e3 * ms / cnt, "us_per_frame": 1e3 * ms / n_frames}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

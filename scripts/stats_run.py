@@ -28,6 +28,7 @@ for k in range(12):
     if k in (1, 11):
         print("   lists: lookups %d, overflow %.4f%%, mean list length %.1f, cells built %d; lookups with length >16: %d, >32: %d, >64: %d, >128: %d, >512: %d, ==0: %d"
               % (v[12], 100.0 * v[13] / max(v[12], 1), v[14] / max(v[12] - v[13], 1), v[15], v[0], v[1], v[2], v[3], v[4], v[5]))
+        print("   far cells queued %d, of which rebuilt as extended lists %d" % (v[10], v[11]))
     if k in (0, 1, 5, 11):
         print("frame", k, {n: v[i] for i, n in enumerate(names)})
         pc = max(v[0], 1)
