@@ -154,7 +154,7 @@ struct pft_tracker {
   int graph_nodes = 0;
   // device buffers
   DevBuf st, parts[2], mats, slot_aabb, model, model_perm, model_tmp, sort_keys, sort_idx, bbox, raw, partial, cdf, cdf_total, ancestors, bin_keys, tbl_rep,
-      tbl_min, slot_of, klb, d_usel, d_normals, d_umot, idx_hdr, cell_start, ipts, ihsv, icount, dbg_idx, dbg_d2, d_trans, row_table, fcount, flists, fneeded, fneeded_list, ffar_list, xlists, xcount;
+      tbl_min, slot_of, klb, d_usel, d_normals, d_umot, idx_hdr, cell_start, ipts, ihsv, icount, dbg_idx, dbg_d2, d_trans, row_table, flists, fneeded, fneeded_list, ffar_list, xlists, xcount;
   int weight_smem = 0;  // dynamic shared memory of the weight kernel (bytes)
   int tbl_size = 0;
   int n_slots = 0;
@@ -184,7 +184,7 @@ void release_all(pft_tracker* t) {
   DevBuf* bufs[] = {&t->st, &t->parts[0], &t->parts[1], &t->mats, &t->slot_aabb, &t->model, &t->model_perm, &t->model_tmp, &t->sort_keys, &t->sort_idx,
                     &t->bbox, &t->raw, &t->partial, &t->cdf, &t->cdf_total, &t->ancestors, &t->bin_keys, &t->tbl_rep, &t->tbl_min, &t->slot_of, &t->klb,
                     &t->d_usel, &t->d_normals, &t->d_umot, &t->idx_hdr, &t->cell_start, &t->ipts, &t->ihsv, &t->icount, &t->dbg_idx,
-                    &t->dbg_d2, &t->d_trans, &t->row_table, &t->fcount, &t->flists, &t->fneeded, &t->fneeded_list, &t->ffar_list, &t->xlists, &t->xcount};
+                    &t->dbg_d2, &t->d_trans, &t->row_table, &t->flists, &t->fneeded, &t->fneeded_list, &t->ffar_list, &t->xlists, &t->xcount};
   for (auto* b : bufs) b->release();
 }
 
@@ -285,7 +285,6 @@ int ensure_particle_buffers(pft_tracker* t) {
     if ((rc = t->icount.reserve(((size_t)t->max_cells + 16) * sizeof(int)))) return rc;
     if ((rc = upload_row_table(t))) return rc;
     if (t->list_max_cells > 0) {
-      if ((rc = t->fcount.reserve(((size_t)t->list_max_cells + 16) * sizeof(unsigned short)))) return rc;
       if ((rc = t->flists.reserve(((size_t)t->list_max_cells + 1) * kListK * sizeof(unsigned short)))) return rc;
       if ((rc = t->fneeded.reserve(((size_t)t->list_max_cells + 16) * sizeof(unsigned int)))) return rc;
       // blocks of 2x2x2 fine cells: at most ceil(d/2)^3 <= (d+1)^3/8, bounded generously by cells/2 + 4096
@@ -573,20 +572,20 @@ int weight_phase_eval(pft_tracker* t) {
     cand_collect_kernel<<<sm * 2, 256, 0, s>>>(hdr, t->fneeded.as<unsigned int>(), t->fneeded_list.as<int>(), t->xcount.as<int>());
     PFT_LAUNCH_CHECK();
     stage_mark(t, "cand_collect_kernel");
-    cand_build_kernel<<<sm * 8, 256, 0, s>>>(hdr, t->cell_start.as<int>(), t->ipts.as<float4>(), t->max_dist * t->max_dist, t->fcount.as<unsigned short>(), t->flists.as<unsigned short>(),
+    cand_build_kernel<<<sm * 8, 256, 0, s>>>(hdr, t->cell_start.as<int>(), t->ipts.as<float4>(), t->max_dist * t->max_dist, t->flists.as<unsigned short>(),
                                             t->fneeded.as<unsigned int>(), t->fneeded_list.as<int>(), t->xlists.as<unsigned short>(),
                                             t->xcount.as<int>(), t->ffar_list.as<int>());
     PFT_LAUNCH_CHECK();
     stage_mark(t, "cand_build_kernel");
     cand_build_far_kernel<<<sm * 8, 256, 0, s>>>(hdr, t->cell_start.as<int>(), t->ipts.as<float4>(), t->max_dist * t->max_dist,
-                                                t->fcount.as<unsigned short>(), t->flists.as<unsigned short>(), t->xlists.as<unsigned short>(),
+                                                t->flists.as<unsigned short>(), t->xlists.as<unsigned short>(),
                                                 t->xcount.as<int>(), t->ffar_list.as<int>());
     PFT_LAUNCH_CHECK();
     stage_mark(t, "cand_build_far_kernel");
   }
   WeightArgs a;
   a.st = st; a.hdr = hdr;
-  a.fcount = t->fcount.as<unsigned short>(); a.flists = t->flists.as<unsigned short>(); a.xlists = t->xlists.as<unsigned short>();
+  a.flists = t->flists.as<unsigned short>(); a.xlists = t->xlists.as<unsigned short>();
   a.cell_start = t->cell_start.as<int>(); a.pts = t->ipts.as<float4>();
   a.hsv = t->ihsv.as<unsigned int>(); a.table = t->row_table.as<RowEntry>(); a.smem_bytes = t->weight_smem;
   a.model = t->model.as<float4>(); a.model_perm = t->model_perm.as<int>(); a.M = t->M;

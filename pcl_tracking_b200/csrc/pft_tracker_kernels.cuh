@@ -605,11 +605,11 @@ __device__ __forceinline__ NNResult nn_search(const CS* __restrict__ cs, const f
 // query q in c has |q - NN(q)| <= |q - p0| <= U, hence mindist(c, NN(q)) <= U; the list is {p : mindist(c, p) <= U}
 // (ties included), cut at maximum_distance_.  A query then scans one short list instead of walking the grid.  Cells
 // whose list would not fit kListK entries are marked and their queries use the row-table search.
-constexpr int kListK = 128;                        // entries of a regular list
+constexpr int kListK = 128;                        // 16-bit words of a cell's record: [0] = header (entry count or a code below), [1..] entries
 constexpr int kListKX = 1024;                      // entries of an extended list (cells far from the surface)
 constexpr int kListXCells = 8192;                  // extended lists available per build
 constexpr unsigned short kListOverflow = 0xffffu;  // no list: use the row-table search
-constexpr unsigned short kListExtended = 0xfffeu;  // list[0..1] = index of the extended list, list[2] = its length
+constexpr unsigned short kListExtended = 0xfffeu;  // record[1..2] = index of the extended list, record[3] = its length
 // list entries are 16-bit slots (+ the dummy slot n_cropped): larger crops use the row-table search only
 __device__ __forceinline__ bool lists_on(const IndexHeader& h) { return h.use_lists && h.n_cropped < 65535; }
 
@@ -726,7 +726,7 @@ __global__ void __launch_bounds__(256) cand_collect_kernel(const IndexHeader* __
 struct RowSpan { int s0, cnt; };
 
 template <typename RowFn, typename PointFn>
-__device__ __forceinline__ void warp_points_of_rows(int nrows, int* __restrict__ s_pref, int* __restrict__ s_start, RowFn row_span, PointFn fn) {
+__device__ __forceinline__ void warp_points_of_rows(int nrows, int* s_pref, int* s_start, RowFn row_span, PointFn fn) {
   const int lane = threadIdx.x & 31;
   for (int rbase = 0; rbase < nrows; rbase += 32) {
     RowSpan sp{0, 0};
@@ -761,141 +761,167 @@ __device__ __forceinline__ bool can_win(const float4& p, const float4& p0, const
   return fmin <= 1.0e-6f * (pn + p0n) + 1.0e-9f;
 }
 
-// One warp builds the list of ONE fine cell straight from the grid (no shared-memory superset): used for the cells of
-// blocks whose superset does not fit, i.e. far from the surface, where lists are long (extended lists up to kListKX).
-__device__ __noinline__ void build_cell_direct(const IndexHeader& h, const int* __restrict__ cs, const float4* __restrict__ pts, int cell,
-                                               float leaf, float margin, float r_max, unsigned short* __restrict__ fcount,
-                                               unsigned short* __restrict__ flists, unsigned short* __restrict__ xlists,
-                                               int* __restrict__ list_counters, int* pref, int* start, int* s_cnt_w) {
+// The points of a set of rows, flattened across a whole thread block (the block-wide sibling of warp_points_of_rows):
+// warp 0 fetches the slot ranges of 32 rows and scans their lengths, then all threads take consecutive points of the
+// concatenation.  Every thread of the block must call it.
+template <typename RowFn, typename PointFn>
+// (no __restrict__ on the shared arrays: they carry data between threads across the barriers)
+__device__ __forceinline__ void block_points_of_rows(int nrows, int* s_pref /* [34]: [32] = sentinel, [33] = total */, int* s_start, RowFn row_span,
+                                                     PointFn fn) {
   const int lane = threadIdx.x & 31;
+  for (int rbase = 0; rbase < nrows; rbase += 32) {
+    if (threadIdx.x < 32) {
+      RowSpan sp{0, 0};
+      if (rbase + lane < nrows) sp = row_span(rbase + lane);
+      int inc = sp.cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(kFull, inc, o); if (lane >= o) inc += t; }
+      s_pref[lane] = inc - sp.cnt;
+      s_start[lane] = sp.s0;
+      if (lane == 31) s_pref[33] = inc;
+    }
+    __syncthreads();
+    const int total = s_pref[33];
+    for (int t = threadIdx.x; t < total; t += blockDim.x) {
+      int r = 0;
+#pragma unroll
+      for (int step = 16; step > 0; step >>= 1) if (s_pref[r + step] <= t) r += step;  // last row whose offset is <= t
+      fn(s_start[r] + (t - s_pref[r]));
+    }
+    __syncthreads();
+  }
+}
+
+// One thread BLOCK builds the list of ONE fine cell straight from the grid (no shared-memory superset): used for the
+// cells of blocks whose superset does not fit, i.e. far from the surface, where lists are long (extended lists up to
+// kListKX) and a single warp would walk ~1000 points on its own while the rest of the GPU waits.
+__device__ __forceinline__ void build_cell_direct(const IndexHeader& h, const int* __restrict__ cs, const float4* __restrict__ pts, int cell,
+                                                  float leaf, float margin, float r_max,
+                                                  unsigned short* __restrict__ flists, unsigned short* __restrict__ xlists,
+                                                  int* __restrict__ list_counters, int* pref, int* start, int* s_cnt, float* s_m2, int* s_ms, int* s_xi) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int fdx = h.f_dim[0], fdy = h.f_dim[1];
   const float cell_m = h.cell;
   const int dimx = h.dim[0], dimy = h.dim[1];
-    const int fz = cell / (fdx * fdy), r2 = cell - fz * fdx * fdy, fy = r2 / fdx, fx = r2 - fy * fdx;
-    // the cell in metric space, widened by the rounding of q * inv_leaf near its faces
-    float lo[3], hi[3];
-    lo[0] = (float)(h.f_origin[0] + fx) * leaf - margin; hi[0] = (float)(h.f_origin[0] + fx + 1) * leaf + margin;
-    lo[1] = (float)(h.f_origin[1] + fy) * leaf - margin; hi[1] = (float)(h.f_origin[1] + fy + 1) * leaf + margin;
-    lo[2] = (float)(h.f_origin[2] + fz) * leaf - margin; hi[2] = (float)(h.f_origin[2] + fz + 1) * leaf + margin;
-    // coarse cells overlapping the box dilated by r.  floor((p * inv_leaf) * 2^-level) is monotone in p, so every point
-    // with lo - r <= p <= hi + r (per axis) lies in cells [c0, c1]: no padding is needed.
-    auto coarse_range = [&](int d, float r, int& a, int& b) {
-      a = max((int)floorf(((lo[d] - r) * h.inv_leaf) * h.level_scale) - h.origin[d], 0);
-      b = min((int)floorf(((hi[d] + r) * h.inv_leaf) * h.level_scale) - h.origin[d], h.dim[d] - 1);
-    };
-    // ---- (1) U: probe the box dilated by a growing radius until it holds a point
-    float U2 = 3.0e38f;
-    int p0_slot = -1;
-    bool no_match = false;
-    float pr = fmaxf(2.0f * leaf, 0.5f * cell_m);
-    for (int round = 0; round < 8; ++round, pr *= 2.0f) {
-      int x0, x1, y0, y1, z0, z1;
-      coarse_range(0, pr, x0, x1); coarse_range(1, pr, y0, y1); coarse_range(2, pr, z0, z1);
-      float m2 = 3.0e38f;
-      int ms = -1;
-      if (x0 <= x1 && y0 <= y1 && z0 <= z1) {
-        const int ny = y1 - y0 + 1;
-        warp_points_of_rows(
-            ny * (z1 - z0 + 1), pref, start,
-            [&](int r) { const int zz = r / ny; const int base = ((z0 + zz) * dimy + (y0 + r - zz * ny)) * dimx; const int a = cs[base + x0]; return RowSpan{a, cs[base + x1 + 1] - a}; },
-            [&](int s) { const float v = box_maxdist2(lo, hi, pts[s]); if (v < m2) { m2 = v; ms = s; } });
+  const int fz = cell / (fdx * fdy), r2 = cell - fz * fdx * fdy, fy = r2 / fdx, fx = r2 - fy * fdx;
+  // the cell in metric space, widened by the rounding of q * inv_leaf near its faces
+  float lo[3], hi[3];
+  lo[0] = (float)(h.f_origin[0] + fx) * leaf - margin; hi[0] = (float)(h.f_origin[0] + fx + 1) * leaf + margin;
+  lo[1] = (float)(h.f_origin[1] + fy) * leaf - margin; hi[1] = (float)(h.f_origin[1] + fy + 1) * leaf + margin;
+  lo[2] = (float)(h.f_origin[2] + fz) * leaf - margin; hi[2] = (float)(h.f_origin[2] + fz + 1) * leaf + margin;
+  // coarse cells overlapping the box dilated by r.  floor((p * inv_leaf) * 2^-level) is monotone in p, so every point
+  // with lo - r <= p <= hi + r (per axis) lies in cells [c0, c1]: no padding is needed.
+  auto coarse_range = [&](int d, float r, int& a, int& b) {
+    a = max((int)floorf(((lo[d] - r) * h.inv_leaf) * h.level_scale) - h.origin[d], 0);
+    b = min((int)floorf(((hi[d] + r) * h.inv_leaf) * h.level_scale) - h.origin[d], h.dim[d] - 1);
+  };
+  unsigned short* list = flists + (size_t)cell * kListK;
+  // ---- (1) U: probe the box dilated by a growing radius until it holds a point
+  float U2 = 3.0e38f;
+  int p0_slot = -1;
+  bool no_match = false;
+  float pr = fmaxf(2.0f * leaf, 0.5f * cell_m);
+  for (int round = 0; round < 8; ++round, pr *= 2.0f) {
+    int x0, x1, y0, y1, z0, z1;
+    coarse_range(0, pr, x0, x1); coarse_range(1, pr, y0, y1); coarse_range(2, pr, z0, z1);
+    float m2 = 3.0e38f;
+    int ms = -1;
+    if (x0 <= x1 && y0 <= y1 && z0 <= z1) {
+      const int ny = y1 - y0 + 1;
+      block_points_of_rows(
+          ny * (z1 - z0 + 1), pref, start,
+          [&](int r) { const int zz = r / ny; const int base = ((z0 + zz) * dimy + (y0 + r - zz * ny)) * dimx; const int a = cs[base + x0]; return RowSpan{a, cs[base + x1 + 1] - a}; },
+          [&](int s) { const float v = box_maxdist2(lo, hi, pts[s]); if (v < m2 || (v == m2 && s > ms)) { m2 = v; ms = s; } });
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          const float om = __shfl_xor_sync(kFull, m2, o);
-          const int os = __shfl_xor_sync(kFull, ms, o);
-          if (om < m2 || (om == m2 && os > ms)) { m2 = om; ms = os; }  // any deterministic choice among equals
-        }
+      for (int o = 16; o > 0; o >>= 1) {
+        const float om = __shfl_xor_sync(kFull, m2, o);
+        const int os = __shfl_xor_sync(kFull, ms, o);
+        if (om < m2 || (om == m2 && os > ms)) { m2 = om; ms = os; }  // any deterministic choice among equals
       }
-      if (m2 < 3.0e38f) { U2 = m2 * 1.00002f; p0_slot = ms; break; }
-      if (pr > r_max) { no_match = true; break; }  // nothing within pr (> maximum_distance_) of the box: no query of the cell can match
+      if (lane == 0) { s_m2[wid] = m2; s_ms[wid] = ms; }
+      __syncthreads();
+      m2 = s_m2[0]; ms = s_ms[0];
+      for (int w = 1; w < nw; ++w) { const float om = s_m2[w]; const int os = s_ms[w]; if (om < m2 || (om == m2 && os > ms)) { m2 = om; ms = os; } }
+      __syncthreads();
     }
-    if (U2 >= 3.0e38f) {
-      // provably no point within maximum_distance_ of any query of the cell (empty list), or the probe gave up (the
-      // queries of this cell use the row-table search)
-      if (lane == 0) fcount[cell] = no_match ? (unsigned short)0 : kListOverflow;
-      return;
-    }
-    U2 = fminf(U2, r_max * r_max);
-    const float reach = sqrtf(U2) * 1.00001f;
-    // Second, sharper filter: the nearest neighbour p* of a query q of the cell satisfies |q - p*| <= |q - p0| for the
-    // reference point p0 found above, i.e. q lies on p*'s side of the bisector plane of (p*, p0).  A point p whose side
-    // of that plane misses the box can therefore never be the answer: min over the box of |q-p|^2 - |q-p0|^2 is linear
-    // in q and attained at a corner.  Coordinates are taken relative to the box centre to keep the fp32 error ~1e-9.
-    const float bcx = 0.5f * (lo[0] + hi[0]), bcy = 0.5f * (lo[1] + hi[1]), bcz = 0.5f * (lo[2] + hi[2]);
-    const float bhx = 0.5f * (hi[0] - lo[0]), bhy = 0.5f * (hi[1] - lo[1]), bhz = 0.5f * (hi[2] - lo[2]);
-    const float4 p0 = pts[p0_slot];
-    const float p0x = p0.x - bcx, p0y = p0.y - bcy, p0z = p0.z - bcz;
-    const float p0n = (p0x * p0x + p0y * p0y) + p0z * p0z;
-    auto can_win = [&](const float4& p) -> bool {
-      const float px = p.x - bcx, py = p.y - bcy, pz = p.z - bcz;
-      const float pn = (px * px + py * py) + pz * pz;
-      const float ex = px - p0x, ey = py - p0y, ez = pz - p0z;
-      // min over q in [-bh, bh]^3 of (pn - p0n) - 2 q.e  =  (pn - p0n) - 2 (bhx|ex| + bhy|ey| + bhz|ez|)
-      const float fmin = (pn - p0n) - 2.0f * ((bhx * fabsf(ex) + bhy * fabsf(ey)) + bhz * fabsf(ez));
-      return fmin <= 1.0e-6f * (pn + p0n) + 1.0e-9f;
-    };
-    // ---- (2) gather: rows of coarse cells that intersect the ball-dilated box
-    int c0[3], c1[3];
-    coarse_range(1, reach, c0[1], c1[1]); coarse_range(2, reach, c0[2], c1[2]);
-    const int ny = c1[1] - c0[1] + 1, nrows = max(ny, 0) * max(c1[2] - c0[2] + 1, 0);
-    unsigned short* list = flists + (size_t)cell * kListK;
-    unsigned short* xl = nullptr;
-    int cap = kListK;
-    for (int attempt = 0; attempt < 2; ++attempt) {
-      if (lane == 0) (*s_cnt_w) = 0;
-      __syncwarp();
-      unsigned short* dst = attempt ? xl : list;
-      warp_points_of_rows(
-          nrows, pref, start,
-          [&](int r) {
-            const int zz = r / ny, y = c0[1] + (r - zz * ny), z = c0[2] + zz;
-            const float zlo = (float)(z + h.origin[2]) * cell_m - 2.0f * margin, zhi = (float)(z + 1 + h.origin[2]) * cell_m + 2.0f * margin;
-            const float gz = fmaxf(fmaxf(lo[2] - zhi, zlo - hi[2]), 0.f);
-            const float ylo = (float)(y + h.origin[1]) * cell_m - 2.0f * margin, yhi = (float)(y + 1 + h.origin[1]) * cell_m + 2.0f * margin;
-            const float gy = fmaxf(fmaxf(lo[1] - yhi, ylo - hi[1]), 0.f);
-            const float rem = U2 - (gy * gy + gz * gz) * 0.9999f;
-            if (rem < 0.f) return RowSpan{0, 0};
-            const float xr = sqrtf(rem) * 1.00001f + 2.0f * margin;
-            const int xa = max((int)floorf(((lo[0] - xr) * h.inv_leaf) * h.level_scale) - h.origin[0], 0);
-            const int xb = min((int)floorf(((hi[0] + xr) * h.inv_leaf) * h.level_scale) - h.origin[0], dimx - 1);
-            if (xa > xb) return RowSpan{0, 0};
-            const int base = (z * dimy + y) * dimx;
-            const int a = cs[base + xa];
-            return RowSpan{a, cs[base + xb + 1] - a};
-          },
-          [&](int s) {
-            const float4 p = pts[s];
-            if (box_mindist2(lo, hi, p) <= U2 && can_win(p)) {
-              const int pos = atomicAdd(&(*s_cnt_w), 1);
-              if (pos < cap) dst[pos] = (unsigned short)s;
-            }
-          });
-      __syncwarp();
-      const int n = (*s_cnt_w);
-      __syncwarp();
-      if (n <= cap) {
-        // pad to a multiple of 8 entries with the dummy slot (the lookup reads whole 16-byte groups unconditionally)
-        const int n8 = (n + 7) & ~7;
-        if (n + lane < n8) dst[n + lane] = (unsigned short)h.n_cropped;
-        if (lane == 0) {
-          if (!attempt) fcount[cell] = (unsigned short)n;
-          else { list[2] = (unsigned short)n; fcount[cell] = kListExtended; }
-        }
-        break;
+    if (m2 < 3.0e38f) { U2 = m2 * 1.00002f; p0_slot = ms; break; }
+    if (pr > r_max) { no_match = true; break; }  // nothing within pr (> maximum_distance_) of the box: no query of the cell can match
+  }
+  if (U2 >= 3.0e38f) {
+    // provably no point within maximum_distance_ of any query of the cell (empty list), or the probe gave up (the
+    // queries of this cell use the row-table search)
+    if (threadIdx.x < 8) list[threadIdx.x] = threadIdx.x ? (unsigned short)h.n_cropped : (no_match ? (unsigned short)0 : kListOverflow);
+    return;
+  }
+  U2 = fminf(U2, r_max * r_max);
+  const float reach = sqrtf(U2) * 1.00001f;
+  // Second, sharper filter: the nearest neighbour p* of a query q of the cell satisfies |q - p*| <= |q - p0| for the
+  // reference point p0 found above, i.e. q lies on p*'s side of the bisector plane of (p*, p0) (see can_win).
+  float bc[3], bh[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) { bc[d] = 0.5f * (lo[d] + hi[d]); bh[d] = 0.5f * (hi[d] - lo[d]); }
+  const float4 p0 = pts[p0_slot];
+  // ---- (2) gather: rows of coarse cells that intersect the ball-dilated box
+  int c0[3], c1[3];
+  coarse_range(1, reach, c0[1], c1[1]); coarse_range(2, reach, c0[2], c1[2]);
+  const int ny = c1[1] - c0[1] + 1, nrows = max(ny, 0) * max(c1[2] - c0[2] + 1, 0);
+  unsigned short* xl = nullptr;
+  int cap = kListK - 1;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    if (threadIdx.x == 0) *s_cnt = 0;
+    __syncthreads();
+    unsigned short* dst = attempt ? xl : list + 1;
+    block_points_of_rows(
+        nrows, pref, start,
+        [&](int r) {
+          const int zz = r / ny, y = c0[1] + (r - zz * ny), z = c0[2] + zz;
+          const float zlo = (float)(z + h.origin[2]) * cell_m - 2.0f * margin, zhi = (float)(z + 1 + h.origin[2]) * cell_m + 2.0f * margin;
+          const float gz = fmaxf(fmaxf(lo[2] - zhi, zlo - hi[2]), 0.f);
+          const float ylo = (float)(y + h.origin[1]) * cell_m - 2.0f * margin, yhi = (float)(y + 1 + h.origin[1]) * cell_m + 2.0f * margin;
+          const float gy = fmaxf(fmaxf(lo[1] - yhi, ylo - hi[1]), 0.f);
+          const float rem = U2 - (gy * gy + gz * gz) * 0.9999f;
+          if (rem < 0.f) return RowSpan{0, 0};
+          const float xr = sqrtf(rem) * 1.00001f + 2.0f * margin;
+          const int xa = max((int)floorf(((lo[0] - xr) * h.inv_leaf) * h.level_scale) - h.origin[0], 0);
+          const int xb = min((int)floorf(((hi[0] + xr) * h.inv_leaf) * h.level_scale) - h.origin[0], dimx - 1);
+          if (xa > xb) return RowSpan{0, 0};
+          const int base = (z * dimy + y) * dimx;
+          const int a = cs[base + xa];
+          return RowSpan{a, cs[base + xb + 1] - a};
+        },
+        [&](int s) {
+          const float4 p = pts[s];
+          if (box_mindist2(lo, hi, p) <= U2 && can_win(p, p0, bc, bh)) {
+            const int pos = atomicAdd(s_cnt, 1);
+            if (pos < cap) dst[pos] = (unsigned short)s;
+          }
+        });
+    const int n = *s_cnt;
+    __syncthreads();
+    if (n <= cap) {
+      // pad to whole 16-byte groups with the dummy slot (the lookup reads whole groups unconditionally; a regular
+      // record starts with its header word)
+      const int off = attempt ? 0 : 1;
+      const int n8 = ((n + off + 7) & ~7) - off;
+      if (n + (int)threadIdx.x < n8) dst[n + threadIdx.x] = (unsigned short)h.n_cropped;
+      if (threadIdx.x == 0) {
+        if (!attempt) list[0] = (unsigned short)n;
+        else { list[3] = (unsigned short)n; list[0] = kListExtended; }
       }
-      // does not fit: take an extended list and gather again into it (rare: cells far from the surface)
-      int xi = -1;
-      if (!attempt && n <= kListKX) {
-        if (lane == 0) xi = atomicAdd(&list_counters[0], 1);
-        xi = __shfl_sync(kFull, xi, 0);
-      }
-      if (xi < 0 || xi >= kListXCells) { if (lane == 0) fcount[cell] = kListOverflow; break; }
-      xl = xlists + (size_t)xi * kListKX;
-      cap = kListKX;
-      PFT_STAT(11, lane == 0 ? 1 : 0);
-      if (lane == 0) { list[0] = (unsigned short)(xi & 0xffff); list[1] = (unsigned short)(xi >> 16); }
+      break;
     }
-    PFT_STAT(15, lane == 0 ? 1 : 0);
+    // does not fit: take an extended list and gather again into it (cells far from the surface)
+    if (threadIdx.x == 0) *s_xi = (!attempt && n <= kListKX) ? atomicAdd(&list_counters[0], 1) : -1;
+    __syncthreads();
+    const int xi = *s_xi;
+    __syncthreads();
+    if (xi < 0 || xi >= kListXCells) { if (threadIdx.x == 0) list[0] = kListOverflow; break; }
+    xl = xlists + (size_t)xi * kListKX;
+    cap = kListKX;
+    PFT_STAT(11, threadIdx.x == 0 ? 1 : 0);
+    if (threadIdx.x == 0) { list[1] = (unsigned short)(xi & 0xffff); list[2] = (unsigned short)(xi >> 16); }
+  }
+  PFT_STAT(15, threadIdx.x == 0 ? 1 : 0);
 }
 
 // One warp builds the lists of one block of 2x2x2 fine cells: the points that can be the nearest neighbour of some
@@ -903,7 +929,7 @@ __device__ __noinline__ void build_cell_direct(const IndexHeader& h, const int* 
 // of the block filters that superset with its own bound and bisector test.
 __global__ void __launch_bounds__(256) cand_build_kernel(const IndexHeader* __restrict__ hdr, const int* __restrict__ cs,
                                                          const float4* __restrict__ pts, double max_d2,
-                                                         unsigned short* __restrict__ fcount, unsigned short* __restrict__ flists,
+                                                         unsigned short* __restrict__ flists,
                                                          const unsigned int* __restrict__ needed, const int* __restrict__ needed_list,
                                                          unsigned short* __restrict__ xlists, int* __restrict__ list_counters,
                                                          int* __restrict__ far_list) {
@@ -942,7 +968,11 @@ __global__ void __launch_bounds__(256) cand_build_kernel(const IndexHeader* __re
     auto set_all = [&](unsigned short value) {
       if (lane < 8) {
         const int fx = 2 * bx + (lane & 1), fy = 2 * by + ((lane >> 1) & 1), fz = 2 * bz + (lane >> 2);
-        if (fx < fdx && fy < fdy && fz < fdz) { const int c = (fz * fdy + fy) * fdx + fx; if (needed[c]) fcount[c] = value; }
+        if (fx < fdx && fy < fdy && fz < fdz) {
+          const int c = (fz * fdy + fy) * fdx + fx;
+          // header + a first group of dummy slots (value 0 = empty list: the lookup returns before reading them)
+          if (needed[c]) { uint4 r; r.x = (unsigned int)value | ((unsigned int)h.n_cropped << 16); r.y = r.z = r.w = (unsigned int)h.n_cropped * 0x10001u; *reinterpret_cast<uint4*>(flists + (size_t)c * kListK) = r; }
+        }
       }
     };
     // coarse cells overlapping the box dilated by r.  floor((p * inv_leaf) * 2^-level) is monotone in p, so every point
@@ -1067,16 +1097,17 @@ __global__ void __launch_bounds__(256) cand_build_kernel(const IndexHeader* __re
         n += __popc(__ballot_sync(kFull, keep));
       }
       unsigned short* list = flists + (size_t)cell * kListK;
-      unsigned short* dst = list;
-      if (n > kListK) {
+      unsigned short* dst = list + 1;
+      const bool extended = n > kListK - 1;
+      if (extended) {
         int xi = -1;
         if (n <= kListKX) {
           if (lane == 0) xi = atomicAdd(&list_counters[0], 1);
           xi = __shfl_sync(kFull, xi, 0);
         }
-        if (xi < 0 || xi >= kListXCells) { if (lane == 0) fcount[cell] = kListOverflow; continue; }
+        if (xi < 0 || xi >= kListXCells) { if (lane == 0) list[0] = kListOverflow; continue; }
         dst = xlists + (size_t)xi * kListKX;
-        if (lane == 0) { list[0] = (unsigned short)(xi & 0xffff); list[1] = (unsigned short)(xi >> 16); list[2] = (unsigned short)n; }
+        if (lane == 0) { list[1] = (unsigned short)(xi & 0xffff); list[2] = (unsigned short)(xi >> 16); list[3] = (unsigned short)n; }
       }
       int w = 0;
       for (int t0 = 0; t0 < ns; t0 += 32) {
@@ -1086,39 +1117,42 @@ __global__ void __launch_bounds__(256) cand_build_kernel(const IndexHeader* __re
         if (keep) dst[w + __popc(bal & ((1u << lane) - 1u))] = sslot[t];
         w += __popc(bal);
       }
-      // pad to a multiple of 8 entries with the dummy slot (the lookup reads whole 16-byte groups unconditionally)
-      const int n8 = (n + 7) & ~7;
+      // pad to whole 16-byte groups with the dummy slot (the lookup reads whole groups unconditionally; a regular record
+      // starts with its header word)
+      const int off = extended ? 0 : 1;
+      const int n8 = ((n + off + 7) & ~7) - off;
       if (n + lane < n8) dst[n + lane] = (unsigned short)h.n_cropped;
-      if (lane == 0) fcount[cell] = n > kListK ? kListExtended : (unsigned short)n;
+      if (lane == 0) list[0] = extended ? kListExtended : (unsigned short)n;
       PFT_STAT(15, lane == 0 ? 1 : 0);
     }
   }
 }
 
-// second pass of the build: the cells queued by cand_build_kernel, one warp each
+// second pass of the build: the cells queued by cand_build_kernel, one thread block each
 __global__ void __launch_bounds__(256) cand_build_far_kernel(const IndexHeader* __restrict__ hdr, const int* __restrict__ cs,
-                                                             const float4* __restrict__ pts, double max_d2, unsigned short* __restrict__ fcount,
+                                                             const float4* __restrict__ pts, double max_d2,
                                                              unsigned short* __restrict__ flists, unsigned short* __restrict__ xlists,
                                                              int* __restrict__ list_counters, const int* __restrict__ far_list) {
   __shared__ IndexHeader h;
-  __shared__ int s_cnt[8];
-  __shared__ int s_pref[8][33], s_start[8][32];
-  if (threadIdx.x == 0) h = *hdr;
+  __shared__ int s_cnt, s_xi;
+  __shared__ int s_pref[34], s_start[32], s_ms[8];
+  __shared__ float s_m2[8];
+  if (threadIdx.x == 0) { h = *hdr; s_pref[32] = 0x7fffffff; }
   __syncthreads();
   if (!h.valid || !lists_on(h)) return;
   const int n_far = list_counters[2];
   const float leaf = 1.0f / h.inv_leaf;
   const float margin = 1.0e-5f + 4.0e-6f * leaf * (float)(abs(h.f_origin[0]) + abs(h.f_origin[1]) + abs(h.f_origin[2]) + h.f_dim[0] + h.f_dim[1] + h.f_dim[2]);
   const float r_max = max_d2 >= 1.0e30 ? 1.0e15f : (float)sqrt(max_d2) * 1.00001f;
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-  if (lane == 0) s_pref[wib][32] = 0x7fffffff;
-  for (int idx = warp; idx < n_far; idx += nwarps)
-    build_cell_direct(h, cs, pts, far_list[idx], leaf, margin, r_max, fcount, flists, xlists, list_counters, s_pref[wib], s_start[wib], &s_cnt[wib]);
+  for (int idx = blockIdx.x; idx < n_far; idx += gridDim.x) {
+    build_cell_direct(h, cs, pts, far_list[idx], leaf, margin, r_max, flists, xlists, list_counters, s_pref, s_start, &s_cnt, s_m2, s_ms, &s_xi);
+    __syncthreads();
+  }
 }
 
-// Query through the candidate lists; returns false when the row-table search has to be used instead.
-__device__ __forceinline__ bool nn_lookup(const IndexHeader& h, const unsigned short* __restrict__ fcount, const unsigned short* __restrict__ flists,
+// Query through the candidate lists; returns false when the row-table search has to be used instead.  One 16-byte
+// load brings the header of the cell's record and its first seven entries; longer lists continue in groups of eight.
+__device__ __forceinline__ bool nn_lookup(const IndexHeader& h, const unsigned short* __restrict__ flists,
                                           const unsigned short* __restrict__ xlists, const float4* __restrict__ pts, float qx, float qy, float qz,
                                           float lim2, NNResult& best) {
   const float fx = floorf(qx * h.inv_leaf), fy = floorf(qy * h.inv_leaf), fz = floorf(qz * h.inv_leaf);
@@ -1127,26 +1161,42 @@ __device__ __forceinline__ bool nn_lookup(const IndexHeader& h, const unsigned s
             iz = (int)fminf(fmaxf(fz, -big), big) - h.f_origin[2];
   if ((unsigned)ix >= (unsigned)h.f_dim[0] || (unsigned)iy >= (unsigned)h.f_dim[1] || (unsigned)iz >= (unsigned)h.f_dim[2]) return false;
   const int cell = (iz * h.f_dim[1] + iy) * h.f_dim[0] + ix;
-  int cnt = fcount[cell];
+  const uint4* l4 = reinterpret_cast<const uint4*>(flists + (size_t)cell * kListK);
+  uint4 v = l4[0];
+  int cnt = (int)(v.x & 0xffffu);
   PFT_STAT(12, 1);
-  if (cnt == kListOverflow) { PFT_STAT(13, 1); return false; }
-  const unsigned short* lst = flists + (size_t)cell * kListK;
-  if (cnt == kListExtended) {
-    const int xi = (int)lst[0] | ((int)lst[1] << 16);
-    cnt = lst[2];
-    lst = xlists + (size_t)xi * kListKX;
+  best = nn_none(lim2);
+  if (cnt >= (int)kListExtended) {
+    if (cnt == (int)kListOverflow) { PFT_STAT(13, 1); return false; }
+    // extended list (cells far from the surface): groups of eight from its own storage
+    const int xi = (int)(v.x >> 16) | ((int)(v.y & 0xffffu) << 16);
+    cnt = (int)(v.y >> 16);
+    PFT_STAT(14, cnt); PFT_STAT(3, 1);
+    const uint4* x4 = reinterpret_cast<const uint4*>(xlists + (size_t)xi * kListKX);
+    const int groups = (cnt + 7) >> 3;
+    for (int g = 0; g < groups; ++g) {
+      const uint4 cur = x4[g];
+      nn_eval(pts, (int)(cur.x & 0xffffu), qx, qy, qz, best); nn_eval(pts, (int)(cur.x >> 16), qx, qy, qz, best);
+      nn_eval(pts, (int)(cur.y & 0xffffu), qx, qy, qz, best); nn_eval(pts, (int)(cur.y >> 16), qx, qy, qz, best);
+      nn_eval(pts, (int)(cur.z & 0xffffu), qx, qy, qz, best); nn_eval(pts, (int)(cur.z >> 16), qx, qy, qz, best);
+      nn_eval(pts, (int)(cur.w & 0xffffu), qx, qy, qz, best); nn_eval(pts, (int)(cur.w >> 16), qx, qy, qz, best);
+    }
+    return true;
   }
   PFT_STAT(14, cnt);
-  PFT_STAT(0, cnt > 16 ? 1 : 0); PFT_STAT(1, cnt > 32 ? 1 : 0); PFT_STAT(2, cnt > 64 ? 1 : 0); PFT_STAT(3, cnt > 128 ? 1 : 0); PFT_STAT(4, cnt > 512 ? 1 : 0);
+  PFT_STAT(0, cnt > 15 ? 1 : 0); PFT_STAT(1, cnt > 31 ? 1 : 0); PFT_STAT(2, cnt > 63 ? 1 : 0);
   PFT_STAT(5, cnt == 0 ? 1 : 0);
-  best = nn_none(lim2);
-  const uint4* l4 = reinterpret_cast<const uint4*>(lst);
-  const int groups = (cnt + 7) >> 3;  // lists are padded with the dummy slot to whole groups of 8
-  if (groups == 0) return true;
-  uint4 v = l4[0];
-  for (int g = 0; g < groups; ++g) {
-    const uint4 cur = v;
-    if (g + 1 < groups) v = l4[g + 1];  // next group in flight while this one is evaluated
+  if (cnt == 0) return true;
+  const int groups = (cnt + 8) >> 3;  // the header word + cnt entries, padded with the dummy slot to whole groups of 8
+  uint4 nxt = v;
+  if (groups > 1) nxt = l4[1];  // next group in flight while this one is evaluated
+  nn_eval(pts, (int)(v.x >> 16), qx, qy, qz, best);
+  nn_eval(pts, (int)(v.y & 0xffffu), qx, qy, qz, best); nn_eval(pts, (int)(v.y >> 16), qx, qy, qz, best);
+  nn_eval(pts, (int)(v.z & 0xffffu), qx, qy, qz, best); nn_eval(pts, (int)(v.z >> 16), qx, qy, qz, best);
+  nn_eval(pts, (int)(v.w & 0xffffu), qx, qy, qz, best); nn_eval(pts, (int)(v.w >> 16), qx, qy, qz, best);
+  for (int g = 1; g < groups; ++g) {
+    const uint4 cur = nxt;
+    if (g + 1 < groups) nxt = l4[g + 1];
     nn_eval(pts, (int)(cur.x & 0xffffu), qx, qy, qz, best); nn_eval(pts, (int)(cur.x >> 16), qx, qy, qz, best);
     nn_eval(pts, (int)(cur.y & 0xffffu), qx, qy, qz, best); nn_eval(pts, (int)(cur.y >> 16), qx, qy, qz, best);
     nn_eval(pts, (int)(cur.z & 0xffffu), qx, qy, qz, best); nn_eval(pts, (int)(cur.z >> 16), qx, qy, qz, best);
@@ -1162,8 +1212,7 @@ struct WeightArgs {
   const float4* pts;          // {x, y, z, input index} in cell order
   const unsigned int* hsv;    // packed HSV of every slot
   const RowEntry* table;      // kRows entries sorted by lb2
-  const unsigned short* fcount;  // candidate lists (see cand_build_kernel): per fine cell count and kListK slots
-  const unsigned short* flists;
+  const unsigned short* flists;  // candidate lists (see cand_build_kernel): one record of kListK 16-bit words per fine cell
   const unsigned short* xlists;  // extended lists
   const float4* model;        // {x,y,z,hsv} in tile order
   const int* model_perm;      // tile order -> order of the reference cloud as given
@@ -1180,7 +1229,8 @@ struct WeightArgs {
 // One (particle, model chunk) item by one warp: transform, nearest neighbour, coherence, warp reduction.
 template <bool USE_HSV, typename CS>
 __device__ __forceinline__ void weight_items(const WeightArgs& a, const IndexHeader& h, const CS* __restrict__ cs, const float4* __restrict__ pts,
-                                             const RowEntry* __restrict__ table, const float* __restrict__ lut_h, const float* __restrict__ lut_s) {
+                                             const unsigned int* __restrict__ hsv, const RowEntry* __restrict__ table, const float* __restrict__ lut_h,
+                                             const float* __restrict__ lut_s) {
   const int n = a.st->particle_num;
   const int n_local = n > a.rank_id ? (n - a.rank_id + a.nranks - 1) / a.nranks : 0;
   const int items = n_local * a.chunks;
@@ -1190,8 +1240,12 @@ __device__ __forceinline__ void weight_items(const WeightArgs& a, const IndexHea
   const int warp_id = (threadIdx.x >> 5) * gridDim.x + blockIdx.x;
   // maximum_distance_^2 as the float just above it: every point with (double)d2 < max_d2 has d2 <= lim2
   const float lim2 = a.co.max_d2 >= 3.0e38 ? FLT_MAX : __double2float_ru(a.co.max_d2);
-  for (int item = warp_id; item < items; item += total_warps) {
-    const int i = a.rank_id + (item / a.chunks) * a.nranks, c = item % a.chunks;
+  // (particle, chunk) of the warp's current item, advanced without divisions
+  int il = warp_id / a.chunks, c = warp_id - il * a.chunks;
+  const int dl = total_warps / a.chunks, dc = total_warps - dl * a.chunks;
+  const bool use_lists = lists_on(h);
+  for (int item = warp_id; item < items; item += total_warps, il += dl, c += dc, il += (c >= a.chunks), c -= (c >= a.chunks) ? a.chunks : 0) {
+    const int i = a.rank_id + il * a.nranks;
     float m[12];
     {
       const float4* mp = reinterpret_cast<const float4*>(a.mats) + (size_t)i * 3;
@@ -1208,7 +1262,7 @@ __device__ __forceinline__ void weight_items(const WeightArgs& a, const IndexHea
       xform(m, mp.x, mp.y, mp.z, qx, qy, qz);
       NNResult nn = nn_none(lim2);
       if (h.n_cropped > 0) {
-        if (!(lists_on(h) && nn_lookup(h, a.fcount, a.flists, a.xlists, pts, qx, qy, qz, lim2, nn))) nn = nn_search<CS>(cs, pts, h, table, qx, qy, qz, lim2);
+        if (!(use_lists && nn_lookup(h, a.flists, a.xlists, pts, qx, qy, qz, lim2, nn))) nn = nn_search<CS>(cs, pts, h, table, qx, qy, qz, lim2);
       }
       if (i < a.dbg_k) {
         const size_t o = (size_t)i * a.M + a.model_perm[j];
@@ -1227,7 +1281,7 @@ __device__ __forceinline__ void weight_items(const WeightArgs& a, const IndexHea
           den = 1.0 + d * d * a.co.dist_w;
         }
         if (USE_HSV) {
-          const unsigned int sb = __float_as_uint(mp.w), tb = a.hsv[nn.slot];
+          const unsigned int sb = __float_as_uint(mp.w), tb = hsv[nn.slot];
           const float sh = lut_h[sb & 0xff], ss = lut_s[(sb >> 8) & 0xff], sv = lut_s[(sb >> 16) & 0xff];
           const float th = lut_h[tb & 0xff], ts = lut_s[(tb >> 8) & 0xff], tv = lut_s[(tb >> 16) & 0xff];
           const float hd = fabsf(sh - th);
@@ -1266,29 +1320,42 @@ __global__ void __launch_bounds__(THREADS, 1) weight_kernel(const WeightArgs a) 
     for (int i = threadIdx.x; i < 256; i += blockDim.x) { lut_h[i] = (float)i / 180.0f; lut_s[i] = (float)i / 255.0f; }
   }
   __syncthreads();
-  // ---- stage the scene index into shared memory: the points (float4) whenever they fit, the cell starts (as 16-bit,
-  // only the row-table search reads them) when there is room left
+  // ---- stage the scene index into shared memory: the points (float4) whenever they fit, then their packed HSV, then
+  // (only when the candidate lists are off: nothing else reads them) the cell starts as 16-bit values
   const int n_pts = h.n_cropped + 1;  // + the dummy point that pads the candidate lists
   const long long need_pts = 16ll * n_pts;
+  const long long need_hsv = 4ll * ((n_pts + 3) & ~3);
   const long long need_cs = 2ll * (((long long)h.n_cells + 1 + 7) & ~7ll);
   const bool pts_staged = h.valid && need_pts <= (long long)a.smem_bytes;
-  const bool cs_staged = pts_staged && n_pts < 65536 && need_pts + need_cs <= (long long)a.smem_bytes;
+#ifdef PFT_NO_HSV_STAGE
+  const bool hsv_staged = false;
+#else
+  const bool hsv_staged = USE_HSV && pts_staged && need_pts + need_hsv <= (long long)a.smem_bytes;
+#endif
+  const long long used = need_pts + (hsv_staged ? need_hsv : 0);
+  const bool cs_staged = pts_staged && !lists_on(h) && n_pts < 65536 && used + need_cs <= (long long)a.smem_bytes;
   uint4* s_pts = dyn_smem;
+  unsigned int* s_hsv = reinterpret_cast<unsigned int*>(dyn_smem + n_pts);
   if (pts_staged) {
     const uint4* gp = reinterpret_cast<const uint4*>(a.pts);
     for (int i = threadIdx.x; i < n_pts; i += blockDim.x) s_pts[i] = gp[i];
   }
-  // (three call sites so that the compiler sees which pointers are shared memory: LDS instead of generic loads)
+  if (hsv_staged) {
+    for (int i = threadIdx.x; i < h.n_cropped; i += blockDim.x) s_hsv[i] = a.hsv[i];
+  }
+  // (separate call sites so that the compiler sees which pointers are shared memory: LDS instead of generic loads)
   if (cs_staged) {
-    unsigned short* s_cs = reinterpret_cast<unsigned short*>(dyn_smem + n_pts);
+    unsigned short* s_cs = reinterpret_cast<unsigned short*>(reinterpret_cast<unsigned char*>(dyn_smem) + used);
     for (int i = threadIdx.x; i <= h.n_cells; i += blockDim.x) s_cs[i] = (unsigned short)a.cell_start[i];
     __syncthreads();
-    weight_items<USE_HSV, unsigned short>(a, h, s_cs, reinterpret_cast<const float4*>(s_pts), s_table, lut_h, lut_s);
+    if (hsv_staged) weight_items<USE_HSV, unsigned short>(a, h, s_cs, reinterpret_cast<const float4*>(s_pts), s_hsv, s_table, lut_h, lut_s);
+    else weight_items<USE_HSV, unsigned short>(a, h, s_cs, reinterpret_cast<const float4*>(s_pts), a.hsv, s_table, lut_h, lut_s);
   } else if (pts_staged) {
     __syncthreads();
-    weight_items<USE_HSV, int>(a, h, a.cell_start, reinterpret_cast<const float4*>(s_pts), s_table, lut_h, lut_s);
+    if (hsv_staged) weight_items<USE_HSV, int>(a, h, a.cell_start, reinterpret_cast<const float4*>(s_pts), s_hsv, s_table, lut_h, lut_s);
+    else weight_items<USE_HSV, int>(a, h, a.cell_start, reinterpret_cast<const float4*>(s_pts), a.hsv, s_table, lut_h, lut_s);
   } else {
-    weight_items<USE_HSV, int>(a, h, a.cell_start, a.pts, s_table, lut_h, lut_s);
+    weight_items<USE_HSV, int>(a, h, a.cell_start, a.pts, a.hsv, s_table, lut_h, lut_s);
   }
 }
 
