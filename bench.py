@@ -15,6 +15,10 @@ Workloads (config.workload):
        ncclAllReduce / ncclAllGather (--exchange nccl, with rank 0 downsampling and broadcasting the
        scene); resample/normalise/update run replicated.
   c4   BASELINE.json configs[3]: 100 000 particles in total, sharded over the N GPUs (strong scaling).
+  c3   BASELINE.json configs[2]: KLD-adaptive tracker, at most 10 000 particles (epsilon 0.02, bins 2 cm / 0.02 rad),
+       per-frame downsample + index rebuild; the particle count lives on the device, evals are counted there.
+  c5   BASELINE.json configs[4]: 8 objects (8 models, 1000 particles each) tracked in one 217k-pt scene through
+       pft_compute_batch (every tracker on its own stream, forked from / joined to the scene's stream).
 
 `value`   = likelihood evals/s, whole job, inputs resident in HBM (raw frames pre-uploaded).
 `e2e`     = the same through the public API with HOST buffers: every step uploads the raw frame from
@@ -42,6 +46,8 @@ N_FRAMES = 6          # pre-rendered frames, played ping-pong so that motion sta
 LEAF = 0.01
 PARTICLES_PER_GPU = 1000
 C4_PARTICLES = 100_000
+C3_MAX_PARTICLES = 10_000
+C5_OBJECTS = 8
 ITERATIONS = 2
 
 
@@ -53,9 +59,9 @@ def env_int(name, default):
 
 
 # ------------------------------------------------------------------ workload
-def make_frames(n_frames):
+def make_frames(n_frames, n_objects=1):
     from pcl_tracking_b200 import synth
-    objs = synth.default_objects(1)
+    objs = synth.default_objects(n_objects)
     frames = []
     oid0 = None
     for f in range(n_frames):
@@ -73,9 +79,9 @@ def frame_order(k, n_frames):
     return r if r < n_frames else period - r
 
 
-def raw_model(frames, oid0):
+def raw_model(frames, oid0, k=0):
     from pcl_tracking_b200 import synth
-    return synth.model_points(frames[0], oid0, 0)
+    return synth.model_points(frames[0], oid0, k)
 
 
 # ------------------------------------------------------------------ clocks
@@ -211,11 +217,11 @@ def reference_arm(args):
     if rank != 0:
         return 0
     frames, oid0 = make_frames(N_FRAMES)
-    n_particles = PARTICLES_PER_GPU * args.gpus if args.workload == "c2" else C4_PARTICLES
+    n_particles = C4_PARTICLES if args.workload == "c4" else PARTICLES_PER_GPU * args.gpus
     r = run_cpu(frames, oid0, n_particles, args.steps, args.warmup, budget_s=150.0)
     line = {
         "impl": "reference", "metric": METRIC, "value": r["evals_per_s"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak" if args.workload == "c2" else "strong",
+        "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong" if args.workload == "c4" else "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, r["model_points"], n_particles),
         "frames_per_s": r["frames_per_s"],
@@ -229,11 +235,17 @@ def reference_arm(args):
 
 
 def workload_config(args, M, n_particles):
+    names = {
+        "c2": "c2: BASELINE.json configs[1], 512x424 (217088-pt) Kinect2-shaped synthetic scene, %d-pt model, %d particles"
+              " per GPU (one tracker sharded by particle), Distance+HSV coherence, 2 iterations/frame" % (M, PARTICLES_PER_GPU),
+        "c4": "c4: BASELINE.json configs[3], 100000 particles sharded over the GPUs, 217088-pt scene, %d-pt model, Distance+HSV" % M,
+        "c3": "c3: BASELINE.json configs[2], KLD-adaptive particle count (<= %d, epsilon 0.02, bins 2 cm / 0.02 rad), 217088-pt scene, %d-pt model,"
+              " per-frame voxel-grid downsample + index rebuild, Distance+HSV" % (C3_MAX_PARTICLES, M),
+        "c5": "c5: BASELINE.json configs[4], %d objects (%d model points in total, %d particles each) tracked simultaneously in one 217088-pt scene"
+              " (pft_compute_batch), Distance+HSV" % (C5_OBJECTS, M, PARTICLES_PER_GPU),
+    }
     return {
-        "workload": ("c2: BASELINE.json configs[1], 512x424 (217088-pt) Kinect2-shaped synthetic scene, %d-pt model, %d particles"
-                     " per GPU (one tracker sharded by particle), Distance+HSV coherence, 2 iterations/frame" % (M, PARTICLES_PER_GPU))
-        if args.workload == "c2" else
-        ("c4: BASELINE.json configs[3], 100000 particles sharded over the GPUs, 217088-pt scene, %d-pt model, Distance+HSV" % M),
+        "workload": names[args.workload],
         "scene_points": 217088, "model_points": M, "particles_total": n_particles, "iterations_per_frame": ITERATIONS,
         "leaf_m": LEAF, "max_distance_m": 0.1, "l2": "flushed between timed steps (256 MiB write)", "parallelism": "particle-shard x%d" % args.gpus + ("" if args.gpus == 1 else
                                                                  ", %s exchange, scene %s" % (args.exchange, args.scene or ("replicate" if args.exchange == "peer" else "broadcast"))),
@@ -247,7 +259,7 @@ def main():
     ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c2", "c4"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true", help="debug only: do not flush L2 between steps")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
@@ -289,31 +301,53 @@ def main():
     owns_frames = rank == 0 or scene_mode == "replicate"
     stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
 
-    frames, oid0 = make_frames(N_FRAMES)
+    n_objects = C5_OBJECTS if args.workload == "c5" else 1
+    if n_objects > 1 and world > 1:
+        print("bench.py: the multi-object workload runs on one GPU (independent trackers: replicas only)", file=sys.stderr)
+        return 2
+    frames, oid0 = make_frames(N_FRAMES, n_objects)
     n_pts = len(frames[0])
-    n_particles = PARTICLES_PER_GPU * world if args.workload == "c2" else C4_PARTICLES
+    n_particles = {"c2": PARTICLES_PER_GPU * world, "c4": C4_PARTICLES, "c3": C3_MAX_PARTICLES, "c5": PARTICLES_PER_GPU}[args.workload]
 
-    # model preparation on the GPU (ref :656-674) -- init-time, untimed
-    raw_model_cloud = pcl.PointCloud(raw_model(frames, oid0), ctx=ctx)
-    model_cloud, centroid = pcl.prepare_model(raw_model_cloud, LEAF, ctx=ctx)
-    M = model_cloud.size()
+    trackers, M = [], 0
+    for k in range(n_objects):
+        # model preparation on the GPU (ref :656-674) -- init-time, untimed
+        raw_model_cloud = pcl.PointCloud(raw_model(frames, oid0, k), ctx=ctx)
+        model_cloud, centroid = pcl.prepare_model(raw_model_cloud, LEAF, ctx=ctx)
+        M += model_cloud.size()
+        if args.workload == "c3":
+            tracker = pcl.KLDAdaptiveParticleFilterOMPTracker(16, ctx=ctx)
+            pcl.configure_like_reference(tracker, particle_num=n_particles, max_particle_num=n_particles, use_hsv=True, iteration_num=ITERATIONS)
+            tracker.setEpsilon(0.02)
+            tracker.setBinSize([0.02] * 6)
+        else:
+            tracker = pcl.ParticleFilterOMPTracker(16, ctx=ctx)
+            pcl.configure_like_reference(tracker, particle_num=n_particles, use_hsv=True, iteration_num=ITERATIONS)
+        m = np.eye(4, dtype=np.float32)
+        m[:3, 3] = centroid
+        tracker.setTrans(m)
+        tracker.seed(1234 + k)
+        if world > 1 and args.exchange == "nccl":
+            tracker.commInit(world, rank, uid[0])
+        elif world > 1:
+            # NVLink peer exchange: windows mapped with CUDA IPC, handles shipped by torch.distributed
+            tracker.setShard(world, rank)
+            handles = [None] * world
+            dist.all_gather_object(handles, tracker.peerExport())
+            tracker.peerAttach(handles)
+            dist.barrier()
+        tracker.setReferenceCloud(model_cloud)
+        trackers.append(tracker)
+    tracker = trackers[0]
 
-    tracker = pcl.ParticleFilterOMPTracker(16, ctx=ctx)
-    pcl.configure_like_reference(tracker, particle_num=n_particles, use_hsv=True, iteration_num=ITERATIONS)
-    m = np.eye(4, dtype=np.float32)
-    m[:3, 3] = centroid
-    tracker.setTrans(m)
-    tracker.seed(1234)
-    if world > 1 and args.exchange == "nccl":
-        tracker.commInit(world, rank, uid[0])
-    elif world > 1:
-        # NVLink peer exchange: windows mapped with CUDA IPC, handles shipped by torch.distributed
-        tracker.setShard(world, rank)
-        handles = [None] * world
-        dist.all_gather_object(handles, tracker.peerExport())
-        tracker.peerAttach(handles)
-        dist.barrier()
-    tracker.setReferenceCloud(model_cloud)
+    def compute_all():
+        if len(trackers) > 1:
+            pcl.compute_batch(trackers)
+        else:
+            tracker.compute()
+
+    def eval_count():
+        return sum(t.evalCount() for t in trackers)
 
     # resident inputs: raw frames in HBM (rank 0 owns the sensor; the other ranks receive the downsampled scene)
     dev_frames = [pcl.PointCloud(f, ctx=ctx) for f in frames] if owns_frames else None
@@ -337,8 +371,9 @@ def main():
             vg.filter(ds)
         if world > 1 and scene_mode == "broadcast":
             ds.broadcast(n_pts, 0)
-        tracker.setInputCloud(ds)
-        tracker.compute()
+        for t in trackers:
+            t.setInputCloud(ds)
+        compute_all()
 
     def step_e2e(k):
         if owns_frames:
@@ -347,9 +382,10 @@ def main():
             vg.filter(ds)
         if world > 1 and scene_mode == "broadcast":
             ds.broadcast(n_pts, 0)
-        tracker.setInputCloud(ds)
-        tracker.compute()
-        return tracker.getResult()  # D2H of the pose: synchronises
+        for t in trackers:
+            t.setInputCloud(ds)
+        compute_all()
+        return [t.getResult() for t in trackers]  # D2H of the pose(s): synchronises
 
     flush_buf = None if args.no_flush else torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
 
@@ -398,39 +434,48 @@ def main():
     sync_all()
     sampler = ClockSampler(local_rank)
     launches0 = pcl.kernel_launch_count()
+    evals0 = eval_count()  # counted on the device (the live particle count of a KLD tracker never travels to the host)
     total_ms, wall_s = timed(step_resident, args.steps, W, sampler)
+    evals_timed = eval_count() - evals0
     launches = pcl.kernel_launch_count() - launches0
     if rank == 0:
         print("bench: timed %d steps: %.3f ms/step, ds %d pts, launches %d" % (args.steps, total_ms / args.steps, ds.size(), launches), file=sys.stderr)
     ms_per_step = total_ms / args.steps
-    evals_per_step = float(n_particles) * M * ITERATIONS
+    evals_per_step = float(evals_timed) / args.steps
     value = evals_per_step / (ms_per_step * 1e-3)
     graph_replays = tracker.graphReplays()
 
     # ---- e2e: host buffers in, pose out, every step
     for k in range(3):
         step_e2e(k)
+    evals0 = eval_count()
     e2e_ms, _ = timed(step_e2e, args.steps, W + args.steps)
     e2e_ms_per_step = e2e_ms / args.steps
-    e2e_value = evals_per_step / (e2e_ms_per_step * 1e-3)
+    e2e_value = float(eval_count() - evals0) / args.steps / (e2e_ms_per_step * 1e-3)
 
     # ---- roofline of the dominant kernel (weight_kernel): CUDA events around every launch of it on the
     # library's stream, over `steps` more frames driven through the same code path without the graph
-    tracker.enableTiming(True)
+    for t in trackers:
+        t.enableTiming(True)
     w_ms, n_w = 0.0, 0
     c_ms = 0.0
     rsteps = min(args.steps, 100)
+    evals0 = eval_count()
     for k in range(rsteps):
         flush_l2()
         step_resident(W + k)
-        a, b = tracker.timing()
-        w_ms += a
-        c_ms += b
-        n_w += ITERATIONS
-    tracker.enableTiming(False)
+        for t in trackers:
+            a, b = t.timing()
+            w_ms += a
+            c_ms += b
+            n_w += ITERATIONS
+    evals_per_launch = float(eval_count() - evals0) / max(n_w, 1) / world  # this rank's share of every weight()
+    for t in trackers:
+        t.enableTiming(False)
     info = tracker.indexInfo()
-    n_local = (n_particles - rank + world - 1) // world
-    bytes_per_launch = 32.0 * n_local * M + 36.0 * n_local + 16.0 * info["n_cropped"]
+    M_mean = float(M) / len(trackers)
+    n_local = evals_per_launch / M_mean
+    bytes_per_launch = 32.0 * evals_per_launch + 36.0 * n_local + 16.0 * info["n_cropped"]
     w_ms_per_launch = w_ms / max(n_w, 1)
     achieved = bytes_per_launch / (w_ms_per_launch * 1e-3) / 1e9
     peak, peak_src = 6650.0, "fallback"
@@ -459,10 +504,11 @@ def main():
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W, "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "weak" if args.workload == "c2" else "strong", "vs_baseline": None, "dtype": "f32",
+            "higher_is_better": True, "scaling": "strong" if args.workload == "c4" else "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": workload_config(args, M, n_particles),
+            "evals_per_step": evals_per_step,
             "frames_per_s": 1e3 / ms_per_step,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(frames[0].nbytes) * (world if scene_mode == "replicate" else 1), "d2h_bytes_per_step": 32 + 64,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(frames[0].nbytes) * (world if scene_mode == "replicate" else 1), "d2h_bytes_per_step": (32 + 64) * len(trackers),
                     "ms_per_step": e2e_ms_per_step, "frames_per_s": 1e3 / e2e_ms_per_step},
             "gpu_launches": int(launches),
             "graph_replays": int(graph_replays),
@@ -470,7 +516,8 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                          "kernel": "weight_kernel<HSV>", "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": bytes_per_launch, "ms_per_launch": w_ms_per_launch,
-                         "evals_per_s_in_kernel": n_local * M / (w_ms_per_launch * 1e-3),
+                         "evals_per_s_in_kernel": evals_per_launch / (w_ms_per_launch * 1e-3),
+                         "particles_per_launch": n_local,
                          "share_of_compute": w_ms / c_ms if c_ms > 0 else None,
                          "how": "CUDA events around each weight_kernel launch on the library stream, %d frames, stream-launched (no graph)" % rsteps},
             "scene_index": info,

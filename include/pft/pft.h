@@ -157,6 +157,9 @@ PFT_API int pft_tracker_get_particles(pft_tracker* t, pft_particle* out, size_t 
 PFT_API int pft_particle_to_matrix(pft_context* ctx, const pft_particle* p, float* m12);
 /* resetTracking */
 PFT_API int pft_tracker_reset(pft_tracker* t);
+/* likelihood evaluations so far (sum over weight() calls of live particles x model points; counted on the device,
+ * the particle count of a KLD tracker never travels to the host) */
+PFT_API int pft_tracker_get_eval_count(pft_tracker* t, uint64_t* out);
 /* getFitRatio */
 PFT_API int pft_tracker_get_fit_ratio(pft_tracker* t, double* out);
 

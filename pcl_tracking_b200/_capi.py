@@ -75,6 +75,7 @@ SIGNATURES = {
     "pft_tracker_get_particles": (_i, [_vp, _vp, _sz, _psz]),
     "pft_particle_to_matrix": (_i, [_vp, _vp, _vp]),
     "pft_tracker_reset": (_i, [_vp]),
+    "pft_tracker_get_eval_count": (_i, [_vp, C.POINTER(C.c_uint64)]),
     "pft_tracker_get_fit_ratio": (_i, [_vp, C.POINTER(C.c_double)]),
     "pft_tracker_set_particles": (_i, [_vp, _vp, _sz]),
     "pft_tracker_set_result": (_i, [_vp, _vp, _vp]),

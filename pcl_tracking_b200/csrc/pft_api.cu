@@ -102,6 +102,7 @@ void pft_context_destroy(pft_context* c) {
   pft::DevBuf* bufs[] = {&c->k1_keys, &c->k1_first, &c->k1_vid, &c->k1_slot_of, &c->k1_acc_xyz, &c->k1_acc_rgbc, &c->k1_blk, &c->staging, &c->tmp_cloud_pts, &c->tmp_hdr, &c->tmp_f};
   for (auto* b : bufs) b->release();
   if (c->pinned) cudaFreeHost(c->pinned);
+  if (c->batch_fork) cudaEventDestroy(c->batch_fork);
   cudaStreamDestroy(c->stream);
   delete c;
 }

@@ -32,6 +32,7 @@ struct pft_context {
   // NCCL communicator shared by the clouds and trackers of this context (one process per GPU)
   void* comm = nullptr;
   int nranks = 1, rank = 0;
+  cudaEvent_t batch_fork = nullptr;  // pft_compute_batch: the point of the context stream the trackers' streams fork from
 };
 
 struct pft_cloud {

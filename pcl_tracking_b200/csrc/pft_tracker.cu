@@ -160,7 +160,13 @@ struct pft_tracker {
   int n_slots = 0;
   int chunks = 1, chunk_len = 0;
 
+  // pft_compute_batch: every tracker of a batch runs on a stream of its own, forked from / joined to the context stream
+  cudaStream_t batch_stream = nullptr;
+  cudaEvent_t batch_done = nullptr;
+  bool batch_active = false;
+
   int slice_cap() const { return (n_cap + nranks - 1) / nranks; }
+  cudaStream_t run_stream() const { return batch_active ? batch_stream : ctx->stream; }
 };
 
 namespace {
@@ -177,7 +183,7 @@ void stage_mark(pft_tracker* t, const char* name) {
     t->ev_k_name.push_back(name);
   }
   t->ev_k_name[t->n_ev_k] = name;
-  cudaEventRecord(t->ev_k[t->n_ev_k++], t->ctx->stream);
+  cudaEventRecord(t->ev_k[t->n_ev_k++], t->run_stream());
 }
 
 void release_all(pft_tracker* t) {
@@ -269,7 +275,7 @@ int wanted_cap(const pft_tracker* t) { return t->kld ? std::max(t->max_particle_
 int ensure_particle_buffers(pft_tracker* t) {
   const int cap = wanted_cap(t);
   if (cap <= 0) { set_last_error("particle count is zero: call setParticleNum / setMaximumParticleNum first"); return PFT_ERR_STATE; }
-  cudaStream_t s = t->ctx->stream;
+  cudaStream_t s = t->run_stream();
   int rc;
   if (!t->st.p) {
     if ((rc = t->st.reserve(sizeof(TrackerState)))) return rc;
@@ -346,8 +352,8 @@ int upload_kl_table(pft_tracker* t) {
   const int n = t->n_cap + 2;
   std::vector<double> tab(n, 0.0);
   for (int k = 2; k < n; ++k) tab[k] = kl_bound(k, t->delta, t->epsilon);
-  PFT_CUDA_TRY(cudaMemcpyAsync(t->klb.p, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice, t->ctx->stream));
-  PFT_CUDA_TRY(cudaStreamSynchronize(t->ctx->stream));
+  PFT_CUDA_TRY(cudaMemcpyAsync(t->klb.p, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice, t->run_stream()));
+  PFT_CUDA_TRY(cudaStreamSynchronize(t->run_stream()));
   return PFT_OK;
 }
 
@@ -362,7 +368,7 @@ int ensure_draw_buffers(pft_tracker* t, int slots, int stride) {
 
 // Draw arrays of one resample slot: injected (slot-indexed) or generated on the device into slot 0.
 int prepare_draws(pft_tracker* t, int slot, int count, const float** usel, const float** normals, const float** umot) {
-  cudaStream_t s = t->ctx->stream;
+  cudaStream_t s = t->run_stream();
   if (t->inj_stride > 0) {
     if (slot >= t->inj_slots || count > t->inj_stride) {
       set_last_error("injected draws cover %d slots x %d, need slot %d x %d", t->inj_slots, t->inj_stride, slot, count);
@@ -391,7 +397,7 @@ int ensure_index_buffers(pft_tracker* t) {
   const size_t cap = std::max<size_t>(t->input ? t->input->capacity : 0, 1);
   if (cap <= t->scene_cap) return PFT_OK;
   invalidate_graph(t);
-  PFT_CUDA_TRY(cudaStreamSynchronize(t->ctx->stream));
+  PFT_CUDA_TRY(cudaStreamSynchronize(t->run_stream()));
   int rc;
   if ((rc = t->ipts.reserve((cap + 4) * sizeof(float4)))) return rc;
   if ((rc = t->ihsv.reserve((cap + 4) * sizeof(unsigned int)))) return rc;
@@ -433,7 +439,7 @@ int stage_init_particles(pft_tracker* t) {
   if (rc) return rc;
   if (t->particle_num <= 0) { set_last_error("setParticleNum was not called"); return PFT_ERR_STATE; }
   if ((rc = upload_kl_table(t))) return rc;
-  cudaStream_t s = t->ctx->stream;
+  cudaStream_t s = t->run_stream();
   PFT_CUDA_TRY(cudaMemcpyAsync(t->d_trans.p, t->trans, sizeof(t->trans), cudaMemcpyHostToDevice, s));
   const float *usel, *normals, *umot;
   if ((rc = prepare_draws(t, 0, t->particle_num, &usel, &normals, &umot))) return rc;
@@ -450,7 +456,7 @@ int stage_resample(pft_tracker* t, int slot) {
   if (!t->has_particles) { set_last_error("resample before particles exist"); return PFT_ERR_STATE; }
   if (!t->input) { set_last_error("resample needs an input cloud (setInputCloud)"); return PFT_ERR_STATE; }
   if (t->kld && t->max_particle_num <= 0) { set_last_error("KLD tracker: setMaximumParticleNum was not called"); return PFT_ERR_STATE; }
-  cudaStream_t s = t->ctx->stream;
+  cudaStream_t s = t->run_stream();
   const int count = t->kld ? t->max_particle_num : t->n_cap;
   const float *usel, *normals, *umot;
   int rc = prepare_draws(t, slot, count, &usel, &normals, &umot);
@@ -501,7 +507,7 @@ int check_weight_ready(pft_tracker* t) {
 int weight_phase_box(pft_tracker* t) {
   int rc = check_weight_ready(t);
   if (rc) return rc;
-  cudaStream_t s = t->ctx->stream;
+  cudaStream_t s = t->run_stream();
   const int sm = t->ctx->sm_count;
   TrackerState* st = t->st.as<TrackerState>();
   DevParticle* parts = t->parts[t->cur].as<DevParticle>();
@@ -522,7 +528,7 @@ int weight_phase_box(pft_tracker* t) {
 
 // crop box exchange: union over ranks
 int weight_comm_box(pft_tracker* t) {
-  cudaStream_t s = t->ctx->stream;
+  cudaStream_t s = t->run_stream();
   TrackerState* st = t->st.as<TrackerState>();
   if (t->peer_mode) {
     peer_box_exchange_kernel<<<1, 32, 0, s>>>(st, t->peers);
@@ -542,7 +548,7 @@ int weight_comm_box(pft_tracker* t) {
 int weight_phase_eval(pft_tracker* t) {
   int rc = check_weight_ready(t);
   if (rc) return rc;
-  cudaStream_t s = t->ctx->stream;
+  cudaStream_t s = t->run_stream();
   const int sm = t->ctx->sm_count;
   TrackerState* st = t->st.as<TrackerState>();
   const pft_cloud* in = t->input;
@@ -617,7 +623,7 @@ int weight_comm_raw(pft_tracker* t) {
   if (t->peer_mode || !t->comm) return PFT_OK;  // peer mode: raw_weights_kernel has already pushed the values
   const int local_cap = t->slice_cap();
   PFT_NCCL_TRY(g_nccl.AllGather(t->raw.as<float>() + (size_t)t->rank * local_cap, t->raw.as<float>(), (size_t)local_cap, kNcclFloat, t->comm,
-                                t->ctx->stream));
+                                t->run_stream()));
   return PFT_OK;
 }
 
@@ -625,8 +631,8 @@ int weight_comm_raw(pft_tracker* t) {
 int weight_phase_normalize(pft_tracker* t) {
   int rc = check_weight_ready(t);
   if (rc) return rc;
-  normalize_kernel<<<1, 1024, 0, t->ctx->stream>>>(t->st.as<TrackerState>(), t->parts[t->cur].as<DevParticle>(), t->raw.as<float>(), t->alpha, t->nranks,
-                                                   t->slice_cap(), t->input->d_hdr(), t->peer_mode ? reinterpret_cast<PeerWindow*>(t->peer_local) : nullptr);
+  normalize_kernel<<<1, 1024, 0, t->run_stream()>>>(t->st.as<TrackerState>(), t->parts[t->cur].as<DevParticle>(), t->raw.as<float>(), t->alpha, t->nranks,
+                                                   t->slice_cap(), t->input->d_hdr(), t->peer_mode ? reinterpret_cast<PeerWindow*>(t->peer_local) : nullptr, t->M);
   PFT_LAUNCH_CHECK();
   stage_mark(t, "normalize_kernel");
   t->changed = true;  // change detector is off upstream => changed_ = true after every weight()
@@ -644,7 +650,7 @@ int stage_weight(pft_tracker* t) {
 
 int stage_update(pft_tracker* t) {
   if (!t->has_particles || !t->input) { set_last_error("update before weight"); return PFT_ERR_STATE; }
-  update_kernel<<<1, 1024, 0, t->ctx->stream>>>(t->st.as<TrackerState>(), t->parts[t->cur].as<DevParticle>(), t->input->d_hdr());
+  update_kernel<<<1, 1024, 0, t->run_stream()>>>(t->st.as<TrackerState>(), t->parts[t->cur].as<DevParticle>(), t->input->d_hdr());
   PFT_LAUNCH_CHECK();
   stage_mark(t, "update_kernel");
   return PFT_OK;
@@ -668,14 +674,14 @@ int prepare_compute(pft_tracker* t) {
   const size_t need_partial = (size_t)t->chunks * t->n_cap * sizeof(double);
   if (need_partial > t->partial.bytes) {
     invalidate_graph(t);
-    PFT_CUDA_TRY(cudaStreamSynchronize(t->ctx->stream));
+    PFT_CUDA_TRY(cudaStreamSynchronize(t->run_stream()));
     if ((rc = t->partial.reserve(need_partial))) return rc;
   }
   if (t->debug_nn > 0) {
     const size_t need = (size_t)t->debug_nn * t->M;
     if (need * sizeof(int) > t->dbg_idx.bytes) {
       invalidate_graph(t);
-      PFT_CUDA_TRY(cudaStreamSynchronize(t->ctx->stream));
+      PFT_CUDA_TRY(cudaStreamSynchronize(t->run_stream()));
       if ((rc = t->dbg_idx.reserve(need * sizeof(int)))) return rc;
       if ((rc = t->dbg_d2.reserve(need * sizeof(float)))) return rc;
     }
@@ -711,13 +717,15 @@ int pft_tracker_create(pft_context* ctx, int kld, pft_tracker** out) {
 void pft_tracker_destroy(pft_tracker* t) {
   if (!t) return;
   cudaSetDevice(t->ctx->device);
-  cudaStreamSynchronize(t->ctx->stream);
+  cudaStreamSynchronize(t->run_stream());
   if (t->graph_exec) cudaGraphExecDestroy(t->graph_exec);
   for (auto e : t->ev_w) cudaEventDestroy(e);
   for (auto e : t->ev_k) cudaEventDestroy(e);
   if (t->ev_c0) cudaEventDestroy(t->ev_c0);
   if (t->ev_c1) cudaEventDestroy(t->ev_c1);
   pft_tracker_peer_detach(t);
+  if (t->batch_stream) cudaStreamDestroy(t->batch_stream);
+  if (t->batch_done) cudaEventDestroy(t->batch_done);
   release_all(t);
   delete t;
 }
@@ -849,7 +857,7 @@ int pft_tracker_set_reference_points(pft_tracker* t, const void* host_points, si
   int rc = tmp.ensure(n);
   if (!rc) rc = pft_cloud_upload(&tmp, host_points, n, layout);
   if (!rc) rc = set_reference_device(t, tmp.d_pts(), (int)n);
-  cudaStreamSynchronize(t->ctx->stream);
+  cudaStreamSynchronize(t->run_stream());
   tmp.pts.release(); tmp.hdr.release();
   return rc;
 }
@@ -865,7 +873,7 @@ int pft_tracker_set_input_cloud(pft_tracker* t, const pft_cloud* cloud) {
 static int compute_one(pft_tracker* t) {
   if (is_noop(t)) return PFT_OK;
   PFT_CUDA_TRY(cudaSetDevice(t->ctx->device));
-  cudaStream_t s = t->ctx->stream;
+  cudaStream_t s = t->run_stream();
   int rc = prepare_compute(t);
   if (rc) return rc;
   if (!t->has_particles && (rc = stage_init_particles(t))) return rc;
@@ -930,20 +938,50 @@ int pft_tracker_compute(pft_tracker* t) {
 
 int pft_compute_batch(pft_tracker** ts, int n) {
   if (n < 0 || (n && !ts)) { set_last_error("pft_compute_batch: bad arguments"); return PFT_ERR_INVALID; }
-  // Independent trackers on one scene (ref: src/auto_tracking.cpp:688-697 loops them serially).  Each
-  // tracker's frame is one graph launch on its context's stream.
+  // Independent trackers on one scene (ref: src/auto_tracking.cpp:688-697 loops them serially).  Each tracker's frame
+  // (one graph launch in steady state) runs on a stream of its own, forked from the context stream -- which carries
+  // the scene that was just downsampled -- and joined back to it, so that the many small latency-bound kernels of
+  // the trackers overlap on the GPU.
   for (int i = 0; i < n; ++i) {
     if (!ts[i]) { set_last_error("pft_compute_batch: null tracker %d", i); return PFT_ERR_INVALID; }
-    int rc = compute_one(ts[i]);
-    if (rc) return rc;
   }
-  return PFT_OK;
+  bool concurrent = n > 1;
+  for (int i = 1; i < n && concurrent; ++i) concurrent = ts[i]->ctx == ts[0]->ctx;
+  for (int i = 0; i < n && concurrent; ++i) concurrent = !ts[i]->timing && !ts[i]->comm && !ts[i]->peer_mode;
+  if (!concurrent) {
+    for (int i = 0; i < n; ++i) {
+      int rc = compute_one(ts[i]);
+      if (rc) return rc;
+    }
+    return PFT_OK;
+  }
+  pft_context* ctx = ts[0]->ctx;
+  PFT_CUDA_TRY(cudaSetDevice(ctx->device));
+  if (!ctx->batch_fork) PFT_CUDA_TRY(cudaEventCreateWithFlags(&ctx->batch_fork, cudaEventDisableTiming));
+  PFT_CUDA_TRY(cudaEventRecord(ctx->batch_fork, ctx->stream));
+  int rc = PFT_OK;
+  int launched = 0;
+  for (int i = 0; i < n && rc == PFT_OK; ++i) {
+    pft_tracker* t = ts[i];
+    if (!t->batch_stream) {
+      PFT_CUDA_TRY(cudaStreamCreateWithFlags(&t->batch_stream, cudaStreamNonBlocking));
+      PFT_CUDA_TRY(cudaEventCreateWithFlags(&t->batch_done, cudaEventDisableTiming));
+    }
+    PFT_CUDA_TRY(cudaStreamWaitEvent(t->batch_stream, ctx->batch_fork, 0));
+    t->batch_active = true;
+    rc = compute_one(t);
+    t->batch_active = false;
+    cudaEventRecord(t->batch_done, t->batch_stream);
+    ++launched;
+  }
+  for (int i = 0; i < launched; ++i) cudaStreamWaitEvent(ctx->stream, ts[i]->batch_done, 0);
+  return rc;
 }
 
 static int read_state(pft_tracker* t, TrackerState* host) {
   if (!t->st.p) { memset(host, 0, sizeof(*host)); host->rep.one = 1.f; host->motion.one = 1.f; return PFT_OK; }
   PFT_CUDA_TRY(cudaSetDevice(t->ctx->device));
-  cudaStream_t s = t->ctx->stream;
+  cudaStream_t s = t->run_stream();
   PFT_CUDA_TRY(cudaMemcpyAsync(t->ctx->pinned, t->st.p, sizeof(TrackerState), cudaMemcpyDeviceToHost, s));
   PFT_CUDA_TRY(cudaStreamSynchronize(s));
   memcpy(host, t->ctx->pinned, sizeof(TrackerState));
@@ -969,6 +1007,15 @@ int pft_tracker_get_motion(pft_tracker* t, pft_particle* out) {
   return PFT_OK;
 }
 
+int pft_tracker_get_eval_count(pft_tracker* t, uint64_t* out) {
+  if (!t || !out) { set_last_error("null argument"); return PFT_ERR_INVALID; }
+  TrackerState h;
+  int rc = read_state(t, &h);
+  if (rc) return rc;
+  *out = h.evals;
+  return PFT_OK;
+}
+
 int pft_tracker_get_fit_ratio(pft_tracker* t, double* out) {
   if (!t || !out) { set_last_error("null argument"); return PFT_ERR_INVALID; }
   TrackerState h;
@@ -991,7 +1038,7 @@ int pft_tracker_get_particles(pft_tracker* t, pft_particle* out, size_t capacity
   if (n > capacity) { set_last_error("pft_tracker_get_particles: %zu particles, capacity %zu", n, capacity); return PFT_ERR_CAPACITY; }
   if (n == 0) return PFT_OK;
   if (!out) { set_last_error("null buffer"); return PFT_ERR_INVALID; }
-  cudaStream_t s = t->ctx->stream;
+  cudaStream_t s = t->run_stream();
   PFT_CUDA_TRY(cudaMemcpyAsync(out, t->parts[t->cur].p, n * sizeof(pft_particle), cudaMemcpyDeviceToHost, s));
   PFT_CUDA_TRY(cudaStreamSynchronize(s));
   return PFT_OK;
@@ -1020,7 +1067,7 @@ int pft_tracker_reset(pft_tracker* t) {
   invalidate_graph(t);
   if (t->st.p) {
     PFT_CUDA_TRY(cudaSetDevice(t->ctx->device));
-    cudaStream_t s = t->ctx->stream;
+    cudaStream_t s = t->run_stream();
     PFT_CUDA_TRY(cudaMemsetAsync(&t->st.as<TrackerState>()->has_particles, 0, sizeof(int), s));
     if (t->slot_aabb.p && t->n_cap > 0) {
       std::vector<float> init((size_t)t->n_cap * 6);
@@ -1041,7 +1088,7 @@ int pft_tracker_set_particles(pft_tracker* t, const pft_particle* p, size_t n) {
   int rc = ensure_particle_buffers(t);
   if (rc) return rc;
   if ((rc = upload_kl_table(t))) return rc;
-  cudaStream_t s = t->ctx->stream;
+  cudaStream_t s = t->run_stream();
   PFT_CUDA_TRY(cudaMemcpyAsync(t->parts[t->cur].p, p, n * sizeof(pft_particle), cudaMemcpyHostToDevice, s));
   const int nn = (int)n, one = 1;
   PFT_CUDA_TRY(cudaMemcpyAsync(&t->st.as<TrackerState>()->particle_num, &nn, sizeof(int), cudaMemcpyHostToDevice, s));
@@ -1057,7 +1104,7 @@ int pft_tracker_set_result(pft_tracker* t, const pft_particle* rep, const pft_pa
   PFT_CUDA_TRY(cudaSetDevice(t->ctx->device));
   int rc = ensure_particle_buffers(t);
   if (rc) return rc;
-  cudaStream_t s = t->ctx->stream;
+  cudaStream_t s = t->run_stream();
   if (rep) PFT_CUDA_TRY(cudaMemcpyAsync(&t->st.as<TrackerState>()->rep, rep, sizeof(pft_particle), cudaMemcpyHostToDevice, s));
   if (motion) PFT_CUDA_TRY(cudaMemcpyAsync(&t->st.as<TrackerState>()->motion, motion, sizeof(pft_particle), cudaMemcpyHostToDevice, s));
   PFT_CUDA_TRY(cudaStreamSynchronize(s));
@@ -1068,7 +1115,7 @@ int pft_tracker_inject_draws(pft_tracker* t, const float* usel, const float* nor
   if (!t) { set_last_error("null tracker"); return PFT_ERR_INVALID; }
   PFT_CUDA_TRY(cudaSetDevice(t->ctx->device));
   invalidate_graph(t);
-  PFT_CUDA_TRY(cudaStreamSynchronize(t->ctx->stream));
+  PFT_CUDA_TRY(cudaStreamSynchronize(t->run_stream()));
   if (!usel || !normals6 || !umot) {
     t->inj_slots = 0; t->inj_stride = 0; t->draw_cap = 0;
     return PFT_OK;
@@ -1077,7 +1124,7 @@ int pft_tracker_inject_draws(pft_tracker* t, const float* usel, const float* nor
   int rc = ensure_draw_buffers(t, slots, stride);
   if (rc) return rc;
   const size_t n = (size_t)slots * stride;
-  cudaStream_t s = t->ctx->stream;
+  cudaStream_t s = t->run_stream();
   PFT_CUDA_TRY(cudaMemcpyAsync(t->d_usel.p, usel, n * sizeof(float), cudaMemcpyHostToDevice, s));
   PFT_CUDA_TRY(cudaMemcpyAsync(t->d_normals.p, normals6, n * 6 * sizeof(float), cudaMemcpyHostToDevice, s));
   PFT_CUDA_TRY(cudaMemcpyAsync(t->d_umot.p, umot, n * sizeof(float), cudaMemcpyHostToDevice, s));
@@ -1092,7 +1139,7 @@ int pft_tracker_seed(pft_tracker* t, uint64_t seed) {
   invalidate_graph(t);
   if (t->st.p) {
     PFT_CUDA_TRY(cudaSetDevice(t->ctx->device));
-    PFT_CUDA_TRY(cudaMemsetAsync(&t->st.as<TrackerState>()->draw_call, 0, sizeof(unsigned long long), t->ctx->stream));
+    PFT_CUDA_TRY(cudaMemsetAsync(&t->st.as<TrackerState>()->draw_call, 0, sizeof(unsigned long long), t->run_stream()));
   }
   return PFT_OK;
 }
@@ -1132,7 +1179,7 @@ int pft_tracker_get_aabb(pft_tracker* t, float* aabb6) {
   if (!t || !aabb6) { set_last_error("null argument"); return PFT_ERR_INVALID; }
   if (!t->idx_hdr.p) { set_last_error("no weight() has run"); return PFT_ERR_STATE; }
   PFT_CUDA_TRY(cudaSetDevice(t->ctx->device));
-  cudaStream_t s = t->ctx->stream;
+  cudaStream_t s = t->run_stream();
   PFT_CUDA_TRY(cudaMemcpyAsync(t->ctx->pinned, t->idx_hdr.p, sizeof(IndexHeader), cudaMemcpyDeviceToHost, s));
   PFT_CUDA_TRY(cudaStreamSynchronize(s));
   memcpy(aabb6, reinterpret_cast<IndexHeader*>(t->ctx->pinned)->aabb, 6 * sizeof(float));
@@ -1143,7 +1190,7 @@ int pft_tracker_get_cropped_count(pft_tracker* t, size_t* n) {
   if (!t || !n) { set_last_error("null argument"); return PFT_ERR_INVALID; }
   if (!t->idx_hdr.p) { set_last_error("no weight() has run"); return PFT_ERR_STATE; }
   PFT_CUDA_TRY(cudaSetDevice(t->ctx->device));
-  cudaStream_t s = t->ctx->stream;
+  cudaStream_t s = t->run_stream();
   PFT_CUDA_TRY(cudaMemcpyAsync(t->ctx->pinned, t->idx_hdr.p, sizeof(IndexHeader), cudaMemcpyDeviceToHost, s));
   PFT_CUDA_TRY(cudaStreamSynchronize(s));
   *n = (size_t)reinterpret_cast<IndexHeader*>(t->ctx->pinned)->n_cropped;
@@ -1154,7 +1201,7 @@ int pft_tracker_get_index_info(pft_tracker* t, int* info8) {
   if (!t || !info8) { set_last_error("null argument"); return PFT_ERR_INVALID; }
   if (!t->idx_hdr.p) { set_last_error("no weight() has run"); return PFT_ERR_STATE; }
   PFT_CUDA_TRY(cudaSetDevice(t->ctx->device));
-  cudaStream_t s = t->ctx->stream;
+  cudaStream_t s = t->run_stream();
   PFT_CUDA_TRY(cudaMemcpyAsync(t->ctx->pinned, t->idx_hdr.p, sizeof(IndexHeader), cudaMemcpyDeviceToHost, s));
   PFT_CUDA_TRY(cudaStreamSynchronize(s));
   const IndexHeader* h = reinterpret_cast<IndexHeader*>(t->ctx->pinned);
@@ -1198,7 +1245,7 @@ int pft_tracker_get_nn(pft_tracker* t, int particle, int32_t* idx, float* d2, si
   if (particle < 0 || particle >= t->debug_nn || !t->dbg_idx.p) { set_last_error("particle %d was not recorded (PFT_DEBUG_NN = %d)", particle, t->debug_nn); return PFT_ERR_STATE; }
   if ((size_t)t->M > capacity) { set_last_error("capacity %zu < %d", capacity, t->M); return PFT_ERR_CAPACITY; }
   PFT_CUDA_TRY(cudaSetDevice(t->ctx->device));
-  PFT_CUDA_TRY(cudaStreamSynchronize(t->ctx->stream));
+  PFT_CUDA_TRY(cudaStreamSynchronize(t->run_stream()));
   PFT_CUDA_TRY(cudaMemcpy(idx, t->dbg_idx.as<int>() + (size_t)particle * t->M, (size_t)t->M * sizeof(int), cudaMemcpyDeviceToHost));
   PFT_CUDA_TRY(cudaMemcpy(d2, t->dbg_d2.as<float>() + (size_t)particle * t->M, (size_t)t->M * sizeof(float), cudaMemcpyDeviceToHost));
   return PFT_OK;
@@ -1214,7 +1261,7 @@ int pft_tracker_get_timing(pft_tracker* t, float* weight_ms, float* compute_ms) 
   if (!t) { set_last_error("null tracker"); return PFT_ERR_INVALID; }
   if (!t->timing || !t->ev_c0) { set_last_error("timing is not enabled or no compute() has run"); return PFT_ERR_STATE; }
   PFT_CUDA_TRY(cudaSetDevice(t->ctx->device));
-  PFT_CUDA_TRY(cudaStreamSynchronize(t->ctx->stream));
+  PFT_CUDA_TRY(cudaStreamSynchronize(t->run_stream()));
   float w = 0.f;
   for (int k = 0; k < t->n_ev_used; ++k) {
     float ms = 0.f;
@@ -1234,7 +1281,7 @@ int pft_tracker_get_kernel_times(pft_tracker* t, const char** names, float* ms, 
   if (!t) { set_last_error("null tracker"); return PFT_ERR_INVALID; }
   if (!t->timing || !t->ev_c0) { set_last_error("timing is not enabled or no compute() has run"); return PFT_ERR_STATE; }
   PFT_CUDA_TRY(cudaSetDevice(t->ctx->device));
-  PFT_CUDA_TRY(cudaStreamSynchronize(t->ctx->stream));
+  PFT_CUDA_TRY(cudaStreamSynchronize(t->run_stream()));
   if (n_out) *n_out = t->n_ev_k;
   if (t->n_ev_k > capacity) { set_last_error("capacity %d < %d", capacity, t->n_ev_k); return PFT_ERR_CAPACITY; }
   for (int k = 0; k < t->n_ev_k; ++k) {
@@ -1272,8 +1319,8 @@ int pft_tracker_get_crop_box(pft_tracker* t, float* aabb6) {
 int pft_tracker_set_crop_box(pft_tracker* t, const float* aabb6) {
   if (!t || !aabb6 || !t->st.p) { set_last_error("null argument / no state"); return PFT_ERR_INVALID; }
   PFT_CUDA_TRY(cudaSetDevice(t->ctx->device));
-  PFT_CUDA_TRY(cudaMemcpyAsync(t->st.as<TrackerState>()->aabb, aabb6, 6 * sizeof(float), cudaMemcpyHostToDevice, t->ctx->stream));
-  PFT_CUDA_TRY(cudaStreamSynchronize(t->ctx->stream));
+  PFT_CUDA_TRY(cudaMemcpyAsync(t->st.as<TrackerState>()->aabb, aabb6, 6 * sizeof(float), cudaMemcpyHostToDevice, t->run_stream()));
+  PFT_CUDA_TRY(cudaStreamSynchronize(t->run_stream()));
   return PFT_OK;
 }
 int pft_tracker_get_raw_slice(pft_tracker* t, int rank, float* out, size_t capacity, size_t* n_out) {
@@ -1283,7 +1330,7 @@ int pft_tracker_get_raw_slice(pft_tracker* t, int rank, float* out, size_t capac
   if (n_out) *n_out = n;
   if (n > capacity || !out) { set_last_error("capacity %zu < %zu", capacity, n); return PFT_ERR_CAPACITY; }
   PFT_CUDA_TRY(cudaSetDevice(t->ctx->device));
-  PFT_CUDA_TRY(cudaStreamSynchronize(t->ctx->stream));
+  PFT_CUDA_TRY(cudaStreamSynchronize(t->run_stream()));
   PFT_CUDA_TRY(cudaMemcpy(out, t->raw.as<float>() + (size_t)rank * n, n * sizeof(float), cudaMemcpyDeviceToHost));
   return PFT_OK;
 }
@@ -1291,8 +1338,8 @@ int pft_tracker_set_raw_slice(pft_tracker* t, int rank, const float* in, size_t 
   if (!t || !in || !t->raw.p) { set_last_error("null argument / no state"); return PFT_ERR_INVALID; }
   if (rank < 0 || rank >= t->nranks || n != (size_t)t->slice_cap()) { set_last_error("bad rank or slice length"); return PFT_ERR_INVALID; }
   PFT_CUDA_TRY(cudaSetDevice(t->ctx->device));
-  PFT_CUDA_TRY(cudaMemcpyAsync(t->raw.as<float>() + (size_t)rank * n, in, n * sizeof(float), cudaMemcpyHostToDevice, t->ctx->stream));
-  PFT_CUDA_TRY(cudaStreamSynchronize(t->ctx->stream));
+  PFT_CUDA_TRY(cudaMemcpyAsync(t->raw.as<float>() + (size_t)rank * n, in, n * sizeof(float), cudaMemcpyHostToDevice, t->run_stream()));
+  PFT_CUDA_TRY(cudaStreamSynchronize(t->run_stream()));
   return PFT_OK;
 }
 
@@ -1449,7 +1496,7 @@ int pft_tracker_peer_detach(pft_tracker* t) {
   if (!t) { set_last_error("null tracker"); return PFT_ERR_INVALID; }
   if (!t->peer_local && !t->peer_mode) return PFT_OK;
   cudaSetDevice(t->ctx->device);
-  cudaStreamSynchronize(t->ctx->stream);
+  cudaStreamSynchronize(t->run_stream());
   if (t->peer_mode) {
     for (int r = 0; r < t->peers.nranks; ++r) if (r != t->peers.rank && t->peers.win[r]) cudaIpcCloseMemHandle(t->peers.win[r]);
   }

@@ -32,6 +32,7 @@ struct TrackerState {
   unsigned int peer_epoch;       // weight() calls so far in peer (NVLink P2P) exchange mode
   unsigned int peer_blocks_done; // raw_weights_kernel blocks that have pushed their slice this epoch
   unsigned int peer_error;       // a wait on a peer's flag timed out (sticky)
+  unsigned long long evals;      // likelihood evaluations so far: sum over weight() calls of particles x model points (whole job)
 };
 
 // ------------------------------------------------------------------ NVLink peer exchange (one process per GPU)
@@ -1394,7 +1395,7 @@ __global__ void raw_weights_kernel(TrackerState* st, const double* __restrict__ 
 // ------------------------------------------------------------------ K4a: normalizeWeight (one block)
 __global__ void __launch_bounds__(1024) normalize_kernel(TrackerState* st, DevParticle* parts, const float* raw, double alpha,
                                                          int nranks, int slice_cap, const CloudHeader* __restrict__ scene_hdr,
-                                                         PeerWindow* peer_window /* non-null: wait for the peers' raw weights */) {
+                                                         PeerWindow* peer_window /* non-null: wait for the peers' raw weights */, int M) {
   __shared__ double red[32];
   __shared__ double s_min, s_max, s_sum;
   if (peer_window) {
@@ -1404,6 +1405,7 @@ __global__ void __launch_bounds__(1024) normalize_kernel(TrackerState* st, DevPa
   }
   if (scene_hdr->n <= 0) return;  // Tracker::initCompute fails on an empty input cloud: compute() is a no-op
   const int n = st->particle_num;
+  if (threadIdx.x == 0) st->evals += (unsigned long long)n * (unsigned long long)M;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   double wmin = DBL_MAX, wmax = -DBL_MAX;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {

@@ -528,6 +528,11 @@ class ParticleFilterOMPTracker:
         check(capi.load().pft_tracker_get_kernel_times(self._h, names, ms, cap, C.byref(n)))
         return [(names[i].decode(), float(ms[i])) for i in range(n.value)]
 
+    def evalCount(self):
+        n = C.c_uint64()
+        check(capi.load().pft_tracker_get_eval_count(self._h, C.byref(n)))
+        return n.value
+
     def graphReplays(self):
         n = C.c_uint64()
         check(capi.load().pft_tracker_graph_replays(self._h, C.byref(n)))
