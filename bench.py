@@ -15,7 +15,7 @@ Workloads (config.workload):
        ncclAllReduce / ncclAllGather (--exchange nccl, with rank 0 downsampling and broadcasting the
        scene); resample/normalise/update run replicated.
   c4   BASELINE.json configs[3]: 100 000 particles in total, sharded over the N GPUs (strong scaling).
-  c3   BASELINE.json configs[2]: KLD-adaptive tracker, at most 10 000 particles (epsilon 0.02, bins 2 cm / 0.02 rad),
+  c3   BASELINE.json configs[2]: KLD-adaptive tracker, at most 10 000 particles (epsilon 0.2, bins 0.1 m / rad as the reference),
        per-frame downsample + index rebuild; the particle count lives on the device, evals are counted there.
   c5   BASELINE.json configs[4]: 8 objects (8 models, 1000 particles each) tracked in one 217k-pt scene through
        pft_compute_batch (every tracker on its own stream, forked from / joined to the scene's stream).
@@ -239,8 +239,8 @@ def workload_config(args, M, n_particles):
         "c2": "c2: BASELINE.json configs[1], 512x424 (217088-pt) Kinect2-shaped synthetic scene, %d-pt model, %d particles"
               " per GPU (one tracker sharded by particle), Distance+HSV coherence, 2 iterations/frame" % (M, PARTICLES_PER_GPU),
         "c4": "c4: BASELINE.json configs[3], 100000 particles sharded over the GPUs, 217088-pt scene, %d-pt model, Distance+HSV" % M,
-        "c3": "c3: BASELINE.json configs[2], KLD-adaptive particle count (<= %d, epsilon 0.02, bins 2 cm / 0.02 rad), 217088-pt scene, %d-pt model,"
-              " per-frame voxel-grid downsample + index rebuild, Distance+HSV" % (C3_MAX_PARTICLES, M),
+        "c3": "c3: BASELINE.json configs[2], KLD-adaptive particle count (<= %d, epsilon %g, bins %g m / rad), 217088-pt scene, %d-pt model,"
+              " per-frame voxel-grid downsample + index rebuild, Distance+HSV" % (C3_MAX_PARTICLES, args.kld_epsilon, args.kld_bin, M),
         "c5": "c5: BASELINE.json configs[4], %d objects (%d model points in total, %d particles each) tracked simultaneously in one 217088-pt scene"
               " (pft_compute_batch), Distance+HSV" % (C5_OBJECTS, M, PARTICLES_PER_GPU),
     }
@@ -260,6 +260,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"])
+    ap.add_argument("--kld-epsilon", type=float, default=0.2, help="c3: setEpsilon (the reference uses 0.2: a few hundred particles)")
+    ap.add_argument("--kld-bin", type=float, default=0.1, help="c3: setBinSize (m and rad; the reference uses 0.1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true", help="debug only: do not flush L2 between steps")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
@@ -318,8 +320,8 @@ def main():
         if args.workload == "c3":
             tracker = pcl.KLDAdaptiveParticleFilterOMPTracker(16, ctx=ctx)
             pcl.configure_like_reference(tracker, particle_num=n_particles, max_particle_num=n_particles, use_hsv=True, iteration_num=ITERATIONS)
-            tracker.setEpsilon(0.02)
-            tracker.setBinSize([0.02] * 6)
+            tracker.setEpsilon(args.kld_epsilon)
+            tracker.setBinSize([args.kld_bin] * 6)
         else:
             tracker = pcl.ParticleFilterOMPTracker(16, ctx=ctx)
             pcl.configure_like_reference(tracker, particle_num=n_particles, use_hsv=True, iteration_num=ITERATIONS)

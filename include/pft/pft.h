@@ -73,6 +73,13 @@ PFT_API int pft_cloud_create(pft_context* ctx, pft_cloud** out);
 PFT_API void pft_cloud_destroy(pft_cloud* cloud);
 /* replaces pcl::fromPCLPointCloud2 / cloud assignment (ref: src/auto_tracking.cpp:619-622) */
 PFT_API int pft_cloud_upload(pft_cloud* cloud, const void* host_points, size_t n, int layout);
+/* frame ingest: a sensor_msgs/PointCloud2 payload as it arrives from the camera driver -> device cloud.  Replaces
+ * pcl_conversions::toPCL + pcl::fromPCLPointCloud2 (ref: src/auto_tracking.cpp:619-622): `data` holds `height` rows of
+ * `row_step` bytes with `width` records of `point_step` bytes each; off_* are the byte offsets of the float32 fields
+ * x, y, z and of the packed rgb/rgba word inside a record (off_rgb < 0: no colour, rgba = 0).  Point order is
+ * row-major, NaN points are kept (the PassThrough that follows drops them, ref :637). */
+PFT_API int pft_cloud_upload_pointcloud2(pft_cloud* cloud, const void* data, uint32_t width, uint32_t height, uint32_t point_step,
+                                         uint32_t row_step, int32_t off_x, int32_t off_y, int32_t off_z, int32_t off_rgb, int is_bigendian);
 PFT_API int pft_cloud_size(pft_cloud* cloud, size_t* n);
 PFT_API int pft_cloud_download(pft_cloud* cloud, void* host_points, size_t capacity, int layout, size_t* n);
 
@@ -155,6 +162,22 @@ PFT_API int pft_tracker_get_result(pft_tracker* t, pft_particle* out);
 PFT_API int pft_tracker_get_particles(pft_tracker* t, pft_particle* out, size_t capacity, size_t* n);
 /* ParticleXYZRPY::toEigenMatrix (ref :310): row-major 3x4, computed by the same device routine as weight() */
 PFT_API int pft_particle_to_matrix(pft_context* ctx, const pft_particle* p, float* m12);
+/* Result post-processing, what viz_cb derives from getResult() per object (ref: src/auto_tracking.cpp:309-316,
+ * :432-466, :481-515): the reference cloud moved to the result pose (translation.z + z_offset; the reference passes
+ * -0.005), its compute3DCentroid (the position published on /visual/cam_frame_obj_pos_vector), the eigenvectors of
+ * its normalised covariance (ascending eigenvalues, third axis = first x second; the sign of an eigenvector is
+ * unspecified in Eigen, here the largest component of the first two axes is positive) and the oriented bounding box
+ * in that frame: edge lengths, centre (tfinal) and orientation quaternion (qfinal: w, x, y, z). */
+typedef struct {
+  float centroid[3];
+  float axes[9];      /* row-major 3x3, columns = box axes */
+  float extent[3];
+  float center[3];
+  float quat[4];
+  float eigenvalues[3];
+  int32_t n;          /* model points */
+} pft_result_box;
+PFT_API int pft_tracker_get_result_box(pft_tracker* t, float z_offset, pft_result_box* out);
 /* resetTracking */
 PFT_API int pft_tracker_reset(pft_tracker* t);
 /* likelihood evaluations so far (sum over weight() calls of live particles x model points; counted on the device,

@@ -160,6 +160,21 @@ def voxel_grid_exact(pts, leaf, field=2, lo=0.0, hi=10.0):
     return out[:n].copy()
 
 
+def from_pointcloud2(data, width, height, point_step, row_step=None, off_x=0, off_y=4, off_z=8, off_rgb=16):
+    """pcl::fromPCLPointCloud2 for PointXYZRGBA (PCL-1.8.0 common/include/pcl/conversions.h: one memcpy per mapped field
+    and point, rows of row_step bytes, records of point_step bytes; call site ref: src/auto_tracking.cpp:619-622), restated
+    with numpy byte views.  Returns the packed {x,y,z,rgba} points in row-major order; NaNs are kept."""
+    row_step = width * point_step if row_step is None else row_step
+    raw = np.frombuffer(bytes(data), dtype=np.uint8)[:row_step * height].reshape(height, row_step)
+    rec = raw[:, :width * point_step].reshape(height * width, point_step)
+    out = np.zeros(height * width, dtype=POINT)
+    for name, off in (("x", off_x), ("y", off_y), ("z", off_z)):
+        out[name] = np.ascontiguousarray(rec[:, off:off + 4]).view("<f4")[:, 0]
+    if off_rgb >= 0:
+        out["rgba"] = np.ascontiguousarray(rec[:, off_rgb:off_rgb + 4]).view("<u4")[:, 0]
+    return out
+
+
 def remove_zero_points(pts):
     pts = as_points(pts)
     out = np.empty_like(pts)
@@ -204,6 +219,41 @@ def matrix_to_particle(m34):
     p = np.zeros(1, dtype=PARTICLE)
     lib().orc_matrix_to_particle(_p(m), _p(p))
     return p[0]
+
+
+def result_box(model_pts, state6, z_offset=-0.005):
+    """Post-processing of getResult() in viz_cb (ref: src/auto_tracking.cpp:309-316, :432-466), restated with numpy:
+    transformPointCloud(reference, toEigenMatrix(result) with translation.z += z_offset) -> compute3DCentroid ->
+    computeCovarianceMatrixNormalized -> SelfAdjointEigenSolver (ascending eigenvalues; eigDx.col(2) = col(0) x col(1)) ->
+    transformPointCloud into the eigenframe -> getMinMax3D -> box edge lengths, centre (tfinal) and axes.
+    Eigen leaves the sign of an eigenvector unspecified: the largest component of the first two axes is made positive
+    (extents and the box centre do not depend on that choice)."""
+    f = np.float32
+    pts = as_points(model_pts)
+    m = particle_to_matrix(state6).astype(f)
+    m[2, 3] = f(m[2, 3] + f(z_offset))
+    x, y, z = pts["x"].astype(f), pts["y"].astype(f), pts["z"].astype(f)
+    p = np.stack([((m[r, 0] * x + m[r, 1] * y) + m[r, 2] * z) + m[r, 3] for r in range(3)], axis=1).astype(f)
+    n = len(p)
+    c = (p.astype(np.float64).sum(0) / n).astype(f)
+    d = (p - c).astype(f)
+    cov = np.zeros((3, 3))
+    for i in range(3):
+        for j in range(3):
+            cov[i, j] = (d[:, i] * d[:, j]).astype(f).astype(np.float64).sum() / n
+    cov = cov.astype(f).astype(np.float64)
+    w, v = np.linalg.eigh(cov)
+    for col in range(2):
+        k = int(np.argmax(np.abs(v[:, col])))
+        if v[k, col] < 0:
+            v[:, col] = -v[:, col]
+    e = v.astype(f)
+    e[:, 2] = np.cross(e[:, 0], e[:, 1]).astype(f)
+    t = -(e.T @ c).astype(f)
+    cp = (p @ e + t).astype(f)
+    mn, mx = cp.min(0), cp.max(0)
+    md = (f(0.5) * (mx + mn)).astype(f)
+    return {"centroid": c, "axes": e, "extent": (mx - mn).astype(f), "center": (e @ md + c).astype(f), "eigenvalues": w.astype(f), "n": n}
 
 
 def distance_coherence(a, b, w=1.0):

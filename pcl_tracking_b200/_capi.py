@@ -17,6 +17,9 @@ POINT_PCL32 = np.dtype([("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("w", "<f4"), 
 PARTICLE = np.dtype([("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("one", "<f4"),
                      ("roll", "<f4"), ("pitch", "<f4"), ("yaw", "<f4"), ("weight", "<f4")])
 
+RESULT_BOX = np.dtype([("centroid", "<f4", (3,)), ("axes", "<f4", (3, 3)), ("extent", "<f4", (3,)), ("center", "<f4", (3,)),
+                       ("quat", "<f4", (4,)), ("eigenvalues", "<f4", (3,)), ("n", "<i4")])
+
 LAYOUT_PACKED16, LAYOUT_PCL32 = 0, 1
 OK, ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_CAPACITY, ERR_COMM = 0, -1, -2, -3, -4, -5
 
@@ -55,6 +58,7 @@ SIGNATURES = {
     "pft_cloud_create": (_i, [_vp, _pp]),
     "pft_cloud_destroy": (None, [_vp]),
     "pft_cloud_upload": (_i, [_vp, _vp, _sz, _i]),
+    "pft_cloud_upload_pointcloud2": (_i, [_vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _i]),
     "pft_cloud_size": (_i, [_vp, _psz]),
     "pft_cloud_download": (_i, [_vp, _vp, _sz, _i, _psz]),
     "pft_passthrough": (_i, [_vp, _vp, _vp, _i, _f, _f]),
@@ -74,6 +78,7 @@ SIGNATURES = {
     "pft_tracker_get_result": (_i, [_vp, _vp]),
     "pft_tracker_get_particles": (_i, [_vp, _vp, _sz, _psz]),
     "pft_particle_to_matrix": (_i, [_vp, _vp, _vp]),
+    "pft_tracker_get_result_box": (_i, [_vp, _f, _vp]),
     "pft_tracker_reset": (_i, [_vp]),
     "pft_tracker_get_eval_count": (_i, [_vp, C.POINTER(C.c_uint64)]),
     "pft_tracker_get_fit_ratio": (_i, [_vp, C.POINTER(C.c_double)]),

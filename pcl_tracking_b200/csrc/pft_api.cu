@@ -175,6 +175,43 @@ int pft_cloud_upload(pft_cloud* c, const void* host_points, size_t n, int layout
   return PFT_OK;
 }
 
+int pft_cloud_upload_pointcloud2(pft_cloud* c, const void* data, uint32_t width, uint32_t height, uint32_t point_step, uint32_t row_step,
+                                 int32_t off_x, int32_t off_y, int32_t off_z, int32_t off_rgb, int is_bigendian) {
+  if (!c) { set_last_error("pft_cloud_upload_pointcloud2: null cloud"); return PFT_ERR_INVALID; }
+  const size_t n = (size_t)width * height;
+  if (n && !data) { set_last_error("pft_cloud_upload_pointcloud2: null data"); return PFT_ERR_INVALID; }
+  if (n > 0x7fffffffull) { set_last_error("cloud too large"); return PFT_ERR_INVALID; }
+  if (is_bigendian) { set_last_error("big-endian PointCloud2 data is not supported"); return PFT_ERR_INVALID; }
+  if (n) {
+    if (point_step < 12 || (point_step & 3) || (row_step & 3) || (size_t)row_step < (size_t)width * point_step) {
+      set_last_error("bad PointCloud2 strides: point_step %u, row_step %u, width %u (4-byte multiples, row_step >= width * point_step)", point_step, row_step, width);
+      return PFT_ERR_INVALID;
+    }
+    const int32_t offs[4] = {off_x, off_y, off_z, off_rgb};
+    for (int k = 0; k < 4; ++k) {
+      const bool optional = k == 3 && offs[k] < 0;  // no colour field: rgba = 0
+      if (!optional && (offs[k] < 0 || (offs[k] & 3) || (uint32_t)offs[k] + 4 > point_step)) {
+        set_last_error("bad PointCloud2 field offset %d (float32 x, y, z and the packed rgb(a) word, 4-byte aligned inside point_step %u)", offs[k], point_step);
+        return PFT_ERR_INVALID;
+      }
+    }
+  }
+  pft_context* ctx = c->ctx;
+  PFT_CUDA_TRY(cudaSetDevice(ctx->device));
+  int rc = c->ensure(n);
+  if (rc) return rc;
+  cudaStream_t s = ctx->stream;
+  if (n) {
+    const size_t bytes = (size_t)row_step * height;
+    if ((rc = ctx->staging.reserve(bytes))) return rc;
+    PFT_CUDA_TRY(cudaMemcpyAsync(ctx->staging.p, data, bytes, cudaMemcpyHostToDevice, s));
+    if ((rc = launch_unpack_pointcloud2(s, ctx->staging.p, c->d_pts(), width, height, point_step, row_step, off_x, off_y, off_z, off_rgb))) return rc;
+  }
+  if ((rc = launch_set_header(s, c->d_hdr(), (int)n))) return rc;
+  c->host_n = (long long)n;
+  return PFT_OK;
+}
+
 int pft_cloud_size(pft_cloud* c, size_t* n) {
   if (!c || !n) { set_last_error("pft_cloud_size: null argument"); return PFT_ERR_INVALID; }
   if (c->host_n < 0) {

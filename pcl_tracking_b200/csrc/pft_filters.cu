@@ -54,6 +54,21 @@ __global__ void pack_pcl32_kernel(const float4* __restrict__ src, uint4* __restr
     dst[2 * i + 1] = make_uint4(__float_as_uint(p.w), 0u, 0u, 0u);
   }
 }
+// sensor_msgs/PointCloud2 -> float4 {x,y,z,rgba}: replaces pcl_conversions::toPCL + pcl::fromPCLPointCloud2
+// (ref: src/auto_tracking.cpp:619-622).  Rows of `row_step` bytes hold `width` records of `point_step` bytes; the
+// float32 fields x, y, z and the 4 colour bytes sit at arbitrary (4-byte aligned) offsets inside a record.  Organised
+// clouds keep their row-major order, as fromPCLPointCloud2 does.  A warp reads whole 4-byte words of consecutive
+// records, so the loads of a row are as coalesced as the record stride allows.
+__global__ void unpack_pointcloud2_kernel(const unsigned int* __restrict__ src, float4* __restrict__ dst, unsigned int width, unsigned int height,
+                                          unsigned int point_words, unsigned int row_words, int wx, int wy, int wz, int wrgb) {
+  const size_t n = (size_t)width * height;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t row = i / width, col = i - row * width;
+    const unsigned int* rec = src + row * row_words + col * point_words;
+    const unsigned int rgba = wrgb >= 0 ? rec[wrgb] : 0u;
+    dst[i] = make_float4(__uint_as_float(rec[wx]), __uint_as_float(rec[wy]), __uint_as_float(rec[wz]), __uint_as_float(rgba));
+  }
+}
 __global__ void set_header_kernel(CloudHeader* h, int n) { h->n = n; }
 
 // ---- PassThrough (order-preserving compaction), one thread block: flags -> exclusive scan -> scatter.
@@ -224,6 +239,15 @@ inline int grid_for(size_t n, int block, int sm_count) {
 int launch_unpack_pcl32(cudaStream_t s, const void* src32, float4* dst, size_t n) {
   if (n == 0) return PFT_OK;
   unpack_pcl32_kernel<<<grid_for(n, 256, 148), 256, 0, s>>>(reinterpret_cast<const uint4*>(src32), dst, n);
+  PFT_LAUNCH_CHECK();
+  return PFT_OK;
+}
+int launch_unpack_pointcloud2(cudaStream_t s, const void* src, float4* dst, unsigned int width, unsigned int height, unsigned int point_step,
+                              unsigned int row_step, int off_x, int off_y, int off_z, int off_rgb) {
+  const size_t n = (size_t)width * height;
+  if (n == 0) return PFT_OK;
+  unpack_pointcloud2_kernel<<<grid_for(n, 256, 148), 256, 0, s>>>(reinterpret_cast<const unsigned int*>(src), dst, width, height, point_step / 4, row_step / 4,
+                                                                 off_x / 4, off_y / 4, off_z / 4, off_rgb >= 0 ? off_rgb / 4 : -1);
   PFT_LAUNCH_CHECK();
   return PFT_OK;
 }

@@ -51,6 +51,8 @@ namespace pft {
 // ---- filters (pft_filters.cu)
 int launch_unpack_pcl32(cudaStream_t s, const void* src32, float4* dst, size_t n);
 int launch_pack_pcl32(cudaStream_t s, const float4* src, void* dst32, size_t n);
+int launch_unpack_pointcloud2(cudaStream_t s, const void* src, float4* dst, unsigned int width, unsigned int height, unsigned int point_step,
+                              unsigned int row_step, int off_x, int off_y, int off_z, int off_rgb);
 int launch_set_header(cudaStream_t s, CloudHeader* hdr, int n);
 int run_passthrough(pft_context* ctx, const pft_cloud* in, pft_cloud* out, int field, float lo, float hi, int drop_zero);
 int run_voxel_grid(pft_context* ctx, const pft_cloud* in, pft_cloud* out, float leaf, int field, float lo, float hi);

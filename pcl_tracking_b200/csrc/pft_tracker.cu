@@ -154,7 +154,7 @@ struct pft_tracker {
   int graph_nodes = 0;
   // device buffers
   DevBuf st, parts[2], mats, slot_aabb, model, model_perm, model_tmp, sort_keys, sort_idx, bbox, raw, partial, cdf, cdf_total, ancestors, bin_keys, tbl_rep,
-      tbl_min, slot_of, klb, d_usel, d_normals, d_umot, idx_hdr, cell_start, ipts, ihsv, icount, dbg_idx, dbg_d2, d_trans, row_table, flists, fneeded, fneeded_list, ffar_list, xlists, xcount;
+      tbl_min, slot_of, klb, d_usel, d_normals, d_umot, idx_hdr, cell_start, ipts, ihsv, icount, dbg_idx, dbg_d2, d_trans, row_table, flists, fneeded, fneeded_list, ffar_list, xlists, xcount, result_box;
   int weight_smem = 0;  // dynamic shared memory of the weight kernel (bytes)
   int tbl_size = 0;
   int n_slots = 0;
@@ -190,7 +190,7 @@ void release_all(pft_tracker* t) {
   DevBuf* bufs[] = {&t->st, &t->parts[0], &t->parts[1], &t->mats, &t->slot_aabb, &t->model, &t->model_perm, &t->model_tmp, &t->sort_keys, &t->sort_idx,
                     &t->bbox, &t->raw, &t->partial, &t->cdf, &t->cdf_total, &t->ancestors, &t->bin_keys, &t->tbl_rep, &t->tbl_min, &t->slot_of, &t->klb,
                     &t->d_usel, &t->d_normals, &t->d_umot, &t->idx_hdr, &t->cell_start, &t->ipts, &t->ihsv, &t->icount, &t->dbg_idx,
-                    &t->dbg_d2, &t->d_trans, &t->row_table, &t->flists, &t->fneeded, &t->fneeded_list, &t->ffar_list, &t->xlists, &t->xcount};
+                    &t->dbg_d2, &t->d_trans, &t->row_table, &t->flists, &t->fneeded, &t->fneeded_list, &t->ffar_list, &t->xlists, &t->xcount, &t->result_box};
   for (auto* b : bufs) b->release();
 }
 
@@ -1056,6 +1056,22 @@ int pft_particle_to_matrix(pft_context* ctx, const pft_particle* p, float* m12) 
   PFT_CUDA_TRY(cudaMemcpyAsync(ctx->pinned, ctx->tmp_f.as<float>() + 4, 12 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
   PFT_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   memcpy(m12, ctx->pinned, 12 * sizeof(float));
+  return PFT_OK;
+}
+
+int pft_tracker_get_result_box(pft_tracker* t, float z_offset, pft_result_box* out) {
+  if (!t || !out) { set_last_error("null argument"); return PFT_ERR_INVALID; }
+  static_assert(sizeof(pft_result_box) == sizeof(ResultBox), "pft_result_box layout");
+  if (!t->st.p || t->M <= 0) { set_last_error("no result yet: setReferenceCloud and compute() first"); return PFT_ERR_STATE; }
+  PFT_CUDA_TRY(cudaSetDevice(t->ctx->device));
+  cudaStream_t s = t->run_stream();
+  int rc = t->result_box.reserve(sizeof(ResultBox));
+  if (rc) return rc;
+  result_box_kernel<<<1, 1024, 0, s>>>(t->st.as<TrackerState>(), t->model.as<float4>(), t->M, z_offset, t->result_box.as<ResultBox>());
+  PFT_LAUNCH_CHECK();
+  PFT_CUDA_TRY(cudaMemcpyAsync(t->ctx->pinned, t->result_box.p, sizeof(ResultBox), cudaMemcpyDeviceToHost, s));
+  PFT_CUDA_TRY(cudaStreamSynchronize(s));
+  memcpy(out, t->ctx->pinned, sizeof(ResultBox));
   return PFT_OK;
 }
 

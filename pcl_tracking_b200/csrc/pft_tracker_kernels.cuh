@@ -1704,4 +1704,135 @@ __global__ void model_gather_kernel(const float4* __restrict__ in, const int* __
 
 __global__ void single_matrix_kernel(DevParticle p, float* m12) { particle_to_matrix(p.x, p.y, p.z, p.roll, p.pitch, p.yaw, m12); }
 
+// ------------------------------------------------------------------ result post-processing
+// What viz_cb derives from getResult() for every object (ref: src/auto_tracking.cpp:309-316, :432-466): the model
+// moved to the result pose (+ the viewer's z offset), its centroid (compute3DCentroid: the position that is published
+// on /visual/cam_frame_obj_pos_vector, ref :481-515), the normalised covariance, its eigenvectors (ascending
+// eigenvalues; third axis = first x second as in the reference) and the oriented bounding box in that frame.
+// Sums are accumulated in fp64 from fp32 terms (order independent); Eigen's SelfAdjointEigenSolver leaves the sign
+// of an eigenvector unspecified, here the largest component of the first two axes is made positive.
+struct ResultBox {
+  float centroid[3];
+  float axes[9];        // row-major 3x3, columns = box axes (eigDx)
+  float extent[3];      // max_pt - min_pt in the box frame
+  float center[3];      // tfinal = eigDx * 0.5 (max_pt + min_pt) + centroid
+  float quat[4];        // qfinal = Quaternionf(eigDx): w, x, y, z
+  float eigenvalues[3];
+  int n;
+};
+
+__device__ inline void jacobi_eigen3(double A[3][3], double V[3][3], double w[3]) {
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) V[i][j] = i == j ? 1.0 : 0.0;
+  for (int sweep = 0; sweep < 32; ++sweep) {
+    const double off = fabs(A[0][1]) + fabs(A[0][2]) + fabs(A[1][2]);
+    if (off <= 1.0e-300 || off <= 1.0e-18 * (fabs(A[0][0]) + fabs(A[1][1]) + fabs(A[2][2]))) break;
+    for (int p = 0; p < 2; ++p) for (int q = p + 1; q < 3; ++q) {
+      if (fabs(A[p][q]) <= 1.0e-300) continue;
+      const double theta = (A[q][q] - A[p][p]) / (2.0 * A[p][q]);
+      const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+      const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+      for (int k = 0; k < 3; ++k) { const double akp = A[k][p], akq = A[k][q]; A[k][p] = c * akp - sn * akq; A[k][q] = sn * akp + c * akq; }
+      for (int k = 0; k < 3; ++k) { const double apk = A[p][k], aqk = A[q][k]; A[p][k] = c * apk - sn * aqk; A[q][k] = sn * apk + c * aqk; }
+      for (int k = 0; k < 3; ++k) { const double vkp = V[k][p], vkq = V[k][q]; V[k][p] = c * vkp - sn * vkq; V[k][q] = sn * vkp + c * vkq; }
+    }
+  }
+  for (int i = 0; i < 3; ++i) w[i] = A[i][i];
+  // ascending eigenvalues (selection sort of three)
+  for (int i = 0; i < 2; ++i) for (int j = i + 1; j < 3; ++j) if (w[j] < w[i]) {
+    const double tw = w[i]; w[i] = w[j]; w[j] = tw;
+    for (int k = 0; k < 3; ++k) { const double tv = V[k][i]; V[k][i] = V[k][j]; V[k][j] = tv; }
+  }
+}
+
+__global__ void __launch_bounds__(1024) result_box_kernel(const TrackerState* __restrict__ st, const float4* __restrict__ model, int M, float z_offset,
+                                                          ResultBox* __restrict__ out) {
+  __shared__ double red[32];
+  __shared__ double s_sum[9];
+  __shared__ float s_c[3], s_E[9], s_t[3];
+  __shared__ float s_mn[32][3], s_mx[32][3];
+  float m[12];
+  const DevParticle rep = st->rep;
+  particle_to_matrix(rep.x, rep.y, rep.z, rep.roll, rep.pitch, rep.yaw, m);
+  m[11] += z_offset;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  // ---- centroid
+  double sx = 0.0, sy = 0.0, sz = 0.0;
+  for (int j = threadIdx.x; j < M; j += blockDim.x) {
+    const float4 p = model[j];
+    float x, y, z;
+    xform(m, p.x, p.y, p.z, x, y, z);
+    sx += (double)x; sy += (double)y; sz += (double)z;
+  }
+  sx = block_sum(sx, red); if (threadIdx.x == 0) s_sum[0] = sx;
+  sy = block_sum(sy, red); if (threadIdx.x == 0) s_sum[1] = sy;
+  sz = block_sum(sz, red); if (threadIdx.x == 0) s_sum[2] = sz;
+  __syncthreads();
+  if (threadIdx.x < 3) s_c[threadIdx.x] = M > 0 ? (float)(s_sum[threadIdx.x] / (double)M) : 0.f;
+  __syncthreads();
+  const float cx = s_c[0], cy = s_c[1], cz = s_c[2];
+  // ---- normalised covariance about the fp32 centroid (computeCovarianceMatrixNormalized)
+  double c6[6] = {0, 0, 0, 0, 0, 0};
+  for (int j = threadIdx.x; j < M; j += blockDim.x) {
+    const float4 p = model[j];
+    float x, y, z;
+    xform(m, p.x, p.y, p.z, x, y, z);
+    const float dx = x - cx, dy = y - cy, dz = z - cz;
+    c6[0] += (double)(dx * dx); c6[1] += (double)(dx * dy); c6[2] += (double)(dx * dz);
+    c6[3] += (double)(dy * dy); c6[4] += (double)(dy * dz); c6[5] += (double)(dz * dz);
+  }
+  for (int k = 0; k < 6; ++k) { const double v = block_sum(c6[k], red); if (threadIdx.x == 0) s_sum[k] = v; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const double inv = M > 0 ? 1.0 / (double)M : 0.0;
+    // the reference decomposes the fp32 matrix
+    double A[3][3], V[3][3], w[3];
+    A[0][0] = (double)(float)(s_sum[0] * inv); A[0][1] = A[1][0] = (double)(float)(s_sum[1] * inv); A[0][2] = A[2][0] = (double)(float)(s_sum[2] * inv);
+    A[1][1] = (double)(float)(s_sum[3] * inv); A[1][2] = A[2][1] = (double)(float)(s_sum[4] * inv); A[2][2] = (double)(float)(s_sum[5] * inv);
+    jacobi_eigen3(A, V, w);
+    for (int col = 0; col < 2; ++col) {  // sign convention: the largest component of an axis is positive
+      int big = 0;
+      for (int k = 1; k < 3; ++k) if (fabs(V[k][col]) > fabs(V[big][col])) big = k;
+      if (V[big][col] < 0.0) for (int k = 0; k < 3; ++k) V[k][col] = -V[k][col];
+    }
+    float E[9];
+    for (int r = 0; r < 3; ++r) for (int col = 0; col < 2; ++col) E[3 * r + col] = (float)V[r][col];
+    // eigDx.col(2) = eigDx.col(0).cross(eigDx.col(1))
+    E[2] = E[3] * E[7] - E[6] * E[4];
+    E[5] = E[6] * E[1] - E[0] * E[7];
+    E[8] = E[0] * E[4] - E[3] * E[1];
+    for (int k = 0; k < 9; ++k) { s_E[k] = E[k]; out->axes[k] = E[k]; }
+    for (int k = 0; k < 3; ++k) out->eigenvalues[k] = (float)w[k];
+    // p2w: rotation = eigDx^T, translation = -(eigDx^T * centroid)
+    for (int r = 0; r < 3; ++r) s_t[r] = -1.f * ((E[r] * cx + E[3 + r] * cy) + E[6 + r] * cz);
+  }
+  __syncthreads();
+  // ---- extents in the box frame (transformPointCloud with p2w + getMinMax3D)
+  float p2w[12];
+  for (int r = 0; r < 3; ++r) { p2w[4 * r] = s_E[r]; p2w[4 * r + 1] = s_E[3 + r]; p2w[4 * r + 2] = s_E[6 + r]; p2w[4 * r + 3] = s_t[r]; }
+  float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  for (int j = threadIdx.x; j < M; j += blockDim.x) {
+    const float4 p = model[j];
+    float x, y, z, u, v, w;
+    xform(m, p.x, p.y, p.z, x, y, z);
+    xform(p2w, x, y, z, u, v, w);
+    mn[0] = fminf(mn[0], u); mn[1] = fminf(mn[1], v); mn[2] = fminf(mn[2], w);
+    mx[0] = fmaxf(mx[0], u); mx[1] = fmaxf(mx[1], v); mx[2] = fmaxf(mx[2], w);
+  }
+  for (int d = 0; d < 3; ++d) { mn[d] = warp_min(mn[d]); mx[d] = warp_max(mx[d]); }
+  if (lane == 0) for (int d = 0; d < 3; ++d) { s_mn[wid][d] = mn[d]; s_mx[wid][d] = mx[d]; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < nw; ++w) for (int d = 0; d < 3; ++d) { mn[d] = fminf(mn[d], s_mn[w][d]); mx[d] = fmaxf(mx[d], s_mx[w][d]); }
+    if (M <= 0) for (int d = 0; d < 3; ++d) { mn[d] = 0.f; mx[d] = 0.f; }
+    float md[3];
+    for (int d = 0; d < 3; ++d) { out->extent[d] = mx[d] - mn[d]; md[d] = 0.5f * (mx[d] + mn[d]); out->centroid[d] = s_c[d]; }
+    for (int r = 0; r < 3; ++r) out->center[r] = ((s_E[3 * r] * md[0] + s_E[3 * r + 1] * md[1]) + s_E[3 * r + 2] * md[2]) + s_c[r];
+    float m34[12];
+    for (int r = 0; r < 3; ++r) { m34[4 * r] = s_E[3 * r]; m34[4 * r + 1] = s_E[3 * r + 1]; m34[4 * r + 2] = s_E[3 * r + 2]; m34[4 * r + 3] = 0.f; }
+    const Quat q = quat_from_matrix(m34);
+    out->quat[0] = q.w; out->quat[1] = q.x; out->quat[2] = q.y; out->quat[3] = q.z;
+    out->n = M;
+  }
+}
+
 }  // namespace pft

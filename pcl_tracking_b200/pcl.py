@@ -87,6 +87,22 @@ class PointCloud:
         check(capi.load().pft_cloud_upload(self._h, C.c_void_p(host_ptr), n, layout))
         return self
 
+    def fromPointCloud2(self, data, width, height, point_step, row_step=None, off_x=0, off_y=4, off_z=8, off_rgb=16, is_bigendian=False):
+        """sensor_msgs/PointCloud2 payload -> device cloud (pcl::fromPCLPointCloud2, ref: src/auto_tracking.cpp:619-622).
+        `data`: bytes / uint8 array of height x row_step bytes, or a raw host pointer (int)."""
+        row_step = int(width) * int(point_step) if row_step is None else int(row_step)
+        if isinstance(data, int):
+            p = C.c_void_p(data)
+        else:
+            a = np.ascontiguousarray(np.frombuffer(data, dtype=np.uint8) if isinstance(data, (bytes, bytearray, memoryview)) else data)
+            if a.nbytes < row_step * int(height):
+                raise ValueError("PointCloud2 data holds %d bytes, need %d" % (a.nbytes, row_step * int(height)))
+            self._keep = a
+            p = ptr(a)
+        check(capi.load().pft_cloud_upload_pointcloud2(self._h, p, int(width), int(height), int(point_step), row_step, int(off_x), int(off_y),
+                                                       int(off_z), int(off_rgb), 1 if is_bigendian else 0))
+        return self
+
     def broadcast(self, capacity, root=0):
         """NVLink broadcast of this cloud from `root` over the context communicator."""
         check(capi.load().pft_cloud_broadcast(self._h, int(capacity), int(root)))
@@ -359,6 +375,12 @@ class ParticleFilterOMPTracker:
     def getResult(self):
         out = np.zeros(1, dtype=PARTICLE)
         check(capi.load().pft_tracker_get_result(self._h, ptr(out)))
+        return out[0]
+
+    def getResultBox(self, z_offset=-0.005):
+        """Centroid + PCA oriented bounding box of the model at the result pose (viz_cb, ref: src/auto_tracking.cpp:432-466)."""
+        out = np.zeros(1, dtype=capi.RESULT_BOX)
+        check(capi.load().pft_tracker_get_result_box(self._h, float(z_offset), ptr(out)))
         return out[0]
 
     def getParticles(self):

@@ -173,3 +173,30 @@ def test_device_philox_draws_are_standard():
     z = np.stack([p["x"] - centre[0], p["y"] - centre[1], p["z"] - centre[2], p["roll"], p["pitch"], p["yaw"]], 1).astype(np.float64)
     assert np.all(np.abs(z.mean(0)) < 0.08) and np.all(np.abs(z.std(0) - 1.0) < 0.06)
     assert np.abs(np.corrcoef(z.T) - np.eye(6)).max() < 0.08
+
+
+def test_result_box_matches_oracle():
+    """centroid + PCA oriented bounding box of the model at the result pose (viz_cb, ref :432-466)."""
+    scene, model, centre = util.small_case(31, n_scene=3000, n_model=500)
+    t = _tracker_for(model, centre, kld=True, n=100, nmax=150)
+    t.setInputCloud(pcl.PointCloud(scene))
+    t.compute(); t.compute()
+    r = t.getResult()
+    for z_off in (-0.005, 0.0):
+        got = t.getResultBox(z_off)
+        want = oracle.result_box(model, [r["x"], r["y"], r["z"], r["roll"], r["pitch"], r["yaw"]], z_off)
+        assert got["n"] == want["n"] == len(model)
+        np.testing.assert_allclose(got["centroid"], want["centroid"], atol=1e-5)
+        np.testing.assert_allclose(got["eigenvalues"], want["eigenvalues"], rtol=1e-4, atol=1e-9)
+        np.testing.assert_allclose(got["extent"], want["extent"], atol=1e-4)
+        np.testing.assert_allclose(got["center"], want["center"], atol=1e-4)
+        np.testing.assert_allclose(got["axes"], want["axes"], atol=2e-3)
+        q = got["quat"].astype(np.float64)
+        assert abs(np.linalg.norm(q) - 1.0) < 1e-5
+        w, x, y, z = q
+        R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                      [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                      [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+        np.testing.assert_allclose(R, got["axes"], atol=1e-4)   # qfinal = Quaternionf(eigDx)
+    # the published object position is the centroid of the tracked cloud, near the object
+    assert np.linalg.norm(t.getResultBox()["centroid"] - centre) < 0.05

@@ -145,3 +145,58 @@ def test_all_points_rejected():
     vg = pcl.ApproximateVoxelGrid()
     vg.setInputCloud(pcl.PointCloud(pts))
     assert len(vg.filter()) == 0
+
+
+def _pointcloud2_payload(pts, width, height, point_step, row_step, offs, seed):
+    """Serialise packed points into a sensor_msgs/PointCloud2 byte payload with the given strides/offsets; padding
+    bytes are random so that a parser reading the wrong bytes is caught."""
+    rng = np.random.default_rng(seed)
+    raw = rng.integers(0, 256, (height, row_step), dtype=np.uint8)
+    rec = np.zeros((height * width, point_step), dtype=np.uint8)
+    rec[:] = rng.integers(0, 256, rec.shape, dtype=np.uint8)
+    for name, off in zip(("x", "y", "z", "rgba"), offs):
+        if off >= 0:
+            rec[:, off:off + 4] = np.ascontiguousarray(pts[name]).view(np.uint8).reshape(-1, 4)
+    raw[:, :width * point_step] = rec.reshape(height, width * point_step)
+    return raw
+
+
+@pytest.mark.parametrize("width,height,point_step,pad,offs", [
+    (512, 424, 32, 0, (0, 4, 8, 16)),     # kinect2_bridge: the PointXYZRGBA record as PCL serialises it
+    (640, 480, 16, 64, (0, 4, 8, 12)),    # packed xyz + rgb, padded rows
+    (97, 3, 24, 8, (8, 12, 16, 0)),       # colour first, ragged sizes
+    (33, 1, 12, 0, (0, 4, 8, -1)),        # xyz only
+    (0, 0, 32, 0, (0, 4, 8, 16)),         # empty message
+])
+def test_pointcloud2_ingest_bit_exact(width, height, point_step, pad, offs):
+    """Frame ingest (SURVEY 8 f-1): PointCloud2 payload -> device cloud == pcl::fromPCLPointCloud2 restated."""
+    n = width * height
+    pts = _random_cloud(n, 5 + width)
+    row_step = width * point_step + pad
+    raw = _pointcloud2_payload(pts, width, height, point_step, row_step, offs, 11)
+    want = oracle.from_pointcloud2(raw.tobytes(), width, height, point_step, row_step, *offs)
+    if offs[3] < 0:
+        assert not want["rgba"].any()
+    else:
+        assert np.array_equal(_bits(want), _bits(pts))  # the oracle parser recovers what was serialised
+    got = pcl.PointCloud().fromPointCloud2(raw, width, height, point_step, row_step, *offs).to_numpy()
+    assert len(got) == n
+    assert np.array_equal(_bits(got), _bits(want))
+    # and the ingest feeds the frame pipeline: PassThrough(z) of the ingested cloud == of the original points
+    if n:
+        pt = pcl.PassThrough()
+        pt.setFilterFieldName("z")
+        pt.setFilterLimits(0.0, 10.0)
+        pt.setInputCloud(pcl.PointCloud().fromPointCloud2(raw, width, height, point_step, row_step, *offs))
+        assert np.array_equal(_bits(pt.filter().to_numpy()), _bits(oracle.passthrough(want, 2, 0.0, 10.0)))
+
+
+def test_pointcloud2_ingest_rejects_bad_layouts():
+    c = pcl.PointCloud()
+    data = np.zeros(64, dtype=np.uint8)
+    for kw in (dict(point_step=10), dict(point_step=16, row_step=8), dict(point_step=16, off_x=14), dict(point_step=16, off_z=3),
+               dict(point_step=16, is_bigendian=True)):
+        args = dict(width=2, height=1, point_step=16, off_rgb=12)
+        args.update(kw)
+        with pytest.raises(pcl.capi.PftError):
+            c.fromPointCloud2(data, **args)

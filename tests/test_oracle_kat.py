@@ -345,3 +345,32 @@ def test_particle_sample_modes():
     # zero noise keeps the pose
     q0 = oracle.particle_sample([1, 2, 3, 0.1, 0.2, 0.3], [0] * 6, [0] * 6, z, quat_mode=1)
     np.testing.assert_allclose([q0["roll"], q0["pitch"], q0["yaw"]], [0.1, 0.2, 0.3], atol=1e-6)
+
+
+def test_from_pointcloud2_known_layout():
+    """fromPCLPointCloud2 restatement: the 32-byte PointXYZRGBA record of kinect2_bridge (x,y,z at 0,4,8; rgba at 16)."""
+    import struct
+    recs = [(1.0, -2.5, 3.25, 0x11223344), (float("nan"), 0.0, 7.0, 0xff000001)]
+    blob = b"".join(struct.pack("<fff4xI12x", *r) for r in recs) + b"\xaa" * 16  # row padding
+    out = oracle.from_pointcloud2(blob, 2, 1, 32, 80)
+    assert out["x"][0] == 1.0 and out["y"][0] == -2.5 and out["z"][0] == 3.25 and out["rgba"][0] == 0x11223344
+    assert np.isnan(out["x"][1]) and out["z"][1] == 7.0 and out["rgba"][1] == 0xff000001
+    xyz = oracle.from_pointcloud2(blob, 2, 1, 32, 80, off_rgb=-1)
+    assert not xyz["rgba"].any()
+
+
+def test_result_box_known_answer():
+    """PCA oriented bounding box of viz_cb (ref: src/auto_tracking.cpp:432-466) on a cloud whose box is known: an
+    8 x 4 x 2 cm grid-filled cuboid, rotated and translated by the result pose."""
+    g = np.stack(np.meshgrid(np.linspace(-0.04, 0.04, 17), np.linspace(-0.02, 0.02, 9), np.linspace(-0.01, 0.01, 5), indexing="ij"), -1).reshape(-1, 3)
+    model = oracle.make_points(g.astype(np.float32))
+    state = [0.3, -0.2, 1.1, 0.4, -0.3, 0.9]
+    box = oracle.result_box(model, state, z_offset=-0.005)
+    np.testing.assert_allclose(box["centroid"], [0.3, -0.2, 1.095], atol=2e-6)
+    np.testing.assert_allclose(box["extent"], [0.02, 0.04, 0.08], atol=1e-5)       # ascending eigenvalues: thinnest axis first
+    np.testing.assert_allclose(box["center"], box["centroid"], atol=1e-5)          # symmetric cloud: box centre = centroid
+    m = oracle.particle_to_matrix(state)[:, :3]
+    # the box axes are the rotated model axes (z, y, x in ascending order of variance), up to sign
+    for col, axis in enumerate((2, 1, 0)):
+        assert abs(abs(float(box["axes"][:, col] @ m[:, axis])) - 1.0) < 1e-4
+    assert abs(np.linalg.det(box["axes"].astype(np.float64)) - 1.0) < 1e-5        # right-handed: col2 = col0 x col1
