@@ -234,6 +234,7 @@ double kl_bound(int k, double delta, double eps) {
   return ((k - 1.0) / (2.0 * eps)) * chi * chi * chi;
 }
 
+constexpr int kClusterMinParticles = 4096;  // above this capacity the O(N) replicated stages run as a cluster of kClusterCtas CTAs
 constexpr int kWeightThreads = PFT_WEIGHT_THREADS;  // CTA size of the persistent weight kernel (one CTA per SM)
 
 // Row table of the nearest-neighbour search: the (dy,dz) offsets within kRT cells sorted by the lower bound
@@ -464,7 +465,9 @@ int stage_resample(pft_tracker* t, int slot) {
   TrackerState* st = t->st.as<TrackerState>();
   const DevParticle* old_parts = t->parts[t->cur].as<DevParticle>();
   DevParticle* new_parts = t->parts[t->cur ^ 1].as<DevParticle>();
-  cdf_kernel<<<1, 1024, 0, s>>>(st, old_parts, t->cdf.as<unsigned long long>(), t->cdf_total.as<unsigned long long>(), t->tbl_rep.as<int>(),
+  if (t->n_cap > kClusterMinParticles) cdf_kernel<kClusterCtas><<<kClusterCtas, 1024, 0, s>>>(st, old_parts, t->cdf.as<unsigned long long>(), t->cdf_total.as<unsigned long long>(), t->tbl_rep.as<int>(),
+                                t->tbl_min.as<int>(), t->kld ? t->tbl_size : 0);
+  else cdf_kernel<1><<<1, 1024, 0, s>>>(st, old_parts, t->cdf.as<unsigned long long>(), t->cdf_total.as<unsigned long long>(), t->tbl_rep.as<int>(),
                                 t->tbl_min.as<int>(), t->kld ? t->tbl_size : 0);
   PFT_LAUNCH_CHECK();
   stage_mark(t, "cdf_kernel");
@@ -631,7 +634,9 @@ int weight_comm_raw(pft_tracker* t) {
 int weight_phase_normalize(pft_tracker* t) {
   int rc = check_weight_ready(t);
   if (rc) return rc;
-  normalize_kernel<<<1, 1024, 0, t->run_stream()>>>(t->st.as<TrackerState>(), t->parts[t->cur].as<DevParticle>(), t->raw.as<float>(), t->alpha, t->nranks,
+  if (t->n_cap > kClusterMinParticles) normalize_kernel<kClusterCtas><<<kClusterCtas, 1024, 0, t->run_stream()>>>(t->st.as<TrackerState>(), t->parts[t->cur].as<DevParticle>(), t->raw.as<float>(), t->alpha, t->nranks,
+                                                   t->slice_cap(), t->input->d_hdr(), t->peer_mode ? reinterpret_cast<PeerWindow*>(t->peer_local) : nullptr, t->M);
+  else normalize_kernel<1><<<1, 1024, 0, t->run_stream()>>>(t->st.as<TrackerState>(), t->parts[t->cur].as<DevParticle>(), t->raw.as<float>(), t->alpha, t->nranks,
                                                    t->slice_cap(), t->input->d_hdr(), t->peer_mode ? reinterpret_cast<PeerWindow*>(t->peer_local) : nullptr, t->M);
   PFT_LAUNCH_CHECK();
   stage_mark(t, "normalize_kernel");
@@ -650,7 +655,8 @@ int stage_weight(pft_tracker* t) {
 
 int stage_update(pft_tracker* t) {
   if (!t->has_particles || !t->input) { set_last_error("update before weight"); return PFT_ERR_STATE; }
-  update_kernel<<<1, 1024, 0, t->run_stream()>>>(t->st.as<TrackerState>(), t->parts[t->cur].as<DevParticle>(), t->input->d_hdr());
+  if (t->n_cap > kClusterMinParticles) update_kernel<kClusterCtas><<<kClusterCtas, 1024, 0, t->run_stream()>>>(t->st.as<TrackerState>(), t->parts[t->cur].as<DevParticle>(), t->input->d_hdr());
+  else update_kernel<1><<<1, 1024, 0, t->run_stream()>>>(t->st.as<TrackerState>(), t->parts[t->cur].as<DevParticle>(), t->input->d_hdr());
   PFT_LAUNCH_CHECK();
   stage_mark(t, "update_kernel");
   return PFT_OK;

@@ -12,6 +12,8 @@
 //   cdf/resample/kld_*   (KLDAdaptive)ParticleFilterTracker::resample                     (A.7)
 //   init_particles_kernel ParticleFilterTracker::initParticles                            (A.8)
 #pragma once
+#include <cooperative_groups.h>
+
 #include "pft_common.cuh"
 
 namespace pft {
@@ -1392,23 +1394,34 @@ __global__ void raw_weights_kernel(TrackerState* st, const double* __restrict__ 
   }
 }
 
-// ------------------------------------------------------------------ K4a: normalizeWeight (one block)
-__global__ void __launch_bounds__(1024) normalize_kernel(TrackerState* st, DevParticle* parts, const float* raw, double alpha,
-                                                         int nranks, int slice_cap, const CloudHeader* __restrict__ scene_hdr,
-                                                         PeerWindow* peer_window /* non-null: wait for the peers' raw weights */, int M) {
+// ------------------------------------------------------------------ K4a: normalizeWeight
+// The O(N) stages between two weight() calls (normalise, update, cumulative table) are replicated on every rank and
+// grow with the TOTAL particle count, so they run as ONE thread-block cluster of kClusterCtas CTAs: every CTA reduces
+// its slice, the per-CTA partials are exchanged through distributed shared memory and combined in a fixed order
+// (identical results on every rank and every run), with cluster.sync() between the phases.  Small particle sets use
+// the CTAS = 1 instantiation (no cluster launch overhead).
+namespace cg = cooperative_groups;
+constexpr int kClusterCtas = 8;
+
+template <int CTAS>
+__global__ void __cluster_dims__(CTAS, 1, 1) __launch_bounds__(1024)
+normalize_kernel(TrackerState* st, DevParticle* parts, const float* raw, double alpha, int nranks, int slice_cap,
+                 const CloudHeader* __restrict__ scene_hdr, PeerWindow* peer_window /* non-null: wait for the peers' raw weights */, int M) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned int crank = cluster.block_rank();
   __shared__ double red[32];
-  __shared__ double s_min, s_max, s_sum;
+  __shared__ double s_part[3];  // this CTA's partial min, max, sum (read by the other CTAs of the cluster)
   if (peer_window) {
-    if (threadIdx.x == 0) peer_wait(&peer_window->flag_raw, st->peer_epoch * (unsigned int)nranks, &st->peer_error);
-    __syncthreads();
+    if (crank == 0 && threadIdx.x == 0) peer_wait(&peer_window->flag_raw, st->peer_epoch * (unsigned int)nranks, &st->peer_error);
+    cluster.sync();
     raw = peer_window->raw;
   }
   if (scene_hdr->n <= 0) return;  // Tracker::initCompute fails on an empty input cloud: compute() is a no-op
   const int n = st->particle_num;
-  if (threadIdx.x == 0) st->evals += (unsigned long long)n * (unsigned long long)M;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int first = crank * blockDim.x + threadIdx.x, stride = CTAS * blockDim.x;
   double wmin = DBL_MAX, wmax = -DBL_MAX;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+  for (int i = first; i < n; i += stride) {
     const double w = (double)__ldcg(&raw[raw_slot(i, nranks, slice_cap)]);
     if (wmin > w) wmin = w;
     if (w != 0.0 && wmax < w) wmax = w;
@@ -1416,15 +1429,19 @@ __global__ void __launch_bounds__(1024) normalize_kernel(TrackerState* st, DevPa
   for (int o = 16; o > 0; o >>= 1) { wmin = fmin(wmin, __shfl_xor_sync(kFull, wmin, o)); wmax = fmax(wmax, __shfl_xor_sync(kFull, wmax, o)); }
   if (lane == 0) red[wid] = wmin;
   __syncthreads();
-  if (threadIdx.x == 0) { double v = DBL_MAX; for (int k = 0; k < nw; ++k) v = fmin(v, red[k]); s_min = v; }
+  if (threadIdx.x == 0) { double v = DBL_MAX; for (int k = 0; k < nw; ++k) v = fmin(v, red[k]); s_part[0] = v; }
   __syncthreads();
   if (lane == 0) red[wid] = wmax;
   __syncthreads();
-  if (threadIdx.x == 0) { double v = -DBL_MAX; for (int k = 0; k < nw; ++k) v = fmax(v, red[k]); s_max = v; }
-  __syncthreads();
-  wmin = s_min; wmax = s_max;
+  if (threadIdx.x == 0) { double v = -DBL_MAX; for (int k = 0; k < nw; ++k) v = fmax(v, red[k]); s_part[1] = v; }
+  cluster.sync();
+  wmin = DBL_MAX; wmax = -DBL_MAX;
+  for (int r = 0; r < CTAS; ++r) {
+    const double* p = cluster.map_shared_rank(s_part, r);
+    wmin = fmin(wmin, p[0]); wmax = fmax(wmax, p[1]);
+  }
   double sum = 0.0;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+  for (int i = first; i < n; i += stride) {
     float w = __ldcg(&raw[raw_slot(i, nranks, slice_cap)]);
     if (wmax != wmin) {
       if (w != 0.0f) w = (float)exp(1.0 - alpha * ((double)w - wmin) / (wmax - wmin));
@@ -1435,56 +1452,86 @@ __global__ void __launch_bounds__(1024) normalize_kernel(TrackerState* st, DevPa
     sum += (double)w;
   }
   sum = block_sum(sum, red);
-  if (threadIdx.x == 0) { s_sum = sum; st->fit_ratio = wmin; st->weight_sum = sum; }
-  __syncthreads();
-  sum = s_sum;
+  if (threadIdx.x == 0) s_part[2] = sum;
+  cluster.sync();
+  sum = 0.0;
+  for (int r = 0; r < CTAS; ++r) sum += cluster.map_shared_rank(s_part, r)[2];  // fixed order
+  if (crank == 0 && threadIdx.x == 0) { st->fit_ratio = wmin; st->weight_sum = sum; st->evals += (unsigned long long)n * (unsigned long long)M; }
   const float fs = (float)sum;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+  for (int i = first; i < n; i += stride) {
     if (sum != 0.0) parts[i].weight = parts[i].weight / fs;
     else parts[i].weight = 1.0f / (float)n;
   }
+  cluster.sync();  // the partials of this CTA stay readable until every CTA of the cluster is done with them
 }
 
-// ------------------------------------------------------------------ K4c: update (one block)
-__global__ void __launch_bounds__(1024) update_kernel(TrackerState* st, const DevParticle* __restrict__ parts,
-                                                      const CloudHeader* __restrict__ scene_hdr) {
+// ------------------------------------------------------------------ K4c: update
+template <int CTAS>
+__global__ void __cluster_dims__(CTAS, 1, 1) __launch_bounds__(1024)
+update_kernel(TrackerState* st, const DevParticle* __restrict__ parts, const CloudHeader* __restrict__ scene_hdr) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned int crank = cluster.block_rank();
   __shared__ double red[32];
+  __shared__ double s_part[6];
   if (scene_hdr->n <= 0) return;
   const int n = st->particle_num;
   double acc[6] = {0, 0, 0, 0, 0, 0};
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+  for (int i = crank * blockDim.x + threadIdx.x; i < n; i += CTAS * blockDim.x) {
     const DevParticle p = parts[i];
     const double w = (double)p.weight;
     acc[0] += (double)(float)((double)p.x * w); acc[1] += (double)(float)((double)p.y * w); acc[2] += (double)(float)((double)p.z * w);
     acc[3] += (double)(float)((double)p.roll * w); acc[4] += (double)(float)((double)p.pitch * w); acc[5] += (double)(float)((double)p.yaw * w);
   }
-  double tot[6];
 #pragma unroll
-  for (int d = 0; d < 6; ++d) tot[d] = block_sum(acc[d], red);
-  if (threadIdx.x == 0) {
+  for (int d = 0; d < 6; ++d) { const double v = block_sum(acc[d], red); if (threadIdx.x == 0) s_part[d] = v; }
+  cluster.sync();
+  if (crank == 0 && threadIdx.x == 0) {
+    double tot[6] = {0, 0, 0, 0, 0, 0};
+    for (int r = 0; r < CTAS; ++r) {  // fixed order
+      const double* p = cluster.map_shared_rank(s_part, r);
+      for (int d = 0; d < 6; ++d) tot[d] += p[d];
+    }
     const DevParticle o = st->rep;
     DevParticle r{(float)tot[0], (float)tot[1], (float)tot[2], 1.f, (float)tot[3], (float)tot[4], (float)tot[5], 1.0f / (float)n};
     st->rep = r;
     st->motion = DevParticle{r.x - o.x, r.y - o.y, r.z - o.z, 1.f, r.roll - o.roll, r.pitch - o.pitch, r.yaw - o.yaw, 0.f};
   }
+  cluster.sync();
 }
 
 // ------------------------------------------------------------------ K4b: resample
-// Cumulative table in 2^-40 fixed point (order-independent integer prefix sums), one block.
-__global__ void __launch_bounds__(1024) cdf_kernel(TrackerState* st, const DevParticle* __restrict__ parts,
-                                                   unsigned long long* __restrict__ cdf, unsigned long long* total_out,
-                                                   int* __restrict__ tbl_rep, int* __restrict__ tbl_min, int tbl_size) {
+// Cumulative table in 2^-40 fixed point (order-independent integer prefix sums).  Every CTA of the cluster scans one
+// contiguous segment; the segment totals travel through distributed shared memory.
+template <int CTAS>
+__global__ void __cluster_dims__(CTAS, 1, 1) __launch_bounds__(1024)
+cdf_kernel(TrackerState* st, const DevParticle* __restrict__ parts, unsigned long long* __restrict__ cdf, unsigned long long* total_out,
+           int* __restrict__ tbl_rep, int* __restrict__ tbl_min, int tbl_size) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned int crank = cluster.block_rank();
   __shared__ unsigned long long smem[34];
+  __shared__ unsigned long long s_total;
   const int n = st->particle_num;
-  if (threadIdx.x == 0) st->draw_call += 1ull;  // the draws of this resample were generated by the previous launch
-  for (int i = threadIdx.x; i < tbl_size; i += blockDim.x) { tbl_rep[i] = -1; tbl_min[i] = 0x7fffffff; }
+  if (crank == 0 && threadIdx.x == 0) st->draw_call += 1ull;  // the draws of this resample were generated by the previous launch
+  for (int i = crank * blockDim.x + threadIdx.x; i < tbl_size; i += CTAS * blockDim.x) { tbl_rep[i] = -1; tbl_min[i] = 0x7fffffff; }
+  const int seg = (((n + CTAS - 1) / CTAS) + 3) & ~3;
+  const int i0 = min((int)crank * seg, n), i1 = min(i0 + seg, n);
   auto wq = [&](int i) -> unsigned long long {
-    const double w = (double)parts[i].weight;
+    const double w = (double)parts[i0 + i].weight;
     return (w > 0.0) ? (unsigned long long)(w * 1099511627776.0) : 0ull;
   };
-  const unsigned long long total = block_exclusive_scan<unsigned long long>(
-      n, wq, [&](int i, unsigned long long ex) { cdf[i] = ex + wq(i); }, smem);
-  if (threadIdx.x == 0) *total_out = total;
+  const unsigned long long mine = block_exclusive_scan<unsigned long long>(
+      i1 - i0, wq, [&](int i, unsigned long long ex) { cdf[i0 + i] = ex + wq(i); }, smem);
+  if (threadIdx.x == 0) s_total = mine;
+  cluster.sync();
+  unsigned long long before = 0ull, total = 0ull;
+  for (int r = 0; r < CTAS; ++r) {
+    const unsigned long long v = *cluster.map_shared_rank(&s_total, r);
+    if (r < (int)crank) before += v;
+    total += v;
+  }
+  if (before) for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) cdf[i] += before;
+  if (crank == 0 && threadIdx.x == 0) *total_out = total;
+  cluster.sync();
 }
 
 struct ResampleArgs {
