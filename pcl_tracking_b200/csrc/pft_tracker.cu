@@ -258,12 +258,14 @@ int upload_row_table(pft_tracker* t) {
   int dev = t->ctx->device, max_optin = 0;
   PFT_CUDA_TRY(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   cudaFuncAttributes fa;
-  PFT_CUDA_TRY(cudaFuncGetAttributes(&fa, weight_kernel<true, kWeightThreads>));
+  PFT_CUDA_TRY(cudaFuncGetAttributes(&fa, weight_kernel<true, kWeightThreads, true>));
   int dyn = max_optin - (int)fa.sharedSizeBytes - 1024;
   if (dyn < 0) dyn = 0;
   dyn &= ~15;
-  PFT_CUDA_TRY(cudaFuncSetAttribute(weight_kernel<true, kWeightThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
-  PFT_CUDA_TRY(cudaFuncSetAttribute(weight_kernel<false, kWeightThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+  PFT_CUDA_TRY(cudaFuncSetAttribute(weight_kernel<true, kWeightThreads, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+  PFT_CUDA_TRY(cudaFuncSetAttribute(weight_kernel<true, kWeightThreads, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+  PFT_CUDA_TRY(cudaFuncSetAttribute(weight_kernel<false, kWeightThreads, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+  PFT_CUDA_TRY(cudaFuncSetAttribute(weight_kernel<false, kWeightThreads, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
   t->weight_smem = dyn;
   if (t->list_max_cells / 8 + 64 > max_optin - 2048) t->list_max_cells = (max_optin - 4096) * 8;  // the mark kernel keeps one bit per fine cell in shared memory
   PFT_CUDA_TRY(cudaFuncSetAttribute(cand_mark_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, t->list_max_cells / 8 + 64));
@@ -411,7 +413,8 @@ int ensure_index_buffers(pft_tracker* t) {
 void choose_chunks(pft_tracker* t) {
   const int n_expected = std::max(1, (t->particle_num > 0 ? t->particle_num : t->n_cap) / t->nranks);
   const int total_warps = t->ctx->sm_count * (kWeightThreads / 32);
-  const int target_items = total_warps * 6;
+  static const int per_warp = [] { const char* e = getenv("PFT_ITEMS_PER_WARP"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 6; }();  // tuning knob
+  const int target_items = total_warps * per_warp;
   const int max_chunks = std::max(1, (t->M + 63) / 64);
   int chunks = (target_items + n_expected - 1) / n_expected;
   chunks = std::min(std::max(chunks, 1), std::min(max_chunks, 256));
@@ -601,6 +604,8 @@ int weight_phase_eval(pft_tracker* t) {
   a.mats = t->mats.as<float>();
   a.partial = t->partial.as<double>(); a.chunks = t->chunks; a.chunk_len = t->chunk_len; a.n_max = t->n_cap;
   a.nranks = t->nranks; a.rank_id = t->rank;
+  // many items per warp (large particle sets): dynamic hand-out; few: static interleaved split (see weight_items)
+  const bool dyn = (long long)std::max(1, (t->particle_num > 0 ? t->particle_num : t->n_cap) / t->nranks) * t->chunks >= 12ll * sm * (kWeightThreads / 32);
   a.co = make_coherence(t);
   a.dbg_k = t->debug_nn; a.dbg_idx = t->dbg_idx.as<int>(); a.dbg_d2 = t->dbg_d2.as<float>();
   const int local_cap = t->slice_cap();
@@ -609,8 +614,13 @@ int weight_phase_eval(pft_tracker* t) {
     while ((int)t->ev_w.size() < 2 * (t->n_ev_used + 1)) { cudaEvent_t e; PFT_CUDA_TRY(cudaEventCreate(&e)); t->ev_w.push_back(e); }
     PFT_CUDA_TRY(cudaEventRecord(t->ev_w[2 * t->n_ev_used], s));
   }
-  if (t->use_hsv) weight_kernel<true, kWeightThreads><<<wgrid, kWeightThreads, t->weight_smem, s>>>(a);
-  else weight_kernel<false, kWeightThreads><<<wgrid, kWeightThreads, t->weight_smem, s>>>(a);
+  if (t->use_hsv) {
+    if (dyn) weight_kernel<true, kWeightThreads, true><<<wgrid, kWeightThreads, t->weight_smem, s>>>(a);
+    else weight_kernel<true, kWeightThreads, false><<<wgrid, kWeightThreads, t->weight_smem, s>>>(a);
+  } else {
+    if (dyn) weight_kernel<false, kWeightThreads, true><<<wgrid, kWeightThreads, t->weight_smem, s>>>(a);
+    else weight_kernel<false, kWeightThreads, false><<<wgrid, kWeightThreads, t->weight_smem, s>>>(a);
+  }
   PFT_LAUNCH_CHECK();
   stage_mark(t, "weight_kernel");
   if (t->timing) { PFT_CUDA_TRY(cudaEventRecord(t->ev_w[2 * t->n_ev_used + 1], s)); t->n_ev_used++; }

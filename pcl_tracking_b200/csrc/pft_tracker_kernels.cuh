@@ -34,6 +34,7 @@ struct TrackerState {
   unsigned int peer_epoch;       // weight() calls so far in peer (NVLink P2P) exchange mode
   unsigned int peer_blocks_done; // raw_weights_kernel blocks that have pushed their slice this epoch
   unsigned int peer_error;       // a wait on a peer's flag timed out (sticky)
+  unsigned int work_counter;     // next (particle, model chunk) item of the running weight kernel (reset by index_begin_kernel)
   unsigned long long evals;      // likelihood evaluations so far: sum over weight() calls of particles x model points (whole job)
 };
 
@@ -384,7 +385,7 @@ __device__ inline void compute_index_header(const float* aabb, float inv_leaf, i
 // blocks clear the per-cell counters.
 // base_level < 0: choose the cell edge from the mean nearest-neighbour distance of the previous weight() (a query
 // that is d away from the surface walks ~pi (d/cell + 1)^2 rows and ~(d + cell)^2 candidates: cell ~ d balances them)
-__global__ void index_begin_kernel(const TrackerState* __restrict__ st, IndexHeader* hdr, int* cell_count, float inv_leaf, int base_level,
+__global__ void index_begin_kernel(TrackerState* st, IndexHeader* hdr, int* cell_count, float inv_leaf, int base_level,
                                    int max_cells, int list_max_cells, int M, int nranks, int rank, unsigned int* needed_words,
                                    int* list_counters /* [0] extended lists handed out, [1] needed blocks, [2] cells queued for the far pass */) {
   __shared__ IndexHeader h;
@@ -411,7 +412,7 @@ __global__ void index_begin_kernel(const TrackerState* __restrict__ st, IndexHea
   if (h.use_lists) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < h.f_cells; i += gridDim.x * blockDim.x) needed_words[i] = 0u;
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) { list_counters[0] = 0; list_counters[1] = 0; list_counters[2] = 0; }
+  if (blockIdx.x == 0 && threadIdx.x == 0) { list_counters[0] = 0; list_counters[1] = 0; list_counters[2] = 0; st->work_counter = 0u; }
 }
 
 __device__ __forceinline__ bool in_crop(const float4& p, const IndexHeader& h) {
@@ -1230,7 +1231,7 @@ struct WeightArgs {
 };
 
 // One (particle, model chunk) item by one warp: transform, nearest neighbour, coherence, warp reduction.
-template <bool USE_HSV, typename CS>
+template <bool USE_HSV, bool DYN, typename CS>
 __device__ __forceinline__ void weight_items(const WeightArgs& a, const IndexHeader& h, const CS* __restrict__ cs, const float4* __restrict__ pts,
                                              const unsigned int* __restrict__ hsv, const RowEntry* __restrict__ table, const float* __restrict__ lut_h,
                                              const float* __restrict__ lut_s) {
@@ -1238,16 +1239,24 @@ __device__ __forceinline__ void weight_items(const WeightArgs& a, const IndexHea
   const int n_local = n > a.rank_id ? (n - a.rank_id + a.nranks - 1) / a.nranks : 0;
   const int items = n_local * a.chunks;
   const int lane = threadIdx.x & 31;
-  const int total_warps = gridDim.x * (blockDim.x >> 5);
-  // interleave blocks first so that consecutive items spread over the SMs
-  const int warp_id = (threadIdx.x >> 5) * gridDim.x + blockIdx.x;
   // maximum_distance_^2 as the float just above it: every point with (double)d2 < max_d2 has d2 <= lim2
   const float lim2 = a.co.max_d2 >= 3.0e38 ? FLT_MAX : __double2float_ru(a.co.max_d2);
-  // (particle, chunk) of the warp's current item, advanced without divisions
-  int il = warp_id / a.chunks, c = warp_id - il * a.chunks;
-  const int dl = total_warps / a.chunks, dc = total_warps - dl * a.chunks;
   const bool use_lists = lists_on(h);
-  for (int item = warp_id; item < items; item += total_warps, il += dl, c += dc, il += (c >= a.chunks), c -= (c >= a.chunks) ? a.chunks : 0) {
+  // Large particle sets (many items per warp): items are handed out dynamically, one atomic per item with the next
+  // one requested before the current one is worked on -- query cost varies with the list lengths (measured -4 % on
+  // 100k particles).  Small sets (~4 items per warp): static interleaved assignment; there the atomic's latency costs
+  // more than the imbalance.  Which warp evaluates an item never matters: each item owns its output slot.
+  const int total_warps = gridDim.x * (blockDim.x >> 5);
+  int next = (threadIdx.x >> 5) * gridDim.x + blockIdx.x;  // static: blocks interleaved so that consecutive items spread over the SMs
+  if (DYN) {
+    if (lane == 0) next = (int)atomicAdd(&a.st->work_counter, 1u);
+    next = __shfl_sync(kFull, next, 0);
+  }
+  while (next < items) {
+    const int item = next;
+    if (!DYN) next = item + total_warps;
+    else if (lane == 0) next = (int)atomicAdd(&a.st->work_counter, 1u);
+    const int il = item / a.chunks, c = item - il * a.chunks;
     const int i = a.rank_id + il * a.nranks;
     float m[12];
     {
@@ -1307,11 +1316,12 @@ __device__ __forceinline__ void weight_items(const WeightArgs& a, const IndexHea
       a.partial[(size_t)c * a.n_max + i] = val;
       if (matched) { atomicAdd(&a.st->nn_sum_um, (unsigned long long)sum_um); atomicAdd(&a.st->nn_count, (unsigned long long)matched); }
     }
+    if (DYN) next = __shfl_sync(kFull, next, 0);
   }
 }
 
 // Persistent launch: one CTA per SM, each warp works through (particle, model chunk) items.
-template <bool USE_HSV, int THREADS>
+template <bool USE_HSV, int THREADS, bool DYN>
 __global__ void __launch_bounds__(THREADS, 1) weight_kernel(const WeightArgs a) {
   extern __shared__ uint4 dyn_smem[];
   __shared__ IndexHeader h;
@@ -1351,14 +1361,14 @@ __global__ void __launch_bounds__(THREADS, 1) weight_kernel(const WeightArgs a) 
     unsigned short* s_cs = reinterpret_cast<unsigned short*>(reinterpret_cast<unsigned char*>(dyn_smem) + used);
     for (int i = threadIdx.x; i <= h.n_cells; i += blockDim.x) s_cs[i] = (unsigned short)a.cell_start[i];
     __syncthreads();
-    if (hsv_staged) weight_items<USE_HSV, unsigned short>(a, h, s_cs, reinterpret_cast<const float4*>(s_pts), s_hsv, s_table, lut_h, lut_s);
-    else weight_items<USE_HSV, unsigned short>(a, h, s_cs, reinterpret_cast<const float4*>(s_pts), a.hsv, s_table, lut_h, lut_s);
+    if (hsv_staged) weight_items<USE_HSV, DYN, unsigned short>(a, h, s_cs, reinterpret_cast<const float4*>(s_pts), s_hsv, s_table, lut_h, lut_s);
+    else weight_items<USE_HSV, DYN, unsigned short>(a, h, s_cs, reinterpret_cast<const float4*>(s_pts), a.hsv, s_table, lut_h, lut_s);
   } else if (pts_staged) {
     __syncthreads();
-    if (hsv_staged) weight_items<USE_HSV, int>(a, h, a.cell_start, reinterpret_cast<const float4*>(s_pts), s_hsv, s_table, lut_h, lut_s);
-    else weight_items<USE_HSV, int>(a, h, a.cell_start, reinterpret_cast<const float4*>(s_pts), a.hsv, s_table, lut_h, lut_s);
+    if (hsv_staged) weight_items<USE_HSV, DYN, int>(a, h, a.cell_start, reinterpret_cast<const float4*>(s_pts), s_hsv, s_table, lut_h, lut_s);
+    else weight_items<USE_HSV, DYN, int>(a, h, a.cell_start, reinterpret_cast<const float4*>(s_pts), a.hsv, s_table, lut_h, lut_s);
   } else {
-    weight_items<USE_HSV, int>(a, h, a.cell_start, a.pts, a.hsv, s_table, lut_h, lut_s);
+    weight_items<USE_HSV, DYN, int>(a, h, a.cell_start, a.pts, a.hsv, s_table, lut_h, lut_s);
   }
 }
 
