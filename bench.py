@@ -490,7 +490,7 @@ def main():
     # DRAM traffic of the dominant kernel per launch, from the committed `ncu --set full` capture of this workload
     traffic, traffic_src = None, None
     try:
-        km = json.load(open(os.path.join(ROOT, "profiles", "r01_final_kernel_metrics.json")))
+        km = json.load(open(os.path.join(ROOT, "profiles", "r01f_kernel_metrics.json")))
         wk = [v for k, v in km.items() if k.startswith("weight_kernel")][0]
         scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
         tot = 0.0
@@ -498,7 +498,7 @@ def main():
             if key.startswith("dram__bytes_read.sum") or key.startswith("dram__bytes_write.sum"):
                 tot += float(val) * scale[key.split("[")[1].rstrip("]")]
         if args.workload == "c2" and world == 1:
-            traffic, traffic_src = tot, "profiles/r01_weight_and_build_final.ncu-rep (dram__bytes_read.sum + dram__bytes_write.sum, one launch)"
+            traffic, traffic_src = tot, "profiles/r01f_hot_kernels.ncu-rep (dram__bytes_read.sum + dram__bytes_write.sum, one launch)"
     except Exception:
         pass
 
