@@ -624,10 +624,12 @@ int weight_phase_eval(pft_tracker* t) {
   PFT_LAUNCH_CHECK();
   stage_mark(t, "weight_kernel");
   if (t->timing) { PFT_CUDA_TRY(cudaEventRecord(t->ev_w[2 * t->n_ev_used + 1], s)); t->n_ev_used++; }
-  raw_weights_kernel<<<blocks_for(local_cap, 256, sm * 4), 256, 0, s>>>(st, t->partial.as<double>(), t->chunks, t->n_cap, t->raw.as<float>(), local_cap,
-                                                                       t->nranks, t->rank, t->peers, t->peer_mode ? 1 : 0);
-  PFT_LAUNCH_CHECK();
-  stage_mark(t, "raw_weights_kernel");
+  if (t->nranks > 1) {  // (single rank: normalize_kernel sums the per-chunk partials itself)
+    raw_weights_kernel<<<blocks_for(local_cap, 256, sm * 4), 256, 0, s>>>(st, t->partial.as<double>(), t->chunks, t->n_cap, t->raw.as<float>(), local_cap,
+                                                                         t->nranks, t->rank, t->peers, t->peer_mode ? 1 : 0);
+    PFT_LAUNCH_CHECK();
+    stage_mark(t, "raw_weights_kernel");
+  }
   return PFT_OK;
 }
 
@@ -641,26 +643,28 @@ int weight_comm_raw(pft_tracker* t) {
 }
 
 // weight(), part 3: normalizeWeight (replicated)
-int weight_phase_normalize(pft_tracker* t) {
+int weight_phase_normalize(pft_tracker* t, bool fuse_update = false) {
   int rc = check_weight_ready(t);
   if (rc) return rc;
   if (t->n_cap > kClusterMinParticles) normalize_kernel<kClusterCtas><<<kClusterCtas, 1024, 0, t->run_stream()>>>(t->st.as<TrackerState>(), t->parts[t->cur].as<DevParticle>(), t->raw.as<float>(), t->alpha, t->nranks,
-                                                   t->slice_cap(), t->input->d_hdr(), t->peer_mode ? reinterpret_cast<PeerWindow*>(t->peer_local) : nullptr, t->M);
+                                                   t->slice_cap(), t->input->d_hdr(), t->peer_mode ? reinterpret_cast<PeerWindow*>(t->peer_local) : nullptr, t->M,
+                                                   t->nranks == 1 ? t->partial.as<double>() : nullptr, t->chunks, t->n_cap, t->raw.as<float>(), fuse_update ? 1 : 0);
   else normalize_kernel<1><<<1, 1024, 0, t->run_stream()>>>(t->st.as<TrackerState>(), t->parts[t->cur].as<DevParticle>(), t->raw.as<float>(), t->alpha, t->nranks,
-                                                   t->slice_cap(), t->input->d_hdr(), t->peer_mode ? reinterpret_cast<PeerWindow*>(t->peer_local) : nullptr, t->M);
+                                                   t->slice_cap(), t->input->d_hdr(), t->peer_mode ? reinterpret_cast<PeerWindow*>(t->peer_local) : nullptr, t->M,
+                                                   t->nranks == 1 ? t->partial.as<double>() : nullptr, t->chunks, t->n_cap, t->raw.as<float>(), fuse_update ? 1 : 0);
   PFT_LAUNCH_CHECK();
   stage_mark(t, "normalize_kernel");
   t->changed = true;  // change detector is off upstream => changed_ = true after every weight()
   return PFT_OK;
 }
 
-int stage_weight(pft_tracker* t) {
+int stage_weight(pft_tracker* t, bool fuse_update = false) {
   int rc;
   if ((rc = weight_phase_box(t))) return rc;
   if ((rc = weight_comm_box(t))) return rc;
   if ((rc = weight_phase_eval(t))) return rc;
   if ((rc = weight_comm_raw(t))) return rc;
-  return weight_phase_normalize(t);
+  return weight_phase_normalize(t, fuse_update);
 }
 
 int stage_update(pft_tracker* t) {
@@ -676,8 +680,9 @@ int enqueue_tracking(pft_tracker* t) {
   int rc;
   for (int it = 0; it < t->iteration_num; ++it) {
     if (t->changed && (rc = stage_resample(t, it))) return rc;
-    if ((rc = stage_weight(t))) return rc;
-    if (t->changed && (rc = stage_update(t))) return rc;
+    // upstream: update() runs when changed_, which every weight() sets (the change detector is off): it is fused into
+    // the normalise launch
+    if ((rc = stage_weight(t, true))) return rc;
   }
   return PFT_OK;
 }

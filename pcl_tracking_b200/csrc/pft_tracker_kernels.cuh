@@ -1416,11 +1416,15 @@ constexpr int kClusterCtas = 8;
 template <int CTAS>
 __global__ void __cluster_dims__(CTAS, 1, 1) __launch_bounds__(1024)
 normalize_kernel(TrackerState* st, DevParticle* parts, const float* raw, double alpha, int nranks, int slice_cap,
-                 const CloudHeader* __restrict__ scene_hdr, PeerWindow* peer_window /* non-null: wait for the peers' raw weights */, int M) {
+                 const CloudHeader* __restrict__ scene_hdr, PeerWindow* peer_window /* non-null: wait for the peers' raw weights */, int M,
+                 const double* __restrict__ partial /* non-null (single rank): the raw weights are summed here from the weight kernel's
+                                                       per-chunk partials instead of by raw_weights_kernel */,
+                 int chunks, int n_max, float* raw_out, int fuse_update /* compute(): update() follows every weight(), do it in the same launch */) {
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned int crank = cluster.block_rank();
   __shared__ double red[32];
   __shared__ double s_part[3];  // this CTA's partial min, max, sum (read by the other CTAs of the cluster)
+  __shared__ double s_upd[6];   // fused update(): this CTA's partial weighted state
   if (peer_window) {
     if (crank == 0 && threadIdx.x == 0) peer_wait(&peer_window->flag_raw, st->peer_epoch * (unsigned int)nranks, &st->peer_error);
     cluster.sync();
@@ -1432,10 +1436,21 @@ normalize_kernel(TrackerState* st, DevParticle* parts, const float* raw, double 
   const int first = crank * blockDim.x + threadIdx.x, stride = CTAS * blockDim.x;
   double wmin = DBL_MAX, wmax = -DBL_MAX;
   for (int i = first; i < n; i += stride) {
-    const double w = (double)__ldcg(&raw[raw_slot(i, nranks, slice_cap)]);
+    double w;
+    if (partial) {
+      // raw weight = -(float)sum over chunks (fixed order), exactly as raw_weights_kernel (nranks == 1: slot i)
+      double v = 0.0;
+      for (int c = 0; c < chunks; ++c) v += partial[(size_t)c * n_max + i];
+      const float wf = -(float)v;
+      raw_out[i] = wf;
+      w = (double)wf;
+    } else {
+      w = (double)__ldcg(&raw[raw_slot(i, nranks, slice_cap)]);
+    }
     if (wmin > w) wmin = w;
     if (w != 0.0 && wmax < w) wmax = w;
   }
+  if (partial) raw = raw_out;  // (every thread re-reads only the slots it has just written)
   for (int o = 16; o > 0; o >>= 1) { wmin = fmin(wmin, __shfl_xor_sync(kFull, wmin, o)); wmax = fmax(wmax, __shfl_xor_sync(kFull, wmax, o)); }
   if (lane == 0) red[wid] = wmin;
   __syncthreads();
@@ -1468,9 +1483,33 @@ normalize_kernel(TrackerState* st, DevParticle* parts, const float* raw, double 
   for (int r = 0; r < CTAS; ++r) sum += cluster.map_shared_rank(s_part, r)[2];  // fixed order
   if (crank == 0 && threadIdx.x == 0) { st->fit_ratio = wmin; st->weight_sum = sum; st->evals += (unsigned long long)n * (unsigned long long)M; }
   const float fs = (float)sum;
+  double acc[6] = {0, 0, 0, 0, 0, 0};
   for (int i = first; i < n; i += stride) {
-    if (sum != 0.0) parts[i].weight = parts[i].weight / fs;
-    else parts[i].weight = 1.0f / (float)n;
+    DevParticle p = parts[i];
+    if (sum != 0.0) p.weight = p.weight / fs;
+    else p.weight = 1.0f / (float)n;
+    parts[i].weight = p.weight;
+    if (fuse_update) {  // the same terms, slices and reduction order as update_kernel: bit-identical result
+      const double w = (double)p.weight;
+      acc[0] += (double)(float)((double)p.x * w); acc[1] += (double)(float)((double)p.y * w); acc[2] += (double)(float)((double)p.z * w);
+      acc[3] += (double)(float)((double)p.roll * w); acc[4] += (double)(float)((double)p.pitch * w); acc[5] += (double)(float)((double)p.yaw * w);
+    }
+  }
+  if (fuse_update) {
+#pragma unroll
+    for (int d = 0; d < 6; ++d) { const double v = block_sum(acc[d], red); if (threadIdx.x == 0) s_upd[d] = v; }
+    cluster.sync();
+    if (crank == 0 && threadIdx.x == 0) {
+      double tot[6] = {0, 0, 0, 0, 0, 0};
+      for (int r = 0; r < CTAS; ++r) {  // fixed order
+        const double* p = cluster.map_shared_rank(s_upd, r);
+        for (int d = 0; d < 6; ++d) tot[d] += p[d];
+      }
+      const DevParticle o = st->rep;
+      DevParticle r{(float)tot[0], (float)tot[1], (float)tot[2], 1.f, (float)tot[3], (float)tot[4], (float)tot[5], 1.0f / (float)n};
+      st->rep = r;
+      st->motion = DevParticle{r.x - o.x, r.y - o.y, r.z - o.z, 1.f, r.roll - o.roll, r.pitch - o.pitch, r.yaw - o.yaw, 0.f};
+    }
   }
   cluster.sync();  // the partials of this CTA stay readable until every CTA of the cluster is done with them
 }
