@@ -462,9 +462,9 @@ int stage_resample(pft_tracker* t, int slot) {
   if (t->kld && t->max_particle_num <= 0) { set_last_error("KLD tracker: setMaximumParticleNum was not called"); return PFT_ERR_STATE; }
   cudaStream_t s = t->run_stream();
   const int count = t->kld ? t->max_particle_num : t->n_cap;
-  const float *usel, *normals, *umot;
-  int rc = prepare_draws(t, slot, count, &usel, &normals, &umot);
-  if (rc) return rc;
+  const float *usel = nullptr, *normals = nullptr, *umot = nullptr;  // null: resample_kernel generates its draws inline (Philox)
+  int rc = PFT_OK;
+  if (t->inj_stride > 0 && (rc = prepare_draws(t, slot, count, &usel, &normals, &umot))) return rc;
   TrackerState* st = t->st.as<TrackerState>();
   const DevParticle* old_parts = t->parts[t->cur].as<DevParticle>();
   DevParticle* new_parts = t->parts[t->cur ^ 1].as<DevParticle>();
@@ -477,7 +477,7 @@ int stage_resample(pft_tracker* t, int slot) {
   ResampleArgs a;
   a.st = st; a.old_parts = old_parts; a.new_parts = new_parts;
   a.cdf = t->cdf.as<unsigned long long>(); a.cdf_total = t->cdf_total.as<unsigned long long>();
-  a.u_select = usel; a.normals = normals; a.u_motion = umot;
+  a.u_select = usel; a.normals = normals; a.u_motion = umot; a.seed = t->seed;
   a.scene_hdr = t->input->d_hdr();
   a.ancestors = t->ancestors.as<int>(); a.bin_keys = t->bin_keys.as<int>();
   const double zero[6] = {0, 0, 0, 0, 0, 0};

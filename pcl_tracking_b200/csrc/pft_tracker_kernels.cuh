@@ -1583,15 +1583,61 @@ cdf_kernel(TrackerState* st, const DevParticle* __restrict__ parts, unsigned lon
   cluster.sync();
 }
 
+// ------------------------------------------------------------------ on-device draws (Philox4x32-10)
+__device__ __forceinline__ void philox_round(unsigned int& c0, unsigned int& c1, unsigned int& c2, unsigned int& c3, unsigned int k0, unsigned int k1) {
+  const unsigned int hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+  const unsigned int hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+  c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
+}
+__device__ inline void philox4(unsigned int c0, unsigned int c1, unsigned int c2, unsigned int c3, unsigned int k0, unsigned int k1, unsigned int* out) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) { philox_round(c0, c1, c2, c3, k0, k1); k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+// the draws of candidate n in resample call `call`: one selection uniform, one motion uniform, six standard normals
+// (Box-Muller).  A pure function of (seed, call, n): every rank and every graph replay generates the same numbers.
+__device__ inline void gen_draws(int n, unsigned long long call, unsigned long long seed, float& u_select, float& u_motion, float* z6) {
+  unsigned int r[8];
+  philox4((unsigned int)n, (unsigned int)call, (unsigned int)(call >> 32), 0u, (unsigned int)seed, (unsigned int)(seed >> 32), r);
+  philox4((unsigned int)n, (unsigned int)call, (unsigned int)(call >> 32), 1u, (unsigned int)seed, (unsigned int)(seed >> 32), r + 4);
+  const float k = 1.0f / 16777216.0f;
+  u_select = (float)(r[0] >> 8) * k;
+  u_motion = (float)(r[1] >> 8) * k;
+#pragma unroll
+  for (int p = 0; p < 3; ++p) {
+    const float u1 = ((float)(r[2 + 2 * p] >> 8) + 1.0f) * k;  // (0,1]
+    const float u2 = (float)(r[3 + 2 * p] >> 8) * k;
+    const float rad = sqrtf(-2.0f * logf(u1));
+    float sn, cs;
+    sincosf(6.28318530718f * u2, &sn, &cs);
+    z6[2 * p] = rad * cs;
+    z6[2 * p + 1] = rad * sn;
+  }
+}
+// draw arrays of one call (initParticles; resample generates its draws inline unless they are injected)
+__global__ void draws_kernel(const TrackerState* __restrict__ st, float* u_select, float* normals, float* u_motion, int count,
+                             unsigned long long seed) {
+  const unsigned long long call = st->draw_call;
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < count; n += gridDim.x * blockDim.x) {
+    float us, um, z[6];
+    gen_draws(n, call, seed, us, um, z);
+    u_select[n] = us;
+    u_motion[n] = um;
+#pragma unroll
+    for (int d = 0; d < 6; ++d) normals[(size_t)n * 6 + d] = z[d];
+  }
+}
+
 struct ResampleArgs {
   const TrackerState* st;
   const DevParticle* old_parts;
   DevParticle* new_parts;
   const unsigned long long* cdf;
   const unsigned long long* cdf_total;
-  const float* u_select;   // [stride]
+  const float* u_select;   // [stride]      injected draws; all three null: generated inline from (seed, draw call, n)
   const float* normals;    // [stride][6]
   const float* u_motion;   // [stride]
+  unsigned long long seed;
   const CloudHeader* scene_hdr;
   int* ancestors;
   int* bin_keys;           // [n_max][6] (KLD)
@@ -1613,7 +1659,11 @@ __global__ void resample_kernel(const ResampleArgs a) {
   const int n_old = a.st->particle_num;
   const int n_cand = a.kld ? a.n_max : n_old;
   const unsigned long long total = *a.cdf_total;
-  const float u0 = a.u_select[0];
+  const bool inline_draws = a.u_select == nullptr;
+  const unsigned long long call = a.st->draw_call - 1ull;  // cdf_kernel has already advanced the stream position past this resample
+  float u0;
+  if (inline_draws) { float um0, z0[6]; gen_draws(0, call, a.seed, u0, um0, z0); }
+  else u0 = a.u_select[0];
   const bool skip = a.scene_hdr->n <= 0;  // empty input cloud: compute() is a no-op, particles carried over unchanged
   for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < n_cand; n += gridDim.x * blockDim.x) {
     if (skip) {
@@ -1629,20 +1679,25 @@ __global__ void resample_kernel(const ResampleArgs a) {
       a.ancestors[0] = -1;
       continue;
     }
+    float us, um, z[6];
+    if (inline_draws) {
+      gen_draws(n, call, a.seed, us, um, z);
+    } else {
+      us = a.u_select[n]; um = a.u_motion[n];
+#pragma unroll
+      for (int d = 0; d < 6; ++d) z[d] = a.normals[(size_t)n * 6 + d];
+    }
     double u;
     if (a.sampler == PFT_SAMPLER_CDF_VDC) {
       u = (double)u0 + (double)__brev((unsigned int)n) * (1.0 / 4294967296.0);
       if (u >= 1.0) u -= 1.0;
     } else {
-      u = (double)a.u_select[n];
+      u = (double)us;
     }
     const int j = cdf_pick(a.cdf, total, n_old, u);
     DevParticle x = a.old_parts[j];
-    float z[6];
-#pragma unroll
-    for (int d = 0; d < 6; ++d) z[d] = a.normals[(size_t)n * 6 + d];
     particle_sample(x, a.np, z);
-    if (a.kld && (double)a.u_motion[n] < a.motion_ratio) {
+    if (a.kld && (double)um < a.motion_ratio) {
       const DevParticle mo = a.st->motion;
       x.x += mo.x; x.y += mo.y; x.z += mo.z; x.roll += mo.roll; x.pitch += mo.pitch; x.yaw += mo.yaw;
     }
@@ -1697,40 +1752,6 @@ __global__ void __launch_bounds__(1024) kld_stop_kernel(TrackerState* st, const 
       smem);
   __syncthreads();
   if (threadIdx.x == 0) st->particle_num = stop;
-}
-
-// ------------------------------------------------------------------ on-device draws (Philox4x32-10)
-__device__ __forceinline__ void philox_round(unsigned int& c0, unsigned int& c1, unsigned int& c2, unsigned int& c3, unsigned int k0, unsigned int k1) {
-  const unsigned int hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-  const unsigned int hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-  c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
-}
-__device__ inline void philox4(unsigned int c0, unsigned int c1, unsigned int c2, unsigned int c3, unsigned int k0, unsigned int k1, unsigned int* out) {
-#pragma unroll
-  for (int r = 0; r < 10; ++r) { philox_round(c0, c1, c2, c3, k0, k1); k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
-  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
-}
-__global__ void draws_kernel(const TrackerState* __restrict__ st, float* u_select, float* normals, float* u_motion, int count,
-                             unsigned long long seed) {
-  const unsigned long long call = st->draw_call;
-  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < count; n += gridDim.x * blockDim.x) {
-    unsigned int r[8];
-    philox4((unsigned int)n, (unsigned int)call, (unsigned int)(call >> 32), 0u, (unsigned int)seed, (unsigned int)(seed >> 32), r);
-    philox4((unsigned int)n, (unsigned int)call, (unsigned int)(call >> 32), 1u, (unsigned int)seed, (unsigned int)(seed >> 32), r + 4);
-    const float k = 1.0f / 16777216.0f;
-    u_select[n] = (float)(r[0] >> 8) * k;
-    u_motion[n] = (float)(r[1] >> 8) * k;
-#pragma unroll
-    for (int p = 0; p < 3; ++p) {
-      const float u1 = ((float)(r[2 + 2 * p] >> 8) + 1.0f) * k;  // (0,1]
-      const float u2 = (float)(r[3 + 2 * p] >> 8) * k;
-      const float rad = sqrtf(-2.0f * logf(u1));
-      float s, c;
-      sincosf(6.28318530718f * u2, &s, &c);
-      normals[(size_t)n * 6 + 2 * p] = rad * c;
-      normals[(size_t)n * 6 + 2 * p + 1] = rad * s;
-    }
-  }
 }
 
 // ------------------------------------------------------------------ model preparation
