@@ -102,6 +102,17 @@ class PointCloud {
     }
     return dev_;
   }
+  // Frame ingest straight from a sensor_msgs/PointCloud2 message, replacing pcl_conversions::toPCL +
+  // pcl::fromPCLPointCloud2 (ref: src/auto_tracking.cpp:619-622): the payload is unpacked on the device; the host
+  // vector stays empty until download().  off_* = byte offsets of the x, y, z and rgb/rgba fields (msg.fields).
+  void fromPointCloud2(const void* data, uint32_t w, uint32_t h, uint32_t point_step, uint32_t row_step, int off_x, int off_y, int off_z,
+                       int off_rgb, bool is_bigendian = false, const std::shared_ptr<pft::Context>& ctx = pft::Context::Default()) {
+    if (!dev_) { ctx_ = ctx; pft::check(pft_cloud_create(ctx_->get(), &dev_)); }
+    pft::check(pft_cloud_upload_pointcloud2(dev_, data, w, h, point_step, row_step, off_x, off_y, off_z, off_rgb, is_bigendian ? 1 : 0));
+    points.clear();
+    width = w; height = h;
+    mark_device_written();
+  }
   // a filter wrote the device mirror: the host vector is stale until download()
   void mark_device_written() { device_only_ = true; host_dirty_ = false; }
   void download() {
@@ -275,6 +286,12 @@ class ParticleFilterOMPTracker {
     out->points.resize(n);
     if (n) pft::check(pft_tracker_get_particles(h_, reinterpret_cast<pft_particle*>(out->points.data()), n, &n));
     return out;
+  }
+  // what viz_cb derives from getResult() per object (ref :309-316, :432-466, :481-515): published centroid + PCA box
+  pft_result_box getResultBox(float z_offset = -0.005f) const {
+    pft_result_box b;
+    pft::check(pft_tracker_get_result_box(h_, z_offset, &b));
+    return b;
   }
   void resetTracking() { pft::check(pft_tracker_reset(h_)); }
   double getFitRatio() const { double v = 0; pft::check(pft_tracker_get_fit_ratio(h_, &v)); return v; }
