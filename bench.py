@@ -61,7 +61,7 @@ def env_int(name, default):
 # ------------------------------------------------------------------ workload
 def make_frames(n_frames, n_objects=1):
     from pcl_tracking_b200 import synth
-    objs = synth.default_objects(n_objects)
+    objs = synth.default_objects(n_objects) if n_objects == 1 else synth.default_objects(n_objects, seed=3)  # (seed 3: no two objects touch)
     frames = []
     oid0 = None
     for f in range(n_frames):
@@ -242,7 +242,7 @@ def workload_config(args, M, n_particles):
         "c3": "c3: BASELINE.json configs[2], KLD-adaptive particle count (<= %d, epsilon %g, bins %g m / rad), 217088-pt scene, %d-pt model,"
               " per-frame voxel-grid downsample + index rebuild, Distance+HSV" % (C3_MAX_PARTICLES, args.kld_epsilon, args.kld_bin, M),
         "c5": "c5: BASELINE.json configs[4], %d objects (%d model points in total, %d particles each) tracked simultaneously in one 217088-pt scene"
-              " (pft_compute_batch), Distance+HSV" % (C5_OBJECTS, M, PARTICLES_PER_GPU),
+              " (models = Euclidean clusters of the object points, pft_euclidean_clusters; pft_compute_batch), Distance+HSV" % (C5_OBJECTS, M, PARTICLES_PER_GPU),
     }
     return {
         "workload": names[args.workload],
@@ -312,9 +312,23 @@ def main():
     n_particles = {"c2": PARTICLES_PER_GPU * world, "c4": C4_PARTICLES, "c3": C3_MAX_PARTICLES, "c5": PARTICLES_PER_GPU}[args.workload]
 
     trackers, M = [], 0
+    cluster_src = None
+    if n_objects > 1:
+        # model acquisition on the GPU (ref: src/create_model.cpp:148-230) -- init-time, untimed: Euclidean clustering of the
+        # points left after the table plane is cut away gives one model cloud per object
+        keep = (oid0 >= 0) & np.isfinite(frames[0]["x"])
+        cluster_src = pcl.PointCloud(frames[0][keep], ctx=ctx)
+        ec = pcl.EuclideanClusterExtraction(ctx=ctx)
+        ec.setClusterTolerance(0.02)
+        ec.setMinClusterSize(200)
+        ec.setMaxClusterSize(25000)
+        ec.setInputCloud(cluster_src)
+        if len(ec.extract()) != n_objects:
+            print("bench.py: expected %d clusters, got %d" % (n_objects, len(ec.sizes)), file=sys.stderr)
+            return 4
     for k in range(n_objects):
         # model preparation on the GPU (ref :656-674) -- init-time, untimed
-        raw_model_cloud = pcl.PointCloud(raw_model(frames, oid0, k), ctx=ctx)
+        raw_model_cloud = ec.cluster_cloud(k) if cluster_src is not None else pcl.PointCloud(raw_model(frames, oid0, k), ctx=ctx)
         model_cloud, centroid = pcl.prepare_model(raw_model_cloud, LEAF, ctx=ctx)
         M += model_cloud.size()
         if args.workload == "c3":

@@ -98,6 +98,18 @@ PFT_API int pft_passthrough_voxel_grid(pft_context* ctx, const pft_cloud* in, pf
  * caller passes to pft_tracker_set_trans. */
 PFT_API int pft_prepare_model(pft_context* ctx, const pft_cloud* raw, pft_cloud* out, float leaf, float* centroid3);
 
+/* ---------------------------------------------------------------- model acquisition */
+/* pcl::EuclideanClusterExtraction::extract as the model builder runs it (ref: src/create_model.cpp:169-179:
+ * tolerance 0.02, min 500, max 25000): connected components of "closer than `tolerance`" (squared fp32 distance <
+ * (float)(tolerance^2), as FLANN's radius search), kept when min_size <= size <= max_size, ranked by size descending
+ * (ties: lower first point index).  labels[i] (host, may be NULL) = cluster rank of point i or -1; sizes[k] (host, may
+ * be NULL) = points of cluster k.  Non-finite points belong to no cluster.  The labels stay on the device for
+ * pft_cloud_select_cluster, which extracts cluster k as a cloud in input order (= the sorted indices upstream): the
+ * clouds create_model writes to models/<time>/<k>.pcd and returns to auto_tracking (ref: src/create_model.cpp:209-230). */
+PFT_API int pft_euclidean_clusters(pft_context* ctx, const pft_cloud* in, double tolerance, int min_size, int max_size, int32_t* labels,
+                                   size_t labels_capacity, int32_t* sizes, size_t sizes_capacity, size_t* n_clusters);
+PFT_API int pft_cloud_select_cluster(pft_context* ctx, const pft_cloud* in, int k, pft_cloud* out);
+
 /* ---------------------------------------------------------------- tracker configuration */
 typedef enum {
   /* int keys */

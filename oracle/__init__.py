@@ -49,6 +49,7 @@ def lib():
             "orc_voxel_grid_pcl": (i, [vp, i, f, vp]),
             "orc_voxel_grid_exact": (i, [vp, i, f, i, f, f, vp]),
             "orc_remove_zero_points": (i, [vp, i, vp]),
+            "orc_euclidean_clusters": (i, [vp, i, d, i, i, vp, vp, i]),
             "orc_centroid": (None, [vp, i, vp]),
             "orc_rgb2hsv": (None, [i, i, i, vp, vp, vp]),
             "orc_div_table": (i, [i]),
@@ -173,6 +174,16 @@ def from_pointcloud2(data, width, height, point_step, row_step=None, off_x=0, of
     if off_rgb >= 0:
         out["rgba"] = np.ascontiguousarray(rec[:, off_rgb:off_rgb + 4]).view("<u4")[:, 0]
     return out
+
+
+def euclidean_clusters(pts, tolerance=0.02, min_size=500, max_size=25000):
+    """pcl::EuclideanClusterExtraction (ref: src/create_model.cpp:169-179).  Returns (labels per point: cluster rank
+    or -1, cluster sizes in rank order: descending)."""
+    pts = as_points(pts)
+    labels = np.full(len(pts), -1, dtype=np.int32)
+    sizes = np.zeros(max(len(pts), 1), dtype=np.int32)
+    k = lib().orc_euclidean_clusters(_p(pts), len(pts), float(tolerance), int(min_size), int(max_size), _p(labels), _p(sizes), len(sizes))
+    return labels, sizes[:k].copy()
 
 
 def remove_zero_points(pts):

@@ -1015,6 +1015,59 @@ int orc_approx_voxel_grid_pcl(const orc_point* in, int n, float leaf, orc_point*
 int orc_voxel_grid_pcl(const orc_point* in, int n, float leaf, orc_point* out) { return voxel_grid_pcl(in, n, leaf, out); }
 int orc_voxel_grid_exact(const orc_point* in, int n, float leaf, int field, float lo, float hi, orc_point* out) { return voxel_grid_exact(in, n, leaf, field, lo, hi, out); }
 // removeZeroPoints, ref: src/auto_tracking.cpp:577-595
+// pcl::EuclideanClusterExtraction::extract as the model builder uses it (ref: src/create_model.cpp:169-179),
+// restating PCL-1.8.0 segmentation/impl/extract_clusters.hpp (extractEuclideanClusters): every unprocessed point in
+// index order seeds a breadth-first growth through KdTree radius searches; FLANN's radius search keeps the points
+// whose squared L2 distance -- ((dx*dx) + dy*dy) + dz*dz in fp32 -- is < (float)(tolerance * tolerance).  Clusters
+// inside [min_size, max_size] are kept with their indices sorted, then ordered by size descending (upstream:
+// std::sort over reverse iterators, ties unspecified; here the lower seed index first).  The radius search is
+// served by a uniform grid instead of a kd-tree (same result set).  labels[i] = cluster rank or -1.
+int orc_euclidean_clusters(const orc_point* pts, int n, double tolerance, int min_size, int max_size, int* labels, int* sizes, int sizes_cap) {
+  const float tol2 = (float)(tolerance * tolerance);
+  const float cell = (float)tolerance * 1.0001f;
+  struct Key { long long x, y, z; bool operator==(const Key& o) const { return x == o.x && y == o.y && z == o.z; } };
+  struct KeyHash { size_t operator()(const Key& k) const { return (size_t)(k.x * 73856093ll ^ k.y * 19349663ll ^ k.z * 83492791ll); } };
+  std::unordered_map<Key, std::vector<int>, KeyHash> grid;
+  auto key_of = [&](const Pt& p) { return Key{(long long)std::floor(p.x / cell), (long long)std::floor(p.y / cell), (long long)std::floor(p.z / cell)}; };
+  for (int i = 0; i < n; ++i) { labels[i] = -1; if (finite3(pts[i])) grid[key_of(pts[i])].push_back(i); }
+  std::vector<char> processed(n, 0);
+  std::vector<std::vector<int>> clusters;
+  std::vector<int> queue;
+  for (int i = 0; i < n; ++i) {
+    if (processed[i] || !finite3(pts[i])) continue;
+    queue.clear();
+    queue.push_back(i);
+    processed[i] = 1;
+    for (size_t q = 0; q < queue.size(); ++q) {
+      const Pt& p = pts[queue[q]];
+      const Key k = key_of(p);
+      for (long long dz = -1; dz <= 1; ++dz) for (long long dy = -1; dy <= 1; ++dy) for (long long dx = -1; dx <= 1; ++dx) {
+        auto it = grid.find(Key{k.x + dx, k.y + dy, k.z + dz});
+        if (it == grid.end()) continue;
+        for (int j : it->second) {
+          if (processed[j]) continue;
+          const float ex = p.x - pts[j].x, ey = p.y - pts[j].y, ez = p.z - pts[j].z;
+          const float d2 = (ex * ex + ey * ey) + ez * ez;
+          if (d2 < tol2) { processed[j] = 1; queue.push_back(j); }
+        }
+      }
+    }
+    if ((int)queue.size() >= min_size && (int)queue.size() <= max_size) {
+      std::sort(queue.begin(), queue.end());
+      clusters.push_back(queue);
+    }
+  }
+  std::stable_sort(clusters.begin(), clusters.end(), [](const std::vector<int>& a, const std::vector<int>& b) {
+    if (a.size() != b.size()) return a.size() > b.size();
+    return a[0] < b[0];
+  });
+  for (size_t c = 0; c < clusters.size(); ++c) {
+    if ((int)c < sizes_cap) sizes[c] = (int)clusters[c].size();
+    for (int j : clusters[c]) labels[j] = (int)c;
+  }
+  return (int)clusters.size();
+}
+
 int orc_remove_zero_points(const orc_point* in, int n, orc_point* out) {
   int m = 0;
   for (int i = 0; i < n; ++i) {

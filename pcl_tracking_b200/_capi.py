@@ -64,6 +64,8 @@ SIGNATURES = {
     "pft_passthrough": (_i, [_vp, _vp, _vp, _i, _f, _f]),
     "pft_passthrough_voxel_grid": (_i, [_vp, _vp, _vp, _f, _i, _f, _f]),
     "pft_prepare_model": (_i, [_vp, _vp, _vp, _f, _vp]),
+    "pft_euclidean_clusters": (_i, [_vp, _vp, _d, _i, _i, _vp, _sz, _vp, _sz, _psz]),
+    "pft_cloud_select_cluster": (_i, [_vp, _vp, _i, _vp]),
     "pft_tracker_create": (_i, [_vp, _i, _pp]),
     "pft_tracker_destroy": (None, [_vp]),
     "pft_tracker_set_i": (_i, [_vp, _i, _i]),

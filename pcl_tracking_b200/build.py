@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libpft.so")
-SOURCES = ["pft_api.cu", "pft_filters.cu", "pft_tracker.cu"]
+SOURCES = ["pft_api.cu", "pft_filters.cu", "pft_cluster.cu", "pft_tracker.cu"]
 HEADERS = ["pft_common.cuh", "pft_internal.h", "pft_tracker_kernels.cuh", os.path.join("..", "..", "include", "pft", "pft.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",

@@ -99,7 +99,8 @@ void pft_context_destroy(pft_context* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   pft_context_comm_destroy(c);
-  pft::DevBuf* bufs[] = {&c->k1_keys, &c->k1_first, &c->k1_vid, &c->k1_slot_of, &c->k1_acc_xyz, &c->k1_acc_rgbc, &c->k1_blk, &c->staging, &c->tmp_cloud_pts, &c->tmp_hdr, &c->tmp_f};
+  pft::DevBuf* bufs[] = {&c->k1_keys, &c->k1_first, &c->k1_vid, &c->k1_slot_of, &c->k1_acc_xyz, &c->k1_acc_rgbc, &c->k1_blk, &c->staging, &c->tmp_cloud_pts, &c->tmp_hdr, &c->tmp_f,
+                         &c->cl_grid, &c->cl_cells, &c->cl_work, &c->cl_sel};
   for (auto* b : bufs) b->release();
   if (c->pinned) cudaFreeHost(c->pinned);
   if (c->batch_fork) cudaEventDestroy(c->batch_fork);

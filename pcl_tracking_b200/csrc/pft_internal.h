@@ -32,6 +32,11 @@ struct pft_context {
   // NCCL communicator shared by the clouds and trackers of this context (one process per GPU)
   void* comm = nullptr;
   int nranks = 1, rank = 0;
+  // Euclidean clustering scratch (pft_cluster.cu); the labels of the last call stay on the device for pft_cloud_select_cluster
+  pft::DevBuf cl_grid, cl_cells, cl_work, cl_sel;
+  size_t cl_n = 0;
+  int cl_count = 0;
+  const pft_cloud* cl_src = nullptr;
   cudaEvent_t batch_fork = nullptr;  // pft_compute_batch: the point of the context stream the trackers' streams fork from
 };
 

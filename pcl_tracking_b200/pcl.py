@@ -162,6 +162,47 @@ class PassThrough:
         return out
 
 
+class EuclideanClusterExtraction:
+    """pcl::EuclideanClusterExtraction<PointXYZRGBA> as the model builder configures it (ref: src/create_model.cpp:169-179).
+    extract() returns the clusters as index arrays (sorted indices, largest cluster first), cluster_cloud(k) the k-th
+    cluster as a device cloud (what create_model returns to auto_tracking, ref: src/create_model.cpp:209-230)."""
+
+    def __init__(self, ctx=None):
+        self.ctx = ctx or Context.default()
+        self._tol, self._min, self._max, self._in = 0.0, 1, 2 ** 31 - 1, None
+        self.labels, self.sizes = None, None
+
+    def setClusterTolerance(self, tol):
+        self._tol = float(tol)
+
+    def setMinClusterSize(self, n):
+        self._min = int(n)
+
+    def setMaxClusterSize(self, n):
+        self._max = int(n)
+
+    def setSearchMethod(self, tree):
+        pass  # the KdTree of ref :169-173 is replaced by the uniform grid built inside extract()
+
+    def setInputCloud(self, cloud):
+        self._in = cloud
+
+    def extract(self):
+        n = self._in.size()
+        labels = np.full(n, -1, dtype=np.int32)
+        sizes = np.zeros(4096, dtype=np.int32)
+        k = C.c_size_t()
+        check(capi.load().pft_euclidean_clusters(self.ctx._h, self._in._h, self._tol, self._min, self._max, ptr(labels) if n else None, n,
+                                                 ptr(sizes), len(sizes), C.byref(k)))
+        self.labels, self.sizes = labels, sizes[:k.value].copy()
+        return [np.flatnonzero(labels == c).astype(np.int32) for c in range(k.value)]
+
+    def cluster_cloud(self, k, out=None):
+        out = PointCloud(ctx=self.ctx) if out is None else out
+        check(capi.load().pft_cloud_select_cluster(self.ctx._h, self._in._h, int(k), out._h))
+        return out
+
+
 class VoxelGrid:
     """pcl::VoxelGrid / pcl::ApproximateVoxelGrid (ref: src/auto_tracking.cpp:553-557, :568-571): one
     centroid per occupied voxel of the lattice floor(coord / leaf).  setPassThrough() folds the

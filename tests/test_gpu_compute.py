@@ -200,3 +200,42 @@ def test_result_box_matches_oracle():
         np.testing.assert_allclose(R, got["axes"], atol=1e-4)   # qfinal = Quaternionf(eigDx)
     # the published object position is the centroid of the tracked cloud, near the object
     assert np.linalg.norm(t.getResultBox()["centroid"] - centre) < 0.05
+
+
+def test_cluster_models_feed_the_trackers():
+    """C5 end to end: the object models come from Euclidean clustering of the non-table points (the model builder,
+    ref: src/create_model.cpp:148-230), one tracker per cluster, all tracked in the same scene."""
+    objs = synth.default_objects(8, seed=3)              # (a layout in which no two objects touch)
+    pts, oid = synth.render(0, objs)
+    keep = (oid >= 0) & np.isfinite(pts["x"])            # what remains after the table plane is cut away
+    obj_pts = pts[keep]
+    ec = pcl.EuclideanClusterExtraction()
+    ec.setClusterTolerance(0.02); ec.setMinClusterSize(200); ec.setMaxClusterSize(25000)
+    cloud = pcl.PointCloud(obj_pts)
+    ec.setInputCloud(cloud)
+    clusters = ec.extract()
+    assert len(clusters) == 8
+    ids = oid[keep]
+    seen = set()
+    for k, idx in enumerate(clusters):
+        owner = np.unique(ids[idx])
+        assert len(owner) == 1                            # a cluster is one object ...
+        assert len(idx) == int((ids == owner[0]).sum())   # ... and the whole of it
+        seen.add(int(owner[0]))
+    assert seen == set(range(8))
+    vg = pcl.ApproximateVoxelGrid()
+    vg.setLeafSize(0.01); vg.setPassThrough("z", 0.0, 10.0); vg.setInputCloud(pcl.PointCloud(pts))
+    ds = vg.filter()
+    trackers = []
+    for k in range(8):
+        model, c = pcl.prepare_model(ec.cluster_cloud(k), 0.01)
+        t = _tracker_for(model, c, kld=False, n=200, nmax=200, use_hsv=True, seed=7 + k)
+        t.setInputCloud(ds)
+        trackers.append(t)
+    for _ in range(2):
+        pcl.compute_batch(trackers)
+    for k, t in enumerate(trackers):
+        box = t.getResultBox()
+        want = obj_pts[clusters[k]]
+        centre = np.array([want["x"].mean(), want["y"].mean(), want["z"].mean()])
+        assert np.linalg.norm(box["centroid"] - centre) < 0.03   # every tracker stays on its own cluster

@@ -200,3 +200,49 @@ def test_pointcloud2_ingest_rejects_bad_layouts():
         args.update(kw)
         with pytest.raises(pcl.capi.PftError):
             c.fromPointCloud2(data, **args)
+
+
+def _cluster_scene(seed, n_blobs, n_noise):
+    rng = np.random.default_rng(seed)
+    parts = []
+    for b in range(n_blobs):
+        c = rng.uniform(-0.6, 0.6, 3) + np.array([0, 0, 1.2])
+        m = int(rng.integers(150, 900))
+        q = rng.uniform(-0.5, 0.5, (m, 3)) * rng.uniform(0.04, 0.12, 3)   # dense blob: 1-2 cm spacing
+        parts.append(c + q)
+    parts.append(rng.uniform(-1.0, 1.0, (n_noise, 3)) + np.array([0, 0, 1.2]))   # sparse clutter: singletons and small groups
+    xyz = np.concatenate(parts).astype(np.float32)
+    xyz = xyz[rng.permutation(len(xyz))]
+    xyz[rng.random(len(xyz)) < 0.01] = np.nan
+    return oracle.make_points(xyz, rng.integers(0, 1 << 32, len(xyz), dtype=np.uint64).astype(np.uint32))
+
+
+@pytest.mark.parametrize("seed,n_blobs,n_noise,tol,mn,mx", [(1, 6, 2000, 0.02, 100, 25000), (2, 12, 500, 0.02, 200, 600), (3, 3, 0, 0.015, 1, 25000),
+                                                            (4, 0, 300, 0.02, 500, 25000)])
+def test_euclidean_clusters_match_oracle(seed, n_blobs, n_noise, tol, mn, mx):
+    """Model acquisition: EuclideanClusterExtraction on the GPU == the BFS restatement: same components,
+    same size filter, same ranking; each cluster cloud = the input points of its (sorted) indices."""
+    pts = _cluster_scene(seed, n_blobs, n_noise)
+    want_labels, want_sizes = oracle.euclidean_clusters(pts, tol, mn, mx)
+    cloud = pcl.PointCloud(pts)
+    ec = pcl.EuclideanClusterExtraction()
+    ec.setClusterTolerance(tol); ec.setMinClusterSize(mn); ec.setMaxClusterSize(mx); ec.setInputCloud(cloud)
+    clusters = ec.extract()
+    assert ec.sizes.tolist() == want_sizes.tolist()
+    assert np.array_equal(ec.labels, want_labels)
+    for k, idx in enumerate(clusters):
+        assert len(idx) == want_sizes[k]
+        got = ec.cluster_cloud(k).to_numpy()
+        assert np.array_equal(_bits(got), _bits(pts[idx]))
+
+
+def test_euclidean_clusters_edge_cases():
+    ec = pcl.EuclideanClusterExtraction()
+    ec.setClusterTolerance(0.02); ec.setMinClusterSize(1); ec.setMaxClusterSize(10)
+    ec.setInputCloud(pcl.PointCloud(np.zeros(0, dtype=pcl.POINT)))
+    assert ec.extract() == []
+    one = oracle.make_points(np.array([[0.1, 0.2, 0.3]], dtype=np.float32))
+    ec.setInputCloud(pcl.PointCloud(one))
+    assert [c.tolist() for c in ec.extract()] == [[0]]
+    with pytest.raises(pcl.capi.PftError):
+        ec.setClusterTolerance(0.0); ec.extract()

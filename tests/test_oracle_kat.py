@@ -374,3 +374,20 @@ def test_result_box_known_answer():
     for col, axis in enumerate((2, 1, 0)):
         assert abs(abs(float(box["axes"][:, col] @ m[:, axis])) - 1.0) < 1e-4
     assert abs(np.linalg.det(box["axes"].astype(np.float64)) - 1.0) < 1e-5        # right-handed: col2 = col0 x col1
+
+
+def test_euclidean_clusters_known_answer():
+    """EuclideanClusterExtraction restatement (ref: src/create_model.cpp:169-179): two chains of points 1.5 cm apart
+    (connected under a 2 cm tolerance), a third one too short for min_size, a NaN point and an isolated point."""
+    def chain(x0, y, n):
+        return [(x0 + 0.015 * k, y, 1.0) for k in range(n)]
+    xyz = np.array(chain(0.0, 0.0, 30) + [(np.nan, 0.0, 1.0)] + chain(0.0, 0.5, 40) + chain(0.0, 1.0, 5) + [(5.0, 5.0, 5.0)], dtype=np.float32)
+    labels, sizes = oracle.euclidean_clusters(oracle.make_points(xyz), 0.02, 10, 1000)
+    assert sizes.tolist() == [40, 30]                       # largest first
+    assert (labels[31:71] == 0).all() and (labels[:30] == 1).all()
+    assert labels[30] == -1 and (labels[71:] == -1).all()   # NaN, too-small chain, isolated point
+    # the tolerance is strict: points exactly 2 cm apart (in fp32) are not neighbours
+    pair = oracle.make_points(np.array([(0.0, 0.0, 0.0), (0.02, 0.0, 0.0)], dtype=np.float32))
+    assert (np.float32(0.02) * np.float32(0.02) < np.float32(0.02 * 0.02)) == (oracle.euclidean_clusters(pair, 0.02, 2, 10)[1].tolist() == [2])
+    # max_size drops oversized components
+    assert oracle.euclidean_clusters(oracle.make_points(xyz), 0.02, 10, 35)[1].tolist() == [30]
