@@ -179,6 +179,38 @@ class VoxelGrid {
 };
 template <typename PointT> using ApproximateVoxelGrid = VoxelGrid<PointT>;
 
+// pcl::PointIndices + pcl::EuclideanClusterExtraction as the model builder uses them (ref: src/create_model.cpp:169-179)
+struct PointIndices { std::vector<int> indices; };
+template <typename PointT>
+class EuclideanClusterExtraction {
+ public:
+  void setClusterTolerance(double t) { tol_ = t; }
+  void setMinClusterSize(int n) { min_ = n; }
+  void setMaxClusterSize(int n) { max_ = n; }
+  template <typename TreePtr> void setSearchMethod(const TreePtr&) {}  // the KdTree (ref :169-173) is replaced by a uniform grid
+  void setInputCloud(const typename PointCloud<PointT>::ConstPtr& c) { in_ = c; }
+  // clusters ranked by size descending, indices sorted (as upstream); cluster k as a device cloud: clusterCloud(k, out)
+  void extract(std::vector<PointIndices>& clusters) {
+    auto& ctx = pft::Context::Default();
+    const size_t n = in_->size();
+    std::vector<int32_t> labels(n ? n : 1), sizes(4096);
+    size_t k = 0;
+    pft::check(pft_euclidean_clusters(ctx->get(), in_->device(ctx), tol_, min_, max_, n ? labels.data() : nullptr, n, sizes.data(), sizes.size(), &k));
+    clusters.assign(k, PointIndices());
+    for (size_t c = 0; c < k; ++c) clusters[c].indices.reserve((size_t)sizes[c]);
+    for (size_t i = 0; i < n; ++i) if (labels[i] >= 0) clusters[(size_t)labels[i]].indices.push_back((int)i);
+  }
+  void clusterCloud(int k, PointCloud<PointT>& out) {  // ref: src/create_model.cpp:209-230 (one cloud per cluster)
+    auto& ctx = pft::Context::Default();
+    pft::check(pft_cloud_select_cluster(ctx->get(), in_->device(ctx), k, out.device(ctx)));
+    out.mark_device_written();
+  }
+ private:
+  typename PointCloud<PointT>::ConstPtr in_;
+  double tol_ = 0.0;
+  int min_ = 1, max_ = 2147483647;
+};
+
 namespace search {
 // pcl::search::Octree(resolution) (ref :250): the cell size of the uniform-grid index
 template <typename PointT> struct Octree { explicit Octree(double r) : resolution(r) {} double resolution; };
