@@ -49,6 +49,38 @@ def compute():
     return out
 
 
+def compute_aux():
+    """Second fixture (oracle_aux_case.npz): the steps either side of the path -- frame ingest, model acquisition,
+    result post-processing."""
+    rng = np.random.default_rng(4321)
+    # a 24 x 5 PointCloud2 message with 24-byte records (rgb first, xyz at 8/12/16) and 8 bytes of row padding
+    w, h, step, pad = 24, 5, 24, 8
+    pts = oracle.make_points(rng.uniform(-1, 3, (w * h, 3)).astype(np.float32), rng.integers(0, 1 << 32, w * h, dtype=np.uint64).astype(np.uint32))
+    pts["x"][7] = np.nan
+    rec = rng.integers(0, 256, (w * h, step), dtype=np.uint8)
+    for name, off in (("rgba", 0), ("x", 8), ("y", 12), ("z", 16)):
+        rec[:, off:off + 4] = np.ascontiguousarray(pts[name]).view(np.uint8).reshape(-1, 4)
+    raw = rng.integers(0, 256, (h, w * step + pad), dtype=np.uint8)
+    raw[:, :w * step] = rec.reshape(h, w * step)
+    out = dict(pc2_raw=raw, pc2_points=oracle.from_pointcloud2(raw.tobytes(), w, h, step, w * step + pad, 8, 12, 16, 0))
+    # clustering: three blobs + clutter
+    blobs = [np.array(c) + rng.uniform(-0.5, 0.5, (m, 3)) * np.array(sz) for c, m, sz in
+             (((0.0, 0.0, 1.0), 260, (0.10, 0.06, 0.05)), ((0.4, 0.1, 1.1), 150, (0.05, 0.05, 0.08)), ((-0.3, 0.3, 0.9), 60, (0.04, 0.04, 0.04)))]
+    xyz = np.concatenate(blobs + [rng.uniform(-1, 1, (80, 3)) + np.array([0, 0, 1.0])]).astype(np.float32)
+    xyz = xyz[rng.permutation(len(xyz))]
+    cl_pts = oracle.make_points(xyz, rng.integers(0, 1 << 32, len(xyz), dtype=np.uint64).astype(np.uint32))
+    labels, sizes = oracle.euclidean_clusters(cl_pts, 0.02, 50, 25000)
+    out.update(cluster_points=cl_pts, cluster_labels=labels, cluster_sizes=sizes)
+    # result box of a model at a pose
+    _, model, _ = util.small_case(seed=99, n_scene=10, n_model=300)
+    state = np.array([0.21, -0.13, 1.07, 0.3, -0.2, 0.7], dtype=np.float32)
+    box = oracle.result_box(model, state, -0.005)
+    out.update(box_model=model, box_state=state, box_centroid=box["centroid"], box_axes=box["axes"], box_extent=box["extent"],
+               box_center=box["center"], box_eigenvalues=box["eigenvalues"])
+    return out
+
+
 if __name__ == "__main__":
+    np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "oracle_aux_case.npz"), **compute_aux())
     np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "oracle_small_case.npz"), **compute())
     print("written")

@@ -54,3 +54,48 @@ def test_cuda_path_matches_committed_fixture():
     vg.setLeafSize(0.02); vg.setPassThrough("z", 0.0, 10.0); vg.setInputCloud(cloud)
     ds = vg.filter().to_numpy()
     assert ds.tobytes() == want["downsampled"].tobytes()
+
+
+AUX = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_aux_case.npz")
+
+
+def test_oracle_reproduces_committed_aux_fixture():
+    want = np.load(AUX)
+    got = make_golden.compute_aux()
+    for k in want.files:
+        a, b = want[k], np.asarray(got[k])
+        assert a.shape == b.shape, k
+        if k.startswith("box_") and k not in ("box_model", "box_state"):
+            np.testing.assert_allclose(b, a, rtol=1e-6, atol=1e-7, err_msg=k)  # (numpy's eigh may differ in the last bit between builds)
+        else:
+            assert a.tobytes() == b.tobytes(), k
+
+
+@pytest.mark.gpu
+def test_cuda_path_matches_committed_aux_fixture():
+    from pcl_tracking_b200 import pcl
+    want = np.load(AUX)
+    raw = want["pc2_raw"]
+    got = pcl.PointCloud().fromPointCloud2(raw, 24, 5, 24, raw.shape[1], 8, 12, 16, 0).to_numpy()
+    assert got.tobytes() == want["pc2_points"].tobytes()
+    ec = pcl.EuclideanClusterExtraction()
+    ec.setClusterTolerance(0.02); ec.setMinClusterSize(50); ec.setMaxClusterSize(25000)
+    ec.setInputCloud(pcl.PointCloud(want["cluster_points"]))
+    ec.extract()
+    np.testing.assert_array_equal(ec.labels, want["cluster_labels"])
+    np.testing.assert_array_equal(ec.sizes, want["cluster_sizes"])
+    t = pcl.ParticleFilterOMPTracker(16)
+    pcl.configure_like_reference(t, particle_num=8)
+    t.setReferenceCloud(want["box_model"])
+    st = want["box_state"]
+    rep = np.zeros(1, dtype=pcl.PARTICLE)
+    for k, v in zip(("x", "y", "z", "roll", "pitch", "yaw"), st):
+        rep[k] = v
+    rep["one"] = 1.0
+    t.setResult(rep[0])
+    box = t.getResultBox(-0.005)
+    np.testing.assert_allclose(box["centroid"], want["box_centroid"], atol=1e-5)
+    np.testing.assert_allclose(box["extent"], want["box_extent"], atol=1e-4)
+    np.testing.assert_allclose(box["center"], want["box_center"], atol=1e-4)
+    np.testing.assert_allclose(box["eigenvalues"], want["box_eigenvalues"], rtol=1e-4, atol=1e-9)
+    np.testing.assert_allclose(box["axes"], want["box_axes"], atol=2e-3)
