@@ -551,7 +551,7 @@ int weight_comm_box(pft_tracker* t) {
 }
 
 // weight(), part 2: cropInputPointCloud + search index rebuild (K2), coherence of this rank's particles (K3)
-int weight_phase_eval(pft_tracker* t) {
+int weight_phase_eval(pft_tracker* t, bool force_raw = false) {
   int rc = check_weight_ready(t);
   if (rc) return rc;
   cudaStream_t s = t->run_stream();
@@ -624,7 +624,7 @@ int weight_phase_eval(pft_tracker* t) {
   PFT_LAUNCH_CHECK();
   stage_mark(t, "weight_kernel");
   if (t->timing) { PFT_CUDA_TRY(cudaEventRecord(t->ev_w[2 * t->n_ev_used + 1], s)); t->n_ev_used++; }
-  if (t->nranks > 1) {  // (single rank: normalize_kernel sums the per-chunk partials itself)
+  if (t->nranks > 1 || force_raw) {  // (single rank: normalize_kernel sums the per-chunk partials itself)
     raw_weights_kernel<<<blocks_for(local_cap, 256, sm * 4), 256, 0, s>>>(st, t->partial.as<double>(), t->chunks, t->n_cap, t->raw.as<float>(), local_cap,
                                                                          t->nranks, t->rank, t->peers, t->peer_mode ? 1 : 0);
     PFT_LAUNCH_CHECK();
@@ -1340,7 +1340,7 @@ int pft_tracker_weight_phase(pft_tracker* t, int phase) {
   if (rc) return rc;
   switch (phase) {
     case 0: return weight_phase_box(t);
-    case 1: if (t->timing) t->n_ev_used = 0; return weight_phase_eval(t);
+    case 1: if (t->timing) t->n_ev_used = 0; return weight_phase_eval(t, true);  // (raw slices are readable between the phases)
     case 2: return weight_phase_normalize(t);
     default: set_last_error("phase must be 0, 1 or 2"); return PFT_ERR_INVALID;
   }

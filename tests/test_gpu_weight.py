@@ -114,3 +114,43 @@ def test_weight_no_scene_point_in_crop():
     assert g.croppedCount() == 0
     np.testing.assert_array_equal(g.rawWeights(), np.zeros(10, dtype=np.float32))
     np.testing.assert_allclose(g.getParticles()["weight"], o.get_particles()["weight"], rtol=1e-6)
+
+
+def test_weight_crop_beyond_16_bit_slots():
+    """A crop of more than 65 535 points: the candidate lists (16-bit slots) switch themselves off, the index is too
+    large for shared memory and is read through L1/L2 -- the row-table search alone must still be exact."""
+    scene, model, centre = util.small_case(21, n_scene=150000, n_model=96, spread=0.22)
+    g, o = util.make_pair(kld=False, particle_num=6, use_hsv=True, oracle_nn=oracle.NN_EXACT_GRID)
+    parts = util.particles_around(centre, 6, seed=5)
+    cloud = pcl.PointCloud(scene)
+    g.setReferenceCloud(model); g.setInputCloud(cloud); g.setParticles(parts); g.setDebugNN(6); g.setCandidateLists(2); g.weight()
+    o.set_reference(model); o.set_input(scene); o.set_particles(parts); o.weight(keep_nn=True)
+    cidx, _ = o.cropped()
+    assert g.croppedCount() == len(cidx) and len(cidx) > 65535
+    for p in range(6):
+        gi, gd = g.nn(p, len(model))
+        oi, od = o.nn(p, len(model))
+        m = od.astype(np.float64) < 0.1 * 0.1
+        np.testing.assert_array_equal(gi[m], cidx[oi[m]])
+        np.testing.assert_array_equal(gd[m], od[m])
+    np.testing.assert_allclose(g.rawWeights(), o.raw_weights(), rtol=W_RTOL)
+
+
+def test_weight_dense_scene_long_lists():
+    """3 mm point spacing against 1 cm list cells: candidate lists of 50-150 entries, some beyond the 127 of a regular
+    record (extended lists) -- same nearest neighbours as brute force."""
+    scene, model, centre = util.small_case(22, n_scene=60000, n_model=160, spread=0.12)
+    g, o = util.make_pair(kld=False, particle_num=8, use_hsv=True, oracle_nn=oracle.NN_EXACT_GRID)
+    parts = util.particles_around(centre, 8, seed=6, sigma_t=0.02)
+    cloud = pcl.PointCloud(scene)
+    g.setReferenceCloud(model); g.setInputCloud(cloud); g.setParticles(parts); g.setDebugNN(8); g.setCandidateLists(2); g.weight()
+    assert g.indexInfo()["use_lists"] == 1
+    o.set_reference(model); o.set_input(scene); o.set_particles(parts); o.weight(keep_nn=True)
+    cidx, _ = o.cropped()
+    for p in range(8):
+        gi, gd = g.nn(p, len(model))
+        oi, od = o.nn(p, len(model))
+        m = od.astype(np.float64) < 0.1 * 0.1
+        np.testing.assert_array_equal(gi[m], cidx[oi[m]])
+        np.testing.assert_array_equal(gd[m], od[m])
+    np.testing.assert_allclose(g.rawWeights(), o.raw_weights(), rtol=W_RTOL)
