@@ -82,7 +82,10 @@ __global__ void peer_box_exchange_kernel(TrackerState* st, PeerSet ps) {
     const int r = r0 + (lane >> 3), d = lane & 7;
     if (r < ps.nranks && d < 6) ps.win[r]->box[cur][ps.rank][d] = st->aabb[d];
   }
-  __threadfence_system();
+  // (the pattern NCCL's primitives use: the writers synchronise, ONE thread issues the system-scope fence -- it is
+  //  cumulative over what the barrier ordered before it -- and only then are the flags raised)
+  __syncwarp();
+  if (lane == 0) __threadfence_system();
   __syncwarp();
   if (lane < ps.nranks) atomicAdd_system(&ps.win[lane]->flag_box, 1u);
   bool ok = true;
@@ -1392,9 +1395,9 @@ __global__ void raw_weights_kernel(TrackerState* st, const double* __restrict__ 
     }
   }
   if (peer_mode) {
-    __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
+      __threadfence_system();  // one system-scope fence per block, after the barrier (cumulative over the block's stores)
       const unsigned int done = atomicAdd(&st->peer_blocks_done, 1u) + 1u;
       if (done == gridDim.x) {  // every block of this rank has pushed its values
         __threadfence_system();

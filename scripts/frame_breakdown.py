@@ -19,8 +19,15 @@ def main():
     workload = sys.argv[1] if len(sys.argv) > 1 else "c2"
     n_frames = int(sys.argv[2]) if len(sys.argv) > 2 else 50
     n_particles = int(sys.argv[3]) if len(sys.argv) > 3 else (1000 if workload == "c2" else 100000)
-    ctx = pcl.Context(0)
-    stream = torch.cuda.ExternalStream(ctx.stream)
+    rank, world, local_rank = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local_rank)
+    if world > 1:  # torchrun: one tracker sharded by particle over the ranks, NVLink peer exchange (as bench.py)
+        import torch.distributed as dist
+        dist.init_process_group("gloo")
+        if workload == "c2" and len(sys.argv) <= 3:
+            n_particles *= world
+    ctx = pcl.Context(local_rank)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
     frames, oid0 = bench.make_frames(bench.N_FRAMES)
     model_cloud, centroid = pcl.prepare_model(pcl.PointCloud(bench.raw_model(frames, oid0), ctx=ctx), bench.LEAF, ctx=ctx)
     M = model_cloud.size()
@@ -30,6 +37,12 @@ def main():
     m[:3, 3] = centroid
     tracker.setTrans(m)
     tracker.seed(1234)
+    if world > 1:
+        tracker.setShard(world, rank)
+        handles = [None] * world
+        dist.all_gather_object(handles, tracker.peerExport())
+        tracker.peerAttach(handles)
+        dist.barrier()
     tracker.setReferenceCloud(model_cloud)
     dev_frames = [pcl.PointCloud(f, ctx=ctx) for f in frames]
     ds = pcl.PointCloud(ctx=ctx)
@@ -77,6 +90,10 @@ def main():
     out = {"workload": workload, "particles": n_particles, "model_points": M, "frames": n_frames,
            "frame_ms_graph_replay": graph_ms, "frame_ms_stream_launched_sum": (total + k1_ms) / n_frames,
            "k1_downsample_ms_per_frame": k1_ms / n_frames, "index": tracker.indexInfo(), "kernels": {}}
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+        return
     print("%s: %d particles x %d pts; frame %.3f ms (graph replay), %.3f ms (sum of stream-launched kernels incl. K1 %.3f ms)"
           % (workload, n_particles, M, graph_ms, (total + k1_ms) / n_frames, k1_ms / n_frames))
     for name, (cnt, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
@@ -84,6 +101,8 @@ def main():
               % (name, cnt / n_frames, 1e3 * ms / cnt, 1e3 * ms / n_frames, 100.0 * ms / (total + k1_ms)))
         out["kernels"][name] = {"launches_per_frame": cnt / n_frames, "us_per_launch": 1e3 * ms / cnt, "us_per_frame": 1e3 * ms / n_frames}
     print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
 
 
 if __name__ == "__main__":
