@@ -109,6 +109,17 @@ PFT_API int pft_prepare_model(pft_context* ctx, const pft_cloud* raw, pft_cloud*
 PFT_API int pft_euclidean_clusters(pft_context* ctx, const pft_cloud* in, double tolerance, int min_size, int max_size, int32_t* labels,
                                    size_t labels_capacity, int32_t* sizes, size_t sizes_capacity, size_t* n_clusters);
 PFT_API int pft_cloud_select_cluster(pft_context* ctx, const pft_cloud* in, int k, pft_cloud* out);
+/* pcl::SACSegmentation(SACMODEL_PLANE, SAC_RANSAC)::segment + pcl::ExtractIndices of the model builder's plane variant
+ * (ref: src/create_model_planar_segmentation.cpp:157-174: setMaxIterations(1000), setDistanceThreshold(0.015); upstream
+ * defaults probability 0.99, optimize_coefficients true).  samples3 (host, n_samples x 3 point indices) injects the
+ * RANSAC draws in draw order (upstream uses rand(): not reproducible); NULL: generated on the device from `seed`.
+ * Every hypothesis is scored, then the sequential accept / adapt-k / stop rule is replayed over the scores: the same
+ * plane as upstream's loop for the same draws (a collinear sample is skipped without counting as an iteration).
+ * coefficients4 = (a, b, c, d) of the (refined) plane; plane_out / rest_out (may be NULL) = ExtractIndices with
+ * setNegative(false) / (true), both in input order; non-finite points are never inliers. */
+PFT_API int pft_segment_plane(pft_context* ctx, const pft_cloud* in, double distance_threshold, int max_iterations, double probability,
+                              const int32_t* samples3, int n_samples, uint64_t seed, int optimize_coefficients, float* coefficients4,
+                              int32_t* iterations, pft_cloud* plane_out, pft_cloud* rest_out, size_t* n_inliers);
 
 /* ---------------------------------------------------------------- tracker configuration */
 typedef enum {

@@ -186,6 +186,81 @@ def euclidean_clusters(pts, tolerance=0.02, min_size=500, max_size=25000):
     return labels, sizes[:k].copy()
 
 
+def segment_plane(pts, samples3, distance_threshold=0.015, max_iterations=1000, probability=0.99, optimize=True):
+    """pcl::SACSegmentation(SACMODEL_PLANE, SAC_RANSAC)::segment (ref: src/create_model_planar_segmentation.cpp:157-163)
+    restated with numpy from PCL-1.8.0 sample_consensus/impl/ransac.hpp (computeModel), impl/sac_model_plane.hpp
+    (computeModelCoefficients, countWithinDistance, selectWithinDistance, optimizeModelCoefficients) and
+    segmentation/impl/sac_segmentation.hpp, with the RANSAC draws injected (`samples3`: rows of three point indices,
+    consumed in order; a collinear sample is skipped without counting as an iteration -- upstream redraws).
+    fp32 arithmetic where upstream uses Eigen float vectors (4-lane reductions add as (0 + 2) + (1 + 3)); the
+    refinement accumulates in fp64 (upstream: sequential fp32).  Returns dict(coeff, ransac_coeff, best, iterations, inliers mask)."""
+    f = np.float32
+    pts = as_points(pts)
+    x, y, z = pts["x"].astype(f), pts["y"].astype(f), pts["z"].astype(f)
+    n = len(pts)
+
+    def dist_mask(c):
+        with np.errstate(invalid="ignore", over="ignore"):
+            d = ((c[0] * x + c[2] * z).astype(f) + (c[1] * y + c[3]).astype(f)).astype(f)
+            return np.abs(d).astype(np.float64) < distance_threshold
+
+    def model(i0, i1, i2):
+        if not (0 <= i0 < n and 0 <= i1 < n and 0 <= i2 < n) or len({i0, i1, i2}) < 3:
+            return None
+        with np.errstate(all="ignore"):
+            p0 = np.array([x[i0], y[i0], z[i0]], dtype=f)
+            a = (np.array([x[i1], y[i1], z[i1]], dtype=f) - p0).astype(f)
+            b = (np.array([x[i2], y[i2], z[i2]], dtype=f) - p0).astype(f)
+            r = (a / b).astype(f)
+            if r[0] == r[1] and r[2] == r[1]:
+                return None
+            nrm = np.array([f(a[1] * b[2]) - f(a[2] * b[1]), f(a[2] * b[0]) - f(a[0] * b[2]), f(a[0] * b[1]) - f(a[1] * b[0])], dtype=f)
+            ln = np.sqrt(f(f(nrm[0] * nrm[0]) + f(nrm[2] * nrm[2])) + f(f(nrm[1] * nrm[1]) + f(0)), dtype=f)
+            nrm = (nrm / ln).astype(f)
+            d = f(-1.0) * f(f(f(nrm[0] * p0[0]) + f(nrm[2] * p0[2])) + f(f(nrm[1] * p0[1]) + f(0)))
+            c = np.array([nrm[0], nrm[1], nrm[2], d], dtype=f)
+        return c if np.isfinite(c).all() else None
+
+    iterations, best, best_count, skipped, k = 0, -1, -(2 ** 31 - 1), 0, 1.0
+    log_p = np.log(1.0 - probability)
+    best_c = None
+    for s, (i0, i1, i2) in enumerate(np.asarray(samples3).reshape(-1, 3).tolist()):
+        if not (iterations < k and skipped < max_iterations * 10):
+            break
+        c = model(i0, i1, i2)
+        if c is None:
+            skipped += 1
+            continue
+        cnt = int(dist_mask(c).sum())
+        if cnt > best_count:
+            best_count, best, best_c = cnt, s, c
+            w = cnt / float(n)
+            p_no = min(max(1.0 - w * w * w, np.finfo(np.float64).eps), 1.0 - np.finfo(np.float64).eps)
+            k = log_p / np.log(p_no)
+        iterations += 1
+        if iterations > max_iterations:
+            break
+    if best < 0:
+        return dict(coeff=None, ransac_coeff=None, best=-1, iterations=iterations, inliers=np.zeros(n, dtype=bool))
+    coeff = best_c.copy()
+    m = dist_mask(best_c)
+    if optimize and m.sum() >= 3:
+        q = np.stack([x[m], y[m], z[m]], 1)
+        xx = np.stack([q[:, 0] * q[:, 0], q[:, 0] * q[:, 1], q[:, 0] * q[:, 2], q[:, 1] * q[:, 1], q[:, 1] * q[:, 2], q[:, 2] * q[:, 2]], 1).astype(f)
+        a6 = xx.astype(np.float64).sum(0) / m.sum()
+        mean = q.astype(np.float64).sum(0) / m.sum()
+        cov = np.array([[a6[0], a6[1], a6[2]], [a6[1], a6[3], a6[4]], [a6[2], a6[4], a6[5]]]) - np.outer(mean, mean)
+        w_, v_ = np.linalg.eigh(cov)
+        nrm = v_[:, 0]
+        if nrm @ best_c[:3].astype(np.float64) < 0:
+            nrm = -nrm
+        nf, mf = nrm.astype(f), mean.astype(f)
+        d = f(-1.0) * f(f(f(nf[0] * mf[0]) + f(nf[1] * mf[1])) + f(nf[2] * mf[2]))
+        coeff = np.array([nf[0], nf[1], nf[2], d], dtype=f)
+        m = dist_mask(coeff)
+    return dict(coeff=coeff, ransac_coeff=best_c, best=best, iterations=iterations, inliers=m)
+
+
 def remove_zero_points(pts):
     pts = as_points(pts)
     out = np.empty_like(pts)

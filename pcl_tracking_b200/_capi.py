@@ -66,6 +66,7 @@ SIGNATURES = {
     "pft_prepare_model": (_i, [_vp, _vp, _vp, _f, _vp]),
     "pft_euclidean_clusters": (_i, [_vp, _vp, _d, _i, _i, _vp, _sz, _vp, _sz, _psz]),
     "pft_cloud_select_cluster": (_i, [_vp, _vp, _i, _vp]),
+    "pft_segment_plane": (_i, [_vp, _vp, _d, _i, _d, _vp, _i, _u64, _i, _vp, C.POINTER(C.c_int32), _vp, _vp, _psz]),
     "pft_tracker_create": (_i, [_vp, _i, _pp]),
     "pft_tracker_destroy": (None, [_vp]),
     "pft_tracker_set_i": (_i, [_vp, _i, _i]),

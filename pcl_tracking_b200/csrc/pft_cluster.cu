@@ -11,6 +11,7 @@
 // upstream starts it from), component sizes, then the components inside [min, max] ordered by size descending
 // (upstream: std::sort over reverse iterators; ties are unspecified there, here the lower seed index goes first).
 #include <float.h>
+#include <string.h>
 
 #include <algorithm>
 
@@ -325,6 +326,271 @@ int pft_cloud_select_cluster(pft_context* ctx, const pft_cloud* in, int k, pft_c
   cl_extract_kernel<<<1, 1024, 0, ctx->stream>>>(in->d_pts(), in->d_hdr(), dlabels, k, out->d_pts(), out->d_hdr());
   PFT_LAUNCH_CHECK();
   out->host_n = -1;
+  return PFT_OK;
+}
+
+}  // extern "C"
+
+// =====================================================================================================================
+// Plane segmentation of the model builder's second variant (ref: src/create_model_planar_segmentation.cpp:157-174):
+// pcl::SACSegmentation<PointT>(SACMODEL_PLANE, SAC_RANSAC, setMaxIterations(1000), setDistanceThreshold(0.015))::segment
+// followed by pcl::ExtractIndices (setNegative(false) -> the plane, setNegative(true) -> everything else).
+// Upstream (PCL-1.8.0 sample_consensus/impl/ransac.hpp, sac_model_plane.hpp, segmentation/impl/sac_segmentation.hpp):
+//   loop: draw 3 point indices -> plane through them (computeModelCoefficients) -> countWithinDistance -> keep the
+//   best, k = log(1 - probability) / log(1 - w^3) with w = best inlier ratio; stop at iterations >= k or > max;
+//   selectWithinDistance(best); optimizeModelCoefficients = least-squares plane of the inliers (smallest eigenvector of
+//   their covariance, d = -n . centroid); selectWithinDistance(refined).
+// Here every drawn hypothesis is scored at once (one thread block per hypothesis over all points), then ONE thread
+// replays the sequential accept / adapt-k / stop logic over the scores in draw order: the same plane as the sequential
+// loop for the same draws.  The draws are injected (upstream uses rand(): not reproducible) or generated with Philox.
+// A collinear sample is skipped without counting as an iteration (upstream redraws inside getSamples).
+namespace pft {
+namespace {
+
+struct PlaneResult {
+  float coeff[4];        // after the optional refinement
+  float ransac_coeff[4]; // the winning hypothesis
+  int best;              // index of the winning hypothesis (-1: none)
+  int iterations;        // RANSAC iterations performed
+  int n_inliers;         // final inlier count
+  int pad;
+};
+
+__device__ __forceinline__ bool plane_from_sample(const float4& p0, const float4& p1, const float4& p2, float* c) {
+  // SampleConsensusModelPlane::computeModelCoefficients
+  const float ax = p1.x - p0.x, ay = p1.y - p0.y, az = p1.z - p0.z;
+  const float bx = p2.x - p0.x, by = p2.y - p0.y, bz = p2.z - p0.z;
+  const float rx = ax / bx, ry = ay / by, rz = az / bz;      // dy1dy2 = p1p0 / p2p0
+  if (rx == ry && rz == ry) return false;                    // collinear
+  float nx = ay * bz - az * by, ny = az * bx - ax * bz, nz = ax * by - ay * bx;
+  // Eigen's 4-float reductions (normalize, dot) add lanes as (0 + 2) + (1 + 3) on SSE; lane 3 of the normal is 0
+  const float len = sqrtf((nx * nx + nz * nz) + (ny * ny + 0.0f));
+  nx = nx / len; ny = ny / len; nz = nz / len;
+  c[0] = nx; c[1] = ny; c[2] = nz;
+  c[3] = -1.0f * ((nx * p0.x + nz * p0.z) + (ny * p0.y + 0.0f));
+  return isfinite(c[0]) && isfinite(c[1]) && isfinite(c[2]) && isfinite(c[3]);
+}
+__device__ __forceinline__ bool plane_inlier(const float* c, const float4& p, double thr) {
+  // fabs(model_coefficients.dot(Vector4f(x, y, z, 1))) < threshold  (float dot in Eigen's (0 + 2) + (1 + 3) lane order,
+  // double compare)
+  const float d = (c[0] * p.x + c[2] * p.z) + (c[1] * p.y + c[3]);
+  return (double)fabsf(d) < thr;   // (NaN points fail the comparison)
+}
+
+// one block per hypothesis: coefficients + inlier count
+__global__ void __launch_bounds__(256) plane_score_kernel(const float4* __restrict__ pts, const CloudHeader* __restrict__ hdr, const int* __restrict__ samples3,
+                                                          int n_samples, double thr, float* __restrict__ coeffs, int* __restrict__ counts) {
+  __shared__ float c[4];
+  __shared__ int ok;
+  __shared__ int red[8];
+  const int n = hdr->n;
+  for (int s = blockIdx.x; s < n_samples; s += gridDim.x) {
+    if (threadIdx.x == 0) {
+      const int i0 = samples3[3 * s], i1 = samples3[3 * s + 1], i2 = samples3[3 * s + 2];
+      ok = 0;
+      if ((unsigned)i0 < (unsigned)n && (unsigned)i1 < (unsigned)n && (unsigned)i2 < (unsigned)n && i0 != i1 && i0 != i2 && i1 != i2)
+        ok = plane_from_sample(pts[i0], pts[i1], pts[i2], c) ? 1 : 0;
+      for (int k = 0; k < 4; ++k) coeffs[4 * s + k] = ok ? c[k] : 0.f;
+    }
+    __syncthreads();
+    int cnt = 0;
+    if (ok) {
+      const float cc[4] = {c[0], c[1], c[2], c[3]};
+      for (int i = threadIdx.x; i < n; i += blockDim.x) cnt += plane_inlier(cc, pts[i], thr) ? 1 : 0;
+    }
+    cnt = warp_sum(cnt);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int t = 0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+      counts[s] = ok ? t : -1;
+    }
+    __syncthreads();
+  }
+}
+
+// RandomSampleConsensus::computeModel replayed over the scores (one thread)
+__global__ void plane_pick_kernel(const CloudHeader* __restrict__ hdr, const float* __restrict__ coeffs, const int* __restrict__ counts, int n_samples,
+                                  int max_iterations, double probability, PlaneResult* out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const int n = hdr->n;
+  int iterations = 0, best = -1, best_count = -2147483647, skipped = 0;
+  double k = 1.0;
+  const double log_probability = log(1.0 - probability);
+  const double one_over_indices = n > 0 ? 1.0 / (double)n : 0.0;
+  const int max_skip = max_iterations * 10;
+  for (int s = 0; s < n_samples && (double)iterations < k && skipped < max_skip; ++s) {
+    if (counts[s] < 0) { ++skipped; continue; }   // bad sample: no model
+    if (counts[s] > best_count) {
+      best_count = counts[s]; best = s;
+      const double w = (double)best_count * one_over_indices;
+      double p_no_outliers = 1.0 - w * w * w;     // pow(w, 3 samples)
+      p_no_outliers = fmax(2.220446049250313e-16, p_no_outliers);
+      p_no_outliers = fmin(1.0 - 2.220446049250313e-16, p_no_outliers);
+      k = log_probability / log(p_no_outliers);
+    }
+    ++iterations;
+    if (iterations > max_iterations) break;
+  }
+  PlaneResult r;
+  for (int q = 0; q < 4; ++q) { r.ransac_coeff[q] = best >= 0 ? coeffs[4 * best + q] : 0.f; r.coeff[q] = r.ransac_coeff[q]; }
+  r.best = best; r.iterations = iterations; r.n_inliers = best >= 0 ? best_count : 0; r.pad = 0;
+  *out = r;
+}
+
+// optimizeModelCoefficients: least-squares plane of the inliers of the winning hypothesis (one block; fp64 sums of
+// fp32 terms: order independent -- upstream accumulates in fp32 sequentially)
+__global__ void __launch_bounds__(1024) plane_refine_kernel(const float4* __restrict__ pts, const CloudHeader* __restrict__ hdr, double thr, PlaneResult* res) {
+  __shared__ double red[32];
+  __shared__ double s_sum[9];
+  const int n = hdr->n;
+  if (res->best < 0) return;
+  const float c[4] = {res->ransac_coeff[0], res->ransac_coeff[1], res->ransac_coeff[2], res->ransac_coeff[3]};
+  double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  double cnt = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float4 p = pts[i];
+    if (!plane_inlier(c, p, thr)) continue;
+    cnt += 1.0;
+    acc[0] += (double)(p.x * p.x); acc[1] += (double)(p.x * p.y); acc[2] += (double)(p.x * p.z);
+    acc[3] += (double)(p.y * p.y); acc[4] += (double)(p.y * p.z); acc[5] += (double)(p.z * p.z);
+    acc[6] += (double)p.x; acc[7] += (double)p.y; acc[8] += (double)p.z;
+  }
+  for (int k = 0; k < 9; ++k) { const double v = block_sum(acc[k], red); if (threadIdx.x == 0) s_sum[k] = v; }
+  cnt = block_sum(cnt, red);
+  if (threadIdx.x != 0 || cnt < 3.0) return;   // upstream needs >= 3 inliers to refine
+  // computeMeanAndCovarianceMatrix: accu /= n; cov = E[xx^T] - mean mean^T
+  double a[9];
+  for (int k = 0; k < 9; ++k) a[k] = s_sum[k] / cnt;
+  const double mx = a[6], my = a[7], mz = a[8];
+  double A[3][3] = {{a[0] - mx * mx, a[1] - mx * my, a[2] - mx * mz}, {a[1] - mx * my, a[3] - my * my, a[4] - my * mz}, {a[2] - mx * mz, a[4] - my * mz, a[5] - mz * mz}};
+  // smallest eigenvector by Jacobi sweeps
+  double V[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+  for (int sweep = 0; sweep < 32; ++sweep) {
+    const double off = fabs(A[0][1]) + fabs(A[0][2]) + fabs(A[1][2]);
+    if (off <= 1.0e-300 || off <= 1.0e-18 * (fabs(A[0][0]) + fabs(A[1][1]) + fabs(A[2][2]))) break;
+    for (int p = 0; p < 2; ++p) for (int q = p + 1; q < 3; ++q) {
+      if (fabs(A[p][q]) <= 1.0e-300) continue;
+      const double theta = (A[q][q] - A[p][p]) / (2.0 * A[p][q]);
+      const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+      const double cs = 1.0 / sqrt(t * t + 1.0), sn = t * cs;
+      for (int k = 0; k < 3; ++k) { const double akp = A[k][p], akq = A[k][q]; A[k][p] = cs * akp - sn * akq; A[k][q] = sn * akp + cs * akq; }
+      for (int k = 0; k < 3; ++k) { const double apk = A[p][k], aqk = A[q][k]; A[p][k] = cs * apk - sn * aqk; A[q][k] = sn * apk + cs * aqk; }
+      for (int k = 0; k < 3; ++k) { const double vkp = V[k][p], vkq = V[k][q]; V[k][p] = cs * vkp - sn * vkq; V[k][q] = sn * vkp + cs * vkq; }
+    }
+  }
+  int m = 0;
+  if (A[1][1] < A[m][m]) m = 1;
+  if (A[2][2] < A[m][m]) m = 2;
+  double nx = V[0][m], ny = V[1][m], nz = V[2][m];
+  // Eigen leaves the sign of the eigenvector open: keep the side of the RANSAC normal
+  if (nx * (double)c[0] + ny * (double)c[1] + nz * (double)c[2] < 0.0) { nx = -nx; ny = -ny; nz = -nz; }
+  res->coeff[0] = (float)nx; res->coeff[1] = (float)ny; res->coeff[2] = (float)nz;
+  res->coeff[3] = -1.0f * (((float)nx * (float)mx + (float)ny * (float)my) + (float)nz * (float)mz);
+}
+
+// ExtractIndices: inliers (setNegative(false)) and the rest (setNegative(true)), both in input order (one block)
+__global__ void __launch_bounds__(1024) plane_extract_kernel(const float4* __restrict__ pts, const CloudHeader* __restrict__ hdr, double thr, PlaneResult* res,
+                                                             float4* out_in, CloudHeader* out_in_hdr, float4* out_rest, CloudHeader* out_rest_hdr) {
+  __shared__ int smem[34];
+  const int n = hdr->n;
+  const bool have = res->best >= 0;
+  const float c[4] = {res->coeff[0], res->coeff[1], res->coeff[2], res->coeff[3]};
+  auto is_in = [&](int i) -> int { return (have && plane_inlier(c, pts[i], thr)) ? 1 : 0; };
+  const int total = block_exclusive_scan<int>(
+      n, is_in,
+      [&](int i, int ex) {
+        const float4 p = pts[i];
+        if (is_in(i)) { if (out_in) out_in[ex] = p; }
+        else if (out_rest) out_rest[i - ex] = p;
+      },
+      smem);
+  if (threadIdx.x == 0) {
+    res->n_inliers = total;
+    if (out_in_hdr) out_in_hdr->n = total;
+    if (out_rest_hdr) out_rest_hdr->n = n - total;
+  }
+}
+
+// RANSAC draws when none are injected: 3 distinct indices per hypothesis from Philox-style integer hashing
+__global__ void plane_draw_kernel(const CloudHeader* __restrict__ hdr, int n_samples, unsigned long long seed, int* __restrict__ samples3) {
+  const int n = hdr->n;
+  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n_samples; s += gridDim.x * blockDim.x) {
+    unsigned long long x = seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(s + 1);
+    int idx[3];
+    for (int k = 0; k < 3; ++k) {
+      for (int tries = 0; tries < 64; ++tries) {
+        x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 27; x *= 0x94D049BB133111EBull; x ^= x >> 31;  // splitmix64
+        idx[k] = n > 0 ? (int)(x % (unsigned long long)n) : 0;
+        bool dup = false;
+        for (int q = 0; q < k; ++q) dup = dup || idx[q] == idx[k];
+        if (!dup) break;
+      }
+      samples3[3 * s + k] = idx[k];
+    }
+  }
+}
+
+}  // namespace
+}  // namespace pft
+
+extern "C" {
+
+int pft_segment_plane(pft_context* ctx, const pft_cloud* in, double distance_threshold, int max_iterations, double probability, const int32_t* samples3,
+                      int n_samples, uint64_t seed, int optimize_coefficients, float* coefficients4, int32_t* iterations, pft_cloud* plane_out,
+                      pft_cloud* rest_out, size_t* n_inliers) {
+  if (!ctx || !in) { set_last_error("pft_segment_plane: null argument"); return PFT_ERR_INVALID; }
+  if (in->ctx != ctx || (plane_out && plane_out->ctx != ctx) || (rest_out && rest_out->ctx != ctx) || plane_out == in || rest_out == in ||
+      (plane_out && plane_out == rest_out)) {
+    set_last_error("pft_segment_plane: clouds must be distinct and belong to the context");
+    return PFT_ERR_INVALID;
+  }
+  if (!(distance_threshold > 0.0) || max_iterations < 1 || !(probability > 0.0 && probability < 1.0)) {
+    set_last_error("pft_segment_plane: need distance_threshold > 0, max_iterations >= 1, 0 < probability < 1");
+    return PFT_ERR_INVALID;
+  }
+  if (samples3 && n_samples < 1) { set_last_error("pft_segment_plane: injected samples need n_samples >= 1"); return PFT_ERR_INVALID; }
+  PFT_CUDA_TRY(cudaSetDevice(ctx->device));
+  size_t n = 0;
+  int rc = pft_cloud_size(const_cast<pft_cloud*>(in), &n);
+  if (rc) return rc;
+  cudaStream_t s = ctx->stream;
+  if (plane_out && (rc = plane_out->ensure(in->capacity))) return rc;
+  if (rest_out && (rc = rest_out->ensure(in->capacity))) return rc;
+  // upstream draws until `iterations >= k`; every draw it can ever need is at most max_iterations + the skipped ones
+  const int S = samples3 ? n_samples : max_iterations + 1 + max_iterations / 8;
+  if ((rc = ctx->cl_sel.reserve((size_t)S * (3 * sizeof(int) + 4 * sizeof(float) + sizeof(int)) + sizeof(PlaneResult) + 256))) return rc;
+  PlaneResult* res = ctx->cl_sel.as<PlaneResult>();
+  int* d_samples = reinterpret_cast<int*>(res + 1);
+  float* d_coeffs = reinterpret_cast<float*>(d_samples + 3 * (size_t)S);
+  int* d_counts = reinterpret_cast<int*>(d_coeffs + 4 * (size_t)S);
+  if (samples3) PFT_CUDA_TRY(cudaMemcpyAsync(d_samples, samples3, (size_t)S * 3 * sizeof(int), cudaMemcpyHostToDevice, s));
+  else {
+    plane_draw_kernel<<<(S + 255) / 256, 256, 0, s>>>(in->d_hdr(), S, seed, d_samples);
+    PFT_LAUNCH_CHECK();
+  }
+  plane_score_kernel<<<std::min(S, ctx->sm_count * 8), 256, 0, s>>>(in->d_pts(), in->d_hdr(), d_samples, S, distance_threshold, d_coeffs, d_counts);
+  PFT_LAUNCH_CHECK();
+  plane_pick_kernel<<<1, 32, 0, s>>>(in->d_hdr(), d_coeffs, d_counts, S, max_iterations, probability, res);
+  PFT_LAUNCH_CHECK();
+  if (optimize_coefficients) {
+    plane_refine_kernel<<<1, 1024, 0, s>>>(in->d_pts(), in->d_hdr(), distance_threshold, res);
+    PFT_LAUNCH_CHECK();
+  }
+  plane_extract_kernel<<<1, 1024, 0, s>>>(in->d_pts(), in->d_hdr(), distance_threshold, res, plane_out ? plane_out->d_pts() : nullptr,
+                                          plane_out ? plane_out->d_hdr() : nullptr, rest_out ? rest_out->d_pts() : nullptr, rest_out ? rest_out->d_hdr() : nullptr);
+  PFT_LAUNCH_CHECK();
+  if (plane_out) plane_out->host_n = -1;
+  if (rest_out) rest_out->host_n = -1;
+  PlaneResult h;
+  PFT_CUDA_TRY(cudaMemcpyAsync(&h, res, sizeof(h), cudaMemcpyDeviceToHost, s));
+  PFT_CUDA_TRY(cudaStreamSynchronize(s));
+  if (coefficients4) memcpy(coefficients4, h.coeff, sizeof(h.coeff));
+  if (iterations) *iterations = h.iterations;
+  if (n_inliers) *n_inliers = (size_t)h.n_inliers;
+  ctx->cl_src = nullptr;  // (the clustering scratch was reused)
+  if (h.best < 0) { set_last_error("pft_segment_plane: no valid plane hypothesis among the %d samples", S); return PFT_ERR_STATE; }
   return PFT_OK;
 }
 

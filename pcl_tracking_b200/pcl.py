@@ -203,6 +203,60 @@ class EuclideanClusterExtraction:
         return out
 
 
+class SACSegmentation:
+    """pcl::SACSegmentation<PointXYZRGBA> configured as the model builder's plane variant does (SACMODEL_PLANE, SAC_RANSAC;
+    ref: src/create_model_planar_segmentation.cpp:157-163) fused with the two pcl::ExtractIndices passes that follow it
+    (ref :166-174): segment() returns (coefficients[4], inlier count) and leaves the plane / everything-else clouds in
+    .plane and .rest.  setSamples() injects the RANSAC draws (rows of three point indices), otherwise they are generated
+    on the device from setSeed()."""
+
+    def __init__(self, ctx=None):
+        self.ctx = ctx or Context.default()
+        self._thr, self._max_it, self._prob, self._opt, self._in = 0.0, 50, 0.99, True, None
+        self._samples, self._seed = None, 0x5EED
+        self.plane, self.rest, self.iterations = None, None, 0
+
+    def setModelType(self, model="SACMODEL_PLANE"):
+        if model not in ("SACMODEL_PLANE", 0):
+            raise NotImplementedError("only SACMODEL_PLANE is on the reference's path")
+
+    def setMethodType(self, method="SAC_RANSAC"):
+        if method not in ("SAC_RANSAC", 0):
+            raise NotImplementedError("only SAC_RANSAC is on the reference's path")
+
+    def setMaxIterations(self, n):
+        self._max_it = int(n)
+
+    def setDistanceThreshold(self, t):
+        self._thr = float(t)
+
+    def setProbability(self, p):
+        self._prob = float(p)
+
+    def setOptimizeCoefficients(self, on):
+        self._opt = bool(on)
+
+    def setSamples(self, samples3):
+        self._samples = None if samples3 is None else np.ascontiguousarray(samples3, dtype=np.int32).reshape(-1, 3)
+
+    def setSeed(self, seed):
+        self._seed = int(seed)
+
+    def setInputCloud(self, cloud):
+        self._in = cloud
+
+    def segment(self):
+        coeff = np.zeros(4, dtype=np.float32)
+        it, n_in = C.c_int32(), C.c_size_t()
+        self.plane, self.rest = PointCloud(ctx=self.ctx), PointCloud(ctx=self.ctx)
+        s = self._samples
+        check(capi.load().pft_segment_plane(self.ctx._h, self._in._h, self._thr, self._max_it, self._prob, ptr(s) if s is not None else None,
+                                            len(s) if s is not None else 0, self._seed, 1 if self._opt else 0, ptr(coeff), C.byref(it),
+                                            self.plane._h, self.rest._h, C.byref(n_in)))
+        self.iterations = it.value
+        return coeff, n_in.value
+
+
 class VoxelGrid:
     """pcl::VoxelGrid / pcl::ApproximateVoxelGrid (ref: src/auto_tracking.cpp:553-557, :568-571): one
     centroid per occupied voxel of the lattice floor(coord / leaf).  setPassThrough() folds the

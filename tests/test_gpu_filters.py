@@ -246,3 +246,60 @@ def test_euclidean_clusters_edge_cases():
     assert [c.tolist() for c in ec.extract()] == [[0]]
     with pytest.raises(pcl.capi.PftError):
         ec.setClusterTolerance(0.0); ec.extract()
+
+
+def _plane_scene(seed, n_plane=30000, n_obj=6000):
+    rng = np.random.default_rng(seed)
+    xy = rng.uniform(-1, 1, (n_plane, 2))
+    plane = np.c_[xy, 0.25 * xy[:, 0] + 0.4 * xy[:, 1] + 1.2 + rng.normal(0, 0.004, n_plane)]
+    objs = [rng.uniform(-0.5, 0.5, (n_obj // 3, 3)) * [0.2, 0.2, 0.15] + [cx, cy, 0.25 * cx + 0.4 * cy + 1.2 - 0.12] for cx, cy in ((-0.4, 0.1), (0.2, -0.3), (0.5, 0.5))]
+    xyz = np.concatenate([plane] + objs).astype(np.float32)
+    xyz = xyz[rng.permutation(len(xyz))]
+    xyz[rng.random(len(xyz)) < 0.01, 0] = np.nan
+    return oracle.make_points(xyz, rng.integers(0, 1 << 32, len(xyz), dtype=np.uint64).astype(np.uint32)), rng
+
+
+@pytest.mark.parametrize("seed,optimize", [(1, False), (2, False), (3, True), (4, True)])
+def test_segment_plane_matches_oracle(seed, optimize):
+    """Plane variant of the model builder (ref: src/create_model_planar_segmentation.cpp:157-174): same winning draw,
+    same iteration count, same plane / rest split as the sequential RANSAC restatement for the same draws."""
+    pts, rng = _plane_scene(seed)
+    samples = rng.integers(0, len(pts), (1126, 3)).astype(np.int32)
+    samples[3] = (7, 7, 11)                                     # degenerate draws are skipped
+    want = oracle.segment_plane(pts, samples, 0.015, 1000, 0.99, optimize)
+    seg = pcl.SACSegmentation()
+    seg.setModelType("SACMODEL_PLANE"); seg.setMethodType("SAC_RANSAC"); seg.setMaxIterations(1000); seg.setDistanceThreshold(0.015)
+    seg.setOptimizeCoefficients(optimize); seg.setSamples(samples); seg.setInputCloud(pcl.PointCloud(pts))
+    coeff, n_in = seg.segment()
+    assert seg.iterations == want["iterations"]
+    if not optimize:
+        assert np.array_equal(coeff.view(np.uint32), want["coeff"].view(np.uint32))      # the winning hypothesis, bit for bit
+        m = want["inliers"]
+    else:
+        np.testing.assert_allclose(coeff, want["coeff"], atol=2e-6)                      # fp64 sums + eigen-solve on both sides
+        # points whose distance is within 1e-5 of the threshold may fall either way
+        x, y, z = pts["x"].astype(np.float64), pts["y"].astype(np.float64), pts["z"].astype(np.float64)
+        with np.errstate(invalid="ignore"):
+            d = np.abs(coeff[0] * x + coeff[1] * y + coeff[2] * z + coeff[3])
+        m = want["inliers"]
+        sure = np.abs(d - 0.015) > 1e-5
+        got_mask = d < 0.015
+        assert np.array_equal(got_mask[sure], m[sure])
+        m = None
+    plane, rest = seg.plane.to_numpy(), seg.rest.to_numpy()
+    assert len(plane) == n_in and len(plane) + len(rest) == len(pts)
+    if m is not None:
+        assert np.array_equal(_bits(plane), _bits(pts[m])) and np.array_equal(_bits(rest), _bits(pts[~m]))
+    assert n_in > 0.95 * 30000 * 0.99 and n_in < 30000 + 3000                            # the table, not the objects
+
+
+def test_segment_plane_feeds_the_clustering():
+    """The whole plane variant of create_model: plane removal, then Euclidean clustering of what is left -> 3 objects."""
+    pts, rng = _plane_scene(9)
+    seg = pcl.SACSegmentation()
+    seg.setMaxIterations(1000); seg.setDistanceThreshold(0.015); seg.setSeed(42); seg.setInputCloud(pcl.PointCloud(pts))
+    coeff, n_in = seg.segment()
+    assert abs(abs(coeff[2]) - 1.0 / np.sqrt(1 + 0.25 ** 2 + 0.4 ** 2)) < 5e-3
+    ec = pcl.EuclideanClusterExtraction()
+    ec.setClusterTolerance(0.02); ec.setMinClusterSize(500); ec.setMaxClusterSize(25000); ec.setInputCloud(seg.rest)
+    assert len(ec.extract()) == 3

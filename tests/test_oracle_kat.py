@@ -391,3 +391,27 @@ def test_euclidean_clusters_known_answer():
     assert (np.float32(0.02) * np.float32(0.02) < np.float32(0.02 * 0.02)) == (oracle.euclidean_clusters(pair, 0.02, 2, 10)[1].tolist() == [2])
     # max_size drops oversized components
     assert oracle.euclidean_clusters(oracle.make_points(xyz), 0.02, 10, 35)[1].tolist() == [30]
+
+
+def test_segment_plane_known_answer():
+    """SACSegmentation(PLANE, RANSAC) restatement (ref: src/create_model_planar_segmentation.cpp:157-163): a noisy plane
+    z = 0.3 x - 0.2 y + 1 under a blob of object points."""
+    rng = np.random.default_rng(0)
+    n = 4000
+    xy = rng.uniform(-1, 1, (n, 2))
+    plane = np.c_[xy, 0.3 * xy[:, 0] - 0.2 * xy[:, 1] + 1.0 + rng.normal(0, 0.003, n)]
+    blob = rng.uniform(-0.3, 0.3, (1200, 3)) + [0, 0, 1.5]
+    pts = oracle.make_points(np.r_[plane, blob].astype(np.float32))
+    samples = rng.integers(0, len(pts), (1001, 3))
+    samples[0] = (5, 5, 9)                                      # a degenerate draw: skipped, not an iteration
+    r = oracle.segment_plane(pts, samples, 0.015, 1000, 0.99, True)
+    want = np.array([-0.3, 0.2, 1.0, -1.0]) / np.linalg.norm([0.3, 0.2, 1.0])
+    c = r["coeff"].astype(np.float64)
+    c = c if c[2] > 0 else -c
+    np.testing.assert_allclose(c, want, atol=2e-3)
+    assert r["inliers"][:n].mean() > 0.995 and r["inliers"][n:].mean() < 0.12
+    # the adaptive stop: with ~77 % inliers k = log(0.01) / log(1 - 0.77^3) ~ 8 iterations, far below the 1000 allowed
+    assert 3 <= r["iterations"] <= 40
+    # without refinement the coefficients are those of the winning sample
+    r0 = oracle.segment_plane(pts, samples, 0.015, 1000, 0.99, False)
+    assert r0["best"] == r["best"] and np.array_equal(r0["coeff"], r["ransac_coeff"])
