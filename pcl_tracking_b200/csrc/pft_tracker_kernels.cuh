@@ -1073,11 +1073,19 @@ __global__ void __launch_bounds__(256) cand_build_kernel(const IndexHeader* __re
       continue;
     }
     // ---- (3) each needed fine cell filters the superset with its own bound and bisector test
+    unsigned int sub_mask;  // which of the block's 8 cells are needed: one load per lane instead of eight serial ones
+    {
+      bool mine = false;
+      if (lane < 8) {
+        const int fx = 2 * bx + (lane & 1), fy = 2 * by + ((lane >> 1) & 1), fz = 2 * bz + (lane >> 2);
+        mine = fx < fdx && fy < fdy && fz < fdz && needed[(fz * fdy + fy) * fdx + fx] != 0u;
+      }
+      sub_mask = __ballot_sync(kFull, mine);
+    }
     for (int sub = 0; sub < 8; ++sub) {
+      if (!((sub_mask >> sub) & 1u)) continue;
       const int fx = 2 * bx + (sub & 1), fy = 2 * by + ((sub >> 1) & 1), fz = 2 * bz + (sub >> 2);
-      if (fx >= fdx || fy >= fdy || fz >= fdz) continue;
       const int cell = (fz * fdy + fy) * fdx + fx;
-      if (!needed[cell]) continue;
       float flo[3], fhi[3], fc[3], fh[3];
       flo[0] = (float)(h.f_origin[0] + fx) * leaf - margin; fhi[0] = (float)(h.f_origin[0] + fx + 1) * leaf + margin;
       flo[1] = (float)(h.f_origin[1] + fy) * leaf - margin; fhi[1] = (float)(h.f_origin[1] + fy + 1) * leaf + margin;
@@ -1096,12 +1104,19 @@ __global__ void __launch_bounds__(256) cand_build_kernel(const IndexHeader* __re
       }
       const float Uf2 = fminf(m2 * 1.00002f, r_max * r_max);
       const float4 pf = spt[mi];
-      // count, choose the destination, write (ballot compaction: the order of a list is the order of the superset)
+      // count, choose the destination, write (ballot compaction: the order of a list is the order of the superset).
+      // The keep test is evaluated once; its ballots (ns <= kSuperCap = 8 x 32) stay in registers for the write pass.
       int n = 0;
-      for (int t0 = 0; t0 < ns; t0 += 32) {
-        const int t = t0 + lane;
-        const bool keep = t < ns && box_mindist2(flo, fhi, spt[t]) <= Uf2 && can_win(spt[t], pf, fc, fh);
-        n += __popc(__ballot_sync(kFull, keep));
+      unsigned int keep_bal[kSuperCap / 32];
+#pragma unroll
+      for (int q = 0; q < kSuperCap / 32; ++q) {
+        keep_bal[q] = 0u;
+        if (q * 32 < ns) {
+          const int t = q * 32 + lane;
+          const bool keep = t < ns && box_mindist2(flo, fhi, spt[t]) <= Uf2 && can_win(spt[t], pf, fc, fh);
+          keep_bal[q] = __ballot_sync(kFull, keep);
+          n += __popc(keep_bal[q]);
+        }
       }
       unsigned short* list = flists + (size_t)cell * kListK;
       unsigned short* dst = list + 1;
@@ -1117,11 +1132,10 @@ __global__ void __launch_bounds__(256) cand_build_kernel(const IndexHeader* __re
         if (lane == 0) { list[1] = (unsigned short)(xi & 0xffff); list[2] = (unsigned short)(xi >> 16); list[3] = (unsigned short)n; }
       }
       int w = 0;
-      for (int t0 = 0; t0 < ns; t0 += 32) {
-        const int t = t0 + lane;
-        const bool keep = t < ns && box_mindist2(flo, fhi, spt[t]) <= Uf2 && can_win(spt[t], pf, fc, fh);
-        const unsigned int bal = __ballot_sync(kFull, keep);
-        if (keep) dst[w + __popc(bal & ((1u << lane) - 1u))] = sslot[t];
+#pragma unroll
+      for (int q = 0; q < kSuperCap / 32; ++q) {
+        const unsigned int bal = keep_bal[q];
+        if ((bal >> lane) & 1u) dst[w + __popc(bal & ((1u << lane) - 1u))] = sslot[q * 32 + lane];
         w += __popc(bal);
       }
       // pad to whole 16-byte groups with the dummy slot (the lookup reads whole groups unconditionally; a regular record
