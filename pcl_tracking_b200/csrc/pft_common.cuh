@@ -110,6 +110,27 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
   return v;
 }
 
+// Six block-wide sums at once (same association order as six block_sum calls, two barriers instead of twelve);
+// results valid in thread 0.  `red6` holds >= 192 doubles.
+__device__ __forceinline__ void block_sum6(double* v, double* red6) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int d = 0; d < 6; ++d) v[d] = warp_sum(v[d]);
+  __syncthreads();
+  if (lane == 0) {
+#pragma unroll
+    for (int d = 0; d < 6; ++d) red6[wid * 6 + d] = v[d];
+  }
+  __syncthreads();
+  if (wid == 0) {
+#pragma unroll
+    for (int d = 0; d < 6; ++d) {
+      double t = lane < nw ? red6[lane * 6 + d] : 0.0;
+      v[d] = warp_sum(t);
+    }
+  }
+}
+
 // Exclusive scan over n values produced by `load(i)`, written through `store(i, exclusive_prefix)`,
 // executed by ONE thread block (any size that is a multiple of 32, <= 1024).  Returns the grand
 // total to every thread.  Integer types only: the result is independent of the association order,

@@ -1442,6 +1442,7 @@ normalize_kernel(TrackerState* st, DevParticle* parts, const float* raw, double 
   __shared__ double red[32];
   __shared__ double s_part[3];  // this CTA's partial min, max, sum (read by the other CTAs of the cluster)
   __shared__ double s_upd[6];   // fused update(): this CTA's partial weighted state
+  __shared__ double red6[192];
   if (peer_window) {
     if (crank == 0 && threadIdx.x == 0) peer_wait(&peer_window->flag_raw, st->peer_epoch * (unsigned int)nranks, &st->peer_error);
     cluster.sync();
@@ -1469,13 +1470,13 @@ normalize_kernel(TrackerState* st, DevParticle* parts, const float* raw, double 
   }
   if (partial) raw = raw_out;  // (every thread re-reads only the slots it has just written)
   for (int o = 16; o > 0; o >>= 1) { wmin = fmin(wmin, __shfl_xor_sync(kFull, wmin, o)); wmax = fmax(wmax, __shfl_xor_sync(kFull, wmax, o)); }
-  if (lane == 0) red[wid] = wmin;
+  if (lane == 0) { red[wid] = wmin; red6[wid] = wmax; }
   __syncthreads();
-  if (threadIdx.x == 0) { double v = DBL_MAX; for (int k = 0; k < nw; ++k) v = fmin(v, red[k]); s_part[0] = v; }
-  __syncthreads();
-  if (lane == 0) red[wid] = wmax;
-  __syncthreads();
-  if (threadIdx.x == 0) { double v = -DBL_MAX; for (int k = 0; k < nw; ++k) v = fmax(v, red[k]); s_part[1] = v; }
+  if (threadIdx.x < 2) {  // thread 0: minimum, thread 1: maximum of the per-warp values
+    double v = threadIdx.x ? -DBL_MAX : DBL_MAX;
+    for (int k = 0; k < nw; ++k) v = threadIdx.x ? fmax(v, red6[k]) : fmin(v, red[k]);
+    s_part[threadIdx.x] = v;
+  }
   cluster.sync();
   wmin = DBL_MAX; wmax = -DBL_MAX;
   for (int r = 0; r < CTAS; ++r) {
@@ -1513,8 +1514,11 @@ normalize_kernel(TrackerState* st, DevParticle* parts, const float* raw, double 
     }
   }
   if (fuse_update) {
+    block_sum6(acc, red6);
+    if (threadIdx.x == 0) {
 #pragma unroll
-    for (int d = 0; d < 6; ++d) { const double v = block_sum(acc[d], red); if (threadIdx.x == 0) s_upd[d] = v; }
+      for (int d = 0; d < 6; ++d) s_upd[d] = acc[d];
+    }
     cluster.sync();
     if (crank == 0 && threadIdx.x == 0) {
       double tot[6] = {0, 0, 0, 0, 0, 0};
@@ -1537,7 +1541,7 @@ __global__ void __cluster_dims__(CTAS, 1, 1) __launch_bounds__(1024)
 update_kernel(TrackerState* st, const DevParticle* __restrict__ parts, const CloudHeader* __restrict__ scene_hdr) {
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned int crank = cluster.block_rank();
-  __shared__ double red[32];
+  __shared__ double red6[192];
   __shared__ double s_part[6];
   if (scene_hdr->n <= 0) return;
   const int n = st->particle_num;
@@ -1548,8 +1552,11 @@ update_kernel(TrackerState* st, const DevParticle* __restrict__ parts, const Clo
     acc[0] += (double)(float)((double)p.x * w); acc[1] += (double)(float)((double)p.y * w); acc[2] += (double)(float)((double)p.z * w);
     acc[3] += (double)(float)((double)p.roll * w); acc[4] += (double)(float)((double)p.pitch * w); acc[5] += (double)(float)((double)p.yaw * w);
   }
+  block_sum6(acc, red6);
+  if (threadIdx.x == 0) {
 #pragma unroll
-  for (int d = 0; d < 6; ++d) { const double v = block_sum(acc[d], red); if (threadIdx.x == 0) s_part[d] = v; }
+    for (int d = 0; d < 6; ++d) s_part[d] = acc[d];
+  }
   cluster.sync();
   if (crank == 0 && threadIdx.x == 0) {
     double tot[6] = {0, 0, 0, 0, 0, 0};
