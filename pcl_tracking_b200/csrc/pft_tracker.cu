@@ -606,7 +606,8 @@ int weight_phase_eval(pft_tracker* t, bool force_raw = false) {
   a.partial = t->partial.as<double>(); a.chunks = t->chunks; a.chunk_len = t->chunk_len; a.n_max = t->n_cap;
   a.nranks = t->nranks; a.rank_id = t->rank;
   // many items per warp (large particle sets): dynamic hand-out; few: static interleaved split (see weight_items)
-  const bool dyn = (long long)std::max(1, (t->particle_num > 0 ? t->particle_num : t->n_cap) / t->nranks) * t->chunks >= 12ll * sm * (kWeightThreads / 32);
+  static const long long dyn_per_warp = [] { const char* e = getenv("PFT_DYN_ITEMS_PER_WARP"); const int v = e ? atoi(e) : 0; return (long long)(v > 0 ? v : 5); }();  // tuning knob (measured: dynamic wins from ~5 items per warp up, 10k-25k particles -7 %)
+  const bool dyn = (long long)std::max(1, (t->particle_num > 0 ? t->particle_num : t->n_cap) / t->nranks) * t->chunks >= dyn_per_warp * sm * (kWeightThreads / 32);
   a.co = make_coherence(t);
   a.dbg_k = t->debug_nn; a.dbg_idx = t->dbg_idx.as<int>(); a.dbg_d2 = t->dbg_d2.as<float>();
   const int local_cap = t->slice_cap();
