@@ -15,7 +15,7 @@
 namespace pft {
 
 static thread_local char g_err[512] = "";
-unsigned long long g_launch_count = 0;
+std::atomic<unsigned long long> g_launch_count{0};
 
 void set_last_error(const char* fmt, ...) {
   va_list ap;
@@ -126,7 +126,7 @@ int pft_host_free(void* ptr) {
   return PFT_OK;
 }
 
-uint64_t pft_kernel_launch_count(void) { return (uint64_t)g_launch_count; }
+uint64_t pft_kernel_launch_count(void) { return (uint64_t)g_launch_count.load(); }
 
 // ------------------------------------------------------------------ clouds
 int pft_cloud_create(pft_context* ctx, pft_cloud** out) {

@@ -317,7 +317,13 @@ int pft_euclidean_clusters(pft_context* ctx, const pft_cloud* in, double toleran
 int pft_cloud_select_cluster(pft_context* ctx, const pft_cloud* in, int k, pft_cloud* out) {
   if (!ctx || !in || !out) { set_last_error("pft_cloud_select_cluster: null argument"); return PFT_ERR_INVALID; }
   if (in->ctx != ctx || out->ctx != ctx || in == out) { set_last_error("pft_cloud_select_cluster: clouds must be distinct and belong to the context"); return PFT_ERR_INVALID; }
-  if (ctx->cl_src != in || !ctx->cl_work.p) { set_last_error("pft_cloud_select_cluster: call pft_euclidean_clusters on this cloud first"); return PFT_ERR_STATE; }
+  size_t n_now = 0;
+  int rc0 = pft_cloud_size(const_cast<pft_cloud*>(in), &n_now);
+  if (rc0) return rc0;
+  if (ctx->cl_src != in || !ctx->cl_work.p || n_now != ctx->cl_n) {
+    set_last_error("pft_cloud_select_cluster: call pft_euclidean_clusters on this cloud first (the labels on the device belong to another cloud)");
+    return PFT_ERR_STATE;
+  }
   if (k < 0 || k >= ctx->cl_count) { set_last_error("pft_cloud_select_cluster: cluster %d of %d", k, ctx->cl_count); return PFT_ERR_INVALID; }
   PFT_CUDA_TRY(cudaSetDevice(ctx->device));
   int rc = out->ensure(in->capacity);

@@ -10,6 +10,8 @@
 #include <stdint.h>
 #include <float.h>
 
+#include <atomic>
+
 namespace pft {
 
 constexpr int kWarp = 32;
@@ -17,7 +19,7 @@ constexpr unsigned kFull = 0xffffffffu;
 
 // ------------------------------------------------------------------ error plumbing (host)
 void set_last_error(const char* fmt, ...);
-extern unsigned long long g_launch_count;
+extern std::atomic<unsigned long long> g_launch_count;  // (trackers of distinct contexts may be driven from distinct threads)
 #define PFT_CUDA_TRY(expr)                                                                         \
   do {                                                                                             \
     cudaError_t _e = (expr);                                                                       \

@@ -925,10 +925,10 @@ static int compute_one(pft_tracker* t) {
         const unsigned long long version = t->config_version;
         cudaGraph_t graph = nullptr;
         PFT_CUDA_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-        const unsigned long long launches_before = g_launch_count;
+        const unsigned long long launches_before = g_launch_count.load();
         rc = enqueue_tracking(t);
         cudaError_t ce = cudaStreamEndCapture(s, &graph);
-        g_launch_count = launches_before;  // captured, not launched
+        g_launch_count -= g_launch_count.load() - launches_before;  // captured, not launched (other threads' launches keep counting)
         if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
         if (ce != cudaSuccess) { set_last_error("graph capture failed: %s", cudaGetErrorString(ce)); cudaGetLastError(); return PFT_ERR_CUDA; }
         size_t n_nodes = 0;
