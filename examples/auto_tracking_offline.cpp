@@ -2,10 +2,10 @@
 //
 // initialize_trackers() and cloud_cb() of ref: src/auto_tracking.cpp:181-259, :597-727, written against
 // include/pft/pcl_shim.hpp (PCL class names over the C ABI).  The ROS subscriber / service / visualiser
-// parts of that file are out of scope; frames and the object model come from raw files of 32-byte
-// pcl::PointXYZRGBA records (written by tests/test_gpu_shim.py or any PCD-to-raw converter).
+// parts of that file are out of scope; frames and the object model come from .pcd files (ASCII or binary, as the
+// model builder writes them, ref: src/create_model.cpp:209-230) or from raw files of 32-byte pcl::PointXYZRGBA records.
 //
-// usage: auto_tracking_offline <model.raw> <seed> <frame0.raw> [frame1.raw ...]
+// usage: auto_tracking_offline <model.pcd|raw> <seed> <frame0.pcd|raw> [frame1 ...]
 // prints one line per frame: frame index, particle count, result x y z roll pitch yaw
 #include <cstdio>
 #include <cstdlib>
@@ -20,6 +20,12 @@ typedef pcl::PointCloud<RefPointType> Cloud;
 typedef pcl::tracking::KLDAdaptiveParticleFilterOMPTracker<RefPointType, ParticleT> Tracker;
 
 static Cloud::Ptr load_raw(const char* path) {
+  const std::string p(path);
+  if (p.size() > 4 && p.compare(p.size() - 4, 4, ".pcd") == 0) {
+    Cloud::Ptr c(new Cloud());
+    if (pcl::io::loadPCDFile(p, *c) != 0) { std::fprintf(stderr, "cannot read %s as a PCD file\n", path); std::exit(2); }
+    return c;
+  }
   FILE* f = std::fopen(path, "rb");
   if (!f) { std::fprintf(stderr, "cannot open %s\n", path); std::exit(2); }
   std::fseek(f, 0, SEEK_END);

@@ -17,8 +17,12 @@
 
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <fstream>
 #include <memory>
+#include <sstream>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -178,6 +182,123 @@ class VoxelGrid {
   float leaf_ = 0.01f;
 };
 template <typename PointT> using ApproximateVoxelGrid = VoxelGrid<PointT>;
+
+// pcl::io::loadPCDFile / savePCDFile* / pcl::PCDWriter::write for PointXYZRGBA clouds (PCD v0.7, DATA ascii | binary):
+// the model builder writes one models/<time>/<k>.pcd per cluster with writer.write(path, cloud, false)
+// (ref: src/create_model.cpp:209-230); offline runs replay frames stored as PCD files.  Fields x, y, z (float32)
+// plus rgba (uint32) or rgb (the same bytes as a float32); other fields are skipped.  Host-side only.
+namespace io {
+namespace detail {
+struct PcdField { std::string name; int size = 4; char type = 'F'; int count = 1; };
+inline double pcd_number(const std::string& tok) { return std::strtod(tok.c_str(), nullptr); }  // accepts nan / inf
+}  // namespace detail
+
+template <typename PointT>
+int loadPCDFile(const std::string& path, PointCloud<PointT>& cloud) {
+  std::ifstream f(path, std::ios::binary);
+  if (!f) return -1;
+  std::vector<detail::PcdField> fields;
+  uint32_t width = 0, height = 1;
+  size_t points = 0;
+  std::string data, line;
+  bool have_points = false;
+  while (std::getline(f, line)) {
+    if (!line.empty() && line.back() == '\r') line.pop_back();
+    if (line.empty() || line[0] == '#') continue;
+    std::istringstream ls(line);
+    std::string key;
+    ls >> key;
+    std::vector<std::string> vals;
+    for (std::string v; ls >> v;) vals.push_back(v);
+    if (key == "FIELDS") { fields.resize(vals.size()); for (size_t i = 0; i < vals.size(); ++i) fields[i].name = vals[i]; }
+    else if (key == "SIZE") { for (size_t i = 0; i < vals.size() && i < fields.size(); ++i) fields[i].size = std::atoi(vals[i].c_str()); }
+    else if (key == "TYPE") { for (size_t i = 0; i < vals.size() && i < fields.size(); ++i) fields[i].type = vals[i][0]; }
+    else if (key == "COUNT") { for (size_t i = 0; i < vals.size() && i < fields.size(); ++i) fields[i].count = std::atoi(vals[i].c_str()); }
+    else if (key == "WIDTH" && !vals.empty()) width = (uint32_t)std::strtoul(vals[0].c_str(), nullptr, 10);
+    else if (key == "HEIGHT" && !vals.empty()) height = (uint32_t)std::strtoul(vals[0].c_str(), nullptr, 10);
+    else if (key == "POINTS" && !vals.empty()) { points = (size_t)std::strtoull(vals[0].c_str(), nullptr, 10); have_points = true; }
+    else if (key == "DATA" && !vals.empty()) { data = vals[0]; break; }
+  }
+  const size_t n = (size_t)width * height;
+  if (data.empty() || fields.empty() || (have_points && points != n)) return -1;
+  int ix = -1, iy = -1, iz = -1, ic = -1;
+  size_t stride = 0;
+  std::vector<size_t> offs(fields.size());
+  size_t cols = 0;
+  std::vector<size_t> col0(fields.size());
+  for (size_t i = 0; i < fields.size(); ++i) {
+    offs[i] = stride; col0[i] = cols;
+    stride += (size_t)fields[i].size * fields[i].count; cols += (size_t)fields[i].count;
+    if (fields[i].count != 1 || fields[i].size != 4) continue;
+    if (fields[i].name == "x") ix = (int)i; else if (fields[i].name == "y") iy = (int)i; else if (fields[i].name == "z") iz = (int)i;
+    else if (fields[i].name == "rgba" || (fields[i].name == "rgb" && ic < 0)) ic = (int)i;
+  }
+  if (ix < 0 || iy < 0 || iz < 0) return -1;
+  cloud.points.assign(n, PointT());
+  if (data == "binary") {
+    std::vector<char> rec(stride);
+    for (size_t p = 0; p < n; ++p) {
+      if (!f.read(rec.data(), (std::streamsize)stride)) return -1;
+      PointT& q = cloud.points[p];
+      std::memcpy(&q.x, rec.data() + offs[ix], 4); std::memcpy(&q.y, rec.data() + offs[iy], 4); std::memcpy(&q.z, rec.data() + offs[iz], 4);
+      if (ic >= 0) std::memcpy(&q.rgba, rec.data() + offs[ic], 4);
+    }
+  } else if (data == "ascii") {
+    for (size_t p = 0; p < n; ++p) {
+      do { if (!std::getline(f, line)) return -1; } while (line.empty());
+      std::istringstream ls(line);
+      std::vector<std::string> tok;
+      for (std::string v; ls >> v;) tok.push_back(v);
+      if (tok.size() < cols) return -1;
+      PointT& q = cloud.points[p];
+      q.x = (float)detail::pcd_number(tok[col0[ix]]); q.y = (float)detail::pcd_number(tok[col0[iy]]); q.z = (float)detail::pcd_number(tok[col0[iz]]);
+      if (ic >= 0) {
+        if (fields[ic].type == 'F') { const float c = (float)detail::pcd_number(tok[col0[ic]]); std::memcpy(&q.rgba, &c, 4); }  // packed colour printed as a float
+        else q.rgba = (uint32_t)std::strtoul(tok[col0[ic]].c_str(), nullptr, 10);
+      }
+    }
+  } else {
+    return -1;  // binary_compressed is not supported
+  }
+  cloud.width = width; cloud.height = height;
+  cloud.touch();
+  return 0;
+}
+
+template <typename PointT>
+int savePCDFile(const std::string& path, const PointCloud<PointT>& cloud_in, bool binary_mode = false) {
+  PointCloud<PointT> cloud(cloud_in);  // (downloads a device-only cloud)
+  std::ofstream f(path, std::ios::binary);
+  if (!f) return -1;
+  const size_t n = cloud.points.size();
+  const bool organised = (size_t)cloud.width * cloud.height == n && cloud.height > 1;
+  f << "# .PCD v0.7 - Point Cloud Data file format\nVERSION 0.7\nFIELDS x y z rgba\nSIZE 4 4 4 4\nTYPE F F F U\nCOUNT 1 1 1 1\n"
+    << "WIDTH " << (organised ? cloud.width : (uint32_t)n) << "\nHEIGHT " << (organised ? cloud.height : 1u) << "\nVIEWPOINT 0 0 0 1 0 0 0\nPOINTS " << n
+    << "\nDATA " << (binary_mode ? "binary" : "ascii") << "\n";
+  for (size_t p = 0; p < n; ++p) {
+    const PointT& q = cloud.points[p];
+    if (binary_mode) {
+      f.write(reinterpret_cast<const char*>(&q.x), 4); f.write(reinterpret_cast<const char*>(&q.y), 4); f.write(reinterpret_cast<const char*>(&q.z), 4);
+      f.write(reinterpret_cast<const char*>(&q.rgba), 4);
+    } else {
+      char buf[128];
+      auto num = [](float v, char* out) { if (std::isnan(v)) std::strcpy(out, "nan"); else if (std::isinf(v)) std::strcpy(out, v > 0 ? "inf" : "-inf"); else std::snprintf(out, 32, "%.9g", (double)v); };
+      char a[32], b[32], c[32];
+      num(q.x, a); num(q.y, b); num(q.z, c);
+      std::snprintf(buf, sizeof(buf), "%s %s %s %u\n", a, b, c, (unsigned)q.rgba);
+      f << buf;
+    }
+  }
+  return f ? 0 : -1;
+}
+template <typename PointT> int savePCDFileASCII(const std::string& path, const PointCloud<PointT>& c) { return savePCDFile(path, c, false); }
+template <typename PointT> int savePCDFileBinary(const std::string& path, const PointCloud<PointT>& c) { return savePCDFile(path, c, true); }
+}  // namespace io
+
+// pcl::PCDWriter (ref: src/create_model.cpp:209-223: writer.write<PointType>(path, *cloud_cluster, false))
+struct PCDWriter {
+  template <typename PointT> int write(const std::string& path, const PointCloud<PointT>& cloud, bool binary = false) { return io::savePCDFile(path, cloud, binary); }
+};
 
 // pcl::PointIndices + pcl::EuclideanClusterExtraction as the model builder uses them (ref: src/create_model.cpp:169-179)
 struct PointIndices { std::vector<int> indices; };

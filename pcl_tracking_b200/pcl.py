@@ -716,6 +716,19 @@ def comm_unique_id():
     return bytes(buf.raw)
 
 
+def loadPCDFile(path, ctx=None):
+    """pcl::io::loadPCDFile<PointXYZRGBA> -> device cloud (host-side parsing in pcd.py)."""
+    from . import pcd
+    pts, _, _ = pcd.loadPCDFile(path)
+    return PointCloud(pts, ctx=ctx)
+
+
+def savePCDFile(path, cloud, binary=False):
+    """pcl::PCDWriter::write(path, cloud, binary) (ref: src/create_model.cpp:223): `cloud` is a PointCloud or a point array."""
+    from . import pcd
+    pcd.savePCDFile(path, cloud.to_numpy() if isinstance(cloud, PointCloud) else cloud, binary=binary)
+
+
 def compute_batch(trackers):
     """compute() of several trackers that share one scene (ref :688-697)."""
     arr = (C.c_void_p * len(trackers))(*[t._h for t in trackers])

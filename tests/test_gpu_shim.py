@@ -52,3 +52,27 @@ def test_offline_driver_matches_python_path(tmp_path):
         got = np.array([float(v) for v in lines[k][2:8]], dtype=np.float32)
         want = np.array([r[n] for n in ("x", "y", "z", "roll", "pitch", "yaw")], dtype=np.float32)
         assert np.array_equal(got, want), (k, got, want)
+
+
+def test_offline_driver_reads_pcd_files(tmp_path):
+    """BASELINE configs[0]: auto_tracking offline from PCD -- the driver fed with .pcd files (ASCII model as the model
+    builder writes it, binary frames) prints the same poses as with raw records."""
+    exe = build_driver()
+    objs = synth.default_objects(1)
+    frames = [synth.render(f, objs)[0] for f in range(2)]
+    pts0, oid0 = synth.render(0, objs)
+    raw_model = synth.model_points(pts0, oid0, 0)
+    (tmp_path / "model.raw").write_bytes(synth.to_pcl32(raw_model).tobytes())
+    pcl.savePCDFile(tmp_path / "model.pcd", raw_model, binary=False)      # ref: src/create_model.cpp:223 (ASCII)
+    raw_names, pcd_names = [], []
+    for k, f in enumerate(frames):
+        (tmp_path / ("frame%d.raw" % k)).write_bytes(synth.to_pcl32(f).tobytes())
+        pcl.savePCDFile(tmp_path / ("frame%d.pcd" % k), f, binary=True)
+        raw_names.append(str(tmp_path / ("frame%d.raw" % k)))
+        pcd_names.append(str(tmp_path / ("frame%d.pcd" % k)))
+    a = subprocess.run([exe, str(tmp_path / "model.raw"), "77"] + raw_names, capture_output=True, text=True, check=True).stdout
+    b = subprocess.run([exe, str(tmp_path / "model.pcd"), "77"] + pcd_names, capture_output=True, text=True, check=True).stdout
+    assert a == b and len(a.strip().splitlines()) == 2
+    # and the Python loader gives the device cloud back bit for bit
+    back = pcl.loadPCDFile(tmp_path / "frame0.pcd").to_numpy()
+    assert back.tobytes() == np.ascontiguousarray(frames[0]).tobytes()
