@@ -157,7 +157,11 @@ typedef enum {
 } pft_key;
 
 typedef enum { PFT_NN_EXACT = 0 } pft_nn_mode;
-typedef enum { PFT_SAMPLER_CDF = 1, PFT_SAMPLER_CDF_VDC = 2 } pft_sampler;
+/* PFT_SAMPLER_ALIAS_PCL: upstream's Walker alias table (genAliasTable / sampleWithReplacement), built sequentially on
+ * one GPU thread -- parity mode: same ancestors as PCL for the same uniforms.  PFT_SAMPLER_CDF (default): inverse-CDF on
+ * a fixed-point cumulative table built in parallel (same distribution).  PFT_SAMPLER_CDF_VDC: one uniform + van der
+ * Corput offsets (low-variance selection). */
+typedef enum { PFT_SAMPLER_ALIAS_PCL = 0, PFT_SAMPLER_CDF = 1, PFT_SAMPLER_CDF_VDC = 2 } pft_sampler;
 
 /* kld != 0: KLDAdaptiveParticleFilterOMPTracker (ref :209-222); kld == 0: ParticleFilterOMPTracker (ref :201-206) */
 PFT_API int pft_tracker_create(pft_context* ctx, int kld, pft_tracker** out);

@@ -30,7 +30,7 @@ THREADS, PARTICLE_NUM, MAX_PARTICLE_NUM, ITERATION_NUM, NN_MODE, USE_HSV, USE_DI
 STEP_NOISE_COV, INIT_NOISE_COV, INIT_NOISE_MEAN, BIN_SIZE = range(40, 44)
 NN_EXACT = 0
 PEER_HANDLE_BYTES = 64
-SAMPLER_CDF, SAMPLER_CDF_VDC = 1, 2
+SAMPLER_ALIAS_PCL, SAMPLER_CDF, SAMPLER_CDF_VDC = 0, 1, 2
 
 
 class PftError(RuntimeError):

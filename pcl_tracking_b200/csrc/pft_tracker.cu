@@ -154,7 +154,7 @@ struct pft_tracker {
   int graph_nodes = 0;
   // device buffers
   DevBuf st, parts[2], mats, slot_aabb, model, model_perm, model_tmp, sort_keys, sort_idx, bbox, raw, partial, cdf, cdf_total, ancestors, bin_keys, tbl_rep,
-      tbl_min, slot_of, klb, d_usel, d_normals, d_umot, idx_hdr, cell_start, ipts, ihsv, icount, dbg_idx, dbg_d2, d_trans, row_table, flists, fneeded, fneeded_list, ffar_list, xlists, xcount, result_box;
+      tbl_min, slot_of, klb, d_usel, d_normals, d_umot, idx_hdr, cell_start, ipts, ihsv, icount, dbg_idx, dbg_d2, d_trans, row_table, flists, fneeded, fneeded_list, ffar_list, xlists, xcount, result_box, alias_a, alias_q, alias_hl;
   int weight_smem = 0;  // dynamic shared memory of the weight kernel (bytes)
   int tbl_size = 0;
   int n_slots = 0;
@@ -190,7 +190,7 @@ void release_all(pft_tracker* t) {
   DevBuf* bufs[] = {&t->st, &t->parts[0], &t->parts[1], &t->mats, &t->slot_aabb, &t->model, &t->model_perm, &t->model_tmp, &t->sort_keys, &t->sort_idx,
                     &t->bbox, &t->raw, &t->partial, &t->cdf, &t->cdf_total, &t->ancestors, &t->bin_keys, &t->tbl_rep, &t->tbl_min, &t->slot_of, &t->klb,
                     &t->d_usel, &t->d_normals, &t->d_umot, &t->idx_hdr, &t->cell_start, &t->ipts, &t->ihsv, &t->icount, &t->dbg_idx,
-                    &t->dbg_d2, &t->d_trans, &t->row_table, &t->flists, &t->fneeded, &t->fneeded_list, &t->ffar_list, &t->xlists, &t->xcount, &t->result_box};
+                    &t->dbg_d2, &t->d_trans, &t->row_table, &t->flists, &t->fneeded, &t->fneeded_list, &t->ffar_list, &t->xlists, &t->xcount, &t->result_box, &t->alias_a, &t->alias_q, &t->alias_hl};
   for (auto* b : bufs) b->release();
 }
 
@@ -475,7 +475,13 @@ int stage_resample(pft_tracker* t, int slot) {
                                 t->tbl_min.as<int>(), t->kld ? t->tbl_size : 0);
   PFT_LAUNCH_CHECK();
   stage_mark(t, "cdf_kernel");
+  if (t->sampler == PFT_SAMPLER_ALIAS_PCL) {  // (buffers sized by prepare_compute: nothing is allocated inside a graph capture)
+    alias_table_kernel<<<1, 32, 0, s>>>(st, old_parts, t->alias_a.as<int>(), t->alias_q.as<double>(), t->alias_hl.as<int>());
+    PFT_LAUNCH_CHECK();
+    stage_mark(t, "alias_table_kernel");
+  }
   ResampleArgs a;
+  a.alias_a = t->alias_a.as<int>(); a.alias_q = t->alias_q.as<double>();
   a.st = st; a.old_parts = old_parts; a.new_parts = new_parts;
   a.cdf = t->cdf.as<unsigned long long>(); a.cdf_total = t->cdf_total.as<unsigned long long>();
   a.u_select = usel; a.normals = normals; a.u_motion = umot; a.seed = t->seed;
@@ -700,6 +706,13 @@ int prepare_compute(pft_tracker* t) {
     PFT_CUDA_TRY(cudaStreamSynchronize(t->run_stream()));
     if ((rc = t->partial.reserve(need_partial))) return rc;
   }
+  if (t->sampler == PFT_SAMPLER_ALIAS_PCL && t->alias_q.bytes < (size_t)t->n_cap * sizeof(double)) {
+    invalidate_graph(t);
+    PFT_CUDA_TRY(cudaStreamSynchronize(t->run_stream()));
+    if ((rc = t->alias_a.reserve((size_t)t->n_cap * sizeof(int)))) return rc;
+    if ((rc = t->alias_q.reserve((size_t)t->n_cap * sizeof(double)))) return rc;
+    if ((rc = t->alias_hl.reserve((size_t)t->n_cap * sizeof(int)))) return rc;
+  }
   if (t->debug_nn > 0) {
     const size_t need = (size_t)t->debug_nn * t->M;
     if (need * sizeof(int) > t->dbg_idx.bytes) {
@@ -772,7 +785,7 @@ int pft_tracker_set_i(pft_tracker* t, int key, int v) {
     case PFT_USE_HSV: t->use_hsv = v != 0; break;
     case PFT_USE_DISTANCE: t->use_dist = v != 0; break;
     case PFT_SAMPLER:
-      if (v != PFT_SAMPLER_CDF && v != PFT_SAMPLER_CDF_VDC) { set_last_error("unknown sampler %d", v); return PFT_ERR_INVALID; }
+      if (v != PFT_SAMPLER_ALIAS_PCL && v != PFT_SAMPLER_CDF && v != PFT_SAMPLER_CDF_VDC) { set_last_error("unknown sampler %d", v); return PFT_ERR_INVALID; }
       t->sampler = v; break;
     case PFT_QUAT_SAMPLE: t->quat_sample = v != 0; break;
     case PFT_USE_NORMAL:

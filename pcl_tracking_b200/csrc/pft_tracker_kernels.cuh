@@ -1662,6 +1662,8 @@ struct ResampleArgs {
   const float* normals;    // [stride][6]
   const float* u_motion;   // [stride]
   unsigned long long seed;
+  const int* alias_a;      // PFT_SAMPLER_ALIAS_PCL: Walker alias table of the old particle set
+  const double* alias_q;
   const CloudHeader* scene_hdr;
   int* ancestors;
   int* bin_keys;           // [n_max][6] (KLD)
@@ -1670,6 +1672,37 @@ struct ResampleArgs {
   float bin_size[6];
   int kld, n_max, sampler;
 };
+
+// ParticleFilterTracker::genAliasTable (Walker's alias method, PCL-1.8.0 impl/particle_filter.hpp) exactly
+// as upstream runs it: a sequential two-stack construction, here on ONE thread.  Parity mode (PFT_SAMPLER_ALIAS_PCL):
+// it reproduces upstream's ancestor choice for the same selection uniforms; the default sampler is the parallel
+// cumulative table.
+__global__ void alias_table_kernel(const TrackerState* __restrict__ st, const DevParticle* __restrict__ parts, int* __restrict__ a, double* __restrict__ q,
+                                   int* __restrict__ HL) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const int N = st->particle_num;
+  if (N <= 0) return;
+  int* H = HL;
+  int* L = HL + N - 1;
+  for (int i = 0; i < N; ++i) { q[i] = (double)(parts[i].weight * (float)N); a[i] = i; }
+  for (int i = 0; i < N; ++i) { if (q[i] >= 1.0) *H++ = i; else *L-- = i; }
+  while (H != HL && L != HL + N - 1) {
+    const int j = *(L + 1);
+    const int k = *(H - 1);
+    a[j] = k;
+    q[k] += q[j] - 1;
+    ++L;
+    if (q[k] < 1.0) { *L-- = k; --H; }
+  }
+}
+// sampleWithReplacement
+__device__ __forceinline__ int alias_pick(const int* __restrict__ a, const double* __restrict__ q, int n, float u) {
+  double rU = (double)u * (double)n;
+  int k = (int)rU;
+  rU -= k;
+  if (k >= n) k = n - 1;
+  return rU < q[k] ? k : a[k];
+}
 
 __device__ __forceinline__ int cdf_pick(const unsigned long long* __restrict__ cdf, unsigned long long total, int n, double u) {
   if (total == 0ull) { const int k = (int)(u * (double)n); return k >= n ? n - 1 : k; }
@@ -1718,7 +1751,7 @@ __global__ void resample_kernel(const ResampleArgs a) {
     } else {
       u = (double)us;
     }
-    const int j = cdf_pick(a.cdf, total, n_old, u);
+    const int j = a.sampler == PFT_SAMPLER_ALIAS_PCL ? alias_pick(a.alias_a, a.alias_q, n_old, us) : cdf_pick(a.cdf, total, n_old, u);
     DevParticle x = a.old_parts[j];
     particle_sample(x, a.np, z);
     if (a.kld && (double)um < a.motion_ratio) {

@@ -36,7 +36,8 @@ def test_init_particles(quat):
         assert abs(float(gr[k]) - float(orr[k])) < 1e-6
 
 
-@pytest.mark.parametrize("kld,sampler,quat", [(True, 1, 1), (True, 2, 1), (True, 1, 0), (False, 1, 1), (False, 2, 0)])
+@pytest.mark.parametrize("kld,sampler,quat", [(True, 1, 1), (True, 2, 1), (True, 1, 0), (False, 1, 1), (False, 2, 0),
+                                              (True, 0, 1), (False, 0, 1)])  # sampler 0 = upstream's Walker alias table
 def test_resample_matches_oracle(kld, sampler, quat):
     n, nmax = 150, 400
     g, o = util.make_pair(kld=kld, particle_num=n, max_particle_num=nmax, quat=quat, sampler=sampler, epsilon=0.1, bin_size=0.05)
