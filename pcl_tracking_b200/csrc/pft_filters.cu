@@ -169,9 +169,7 @@ __global__ void __launch_bounds__(1024) k1_tile_assign_kernel(const CloudHeader*
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     if (f[k]) {
-      vid[slot_of[base + k]] = ex;
-      acc_xyz[3 * ex] = 0.0; acc_xyz[3 * ex + 1] = 0.0; acc_xyz[3 * ex + 2] = 0.0;
-      reinterpret_cast<uint4*>(acc_rgbc)[ex] = make_uint4(0u, 0u, 0u, 0u);
+      vid[slot_of[base + k]] = ex;  // (the accumulators were cleared by two contiguous memsets before the pass)
       ++ex;
     }
   }
@@ -289,6 +287,8 @@ int run_voxel_grid(pft_context* ctx, const pft_cloud* in, pft_cloud* out, float 
   cudaStream_t s = ctx->stream;
   PFT_CUDA_TRY(cudaMemsetAsync(ctx->k1_keys.p, 0xff, H * sizeof(unsigned long long), s));
   PFT_CUDA_TRY(cudaMemsetAsync(ctx->k1_first.p, 0x7f, H * sizeof(int), s));
+  PFT_CUDA_TRY(cudaMemsetAsync(ctx->k1_acc_xyz.p, 0, cap * 3 * sizeof(double), s));
+  PFT_CUDA_TRY(cudaMemsetAsync(ctx->k1_acc_rgbc.p, 0, cap * 4 * sizeof(unsigned int), s));
   const float inv = 1.0f / leaf;
   const int grid = grid_for(cap, 256, ctx->sm_count);
   k1_insert_kernel<<<grid, 256, 0, s>>>(in->d_pts(), in->d_hdr(), ctx->k1_keys.as<unsigned long long>(), ctx->k1_first.as<int>(),
