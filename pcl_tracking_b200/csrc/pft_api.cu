@@ -104,6 +104,7 @@ void pft_context_destroy(pft_context* c) {
   for (auto* b : bufs) b->release();
   if (c->pinned) cudaFreeHost(c->pinned);
   if (c->batch_fork) cudaEventDestroy(c->batch_fork);
+  for (int k = 0; k < pft_context::kK1Graphs; ++k) if (c->k1_exec[k]) cudaGraphExecDestroy(c->k1_exec[k]);
   cudaStreamDestroy(c->stream);
   delete c;
 }

@@ -9,6 +9,9 @@
 // 64-bit packed lattice keys (21 bits per axis); per-voxel sums are kept in double (coordinates) and
 // uint32 (colour bytes), which makes the centroid independent of the order the atomics land in:
 // sums of fp32 sensor-range values are exact in fp64.  Output order = order of first appearance.
+#include <stdlib.h>
+#include <string.h>
+
 #include "pft_internal.h"
 
 namespace pft {
@@ -270,6 +273,34 @@ int run_passthrough(pft_context* ctx, const pft_cloud* in, pft_cloud* out, int f
   return PFT_OK;
 }
 
+// The ten stream operations of one downsample (4 memsets + 6 kernels).
+static int enqueue_voxel_grid(pft_context* ctx, const pft_cloud* in, pft_cloud* out, float leaf, int field, float lo, float hi, size_t cap, size_t H,
+                              int n_tiles) {
+  cudaStream_t s = ctx->stream;
+  PFT_CUDA_TRY(cudaMemsetAsync(ctx->k1_keys.p, 0xff, H * sizeof(unsigned long long), s));
+  PFT_CUDA_TRY(cudaMemsetAsync(ctx->k1_first.p, 0x7f, H * sizeof(int), s));
+  PFT_CUDA_TRY(cudaMemsetAsync(ctx->k1_acc_xyz.p, 0, cap * 3 * sizeof(double), s));
+  PFT_CUDA_TRY(cudaMemsetAsync(ctx->k1_acc_rgbc.p, 0, cap * 4 * sizeof(unsigned int), s));
+  const float inv = 1.0f / leaf;
+  const int grid = grid_for(cap, 256, ctx->sm_count);
+  k1_insert_kernel<<<grid, 256, 0, s>>>(in->d_pts(), in->d_hdr(), ctx->k1_keys.as<unsigned long long>(), ctx->k1_first.as<int>(),
+                                        ctx->k1_slot_of.as<int>(), (unsigned int)(H - 1), inv, field, lo, hi);
+  PFT_LAUNCH_CHECK();
+  k1_tile_count_kernel<<<n_tiles, 1024, 0, s>>>(in->d_hdr(), ctx->k1_slot_of.as<int>(), ctx->k1_first.as<int>(), ctx->k1_blk.as<int>());
+  PFT_LAUNCH_CHECK();
+  k1_tile_scan_kernel<<<1, 1024, 0, s>>>(n_tiles, ctx->k1_blk.as<int>(), out->d_hdr());
+  PFT_LAUNCH_CHECK();
+  k1_tile_assign_kernel<<<n_tiles, 1024, 0, s>>>(in->d_hdr(), ctx->k1_slot_of.as<int>(), ctx->k1_first.as<int>(), ctx->k1_blk.as<int>(),
+                                                 ctx->k1_vid.as<int>(), ctx->k1_acc_xyz.as<double>(), ctx->k1_acc_rgbc.as<unsigned int>());
+  PFT_LAUNCH_CHECK();
+  k1_accum_kernel<<<grid, 256, 0, s>>>(in->d_pts(), in->d_hdr(), ctx->k1_slot_of.as<int>(), ctx->k1_vid.as<int>(),
+                                       ctx->k1_acc_xyz.as<double>(), ctx->k1_acc_rgbc.as<unsigned int>());
+  PFT_LAUNCH_CHECK();
+  k1_final_kernel<<<grid, 256, 0, s>>>(out->d_hdr(), ctx->k1_acc_xyz.as<double>(), ctx->k1_acc_rgbc.as<unsigned int>(), out->d_pts());
+  PFT_LAUNCH_CHECK();
+  return PFT_OK;
+}
+
 int run_voxel_grid(pft_context* ctx, const pft_cloud* in, pft_cloud* out, float leaf, int field, float lo, float hi) {
   if (!(leaf > 0.f)) { set_last_error("leaf size must be positive"); return PFT_ERR_INVALID; }
   const size_t cap = in->capacity;
@@ -284,32 +315,43 @@ int run_voxel_grid(pft_context* ctx, const pft_cloud* in, pft_cloud* out, float 
   if ((rc = ctx->k1_slot_of.reserve(cap * sizeof(int)))) return rc;
   if ((rc = ctx->k1_acc_xyz.reserve(cap * 3 * sizeof(double)))) return rc;
   if ((rc = ctx->k1_acc_rgbc.reserve(cap * 4 * sizeof(unsigned int)))) return rc;
-  cudaStream_t s = ctx->stream;
-  PFT_CUDA_TRY(cudaMemsetAsync(ctx->k1_keys.p, 0xff, H * sizeof(unsigned long long), s));
-  PFT_CUDA_TRY(cudaMemsetAsync(ctx->k1_first.p, 0x7f, H * sizeof(int), s));
-  PFT_CUDA_TRY(cudaMemsetAsync(ctx->k1_acc_xyz.p, 0, cap * 3 * sizeof(double), s));
-  PFT_CUDA_TRY(cudaMemsetAsync(ctx->k1_acc_rgbc.p, 0, cap * 4 * sizeof(unsigned int), s));
-  const float inv = 1.0f / leaf;
-  const int grid = grid_for(cap, 256, ctx->sm_count);
-  k1_insert_kernel<<<grid, 256, 0, s>>>(in->d_pts(), in->d_hdr(), ctx->k1_keys.as<unsigned long long>(), ctx->k1_first.as<int>(),
-                                        ctx->k1_slot_of.as<int>(), (unsigned int)(H - 1), inv, field, lo, hi);
-  PFT_LAUNCH_CHECK();
   const int n_tiles = (int)((cap + kTile - 1) / kTile);
   if ((rc = ctx->k1_blk.reserve((size_t)n_tiles * sizeof(int)))) return rc;
-  k1_tile_count_kernel<<<n_tiles, 1024, 0, s>>>(in->d_hdr(), ctx->k1_slot_of.as<int>(), ctx->k1_first.as<int>(), ctx->k1_blk.as<int>());
-  PFT_LAUNCH_CHECK();
-  k1_tile_scan_kernel<<<1, 1024, 0, s>>>(n_tiles, ctx->k1_blk.as<int>(), out->d_hdr());
-  PFT_LAUNCH_CHECK();
-  k1_tile_assign_kernel<<<n_tiles, 1024, 0, s>>>(in->d_hdr(), ctx->k1_slot_of.as<int>(), ctx->k1_first.as<int>(), ctx->k1_blk.as<int>(),
-                                                 ctx->k1_vid.as<int>(), ctx->k1_acc_xyz.as<double>(), ctx->k1_acc_rgbc.as<unsigned int>());
-  PFT_LAUNCH_CHECK();
-  k1_accum_kernel<<<grid, 256, 0, s>>>(in->d_pts(), in->d_hdr(), ctx->k1_slot_of.as<int>(), ctx->k1_vid.as<int>(),
-                                       ctx->k1_acc_xyz.as<double>(), ctx->k1_acc_rgbc.as<unsigned int>());
-  PFT_LAUNCH_CHECK();
-  k1_final_kernel<<<grid, 256, 0, s>>>(out->d_hdr(), ctx->k1_acc_xyz.as<double>(), ctx->k1_acc_rgbc.as<unsigned int>(), out->d_pts());
-  PFT_LAUNCH_CHECK();
   out->host_n = -1;
   (void)kFirstInit;
+  // A camera stream downsamples frame after frame between the same buffers: the ten operations are captured once
+  // into a CUDA graph and replayed (one launch per frame instead of ten).  Everything the sequence touches is in the key.
+  static const bool use_graph = [] { const char* e = getenv("PFT_NO_GRAPH"); return !(e && e[0] == '1'); }();
+  if (!use_graph) return enqueue_voxel_grid(ctx, in, out, leaf, field, lo, hi, cap, H, n_tiles);
+  pft_context::K1Key key;
+  memset(&key, 0, sizeof(key));
+  key.p[0] = in->d_pts(); key.p[1] = in->d_hdr(); key.p[2] = out->d_pts(); key.p[3] = out->d_hdr();
+  key.p[4] = ctx->k1_keys.p; key.p[5] = ctx->k1_first.p; key.p[6] = ctx->k1_vid.p; key.p[7] = ctx->k1_slot_of.p;
+  key.p[8] = ctx->k1_acc_xyz.p; key.p[9] = ctx->k1_acc_rgbc.p; key.p[10] = ctx->k1_blk.p;
+  key.cap = cap; key.H = H; key.leaf = leaf; key.lo = lo; key.hi = hi; key.field = field;
+  // a few alternating (in, out) pairs are common (double-buffered frames): keep a small set of graphs
+  int slot = -1;
+  for (int k = 0; k < pft_context::kK1Graphs; ++k)
+    if (ctx->k1_exec[k] && memcmp(&ctx->k1_key[k], &key, sizeof(key)) == 0) { slot = k; break; }
+  if (slot < 0) {
+    slot = ctx->k1_next;
+    ctx->k1_next = (ctx->k1_next + 1) % pft_context::kK1Graphs;
+    if (ctx->k1_exec[slot]) { cudaGraphExecDestroy(ctx->k1_exec[slot]); ctx->k1_exec[slot] = nullptr; }
+    cudaGraph_t graph = nullptr;
+    const unsigned long long before = g_launch_count.load();
+    PFT_CUDA_TRY(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    rc = enqueue_voxel_grid(ctx, in, out, leaf, field, lo, hi, cap, H, n_tiles);
+    cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
+    g_launch_count -= g_launch_count.load() - before;  // captured, not launched
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (ce != cudaSuccess) { set_last_error("downsample graph capture failed: %s", cudaGetErrorString(ce)); cudaGetLastError(); return PFT_ERR_CUDA; }
+    cudaError_t ie = cudaGraphInstantiate(&ctx->k1_exec[slot], graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) { set_last_error("downsample graph instantiate failed: %s", cudaGetErrorString(ie)); cudaGetLastError(); ctx->k1_exec[slot] = nullptr; return PFT_ERR_CUDA; }
+    ctx->k1_key[slot] = key;
+  }
+  PFT_CUDA_TRY(cudaGraphLaunch(ctx->k1_exec[slot], ctx->stream));
+  g_launch_count += 6;  // the six kernels of the sequence
   return PFT_OK;
 }
 

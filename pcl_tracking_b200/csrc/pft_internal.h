@@ -32,6 +32,12 @@ struct pft_context {
   // NCCL communicator shared by the clouds and trackers of this context (one process per GPU)
   void* comm = nullptr;
   int nranks = 1, rank = 0;
+  // captured downsample sequences (pft_filters.cu: run_voxel_grid), keyed by every pointer / size / parameter they use
+  struct K1Key { const void* p[11]; size_t cap, H; float leaf, lo, hi; int field; };
+  static constexpr int kK1Graphs = 8;
+  K1Key k1_key[kK1Graphs];
+  cudaGraphExec_t k1_exec[kK1Graphs] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int k1_next = 0;
   // Euclidean clustering scratch (pft_cluster.cu); the labels of the last call stay on the device for pft_cloud_select_cluster
   pft::DevBuf cl_grid, cl_cells, cl_work, cl_sel;
   size_t cl_n = 0;
