@@ -805,7 +805,8 @@ __device__ __forceinline__ void block_points_of_rows(int nrows, int* s_pref /* [
 __device__ __forceinline__ void build_cell_direct(const IndexHeader& h, const int* __restrict__ cs, const float4* __restrict__ pts, int cell,
                                                   float leaf, float margin, float r_max,
                                                   unsigned short* __restrict__ flists, unsigned short* __restrict__ xlists,
-                                                  int* __restrict__ list_counters, int* pref, int* start, int* s_cnt, float* s_m2, int* s_ms, int* s_xi) {
+                                                  int* __restrict__ list_counters, int* pref, int* start, int* s_cnt, float* s_m2, int* s_ms, int* s_xi,
+                                                  unsigned short* s_list /* [kListKX] shared */) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int fdx = h.f_dim[0], fdy = h.f_dim[1];
   const float cell_m = h.cell;
@@ -872,62 +873,54 @@ __device__ __forceinline__ void build_cell_direct(const IndexHeader& h, const in
   int c0[3], c1[3];
   coarse_range(1, reach, c0[1], c1[1]); coarse_range(2, reach, c0[2], c1[2]);
   const int ny = c1[1] - c0[1] + 1, nrows = max(ny, 0) * max(c1[2] - c0[2] + 1, 0);
-  unsigned short* xl = nullptr;
-  int cap = kListK - 1;
-  for (int attempt = 0; attempt < 2; ++attempt) {
-    if (threadIdx.x == 0) *s_cnt = 0;
-    __syncthreads();
-    unsigned short* dst = attempt ? xl : list + 1;
-    block_points_of_rows(
-        nrows, pref, start,
-        [&](int r) {
-          const int zz = r / ny, y = c0[1] + (r - zz * ny), z = c0[2] + zz;
-          const float zlo = (float)(z + h.origin[2]) * cell_m - 2.0f * margin, zhi = (float)(z + 1 + h.origin[2]) * cell_m + 2.0f * margin;
-          const float gz = fmaxf(fmaxf(lo[2] - zhi, zlo - hi[2]), 0.f);
-          const float ylo = (float)(y + h.origin[1]) * cell_m - 2.0f * margin, yhi = (float)(y + 1 + h.origin[1]) * cell_m + 2.0f * margin;
-          const float gy = fmaxf(fmaxf(lo[1] - yhi, ylo - hi[1]), 0.f);
-          const float rem = U2 - (gy * gy + gz * gz) * 0.9999f;
-          if (rem < 0.f) return RowSpan{0, 0};
-          const float xr = sqrtf(rem) * 1.00001f + 2.0f * margin;
-          const int xa = max((int)floorf(((lo[0] - xr) * h.inv_leaf) * h.level_scale) - h.origin[0], 0);
-          const int xb = min((int)floorf(((hi[0] + xr) * h.inv_leaf) * h.level_scale) - h.origin[0], dimx - 1);
-          if (xa > xb) return RowSpan{0, 0};
-          const int base = (z * dimy + y) * dimx;
-          const int a = cs[base + xa];
-          return RowSpan{a, cs[base + xb + 1] - a};
-        },
-        [&](int s) {
-          const float4 p = pts[s];
-          if (box_mindist2(lo, hi, p) <= U2 && can_win(p, p0, bc, bh)) {
-            const int pos = atomicAdd(s_cnt, 1);
-            if (pos < cap) dst[pos] = (unsigned short)s;
-          }
-        });
-    const int n = *s_cnt;
-    __syncthreads();
-    if (n <= cap) {
-      // pad to whole 16-byte groups with the dummy slot (the lookup reads whole groups unconditionally; a regular
-      // record starts with its header word)
-      const int off = attempt ? 0 : 1;
-      const int n8 = ((n + off + 7) & ~7) - off;
-      if (n + (int)threadIdx.x < n8) dst[n + threadIdx.x] = (unsigned short)h.n_cropped;
-      if (threadIdx.x == 0) {
-        if (!attempt) list[0] = (unsigned short)n;
-        else { list[3] = (unsigned short)n; list[0] = kListExtended; }
-      }
-      break;
-    }
-    // does not fit: take an extended list and gather again into it (cells far from the surface)
-    if (threadIdx.x == 0) *s_xi = (!attempt && n <= kListKX) ? atomicAdd(&list_counters[0], 1) : -1;
+  // one gather into shared memory (up to the capacity of an extended list), then the list goes where its length says
+  if (threadIdx.x == 0) *s_cnt = 0;
+  __syncthreads();
+  block_points_of_rows(
+      nrows, pref, start,
+      [&](int r) {
+        const int zz = r / ny, y = c0[1] + (r - zz * ny), z = c0[2] + zz;
+        const float zlo = (float)(z + h.origin[2]) * cell_m - 2.0f * margin, zhi = (float)(z + 1 + h.origin[2]) * cell_m + 2.0f * margin;
+        const float gz = fmaxf(fmaxf(lo[2] - zhi, zlo - hi[2]), 0.f);
+        const float ylo = (float)(y + h.origin[1]) * cell_m - 2.0f * margin, yhi = (float)(y + 1 + h.origin[1]) * cell_m + 2.0f * margin;
+        const float gy = fmaxf(fmaxf(lo[1] - yhi, ylo - hi[1]), 0.f);
+        const float rem = U2 - (gy * gy + gz * gz) * 0.9999f;
+        if (rem < 0.f) return RowSpan{0, 0};
+        const float xr = sqrtf(rem) * 1.00001f + 2.0f * margin;
+        const int xa = max((int)floorf(((lo[0] - xr) * h.inv_leaf) * h.level_scale) - h.origin[0], 0);
+        const int xb = min((int)floorf(((hi[0] + xr) * h.inv_leaf) * h.level_scale) - h.origin[0], dimx - 1);
+        if (xa > xb) return RowSpan{0, 0};
+        const int base = (z * dimy + y) * dimx;
+        const int a = cs[base + xa];
+        return RowSpan{a, cs[base + xb + 1] - a};
+      },
+      [&](int s) {
+        const float4 p = pts[s];
+        if (box_mindist2(lo, hi, p) <= U2 && can_win(p, p0, bc, bh)) {
+          const int pos = atomicAdd(s_cnt, 1);
+          if (pos < kListKX) s_list[pos] = (unsigned short)s;
+        }
+      });
+  const int n = *s_cnt;
+  unsigned short* dst = list + 1;
+  int off = 1;
+  if (n > kListK - 1) {
+    // does not fit a regular record: an extended list (cells far from the surface), or the row-table search
+    if (threadIdx.x == 0) *s_xi = n <= kListKX ? atomicAdd(&list_counters[0], 1) : -1;
     __syncthreads();
     const int xi = *s_xi;
-    __syncthreads();
-    if (xi < 0 || xi >= kListXCells) { if (threadIdx.x == 0) list[0] = kListOverflow; break; }
-    xl = xlists + (size_t)xi * kListKX;
-    cap = kListKX;
+    if (xi < 0 || xi >= kListXCells) { if (threadIdx.x == 0) list[0] = kListOverflow; return; }
+    dst = xlists + (size_t)xi * kListKX;
+    off = 0;
     PFT_STAT(11, threadIdx.x == 0 ? 1 : 0);
-    if (threadIdx.x == 0) { list[1] = (unsigned short)(xi & 0xffff); list[2] = (unsigned short)(xi >> 16); }
+    if (threadIdx.x == 0) { list[1] = (unsigned short)(xi & 0xffff); list[2] = (unsigned short)(xi >> 16); list[3] = (unsigned short)n; }
   }
+  for (int t = threadIdx.x; t < n; t += blockDim.x) dst[t] = s_list[t];
+  // pad to whole 16-byte groups with the dummy slot (the lookup reads whole groups unconditionally; a regular record
+  // starts with its header word)
+  const int n8 = ((n + off + 7) & ~7) - off;
+  if (n + (int)threadIdx.x < n8) dst[n + threadIdx.x] = (unsigned short)h.n_cropped;
+  if (threadIdx.x == 0) list[0] = off ? (unsigned short)n : kListExtended;
   PFT_STAT(15, threadIdx.x == 0 ? 1 : 0);
 }
 
@@ -1158,6 +1151,7 @@ __global__ void __launch_bounds__(256) cand_build_far_kernel(const IndexHeader* 
   __shared__ int s_cnt, s_xi;
   __shared__ int s_pref[34], s_start[32], s_ms[8];
   __shared__ float s_m2[8];
+  __shared__ unsigned short s_list[kListKX];
   if (threadIdx.x == 0) { h = *hdr; s_pref[32] = 0x7fffffff; }
   __syncthreads();
   if (!h.valid || !lists_on(h)) return;
@@ -1166,7 +1160,7 @@ __global__ void __launch_bounds__(256) cand_build_far_kernel(const IndexHeader* 
   const float margin = 1.0e-5f + 4.0e-6f * leaf * (float)(abs(h.f_origin[0]) + abs(h.f_origin[1]) + abs(h.f_origin[2]) + h.f_dim[0] + h.f_dim[1] + h.f_dim[2]);
   const float r_max = max_d2 >= 1.0e30 ? 1.0e15f : (float)sqrt(max_d2) * 1.00001f;
   for (int idx = blockIdx.x; idx < n_far; idx += gridDim.x) {
-    build_cell_direct(h, cs, pts, far_list[idx], leaf, margin, r_max, flists, xlists, list_counters, s_pref, s_start, &s_cnt, s_m2, s_ms, &s_xi);
+    build_cell_direct(h, cs, pts, far_list[idx], leaf, margin, r_max, flists, xlists, list_counters, s_pref, s_start, &s_cnt, s_m2, s_ms, &s_xi, s_list);
     __syncthreads();
   }
 }
