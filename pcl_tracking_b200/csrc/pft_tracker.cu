@@ -277,7 +277,7 @@ int wanted_cap(const pft_tracker* t) { return t->kld ? std::max(t->max_particle_
 
 // (Re)allocate every particle-count dependent buffer.  Existing particles survive a capacity change.
 int ensure_particle_buffers(pft_tracker* t) {
-  const int cap = wanted_cap(t);
+  const int cap = std::max(wanted_cap(t), t->n_cap);  // grow only: a smaller setParticleNum keeps the old set to draw from
   if (cap <= 0) { set_last_error("particle count is zero: call setParticleNum / setMaximumParticleNum first"); return PFT_ERR_STATE; }
   cudaStream_t s = t->run_stream();
   int rc;
@@ -462,7 +462,7 @@ int stage_resample(pft_tracker* t, int slot) {
   if (!t->input) { set_last_error("resample needs an input cloud (setInputCloud)"); return PFT_ERR_STATE; }
   if (t->kld && t->max_particle_num <= 0) { set_last_error("KLD tracker: setMaximumParticleNum was not called"); return PFT_ERR_STATE; }
   cudaStream_t s = t->run_stream();
-  const int count = t->kld ? t->max_particle_num : t->n_cap;
+  const int count = t->kld ? t->max_particle_num : t->particle_num;
   const float *usel = nullptr, *normals = nullptr, *umot = nullptr;  // null: resample_kernel generates its draws inline (Philox)
   int rc = PFT_OK;
   if (t->inj_stride > 0 && (rc = prepare_draws(t, slot, count, &usel, &normals, &umot))) return rc;
@@ -470,9 +470,9 @@ int stage_resample(pft_tracker* t, int slot) {
   const DevParticle* old_parts = t->parts[t->cur].as<DevParticle>();
   DevParticle* new_parts = t->parts[t->cur ^ 1].as<DevParticle>();
   if (t->n_cap > kClusterMinParticles) cdf_kernel<kClusterCtas><<<kClusterCtas, 1024, 0, s>>>(st, old_parts, t->cdf.as<unsigned long long>(), t->cdf_total.as<unsigned long long>(), t->tbl_rep.as<int>(),
-                                t->tbl_min.as<int>(), t->kld ? t->tbl_size : 0);
+                                t->tbl_min.as<int>(), t->kld ? t->tbl_size : 0, t->kld ? 0 : t->particle_num, t->input->d_hdr());
   else cdf_kernel<1><<<1, 1024, 0, s>>>(st, old_parts, t->cdf.as<unsigned long long>(), t->cdf_total.as<unsigned long long>(), t->tbl_rep.as<int>(),
-                                t->tbl_min.as<int>(), t->kld ? t->tbl_size : 0);
+                                t->tbl_min.as<int>(), t->kld ? t->tbl_size : 0, t->kld ? 0 : t->particle_num, t->input->d_hdr());
   PFT_LAUNCH_CHECK();
   stage_mark(t, "cdf_kernel");
   if (t->sampler == PFT_SAMPLER_ALIAS_PCL) {  // (buffers sized by prepare_compute: nothing is allocated inside a graph capture)
@@ -491,7 +491,7 @@ int stage_resample(pft_tracker* t, int slot) {
   a.np = make_noise(t, zero, t->step_cov);
   a.motion_ratio = t->motion_ratio;
   for (int d = 0; d < 6; ++d) a.bin_size[d] = t->bin_size[d];
-  a.kld = t->kld ? 1 : 0; a.n_max = t->max_particle_num; a.sampler = t->sampler;
+  a.kld = t->kld ? 1 : 0; a.n_max = t->max_particle_num; a.sampler = t->sampler; a.n_target = t->particle_num;
   resample_kernel<<<blocks_for(count, 128, t->ctx->sm_count * 16), 128, 0, s>>>(a);
   PFT_LAUNCH_CHECK();
   stage_mark(t, "resample_kernel");

@@ -34,6 +34,7 @@ struct TrackerState {
   unsigned int peer_epoch;       // weight() calls so far in peer (NVLink P2P) exchange mode
   unsigned int peer_blocks_done; // raw_weights_kernel blocks that have pushed their slice this epoch
   unsigned int peer_error;       // a wait on a peer's flag timed out (sticky)
+  int resample_n_old;            // particle count the running resample draws FROM (cdf_kernel publishes the new count for fixed-N trackers)
   unsigned int work_counter;     // next (particle, model chunk) item of the running weight kernel (reset by index_begin_kernel)
   unsigned long long evals;      // likelihood evaluations so far: sum over weight() calls of particles x model points (whole job)
 };
@@ -1572,7 +1573,8 @@ update_kernel(TrackerState* st, const DevParticle* __restrict__ parts, const Clo
 template <int CTAS>
 __global__ void __cluster_dims__(CTAS, 1, 1) __launch_bounds__(1024)
 cdf_kernel(TrackerState* st, const DevParticle* __restrict__ parts, unsigned long long* __restrict__ cdf, unsigned long long* total_out,
-           int* __restrict__ tbl_rep, int* __restrict__ tbl_min, int tbl_size) {
+           int* __restrict__ tbl_rep, int* __restrict__ tbl_min, int tbl_size, int n_target /* fixed-N tracker: particle_num_ (setParticleNum may have
+           changed it since the last resample); 0: KLD, the stop rule sets the count */, const CloudHeader* __restrict__ scene_hdr) {
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned int crank = cluster.block_rank();
   __shared__ unsigned long long smem[34];
@@ -1597,8 +1599,13 @@ cdf_kernel(TrackerState* st, const DevParticle* __restrict__ parts, unsigned lon
     total += v;
   }
   if (before) for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) cdf[i] += before;
-  if (crank == 0 && threadIdx.x == 0) *total_out = total;
+  if (crank == 0 && threadIdx.x == 0) {
+    *total_out = total;
+    st->resample_n_old = n;
+  }
   cluster.sync();
+  // (every CTA has read the old count by now) fixed-N: the resample that follows produces particle_num_ particles
+  if (crank == 0 && threadIdx.x == 0 && n_target > 0 && scene_hdr->n > 0) st->particle_num = n_target;
 }
 
 // ------------------------------------------------------------------ on-device draws (Philox4x32-10)
@@ -1665,6 +1672,7 @@ struct ResampleArgs {
   double motion_ratio;
   float bin_size[6];
   int kld, n_max, sampler;
+  int n_target;            // fixed-N tracker: particles to produce (particle_num_)
 };
 
 // ParticleFilterTracker::genAliasTable (Walker's alias method, PCL-1.8.0 impl/particle_filter.hpp) exactly
@@ -1674,7 +1682,7 @@ struct ResampleArgs {
 __global__ void alias_table_kernel(const TrackerState* __restrict__ st, const DevParticle* __restrict__ parts, int* __restrict__ a, double* __restrict__ q,
                                    int* __restrict__ HL) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  const int N = st->particle_num;
+  const int N = st->resample_n_old;
   if (N <= 0) return;
   int* H = HL;
   int* L = HL + N - 1;
@@ -1707,8 +1715,8 @@ __device__ __forceinline__ int cdf_pick(const unsigned long long* __restrict__ c
 }
 
 __global__ void resample_kernel(const ResampleArgs a) {
-  const int n_old = a.st->particle_num;
-  const int n_cand = a.kld ? a.n_max : n_old;
+  const int n_old = a.st->resample_n_old;
+  const int n_cand = a.kld ? a.n_max : a.n_target;
   const unsigned long long total = *a.cdf_total;
   const bool inline_draws = a.u_select == nullptr;
   const unsigned long long call = a.st->draw_call - 1ull;  // cdf_kernel has already advanced the stream position past this resample

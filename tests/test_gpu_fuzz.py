@@ -51,6 +51,8 @@ def test_random_call_sequences(seed):
         elif op == 3 and kld:
             t.setEpsilon(float(rng.choice([0.2, 0.05, 0.5])))
             t.setBinSize([float(rng.choice([0.1, 0.05, 0.2]))] * 6)
+        elif op == 3 and not kld:
+            t.setParticleNum(int(rng.integers(10, 400)))   # the next resample grows / shrinks the set
         elif op == 4:
             t.setReferenceCloud(scenes[int(rng.integers(0, 3))][1])
         elif op == 5:

@@ -167,3 +167,34 @@ def test_full_stage_sequence_with_resync():
         gr, orr = g.getResult(), o.get_result()
         for k in ("x", "y", "z", "roll", "pitch", "yaw"):
             assert abs(float(gr[k]) - float(orr[k])) <= 1e-4
+
+
+@pytest.mark.parametrize("n_new", [230, 40])
+def test_fixed_tracker_follows_set_particle_num(n_new):
+    """ParticleFilterTracker::resample produces particle_num_ particles: setParticleNum between frames grows or shrinks
+    the set at the next resample, drawing from the whole old set (same ancestors as the oracle)."""
+    n = 120
+    g, o = util.make_pair(kld=False, particle_num=n, use_hsv=False)
+    scene, model, centre = util.small_case(4, n_scene=600, n_model=60)
+    rng = np.random.default_rng(11)
+    parts = util.particles_around(centre, n, seed=12)
+    w = rng.random(n).astype(np.float32)
+    parts["weight"] = w / w.sum()
+    cloud = pcl.PointCloud(scene)
+    g.setReferenceCloud(model); g.setInputCloud(cloud)
+    g.setParticles(parts); o.set_particles(parts)
+    g.setResult(parts[0].copy(), parts[1].copy()); o.set_result(parts[0].copy())
+    g.setParticleNum(n_new); o.set_i(oracle.PARTICLE_NUM, n_new)
+    d = synth.draws(1, max(n, n_new), seed=13)
+    g.injectDraws(*d); o.inject_draws(*d)
+    g.resample(0); o.resample(0)
+    gp, op = g.getParticles(), o.get_particles()
+    assert len(gp) == len(op) == n_new
+    np.testing.assert_array_equal(g.ancestors(), o.ancestors())
+    assert g.ancestors()[1:].max() < n and (n_new < n or g.ancestors()[1:].max() > 0)
+    util.assert_particles_close(gp, op, 1e-6, 2e-6, None)
+    # and a whole compute() keeps the new count
+    g.injectDraws(None, None, None)
+    g.compute()
+    assert len(g.getParticles()) == n_new
+    assert abs(float(g.getParticles()["weight"].astype(np.float64).sum()) - 1.0) < 1e-4
