@@ -37,7 +37,7 @@ typedef enum {
   PFT_ERR_CUDA = -2,      /* CUDA runtime error or no device */
   PFT_ERR_STATE = -3,     /* call order (e.g. compute before setReferenceCloud on a non-empty input) */
   PFT_ERR_CAPACITY = -4,  /* caller buffer too small */
-  PFT_ERR_COMM = -5       /* NCCL error / NCCL not loadable */
+  PFT_ERR_COMM = -5       /* NCCL error / NCCL not loadable / NVLink peer exchange failed (IPC mapping, a peer that never arrived) */
 } pft_status;
 
 /* 16-byte packed point {x,y,z,rgba}; rgba bytes are b,g,r,a as in pcl::PointXYZRGBA */
