@@ -93,6 +93,12 @@ PFT_API int pft_passthrough(pft_context* ctx, const pft_cloud* in, pft_cloud* ou
  * field < 0 disables the PassThrough predicate (finite check only). */
 PFT_API int pft_passthrough_voxel_grid(pft_context* ctx, const pft_cloud* in, pft_cloud* out, float leaf,
                                        int field, float lo, float hi);
+/* Parity mode: pcl::ApproximateVoxelGrid::applyFilter reproduced exactly -- the 512-entry direct-mapped cache walked in
+ * input order, partial centroids emitted on every eviction, sequential fp32 sums (ref: src/auto_tracking.cpp:563-575,
+ * PCL-1.8.0 filters/impl/approximate_voxel_grid.hpp).  The algorithm is a sequential scan and runs on one GPU thread
+ * (~10 ms for a Kinect2 frame): use it to reproduce the reference's downsampled cloud bit for bit, and
+ * pft_passthrough_voxel_grid in production. */
+PFT_API int pft_approx_voxel_grid_pcl(pft_context* ctx, const pft_cloud* in, pft_cloud* out, float leaf, int field, float lo, float hi);
 /* removeZeroPoints + compute3DCentroid + transformPointCloud(-centroid) + VoxelGrid(leaf): the model
  * preparation of ref: src/auto_tracking.cpp:656-674.  centroid3 receives the translation that the
  * caller passes to pft_tracker_set_trans. */

@@ -63,6 +63,7 @@ SIGNATURES = {
     "pft_cloud_download": (_i, [_vp, _vp, _sz, _i, _psz]),
     "pft_passthrough": (_i, [_vp, _vp, _vp, _i, _f, _f]),
     "pft_passthrough_voxel_grid": (_i, [_vp, _vp, _vp, _f, _i, _f, _f]),
+    "pft_approx_voxel_grid_pcl": (_i, [_vp, _vp, _vp, _f, _i, _f, _f]),
     "pft_prepare_model": (_i, [_vp, _vp, _vp, _f, _vp]),
     "pft_euclidean_clusters": (_i, [_vp, _vp, _d, _i, _i, _vp, _sz, _vp, _sz, _psz]),
     "pft_cloud_select_cluster": (_i, [_vp, _vp, _i, _vp]),

@@ -273,6 +273,13 @@ int pft_passthrough_voxel_grid(pft_context* ctx, const pft_cloud* in, pft_cloud*
   return run_voxel_grid(ctx, in, out, leaf, field, lo, hi);
 }
 
+int pft_approx_voxel_grid_pcl(pft_context* ctx, const pft_cloud* in, pft_cloud* out, float leaf, int field, float lo, float hi) {
+  int rc = check_filter_args(ctx, in, out, "pft_approx_voxel_grid_pcl");
+  if (rc) return rc;
+  if (field > 2) { set_last_error("pft_approx_voxel_grid_pcl: field must be <0 (off), 0, 1 or 2"); return PFT_ERR_INVALID; }
+  return run_approx_voxel_grid_pcl(ctx, in, out, leaf, field, lo, hi);
+}
+
 int pft_prepare_model(pft_context* ctx, const pft_cloud* raw, pft_cloud* out, float leaf, float* centroid3) {
   int rc = check_filter_args(ctx, raw, out, "pft_prepare_model");
   if (rc) return rc;

@@ -210,6 +210,45 @@ __global__ void k1_final_kernel(const CloudHeader* __restrict__ out_hdr, const d
   }
 }
 
+// ---- pcl::ApproximateVoxelGrid<PointXYZRGBA>::applyFilter reproduced exactly (PCL-1.8.0 filters/impl/approximate_voxel_grid.hpp,
+// SURVEY A.1; ref: src/auto_tracking.cpp:563-575): a 512-entry direct-mapped cache of voxel accumulators walked in input
+// order, an entry flushed (a partial centroid emitted) whenever another voxel hashes onto it, the rest flushed at the end
+// in slot order.  Output order, duplicate partial centroids and the sequential fp32 sums all depend on the input order:
+// the algorithm is a sequential scan, run here by ONE thread.  Parity mode (pft_approx_voxel_grid_pcl); the product
+// path is the exact one-centroid-per-voxel reduction above.
+__global__ void approx_voxel_grid_pcl_kernel(const float4* __restrict__ in, const CloudHeader* __restrict__ in_hdr, float inv, int field, float lo,
+                                             float hi, float4* __restrict__ out, CloudHeader* out_hdr) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  constexpr int kHist = 512;
+  __shared__ int s_key[kHist][4];   // ix, iy, iz, count
+  __shared__ float s_acc[kHist][6]; // x, y, z, r, g, b  (upstream's 7-vector also carries the constant 1 of the padding lane)
+  for (int k = 0; k < kHist; ++k) { s_key[k][3] = 0; for (int q = 0; q < 6; ++q) s_acc[k][q] = 0.f; }
+  const int n = in_hdr->n;
+  int op = 0;
+  auto flush = [&](int k) {
+    const float cnt = (float)s_key[k][3];
+    const unsigned int r = (unsigned int)(int)(s_acc[k][3] / cnt), g = (unsigned int)(int)(s_acc[k][4] / cnt), b = (unsigned int)(int)(s_acc[k][5] / cnt);
+    out[op++] = make_float4(s_acc[k][0] / cnt, s_acc[k][1] / cnt, s_acc[k][2] / cnt, __uint_as_float((r << 16) | (g << 8) | b));
+  };
+  for (int i = 0; i < n; ++i) {
+    const float4 p = in[i];
+    if (!passes(p, field, lo, hi)) continue;  // the PassThrough that precedes the grid (ref :637), order preserving
+    const int ix = (int)floorf(p.x * inv), iy = (int)floorf(p.y * inv), iz = (int)floorf(p.z * inv);
+    const int k = (int)((unsigned int)(ix * 7171 + iy * 3079 + iz * 4231) & (unsigned int)(kHist - 1));
+    if (s_key[k][3] && (ix != s_key[k][0] || iy != s_key[k][1] || iz != s_key[k][2])) {
+      flush(k);
+      s_key[k][3] = 0;
+      for (int q = 0; q < 6; ++q) s_acc[k][q] = 0.f;
+    }
+    s_key[k][0] = ix; s_key[k][1] = iy; s_key[k][2] = iz; s_key[k][3]++;
+    const unsigned int rgba = __float_as_uint(p.w);
+    s_acc[k][0] += p.x; s_acc[k][1] += p.y; s_acc[k][2] += p.z;
+    s_acc[k][3] += (float)((rgba >> 16) & 0xffu); s_acc[k][4] += (float)((rgba >> 8) & 0xffu); s_acc[k][5] += (float)(rgba & 0xffu);
+  }
+  for (int k = 0; k < kHist; ++k) if (s_key[k][3]) flush(k);
+  out_hdr->n = op;
+}
+
 // ---- centroid (fp64 sums, exact) and in-place translation by -centroid; one block.
 __global__ void __launch_bounds__(1024) centre_kernel(float4* pts, const CloudHeader* __restrict__ hdr, float* centroid3) {
   __shared__ double red[32];
@@ -352,6 +391,16 @@ int run_voxel_grid(pft_context* ctx, const pft_cloud* in, pft_cloud* out, float 
   }
   PFT_CUDA_TRY(cudaGraphLaunch(ctx->k1_exec[slot], ctx->stream));
   g_launch_count += 6;  // the six kernels of the sequence
+  return PFT_OK;
+}
+
+int run_approx_voxel_grid_pcl(pft_context* ctx, const pft_cloud* in, pft_cloud* out, float leaf, int field, float lo, float hi) {
+  if (!(leaf > 0.f)) { set_last_error("leaf size must be positive"); return PFT_ERR_INVALID; }
+  int rc = out->ensure(in->capacity);
+  if (rc) return rc;
+  approx_voxel_grid_pcl_kernel<<<1, 32, 0, ctx->stream>>>(in->d_pts(), in->d_hdr(), 1.0f / leaf, field, lo, hi, out->d_pts(), out->d_hdr());
+  PFT_LAUNCH_CHECK();
+  out->host_n = -1;
   return PFT_OK;
 }
 

@@ -67,6 +67,7 @@ int launch_unpack_pointcloud2(cudaStream_t s, const void* src, float4* dst, unsi
 int launch_set_header(cudaStream_t s, CloudHeader* hdr, int n);
 int run_passthrough(pft_context* ctx, const pft_cloud* in, pft_cloud* out, int field, float lo, float hi, int drop_zero);
 int run_voxel_grid(pft_context* ctx, const pft_cloud* in, pft_cloud* out, float leaf, int field, float lo, float hi);
+int run_approx_voxel_grid_pcl(pft_context* ctx, const pft_cloud* in, pft_cloud* out, float leaf, int field, float lo, float hi);
 int run_centre_on_centroid(pft_context* ctx, pft_cloud* cloud, float* d_centroid3);
 
 }  // namespace pft

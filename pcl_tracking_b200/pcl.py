@@ -266,6 +266,12 @@ class VoxelGrid:
         self.ctx = ctx or Context.default()
         self._leaf, self._in = 0.01, None
         self._field, self._lo, self._hi = -1, 0.0, 0.0
+        self._pcl_approx = False
+
+    def setPclApproximateMode(self, on=True):
+        """Parity mode: reproduce pcl::ApproximateVoxelGrid exactly (512-entry cache, partial centroids on eviction,
+        input-order dependent; sequential on one GPU thread) instead of one exact centroid per voxel."""
+        self._pcl_approx = bool(on)
 
     def setLeafSize(self, lx, ly=None, lz=None):
         ly = lx if ly is None else ly
@@ -283,7 +289,8 @@ class VoxelGrid:
 
     def filter(self, out=None):
         out = PointCloud(ctx=self.ctx) if out is None else out
-        check(capi.load().pft_passthrough_voxel_grid(self.ctx._h, self._in._h, out._h, self._leaf, self._field, self._lo, self._hi))
+        fn = capi.load().pft_approx_voxel_grid_pcl if self._pcl_approx else capi.load().pft_passthrough_voxel_grid
+        check(fn(self.ctx._h, self._in._h, out._h, self._leaf, self._field, self._lo, self._hi))
         return out
 
 

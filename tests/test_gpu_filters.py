@@ -303,3 +303,31 @@ def test_segment_plane_feeds_the_clustering():
     ec = pcl.EuclideanClusterExtraction()
     ec.setClusterTolerance(0.02); ec.setMinClusterSize(500); ec.setMaxClusterSize(25000); ec.setInputCloud(seg.rest)
     assert len(ec.extract()) == 3
+
+
+@pytest.mark.parametrize("n,seed,leaf", [(0, 1, 0.01), (5, 2, 0.01), (20000, 3, 0.05), (60000, 4, 0.01)])
+def test_pcl_approximate_voxel_grid_parity_mode(n, seed, leaf):
+    """The reference's own downsample (pcl::ApproximateVoxelGrid, ref: src/auto_tracking.cpp:563-575) reproduced bit for
+    bit, duplicates and flush order included: PassThrough(z) + the 512-entry cache walked in input order."""
+    pts = _random_cloud(n, seed, span=0.6)
+    want = oracle.approx_voxel_grid_pcl(oracle.passthrough(pts, 2, 0.0, 10.0), leaf)
+    vg = pcl.ApproximateVoxelGrid()
+    vg.setLeafSize(leaf); vg.setPassThrough("z", 0.0, 10.0); vg.setPclApproximateMode(True)
+    vg.setInputCloud(pcl.PointCloud(pts))
+    got = vg.filter().to_numpy()
+    assert len(got) == len(want)
+    assert np.array_equal(_bits(got), _bits(want))
+    if n >= 20000:
+        # upstream's cache emits some voxels more than once; the production path emits each voxel exactly once
+        vg.setPclApproximateMode(False)
+        assert len(vg.filter().to_numpy()) < len(want)
+
+
+def test_pcl_approximate_voxel_grid_on_a_kinect_frame():
+    pts, _ = synth.render(0, synth.default_objects(1))
+    want = oracle.approx_voxel_grid_pcl(oracle.passthrough(pts, 2, 0.0, 10.0), 0.01)
+    vg = pcl.ApproximateVoxelGrid()
+    vg.setLeafSize(0.01); vg.setPassThrough("z", 0.0, 10.0); vg.setPclApproximateMode(True)
+    vg.setInputCloud(pcl.PointCloud(pts))
+    got = vg.filter().to_numpy()
+    assert np.array_equal(_bits(got), _bits(want))
