@@ -375,8 +375,13 @@ template <typename PointT> struct NearestPairPointCloudCoherence {
   void setMaximumDistance(double d) { maximum_distance = d; }
   std::vector<std::shared_ptr<PointCoherence<PointT>>> point_coherences;
   double resolution = 0.01, maximum_distance = 1.79769313486231570815e308;
+  bool pcl_approximate_search = false;
 };
-template <typename PointT> struct ApproxNearestPairPointCloudCoherence : NearestPairPointCloudCoherence<PointT> {};
+// Both classes run the exact search unless setPclApproximateSearch(true) asks for the parity mode that reproduces
+// upstream's greedy approxNearestSearch (PFT_NN_PCL_APPROX: same misses as PCL, far slower).
+template <typename PointT> struct ApproxNearestPairPointCloudCoherence : NearestPairPointCloudCoherence<PointT> {
+  void setPclApproximateSearch(bool on) { this->pcl_approximate_search = on; }
+};
 
 // pcl::tracking::ParticleFilterOMPTracker (ref :201-206)
 template <typename PointT, typename StateT>
@@ -409,7 +414,7 @@ class ParticleFilterOMPTracker {
         use_h = 1; sd(PFT_HSV_WEIGHT, hsv->weight); sd(PFT_H_WEIGHT, hsv->h_weight); sd(PFT_S_WEIGHT, hsv->s_weight); sd(PFT_V_WEIGHT, hsv->v_weight);
       } else throw pft::Error(PFT_ERR_INVALID, "unsupported point coherence");
     }
-    si(PFT_USE_DISTANCE, use_d); si(PFT_USE_HSV, use_h); si(PFT_NN_MODE, PFT_NN_EXACT);
+    si(PFT_USE_DISTANCE, use_d); si(PFT_USE_HSV, use_h); si(PFT_NN_MODE, c->pcl_approximate_search ? PFT_NN_PCL_APPROX : PFT_NN_EXACT);
     sd(PFT_MAX_DIST, c->maximum_distance); sd(PFT_SEARCH_RESOLUTION, c->resolution);
     coherence_ = c;
   }

@@ -162,7 +162,12 @@ typedef enum {
   PFT_BIN_SIZE = 43           /* setBinSize                (ref :214-221) */
 } pft_key;
 
-typedef enum { PFT_NN_EXACT = 0 } pft_nn_mode;
+typedef enum {
+  PFT_NN_EXACT = 0,      /* true nearest neighbour, ties to the lower index (the product path) */
+  PFT_NN_PCL_APPROX = 1  /* parity mode: pcl::octree approxNearestSearch of ApproxNearestPairPointCloudCoherence
+                            (ref: src/auto_tracking.cpp:235-238) -- greedy descent, may miss the nearest point; the
+                            octree is rebuilt sequentially by every weight(), far slower than PFT_NN_EXACT */
+} pft_nn_mode;
 /* PFT_SAMPLER_ALIAS_PCL: upstream's Walker alias table (genAliasTable / sampleWithReplacement), built sequentially on
  * one GPU thread -- parity mode: same ancestors as PCL for the same uniforms.  PFT_SAMPLER_CDF (default): inverse-CDF on
  * a fixed-point cumulative table built in parallel (same distribution).  PFT_SAMPLER_CDF_VDC: one uniform + van der

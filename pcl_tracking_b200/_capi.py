@@ -28,7 +28,7 @@ THREADS, PARTICLE_NUM, MAX_PARTICLE_NUM, ITERATION_NUM, NN_MODE, USE_HSV, USE_DI
 (DELTA, EPSILON, ALPHA, MOTION_RATIO, MAX_DIST, DIST_WEIGHT, HSV_WEIGHT, H_WEIGHT, S_WEIGHT, V_WEIGHT, SEARCH_RESOLUTION,
  RESAMPLE_LIKELIHOOD_THR) = range(20, 32)
 STEP_NOISE_COV, INIT_NOISE_COV, INIT_NOISE_MEAN, BIN_SIZE = range(40, 44)
-NN_EXACT = 0
+NN_EXACT, NN_PCL_APPROX = 0, 1
 PEER_HANDLE_BYTES = 64
 SAMPLER_ALIAS_PCL, SAMPLER_CDF, SAMPLER_CDF_VDC = 0, 1, 2
 

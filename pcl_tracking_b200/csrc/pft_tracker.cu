@@ -154,7 +154,8 @@ struct pft_tracker {
   int graph_nodes = 0;
   // device buffers
   DevBuf st, parts[2], mats, slot_aabb, model, model_perm, model_tmp, sort_keys, sort_idx, bbox, raw, partial, cdf, cdf_total, ancestors, bin_keys, tbl_rep,
-      tbl_min, slot_of, klb, d_usel, d_normals, d_umot, idx_hdr, cell_start, ipts, ihsv, icount, dbg_idx, dbg_d2, d_trans, row_table, flists, fneeded, fneeded_list, ffar_list, xlists, xcount, result_box, alias_a, alias_q, alias_hl;
+      tbl_min, slot_of, klb, d_usel, d_normals, d_umot, idx_hdr, cell_start, ipts, ihsv, icount, dbg_idx, dbg_d2, d_trans, row_table, flists, fneeded, fneeded_list, ffar_list, xlists, xcount, result_box, alias_a, alias_q, alias_hl, oct_hdr, oct_nodes, oct_next;
+  int oct_node_cap = 0;
   int weight_smem = 0;  // dynamic shared memory of the weight kernel (bytes)
   int tbl_size = 0;
   int n_slots = 0;
@@ -190,7 +191,7 @@ void release_all(pft_tracker* t) {
   DevBuf* bufs[] = {&t->st, &t->parts[0], &t->parts[1], &t->mats, &t->slot_aabb, &t->model, &t->model_perm, &t->model_tmp, &t->sort_keys, &t->sort_idx,
                     &t->bbox, &t->raw, &t->partial, &t->cdf, &t->cdf_total, &t->ancestors, &t->bin_keys, &t->tbl_rep, &t->tbl_min, &t->slot_of, &t->klb,
                     &t->d_usel, &t->d_normals, &t->d_umot, &t->idx_hdr, &t->cell_start, &t->ipts, &t->ihsv, &t->icount, &t->dbg_idx,
-                    &t->dbg_d2, &t->d_trans, &t->row_table, &t->flists, &t->fneeded, &t->fneeded_list, &t->ffar_list, &t->xlists, &t->xcount, &t->result_box, &t->alias_a, &t->alias_q, &t->alias_hl};
+                    &t->dbg_d2, &t->d_trans, &t->row_table, &t->flists, &t->fneeded, &t->fneeded_list, &t->ffar_list, &t->xlists, &t->xcount, &t->result_box, &t->alias_a, &t->alias_q, &t->alias_hl, &t->oct_hdr, &t->oct_nodes, &t->oct_next};
   for (auto* b : bufs) b->release();
 }
 
@@ -557,6 +558,40 @@ int weight_comm_box(pft_tracker* t) {
   return PFT_OK;
 }
 
+// Parity mode PFT_NN_PCL_APPROX (see octree_build_kernel): the octree of the cropped cloud and the greedy search
+int weight_eval_pcl_approx(pft_tracker* t, bool force_raw) {
+  cudaStream_t s = t->run_stream();
+  const int sm = t->ctx->sm_count;
+  TrackerState* st = t->st.as<TrackerState>();
+  const pft_cloud* in = t->input;
+  octree_build_kernel<<<1, 32, 0, s>>>(in->d_pts(), in->d_hdr(), t->idx_hdr.as<IndexHeader>(), t->search_res, t->oct_nodes.as<OctNodeD>(), t->oct_node_cap,
+                                       t->oct_next.as<int>(), t->oct_hdr.as<OctHeaderD>());
+  PFT_LAUNCH_CHECK();
+  stage_mark(t, "octree_build_kernel");
+  WeightApproxArgs w;
+  w.st = st; w.oct = t->oct_hdr.as<OctHeaderD>(); w.nodes = t->oct_nodes.as<OctNodeD>(); w.next = t->oct_next.as<int>();
+  w.scene = in->d_pts(); w.model = t->model.as<float4>(); w.model_perm = t->model_perm.as<int>(); w.M = t->M; w.mats = t->mats.as<float>();
+  w.partial = t->partial.as<double>(); w.chunks = t->chunks; w.chunk_len = t->chunk_len; w.n_max = t->n_cap; w.nranks = t->nranks; w.rank_id = t->rank;
+  w.co = make_coherence(t);
+  w.dbg_k = t->debug_nn; w.dbg_idx = t->dbg_idx.as<int>(); w.dbg_d2 = t->dbg_d2.as<float>();
+  if (t->timing) {
+    while ((int)t->ev_w.size() < 2 * (t->n_ev_used + 1)) { cudaEvent_t e; PFT_CUDA_TRY(cudaEventCreate(&e)); t->ev_w.push_back(e); }
+    PFT_CUDA_TRY(cudaEventRecord(t->ev_w[2 * t->n_ev_used], s));
+  }
+  weight_approx_kernel<<<sm * 8, 256, 0, s>>>(w);
+  PFT_LAUNCH_CHECK();
+  stage_mark(t, "weight_approx_kernel");
+  if (t->timing) { PFT_CUDA_TRY(cudaEventRecord(t->ev_w[2 * t->n_ev_used + 1], s)); t->n_ev_used++; }
+  if (t->nranks > 1 || force_raw) {
+    const int local_cap = t->slice_cap();
+    raw_weights_kernel<<<blocks_for(local_cap, 256, sm * 4), 256, 0, s>>>(st, t->partial.as<double>(), t->chunks, t->n_cap, t->raw.as<float>(), local_cap,
+                                                                         t->nranks, t->rank, t->peers, t->peer_mode ? 1 : 0);
+    PFT_LAUNCH_CHECK();
+    stage_mark(t, "raw_weights_kernel");
+  }
+  return PFT_OK;
+}
+
 // weight(), part 2: cropInputPointCloud + search index rebuild (K2), coherence of this rank's particles (K3)
 int weight_phase_eval(pft_tracker* t, bool force_raw = false) {
   int rc = check_weight_ready(t);
@@ -583,7 +618,7 @@ int weight_phase_eval(pft_tracker* t, bool force_raw = false) {
                                               t->ihsv.as<unsigned int>());
   PFT_LAUNCH_CHECK();
   stage_mark(t, "index_scatter_kernel");
-  if (t->list_max_cells > 0 && t->list_mode) {
+  if (t->list_max_cells > 0 && t->list_mode && t->nn_mode == PFT_NN_EXACT) {
     // dynamic shared memory: one bit per fine cell the lists are sized for
     cand_mark_kernel<<<sm * 3, 256, (size_t)(t->list_max_cells / 8 + 64), s>>>(st, hdr, t->model.as<float4>(), t->M, t->mats.as<float>(), t->fneeded.as<unsigned int>(), t->nranks, t->rank);
     PFT_LAUNCH_CHECK();
@@ -602,6 +637,7 @@ int weight_phase_eval(pft_tracker* t, bool force_raw = false) {
     PFT_LAUNCH_CHECK();
     stage_mark(t, "cand_build_far_kernel");
   }
+  if (t->nn_mode == PFT_NN_PCL_APPROX) return weight_eval_pcl_approx(t, force_raw);
   WeightArgs a;
   a.st = st; a.hdr = hdr;
   a.flists = t->flists.as<unsigned short>(); a.xlists = t->xlists.as<unsigned short>();
@@ -713,6 +749,20 @@ int prepare_compute(pft_tracker* t) {
     if ((rc = t->alias_q.reserve((size_t)t->n_cap * sizeof(double)))) return rc;
     if ((rc = t->alias_hl.reserve((size_t)t->n_cap * sizeof(int)))) return rc;
   }
+  if (t->nn_mode == PFT_NN_PCL_APPROX) {
+    // parity mode: upstream's pointer octree, rebuilt by every weight() (sized for the whole input cloud: one leaf chain
+    // of at most 31 nodes per point plus the roots added while the box grows)
+    const size_t cap_pts = std::max<size_t>(t->input ? t->input->capacity : 0, 1);
+    const size_t want_nodes = cap_pts * 12 + 128;
+    if (t->oct_next.bytes < cap_pts * sizeof(int) || (size_t)t->oct_node_cap < want_nodes) {
+      invalidate_graph(t);
+      PFT_CUDA_TRY(cudaStreamSynchronize(t->run_stream()));
+      if ((rc = t->oct_hdr.reserve(sizeof(OctHeaderD)))) return rc;
+      if ((rc = t->oct_next.reserve(cap_pts * sizeof(int)))) return rc;
+      if ((rc = t->oct_nodes.reserve(want_nodes * sizeof(OctNodeD)))) return rc;
+      t->oct_node_cap = (int)want_nodes;
+    }
+  }
   if (t->debug_nn > 0) {
     const size_t need = (size_t)t->debug_nn * t->M;
     if (need * sizeof(int) > t->dbg_idx.bytes) {
@@ -780,7 +830,8 @@ int pft_tracker_set_i(pft_tracker* t, int key, int v) {
       if (v < 0) { set_last_error("iteration number must be >= 0"); return PFT_ERR_INVALID; }
       t->iteration_num = v; break;
     case PFT_NN_MODE:
-      if (v != PFT_NN_EXACT) { set_last_error("only PFT_NN_EXACT is implemented (exact grid search, ties to the lower index)"); return PFT_ERR_INVALID; }
+      if (v != PFT_NN_EXACT && v != PFT_NN_PCL_APPROX) { set_last_error("unknown nearest-neighbour mode %d", v); return PFT_ERR_INVALID; }
+      if (v != t->nn_mode) invalidate_graph(t);
       t->nn_mode = v; break;
     case PFT_USE_HSV: t->use_hsv = v != 0; break;
     case PFT_USE_DISTANCE: t->use_dist = v != 0; break;

@@ -1384,6 +1384,204 @@ __global__ void __launch_bounds__(THREADS, 1) weight_kernel(const WeightArgs a) 
   }
 }
 
+// ------------------------------------------------------------------ parity mode: ApproxNearestPairPointCloudCoherence
+// The reference's own coherence (ref: src/auto_tracking.cpp:235-238, :250-252) searches with
+// pcl::octree::OctreePointCloudSearch::approxNearestSearch: a greedy descent to the child whose voxel centre is
+// nearest, then a linear scan of that leaf -- it may miss the true nearest neighbour.  PFT_NN_PCL_APPROX reproduces it
+// (PCL-1.8.0 octree/impl/octree_pointcloud.hpp, octree_search.hpp): the pointer octree is rebuilt by
+// every weight() exactly as upstream builds it -- point by point in cloud order, the bounding box doubling towards
+// each point that falls outside (the resulting keys depend on that order), which is a sequential process and runs on
+// ONE thread -- and queried by every (particle, model point) in parallel.  Not the product path: the default
+// (PFT_NN_EXACT) finds the true nearest neighbour and is ~100x faster.
+struct OctNodeD { int child[8]; int head, tail; };
+struct OctHeaderD {
+  double mn[3], mx[3];
+  double res;
+  int depth, root, leaf_count, n_nodes, bbox_defined, overflow, pad0, pad1;
+};
+
+__device__ inline int oct_new_node(OctNodeD* nodes, OctHeaderD& H, int cap) {
+  if (H.n_nodes >= cap) { H.overflow = 1; return 0; }
+  OctNodeD& n = nodes[H.n_nodes];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) n.child[c] = -1;
+  n.head = -1; n.tail = -1;
+  return H.n_nodes++;
+}
+
+__global__ void octree_build_kernel(const float4* __restrict__ scene, const CloudHeader* __restrict__ scene_hdr, const IndexHeader* __restrict__ ihdr,
+                                    double res, OctNodeD* nodes, int node_cap, int* __restrict__ next, OctHeaderD* out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const IndexHeader h = *ihdr;
+  OctHeaderD H;
+  for (int d = 0; d < 3; ++d) { H.mn[d] = 0.0; H.mx[d] = 0.0; }
+  H.res = res; H.depth = 0; H.leaf_count = 0; H.n_nodes = 0; H.bbox_defined = 0; H.overflow = 0; H.pad0 = H.pad1 = 0;
+  H.root = oct_new_node(nodes, H, node_cap);
+  const double min_value = (double)1.1920928955078125e-07f;  // std::numeric_limits<float>::epsilon()
+  const int ns = h.valid ? scene_hdr->n : 0;
+  for (int i = 0; i < ns; ++i) {
+    const float4 p = scene[i];
+    if (!in_crop(p, h)) continue;  // cropInputPointCloud: the octree indexes the cropped cloud, in input order
+    const double v[3] = {(double)p.x, (double)p.y, (double)p.z};
+    // adoptBoundingBoxToPoint
+    while (true) {
+      bool up[3], any = false;
+      for (int d = 0; d < 3; ++d) { const bool lo = v[d] < H.mn[d]; up[d] = v[d] >= H.mx[d]; any = any || lo || up[d]; }
+      if (!(any || !H.bbox_defined)) break;
+      if (H.bbox_defined) {
+        const int ci = ((!up[0]) << 2) | ((!up[1]) << 1) | (!up[2]);
+        const int nr = oct_new_node(nodes, H, node_cap);
+        nodes[nr].child[ci] = H.root;
+        H.root = nr;
+        double side = (double)(1 << H.depth) * H.res;
+        for (int d = 0; d < 3; ++d) if (!up[d]) H.mn[d] -= side;
+        H.depth++;
+        side = (double)(1 << H.depth) * H.res - min_value;
+        for (int d = 0; d < 3; ++d) H.mx[d] = H.mn[d] + side;
+        if (H.depth > 30 || H.overflow) { H.overflow = 1; break; }
+      } else {
+        for (int d = 0; d < 3; ++d) { H.mn[d] = v[d] - H.res / 2; H.mx[d] = v[d] + H.res / 2; }
+        // getKeyBitSize
+        unsigned int mk[3];
+        for (int d = 0; d < 3; ++d) mk[d] = (unsigned int)ceil((H.mx[d] - H.mn[d]) / H.res);
+        const unsigned int max_voxels = max(max(max(mk[0], mk[1]), mk[2]), 2u);
+        H.depth = (int)fmax(fmin(30.0, ceil(log2((double)max_voxels) - min_value)), 0.0);
+        const double side = (double)(1 << H.depth) * H.res - min_value;
+        if (H.leaf_count == 0) {
+          for (int d = 0; d < 3; ++d) { const double over = (side - (H.mx[d] - H.mn[d])) / 2.0; H.mn[d] -= over; H.mx[d] += over; }
+        } else {
+          for (int d = 0; d < 3; ++d) H.mx[d] = H.mn[d] + side;
+        }
+        H.bbox_defined = 1;
+      }
+    }
+    if (H.overflow) break;
+    // addPointIdx: key from the CURRENT box, descend / create, append to the leaf (insertion order)
+    const unsigned int key[3] = {(unsigned int)((v[0] - H.mn[0]) / H.res), (unsigned int)((v[1] - H.mn[1]) / H.res), (unsigned int)((v[2] - H.mn[2]) / H.res)};
+    int n = H.root;
+    for (int level = H.depth - 1; level >= 0; --level) {
+      const unsigned int mask = 1u << level;
+      const int ci = ((!!(key[0] & mask)) << 2) | ((!!(key[1] & mask)) << 1) | (!!(key[2] & mask));
+      if (nodes[n].child[ci] < 0) { const int c = oct_new_node(nodes, H, node_cap); nodes[n].child[ci] = c; }
+      n = nodes[n].child[ci];
+    }
+    if (nodes[n].head < 0) { nodes[n].head = i; H.leaf_count++; } else next[nodes[n].tail] = i;
+    nodes[n].tail = i;
+    next[i] = -1;
+  }
+  *out = H;
+}
+
+// approxNearestSearch + approxNearestSearchRecursive.  Returns the index IN THE INPUT CLOUD (-1: empty tree).
+__device__ inline int octree_approx_nearest(const OctHeaderD& H, const OctNodeD* __restrict__ nodes, const int* __restrict__ next,
+                                            const float4* __restrict__ scene, float qx, float qy, float qz, float& d2_out) {
+  d2_out = 0.f;
+  if (H.leaf_count == 0) return -1;
+  int node = H.root;
+  unsigned int key[3] = {0u, 0u, 0u};
+  for (int tree_depth = 1; tree_depth <= H.depth; ++tree_depth) {
+    double best = 1.7976931348623157e308;
+    int best_ci = -1;
+    unsigned int bk[3] = {0u, 0u, 0u};
+    const double cell = H.res * (double)(1 << (H.depth - tree_depth));
+    for (int ci = 0; ci < 8; ++ci) {
+      if (nodes[node].child[ci] < 0) continue;
+      const unsigned int nk[3] = {(key[0] << 1) + (unsigned int)(!!(ci & 4)), (key[1] << 1) + (unsigned int)(!!(ci & 2)), (key[2] << 1) + (unsigned int)(!!(ci & 1))};
+      const float cx = (float)(((double)nk[0] + 0.5) * cell + H.mn[0]);
+      const float cy = (float)(((double)nk[1] + 0.5) * cell + H.mn[1]);
+      const float cz = (float)(((double)nk[2] + 0.5) * cell + H.mn[2]);
+      const float dx = cx - qx, dy = cy - qy, dz = cz - qz;
+      const double dist = (double)((dx * dx + dy * dy) + dz * dz);
+      if (dist >= best) continue;
+      best = dist; best_ci = ci; bk[0] = nk[0]; bk[1] = nk[1]; bk[2] = nk[2];
+    }
+    if (best_ci < 0) return -1;
+    node = nodes[node].child[best_ci];
+    key[0] = bk[0]; key[1] = bk[1]; key[2] = bk[2];
+  }
+  // leaf: linear scan in insertion order, the first of equally near points wins
+  double smallest = 1.7976931348623157e308;
+  int idx = -1;
+  for (int i = nodes[node].head; i >= 0; i = next[i]) {
+    const float4 c = scene[i];
+    const float dx = c.x - qx, dy = c.y - qy, dz = c.z - qz;
+    const double sd = (double)((dx * dx + dy * dy) + dz * dz);
+    if (sd >= smallest) continue;
+    idx = i; smallest = sd; d2_out = (float)sd;
+  }
+  return idx;
+}
+
+struct WeightApproxArgs {
+  const TrackerState* st;
+  const OctHeaderD* oct; const OctNodeD* nodes; const int* next;
+  const float4* scene;        // the input cloud (rgba in .w)
+  const float4* model;        // {x,y,z,packed HSV} in tile order
+  const int* model_perm;
+  int M;
+  const float* mats;
+  double* partial;            // [chunks][n_max]
+  int chunks, chunk_len, n_max, nranks, rank_id;
+  CoherenceParams co;
+  int dbg_k; int* dbg_idx; float* dbg_d2;
+};
+
+__global__ void __launch_bounds__(256) weight_approx_kernel(const WeightApproxArgs a) {
+  __shared__ OctHeaderD H;
+  if (threadIdx.x == 0) H = *a.oct;
+  __syncthreads();
+  const int n = a.st->particle_num;
+  const int n_local = n > a.rank_id ? (n - a.rank_id + a.nranks - 1) / a.nranks : 0;
+  const int items = n_local * a.chunks;
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int item = warp; item < items; item += nwarps) {
+    const int il = item / a.chunks, c = item - il * a.chunks;
+    const int i = a.rank_id + il * a.nranks;
+    float m[12];
+    {
+      const float4* mp = reinterpret_cast<const float4*>(a.mats) + (size_t)i * 3;
+      const float4 r0 = mp[0], r1 = mp[1], r2 = mp[2];
+      m[0] = r0.x; m[1] = r0.y; m[2] = r0.z; m[3] = r0.w; m[4] = r1.x; m[5] = r1.y; m[6] = r1.z; m[7] = r1.w;
+      m[8] = r2.x; m[9] = r2.y; m[10] = r2.z; m[11] = r2.w;
+    }
+    const int j0 = c * a.chunk_len, j1 = min(a.M, j0 + a.chunk_len);
+    double val = 0.0;
+    for (int j = j0 + lane; j < j1; j += 32) {
+      const float4 mp = a.model[j];
+      float qx, qy, qz, d2 = FLT_MAX;
+      xform(m, mp.x, mp.y, mp.z, qx, qy, qz);
+      int idx = H.overflow ? -1 : octree_approx_nearest(H, a.nodes, a.next, a.scene, qx, qy, qz, d2);
+      if (idx < 0) d2 = FLT_MAX;
+      if (i < a.dbg_k) {
+        const size_t o = (size_t)i * a.M + a.model_perm[j];
+        a.dbg_idx[o] = idx;
+        a.dbg_d2[o] = d2;
+      }
+      if (idx >= 0 && (double)d2 < a.co.max_d2) {
+        double den = 1.0;
+        if (a.co.use_dist) { const double d = (double)sqrtf(d2); den = 1.0 + d * d * a.co.dist_w; }
+        if (a.co.use_hsv) {
+          const unsigned int sb = __float_as_uint(mp.w), tb = rgba_to_hsv_packed(__float_as_uint(a.scene[idx].w));
+          const float sh = (float)(sb & 0xff) / 180.0f, ss = (float)((sb >> 8) & 0xff) / 255.0f, sv = (float)((sb >> 16) & 0xff) / 255.0f;
+          const float th = (float)(tb & 0xff) / 180.0f, ts = (float)((tb >> 8) & 0xff) / 255.0f, tv = (float)((tb >> 16) & 0xff) / 255.0f;
+          const float hd = fabsf(sh - th);
+          float hd2;
+          if (sh < th) hd2 = fabsf(1.0f + sh - th); else hd2 = fabsf(1.0f + th - sh);
+          float h_diff;
+          if (hd < hd2) h_diff = a.co.h_w * hd * hd; else h_diff = a.co.h_w * hd2 * hd2;
+          const float s_diff = a.co.s_w * (ss - ts) * (ss - ts);
+          const float v_diff = a.co.v_w * (sv - tv) * (sv - tv);
+          den *= 1.0 + a.co.hsv_w * (double)(h_diff + s_diff + v_diff);
+        }
+        val += 1.0 / den;
+      }
+    }
+    val = warp_sum(val);
+    if (lane == 0) a.partial[(size_t)c * a.n_max + i] = val;
+  }
+}
+
 // Where particle i's raw weight lives in the all-gathered buffer [nranks][slice_cap].
 __device__ __forceinline__ int raw_slot(int i, int nranks, int slice_cap) { return (i % nranks) * slice_cap + i / nranks; }
 

@@ -363,8 +363,17 @@ class NearestPairPointCloudCoherence:
 
 
 class ApproxNearestPairPointCloudCoherence(NearestPairPointCloudCoherence):
-    """pcl::tracking::ApproxNearestPairPointCloudCoherence (ref :235-236).  The GPU index answers the
-    exact nearest neighbour for both coherence classes ("Approx vs exact")."""
+    """pcl::tracking::ApproxNearestPairPointCloudCoherence (ref :235-236).  By default the GPU index answers the
+    exact nearest neighbour for both coherence classes (DESIGN.md, "Approx vs exact");
+    setPclApproximateSearch(True) selects the parity mode that reproduces upstream's greedy octree descent
+    (approxNearestSearch), misses included -- far slower, for result comparisons against a PCL run only."""
+
+    def __init__(self):
+        super().__init__()
+        self.pcl_approximate_search = False
+
+    def setPclApproximateSearch(self, on=True):
+        self.pcl_approximate_search = bool(on)
 
 
 # ------------------------------------------------------------------ trackers
@@ -453,7 +462,7 @@ class ParticleFilterOMPTracker:
                 raise NotImplementedError("point coherence %r is not on the reference's path" % (pc,))
         self._si(capi.USE_DISTANCE, use_d)
         self._si(capi.USE_HSV, use_h)
-        self._si(capi.NN_MODE, capi.NN_EXACT)
+        self._si(capi.NN_MODE, capi.NN_PCL_APPROX if getattr(coherence, "pcl_approximate_search", False) else capi.NN_EXACT)
         self._sd(capi.MAX_DIST, coherence.maximum_distance)
         if coherence.search is not None:
             self._sd(capi.SEARCH_RESOLUTION, coherence.search.resolution)

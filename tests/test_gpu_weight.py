@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 import oracle
-from pcl_tracking_b200 import pcl
+from pcl_tracking_b200 import pcl, synth
 from tests import util
 
 pytestmark = pytest.mark.gpu
@@ -154,3 +154,71 @@ def test_weight_dense_scene_long_lists():
         np.testing.assert_array_equal(gi[m], cidx[oi[m]])
         np.testing.assert_array_equal(gd[m], od[m])
     np.testing.assert_allclose(g.rawWeights(), o.raw_weights(), rtol=W_RTOL)
+
+
+# ------------------------------------------------------------------ parity mode: upstream's approximate octree search
+def _approx_pair(kld, n_particles, use_hsv, search_res=0.01, **kw):
+    g, o = util.make_pair(kld=kld, particle_num=n_particles, use_hsv=use_hsv, oracle_nn=oracle.NN_PCL_APPROX, search_res=search_res, **kw)
+    o.set_d(oracle.OCTREE_RES, search_res)
+    g._si(pcl.capi.NN_MODE, pcl.capi.NN_PCL_APPROX)
+    return g, o
+
+
+@pytest.mark.parametrize("seed,use_hsv,search_res", [(3, True, 0.01), (4, False, 0.01), (5, True, 0.025)])
+def test_weight_pcl_approx_mode_matches_oracle(seed, use_hsv, search_res):
+    """PFT_NN_PCL_APPROX: the greedy octree descent of ApproxNearestPairPointCloudCoherence (ref: src/auto_tracking.cpp
+    :235-236) -- same leaf, same point and same squared distance as the oracle's restatement of pcl::octree, for EVERY
+    query (the approximate search has no distance cut-off), and the same weights."""
+    scene, model, centre = util.small_case(seed, n_scene=5000, n_model=300)
+    g, o = _approx_pair(False, 40, use_hsv, search_res)
+    parts = util.particles_around(centre, 40, seed=seed + 100)
+    cloud = pcl.PointCloud(scene)
+    g.setReferenceCloud(model); g.setInputCloud(cloud); g.setParticles(parts); g.setDebugNN(8); g.weight()
+    o.set_reference(model); o.set_input(scene); o.set_particles(parts); o.weight(keep_nn=True)
+    cidx, _ = o.cropped()
+    assert g.croppedCount() == len(cidx)
+    for p in range(8):
+        gi, gd = g.nn(p, len(model))
+        oi, od = o.nn(p, len(model))
+        assert np.all(oi >= 0)
+        np.testing.assert_array_equal(gi, cidx[oi])
+        np.testing.assert_array_equal(gd, od)
+    np.testing.assert_allclose(g.rawWeights(), o.raw_weights(), rtol=W_RTOL, atol=0)
+    np.testing.assert_allclose(g.getParticles()["weight"], o.get_particles()["weight"], rtol=W_RTOL, atol=1e-12)
+
+
+def test_pcl_approx_mode_differs_from_exact_and_tracks():
+    """The approximate search misses true neighbours (so the two modes give different weights), and a whole KLD
+    compute() in the parity mode follows the oracle run in the same mode."""
+    scene, model, centre = util.small_case(6, n_scene=5000, n_model=300)
+    parts = util.particles_around(centre, 32, seed=9)
+    cloud = pcl.PointCloud(scene)
+    ge, _ = util.make_pair(kld=False, particle_num=32, use_hsv=True)
+    ge.setReferenceCloud(model); ge.setInputCloud(cloud); ge.setParticles(parts); ge.setDebugNN(4); ge.weight()
+    ga, _ = _approx_pair(False, 32, True)
+    ga.setReferenceCloud(model); ga.setInputCloud(cloud); ga.setParticles(parts); ga.setDebugNN(4); ga.weight()
+    worse = 0
+    for p in range(4):
+        ei, ed = ge.nn(p, len(model))
+        ai, ad = ga.nn(p, len(model))
+        m = ei >= 0
+        assert np.all(ad[m] >= ed[m])          # never nearer than the true nearest neighbour
+        worse += int((ad[m] > ed[m]).sum())
+    assert worse > 0
+    assert not np.array_equal(ga.rawWeights(), ge.rawWeights())
+
+    g, o = _approx_pair(True, 100, True, max_particle_num=220)
+    util.set_trans_both(g, o, centre)
+    d = synth.draws(2, 220, seed=23)
+    g.injectDraws(*d); o.inject_draws(*d)
+    g.setReferenceCloud(model); g.setInputCloud(cloud); g.compute()
+    o.set_reference(model); o.set_input(scene); o.compute()
+    gp, op = g.getParticles(), o.get_particles()
+    assert len(gp) == len(op)
+    same = g.ancestors() == o.ancestors()
+    assert same.mean() > 0.97
+    for k in ("x", "y", "z", "roll", "pitch", "yaw"):
+        np.testing.assert_allclose(gp[k][same], op[k][same], atol=1e-4)
+    gr, orr = g.getResult(), o.get_result()
+    for k in ("x", "y", "z"):
+        assert abs(float(gr[k]) - float(orr[k])) < 2e-3
