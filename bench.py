@@ -403,6 +403,22 @@ def main():
         compute_all()
         return [t.getResult() for t in trackers]  # D2H of the pose(s): synchronises
 
+    # the same with the ingest double-buffered: frame k+1 is copied on the library's copy stream while
+    # frame k is tracked; every step still copies one frame in and reads one pose back
+    upload_pair = [pcl.PointCloud(ctx=ctx), pcl.PointCloud(ctx=ctx)]
+
+    def prime_pipelined(k):
+        upload_pair[k % 2].upload_raw_async(pinned[frame_order(k, N_FRAMES)].value, n_pts)
+
+    def step_e2e_pipelined(k):
+        prime_pipelined(k + 1)
+        vg.setInputCloud(upload_pair[k % 2])
+        vg.filter(ds)
+        for t in trackers:
+            t.setInputCloud(ds)
+        compute_all()
+        return [t.getResult() for t in trackers]
+
     flush_buf = None if args.no_flush else torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
 
     def flush_l2():
@@ -469,6 +485,19 @@ def main():
     e2e_ms_per_step = e2e_ms / args.steps
     e2e_value = float(eval_count() - evals0) / args.steps / (e2e_ms_per_step * 1e-3)
 
+    e2e_pipe = None
+    if world == 1 and owns_frames:
+        k0 = W + 2 * args.steps
+        prime_pipelined(k0)
+        for k in range(3):
+            step_e2e_pipelined(k0 + k)
+        evals0 = eval_count()
+        pipe_ms, _ = timed(step_e2e_pipelined, args.steps, k0 + 3)
+        pipe_ms_per_step = pipe_ms / args.steps
+        e2e_pipe = {"value": float(eval_count() - evals0) / args.steps / (pipe_ms_per_step * 1e-3), "unit": UNIT, "ms_per_step": pipe_ms_per_step,
+                    "frames_per_s": 1e3 / pipe_ms_per_step, "h2d_bytes_per_step": int(frames[0].nbytes), "d2h_bytes_per_step": (32 + 64) * len(trackers),
+                    "how": "as e2e, with the upload of frame k+1 (pft_cloud_upload_async, copy stream) issued before frame k is tracked"}
+
     # ---- roofline of the dominant kernel (weight_kernel): CUDA events around every launch of it on the
     # library's stream, over `steps` more frames driven through the same code path without the graph
     for t in trackers:
@@ -526,6 +555,7 @@ def main():
             "frames_per_s": 1e3 / ms_per_step,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(frames[0].nbytes) * (world if scene_mode == "replicate" else 1), "d2h_bytes_per_step": (32 + 64) * len(trackers),
                     "ms_per_step": e2e_ms_per_step, "frames_per_s": 1e3 / e2e_ms_per_step},
+            "e2e_pipelined": e2e_pipe,
             "gpu_launches": int(launches),
             "graph_replays": int(graph_replays),
             "clocks": sampler.summary(),

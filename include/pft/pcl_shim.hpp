@@ -117,6 +117,17 @@ class PointCloud {
     width = w; height = h;
     mark_device_written();
   }
+  // The same on the context's copy stream (pft_cloud_upload_pointcloud2_async): returns at once, the copy overlaps the
+  // tracking enqueued after the call, the first consumer of this cloud waits for it on the device.  `data` must be
+  // pinned (pft_host_alloc) and stay untouched until that consumer has finished.  Use two clouds alternately.
+  void fromPointCloud2Async(const void* data, uint32_t w, uint32_t h, uint32_t point_step, uint32_t row_step, int off_x, int off_y, int off_z,
+                            int off_rgb, bool is_bigendian = false, const std::shared_ptr<pft::Context>& ctx = pft::Context::Default()) {
+    if (!dev_) { ctx_ = ctx; pft::check(pft_cloud_create(ctx_->get(), &dev_)); }
+    pft::check(pft_cloud_upload_pointcloud2_async(dev_, data, w, h, point_step, row_step, off_x, off_y, off_z, off_rgb, is_bigendian ? 1 : 0));
+    points.clear();
+    width = w; height = h;
+    mark_device_written();
+  }
   // a filter wrote the device mirror: the host vector is stale until download()
   void mark_device_written() { device_only_ = true; host_dirty_ = false; }
   void download() {

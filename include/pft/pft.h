@@ -80,6 +80,18 @@ PFT_API int pft_cloud_upload(pft_cloud* cloud, const void* host_points, size_t n
  * row-major, NaN points are kept (the PassThrough that follows drops them, ref :637). */
 PFT_API int pft_cloud_upload_pointcloud2(pft_cloud* cloud, const void* data, uint32_t width, uint32_t height, uint32_t point_step,
                                          uint32_t row_step, int32_t off_x, int32_t off_y, int32_t off_z, int32_t off_rgb, int is_bigendian);
+/* Frame ingest overlapped with the previous frame's compute.  Same arguments as the two uploads above,
+ * but the copy (and the unpack kernel) run on a copy stream of the context instead of its compute stream: the call
+ * returns at once, the copy starts when everything enqueued on the context BEFORE this call has finished (so earlier
+ * readers of `cloud` are safe), and it overlaps whatever is enqueued AFTER it.  The first library call that consumes
+ * `cloud` orders the compute stream behind the copy by itself (no host wait); pft_cloud_wait_upload does the same
+ * explicitly, e.g. before handing the context stream to foreign code.  The host buffer must be pinned
+ * (pft_host_alloc) and stay untouched until a consumer of the cloud has completed.  Typical frame loop with two
+ * clouds A/B: upload_async(B, frame k+1); filter(A) + compute (frame k); read the result; swap A and B. */
+PFT_API int pft_cloud_upload_async(pft_cloud* cloud, const void* host_points, size_t n, int layout);
+PFT_API int pft_cloud_upload_pointcloud2_async(pft_cloud* cloud, const void* data, uint32_t width, uint32_t height, uint32_t point_step,
+                                               uint32_t row_step, int32_t off_x, int32_t off_y, int32_t off_z, int32_t off_rgb, int is_bigendian);
+PFT_API int pft_cloud_wait_upload(pft_cloud* cloud);
 PFT_API int pft_cloud_size(pft_cloud* cloud, size_t* n);
 PFT_API int pft_cloud_download(pft_cloud* cloud, void* host_points, size_t capacity, int layout, size_t* n);
 

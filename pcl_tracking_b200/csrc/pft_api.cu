@@ -57,7 +57,67 @@ int pft_cloud::ensure(size_t cap) {
   return PFT_OK;
 }
 
+// Orders the context stream after an asynchronous upload into this cloud (no host wait).
+int pft_cloud::join_upload() const {
+  if (!upload_pending) return PFT_OK;
+  PFT_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ready, 0));
+  upload_pending = false;
+  return PFT_OK;
+}
+
 using namespace pft;
+
+namespace {
+
+// Common front of the asynchronous uploads: the copy stream, ordered after everything the context stream holds so far
+// (earlier readers of the cloud that is about to be overwritten).
+int begin_async_upload(pft_cloud* c, size_t n, cudaStream_t* cs) {
+  pft_context* ctx = c->ctx;
+  PFT_CUDA_TRY(cudaSetDevice(ctx->device));
+  if (!ctx->copy_stream) {
+    PFT_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    PFT_CUDA_TRY(cudaEventCreateWithFlags(&ctx->copy_fence, cudaEventDisableTiming));
+  }
+  if (!c->ready) PFT_CUDA_TRY(cudaEventCreateWithFlags(&c->ready, cudaEventDisableTiming));
+  int rc = c->ensure(n);
+  if (rc) return rc;
+  PFT_CUDA_TRY(cudaEventRecord(ctx->copy_fence, ctx->stream));
+  PFT_CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_fence, 0));
+  *cs = ctx->copy_stream;
+  return PFT_OK;
+}
+
+int end_async_upload(pft_cloud* c, size_t n, cudaStream_t cs) {
+  int rc = launch_set_header(cs, c->d_hdr(), (int)n);
+  if (rc) return rc;
+  PFT_CUDA_TRY(cudaEventRecord(c->ready, cs));
+  c->upload_pending = true;
+  c->host_n = (long long)n;
+  return PFT_OK;
+}
+
+int check_pointcloud2_layout(size_t n, uint32_t width, uint32_t point_step, uint32_t row_step, int32_t off_x, int32_t off_y, int32_t off_z, int32_t off_rgb,
+                             int is_bigendian) {
+  if (n > 0x7fffffffull) { set_last_error("cloud too large"); return PFT_ERR_INVALID; }
+  if (is_bigendian) { set_last_error("big-endian PointCloud2 data is not supported"); return PFT_ERR_INVALID; }
+  if (n) {
+    if (point_step < 12 || (point_step & 3) || (row_step & 3) || (size_t)row_step < (size_t)width * point_step) {
+      set_last_error("bad PointCloud2 strides: point_step %u, row_step %u, width %u (4-byte multiples, row_step >= width * point_step)", point_step, row_step, width);
+      return PFT_ERR_INVALID;
+    }
+    const int32_t offs[4] = {off_x, off_y, off_z, off_rgb};
+    for (int k = 0; k < 4; ++k) {
+      const bool optional = k == 3 && offs[k] < 0;  // no colour field: rgba = 0
+      if (!optional && (offs[k] < 0 || (offs[k] & 3) || (uint32_t)offs[k] + 4 > point_step)) {
+        set_last_error("bad PointCloud2 field offset %d (float32 x, y, z and the packed rgb(a) word, 4-byte aligned inside point_step %u)", offs[k], point_step);
+        return PFT_ERR_INVALID;
+      }
+    }
+  }
+  return PFT_OK;
+}
+
+}  // namespace
 
 extern "C" {
 
@@ -104,6 +164,8 @@ void pft_context_destroy(pft_context* c) {
   for (auto* b : bufs) b->release();
   if (c->pinned) cudaFreeHost(c->pinned);
   if (c->batch_fork) cudaEventDestroy(c->batch_fork);
+  if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+  if (c->copy_fence) cudaEventDestroy(c->copy_fence);
   for (int k = 0; k < pft_context::kK1Graphs; ++k) if (c->k1_exec[k]) cudaGraphExecDestroy(c->k1_exec[k]);
   cudaStreamDestroy(c->stream);
   delete c;
@@ -148,8 +210,10 @@ void pft_cloud_destroy(pft_cloud* c) {
   if (!c) return;
   cudaSetDevice(c->ctx->device);
   cudaStreamSynchronize(c->ctx->stream);
+  if (c->ready) { cudaEventSynchronize(c->ready); cudaEventDestroy(c->ready); }
   c->pts.release();
   c->hdr.release();
+  c->raw_staging.release();
   delete c;
 }
 
@@ -159,8 +223,9 @@ int pft_cloud_upload(pft_cloud* c, const void* host_points, size_t n, int layout
   if (n > 0x7fffffffull) { set_last_error("cloud too large"); return PFT_ERR_INVALID; }
   pft_context* ctx = c->ctx;
   PFT_CUDA_TRY(cudaSetDevice(ctx->device));
-  int rc = c->ensure(n);
+  int rc = c->join_upload();
   if (rc) return rc;
+  if ((rc = c->ensure(n))) return rc;
   cudaStream_t s = ctx->stream;
   if (n) {
     if (layout == PFT_LAYOUT_PACKED16) {
@@ -182,26 +247,12 @@ int pft_cloud_upload_pointcloud2(pft_cloud* c, const void* data, uint32_t width,
   if (!c) { set_last_error("pft_cloud_upload_pointcloud2: null cloud"); return PFT_ERR_INVALID; }
   const size_t n = (size_t)width * height;
   if (n && !data) { set_last_error("pft_cloud_upload_pointcloud2: null data"); return PFT_ERR_INVALID; }
-  if (n > 0x7fffffffull) { set_last_error("cloud too large"); return PFT_ERR_INVALID; }
-  if (is_bigendian) { set_last_error("big-endian PointCloud2 data is not supported"); return PFT_ERR_INVALID; }
-  if (n) {
-    if (point_step < 12 || (point_step & 3) || (row_step & 3) || (size_t)row_step < (size_t)width * point_step) {
-      set_last_error("bad PointCloud2 strides: point_step %u, row_step %u, width %u (4-byte multiples, row_step >= width * point_step)", point_step, row_step, width);
-      return PFT_ERR_INVALID;
-    }
-    const int32_t offs[4] = {off_x, off_y, off_z, off_rgb};
-    for (int k = 0; k < 4; ++k) {
-      const bool optional = k == 3 && offs[k] < 0;  // no colour field: rgba = 0
-      if (!optional && (offs[k] < 0 || (offs[k] & 3) || (uint32_t)offs[k] + 4 > point_step)) {
-        set_last_error("bad PointCloud2 field offset %d (float32 x, y, z and the packed rgb(a) word, 4-byte aligned inside point_step %u)", offs[k], point_step);
-        return PFT_ERR_INVALID;
-      }
-    }
-  }
+  int rc = check_pointcloud2_layout(n, width, point_step, row_step, off_x, off_y, off_z, off_rgb, is_bigendian);
+  if (rc) return rc;
   pft_context* ctx = c->ctx;
   PFT_CUDA_TRY(cudaSetDevice(ctx->device));
-  int rc = c->ensure(n);
-  if (rc) return rc;
+  if ((rc = c->join_upload())) return rc;
+  if ((rc = c->ensure(n))) return rc;
   cudaStream_t s = ctx->stream;
   if (n) {
     const size_t bytes = (size_t)row_step * height;
@@ -214,8 +265,52 @@ int pft_cloud_upload_pointcloud2(pft_cloud* c, const void* data, uint32_t width,
   return PFT_OK;
 }
 
+int pft_cloud_upload_async(pft_cloud* c, const void* host_points, size_t n, int layout) {
+  if (!c || (n && !host_points)) { set_last_error("pft_cloud_upload_async: null argument"); return PFT_ERR_INVALID; }
+  if (layout != PFT_LAYOUT_PACKED16 && layout != PFT_LAYOUT_PCL32) { set_last_error("unknown layout %d", layout); return PFT_ERR_INVALID; }
+  if (n > 0x7fffffffull) { set_last_error("cloud too large"); return PFT_ERR_INVALID; }
+  cudaStream_t cs = nullptr;
+  int rc = begin_async_upload(c, n, &cs);
+  if (rc) return rc;
+  if (n) {
+    if (layout == PFT_LAYOUT_PACKED16) {
+      PFT_CUDA_TRY(cudaMemcpyAsync(c->d_pts(), host_points, n * sizeof(float4), cudaMemcpyHostToDevice, cs));
+    } else {
+      if ((rc = c->raw_staging.reserve(n * 32))) return rc;
+      PFT_CUDA_TRY(cudaMemcpyAsync(c->raw_staging.p, host_points, n * 32, cudaMemcpyHostToDevice, cs));
+      if ((rc = launch_unpack_pcl32(cs, c->raw_staging.p, c->d_pts(), n))) return rc;
+    }
+  }
+  return end_async_upload(c, n, cs);
+}
+
+int pft_cloud_upload_pointcloud2_async(pft_cloud* c, const void* data, uint32_t width, uint32_t height, uint32_t point_step, uint32_t row_step,
+                                       int32_t off_x, int32_t off_y, int32_t off_z, int32_t off_rgb, int is_bigendian) {
+  if (!c) { set_last_error("pft_cloud_upload_pointcloud2_async: null cloud"); return PFT_ERR_INVALID; }
+  const size_t n = (size_t)width * height;
+  if (n && !data) { set_last_error("pft_cloud_upload_pointcloud2_async: null data"); return PFT_ERR_INVALID; }
+  int rc = check_pointcloud2_layout(n, width, point_step, row_step, off_x, off_y, off_z, off_rgb, is_bigendian);
+  if (rc) return rc;
+  cudaStream_t cs = nullptr;
+  if ((rc = begin_async_upload(c, n, &cs))) return rc;
+  if (n) {
+    const size_t bytes = (size_t)row_step * height;
+    if ((rc = c->raw_staging.reserve(bytes))) return rc;
+    PFT_CUDA_TRY(cudaMemcpyAsync(c->raw_staging.p, data, bytes, cudaMemcpyHostToDevice, cs));
+    if ((rc = launch_unpack_pointcloud2(cs, c->raw_staging.p, c->d_pts(), width, height, point_step, row_step, off_x, off_y, off_z, off_rgb))) return rc;
+  }
+  return end_async_upload(c, n, cs);
+}
+
+int pft_cloud_wait_upload(pft_cloud* c) {
+  if (!c) { set_last_error("pft_cloud_wait_upload: null cloud"); return PFT_ERR_INVALID; }
+  PFT_CUDA_TRY(cudaSetDevice(c->ctx->device));
+  return c->join_upload();
+}
+
 int pft_cloud_size(pft_cloud* c, size_t* n) {
   if (!c || !n) { set_last_error("pft_cloud_size: null argument"); return PFT_ERR_INVALID; }
+  { int jrc = c->join_upload(); if (jrc) return jrc; }  // every consumer that sizes its work from the cloud passes here
   if (c->host_n < 0) {
     pft_context* ctx = c->ctx;
     PFT_CUDA_TRY(cudaSetDevice(ctx->device));
@@ -239,6 +334,7 @@ int pft_cloud_download(pft_cloud* c, void* host_points, size_t capacity, int lay
   if (!host_points) { set_last_error("pft_cloud_download: null buffer"); return PFT_ERR_INVALID; }
   pft_context* ctx = c->ctx;
   cudaStream_t s = ctx->stream;
+  if ((rc = c->join_upload())) return rc;
   if (layout == PFT_LAYOUT_PACKED16) {
     PFT_CUDA_TRY(cudaMemcpyAsync(host_points, c->d_pts(), n * sizeof(float4), cudaMemcpyDeviceToHost, s));
   } else {
@@ -256,7 +352,9 @@ static int check_filter_args(pft_context* ctx, const pft_cloud* in, pft_cloud* o
   if (in == out) { set_last_error("%s: in-place filtering is not supported", who); return PFT_ERR_INVALID; }
   if (in->ctx != ctx || out->ctx != ctx) { set_last_error("%s: clouds belong to another context", who); return PFT_ERR_INVALID; }
   PFT_CUDA_TRY(cudaSetDevice(ctx->device));
-  return PFT_OK;
+  int rc = in->join_upload();  // an asynchronous upload into the input / output must land before the filter touches it
+  if (rc) return rc;
+  return out->join_upload();
 }
 
 int pft_passthrough(pft_context* ctx, const pft_cloud* in, pft_cloud* out, int field, float lo, float hi) {

@@ -44,6 +44,9 @@ struct pft_context {
   int cl_count = 0;
   const pft_cloud* cl_src = nullptr;
   cudaEvent_t batch_fork = nullptr;  // pft_compute_batch: the point of the context stream the trackers' streams fork from
+  // frame ingest overlapped with compute (pft_cloud_upload_async): copies and unpack kernels run on a stream of their own
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t copy_fence = nullptr;  // "everything enqueued on `stream` so far": the copy must not overtake earlier readers
 };
 
 struct pft_cloud {
@@ -52,6 +55,12 @@ struct pft_cloud {
   pft::DevBuf hdr;              // CloudHeader
   size_t capacity = 0;          // host-known upper bound on n
   long long host_n = -1;        // exact n if known on the host, else -1
+  // pft_cloud_upload_async: `ready` fires on the copy stream once the points are in place; the first consumer on the
+  // context stream waits for it (join_upload)
+  pft::DevBuf raw_staging;      // raw PointCloud2 / 32-byte records of an asynchronous upload
+  cudaEvent_t ready = nullptr;
+  mutable bool upload_pending = false;
+  int join_upload() const;
   float4* d_pts() const { return pts.as<float4>(); }
   pft::CloudHeader* d_hdr() const { return hdr.as<pft::CloudHeader>(); }
   int ensure(size_t cap);

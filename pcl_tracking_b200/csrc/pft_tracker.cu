@@ -734,6 +734,7 @@ int enqueue_tracking(pft_tracker* t) {
 int prepare_compute(pft_tracker* t) {
   int rc = ensure_particle_buffers(t);
   if (rc) return rc;
+  if (t->input && (rc = t->input->join_upload())) return rc;  // frame still arriving on the copy stream (pft_cloud_upload_async)
   if ((rc = ensure_index_buffers(t))) return rc;
   choose_chunks(t);
   const size_t need_partial = (size_t)t->chunks * t->n_cap * sizeof(double);
@@ -1045,6 +1046,9 @@ int pft_compute_batch(pft_tracker** ts, int n) {
   pft_context* ctx = ts[0]->ctx;
   PFT_CUDA_TRY(cudaSetDevice(ctx->device));
   if (!ctx->batch_fork) PFT_CUDA_TRY(cudaEventCreateWithFlags(&ctx->batch_fork, cudaEventDisableTiming));
+  for (int i = 0; i < n; ++i) {  // the fork point must already be behind an asynchronous upload of the scene
+    if (ts[i]->input) { int jrc = ts[i]->input->join_upload(); if (jrc) return jrc; }
+  }
   PFT_CUDA_TRY(cudaEventRecord(ctx->batch_fork, ctx->stream));
   int rc = PFT_OK;
   int launched = 0;
@@ -1491,6 +1495,7 @@ int pft_cloud_broadcast(pft_cloud* cloud, size_t capacity, int root) {
   if (ctx->nranks == 1) return PFT_OK;
   if (!ctx->comm) { set_last_error("context has no communicator"); return PFT_ERR_COMM; }
   PFT_CUDA_TRY(cudaSetDevice(ctx->device));
+  { int jrc = cloud->join_upload(); if (jrc) return jrc; }
   if (ctx->rank == root) {
     if (cloud->capacity < capacity && cloud->capacity > 0) capacity = cloud->capacity;  // never read past the root's buffer
   }

@@ -60,6 +60,42 @@ class Context:
             self._h = C.c_void_p()
 
 
+class PinnedBuffer:
+    """Page-locked host memory (pft_host_alloc) for frame buffers: what upload_raw / upload_raw_async copy from."""
+
+    def __init__(self, nbytes):
+        self.nbytes = int(nbytes)
+        self._p = C.c_void_p()
+        check(capi.load().pft_host_alloc(C.byref(self._p), self.nbytes))
+
+    @classmethod
+    def of(cls, array):
+        a = np.ascontiguousarray(array)
+        b = cls(a.nbytes)
+        if a.nbytes:
+            C.memmove(b._p, a.ctypes.data, a.nbytes)
+        return b
+
+    @property
+    def ptr(self):
+        return self._p.value
+
+    def numpy(self, dtype=np.uint8):
+        n = self.nbytes // np.dtype(dtype).itemsize
+        return np.ctypeslib.as_array(C.cast(self._p, C.POINTER(C.c_uint8)), shape=(self.nbytes,)).view(dtype)[:n]
+
+    def free(self):
+        if self._p:
+            capi.load().pft_host_free(self._p)
+            self._p = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
 class PointCloud:
     """pcl::PointCloud<pcl::PointXYZRGBA> resident in HBM as float4 {x, y, z, rgba}."""
 
@@ -87,7 +123,18 @@ class PointCloud:
         check(capi.load().pft_cloud_upload(self._h, C.c_void_p(host_ptr), n, layout))
         return self
 
-    def fromPointCloud2(self, data, width, height, point_step, row_step=None, off_x=0, off_y=4, off_z=8, off_rgb=16, is_bigendian=False):
+    def upload_raw_async(self, host_ptr, n, layout=capi.LAYOUT_PACKED16):
+        """Like upload_raw, on the context's copy stream: overlaps the work enqueued after this call (the previous
+        frame's compute); consumers of this cloud wait for the copy on the device.  `host_ptr` must be pinned."""
+        check(capi.load().pft_cloud_upload_async(self._h, C.c_void_p(host_ptr), n, layout))
+        return self
+
+    def waitUpload(self):
+        check(capi.load().pft_cloud_wait_upload(self._h))
+        return self
+
+    def fromPointCloud2(self, data, width, height, point_step, row_step=None, off_x=0, off_y=4, off_z=8, off_rgb=16, is_bigendian=False,
+                        asynchronous=False):
         """sensor_msgs/PointCloud2 payload -> device cloud (pcl::fromPCLPointCloud2, ref: src/auto_tracking.cpp:619-622).
         `data`: bytes / uint8 array of height x row_step bytes, or a raw host pointer (int)."""
         row_step = int(width) * int(point_step) if row_step is None else int(row_step)
@@ -99,8 +146,9 @@ class PointCloud:
                 raise ValueError("PointCloud2 data holds %d bytes, need %d" % (a.nbytes, row_step * int(height)))
             self._keep = a
             p = ptr(a)
-        check(capi.load().pft_cloud_upload_pointcloud2(self._h, p, int(width), int(height), int(point_step), row_step, int(off_x), int(off_y),
-                                                       int(off_z), int(off_rgb), 1 if is_bigendian else 0))
+        fn = capi.load().pft_cloud_upload_pointcloud2_async if asynchronous else capi.load().pft_cloud_upload_pointcloud2
+        check(fn(self._h, p, int(width), int(height), int(point_step), row_step, int(off_x), int(off_y),
+                 int(off_z), int(off_rgb), 1 if is_bigendian else 0))
         return self
 
     def broadcast(self, capacity, root=0):
