@@ -177,7 +177,12 @@ def run_cpu(frames, oid0, n_particles, steps, warmup, budget_s):
     """Times `steps` CPU frames after `warmup`.  The particle count is bounded so that the run fits
     `budget_s`: throughput in evals/s does not depend on it (weight() is linear in particles)."""
     import oracle
-    threads = oracle.lib().orc_max_threads()
+    # every host core this process may run on -- NOT omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1 to its
+    # workers, which would time the CPU arm single-threaded whenever the driver launches it for N > 1
+    try:
+        threads = max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        threads = max(1, os.cpu_count() or 1)
     model, centroid = cpu_prepare_model(raw_model(frames, oid0))
     M = len(model)
     # calibrate on a small particle set
