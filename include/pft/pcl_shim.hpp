@@ -415,6 +415,11 @@ class ParticleFilterOMPTracker {
   void setResampleLikelihoodThr(double v) { sd(PFT_RESAMPLE_LIKELIHOOD_THR, v); }                 // ref :232
   void setUseNormal(bool u) { si(PFT_USE_NORMAL, u ? 1 : 0); }                                    // ref :233
   void setMinIndices(int n) { si(PFT_MIN_INDICES, n); }                                           // ref :676
+  // change detector (pcl::tracking::ParticleFilterTracker; off by default, never enabled by the reference)
+  void setUseChangeDetector(bool u) { si(PFT_USE_CHANGE_DETECTOR, u ? 1 : 0); }
+  void setIntervalOfChangeDetection(unsigned int n) { si(PFT_CHANGE_DETECTOR_INTERVAL, (int)n); }
+  void setMinPointsOfChangeDetection(unsigned int n) { si(PFT_CHANGE_DETECTOR_MIN_POINTS, (int)n); }
+  void setResolutionOfChangeDetection(double r) { sd(PFT_CHANGE_DETECTOR_RESOLUTION, r); }
   void setAlpha(double a) { sd(PFT_ALPHA, a); }
   void setMotionRatio(double r) { sd(PFT_MOTION_RATIO, r); }
   void setCloudCoherence(const typename NearestPairPointCloudCoherence<PointT>::Ptr& c) {         // ref :254

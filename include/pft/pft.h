@@ -156,6 +156,13 @@ typedef enum {
   PFT_DEBUG_NN = 11,          /* record per-point NN indices for the first K particles of weight() */
   PFT_CANDIDATE_LISTS = 12,   /* exact-NN lookup tables per weight(): 0 never, 1 when they pay off (default), 2 always.
                                  Internal to the search: results are identical in all three modes. */
+  PFT_USE_CHANGE_DETECTOR = 13,        /* setUseChangeDetector (upstream default false; the reference never sets it).  On: every
+                                          `interval` weight() calls the cropped cloud goes through an
+                                          OctreePointCloudChangeDetector; no new voxel => the weights are not recomputed,
+                                          resample() and update() are skipped until something changes.  compute() then
+                                          runs stream-launched with one read-back per test (no graph replay). */
+  PFT_CHANGE_DETECTOR_INTERVAL = 14,   /* setIntervalOfChangeDetection (default 10) */
+  PFT_CHANGE_DETECTOR_MIN_POINTS = 15, /* setMinPointsOfChangeDetection (default 10): new voxels with fewer points are ignored */
   /* double keys */
   PFT_DELTA = 20,             /* setDelta                 (ref :212) */
   PFT_EPSILON = 21,           /* setEpsilon               (ref :213) */
@@ -167,6 +174,7 @@ typedef enum {
   PFT_H_WEIGHT = 27, PFT_S_WEIGHT = 28, PFT_V_WEIGHT = 29,
   PFT_SEARCH_RESOLUTION = 30, /* pcl::search::Octree(resolution) -> index cell size (ref :250) */
   PFT_RESAMPLE_LIKELIHOOD_THR = 31, /* setResampleLikelihoodThr: accepted, inert upstream (ref :232) */
+  PFT_CHANGE_DETECTOR_RESOLUTION = 32, /* setResolutionOfChangeDetection (default 0.01) */
   /* 6-vector keys */
   PFT_STEP_NOISE_COV = 40,    /* setStepNoiseCovariance    (ref :226) */
   PFT_INIT_NOISE_COV = 41,    /* setInitialNoiseCovariance (ref :227) */
@@ -253,6 +261,9 @@ PFT_API int pft_tracker_resample(pft_tracker* t, int slot);  /* resample()      
 PFT_API int pft_tracker_weight(pft_tracker* t);              /* weight() incl. normalizeWeight() */
 PFT_API int pft_tracker_update(pft_tracker* t);              /* update()            */
 PFT_API int pft_tracker_set_changed(pft_tracker* t, int changed);
+/* change detector state: out4 = { change_counter_, tests run so far, point indices the last test reported (-1: no test
+ * yet), changed_ } */
+PFT_API int pft_tracker_get_change_detector_info(pft_tracker* t, int32_t* out4);
 /* Inspection of the last weight(): crop AABB (minx,miny,minz,maxx,maxy,maxz), number of cropped scene
  * points, raw (un-normalised) weights, ancestors chosen by the last resample. */
 PFT_API int pft_tracker_get_aabb(pft_tracker* t, float* aabb6);

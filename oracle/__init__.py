@@ -22,6 +22,8 @@ PARTICLE = np.dtype([("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("one", "<f4"),
 THREADS, PARTICLE_NUM, MAX_PARTICLE_NUM, ITERATION_NUM, NN_MODE, USE_HSV, USE_DISTANCE, SAMPLER, QUAT_SAMPLE, SEED = range(10)
 DELTA, EPSILON, ALPHA, MOTION_RATIO, MAX_DIST, DIST_WEIGHT, HSV_WEIGHT, H_WEIGHT, S_WEIGHT, V_WEIGHT, OCTREE_RES, GRID_CELL = range(20, 32)
 STEP_COV, INIT_COV, INIT_MEAN, BIN_SIZE = range(40, 44)
+USE_CHANGE_DETECTOR, CD_INTERVAL, CD_MIN_POINTS = 10, 11, 12
+CD_RESOLUTION = 32
 NN_EXACT_BRUTE, NN_EXACT_GRID, NN_PCL_APPROX = 0, 1, 2
 SAMPLER_ALIAS_PCL, SAMPLER_CDF, SAMPLER_CDF_VDC = 0, 1, 2
 
@@ -76,6 +78,9 @@ def lib():
             "orc_get_motion": (None, [vp, vp]),
             "orc_set_motion": (None, [vp, vp]),
             "orc_set_changed": (None, [vp, i]),
+            "orc_get_changed": (i, [vp]),
+            "orc_change_detector_info": (None, [vp, vp]),
+            "orc_change_detector_sequence": (i, [vp, vp, i, d, i, vp]),
             "orc_inject_draws": (None, [vp, vp, vp, vp, i, i]),
             "orc_init_particles": (None, [vp]),
             "orc_resample": (None, [vp, i]),
@@ -369,6 +374,16 @@ def octree_approx_nearest(pts, res, queries):
     return idx, d2
 
 
+def change_detector_sequence(clouds, resolution, min_points):
+    """OctreePointCloudChangeDetector fed one cloud after the other (setInputCloud, addPointsFromInputCloud,
+    getPointIndicesFromNewVoxels(min_points), switchBuffers): number of point indices reported per cloud."""
+    sizes = np.array([len(c) for c in clouds], dtype=np.int32)
+    allp = np.ascontiguousarray(np.concatenate([np.ascontiguousarray(c, dtype=POINT) for c in clouds])) if len(clouds) else np.zeros(0, dtype=POINT)
+    found = np.zeros(len(clouds), dtype=np.int32)
+    lib().orc_change_detector_sequence(_p(allp), _p(sizes), len(clouds), float(resolution), int(min_points), _p(found))
+    return found
+
+
 # ------------------------------------------------------------------ tracker
 class Tracker:
     """CPU oracle tracker; method names follow the PCL surface (ref: src/auto_tracking.cpp:201-254)."""
@@ -434,6 +449,22 @@ class Tracker:
 
     def set_changed(self, c):
         lib().orc_set_changed(self._h, 1 if c else 0)
+
+    def changed(self):
+        return bool(lib().orc_get_changed(self._h))
+
+    def set_change_detector(self, on, interval=10, min_points=10, resolution=0.01):
+        """setUseChangeDetector / setIntervalOfChangeDetection / setMinPointsOfChangeDetection /
+        setResolutionOfChangeDetection (PCL defaults; off in the reference)."""
+        self.set_i(USE_CHANGE_DETECTOR, 1 if on else 0)
+        self.set_i(CD_INTERVAL, int(interval))
+        self.set_i(CD_MIN_POINTS, int(min_points))
+        self.set_d(CD_RESOLUTION, float(resolution))
+
+    def change_detector_info(self):
+        out = np.zeros(4, dtype=np.int32)
+        lib().orc_change_detector_info(self._h, _p(out))
+        return {"counter": int(out[0]), "tests": int(out[1]), "last_found": int(out[2]), "changed": bool(out[3])}
 
     def inject_draws(self, usel, normals6, umotion):
         usel = np.ascontiguousarray(usel, dtype=np.float32)

@@ -555,6 +555,96 @@ class PclOctree {
   double min_[3] = {0, 0, 0}, max_[3] = {0, 0, 0};
 };
 
+// ---------------------------------------------------------------------------------
+// pcl::octree::OctreePointCloudChangeDetector restated for ParticleFilterTracker::testChangeDetection
+// [octree/octree_pointcloud_changedetector.h, octree/impl/octree2buf_base.hpp, octree/impl/octree_pointcloud.hpp]
+// -- recalled, not read from disk.  The detector is a double-buffered octree that lives as long as the tracker: every
+// test adds the (cropped) cloud to the current buffer -- same bounding box growth and keys as PclOctree above, the box
+// and the depth persist across tests -- collects the points of the leaves that the PREVIOUS buffer did not have
+// (leaves with fewer than `min_points` points are ignored) and switches buffers.  Octree2BufBase decides "new" at the
+// leaf's parent branch (child present in the current buffer, absent in the previous one); branches are shared by the
+// two buffers and growth only adds levels on top, so this is: the voxel was not occupied at the previous test.
+// ---------------------------------------------------------------------------------
+struct CdNode {
+  CdNode* child[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int last = 0;          // id of the last test that put a point into this leaf
+  int count = 0;         // points of that test
+  bool prev_hit = false; // the leaf was also occupied at the test before `last`
+};
+class ChangeDetector {
+ public:
+  explicit ChangeDetector(double res) : res_(res) {}
+  ~ChangeDetector() { freeNode(root_); }
+  ChangeDetector(const ChangeDetector&) = delete;
+  ChangeDetector& operator=(const ChangeDetector&) = delete;
+  // setInputCloud + addPointsFromInputCloud + getPointIndicesFromNewVoxels(min_points) + switchBuffers;
+  // returns the number of point indices reported
+  int test(const Pt* pts, int n, int min_points) {
+    ++test_id_;
+    if (!root_) root_ = new CdNode();
+    std::vector<CdNode*> touched;
+    for (int i = 0; i < n; ++i) {
+      if (!finite3(pts[i])) continue;
+      CdNode* leaf = insert(pts[i]);
+      if (leaf->last != test_id_) {
+        leaf->prev_hit = leaf->last == test_id_ - 1 && test_id_ > 1;
+        leaf->last = test_id_; leaf->count = 0;
+        touched.push_back(leaf);
+      }
+      leaf->count++;
+    }
+    int found = 0;
+    for (CdNode* leaf : touched) if (!leaf->prev_hit && leaf->count >= min_points) found += leaf->count;
+    return found;
+  }
+ private:
+  void freeNode(CdNode* n) { if (!n) return; for (auto c : n->child) freeNode(c); delete n; }
+  CdNode* insert(const Pt& p) {
+    const float minValue = std::numeric_limits<float>::epsilon();
+    const double v[3] = {p.x, p.y, p.z};
+    while (true) {  // adoptBoundingBoxToPoint
+      bool up[3], any = false;
+      for (int d = 0; d < 3; ++d) { const bool lo = v[d] < min_[d]; up[d] = v[d] >= max_[d]; any = any || lo || up[d]; }
+      if (!(any || !bbox_defined_)) break;
+      if (bbox_defined_) {
+        const int ci = ((!up[0]) << 2) | ((!up[1]) << 1) | (!up[2]);
+        CdNode* nr = new CdNode();
+        nr->child[ci] = root_;
+        root_ = nr;
+        double side = (double)(1 << depth_) * res_;
+        for (int d = 0; d < 3; ++d) if (!up[d]) min_[d] -= side;
+        depth_++;
+        side = (double)(1 << depth_) * res_ - minValue;
+        for (int d = 0; d < 3; ++d) max_[d] = min_[d] + side;
+      } else {
+        for (int d = 0; d < 3; ++d) { min_[d] = v[d] - res_ / 2; max_[d] = v[d] + res_ / 2; }
+        unsigned mk[3];
+        for (int d = 0; d < 3; ++d) mk[d] = (unsigned)std::ceil((max_[d] - min_[d]) / res_);
+        const unsigned max_voxels = std::max(std::max(std::max(mk[0], mk[1]), mk[2]), 2u);
+        depth_ = (int)std::max(std::min(30.0, std::ceil(std::log2((double)max_voxels) - minValue)), 0.0);
+        const double side = (double)(1 << depth_) * res_ - minValue;
+        for (int d = 0; d < 3; ++d) { const double over = (side - (max_[d] - min_[d])) / 2.0; min_[d] -= over; max_[d] += over; }
+        bbox_defined_ = true;
+      }
+    }
+    const unsigned key[3] = {(unsigned)((p.x - min_[0]) / res_), (unsigned)((p.y - min_[1]) / res_), (unsigned)((p.z - min_[2]) / res_)};
+    CdNode* n = root_;
+    for (int level = depth_ - 1; level >= 0; --level) {
+      const unsigned mask = 1u << level;
+      const int ci = ((!!(key[0] & mask)) << 2) | ((!!(key[1] & mask)) << 1) | (!!(key[2] & mask));
+      if (!n->child[ci]) n->child[ci] = new CdNode();
+      n = n->child[ci];
+    }
+    return n;
+  }
+  double res_;
+  CdNode* root_ = nullptr;
+  bool bbox_defined_ = false;
+  int depth_ = 0;
+  int test_id_ = 0;
+  double min_[3] = {0, 0, 0}, max_[3] = {0, 0, 0};
+};
+
 // Uniform-grid exact nearest neighbour (oracle-side accelerator; validated against the
 // brute-force scan in tests).  Ties resolve to the lowest index, same fp32 distance formula.
 class ExactGrid {
@@ -652,6 +742,13 @@ struct Tracker {
   float grid_cell = 0.01f;
   int sampler = SAMPLER_CDF;
   int quat_sample = 1;
+  // change detector (PCL ctor defaults; off in the reference)
+  bool use_change_detector = false;
+  int cd_interval = 10, cd_filter = 10;
+  double cd_resolution = 0.01;
+  int change_counter = 0;
+  int cd_tests = 0, cd_last_found = -1;   // diagnostics: tests run so far, points reported by the last one
+  std::shared_ptr<ChangeDetector> detector;
   // state
   std::vector<Pt> ref, input;
   std::vector<Particle> particles;
@@ -930,7 +1027,34 @@ void weight(Tracker& T, std::vector<int>* nn_out /*optional: [N*M] NN index into
     for (int i = 0; i < n2; ++i) T.cropped_idx[i] = ib[ia[i]];
   }
   double t2 = now_s();
-  T.changed = true;
+  // change_counter_ / testChangeDetection [impl/particle_filter.hpp weight()], SURVEY A.3 (3): with the detector off
+  // every call computes the weights and changed_ is true for ever
+  bool compute_weights = true;
+  if (T.change_counter == 0) {
+    bool change = true;
+    if (T.use_change_detector) {
+      if (!T.detector) T.detector = std::make_shared<ChangeDetector>(T.cd_resolution);  // initCompute: created once
+      T.cd_last_found = T.detector->test(T.cropped.data(), (int)T.cropped.size(), T.cd_filter);
+      T.cd_tests++;
+      change = T.cd_last_found > 0;
+    }
+    if (change) { T.changed = true; T.change_counter = T.cd_interval; }
+    else { T.changed = false; compute_weights = false; }
+  } else {
+    --T.change_counter;
+    T.changed = true;  // (upstream leaves changed_ as it is, which is true here; the parity tests' set_changed hook relies on it)
+  }
+  if (!compute_weights) {
+    // the particles keep their weights and normalizeWeight() runs on them all the same
+    T.raw_weights.resize(N);
+    for (int i = 0; i < N; ++i) T.raw_weights[i] = T.particles[i].weight;
+    if (nn_out) nn_out->assign((size_t)N * M, -1);
+    if (d2_out) d2_out->assign((size_t)N * M, FLT_MAX);
+    double t3s = now_s();
+    normalize_weight(T);
+    T.t_stage[0] += t1 - t0; T.t_stage[1] += t2 - t1; T.t_stage[4] += now_s() - t3s;
+    return;
+  }
   // (3) coherence_->setTargetCloud(cropped); initCompute() => search index rebuild
   const int S = (int)T.cropped.size();
   PclOctree oct(T.octree_res);
@@ -1106,8 +1230,10 @@ void orc_tracker_destroy(orc_tracker* t) { delete t; }
 enum {
   ORC_THREADS = 0, ORC_PARTICLE_NUM = 1, ORC_MAX_PARTICLE_NUM = 2, ORC_ITERATION_NUM = 3, ORC_NN_MODE = 4, ORC_USE_HSV = 5,
   ORC_USE_DISTANCE = 6, ORC_SAMPLER = 7, ORC_QUAT_SAMPLE = 8, ORC_SEED = 9,
+  ORC_USE_CHANGE_DETECTOR = 10, ORC_CD_INTERVAL = 11, ORC_CD_MIN_POINTS = 12,
   ORC_DELTA = 20, ORC_EPSILON = 21, ORC_ALPHA = 22, ORC_MOTION_RATIO = 23, ORC_MAX_DIST = 24, ORC_DIST_WEIGHT = 25, ORC_HSV_WEIGHT = 26,
   ORC_H_WEIGHT = 27, ORC_S_WEIGHT = 28, ORC_V_WEIGHT = 29, ORC_OCTREE_RES = 30, ORC_GRID_CELL = 31,
+  ORC_CD_RESOLUTION = 32,
   ORC_STEP_COV = 40, ORC_INIT_COV = 41, ORC_INIT_MEAN = 42, ORC_BIN_SIZE = 43
 };
 int orc_set_i(orc_tracker* t, int key, int v) {
@@ -1123,6 +1249,9 @@ int orc_set_i(orc_tracker* t, int key, int v) {
     case ORC_SAMPLER: T.sampler = v; break;
     case ORC_QUAT_SAMPLE: T.quat_sample = v; break;
     case ORC_SEED: T.rng.seed((unsigned)v); break;
+    case ORC_USE_CHANGE_DETECTOR: T.use_change_detector = v != 0; break;
+    case ORC_CD_INTERVAL: T.cd_interval = v; break;
+    case ORC_CD_MIN_POINTS: T.cd_filter = v; break;
     default: return -1;
   }
   return 0;
@@ -1142,6 +1271,7 @@ int orc_set_d(orc_tracker* t, int key, double v) {
     case ORC_V_WEIGHT: T.v_weight = v; break;
     case ORC_OCTREE_RES: T.octree_res = v; break;
     case ORC_GRID_CELL: T.grid_cell = (float)v; break;
+    case ORC_CD_RESOLUTION: T.cd_resolution = v; T.detector.reset(); break;
     default: return -1;
   }
   return 0;
@@ -1171,6 +1301,18 @@ void orc_set_result(orc_tracker* t, const orc_particle* in) { t->T.rep = *in; }
 void orc_get_motion(orc_tracker* t, orc_particle* out) { *out = t->T.motion; }
 void orc_set_motion(orc_tracker* t, const orc_particle* in) { t->T.motion = *in; }
 void orc_set_changed(orc_tracker* t, int c) { t->T.changed = c != 0; }
+int orc_get_changed(orc_tracker* t) { return t->T.changed ? 1 : 0; }
+// out[4] = {change_counter_, tests run so far, point indices reported by the last test (-1: none yet), changed_}
+void orc_change_detector_info(orc_tracker* t, int* out) {
+  out[0] = t->T.change_counter; out[1] = t->T.cd_tests; out[2] = t->T.cd_last_found; out[3] = t->T.changed ? 1 : 0;
+}
+// stand-alone detector for known-answer tests: clouds[k] of sizes[k] points tested one after the other
+int orc_change_detector_sequence(const orc_point* pts, const int* sizes, int n_clouds, double res, int min_points, int* found) {
+  ChangeDetector d(res);
+  size_t off = 0;
+  for (int k = 0; k < n_clouds; ++k) { found[k] = d.test(pts + off, sizes[k], min_points); off += (size_t)sizes[k]; }
+  return 0;
+}
 // draws: [slots][stride] uniforms for selection, [slots][stride][6] standard normals, [slots][stride] motion uniforms
 void orc_inject_draws(orc_tracker* t, const float* usel, const float* normals6, const float* umotion, int slots, int stride) {
   Tracker& T = t->T;

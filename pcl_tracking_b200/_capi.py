@@ -28,6 +28,8 @@ THREADS, PARTICLE_NUM, MAX_PARTICLE_NUM, ITERATION_NUM, NN_MODE, USE_HSV, USE_DI
 (DELTA, EPSILON, ALPHA, MOTION_RATIO, MAX_DIST, DIST_WEIGHT, HSV_WEIGHT, H_WEIGHT, S_WEIGHT, V_WEIGHT, SEARCH_RESOLUTION,
  RESAMPLE_LIKELIHOOD_THR) = range(20, 32)
 STEP_NOISE_COV, INIT_NOISE_COV, INIT_NOISE_MEAN, BIN_SIZE = range(40, 44)
+USE_CHANGE_DETECTOR, CHANGE_DETECTOR_INTERVAL, CHANGE_DETECTOR_MIN_POINTS = 13, 14, 15
+CHANGE_DETECTOR_RESOLUTION = 32
 NN_EXACT, NN_PCL_APPROX = 0, 1
 PEER_HANDLE_BYTES = 64
 SAMPLER_ALIAS_PCL, SAMPLER_CDF, SAMPLER_CDF_VDC = 0, 1, 2
@@ -99,6 +101,7 @@ SIGNATURES = {
     "pft_tracker_weight": (_i, [_vp]),
     "pft_tracker_update": (_i, [_vp]),
     "pft_tracker_set_changed": (_i, [_vp, _i]),
+    "pft_tracker_get_change_detector_info": (_i, [_vp, _vp]),
     "pft_tracker_get_aabb": (_i, [_vp, _vp]),
     "pft_tracker_get_cropped_count": (_i, [_vp, _psz]),
     "pft_tracker_get_raw_weights": (_i, [_vp, _vp, _sz, _psz]),

@@ -154,8 +154,12 @@ struct pft_tracker {
   int graph_nodes = 0;
   // device buffers
   DevBuf st, parts[2], mats, slot_aabb, model, model_perm, model_tmp, sort_keys, sort_idx, bbox, raw, partial, cdf, cdf_total, ancestors, bin_keys, tbl_rep,
-      tbl_min, slot_of, klb, d_usel, d_normals, d_umot, idx_hdr, cell_start, ipts, ihsv, icount, dbg_idx, dbg_d2, d_trans, row_table, flists, fneeded, fneeded_list, ffar_list, xlists, xcount, result_box, alias_a, alias_q, alias_hl, oct_hdr, oct_nodes, oct_next;
+      tbl_min, slot_of, klb, d_usel, d_normals, d_umot, idx_hdr, cell_start, ipts, ihsv, icount, dbg_idx, dbg_d2, d_trans, row_table, flists, fneeded, fneeded_list, ffar_list, xlists, xcount, result_box, alias_a, alias_q, alias_hl, oct_hdr, oct_nodes, oct_next, cd_hdr, cd_nodes, cd_out;
   int oct_node_cap = 0;
+  // change detector (PCL ctor defaults, off in the reference): host-driven, one read-back per test
+  bool use_cd = false;
+  int cd_interval = 10, cd_filter = 10, change_counter = 0, cd_tests = 0, cd_last_found = -1, cd_node_cap = 0, cd_resets = 0;
+  double cd_res = 0.01;
   int weight_smem = 0;  // dynamic shared memory of the weight kernel (bytes)
   int tbl_size = 0;
   int n_slots = 0;
@@ -191,7 +195,7 @@ void release_all(pft_tracker* t) {
   DevBuf* bufs[] = {&t->st, &t->parts[0], &t->parts[1], &t->mats, &t->slot_aabb, &t->model, &t->model_perm, &t->model_tmp, &t->sort_keys, &t->sort_idx,
                     &t->bbox, &t->raw, &t->partial, &t->cdf, &t->cdf_total, &t->ancestors, &t->bin_keys, &t->tbl_rep, &t->tbl_min, &t->slot_of, &t->klb,
                     &t->d_usel, &t->d_normals, &t->d_umot, &t->idx_hdr, &t->cell_start, &t->ipts, &t->ihsv, &t->icount, &t->dbg_idx,
-                    &t->dbg_d2, &t->d_trans, &t->row_table, &t->flists, &t->fneeded, &t->fneeded_list, &t->ffar_list, &t->xlists, &t->xcount, &t->result_box, &t->alias_a, &t->alias_q, &t->alias_hl, &t->oct_hdr, &t->oct_nodes, &t->oct_next};
+                    &t->dbg_d2, &t->d_trans, &t->row_table, &t->flists, &t->fneeded, &t->fneeded_list, &t->ffar_list, &t->xlists, &t->xcount, &t->result_box, &t->alias_a, &t->alias_q, &t->alias_hl, &t->oct_hdr, &t->oct_nodes, &t->oct_next, &t->cd_hdr, &t->cd_nodes, &t->cd_out};
   for (auto* b : bufs) b->release();
 }
 
@@ -592,6 +596,18 @@ int weight_eval_pcl_approx(pft_tracker* t, bool force_raw) {
   return PFT_OK;
 }
 
+// crop box -> index header (also what in_crop() reads) + reset of the per-weight() counters
+int launch_index_begin(pft_tracker* t) {
+  const int sm = t->ctx->sm_count;
+  const float inv_leaf = 1.0f / (float)t->search_res;
+  index_begin_kernel<<<sm, 256, 0, t->run_stream()>>>(t->st.as<TrackerState>(), t->idx_hdr.as<IndexHeader>(), t->icount.as<int>(), inv_leaf, t->index_level,
+                                                      t->max_cells, t->list_mode ? t->list_max_cells : 0, t->list_mode == 2 ? 0 : t->M, t->nranks, t->rank,
+                                                      t->fneeded.as<unsigned int>(), t->xcount.as<int>());
+  PFT_LAUNCH_CHECK();
+  stage_mark(t, "index_begin_kernel");
+  return PFT_OK;
+}
+
 // weight(), part 2: cropInputPointCloud + search index rebuild (K2), coherence of this rank's particles (K3)
 int weight_phase_eval(pft_tracker* t, bool force_raw = false) {
   int rc = check_weight_ready(t);
@@ -604,10 +620,7 @@ int weight_phase_eval(pft_tracker* t, bool force_raw = false) {
   IndexHeader* hdr = t->idx_hdr.as<IndexHeader>();
   const float inv_leaf = 1.0f / (float)t->search_res;
   const int gscene = blocks_for(ncap_scene, 256, sm * 4);
-  index_begin_kernel<<<sm, 256, 0, s>>>(st, hdr, t->icount.as<int>(), inv_leaf, t->index_level, t->max_cells, t->list_mode ? t->list_max_cells : 0,
-                                        t->list_mode == 2 ? 0 : t->M, t->nranks, t->rank, t->fneeded.as<unsigned int>(), t->xcount.as<int>());
-  PFT_LAUNCH_CHECK();
-  stage_mark(t, "index_begin_kernel");
+  if ((rc = launch_index_begin(t))) return rc;
   index_count_kernel<<<gscene, 256, 0, s>>>(in->d_pts(), in->d_hdr(), hdr, t->icount.as<int>());
   PFT_LAUNCH_CHECK();
   stage_mark(t, "index_count_kernel");
@@ -702,10 +715,65 @@ int weight_phase_normalize(pft_tracker* t, bool fuse_update = false) {
   return PFT_OK;
 }
 
+// ParticleFilterTracker::testChangeDetection on the cropped cloud: host-driven, the answer is read
+// back before weight() goes on.  Every rank of a sharded tracker sees the same crop and takes the same decision.
+int change_detection_test(pft_tracker* t, bool* change) {
+  int rc = launch_index_begin(t);  // the crop predicate of this weight()
+  if (rc) return rc;
+  cudaStream_t s = t->run_stream();
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    change_detect_kernel<<<1, 32, 0, s>>>(t->input->d_pts(), t->input->d_hdr(), t->idx_hdr.as<IndexHeader>(), t->cd_res, t->cd_nodes.as<CdNodeD>(), t->cd_node_cap,
+                                          t->cd_hdr.as<CdHeaderD>(), t->cd_filter, t->cd_out.as<int>());
+    PFT_LAUNCH_CHECK();
+    stage_mark(t, "change_detect_kernel");
+    int out[2] = {0, 0};
+    PFT_CUDA_TRY(cudaMemcpyAsync(out, t->cd_out.p, sizeof(out), cudaMemcpyDeviceToHost, s));
+    PFT_CUDA_TRY(cudaStreamSynchronize(s));
+    if (!out[1]) { t->cd_last_found = out[0]; t->cd_tests++; *change = out[0] > 0; return PFT_OK; }
+    // node pool exhausted (upstream frees what neither buffer uses, this tree only grows): start a new detector --
+    // its first test reports every voxel as new
+    PFT_CUDA_TRY(cudaMemsetAsync(t->cd_hdr.p, 0, sizeof(CdHeaderD), s));
+    t->cd_resets++;
+  }
+  set_last_error("change detector: the cropped cloud does not fit the node pool");
+  return PFT_ERR_CAPACITY;
+}
+
+// weight() when the change detector found nothing new: the coherence is not evaluated, the particles keep their
+// weights and normalizeWeight() still runs on them (upstream, impl/particle_filter.hpp weight())
+int weight_phase_renormalize(pft_tracker* t) {
+  cudaStream_t s = t->run_stream();
+  TrackerState* st = t->st.as<TrackerState>();
+  DevParticle* parts = t->parts[t->cur].as<DevParticle>();
+  weights_to_raw_kernel<<<blocks_for(t->n_cap, 256, t->ctx->sm_count * 4), 256, 0, s>>>(st, parts, t->raw.as<float>(), t->nranks, t->slice_cap());
+  PFT_LAUNCH_CHECK();
+  stage_mark(t, "weights_to_raw_kernel");
+  if (t->n_cap > kClusterMinParticles) normalize_kernel<kClusterCtas><<<kClusterCtas, 1024, 0, s>>>(st, parts, t->raw.as<float>(), t->alpha, t->nranks, t->slice_cap(), t->input->d_hdr(),
+                                                   nullptr, 0, nullptr, t->chunks, t->n_cap, t->raw.as<float>(), 0);
+  else normalize_kernel<1><<<1, 1024, 0, s>>>(st, parts, t->raw.as<float>(), t->alpha, t->nranks, t->slice_cap(), t->input->d_hdr(),
+                                              nullptr, 0, nullptr, t->chunks, t->n_cap, t->raw.as<float>(), 0);
+  PFT_LAUNCH_CHECK();
+  stage_mark(t, "normalize_kernel");
+  t->changed = false;
+  return PFT_OK;
+}
+
 int stage_weight(pft_tracker* t, bool fuse_update = false) {
   int rc;
   if ((rc = weight_phase_box(t))) return rc;
   if ((rc = weight_comm_box(t))) return rc;
+  if (t->use_cd && t->nranks > 1) { set_last_error("the change detector is not supported on a sharded tracker"); return PFT_ERR_STATE; }
+  if (t->use_cd) {
+    // change_counter_ (upstream weight()): a test every `interval` calls; nothing new => the weights are not recomputed
+    if (t->change_counter == 0) {
+      bool change = true;
+      if ((rc = change_detection_test(t, &change))) return rc;
+      if (!change) return weight_phase_renormalize(t);
+      t->change_counter = t->cd_interval;
+    } else {
+      --t->change_counter;
+    }
+  }
   if ((rc = weight_phase_eval(t))) return rc;
   if ((rc = weight_comm_raw(t))) return rc;
   return weight_phase_normalize(t, fuse_update);
@@ -763,6 +831,14 @@ int prepare_compute(pft_tracker* t) {
       if ((rc = t->oct_nodes.reserve(want_nodes * sizeof(OctNodeD)))) return rc;
       t->oct_node_cap = (int)want_nodes;
     }
+  }
+  if (t->use_cd && !t->cd_nodes.p) {
+    invalidate_graph(t);
+    t->cd_node_cap = 1 << 20;  // the tree lives as long as the tracker; it is rebuilt from scratch if it ever fills up
+    if ((rc = t->cd_hdr.reserve(sizeof(CdHeaderD)))) return rc;
+    if ((rc = t->cd_out.reserve(2 * sizeof(int)))) return rc;
+    if ((rc = t->cd_nodes.reserve((size_t)t->cd_node_cap * sizeof(CdNodeD)))) return rc;
+    PFT_CUDA_TRY(cudaMemsetAsync(t->cd_hdr.p, 0, sizeof(CdHeaderD), t->run_stream()));
   }
   if (t->debug_nn > 0) {
     const size_t need = (size_t)t->debug_nn * t->M;
@@ -850,6 +926,11 @@ int pft_tracker_set_i(pft_tracker* t, int key, int v) {
     case PFT_DEBUG_NN:
       if (v < 0) { set_last_error("PFT_DEBUG_NN must be >= 0"); return PFT_ERR_INVALID; }
       t->debug_nn = v; break;
+    case PFT_USE_CHANGE_DETECTOR: t->use_cd = v != 0; break;
+    case PFT_CHANGE_DETECTOR_INTERVAL:
+      if (v < 0) { set_last_error("interval of change detection must be >= 0"); return PFT_ERR_INVALID; }
+      t->cd_interval = v; break;
+    case PFT_CHANGE_DETECTOR_MIN_POINTS: t->cd_filter = v; break;
     default: set_last_error("unknown int key %d", key); return PFT_ERR_INVALID;
   }
   invalidate_graph(t);
@@ -873,6 +954,13 @@ int pft_tracker_set_d(pft_tracker* t, int key, double v) {
       if (!(v > 0.0)) { set_last_error("search resolution must be positive"); return PFT_ERR_INVALID; }
       t->search_res = v; break;
     case PFT_RESAMPLE_LIKELIHOOD_THR: t->resample_thr = v; break;
+    case PFT_CHANGE_DETECTOR_RESOLUTION:
+      if (!(v > 0.0)) { set_last_error("resolution of change detection must be positive"); return PFT_ERR_INVALID; }
+      if (v != t->cd_res && t->cd_hdr.p) {  // a new detector: forget the tree of the old one
+        PFT_CUDA_TRY(cudaSetDevice(t->ctx->device));
+        PFT_CUDA_TRY(cudaMemsetAsync(t->cd_hdr.p, 0, sizeof(CdHeaderD), t->run_stream()));
+      }
+      t->cd_res = v; break;
     default: set_last_error("unknown double key %d", key); return PFT_ERR_INVALID;
   }
   invalidate_graph(t);
@@ -971,7 +1059,7 @@ static int compute_one(pft_tracker* t) {
     t->n_ev_k = 0;
     PFT_CUDA_TRY(cudaEventRecord(t->ev_c0, s));
   }
-  const bool steady = t->changed && t->graph_enabled && !t->timing && t->debug_nn == 0;
+  const bool steady = t->changed && t->graph_enabled && !t->timing && t->debug_nn == 0 && !t->use_cd;  // (the change detector decides on the host)
   if (steady) {
     // The steady-state frame is a fixed launch sequence over fixed buffers: replay it from a graph.
     // (Particle double-buffering flips `cur` once per resample; a graph is only valid when a whole
@@ -1270,6 +1358,11 @@ int pft_tracker_weight(pft_tracker* t) {
   if (rc) return rc;
   if (t->timing) t->n_ev_used = 0;
   return stage_weight(t);
+}
+int pft_tracker_get_change_detector_info(pft_tracker* t, int32_t* out4) {
+  if (!t || !out4) { set_last_error("null argument"); return PFT_ERR_INVALID; }
+  out4[0] = t->change_counter; out4[1] = t->cd_tests; out4[2] = t->cd_last_found; out4[3] = t->changed ? 1 : 0;
+  return PFT_OK;
 }
 int pft_tracker_update(pft_tracker* t) {
   if (!t) { set_last_error("null tracker"); return PFT_ERR_INVALID; }

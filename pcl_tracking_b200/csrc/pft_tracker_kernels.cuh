@@ -1400,13 +1400,69 @@ struct OctHeaderD {
   int depth, root, leaf_count, n_nodes, bbox_defined, overflow, pad0, pad1;
 };
 
-__device__ inline int oct_new_node(OctNodeD* nodes, OctHeaderD& H, int cap) {
+// Change detector: the same tree with per-leaf test stamps instead of point lists, kept across tests
+struct CdNodeD { int child[8]; int last, count, prev_hit, pad; };
+struct CdHeaderD {
+  double mn[3], mx[3];
+  double res;
+  int depth, root, leaf_count, n_nodes, bbox_defined, overflow, test_id, found;
+};
+
+__device__ inline void oct_node_init(OctNodeD& n) { n.head = -1; n.tail = -1; }
+__device__ inline void oct_node_init(CdNodeD& n) { n.last = 0; n.count = 0; n.prev_hit = 0; n.pad = 0; }
+
+template <typename NodeT, typename HdrT>
+__device__ inline int oct_new_node(NodeT* nodes, HdrT& H, int cap) {
   if (H.n_nodes >= cap) { H.overflow = 1; return 0; }
-  OctNodeD& n = nodes[H.n_nodes];
+  NodeT& n = nodes[H.n_nodes];
 #pragma unroll
   for (int c = 0; c < 8; ++c) n.child[c] = -1;
-  n.head = -1; n.tail = -1;
+  oct_node_init(n);
   return H.n_nodes++;
+}
+
+// OctreePointCloud::addPointIdx up to the leaf: adoptBoundingBoxToPoint (the box doubles towards a point that falls
+// outside: a new root is put on top), then the key from the CURRENT box and the descent, creating what is missing.
+// Returns the leaf node (meaningless once H.overflow is set).
+template <typename NodeT, typename HdrT>
+__device__ inline int oct_insert(HdrT& H, NodeT* nodes, int node_cap, const double v[3]) {
+  const double min_value = (double)1.1920928955078125e-07f;  // std::numeric_limits<float>::epsilon()
+  while (true) {
+    bool up[3], any = false;
+    for (int d = 0; d < 3; ++d) { const bool lo = v[d] < H.mn[d]; up[d] = v[d] >= H.mx[d]; any = any || lo || up[d]; }
+    if (!(any || !H.bbox_defined)) break;
+    if (H.bbox_defined) {
+      const int ci = ((!up[0]) << 2) | ((!up[1]) << 1) | (!up[2]);
+      const int nr = oct_new_node(nodes, H, node_cap);
+      nodes[nr].child[ci] = H.root;
+      H.root = nr;
+      double side = (double)(1 << H.depth) * H.res;
+      for (int d = 0; d < 3; ++d) if (!up[d]) H.mn[d] -= side;
+      H.depth++;
+      side = (double)(1 << H.depth) * H.res - min_value;
+      for (int d = 0; d < 3; ++d) H.mx[d] = H.mn[d] + side;
+      if (H.depth > 30 || H.overflow) { H.overflow = 1; return 0; }
+    } else {
+      for (int d = 0; d < 3; ++d) { H.mn[d] = v[d] - H.res / 2; H.mx[d] = v[d] + H.res / 2; }
+      // getKeyBitSize (the tree is empty whenever the box is still undefined)
+      unsigned int mk[3];
+      for (int d = 0; d < 3; ++d) mk[d] = (unsigned int)ceil((H.mx[d] - H.mn[d]) / H.res);
+      const unsigned int max_voxels = max(max(max(mk[0], mk[1]), mk[2]), 2u);
+      H.depth = (int)fmax(fmin(30.0, ceil(log2((double)max_voxels) - min_value)), 0.0);
+      const double side = (double)(1 << H.depth) * H.res - min_value;
+      for (int d = 0; d < 3; ++d) { const double over = (side - (H.mx[d] - H.mn[d])) / 2.0; H.mn[d] -= over; H.mx[d] += over; }
+      H.bbox_defined = 1;
+    }
+  }
+  const unsigned int key[3] = {(unsigned int)((v[0] - H.mn[0]) / H.res), (unsigned int)((v[1] - H.mn[1]) / H.res), (unsigned int)((v[2] - H.mn[2]) / H.res)};
+  int n = H.root;
+  for (int level = H.depth - 1; level >= 0; --level) {
+    const unsigned int mask = 1u << level;
+    const int ci = ((!!(key[0] & mask)) << 2) | ((!!(key[1] & mask)) << 1) | (!!(key[2] & mask));
+    if (nodes[n].child[ci] < 0) { const int c = oct_new_node(nodes, H, node_cap); nodes[n].child[ci] = c; }
+    n = nodes[n].child[ci];
+  }
+  return n;
 }
 
 __global__ void octree_build_kernel(const float4* __restrict__ scene, const CloudHeader* __restrict__ scene_hdr, const IndexHeader* __restrict__ ihdr,
@@ -1417,59 +1473,62 @@ __global__ void octree_build_kernel(const float4* __restrict__ scene, const Clou
   for (int d = 0; d < 3; ++d) { H.mn[d] = 0.0; H.mx[d] = 0.0; }
   H.res = res; H.depth = 0; H.leaf_count = 0; H.n_nodes = 0; H.bbox_defined = 0; H.overflow = 0; H.pad0 = H.pad1 = 0;
   H.root = oct_new_node(nodes, H, node_cap);
-  const double min_value = (double)1.1920928955078125e-07f;  // std::numeric_limits<float>::epsilon()
   const int ns = h.valid ? scene_hdr->n : 0;
   for (int i = 0; i < ns; ++i) {
     const float4 p = scene[i];
     if (!in_crop(p, h)) continue;  // cropInputPointCloud: the octree indexes the cropped cloud, in input order
     const double v[3] = {(double)p.x, (double)p.y, (double)p.z};
-    // adoptBoundingBoxToPoint
-    while (true) {
-      bool up[3], any = false;
-      for (int d = 0; d < 3; ++d) { const bool lo = v[d] < H.mn[d]; up[d] = v[d] >= H.mx[d]; any = any || lo || up[d]; }
-      if (!(any || !H.bbox_defined)) break;
-      if (H.bbox_defined) {
-        const int ci = ((!up[0]) << 2) | ((!up[1]) << 1) | (!up[2]);
-        const int nr = oct_new_node(nodes, H, node_cap);
-        nodes[nr].child[ci] = H.root;
-        H.root = nr;
-        double side = (double)(1 << H.depth) * H.res;
-        for (int d = 0; d < 3; ++d) if (!up[d]) H.mn[d] -= side;
-        H.depth++;
-        side = (double)(1 << H.depth) * H.res - min_value;
-        for (int d = 0; d < 3; ++d) H.mx[d] = H.mn[d] + side;
-        if (H.depth > 30 || H.overflow) { H.overflow = 1; break; }
-      } else {
-        for (int d = 0; d < 3; ++d) { H.mn[d] = v[d] - H.res / 2; H.mx[d] = v[d] + H.res / 2; }
-        // getKeyBitSize
-        unsigned int mk[3];
-        for (int d = 0; d < 3; ++d) mk[d] = (unsigned int)ceil((H.mx[d] - H.mn[d]) / H.res);
-        const unsigned int max_voxels = max(max(max(mk[0], mk[1]), mk[2]), 2u);
-        H.depth = (int)fmax(fmin(30.0, ceil(log2((double)max_voxels) - min_value)), 0.0);
-        const double side = (double)(1 << H.depth) * H.res - min_value;
-        if (H.leaf_count == 0) {
-          for (int d = 0; d < 3; ++d) { const double over = (side - (H.mx[d] - H.mn[d])) / 2.0; H.mn[d] -= over; H.mx[d] += over; }
-        } else {
-          for (int d = 0; d < 3; ++d) H.mx[d] = H.mn[d] + side;
-        }
-        H.bbox_defined = 1;
-      }
-    }
+    const int n = oct_insert(H, nodes, node_cap, v);
     if (H.overflow) break;
-    // addPointIdx: key from the CURRENT box, descend / create, append to the leaf (insertion order)
-    const unsigned int key[3] = {(unsigned int)((v[0] - H.mn[0]) / H.res), (unsigned int)((v[1] - H.mn[1]) / H.res), (unsigned int)((v[2] - H.mn[2]) / H.res)};
-    int n = H.root;
-    for (int level = H.depth - 1; level >= 0; --level) {
-      const unsigned int mask = 1u << level;
-      const int ci = ((!!(key[0] & mask)) << 2) | ((!!(key[1] & mask)) << 1) | (!!(key[2] & mask));
-      if (nodes[n].child[ci] < 0) { const int c = oct_new_node(nodes, H, node_cap); nodes[n].child[ci] = c; }
-      n = nodes[n].child[ci];
-    }
+    // append to the leaf (insertion order)
     if (nodes[n].head < 0) { nodes[n].head = i; H.leaf_count++; } else next[nodes[n].tail] = i;
     nodes[n].tail = i;
     next[i] = -1;
   }
   *out = H;
+}
+
+// ParticleFilterTracker::testChangeDetection: setInputCloud(cropped) + addPointsFromInputCloud +
+// getPointIndicesFromNewVoxels(min_points) + switchBuffers of a pcl::octree::OctreePointCloudChangeDetector that lives
+// as long as the tracker.  The double-buffered octree reports the leaves the previous buffer did not have: here every
+// leaf carries the id of the last test that filled it, its point count in that test and whether it had also been
+// filled by the test before.  *found = number of point indices upstream would report (changed_ = found > 0).
+// One thread: the keys depend on the order in which the box grew (see octree_build_kernel).
+__global__ void change_detect_kernel(const float4* __restrict__ scene, const CloudHeader* __restrict__ scene_hdr, const IndexHeader* __restrict__ ihdr,
+                                     double res, CdNodeD* nodes, int node_cap, CdHeaderD* hdr, int min_points, int* __restrict__ out /* found, overflow */) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const IndexHeader h = *ihdr;
+  CdHeaderD H = *hdr;
+  if (H.n_nodes == 0) {  // first test (the buffer is zero-filled when it is allocated or reset)
+    for (int d = 0; d < 3; ++d) { H.mn[d] = 0.0; H.mx[d] = 0.0; }
+    H.res = res; H.depth = 0; H.leaf_count = 0; H.bbox_defined = 0; H.overflow = 0; H.test_id = 0; H.found = 0;
+    H.root = oct_new_node(nodes, H, node_cap);
+  }
+  const int test = ++H.test_id;
+  int found = 0;
+  const int ns = h.valid ? scene_hdr->n : 0;
+  for (int i = 0; i < ns; ++i) {
+    const float4 p = scene[i];
+    if (!in_crop(p, h)) continue;
+    const double v[3] = {(double)p.x, (double)p.y, (double)p.z};
+    const int n = oct_insert(H, nodes, node_cap, v);
+    if (H.overflow) break;
+    CdNodeD& leaf = nodes[n];
+    if (leaf.last != test) {
+      leaf.prev_hit = (leaf.last == test - 1 && test > 1) ? 1 : 0;
+      leaf.last = test; leaf.count = 0;
+    }
+    const int c = ++leaf.count;
+    // a new leaf is reported once it holds min_points points: all of them at that moment, one more with each later point
+    if (!leaf.prev_hit) {
+      const int thr = max(min_points, 1);
+      if (c == thr) found += c; else if (c > thr) found += 1;
+    }
+  }
+  H.found = found;
+  *hdr = H;
+  out[0] = found;
+  out[1] = H.overflow;
 }
 
 // approxNearestSearch + approxNearestSearchRecursive.  Returns the index IN THE INPUT CLOUD (-1: empty tree).
@@ -1584,6 +1643,12 @@ __global__ void __launch_bounds__(256) weight_approx_kernel(const WeightApproxAr
 
 // Where particle i's raw weight lives in the all-gathered buffer [nranks][slice_cap].
 __device__ __forceinline__ int raw_slot(int i, int nranks, int slice_cap) { return (i % nranks) * slice_cap + i / nranks; }
+
+// change detector found nothing new: normalizeWeight() runs on the weights the particles already carry
+__global__ void weights_to_raw_kernel(const TrackerState* st, const DevParticle* __restrict__ parts, float* __restrict__ raw, int nranks, int slice_cap) {
+  const int n = st->particle_num;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) raw[raw_slot(i, nranks, slice_cap)] = parts[i].weight;
+}
 
 // raw weight = -(float)sum over chunks (fixed order).  In peer mode the kernel IS the all-gather: every value is
 // stored into every rank's window over NVLink and the last block to finish raises the peers' flags.

@@ -488,6 +488,24 @@ class ParticleFilterOMPTracker:
     def setMinIndices(self, n):
         self._si(capi.MIN_INDICES, n)
 
+    # change detector of pcl::tracking::ParticleFilterTracker (off by default and in the reference)
+    def setUseChangeDetector(self, use):
+        self._si(capi.USE_CHANGE_DETECTOR, 1 if use else 0)
+
+    def setIntervalOfChangeDetection(self, n):
+        self._si(capi.CHANGE_DETECTOR_INTERVAL, int(n))
+
+    def setMinPointsOfChangeDetection(self, n):
+        self._si(capi.CHANGE_DETECTOR_MIN_POINTS, int(n))
+
+    def setResolutionOfChangeDetection(self, r):
+        self._sd(capi.CHANGE_DETECTOR_RESOLUTION, float(r))
+
+    def changeDetectorInfo(self):
+        out = np.zeros(4, dtype=np.int32)
+        check(capi.load().pft_tracker_get_change_detector_info(self._h, ptr(out)))
+        return {"counter": int(out[0]), "tests": int(out[1]), "last_found": int(out[2]), "changed": bool(out[3])}
+
     def setAlpha(self, a):
         self._sd(capi.ALPHA, a)
 

@@ -415,3 +415,89 @@ def test_segment_plane_known_answer():
     # without refinement the coefficients are those of the winning sample
     r0 = oracle.segment_plane(pts, samples, 0.015, 1000, 0.99, False)
     assert r0["best"] == r["best"] and np.array_equal(r0["coeff"], r["ransac_coeff"])
+
+
+# ------------------------------------------------------------------ change detector
+def _cd_cloud(xyz):
+    a = np.zeros(len(xyz), dtype=oracle.POINT)
+    xyz = np.asarray(xyz, dtype=np.float32).reshape(-1, 3)
+    a["x"], a["y"], a["z"] = xyz[:, 0], xyz[:, 1], xyz[:, 2]
+    return a
+
+
+def test_change_detector_known_answers():
+    """OctreePointCloudChangeDetector as testChangeDetection drives it: everything is new for the first cloud, nothing
+    for a repeated cloud, only the voxels the PREVIOUS cloud lacked afterwards (A, B, A reports A's own voxels again),
+    and new voxels with fewer than min_points points are ignored."""
+    # (the first point ever added ends up on the upper edge of its voxel: the initial box [p0 - res/2, p0 + res/2] is
+    #  widened to two voxels per axis around its centre -- the other points are placed well inside their voxels)
+    a = _cd_cloud([(0, 0, 0), (0.103, 0.003, 0.003), (0.104, 0.003, 0.003)])
+    b = _cd_cloud([(0, 0, 0), (0.503, 0.303, 0.203), (0.504, 0.303, 0.203), (0.5045, 0.303, 0.203)])
+    far = _cd_cloud([(-3.003, 2.003, 7.503), (0, 0, 0)])   # forces the bounding box to double several times
+    assert oracle.change_detector_sequence([a, a, b, a, a], 0.01, 0).tolist() == [3, 0, 3, 2, 0]
+    assert oracle.change_detector_sequence([a, b, far, a], 0.01, 0).tolist() == [3, 3, 1, 2]
+    assert oracle.change_detector_sequence([a, b], 0.01, 2).tolist() == [2, 3]
+    assert oracle.change_detector_sequence([a, b], 0.01, 4).tolist() == [0, 0]
+    empty = _cd_cloud(np.zeros((0, 3)))
+    assert oracle.change_detector_sequence([empty, a, empty, a], 0.01, 0).tolist() == [0, 3, 0, 3]
+    nan = _cd_cloud([(np.nan, 0, 0), (0.003, 0.003, 0.003)])
+    assert oracle.change_detector_sequence([nan], 0.01, 0).tolist() == [1]
+
+
+@pytest.mark.parametrize("res,min_points", [(0.01, 0), (0.02, 2), (0.05, 3)])
+def test_change_detector_equals_voxel_set_difference(res, min_points):
+    """The double-buffered octree is a voxel set difference on the lattice the first point anchors (origin = first
+    point - resolution + eps/2, growth shifts the box by whole voxels): checked against numpy on random clouds that
+    overlap partly and make the box grow in every direction."""
+    rng = np.random.default_rng(int(res * 1000) + min_points)
+    clouds = []
+    for k in range(6):
+        centre = rng.uniform(-0.3, 0.3, 3) * (1 + k)
+        n = int(rng.integers(200, 500))
+        pts = centre + rng.uniform(-0.15, 0.15, (n, 3))
+        if k:   # keep a part of the previous cloud
+            prev = np.stack([clouds[-1]["x"], clouds[-1]["y"], clouds[-1]["z"]], axis=1).astype(np.float64)
+            pts = np.concatenate([pts, prev[: len(prev) // 2]])
+        clouds.append(_cd_cloud(pts))
+    got = oracle.change_detector_sequence(clouds, res, min_points)
+    p0 = np.array([clouds[0]["x"][0], clouds[0]["y"][0], clouds[0]["z"][0]], dtype=np.float64)
+    eps = float(np.finfo(np.float32).eps)
+    origin = p0 - res / 2 - ((2 * res - eps) - res) / 2
+    prev_keys = set()
+    for k, c in enumerate(clouds):
+        xyz = np.stack([c["x"], c["y"], c["z"]], axis=1).astype(np.float64)
+        keys = np.floor((xyz - origin) / res).astype(np.int64)
+        uniq, inv, counts = np.unique(keys, axis=0, return_inverse=True, return_counts=True)
+        want = 0
+        for u, cnt in zip(map(tuple, uniq), counts):
+            if u not in prev_keys and cnt >= min_points:
+                want += int(cnt)
+        assert got[k] == want, (k, got[k], want)
+        prev_keys = set(map(tuple, uniq))
+
+
+def test_tracker_with_change_detector_freezes_on_a_static_scene():
+    """weight() with use_change_detector_: a test every `interval` calls; on a static scene the second test finds
+    nothing new, changed_ drops to false, the weights are not recomputed and resample()/update() are skipped."""
+    rng = np.random.default_rng(5)
+    scene = oracle.make_points(rng.uniform(-0.2, 0.2, (3000, 3)).astype(np.float32) + np.float32([0, 0, 1.0]), rng.integers(0, 1 << 24, 3000).astype(np.uint32))
+    model = oracle.make_points(rng.uniform(-0.05, 0.05, (200, 3)).astype(np.float32), rng.integers(0, 1 << 24, 200).astype(np.uint32))
+    t = _tracker(kld=False, particle_num=40, nn_mode=oracle.NN_EXACT_GRID)
+    t.set_change_detector(True, interval=1, min_points=1, resolution=0.02)
+    m = np.eye(4, dtype=np.float32)
+    m[:3, 3] = [0, 0, 1.0]
+    t.set_trans(m[:3])
+    t.set_reference(model)
+    t.set_input(scene)
+    t.set_i(oracle.ITERATION_NUM, 1)
+    infos = []
+    for f in range(5):
+        t.compute()
+        infos.append(t.change_detector_info())
+    # call 1: counter 0 -> test (everything new) -> counter 1; call 2: counter 1 -> 0, weights computed; call 3: test
+    assert [i["tests"] for i in infos[:2]] == [1, 1] and infos[0]["changed"] and infos[1]["changed"]
+    assert infos[0]["last_found"] > 0
+    # later tests only see what a slightly different crop box adds; once the particle set stops moving nothing is new
+    later = [i for i in infos[2:] if not i["changed"]]
+    for i in later:
+        assert i["last_found"] == 0 and i["counter"] == 0
