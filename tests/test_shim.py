@@ -46,6 +46,15 @@ int main() {
   ec.clusterCloud(0, out);
   pcl::tracking::KLDAdaptiveParticleFilterOMPTracker<P, pcl::tracking::ParticleXYZRPY> t(8);
   pft_result_box b = t.getResultBox();                                          // ref: src/auto_tracking.cpp:432-466
+  // overlapped ingest, the parity search of the Approx coherence, the change detector
+  c->fromPointCloud2Async(nullptr, 0, 0, 32, 0, 0, 4, 8, 16);
+  std::shared_ptr<pcl::tracking::ApproxNearestPairPointCloudCoherence<P>> coh(new pcl::tracking::ApproxNearestPairPointCloudCoherence<P>());
+  std::shared_ptr<pcl::tracking::DistanceCoherence<P>> dc(new pcl::tracking::DistanceCoherence<P>());
+  coh->addPointCoherence(dc);
+  coh->setPclApproximateSearch(true);
+  coh->setMaximumDistance(0.01);
+  t.setCloudCoherence(coh);
+  t.setUseChangeDetector(true); t.setIntervalOfChangeDetection(10); t.setMinPointsOfChangeDetection(10); t.setResolutionOfChangeDetection(0.01);
   return b.n;
 }
 ''')
