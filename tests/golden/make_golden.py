@@ -80,7 +80,54 @@ def compute_aux():
     return out
 
 
+def compute_parity_modes():
+    """Third fixture (oracle_parity_modes_case.npz): the modes that reproduce upstream behaviour the product path
+    improves on -- the greedy octree approxNearestSearch of the Approx coherence, the 512-slot ApproximateVoxelGrid
+    cache, and the change detector."""
+    scene, model, centre = util.small_case(seed=4242, n_scene=3500, n_model=180)
+    n = 24
+    parts = util.particles_around(centre, n, seed=31)
+    t = oracle.Tracker(kld=False)
+    oracle.configure_like_reference(t, particle_num=n, max_particle_num=n, use_hsv=True, nn_mode=oracle.NN_PCL_APPROX)
+    t.set_d(oracle.MAX_DIST, 0.1)
+    t.set_d(oracle.OCTREE_RES, 0.01)
+    t.set_reference(model)
+    t.set_input(scene)
+    t.set_particles(parts)
+    t.weight(keep_nn=True)
+    cidx, _ = t.cropped()
+    nn_idx, nn_d2 = [], []
+    for p in range(4):
+        i, d = t.nn(p, len(model))
+        nn_idx.append(np.where(i >= 0, cidx[np.maximum(i, 0)], -1))
+        nn_d2.append(d)
+    out = dict(scene=scene, model=model, particles=parts, approx_nn_idx=np.stack(nn_idx), approx_nn_d2=np.stack(nn_d2),
+               approx_raw=t.raw_weights(), approx_weights=t.get_particles()["weight"])
+    out["approx_grid"] = oracle.approx_voxel_grid_pcl(oracle.passthrough(scene, 2, 0.0, 10.0), 0.02)
+    # change detector: the tracker's own sequence of tests on a scene that stands still, jumps and stands still again
+    c = oracle.Tracker(kld=False)
+    oracle.configure_like_reference(c, particle_num=n, max_particle_num=n, use_hsv=True, nn_mode=oracle.NN_EXACT_GRID)
+    c.set_d(oracle.MAX_DIST, 0.1)
+    c.set_i(oracle.SAMPLER, oracle.SAMPLER_CDF)
+    c.set_change_detector(True, interval=0, min_points=2, resolution=0.03)
+    c.set_reference(model)
+    c.set_particles(parts)
+    infos, weights = [], []
+    for dx in (0.0, 0.0, 0.05, 0.05):
+        sc = scene.copy()
+        sc["x"] += np.float32(dx)
+        c.set_input(sc)
+        c.weight()
+        i = c.change_detector_info()
+        infos.append([i["counter"], i["tests"], i["last_found"], int(i["changed"])])
+        weights.append(c.get_particles()["weight"].copy())
+    out["cd_info"] = np.array(infos, dtype=np.int32)
+    out["cd_weights"] = np.stack(weights)
+    return out
+
+
 if __name__ == "__main__":
+    np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "oracle_parity_modes_case.npz"), **compute_parity_modes())
     np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "oracle_aux_case.npz"), **compute_aux())
     np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "oracle_small_case.npz"), **compute())
     print("written")

@@ -99,3 +99,50 @@ def test_cuda_path_matches_committed_aux_fixture():
     np.testing.assert_allclose(box["center"], want["box_center"], atol=1e-4)
     np.testing.assert_allclose(box["eigenvalues"], want["box_eigenvalues"], rtol=1e-4, atol=1e-9)
     np.testing.assert_allclose(box["axes"], want["box_axes"], atol=2e-3)
+
+
+MODES = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_parity_modes_case.npz")
+
+
+def test_oracle_reproduces_committed_parity_modes_fixture():
+    want = np.load(MODES)
+    got = make_golden.compute_parity_modes()
+    for k in want.files:
+        a, b = want[k], np.asarray(got[k])
+        assert a.shape == b.shape, k
+        assert a.tobytes() == b.tobytes(), k
+
+
+@pytest.mark.gpu
+def test_cuda_parity_modes_match_committed_fixture():
+    """PFT_NN_PCL_APPROX, pft_approx_voxel_grid_pcl and the change detector against the committed fixture."""
+    from pcl_tracking_b200 import pcl
+    from tests import util
+    want = np.load(MODES)
+    scene, model, parts = want["scene"], want["model"], want["particles"]
+    n = len(parts)
+    g, _ = util.make_pair(kld=False, particle_num=n, use_hsv=True)
+    g._si(pcl.capi.NN_MODE, pcl.capi.NN_PCL_APPROX)
+    cloud = pcl.PointCloud(scene)
+    g.setReferenceCloud(model); g.setInputCloud(cloud); g.setParticles(parts); g.setDebugNN(4)
+    g.weight()
+    for p in range(4):
+        gi, gd = g.nn(p, len(model))
+        np.testing.assert_array_equal(gi, want["approx_nn_idx"][p])
+        np.testing.assert_array_equal(gd, want["approx_nn_d2"][p])
+    np.testing.assert_allclose(g.rawWeights(), want["approx_raw"], rtol=1e-5)
+    np.testing.assert_allclose(g.getParticles()["weight"], want["approx_weights"], rtol=1e-5, atol=1e-12)
+    vg = pcl.ApproximateVoxelGrid()
+    vg.setLeafSize(0.02); vg.setPassThrough("z", 0.0, 10.0); vg.setPclApproximateMode(True); vg.setInputCloud(cloud)
+    assert vg.filter().to_numpy().tobytes() == want["approx_grid"].tobytes()
+    c, _ = util.make_pair(kld=False, particle_num=n, use_hsv=True)
+    c.setUseChangeDetector(True); c.setIntervalOfChangeDetection(0); c.setMinPointsOfChangeDetection(2); c.setResolutionOfChangeDetection(0.03)
+    c.setReferenceCloud(model); c.setParticles(parts)
+    for k, dx in enumerate((0.0, 0.0, 0.05, 0.05)):
+        sc = scene.copy()
+        sc["x"] += np.float32(dx)
+        c.setInputCloud(pcl.PointCloud(sc))
+        c.weight()
+        i = c.changeDetectorInfo()
+        assert [i["counter"], i["tests"], i["last_found"], int(i["changed"])] == want["cd_info"][k].tolist()
+        np.testing.assert_allclose(c.getParticles()["weight"], want["cd_weights"][k], rtol=1e-5, atol=1e-12)
