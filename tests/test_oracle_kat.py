@@ -501,3 +501,33 @@ def test_tracker_with_change_detector_freezes_on_a_static_scene():
     later = [i for i in infos[2:] if not i["changed"]]
     for i in later:
         assert i["last_found"] == 0 and i["counter"] == 0
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_euclidean_clusters_equal_scipy_connected_components(seed):
+    """Independent check of the clustering restatement: the clusters are the connected components of the graph that
+    joins points closer than the tolerance (scipy cKDTree + csgraph), filtered by size, largest first."""
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import connected_components
+    from scipy.spatial import cKDTree
+    rng = np.random.default_rng(seed)
+    blobs = [rng.normal(c, s, (m, 3)) for c, s, m in (((0, 0, 1.0), 0.03, 400), ((0.5, 0.1, 1.1), 0.02, 250), ((-0.4, 0.3, 0.9), 0.015, 120),
+                                                      ((0.1, -0.6, 1.3), 0.05, 90))]
+    xyz = np.concatenate(blobs + [rng.uniform(-1, 1, (150, 3)) + np.array([0, 0, 1.0])]).astype(np.float32)
+    xyz = xyz[rng.permutation(len(xyz))]
+    tol, mn, mx = 0.02, 20, 380
+    labels, sizes = oracle.euclidean_clusters(oracle.make_points(xyz), tol, mn, mx)
+    pairs = cKDTree(xyz.astype(np.float64)).query_pairs(tol, output_type="ndarray")
+    n = len(xyz)
+    g = coo_matrix((np.ones(len(pairs)), (pairs[:, 0], pairs[:, 1])), shape=(n, n))
+    _, comp = connected_components(g, directed=False)
+    comp_sizes = np.bincount(comp)
+    kept = [c for c in range(len(comp_sizes)) if mn <= comp_sizes[c] <= mx]
+    assert sorted(sizes.tolist(), reverse=True) == sizes.tolist()
+    assert sorted((int(comp_sizes[c]) for c in kept), reverse=True) == sizes.tolist()
+    assert len(kept) >= 2
+    # same partition: every kept component carries exactly one label, everything else is unlabelled
+    for c in kept:
+        lab = np.unique(labels[comp == c])
+        assert len(lab) == 1 and lab[0] >= 0 and sizes[lab[0]] == comp_sizes[c]
+    assert (labels[~np.isin(comp, kept)] == -1).all()
