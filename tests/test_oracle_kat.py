@@ -531,3 +531,85 @@ def test_euclidean_clusters_equal_scipy_connected_components(seed):
         lab = np.unique(labels[comp == c])
         assert len(lab) == 1 and lab[0] >= 0 and sizes[lab[0]] == comp_sizes[c]
     assert (labels[~np.isin(comp, kept)] == -1).all()
+
+
+def _py_octree_approx_nearest(xyz, res, queries):
+    """Second, flat restatement of OctreePointCloud::addPointsFromInputCloud + approxNearestSearch (SURVEY A.5) in
+    numpy/Python: no tree, only the voxel keys -- the bounding box grows point by point as upstream's does (every
+    growth re-bases the keys of the points already in), and the greedy descent walks the sets of occupied key prefixes."""
+    eps = float(np.finfo(np.float32).eps)
+    mn = np.zeros(3); mx = np.zeros(3)
+    depth, defined = 0, False
+    keys = np.zeros((len(xyz), 3), dtype=np.int64)
+    n_in = 0
+    for i, p in enumerate(xyz.astype(np.float64)):
+        while True:
+            lo = p < mn
+            up = p >= mx
+            if not (lo.any() or up.any() or not defined):
+                break
+            if defined:
+                side = float(1 << depth) * res
+                for d in range(3):
+                    if not up[d]:
+                        mn[d] -= side
+                        keys[:n_in, d] += 1 << depth      # the old root becomes the upper child along this axis
+                depth += 1
+                mx = mn + (float(1 << depth) * res - eps)
+            else:
+                mn = p - res / 2
+                mx = p + res / 2
+                mk = np.ceil((mx - mn) / res).astype(np.int64)
+                depth = int(max(min(30.0, np.ceil(np.log2(float(max(mk.max(), 2))) - eps)), 0.0))
+                side = float(1 << depth) * res - eps
+                over = (side - (mx - mn)) / 2.0
+                mn = mn - over
+                mx = mx + over
+                defined = True
+        keys[i] = ((p - mn) / res).astype(np.int64)   # truncation, as the unsigned cast
+        n_in = i + 1
+    occupied = [set() for _ in range(depth + 1)]          # level l: key prefixes of l bits
+    leaves = {}
+    for i, k in enumerate(map(tuple, keys)):
+        for l in range(depth + 1):
+            occupied[l].add(tuple(int(c) >> (depth - l) for c in k))
+        leaves.setdefault(k, []).append(i)
+    out_idx, out_d2 = [], []
+    f32 = np.float32
+    for q in queries.astype(np.float32):
+        key = (0, 0, 0)
+        for l in range(1, depth + 1):
+            cell = res * float(1 << (depth - l))
+            best, best_key = None, None
+            for ci in range(8):
+                nk = ((key[0] << 1) + ((ci >> 2) & 1), (key[1] << 1) + ((ci >> 1) & 1), (key[2] << 1) + (ci & 1))
+                if nk not in occupied[l]:
+                    continue
+                c = [f32((float(nk[d]) + 0.5) * cell + mn[d]) for d in range(3)]
+                dx, dy, dz = f32(c[0] - q[0]), f32(c[1] - q[1]), f32(c[2] - q[2])
+                dist = float(f32(f32(f32(dx * dx) + f32(dy * dy)) + f32(dz * dz)))
+                if best is None or dist < best:
+                    best, best_key = dist, nk
+            key = best_key
+        smallest, idx, d2 = None, -1, f32(0)
+        for i in leaves[key]:
+            p = xyz[i]
+            dx, dy, dz = f32(p[0] - q[0]), f32(p[1] - q[1]), f32(p[2] - q[2])
+            sd = f32(f32(f32(dx * dx) + f32(dy * dy)) + f32(dz * dz))
+            if smallest is None or float(sd) < smallest:
+                smallest, idx, d2 = float(sd), i, sd
+        out_idx.append(idx)
+        out_d2.append(d2)
+    return np.array(out_idx, dtype=np.int32), np.array(out_d2, dtype=np.float32)
+
+
+@pytest.mark.parametrize("seed,res", [(11, 0.01), (12, 0.02), (13, 0.007)])
+def test_octree_approx_nearest_equals_flat_restatement(seed, res):
+    rng = np.random.default_rng(seed)
+    # an object-sized cloud entered in an order that makes the box grow in every direction
+    xyz = (rng.normal(0, 0.06, (700, 3)) + np.array([0.3, -0.2, 1.1])).astype(np.float32)
+    q = (rng.normal(0, 0.07, (150, 3)) + np.array([0.3, -0.2, 1.1])).astype(np.float32)
+    want_idx, want_d2 = _py_octree_approx_nearest(xyz, res, q)
+    idx, d2 = oracle.octree_approx_nearest(oracle.make_points(xyz), res, q)
+    np.testing.assert_array_equal(idx, want_idx)
+    np.testing.assert_array_equal(d2, want_d2)
