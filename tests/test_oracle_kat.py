@@ -613,3 +613,66 @@ def test_octree_approx_nearest_equals_flat_restatement(seed, res):
     idx, d2 = oracle.octree_approx_nearest(oracle.make_points(xyz), res, q)
     np.testing.assert_array_equal(idx, want_idx)
     np.testing.assert_array_equal(d2, want_d2)
+
+
+@pytest.mark.parametrize("use_hsv", [False, True])
+def test_weight_equals_numpy_composition(use_hsv):
+    """The oracle's weight() as a whole against a numpy composition of its parts: transform in the
+    contract's operation order, crop to the union box (inclusive, finite only), brute-force nearest neighbour with
+    ties to the lower index, coherence summed in model order in fp64, raw weight = -(float)sum, then normalizeWeight."""
+    from tests import util
+    f32 = np.float32
+    scene, model, centre = util.small_case(seed=17, n_scene=1500, n_model=80)
+    scene["x"][5] = np.nan
+    n = 6
+    parts = util.particles_around(centre, n, seed=18)
+    t = _tracker(kld=False, particle_num=n, max_particle_num=n, use_hsv=use_hsv, nn_mode=oracle.NN_EXACT_BRUTE)
+    t.set_d(oracle.MAX_DIST, 0.1)
+    t.set_reference(model)
+    t.set_input(scene)
+    t.set_particles(parts)
+    t.weight(keep_nn=True)
+    # numpy
+    transed = []
+    for p in parts:
+        m = oracle.particle_to_matrix([p["x"], p["y"], p["z"], p["roll"], p["pitch"], p["yaw"]]).astype(f32)
+        x, y, z = model["x"], model["y"], model["z"]
+        q = np.stack([((m[r, 0] * x + m[r, 1] * y) + m[r, 2] * z) + m[r, 3] for r in range(3)], axis=1).astype(f32)
+        transed.append(q)
+    allq = np.concatenate(transed)
+    lo, hi = allq.min(0), allq.max(0)
+    np.testing.assert_array_equal(t.aabb(), np.concatenate([lo, hi]))
+    sxyz = np.stack([scene["x"], scene["y"], scene["z"]], axis=1)
+    keep = np.isfinite(sxyz).all(1)
+    with np.errstate(invalid="ignore"):
+        for d in range(3):
+            keep &= (sxyz[:, d] >= lo[d]) & (sxyz[:, d] <= hi[d])
+    cidx, _ = t.cropped()
+    np.testing.assert_array_equal(cidx, np.nonzero(keep)[0])
+    cxyz = sxyz[keep]
+    crgba = scene["rgba"][keep]
+    raws = []
+    for i, q in enumerate(transed):
+        dx = q[:, None, 0] - cxyz[None, :, 0]
+        dy = q[:, None, 1] - cxyz[None, :, 1]
+        dz = q[:, None, 2] - cxyz[None, :, 2]
+        d2 = ((dx * dx + dy * dy) + dz * dz).astype(f32)
+        nn = d2.argmin(1)                      # first minimum = lowest index
+        oi, od = t.nn(i, len(model))
+        np.testing.assert_array_equal(oi, nn)
+        np.testing.assert_array_equal(od, d2[np.arange(len(model)), nn])
+        val = 0.0
+        for j in range(len(model)):
+            dd = d2[j, nn[j]]
+            if float(dd) < 0.1 * 0.1:
+                d = float(np.sqrt(dd))
+                c = 1.0 / (1.0 + d * d * 1.0)
+                if use_hsv:
+                    c *= oracle.hsv_coherence(int(model["rgba"][j]), int(crgba[nn[j]]), 0.1)
+                val += c
+        raws.append(-f32(val))
+    raws = np.array(raws, dtype=f32)
+    np.testing.assert_allclose(t.raw_weights(), raws, rtol=2e-7)
+    w = raws.astype(np.float64)
+    e = np.where(w != 0, np.exp(1.0 - 15.0 * (w - w.min()) / (w[w != 0].max() - w.min())), 0.0).astype(f32)
+    np.testing.assert_allclose(t.get_particles()["weight"], (e / f32(e.astype(np.float64).sum())).astype(f32), rtol=1e-6)
