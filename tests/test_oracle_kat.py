@@ -676,3 +676,56 @@ def test_weight_equals_numpy_composition(use_hsv):
     w = raws.astype(np.float64)
     e = np.where(w != 0, np.exp(1.0 - 15.0 * (w - w.min()) / (w[w != 0].max() - w.min())), 0.0).astype(f32)
     np.testing.assert_allclose(t.get_particles()["weight"], (e / f32(e.astype(np.float64).sum())).astype(f32), rtol=1e-6)
+
+
+def _py_approx_voxel_grid(pts, leaf):
+    """Python restatement of pcl::ApproximateVoxelGrid<PointXYZRGBA>::applyFilter (SURVEY A.1): a 512-entry direct-mapped
+    cache keyed by the voxel, fp32 running sums of x, y, z, r, g, b in input order, a partial centroid emitted whenever
+    a different voxel claims the slot, everything left flushed in slot order."""
+    f32 = np.float32
+    inv = f32(1.0) / f32(leaf)
+    slots = [None] * 512
+    out = []
+
+    def flush(s):
+        key, cnt, acc = s
+        c = [a / f32(cnt) for a in acc]
+        rgb = (int(c[3]) << 16) | (int(c[4]) << 8) | int(c[5])
+        out.append((c[0], c[1], c[2], rgb))
+
+    for p in pts:
+        x, y, z = f32(p["x"]), f32(p["y"]), f32(p["z"])
+        key = (int(np.floor(x * inv)), int(np.floor(y * inv)), int(np.floor(z * inv)))
+        h = (key[0] * 7171 + key[1] * 3079 + key[2] * 4231) & 511
+        s = slots[h]
+        if s is not None and s[0] != key:
+            flush(s)
+            s = None
+        if s is None:
+            s = [key, 0, [f32(0)] * 6]
+        rgba = int(p["rgba"])
+        vals = (x, y, z, f32((rgba >> 16) & 255), f32((rgba >> 8) & 255), f32(rgba & 255))
+        s[1] += 1
+        s[2] = [f32(a + v) for a, v in zip(s[2], vals)]
+        slots[h] = s
+    for s in slots:
+        if s is not None:
+            flush(s)
+    return out
+
+
+@pytest.mark.parametrize("seed,leaf,n", [(1, 0.01, 3000), (2, 0.02, 4000), (3, 0.005, 2500)])
+def test_approx_voxel_grid_pcl_equals_python_restatement(seed, leaf, n):
+    rng = np.random.default_rng(seed)
+    # a sensor-like stream: neighbouring points are often in the same voxel, with jumps that cause evictions
+    walk = np.cumsum(rng.normal(0, leaf * 0.4, (n, 3)), axis=0) + np.array([0.2, -0.1, 1.0])
+    jumps = rng.random(n) < 0.05
+    walk[jumps] += rng.uniform(-0.5, 0.5, (int(jumps.sum()), 3))
+    pts = oracle.make_points(walk.astype(np.float32), rng.integers(0, 1 << 24, n).astype(np.uint32))
+    got = oracle.approx_voxel_grid_pcl(pts, leaf)
+    want = _py_approx_voxel_grid(pts, leaf)
+    assert len(got) == len(want)
+    assert len(got) > len(np.unique(np.floor(walk.astype(np.float32) / np.float32(leaf)), axis=0)) * 0.9
+    w = np.array([(a, b, c) for a, b, c, _ in want], dtype=np.float32)
+    np.testing.assert_array_equal(np.stack([got["x"], got["y"], got["z"]], axis=1), w)
+    np.testing.assert_array_equal(got["rgba"] & 0xffffff, np.array([r for _, _, _, r in want], dtype=np.uint32))
