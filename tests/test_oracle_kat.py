@@ -729,3 +729,63 @@ def test_approx_voxel_grid_pcl_equals_python_restatement(seed, leaf, n):
     w = np.array([(a, b, c) for a, b, c, _ in want], dtype=np.float32)
     np.testing.assert_array_equal(np.stack([got["x"], got["y"], got["z"]], axis=1), w)
     np.testing.assert_array_equal(got["rgba"] & 0xffffff, np.array([r for _, _, _, r in want], dtype=np.uint32))
+
+
+def _py_alias_table(w):
+    """genAliasTable (Walker): q_i = w_i * N as a float product, a two-ended stack of the indices with
+    q >= 1 (front) and q < 1 (back)."""
+    n = len(w)
+    q = [float(np.float32(wi) * np.float32(n)) for wi in w]
+    a = list(range(n))
+    hl = [0] * n
+    h, l = 0, n - 1
+    for i in range(n):
+        if q[i] >= 1.0:
+            hl[h] = i; h += 1
+        else:
+            hl[l] = i; l -= 1
+    while h != 0 and l != n - 1:
+        j, k = hl[l + 1], hl[h - 1]
+        a[j] = k
+        q[k] += q[j] - 1.0
+        l += 1
+        if q[k] < 1.0:
+            hl[l] = k; l -= 1
+            h -= 1
+    return a, q
+
+
+def test_alias_sampler_equals_python_restatement():
+    n = 300
+    rng = np.random.default_rng(21)
+    w = (rng.random(n).astype(np.float32) ** 4)
+    w = (w / w.sum()).astype(np.float32)
+    a, q = _py_alias_table(w)
+    s = np.zeros((n, 6), dtype=np.float32)
+    s[:, 0] = np.arange(n)
+    t = _tracker(kld=False, particle_num=n)
+    t.set_i(oracle.SAMPLER, oracle.SAMPLER_ALIAS_PCL)
+    t.set_vec6(oracle.STEP_COV, [0] * 6)
+    t.set_i(oracle.QUAT_SAMPLE, 0)
+    t.set_particles(oracle.make_particles(s, w))
+    usel, normals, umot = synth.draws(1, n, seed=22)
+    t.inject_draws(usel, normals, np.ones_like(umot))   # no motion term
+    t.resample(0)
+    anc = t.ancestors()
+    want = []
+    for u in usel[0][1:n]:   # output particle i draws with entry i of the injected arrays (slot 0 is the representative)
+        ru = float(u) * n
+        k = int(ru)
+        ru -= k
+        want.append(k if ru < q[k] else a[k])
+    got = anc[anc >= 0]
+    assert len(got) == len(want)
+    assert (got == np.array(want)).mean() > 0.995   # (the float/double type of U*N may differ at a table boundary)
+    # the table itself reproduces the weights: column i keeps min(q_i, 1), the rest goes to its alias (columns left
+    # on the "heavy" stack when the light one runs out keep q >= 1 up to rounding: they always return themselves)
+    assert min(q) >= 0.0
+    mass = np.zeros(n)
+    for i in range(n):
+        mass[i] += min(q[i], 1.0)
+        mass[a[i]] += max(1.0 - q[i], 0.0)
+    np.testing.assert_allclose(mass / n, w, atol=2e-6)
