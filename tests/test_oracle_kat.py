@@ -789,3 +789,59 @@ def test_alias_sampler_equals_python_restatement():
         mass[i] += min(q[i], 1.0)
         mass[a[i]] += max(1.0 - q[i], 0.0)
     np.testing.assert_allclose(mass / n, w, atol=2e-6)
+
+
+@pytest.mark.parametrize("eps,bin_size,motion_ratio", [(0.2, 0.1, 0.25), (0.05, 0.03, 0.0), (0.1, 0.05, 1.0)])
+def test_kld_resample_equals_python_control_flow(eps, bin_size, motion_ratio):
+    """KLDAdaptiveParticleFilterTracker::resample (SURVEY A.7) restated in Python around the (separately checked)
+    building blocks: alias pick, sample(), motion with probability motion_ratio_, bins by C truncation, and the stop
+    rule n >= n_max || (k >= 2 && n >= calcKLBound(k))."""
+    n0, n_max = 120, 900
+    rng = np.random.default_rng(int(eps * 1000))
+    st = np.zeros((n0, 6), dtype=np.float32)
+    st[:, :3] = np.array([0.1, -0.2, 1.0]) + rng.normal(0, 0.03, (n0, 3))
+    st[:, 3:] = rng.normal(0, 0.1, (n0, 3))
+    w = rng.random(n0).astype(np.float32) ** 2
+    w = (w / w.sum()).astype(np.float32)
+    parts = oracle.make_particles(st, w)
+    t = _tracker(kld=True, particle_num=n0, max_particle_num=n_max)
+    t.set_i(oracle.SAMPLER, oracle.SAMPLER_ALIAS_PCL)
+    t.set_d(oracle.EPSILON, eps)
+    t.set_d(oracle.MOTION_RATIO, motion_ratio)
+    t.set_vec6(oracle.BIN_SIZE, [bin_size] * 6)
+    step = [0.015 * 0.015] * 3 + [0.015 * 0.015 * 40.0] * 3
+    t.set_vec6(oracle.STEP_COV, step)
+    t.set_particles(parts)
+    motion = oracle.make_particles([[0.01, -0.02, 0.005, 0.02, 0.0, -0.01]])[0]
+    t.set_motion(motion)
+    usel, normals, umot = synth.draws(1, n_max, seed=77)
+    t.inject_draws(usel, normals, umot)
+    t.resample(0)
+    got = t.get_particles()
+    anc = t.ancestors()
+    # Python
+    a, q = _py_alias_table(w)
+    names = ("x", "y", "z", "roll", "pitch", "yaw")
+    bins, k, n = set(), 0, 0
+    want_anc, want = [], []
+    while True:
+        ru = float(usel[0][n]) * n0
+        c = int(ru)
+        ru -= c
+        j = c if ru < q[c] else a[c]
+        x = oracle.particle_sample([float(parts[j][m]) for m in names], [0] * 6, step, normals[0][n], quat_mode=1)
+        xs = np.array([x[m] for m in names], dtype=np.float32)
+        if float(umot[0][n]) < motion_ratio:
+            xs = (xs + np.array([motion[m] for m in names], dtype=np.float32)).astype(np.float32)
+        want_anc.append(j)
+        want.append(xs)
+        b = tuple(int(v) for v in np.trunc(xs / np.float32(bin_size)))
+        if b not in bins:
+            bins.add(b)
+            k += 1
+        n += 1
+        if not (n < n_max and (k < 2 or n < oracle.kl_bound(k, 0.99, eps))):
+            break
+    assert len(got) == n
+    np.testing.assert_array_equal(anc[:n], np.array(want_anc))
+    np.testing.assert_array_equal(np.stack([got[m] for m in names], axis=1), np.stack(want))
