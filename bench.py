@@ -23,8 +23,13 @@ Workloads (config.workload):
 `value`   = likelihood evals/s, whole job, inputs resident in HBM (raw frames pre-uploaded).
 `e2e`     = the same through the public API with HOST buffers: every step uploads the raw frame from
             pinned host memory (3.47 MB) and reads the result pose back (32 B).
+`e2e_pipelined` (N = 1, supplementary) = e2e with the ingest double-buffered: the upload of frame k+1 is issued on the
+            library's copy stream (pft_cloud_upload_async) before frame k is tracked; every step still copies one frame
+            in and reads one pose back.
 --impl reference times the CPU restatement of the PCL-1.8.0 path (oracle/, "port": PCL itself is not
-buildable here) on the box's host cores.
+buildable here) on every host core of the box (the thread count is set explicitly: torchrun exports
+OMP_NUM_THREADS=1); when the time budget forces fewer particles per step, the throughput reported is that of the
+full workload (per-particle stages scaled, per-frame stages as timed; `cpu_baseline.sample` says so).
 """
 import argparse
 import ctypes as C
