@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <float.h>
+#include <string.h>
 
 #include <atomic>
 
@@ -95,6 +96,64 @@ __device__ __forceinline__ int warp_sum(int v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
   return v;
+}
+
+// ------------------------------------------------------------------ bulk async copy (TMA, 1-D) + mbarrier
+// One thread arms the barrier with the byte count and issues the copies; every consumer waits on the phase bit.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// global -> shared, `bytes` a multiple of 16, both addresses 16-byte aligned; completion is counted on `bar`
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
+               "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+  asm volatile(
+      "{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+// ------------------------------------------------------------------ packed fp32 pairs (FADD2 / FMUL2: IEEE round-to-nearest per half, no contraction)
+__device__ __forceinline__ float2 sub2_rn(float2 a, float2 b) {
+  unsigned long long ra, rb, rc;
+  memcpy(&ra, &a, 8); memcpy(&rb, &b, 8);
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(rc) : "l"(ra), "l"(rb));
+  float2 c; memcpy(&c, &rc, 8);
+  return c;
+}
+__device__ __forceinline__ float2 mul2_rn(float2 a, float2 b) {
+  unsigned long long ra, rb, rc;
+  memcpy(&ra, &a, 8); memcpy(&rb, &b, 8);
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rc) : "l"(ra), "l"(rb));
+  float2 c; memcpy(&c, &rc, 8);
+  return c;
+}
+__device__ __forceinline__ float2 add2_rn(float2 a, float2 b) {
+  unsigned long long ra, rb, rc;
+  memcpy(&ra, &a, 8); memcpy(&rb, &b, 8);
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rc) : "l"(ra), "l"(rb));
+  float2 c; memcpy(&c, &rc, 8);
+  return c;
+}
+
+// 1 / x for a finite double x >= 1: hardware seed (20 bits) + two Newton steps (explicit fused multiply-adds: the
+// error of the result is below one ulp; it is not the correctly rounded quotient, see DESIGN "Arithmetic contract")
+__device__ __forceinline__ double rcp_f64(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = __fma_rn(-x, r, 1.0);
+  r = __fma_rn(r, e, r);
+  e = __fma_rn(-x, r, 1.0);
+  r = __fma_rn(r, e, r);
+  return r;
 }
 
 // Block-wide sum of doubles; result valid in thread 0.  `red` holds >= 32 doubles.

@@ -146,21 +146,22 @@ struct pft_tracker {
   PeerSet peers{};
   // graph
   bool graph_enabled = true;
-  cudaGraphExec_t graph_exec = nullptr;
-  const void* graph_scene_pts = nullptr;
-  const void* graph_scene_hdr = nullptr;
-  unsigned long long config_version = 1, graph_version = 0;
+  cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};  // one per value of `cur` at the start of the frame
+  const void* graph_scene_pts[2] = {nullptr, nullptr};
+  const void* graph_scene_hdr[2] = {nullptr, nullptr};
+  unsigned long long config_version = 1, graph_version[2] = {0, 0};
   unsigned long long graph_replays = 0;
-  int graph_nodes = 0;
+  int graph_nodes[2] = {0, 0};
   // device buffers
   DevBuf st, parts[2], mats, slot_aabb, model, model_perm, model_tmp, sort_keys, sort_idx, bbox, raw, partial, cdf, cdf_total, ancestors, bin_keys, tbl_rep,
-      tbl_min, slot_of, klb, d_usel, d_normals, d_umot, idx_hdr, cell_start, ipts, ihsv, icount, dbg_idx, dbg_d2, d_trans, row_table, flists, fneeded, fneeded_list, ffar_list, xlists, xcount, result_box, alias_a, alias_q, alias_hl, oct_hdr, oct_nodes, oct_next, cd_hdr, cd_nodes, cd_out;
+      tbl_min, slot_of, klb, d_usel, d_normals, d_umot, idx_hdr, cell_start, ipts, ipts2, ihsv, icount, dbg_idx, dbg_d2, d_trans, row_table, flists, fpool, fcell_items, fl1_slots, fneeded, fneeded_list, ffar_list, xlists, xcount, result_box, alias_a, alias_q, alias_hl, oct_hdr, oct_nodes, oct_next, cd_hdr, cd_nodes, cd_out;
   int oct_node_cap = 0;
   // change detector (PCL ctor defaults, off in the reference): host-driven, one read-back per test
   bool use_cd = false;
   int cd_interval = 10, cd_filter = 10, change_counter = 0, cd_tests = 0, cd_last_found = -1, cd_node_cap = 0, cd_resets = 0;
   double cd_res = 0.01;
   int weight_smem = 0;  // dynamic shared memory of the weight kernel (bytes)
+  int lists_smem = 0;   // ... of weight_lists_kernel
   int tbl_size = 0;
   int n_slots = 0;
   int chunks = 1, chunk_len = 0;
@@ -194,8 +195,8 @@ void stage_mark(pft_tracker* t, const char* name) {
 void release_all(pft_tracker* t) {
   DevBuf* bufs[] = {&t->st, &t->parts[0], &t->parts[1], &t->mats, &t->slot_aabb, &t->model, &t->model_perm, &t->model_tmp, &t->sort_keys, &t->sort_idx,
                     &t->bbox, &t->raw, &t->partial, &t->cdf, &t->cdf_total, &t->ancestors, &t->bin_keys, &t->tbl_rep, &t->tbl_min, &t->slot_of, &t->klb,
-                    &t->d_usel, &t->d_normals, &t->d_umot, &t->idx_hdr, &t->cell_start, &t->ipts, &t->ihsv, &t->icount, &t->dbg_idx,
-                    &t->dbg_d2, &t->d_trans, &t->row_table, &t->flists, &t->fneeded, &t->fneeded_list, &t->ffar_list, &t->xlists, &t->xcount, &t->result_box, &t->alias_a, &t->alias_q, &t->alias_hl, &t->oct_hdr, &t->oct_nodes, &t->oct_next, &t->cd_hdr, &t->cd_nodes, &t->cd_out};
+                    &t->d_usel, &t->d_normals, &t->d_umot, &t->idx_hdr, &t->cell_start, &t->ipts, &t->ipts2, &t->ihsv, &t->icount, &t->dbg_idx,
+                    &t->dbg_d2, &t->d_trans, &t->row_table, &t->flists, &t->fpool, &t->fcell_items, &t->fl1_slots, &t->fneeded, &t->fneeded_list, &t->ffar_list, &t->xlists, &t->xcount, &t->result_box, &t->alias_a, &t->alias_q, &t->alias_hl, &t->oct_hdr, &t->oct_nodes, &t->oct_next, &t->cd_hdr, &t->cd_nodes, &t->cd_out};
   for (auto* b : bufs) b->release();
 }
 
@@ -239,9 +240,14 @@ double kl_bound(int k, double delta, double eps) {
   return ((k - 1.0) / (2.0 * eps)) * chi * chi * chi;
 }
 
+constexpr long long kMarkCountMaxQueries = 16ll << 20;  // up to this many (particle, model point) pairs cand_mark_kernel counts the queries of every cell
 constexpr int kClusterMinParticles = 4096;  // above this capacity the O(N) replicated stages run as a cluster of kClusterCtas CTAs
 constexpr int kWeightThreads = PFT_WEIGHT_THREADS;  // CTA size of the persistent weight kernel (one CTA per SM), large particle sets
 constexpr int kWeightThreadsSmall = 768;            // small sets (static item split): 85 registers per thread instead of 64 (measured -6 %)
+#ifndef PFT_LIST_THREADS
+#define PFT_LIST_THREADS 512
+#endif
+constexpr int kListThreads = PFT_LIST_THREADS;      // CTA size of weight_lists_kernel (one CTA per SM)
 
 // Row table of the nearest-neighbour search: the (dy,dz) offsets within kRT cells sorted by the lower bound
 // gap(dy)^2 + gap(dz)^2 of their distance (gap(d) = max(|d|-1, 0)), nearer rows first.
@@ -259,7 +265,8 @@ int upload_row_table(pft_tracker* t) {
   });
   int rc = t->row_table.reserve(tab.size() * sizeof(RowEntry));
   if (rc) return rc;
-  PFT_CUDA_TRY(cudaMemcpy(t->row_table.p, tab.data(), tab.size() * sizeof(RowEntry), cudaMemcpyHostToDevice));
+  PFT_CUDA_TRY(cudaMemcpyAsync(t->row_table.p, tab.data(), tab.size() * sizeof(RowEntry), cudaMemcpyHostToDevice, t->run_stream()));
+  PFT_CUDA_TRY(cudaStreamSynchronize(t->run_stream()));
   // the weight kernel stages the scene index in shared memory: ask for everything the SM has
   int dev = t->ctx->device, max_optin = 0;
   PFT_CUDA_TRY(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
@@ -273,10 +280,20 @@ int upload_row_table(pft_tracker* t) {
   PFT_CUDA_TRY(cudaFuncSetAttribute(weight_kernel<false, kWeightThreads, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
   PFT_CUDA_TRY(cudaFuncSetAttribute(weight_kernel<false, kWeightThreadsSmall, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
   t->weight_smem = dyn;
+  PFT_CUDA_TRY(cudaFuncGetAttributes(&fa, weight_lists_kernel<true, kListThreads, true>));
+  int dyn_l = (max_optin - (int)fa.sharedSizeBytes - 1024) & ~15;
+  if (dyn_l < 0) dyn_l = 0;
+  PFT_CUDA_TRY(cudaFuncSetAttribute(weight_lists_kernel<true, kListThreads, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_l));
+  PFT_CUDA_TRY(cudaFuncSetAttribute(weight_lists_kernel<true, kListThreads, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_l));
+  PFT_CUDA_TRY(cudaFuncSetAttribute(weight_lists_kernel<false, kListThreads, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_l));
+  PFT_CUDA_TRY(cudaFuncSetAttribute(weight_lists_kernel<false, kListThreads, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_l));
+  t->lists_smem = dyn_l;
   if (t->list_max_cells / 8 + 64 > max_optin - 2048) t->list_max_cells = (max_optin - 4096) * 8;  // the mark kernel keeps one bit per fine cell in shared memory
-  PFT_CUDA_TRY(cudaFuncSetAttribute(cand_mark_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, t->list_max_cells / 8 + 64));
+  PFT_CUDA_TRY(cudaFuncSetAttribute(cand_mark_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, t->list_max_cells / 8 + 64));
   return PFT_OK;
 }
+
+int upload_kl_table(pft_tracker* t);
 
 int wanted_cap(const pft_tracker* t) { return t->kld ? std::max(t->max_particle_num, t->particle_num) : t->particle_num; }
 
@@ -300,7 +317,10 @@ int ensure_particle_buffers(pft_tracker* t) {
     if ((rc = t->icount.reserve(((size_t)t->max_cells + 16) * sizeof(int)))) return rc;
     if ((rc = upload_row_table(t))) return rc;
     if (t->list_max_cells > 0) {
-      if ((rc = t->flists.reserve(((size_t)t->list_max_cells + 1) * kListK * sizeof(unsigned short)))) return rc;
+      if ((rc = t->flists.reserve(((size_t)t->list_max_cells + 1) * 8 * 8 * sizeof(unsigned int)))) return rc;  // 8 octant records of 8 words per fine cell
+      if ((rc = t->fpool.reserve((size_t)kPoolGroups * 8 * sizeof(unsigned int)))) return rc;
+      if ((rc = t->fcell_items.reserve(((size_t)t->list_max_cells + 16) * sizeof(int2)))) return rc;
+      if ((rc = t->fl1_slots.reserve(((size_t)t->list_max_cells + 1) * kL1Cap * sizeof(unsigned short)))) return rc;
       if ((rc = t->fneeded.reserve(((size_t)t->list_max_cells + 16) * sizeof(unsigned int)))) return rc;
       // blocks of 2x2x2 fine cells: at most ceil(d/2)^3 <= (d+1)^3/8, bounded generously by cells/2 + 4096
       if ((rc = t->fneeded_list.reserve(((size_t)t->list_max_cells / 2 + 4096) * sizeof(int)))) return rc;
@@ -336,13 +356,15 @@ int ensure_particle_buffers(pft_tracker* t) {
   {
     std::vector<float> init((size_t)cap * 6);
     for (int i = 0; i < cap; ++i) { for (int d = 0; d < 3; ++d) { init[6 * i + d] = FLT_MAX; init[6 * i + 3 + d] = -FLT_MAX; } }
-    PFT_CUDA_TRY(cudaMemcpy(t->slot_aabb.p, init.data(), init.size() * sizeof(float), cudaMemcpyHostToDevice));
+    PFT_CUDA_TRY(cudaMemcpyAsync(t->slot_aabb.p, init.data(), init.size() * sizeof(float), cudaMemcpyHostToDevice, s));
+    PFT_CUDA_TRY(cudaStreamSynchronize(s));  // (`init` goes out of scope; the work streams do not synchronise with the legacy default stream)
   }
   if ((rc = t->raw.reserve((size_t)slice * t->nranks * sizeof(float)))) return rc;
-  PFT_CUDA_TRY(cudaMemset(t->raw.p, 0, (size_t)slice * t->nranks * sizeof(float)));
+  PFT_CUDA_TRY(cudaMemsetAsync(t->raw.p, 0, (size_t)slice * t->nranks * sizeof(float), s));
   if ((rc = t->cdf.reserve((size_t)cap * sizeof(unsigned long long)))) return rc;
   if ((rc = t->ancestors.reserve((size_t)cap * sizeof(int)))) return rc;
-  PFT_CUDA_TRY(cudaMemset(t->ancestors.p, 0xff, (size_t)cap * sizeof(int)));
+  PFT_CUDA_TRY(cudaMemsetAsync(t->ancestors.p, 0xff, (size_t)cap * sizeof(int), s));
+  PFT_CUDA_TRY(cudaStreamSynchronize(s));
   if (t->kld) {
     if ((rc = t->bin_keys.reserve((size_t)cap * 6 * sizeof(int)))) return rc;
     int ts = 1024;
@@ -352,6 +374,7 @@ int ensure_particle_buffers(pft_tracker* t) {
     if ((rc = t->tbl_min.reserve((size_t)ts * sizeof(int)))) return rc;
     if ((rc = t->slot_of.reserve((size_t)cap * sizeof(int)))) return rc;
     if ((rc = t->klb.reserve((size_t)(cap + 2) * sizeof(double)))) return rc;
+    if ((rc = upload_kl_table(t))) return rc;  // reserve() dropped the old table: the stop rule reads k up to the new capacity
   }
   return PFT_OK;
 }
@@ -409,6 +432,7 @@ int ensure_index_buffers(pft_tracker* t) {
   PFT_CUDA_TRY(cudaStreamSynchronize(t->run_stream()));
   int rc;
   if ((rc = t->ipts.reserve((cap + 4) * sizeof(float4)))) return rc;
+  if ((rc = t->ipts2.reserve((cap + 4) * sizeof(float4)))) return rc;
   if ((rc = t->ihsv.reserve((cap + 4) * sizeof(unsigned int)))) return rc;
   t->scene_cap = cap;
   return PFT_OK;
@@ -624,36 +648,44 @@ int weight_phase_eval(pft_tracker* t, bool force_raw = false) {
   index_count_kernel<<<gscene, 256, 0, s>>>(in->d_pts(), in->d_hdr(), hdr, t->icount.as<int>());
   PFT_LAUNCH_CHECK();
   stage_mark(t, "index_count_kernel");
-  index_scan_kernel<<<1, 1024, 0, s>>>(hdr, t->icount.as<int>(), t->cell_start.as<int>(), st, t->ipts.as<float4>());
+  index_scan_kernel<<<1, 1024, 0, s>>>(hdr, t->icount.as<int>(), t->cell_start.as<int>(), st, t->ipts.as<float4>(), t->ipts2.as<float4>());
   PFT_LAUNCH_CHECK();
   stage_mark(t, "index_scan_kernel");
   index_scatter_kernel<<<gscene, 256, 0, s>>>(in->d_pts(), in->d_hdr(), hdr, t->cell_start.as<int>(), t->icount.as<int>(), t->ipts.as<float4>(),
-                                              t->ihsv.as<unsigned int>());
+                                              t->ihsv.as<unsigned int>(), t->ipts2.as<float4>());
   PFT_LAUNCH_CHECK();
   stage_mark(t, "index_scatter_kernel");
   if (t->list_max_cells > 0 && t->list_mode && t->nn_mode == PFT_NN_EXACT) {
     // dynamic shared memory: one bit per fine cell the lists are sized for
-    cand_mark_kernel<<<sm * 3, 256, (size_t)(t->list_max_cells / 8 + 64), s>>>(st, hdr, t->model.as<float4>(), t->M, t->mats.as<float>(), t->fneeded.as<unsigned int>(), t->nranks, t->rank);
+    // small query sets: exact query counts per cell (cells with few queries get one list instead of eight octant lists)
+    const long long n_queries = (long long)std::max(1, (t->particle_num > 0 ? t->particle_num : t->n_cap) / t->nranks) * t->M;
+    if (n_queries <= kMarkCountMaxQueries) cand_mark_kernel<true><<<sm * 3, 256, 0, s>>>(st, hdr, t->model.as<float4>(), t->M, t->mats.as<float>(), t->fneeded.as<unsigned int>(), t->nranks, t->rank);
+    else cand_mark_kernel<false><<<sm * 3, 256, (size_t)(t->list_max_cells / 8 + 64), s>>>(st, hdr, t->model.as<float4>(), t->M, t->mats.as<float>(), t->fneeded.as<unsigned int>(), t->nranks, t->rank);
     PFT_LAUNCH_CHECK();
     stage_mark(t, "cand_mark_kernel");
     cand_collect_kernel<<<sm * 2, 256, 0, s>>>(hdr, t->fneeded.as<unsigned int>(), t->fneeded_list.as<int>(), t->xcount.as<int>());
     PFT_LAUNCH_CHECK();
     stage_mark(t, "cand_collect_kernel");
-    cand_build_kernel<<<sm * 8, 256, 0, s>>>(hdr, t->cell_start.as<int>(), t->ipts.as<float4>(), t->max_dist * t->max_dist, t->flists.as<unsigned short>(),
+    cand_build_kernel<<<sm * 8, 256, 0, s>>>(hdr, t->cell_start.as<int>(), t->ipts.as<float4>(), t->max_dist * t->max_dist, t->flists.as<unsigned int>(),
                                             t->fneeded.as<unsigned int>(), t->fneeded_list.as<int>(), t->xlists.as<unsigned short>(),
-                                            t->xcount.as<int>(), t->ffar_list.as<int>());
+                                            t->xcount.as<int>(), t->ffar_list.as<int>(), t->fcell_items.as<int2>(), t->fl1_slots.as<unsigned short>());
     PFT_LAUNCH_CHECK();
     stage_mark(t, "cand_build_kernel");
+    cand_octant_kernel<<<sm * 8, 256, 0, s>>>(hdr, t->ipts.as<float4>(), t->max_dist * t->max_dist, t->flists.as<unsigned int>(), t->fpool.as<unsigned int>(),
+                                             t->xcount.as<int>(), t->fcell_items.as<int2>(), t->fl1_slots.as<unsigned short>());
+    PFT_LAUNCH_CHECK();
+    stage_mark(t, "cand_octant_kernel");
     cand_build_far_kernel<<<sm * 8, 256, 0, s>>>(hdr, t->cell_start.as<int>(), t->ipts.as<float4>(), t->max_dist * t->max_dist,
-                                                t->flists.as<unsigned short>(), t->xlists.as<unsigned short>(),
+                                                t->flists.as<unsigned int>(), t->xlists.as<unsigned short>(),
                                                 t->xcount.as<int>(), t->ffar_list.as<int>());
     PFT_LAUNCH_CHECK();
     stage_mark(t, "cand_build_far_kernel");
   }
+  const bool lists_built = t->list_max_cells > 0 && t->list_mode && t->nn_mode == PFT_NN_EXACT;
   if (t->nn_mode == PFT_NN_PCL_APPROX) return weight_eval_pcl_approx(t, force_raw);
   WeightArgs a;
-  a.st = st; a.hdr = hdr;
-  a.flists = t->flists.as<unsigned short>(); a.xlists = t->xlists.as<unsigned short>();
+  a.st = st; a.hdr = hdr; a.pts2 = t->ipts2.as<float4>(); a.lists_kernel_ran = lists_built ? 1 : 0;
+  a.flists = t->flists.as<unsigned int>(); a.pool = t->fpool.as<unsigned int>(); a.xlists = t->xlists.as<unsigned short>();
   a.cell_start = t->cell_start.as<int>(); a.pts = t->ipts.as<float4>();
   a.hsv = t->ihsv.as<unsigned int>(); a.table = t->row_table.as<RowEntry>(); a.smem_bytes = t->weight_smem;
   a.model = t->model.as<float4>(); a.model_perm = t->model_perm.as<int>(); a.M = t->M;
@@ -671,6 +703,24 @@ int weight_phase_eval(pft_tracker* t, bool force_raw = false) {
     while ((int)t->ev_w.size() < 2 * (t->n_ev_used + 1)) { cudaEvent_t e; PFT_CUDA_TRY(cudaEventCreate(&e)); t->ev_w.push_back(e); }
     PFT_CUDA_TRY(cudaEventRecord(t->ev_w[2 * t->n_ev_used], s));
   }
+  if (lists_built) {
+    // the product path: candidate lists (returns at once when the index header says they are off for this crop)
+    a.smem_bytes = t->lists_smem;
+    const bool dyn_l = (long long)std::max(1, (t->particle_num > 0 ? t->particle_num : t->n_cap) / t->nranks) * t->chunks >= dyn_per_warp * sm * (kListThreads / 32);
+    if (t->use_hsv) {
+      if (dyn_l) weight_lists_kernel<true, kListThreads, true><<<wgrid, kListThreads, t->lists_smem, s>>>(a);
+      else weight_lists_kernel<true, kListThreads, false><<<wgrid, kListThreads, t->lists_smem, s>>>(a);
+    } else {
+      if (dyn_l) weight_lists_kernel<false, kListThreads, true><<<wgrid, kListThreads, t->lists_smem, s>>>(a);
+      else weight_lists_kernel<false, kListThreads, false><<<wgrid, kListThreads, t->lists_smem, s>>>(a);
+    }
+    PFT_LAUNCH_CHECK();
+    stage_mark(t, "weight_lists_kernel");
+    // (timing: the event pair brackets the kernel that evaluates the lists -- the launch below returns at once then)
+    if (t->timing) { PFT_CUDA_TRY(cudaEventRecord(t->ev_w[2 * t->n_ev_used + 1], s)); t->n_ev_used++; }
+    a.smem_bytes = t->weight_smem;
+  }
+  // row-table search over the grid: crops the lists do not cover (returns at once otherwise)
   if (t->use_hsv) {
     if (dyn) weight_kernel<true, kWeightThreads, true><<<wgrid, kWeightThreads, t->weight_smem, s>>>(a);
     else weight_kernel<true, kWeightThreadsSmall, false><<<wgrid, kWeightThreadsSmall, t->weight_smem, s>>>(a);
@@ -680,7 +730,7 @@ int weight_phase_eval(pft_tracker* t, bool force_raw = false) {
   }
   PFT_LAUNCH_CHECK();
   stage_mark(t, "weight_kernel");
-  if (t->timing) { PFT_CUDA_TRY(cudaEventRecord(t->ev_w[2 * t->n_ev_used + 1], s)); t->n_ev_used++; }
+  if (t->timing && !lists_built) { PFT_CUDA_TRY(cudaEventRecord(t->ev_w[2 * t->n_ev_used + 1], s)); t->n_ev_used++; }
   if (t->nranks > 1 || force_raw) {  // (single rank: normalize_kernel sums the per-chunk partials itself)
     raw_weights_kernel<<<blocks_for(local_cap, 256, sm * 4), 256, 0, s>>>(st, t->partial.as<double>(), t->chunks, t->n_cap, t->raw.as<float>(), local_cap,
                                                                          t->nranks, t->rank, t->peers, t->peer_mode ? 1 : 0);
@@ -881,7 +931,7 @@ void pft_tracker_destroy(pft_tracker* t) {
   if (!t) return;
   cudaSetDevice(t->ctx->device);
   cudaStreamSynchronize(t->run_stream());
-  if (t->graph_exec) cudaGraphExecDestroy(t->graph_exec);
+  for (int g = 0; g < 2; ++g) if (t->graph_exec[g]) cudaGraphExecDestroy(t->graph_exec[g]);
   for (auto e : t->ev_w) cudaEventDestroy(e);
   for (auto e : t->ev_k) cudaEventDestroy(e);
   if (t->ev_c0) cudaEventDestroy(t->ev_c0);
@@ -1061,45 +1111,57 @@ static int compute_one(pft_tracker* t) {
   }
   const bool steady = t->changed && t->graph_enabled && !t->timing && t->debug_nn == 0 && !t->use_cd;  // (the change detector decides on the host)
   if (steady) {
-    // The steady-state frame is a fixed launch sequence over fixed buffers: replay it from a graph.
-    // (Particle double-buffering flips `cur` once per resample; a graph is only valid when a whole
-    // compute() returns `cur` to where it started, i.e. for an even number of resamples.)
-    const bool even = (t->iteration_num % 2) == 0;
-    if (even) {
-      const bool valid = t->graph_exec && t->graph_version == t->config_version && t->graph_scene_pts == (const void*)t->input->d_pts() &&
-                         t->graph_scene_hdr == (const void*)t->input->d_hdr();
-      if (!valid) {
-        if (t->graph_exec) { cudaGraphExecDestroy(t->graph_exec); t->graph_exec = nullptr; }
-        // make sure every lazily sized buffer exists before capture (no allocation inside a capture)
-        if (t->inj_stride == 0) {
-          const int count = t->kld ? t->max_particle_num : t->n_cap;
-          if (t->draw_cap < count) { if ((rc = ensure_draw_buffers(t, 1, count))) return rc; t->draw_cap = count; }
-        }
-        const unsigned long long version = t->config_version;
-        cudaGraph_t graph = nullptr;
-        PFT_CUDA_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-        const unsigned long long launches_before = g_launch_count.load();
-        rc = enqueue_tracking(t);
-        cudaError_t ce = cudaStreamEndCapture(s, &graph);
-        g_launch_count -= g_launch_count.load() - launches_before;  // captured, not launched (other threads' launches keep counting)
-        if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
-        if (ce != cudaSuccess) { set_last_error("graph capture failed: %s", cudaGetErrorString(ce)); cudaGetLastError(); return PFT_ERR_CUDA; }
-        size_t n_nodes = 0;
-        cudaGraphGetNodes(graph, nullptr, &n_nodes);
-        cudaError_t ie = cudaGraphInstantiate(&t->graph_exec, graph, 0);
-        cudaGraphDestroy(graph);
-        if (ie != cudaSuccess) { set_last_error("graph instantiate failed: %s", cudaGetErrorString(ie)); cudaGetLastError(); t->graph_exec = nullptr; return PFT_ERR_CUDA; }
-        t->graph_version = version;
-        t->config_version = version;  // stages may bump the version while sizing buffers; nothing changed since
-        t->graph_scene_pts = t->input->d_pts();
-        t->graph_scene_hdr = t->input->d_hdr();
-        t->graph_nodes = (int)n_nodes;
+    // The steady-state frame is a fixed launch sequence over fixed buffers: replay it from a graph.  The pointers to
+    // the live particle buffer are baked in, and `cur` flips once per resample: one graph per value of `cur` at the
+    // start of the frame (an even iteration count always starts from the same one, an odd count -- PCL's default is
+    // 1 -- alternates between the two).
+    const int g = t->cur;
+    const bool valid = t->graph_exec[g] && t->graph_version[g] == t->config_version && t->graph_scene_pts[g] == (const void*)t->input->d_pts() &&
+                       t->graph_scene_hdr[g] == (const void*)t->input->d_hdr();
+    if (!valid) {
+      if (t->graph_exec[g]) { cudaGraphExecDestroy(t->graph_exec[g]); t->graph_exec[g] = nullptr; }
+      // make sure every lazily sized buffer exists before capture (no allocation inside a capture)
+      if (t->inj_stride == 0) {
+        const int count = t->kld ? t->max_particle_num : t->n_cap;
+        if (t->draw_cap < count) { if ((rc = ensure_draw_buffers(t, 1, count))) return rc; t->draw_cap = count; }
       }
-      PFT_CUDA_TRY(cudaGraphLaunch(t->graph_exec, s));
-      g_launch_count += (unsigned long long)t->graph_nodes;
-      t->graph_replays++;
-      return PFT_OK;
+      const unsigned long long version = t->config_version;
+      const int cur0 = t->cur;
+      const bool changed0 = t->changed;
+      cudaGraph_t graph = nullptr;
+      PFT_CUDA_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+      const unsigned long long launches_before = g_launch_count.load();
+      rc = enqueue_tracking(t);
+      cudaError_t ce = cudaStreamEndCapture(s, &graph);
+      g_launch_count -= g_launch_count.load() - launches_before;  // captured, not launched (other threads' launches keep counting)
+      if (rc || ce != cudaSuccess) {
+        // nothing has executed: the host mirror goes back to where the frame started
+        t->cur = cur0; t->changed = changed0;
+        if (graph) cudaGraphDestroy(graph);
+        if (rc) return rc;
+        set_last_error("graph capture failed: %s", cudaGetErrorString(ce)); cudaGetLastError(); return PFT_ERR_CUDA;
+      }
+      size_t n_nodes = 0;
+      cudaGraphGetNodes(graph, nullptr, &n_nodes);
+      cudaError_t ie = cudaGraphInstantiate(&t->graph_exec[g], graph, 0);
+      cudaGraphDestroy(graph);
+      if (ie != cudaSuccess) {
+        t->cur = cur0; t->changed = changed0;
+        set_last_error("graph instantiate failed: %s", cudaGetErrorString(ie)); cudaGetLastError(); t->graph_exec[g] = nullptr; return PFT_ERR_CUDA;
+      }
+      t->graph_version[g] = version;
+      t->config_version = version;  // stages may bump the version while sizing buffers; nothing changed since
+      t->graph_scene_pts[g] = t->input->d_pts();
+      t->graph_scene_hdr[g] = t->input->d_hdr();
+      t->graph_nodes[g] = (int)n_nodes;
+    } else {
+      // replay: the host mirror follows what the captured stages do (one flip of `cur` per resample)
+      if (t->iteration_num & 1) t->cur ^= 1;
     }
+    PFT_CUDA_TRY(cudaGraphLaunch(t->graph_exec[g], s));
+    g_launch_count += (unsigned long long)t->graph_nodes[g];
+    t->graph_replays++;
+    return PFT_OK;
   }
   rc = enqueue_tracking(t);
   if (rc) return rc;
@@ -1258,7 +1320,8 @@ int pft_tracker_reset(pft_tracker* t) {
   if (!t) { set_last_error("null tracker"); return PFT_ERR_INVALID; }
   // resetTracking: particles are re-drawn around trans_ on the next compute()
   t->has_particles = false;
-  t->changed = false;
+  // (changed_ is left as it is: upstream's resetTracking() only clears the particle vector, so the compute() that
+  // follows re-draws the particles and, when an earlier weight() had set changed_, resamples them in the same frame)
   invalidate_graph(t);
   if (t->st.p) {
     PFT_CUDA_TRY(cudaSetDevice(t->ctx->device));
@@ -1267,8 +1330,8 @@ int pft_tracker_reset(pft_tracker* t) {
     if (t->slot_aabb.p && t->n_cap > 0) {
       std::vector<float> init((size_t)t->n_cap * 6);
       for (int i = 0; i < t->n_cap; ++i) { for (int d = 0; d < 3; ++d) { init[6 * i + d] = FLT_MAX; init[6 * i + 3 + d] = -FLT_MAX; } }
+      PFT_CUDA_TRY(cudaMemcpyAsync(t->slot_aabb.p, init.data(), init.size() * sizeof(float), cudaMemcpyHostToDevice, s));
       PFT_CUDA_TRY(cudaStreamSynchronize(s));
-      PFT_CUDA_TRY(cudaMemcpy(t->slot_aabb.p, init.data(), init.size() * sizeof(float), cudaMemcpyHostToDevice));
     }
   }
   return PFT_OK;
@@ -1589,11 +1652,11 @@ int pft_cloud_broadcast(pft_cloud* cloud, size_t capacity, int root) {
   if (!ctx->comm) { set_last_error("context has no communicator"); return PFT_ERR_COMM; }
   PFT_CUDA_TRY(cudaSetDevice(ctx->device));
   { int jrc = cloud->join_upload(); if (jrc) return jrc; }
+  // every rank posts the SAME count (mismatched counts are undefined in NCCL): the root must hold `capacity` points of
+  // storage -- it is never clamped to what the root happens to have
   if (ctx->rank == root) {
-    if (cloud->capacity < capacity && cloud->capacity > 0) capacity = cloud->capacity;  // never read past the root's buffer
-  }
-  if (ctx->rank != root || cloud->capacity < capacity) {
-    if (ctx->rank == root) { set_last_error("root cloud holds fewer than %zu points of storage", capacity); return PFT_ERR_CAPACITY; }
+    if (cloud->capacity < capacity) { set_last_error("root cloud holds %zu points of storage, the broadcast needs %zu", cloud->capacity, capacity); return PFT_ERR_CAPACITY; }
+  } else {
     int rc = cloud->ensure(capacity);
     if (rc) return rc;
   }
@@ -1708,6 +1771,15 @@ int pft_tracker_peer_detach(pft_tracker* t) {
   return PFT_OK;
 }
 
+#ifdef PFT_TRACE
+// tuning builds only (not declared in pft.h): read and re-arm the stamps (even entries of a pair are minima, see the macros)
+__attribute__((visibility("default"))) int pft_debug_trace(unsigned long long* out64, const unsigned long long* init64) {
+  cudaDeviceSynchronize();
+  if (cudaMemcpyFromSymbol(out64, g_trace, sizeof(unsigned long long) * 64) != cudaSuccess) return -1;
+  cudaMemcpyToSymbol(g_trace, init64, sizeof(unsigned long long) * 64);
+  return 0;
+}
+#endif
 #ifdef PFT_STATS
 // tuning builds only (not declared in pft.h): read and clear the search statistics
 __attribute__((visibility("default"))) int pft_debug_stats(unsigned long long* out16) {

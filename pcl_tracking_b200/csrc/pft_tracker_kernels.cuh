@@ -18,6 +18,16 @@
 
 namespace pft {
 
+// tuning builds only (-DPFT_TRACE): nanosecond stamps of key points of the frame, min / max over the CTAs that pass them
+#ifdef PFT_TRACE
+__device__ unsigned long long g_trace[64];
+__device__ __forceinline__ unsigned long long trace_now() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define PFT_TRACE_MIN(i) do { if ((threadIdx.x & 31) == 0) atomicMin(&g_trace[i], trace_now()); } while (0)
+#define PFT_TRACE_MAX(i) do { if ((threadIdx.x & 31) == 0) atomicMax(&g_trace[i], trace_now()); } while (0)
+#else
+#define PFT_TRACE_MIN(i)
+#define PFT_TRACE_MAX(i)
+#endif
 // ------------------------------------------------------------------ device-resident tracker state
 struct TrackerState {
   int particle_num;       // live particle count (changes on the device in KLD mode)
@@ -391,8 +401,9 @@ __device__ inline void compute_index_header(const float* aabb, float inv_leaf, i
 // that is d away from the surface walks ~pi (d/cell + 1)^2 rows and ~(d + cell)^2 candidates: cell ~ d balances them)
 __global__ void index_begin_kernel(TrackerState* st, IndexHeader* hdr, int* cell_count, float inv_leaf, int base_level,
                                    int max_cells, int list_max_cells, int M, int nranks, int rank, unsigned int* needed_words,
-                                   int* list_counters /* [0] extended lists handed out, [1] needed blocks, [2] cells queued for the far pass */) {
+                                   int* list_counters /* [0] extended lists handed out, [1] needed blocks, [2] cells queued for the far pass, [3] pool groups handed out, [4] cells queued for the octant pass */) {
   __shared__ IndexHeader h;
+  PFT_TRACE_MIN(0);
   if (threadIdx.x == 0) {
     if (base_level < 0) {
       base_level = 1;
@@ -416,7 +427,7 @@ __global__ void index_begin_kernel(TrackerState* st, IndexHeader* hdr, int* cell
   if (h.use_lists) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < h.f_cells; i += gridDim.x * blockDim.x) needed_words[i] = 0u;
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) { list_counters[0] = 0; list_counters[1] = 0; list_counters[2] = 0; st->work_counter = 0u; }
+  if (blockIdx.x == 0 && threadIdx.x == 0) { list_counters[0] = 0; list_counters[1] = 0; list_counters[2] = 0; list_counters[3] = 0; list_counters[4] = 0; st->work_counter = 0u; }
 }
 
 __device__ __forceinline__ bool in_crop(const float4& p, const IndexHeader& h) {
@@ -450,7 +461,7 @@ __global__ void index_count_kernel(const float4* __restrict__ scene, const Cloud
 
 // exclusive prefix of the cell counts -> cell_start; the counters are cleared again (they become the fill cursors)
 __global__ void __launch_bounds__(1024) index_scan_kernel(const IndexHeader* __restrict__ hdr, int* cell_count, int* __restrict__ cell_start,
-                                                          TrackerState* st, float4* __restrict__ pts) {
+                                                          TrackerState* st, float4* __restrict__ pts, float4* __restrict__ pts2) {
   __shared__ int smem[34];
   const int nc = hdr->n_cells;
   if (threadIdx.x == 0) { st->nn_sum_um = 0ull; st->nn_count = 0ull; }  // consumed by index_begin; refilled by the weight kernel
@@ -460,11 +471,13 @@ __global__ void __launch_bounds__(1024) index_scan_kernel(const IndexHeader* __r
     cell_start[nc] = total;
     // slot `total` is a dummy point infinitely far away: candidate lists are padded with it to a multiple of 8 entries
     pts[total] = make_float4(3.0e38f, 3.0e38f, 3.0e38f, __int_as_float(0x7fffffff));
+    pts2[total] = make_float4(3.0e38f, 3.0e38f, 3.0e38f, 0.f);
   }
 }
 
 __global__ void index_scatter_kernel(const float4* __restrict__ scene, const CloudHeader* __restrict__ scene_hdr, const IndexHeader* __restrict__ hdr,
-                                     const int* __restrict__ cell_start, int* cell_count, float4* __restrict__ pts, unsigned int* __restrict__ hsv) {
+                                     const int* __restrict__ cell_start, int* cell_count, float4* __restrict__ pts, unsigned int* __restrict__ hsv,
+                                     float4* __restrict__ pts2 /* {x, y, z, packed HSV}: what weight_lists_kernel stages into shared memory */) {
   __shared__ IndexHeader h;
   if (threadIdx.x == 0) h = *hdr;
   __syncthreads();
@@ -476,7 +489,9 @@ __global__ void index_scatter_kernel(const float4* __restrict__ scene, const Clo
     const int c = cell_of(p, h);
     const int pos = cell_start[c] + atomicAdd(&cell_count[c], 1);
     pts[pos] = make_float4(p.x, p.y, p.z, __int_as_float(i));  // .w = index in the input cloud (tie-break key)
-    hsv[pos] = rgba_to_hsv_packed(__float_as_uint(p.w));
+    const unsigned int packed = rgba_to_hsv_packed(__float_as_uint(p.w));
+    hsv[pos] = packed;
+    pts2[pos] = make_float4(p.x, p.y, p.z, __uint_as_float(packed));
   }
 }
 
@@ -608,17 +623,30 @@ __device__ __forceinline__ NNResult nn_search(const CS* __restrict__ cs, const f
 }
 
 // ---- candidate lists: the exact nearest neighbour as a table lookup.
-// For every cell c of the fine lattice (edge = resolution) the build stores the slots of ALL points that can be the
-// nearest neighbour of SOME query inside c: with p0 the point nearest to the centre of c and U = maxdist(c, p0), any
-// query q in c has |q - NN(q)| <= |q - p0| <= U, hence mindist(c, NN(q)) <= U; the list is {p : mindist(c, p) <= U}
-// (ties included), cut at maximum_distance_.  A query then scans one short list instead of walking the grid.  Cells
-// whose list would not fit kListK entries are marked and their queries use the row-table search.
-constexpr int kListK = 128;                        // 16-bit words of a cell's record: [0] = header (entry count or a code below), [1..] entries
+// For every cell c of the fine lattice (edge = resolution) the build finds the slots of ALL points that can be the
+// nearest neighbour of SOME query inside c: with p0 the point minimising maxdist(c, .) and U = maxdist(c, p0), any
+// query q in c has |q - NN(q)| <= |q - p0| <= U, hence mindist(c, NN(q)) <= U, and q lies on NN(q)'s side of the
+// bisector plane of (NN(q), p0) (can_win); the list is every point passing both tests (ties included), cut at
+// maximum_distance_.  The same two tests are then applied to each of the cell's eight OCTANTS (edge = resolution / 2),
+// which is what a query reads: one 32-byte record = header + seven entries, enough for 99.7 % of the queries (mean
+// length 3.1); an octant that still holds more than seven points after the p0 tests is pruned pairwise (a point that
+// some other candidate beats everywhere in the octant can never win) and what remains beyond seven goes to groups of
+// eight taken from a pool.  Every sub-list is in ascending order of the input index, so that the lookup
+// resolves distance ties by position (strict <: the first of equals wins = the lower index, the parity contract).
+//
+// Octant record = 8 words of 32 bits (one 32-byte sector, read by ONE 256-bit load):
+//   word 0      header: 0..7 = entry count | count (8..71) + (g << 8) = entries beyond the seventh are in pool groups
+//               g, g+1, .. (eight entries each) | kListExtended = word 1 holds the index of an extended list (cells far
+//               from the surface: up to kListKX slots, not sorted), word 2 its length | kListOverflow = no list (the
+//               query is answered by brute force)
+//   words 1..7  entries as BYTE offsets of the points in the staged array (slot << 4), padded with the dummy slot
+constexpr int kL1Cap = 64;                         // a cell's own list is split into octants up to this length; longer ones become extended lists
 constexpr int kListKX = 1024;                      // entries of an extended list (cells far from the surface)
 constexpr int kListXCells = 8192;                  // extended lists available per build
-constexpr unsigned short kListOverflow = 0xffffu;  // no list: use the row-table search
-constexpr unsigned short kListExtended = 0xfffeu;  // record[1..2] = index of the extended list, record[3] = its length
-// list entries are 16-bit slots (+ the dummy slot n_cropped): larger crops use the row-table search only
+constexpr int kPoolGroups = 1 << 18;               // groups of eight entries for octant lists longer than seven
+constexpr unsigned int kListOverflow = 0xffffffffu;  // no list
+constexpr unsigned int kListExtended = 0xfffffffeu;  // extended list
+// extended-list entries are 16-bit slots: larger crops use the row-table search only
 __device__ __forceinline__ bool lists_on(const IndexHeader& h) { return h.use_lists && h.n_cropped < 65535; }
 
 __device__ __forceinline__ float box_mindist2(const float* lo, const float* hi, const float4& p) {
@@ -632,7 +660,10 @@ __device__ __forceinline__ float box_maxdist2(const float* lo, const float* hi, 
   return (dx * dx + dy * dy) + dz * dz;
 }
 
-// marks the fine cells that this rank's queries fall into (the lists of the others are never read).  No global
+// marks the fine cells that this rank's queries fall into (the lists of the others are never read).
+// COUNT (small query sets): needed[c] = number of queries of the cell, one L2 reduction per query -- cells with fewer
+// than kCoarseBelow queries get one list for the whole cell instead of eight octant lists (half of the cells hold a few
+// per cent of the queries: those of the outlying particles).  Otherwise (large sets: every cell is busy) no global
 // atomics and no global loads: a cell is flagged with a plain store (duplicates are harmless); cand_collect_kernel
 // then queues the blocks.  (Reading a flag back here costs a round trip between the two L2 partitions whenever
 // another SM has just stored to the line: measured 2.5x slower.)
@@ -641,6 +672,8 @@ __device__ __forceinline__ float box_maxdist2(const float* lo, const float* hi, 
 // remembers the cells it has flagged in a bitmap of the fine grid in shared memory (f_cells bits, dynamic): every
 // block stores every cell at most once.
 constexpr int kMarkUnroll = 4;
+constexpr unsigned int kCoarseBelow = 24u;  // queries of a cell below which its list is not split into octants
+template <bool COUNT>
 __global__ void __launch_bounds__(256) cand_mark_kernel(const TrackerState* __restrict__ st, const IndexHeader* __restrict__ hdr, const float4* __restrict__ model, int M,
                                                         const float* __restrict__ mats, unsigned int* __restrict__ needed, int nranks, int rank) {
   extern __shared__ unsigned int s_bits[];  // (f_cells + 31) / 32 words
@@ -648,9 +681,11 @@ __global__ void __launch_bounds__(256) cand_mark_kernel(const TrackerState* __re
   if (threadIdx.x == 0) h = *hdr;
   __syncthreads();
   if (!h.valid || !lists_on(h)) return;
-  const int words = (h.f_cells + 31) >> 5;
-  for (int i = threadIdx.x; i < words; i += blockDim.x) s_bits[i] = 0u;
-  __syncthreads();
+  if (!COUNT) {
+    const int words = (h.f_cells + 31) >> 5;
+    for (int i = threadIdx.x; i < words; i += blockDim.x) s_bits[i] = 0u;
+    __syncthreads();
+  }
   const int n = st->particle_num;
   const int n_local = n > rank ? (n - rank + nranks - 1) / nranks : 0;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, wpb = blockDim.x >> 5;
@@ -680,9 +715,13 @@ __global__ void __launch_bounds__(256) cand_mark_kernel(const TrackerState* __re
                     iz = (int)fminf(fmaxf(floorf(qz * inv_leaf), -big), big) - oz;
           if ((unsigned)ix < (unsigned)fdx && (unsigned)iy < (unsigned)fdy && (unsigned)iz < (unsigned)fdz) {
             const int c = (iz * fdy + iy) * fdx + ix;
-            const unsigned int bit = 1u << (c & 31);
-            if (!(s_bits[c >> 5] & bit)) {  // (cheap pre-test; the atomic decides)
-              if (!(atomicOr(&s_bits[c >> 5], bit) & bit)) needed[c] = 1u;
+            if (COUNT) {
+              atomicAdd(&needed[c], 1u);  // (no return value: a reduction at the L2, nothing comes back)
+            } else {
+              const unsigned int bit = 1u << (c & 31);
+              if (!(s_bits[c >> 5] & bit)) {  // (cheap pre-test; the atomic decides)
+                if (!(atomicOr(&s_bits[c >> 5], bit) & bit)) needed[c] = kCoarseBelow;  // (a flag: at least this many queries)
+              }
             }
           }
         }
@@ -769,6 +808,24 @@ __device__ __forceinline__ bool can_win(const float4& p, const float4& p0, const
   return fmin <= 1.0e-6f * (pn + p0n) + 1.0e-9f;
 }
 
+// index (in records of 8 words) of octant (ox, oy, oz) of fine cell (fx, fy, fz): the octants form one dense lattice of
+// edge resolution / 2 over the crop box, x fastest -- what a query computes directly from floor(q * 2 / resolution)
+__device__ __forceinline__ size_t octant_record(const IndexHeader& h, int fx, int fy, int fz, int o) {
+  return ((size_t)(2 * fz + (o >> 2)) * (size_t)(2 * h.f_dim[1]) + (size_t)(2 * fy + ((o >> 1) & 1))) * (size_t)(2 * h.f_dim[0]) + (size_t)(2 * fx + (o & 1));
+}
+
+// All eight octant records of a cell get the same code (lanes 0..7 of the calling warp):
+// kListOverflow / 0 (empty list) / kListExtended with the index and length of the extended list.
+__device__ __forceinline__ void write_octant_codes(const IndexHeader& h, unsigned int* __restrict__ flists, int fx, int fy, int fz, unsigned int code, int xi, int n) {
+  const int lane = threadIdx.x & 31;
+  if (lane < 8) {
+    const unsigned int dd = (unsigned int)h.n_cropped << 4;
+    uint4* r = reinterpret_cast<uint4*>(flists + octant_record(h, fx, fy, fz, lane) * 8);
+    r[0] = make_uint4(code, code == kListExtended ? (unsigned int)xi : dd, code == kListExtended ? (unsigned int)n : dd, dd);
+    r[1] = make_uint4(dd, dd, dd, dd);
+  }
+}
+
 // The points of a set of rows, flattened across a whole thread block (the block-wide sibling of warp_points_of_rows):
 // warp 0 fetches the slot ranges of 32 rows and scans their lengths, then all threads take consecutive points of the
 // concatenation.  Every thread of the block must call it.
@@ -805,7 +862,7 @@ __device__ __forceinline__ void block_points_of_rows(int nrows, int* s_pref /* [
 // kListKX) and a single warp would walk ~1000 points on its own while the rest of the GPU waits.
 __device__ __forceinline__ void build_cell_direct(const IndexHeader& h, const int* __restrict__ cs, const float4* __restrict__ pts, int cell,
                                                   float leaf, float margin, float r_max,
-                                                  unsigned short* __restrict__ flists, unsigned short* __restrict__ xlists,
+                                                  unsigned int* __restrict__ flists, unsigned short* __restrict__ xlists,
                                                   int* __restrict__ list_counters, int* pref, int* start, int* s_cnt, float* s_m2, int* s_ms, int* s_xi,
                                                   unsigned short* s_list /* [kListKX] shared */) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -824,7 +881,6 @@ __device__ __forceinline__ void build_cell_direct(const IndexHeader& h, const in
     a = max((int)floorf(((lo[d] - r) * h.inv_leaf) * h.level_scale) - h.origin[d], 0);
     b = min((int)floorf(((hi[d] + r) * h.inv_leaf) * h.level_scale) - h.origin[d], h.dim[d] - 1);
   };
-  unsigned short* list = flists + (size_t)cell * kListK;
   // ---- (1) U: probe the box dilated by a growing radius until it holds a point
   float U2 = 3.0e38f;
   int p0_slot = -1;
@@ -857,9 +913,9 @@ __device__ __forceinline__ void build_cell_direct(const IndexHeader& h, const in
     if (pr > r_max) { no_match = true; break; }  // nothing within pr (> maximum_distance_) of the box: no query of the cell can match
   }
   if (U2 >= 3.0e38f) {
-    // provably no point within maximum_distance_ of any query of the cell (empty list), or the probe gave up (the
-    // queries of this cell use the row-table search)
-    if (threadIdx.x < 8) list[threadIdx.x] = threadIdx.x ? (unsigned short)h.n_cropped : (no_match ? (unsigned short)0 : kListOverflow);
+    // provably no point within maximum_distance_ of any query of the cell (empty lists), or the probe gave up (the
+    // queries of this cell are answered by brute force)
+    if (threadIdx.x < 32) write_octant_codes(h, flists, fx, fy, fz, no_match ? 0u : kListOverflow, 0, 0);
     return;
   }
   U2 = fminf(U2, r_max * r_max);
@@ -903,25 +959,16 @@ __device__ __forceinline__ void build_cell_direct(const IndexHeader& h, const in
         }
       });
   const int n = *s_cnt;
-  unsigned short* dst = list + 1;
-  int off = 1;
-  if (n > kListK - 1) {
-    // does not fit a regular record: an extended list (cells far from the surface), or the row-table search
-    if (threadIdx.x == 0) *s_xi = n <= kListKX ? atomicAdd(&list_counters[0], 1) : -1;
-    __syncthreads();
-    const int xi = *s_xi;
-    if (xi < 0 || xi >= kListXCells) { if (threadIdx.x == 0) list[0] = kListOverflow; return; }
-    dst = xlists + (size_t)xi * kListKX;
-    off = 0;
-    PFT_STAT(11, threadIdx.x == 0 ? 1 : 0);
-    if (threadIdx.x == 0) { list[1] = (unsigned short)(xi & 0xffff); list[2] = (unsigned short)(xi >> 16); list[3] = (unsigned short)n; }
-  }
+  // cells far from the surface: one extended list (not sorted; the weight kernel scans it with a whole warp and
+  // resolves ties by input index), shared by the eight octants
+  if (threadIdx.x == 0) *s_xi = n <= kListKX ? atomicAdd(&list_counters[0], 1) : -1;
+  __syncthreads();
+  const int xi = *s_xi;
+  if (xi < 0 || xi >= kListXCells) { if (threadIdx.x < 32) write_octant_codes(h, flists, fx, fy, fz, kListOverflow, 0, 0); return; }
+  unsigned short* dst = xlists + (size_t)xi * kListKX;
+  PFT_STAT(11, threadIdx.x == 0 ? 1 : 0);
   for (int t = threadIdx.x; t < n; t += blockDim.x) dst[t] = s_list[t];
-  // pad to whole 16-byte groups with the dummy slot (the lookup reads whole groups unconditionally; a regular record
-  // starts with its header word)
-  const int n8 = ((n + off + 7) & ~7) - off;
-  if (n + (int)threadIdx.x < n8) dst[n + threadIdx.x] = (unsigned short)h.n_cropped;
-  if (threadIdx.x == 0) list[0] = off ? (unsigned short)n : kListExtended;
+  if (threadIdx.x < 32) write_octant_codes(h, flists, fx, fy, fz, kListExtended, xi, n);
   PFT_STAT(15, threadIdx.x == 0 ? 1 : 0);
 }
 
@@ -930,10 +977,11 @@ __device__ __forceinline__ void build_cell_direct(const IndexHeader& h, const in
 // of the block filters that superset with its own bound and bisector test.
 __global__ void __launch_bounds__(256) cand_build_kernel(const IndexHeader* __restrict__ hdr, const int* __restrict__ cs,
                                                          const float4* __restrict__ pts, double max_d2,
-                                                         unsigned short* __restrict__ flists,
+                                                         unsigned int* __restrict__ flists,
                                                          const unsigned int* __restrict__ needed, const int* __restrict__ needed_list,
                                                          unsigned short* __restrict__ xlists, int* __restrict__ list_counters,
-                                                         int* __restrict__ far_list) {
+                                                         int* __restrict__ far_list, int2* __restrict__ cell_items,
+                                                         unsigned short* __restrict__ l1_slots) {
   __shared__ IndexHeader h;
   __shared__ int s_cnt[8];
   __shared__ int s_pref[8][33], s_start[8][32];
@@ -966,13 +1014,13 @@ __global__ void __launch_bounds__(256) cand_build_kernel(const IndexHeader* __re
     lo[1] = (float)(h.f_origin[1] + 2 * by) * leaf - margin; hi[1] = (float)(h.f_origin[1] + 2 * by + 2) * leaf + margin;
     lo[2] = (float)(h.f_origin[2] + 2 * bz) * leaf - margin; hi[2] = (float)(h.f_origin[2] + 2 * bz + 2) * leaf + margin;
     // every fine cell of the block gets `value` (used when the whole block is decided at once)
-    auto set_all = [&](unsigned short value) {
-      if (lane < 8) {
-        const int fx = 2 * bx + (lane & 1), fy = 2 * by + ((lane >> 1) & 1), fz = 2 * bz + (lane >> 2);
+    auto set_all = [&](unsigned int value) {
+      for (int sub = 0; sub < 8; ++sub) {
+        const int fx = 2 * bx + (sub & 1), fy = 2 * by + ((sub >> 1) & 1), fz = 2 * bz + (sub >> 2);
         if (fx < fdx && fy < fdy && fz < fdz) {
           const int c = (fz * fdy + fy) * fdx + fx;
-          // header + a first group of dummy slots (value 0 = empty list: the lookup returns before reading them)
-          if (needed[c]) { uint4 r; r.x = (unsigned int)value | ((unsigned int)h.n_cropped << 16); r.y = r.z = r.w = (unsigned int)h.n_cropped * 0x10001u; *reinterpret_cast<uint4*>(flists + (size_t)c * kListK) = r; }
+          // every octant: header + dummy slots (value 0 = empty list: nothing within maximum_distance_)
+          if (needed[c]) write_octant_codes(h, flists, fx, fy, fz, value, 0, 0);
         }
       }
     };
@@ -1011,7 +1059,7 @@ __global__ void __launch_bounds__(256) cand_build_kernel(const IndexHeader* __re
     if (U2 >= 3.0e38f) {
       // provably no point within maximum_distance_ of any query of the block (empty lists), or the probe gave up
       // (the queries of the block use the row-table search)
-      set_all(no_match ? (unsigned short)0 : kListOverflow);
+      set_all(no_match ? 0u : kListOverflow);
       continue;
     }
     U2 = fminf(U2, r_max * r_max);
@@ -1076,6 +1124,8 @@ __global__ void __launch_bounds__(256) cand_build_kernel(const IndexHeader* __re
       }
       sub_mask = __ballot_sync(kFull, mine);
     }
+    int my_item = 0, my_xyz = 0;  // lane `sub` remembers the cell it has to queue
+    bool my_valid = false;
     for (int sub = 0; sub < 8; ++sub) {
       if (!((sub_mask >> sub) & 1u)) continue;
       const int fx = 2 * bx + (sub & 1), fy = 2 * by + ((sub >> 1) & 1), fz = 2 * bz + (sub >> 2);
@@ -1098,8 +1148,8 @@ __global__ void __launch_bounds__(256) cand_build_kernel(const IndexHeader* __re
       }
       const float Uf2 = fminf(m2 * 1.00002f, r_max * r_max);
       const float4 pf = spt[mi];
-      // count, choose the destination, write (ballot compaction: the order of a list is the order of the superset).
-      // The keep test is evaluated once; its ballots (ns <= kSuperCap = 8 x 32) stay in registers for the write pass.
+      // the cell's own list L1 (every point that can be the nearest neighbour of some query of the 1 cm cell): the keep
+      // test is evaluated once; its ballots (ns <= kSuperCap = 8 x 32) give the compaction offsets
       int n = 0;
       unsigned int keep_bal[kSuperCap / 32];
 #pragma unroll
@@ -1112,41 +1162,246 @@ __global__ void __launch_bounds__(256) cand_build_kernel(const IndexHeader* __re
           n += __popc(keep_bal[q]);
         }
       }
-      unsigned short* list = flists + (size_t)cell * kListK;
-      unsigned short* dst = list + 1;
-      const bool extended = n > kListK - 1;
-      if (extended) {
+      if (n > kL1Cap) {
+        // long list (far from the surface): an extended list shared by the eight octants, scanned by a whole warp per query
         int xi = -1;
         if (n <= kListKX) {
           if (lane == 0) xi = atomicAdd(&list_counters[0], 1);
           xi = __shfl_sync(kFull, xi, 0);
         }
-        if (xi < 0 || xi >= kListXCells) { if (lane == 0) list[0] = kListOverflow; continue; }
-        dst = xlists + (size_t)xi * kListKX;
-        if (lane == 0) { list[1] = (unsigned short)(xi & 0xffff); list[2] = (unsigned short)(xi >> 16); list[3] = (unsigned short)n; }
-      }
-      int w = 0;
+        if (xi < 0 || xi >= kListXCells) { write_octant_codes(h, flists, fx, fy, fz, kListOverflow, 0, 0); continue; }
+        unsigned short* dst = xlists + (size_t)xi * kListKX;
+        int w = 0;
 #pragma unroll
-      for (int q = 0; q < kSuperCap / 32; ++q) {
-        const unsigned int bal = keep_bal[q];
-        if ((bal >> lane) & 1u) dst[w + __popc(bal & ((1u << lane) - 1u))] = sslot[q * 32 + lane];
-        w += __popc(bal);
+        for (int q = 0; q < kSuperCap / 32; ++q) {
+          const unsigned int bal = keep_bal[q];
+          if ((bal >> lane) & 1u) dst[w + __popc(bal & ((1u << lane) - 1u))] = sslot[q * 32 + lane];
+          w += __popc(bal);
+        }
+        write_octant_codes(h, flists, fx, fy, fz, kListExtended, xi, n);
+        PFT_STAT(15, lane == 0 ? 1 : 0);
+        continue;
       }
-      // pad to whole 16-byte groups with the dummy slot (the lookup reads whole groups unconditionally; a regular record
-      // starts with its header word)
-      const int off = extended ? 0 : 1;
-      const int n8 = ((n + off + 7) & ~7) - off;
-      if (n + lane < n8) dst[n + lane] = (unsigned short)h.n_cropped;
-      if (lane == 0) list[0] = extended ? kListExtended : (unsigned short)n;
+      // ---- (4) hand the cell's list to cand_octant_kernel (slots in superset order; the octant pass sorts them)
+      {
+        unsigned short* dst = l1_slots + (size_t)cell * kL1Cap;
+        int w = 0;
+#pragma unroll
+        for (int q = 0; q < kSuperCap / 32; ++q) {
+          const unsigned int bal = keep_bal[q];
+          if ((bal >> lane) & 1u) dst[w + __popc(bal & ((1u << lane) - 1u))] = sslot[q * 32 + lane];
+          w += __popc(bal);
+        }
+      }
+      if (lane == sub) {
+        // item = cell | list length << 24 | (few queries: one list for the whole cell) << 31, and the cell's coordinates
+        my_item = cell | (n << 24) | (needed[cell] < kCoarseBelow ? (int)0x80000000 : 0);
+        my_xyz = (fx < 1024 && fy < 1024 && fz < 1024) ? (fx | (fy << 10) | (fz << 20)) : -1;
+        my_valid = true;
+      }
       PFT_STAT(15, lane == 0 ? 1 : 0);
     }
+    // queue the cells of this block: one atomic per block
+    {
+      const unsigned int bal = __ballot_sync(kFull, my_valid);
+      if (bal) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&list_counters[4], __popc(bal));
+        base = __shfl_sync(kFull, base, 0);
+        if (my_valid) cell_items[base + __popc(bal & ((1u << lane) - 1u))] = make_int2(my_item, my_xyz);
+      }
+    }
   }
+}
+
+// Third pass of the build: the records of every cell queued by cand_build_kernel, one warp per cell.
+// The cell's list is sorted by input index (the lookup resolves distance ties by position: the first of equals wins).
+// Cells with few queries (`coarse`) get that list in each of their eight octant records.  Otherwise G lanes work on one
+// octant (G = the power of two >= list length, 32 / G octants per pass; lane % G = entry): p0 = the entry minimising
+// maxdist(octant, .), keep = mindist <= U and can-win against p0 (both from the entry's offset to the octant centre:
+// the octant is a cube); when an octant keeps more than seven, every octant of the pass is pruned pairwise (an entry
+// that another kept entry beats everywhere in the octant never wins); ballot compaction keeps the order.  Entries
+// beyond the seventh go to groups of eight taken from a pool (the header carries the first group).  The eight records
+// are assembled in shared memory and written out together.
+__global__ void __launch_bounds__(256) cand_octant_kernel(const IndexHeader* __restrict__ hdr, const float4* __restrict__ pts, double max_d2,
+                                                          unsigned int* __restrict__ flists, unsigned int* __restrict__ pool,
+                                                          int* __restrict__ list_counters, const int2* __restrict__ cell_items,
+                                                          const unsigned short* __restrict__ l1_slots) {
+  __shared__ IndexHeader h;
+  __shared__ float4 s_pt[8][kL1Cap];
+  __shared__ unsigned int s_off[8][kL1Cap];
+  __shared__ __align__(16) unsigned int s_rec[8][64];
+  if (threadIdx.x == 0) h = *hdr;
+  __syncthreads();
+  if (!h.valid || !lists_on(h)) return;
+  const int n_items = list_counters[4];
+  const float leaf = 1.0f / h.inv_leaf;
+  const float margin = 1.0e-5f + 4.0e-6f * leaf * (float)(abs(h.f_origin[0]) + abs(h.f_origin[1]) + abs(h.f_origin[2]) + h.f_dim[0] + h.f_dim[1] + h.f_dim[2]);
+  const float r_max = max_d2 >= 1.0e30 ? 1.0e15f : (float)sqrt(max_d2) * 1.00001f;
+  const float rmax2 = r_max * r_max;
+  const float quarter = 0.25f * leaf;
+  // half extent of an octant box: the octant itself, the rounding of q * inv_leaf near its faces (margin) and of the
+  // centre computed below
+  const float oh = quarter + margin + 1.0e-6f;
+  const int fdx = h.f_dim[0], fdy = h.f_dim[1];
+  const unsigned int d2x = 2u * (unsigned int)h.f_dim[0], d2y = 2u * (unsigned int)h.f_dim[1];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  const unsigned int lt = (1u << lane) - 1u;
+  const unsigned int dummy = (unsigned int)h.n_cropped << 4;
+  float4* spt = s_pt[wib];
+  unsigned int* soff = s_off[wib];
+  unsigned int* srec = s_rec[wib];
+  // can p (offset x, y, z from the octant centre) be at least as near as the competitor (offset cx, cy, cz) somewhere in
+  // the octant?  min over the cube of |q-p|^2 - |q-c|^2 = (|p|^2 - |c|^2) - 2 oh (|px-cx| + |py-cy| + |pz-cz|)
+  auto can_win_c = [&](float x, float y, float z, float cx, float cy, float cz) {
+    const float pn = (x * x + y * y) + z * z, cn = (cx * cx + cy * cy) + cz * cz;
+    const float fmin = (pn - cn) - 2.0f * (oh * ((fabsf(x - cx) + fabsf(y - cy)) + fabsf(z - cz)));
+    return fmin <= 1.0e-6f * (pn + cn) + 1.0e-9f;
+  };
+  auto maxd2 = [&](float x, float y, float z) { const float u = fabsf(x) + oh, v = fabsf(y) + oh, w = fabsf(z) + oh; return (u * u + v * v) + w * w; };
+  auto mind2 = [&](float x, float y, float z) {
+    const float u = fmaxf(fabsf(x) - oh, 0.f), v = fmaxf(fabsf(y) - oh, 0.f), w = fmaxf(fabsf(z) - oh, 0.f);
+    return (u * u + v * v) + w * w;
+  };
+  for (int it = warp; it < n_items; it += nwarps) {
+    const int2 item = cell_items[it];
+    const int cell = item.x & 0xffffff, n = (item.x >> 24) & 0x7f;
+    const bool coarse = item.x < 0;
+    int fx, fy, fz;
+    if (item.y >= 0) { fx = item.y & 1023; fy = (item.y >> 10) & 1023; fz = item.y >> 20; }
+    else { fz = cell / (fdx * fdy); const int r2 = cell - fz * fdx * fdy; fy = r2 / fdx; fx = r2 - fy * fdx; }
+    const bool two = n > 32;
+    // ---- the list in ascending order of the input index (rank = how many keys are smaller; keys are distinct)
+    {
+      const unsigned short* src = l1_slots + (size_t)cell * kL1Cap;
+      const int s0 = lane < n ? (int)src[lane] : 0;
+      const float4 p0 = pts[s0];
+      const int k0 = lane < n ? __float_as_int(p0.w) : 0x7fffffff;
+      int r0 = 0;
+      if (!two) {
+        for (int c = 0; c < n; ++c) r0 += __shfl_sync(kFull, k0, c) < k0 ? 1 : 0;
+      } else {
+        const int s1 = lane + 32 < n ? (int)src[lane + 32] : 0;
+        const float4 p1 = pts[s1];
+        const int k1 = lane + 32 < n ? __float_as_int(p1.w) : 0x7fffffff;
+        int r1 = 0;
+        for (int c = 0; c < 32; ++c) { const int k = __shfl_sync(kFull, k0, c); r0 += k < k0 ? 1 : 0; r1 += k < k1 ? 1 : 0; }
+        for (int c = 32; c < n; ++c) { const int k = __shfl_sync(kFull, k1, c - 32); r0 += k < k0 ? 1 : 0; r1 += k < k1 ? 1 : 0; }
+        if (lane + 32 < n) { spt[r1] = p1; soff[r1] = (unsigned int)s1 << 4; }
+      }
+      if (lane < n) { spt[r0] = p0; soff[r0] = (unsigned int)s0 << 4; }
+    }
+    srec[lane] = dummy; srec[lane + 32] = dummy;
+    __syncwarp();
+    // records of octant o: word index of its first word (the octants form one dense lattice, x fastest)
+    auto rec_word = [&](int o) { return (((unsigned int)(2 * fz + (o >> 2)) * d2y + (unsigned int)(2 * fy + ((o >> 1) & 1))) * d2x + (unsigned int)(2 * fx + (o & 1))) * 8u; };
+    if (coarse) {
+      // few queries: the cell's own list in every octant record (entries beyond the seventh in ONE run of pool groups)
+      unsigned int hw = (unsigned int)n;
+      int pg = 0;
+      if (n > 7) {
+        const int need = (n - 7 + 7) >> 3;
+        if (lane == 0) pg = atomicAdd(&list_counters[3], need);
+        pg = __shfl_sync(kFull, pg, 0);
+        if (pg + need > kPoolGroups) hw = kListOverflow;
+        else {
+          hw |= (unsigned int)pg << 8;
+          for (int t = 7 + lane; t < 7 + need * 8; t += 32) pool[(size_t)pg * 8 + (size_t)(t - 7)] = t < n ? soff[t] : dummy;
+        }
+      }
+      // lane l: word (l & 7) of octants (l >> 3) and 4 + (l >> 3)
+      const int w = lane & 7;
+      const unsigned int val = w == 0 ? hw : ((hw != kListOverflow && w - 1 < n) ? soff[w - 1] : dummy);
+      flists[rec_word(lane >> 3) + (unsigned int)w] = val;
+      flists[rec_word(4 + (lane >> 3)) + (unsigned int)w] = val;
+      __syncwarp();
+      continue;
+    }
+    // ---- octants: G lanes each
+    const int G = n > 16 ? 32 : (n > 8 ? 16 : (n > 4 ? 8 : 4));
+    const int P = 32 / G;
+    const int e = lane & (G - 1), gbase = lane & ~(G - 1), sub = lane / G;
+    const unsigned int gmask = G == 32 ? kFull : (((1u << G) - 1u) << gbase);
+    const bool va = e < n, vb = two && e + 32 < n;
+    const float4 far_pt = make_float4(3.0e38f, 3.0e38f, 3.0e38f, 0.f);
+    const float4 pa = va ? spt[e] : far_pt, pb = vb ? spt[e + 32] : far_pt;
+    const unsigned int sa = soff[va ? e : 0], sb = soff[vb ? e + 32 : 0];
+    const int cx4 = 4 * (h.f_origin[0] + fx) + 1, cy4 = 4 * (h.f_origin[1] + fy) + 1, cz4 = 4 * (h.f_origin[2] + fz) + 1;
+#pragma unroll 1
+    for (int ps = 0; ps < 8 / P; ++ps) {
+      const int o = ps * P + sub;
+      const float ocx = (float)(cx4 + 2 * (o & 1)) * quarter, ocy = (float)(cy4 + 2 * ((o >> 1) & 1)) * quarter, ocz = (float)(cz4 + 2 * (o >> 2)) * quarter;
+      const float ax = pa.x - ocx, ay = pa.y - ocy, az = pa.z - ocz;
+      const float bx = pb.x - ocx, by = pb.y - ocy, bz = pb.z - ocz;
+      // (non-negative floats order like their bit patterns) minimum over the group: xor butterfly
+      const unsigned int mda = va ? __float_as_uint(maxd2(ax, ay, az)) : 0x7f7fffffu;
+      const unsigned int mdb = vb ? __float_as_uint(maxd2(bx, by, bz)) : 0x7f7fffffu;
+      unsigned int mb = min(mda, mdb);
+      for (int x = G >> 1; x > 0; x >>= 1) mb = min(mb, __shfl_xor_sync(kFull, mb, x));
+      const unsigned int who_a = __ballot_sync(kFull, mda == mb) & gmask, who_b = __ballot_sync(kFull, mdb == mb) & gmask;
+      // p0 relative to the octant centre
+      const int src = who_a ? __ffs(who_a) - 1 : __ffs(who_b) - 1;
+      const float qx = __shfl_sync(kFull, who_a ? ax : bx, src), qy = __shfl_sync(kFull, who_a ? ay : by, src), qz = __shfl_sync(kFull, who_a ? az : bz, src);
+      const float U2 = fminf(__uint_as_float(mb) * 1.00002f, rmax2);
+      bool ka = va && mind2(ax, ay, az) <= U2 && can_win_c(ax, ay, az, qx, qy, qz);
+      bool kb = vb && mind2(bx, by, bz) <= U2 && can_win_c(bx, by, bz, qx, qy, qz);
+      unsigned int ba = __ballot_sync(kFull, ka) & gmask, bb = two ? (__ballot_sync(kFull, kb) & gmask) : 0u;
+      int cnt = __popc(ba) + __popc(bb);
+      if (__any_sync(kFull, cnt > 7)) {
+        // pairwise pruning against every entry the p0 tests kept (valid for every octant: it only shortens lists)
+        for (int c = 0; c < G; ++c) {
+          const float cx = __shfl_sync(kFull, ax, gbase + c), cy = __shfl_sync(kFull, ay, gbase + c), cz = __shfl_sync(kFull, az, gbase + c);
+          if ((ba >> (gbase + c)) & 1u) {
+            if (ka && !can_win_c(ax, ay, az, cx, cy, cz)) ka = false;
+            if (kb && !can_win_c(bx, by, bz, cx, cy, cz)) kb = false;
+          }
+          if (two) {
+            const float dx = __shfl_sync(kFull, bx, c), dy = __shfl_sync(kFull, by, c), dz = __shfl_sync(kFull, bz, c);
+            if ((bb >> c) & 1u) {
+              if (ka && !can_win_c(ax, ay, az, dx, dy, dz)) ka = false;
+              if (kb && !can_win_c(bx, by, bz, dx, dy, dz)) kb = false;
+            }
+          }
+        }
+        ba = __ballot_sync(kFull, ka) & gmask;
+        bb = two ? (__ballot_sync(kFull, kb) & gmask) : 0u;
+        cnt = __popc(ba) + __popc(bb);
+      }
+      PFT_STAT(0, e == 0 && cnt > 7 ? 1 : 0); PFT_STAT(1, e == 0 ? cnt : 0); PFT_STAT(2, e == 0 ? 1 : 0);
+      unsigned int hw = (unsigned int)cnt;
+      int pg = 0;
+      if (cnt > 7) {  // (uniform within the group)
+        const int need = (cnt - 7 + 7) >> 3;
+        if (e == 0) pg = atomicAdd(&list_counters[3], need);
+        pg = __shfl_sync(gmask, pg, gbase);
+        if (pg + need > kPoolGroups) hw = kListOverflow;
+        else {
+          hw |= (unsigned int)pg << 8;
+          // pad the last group with the dummy slot (the lookup reads whole groups)
+          const int tail = need * 8 - (cnt - 7);
+          if (e < tail) pool[(size_t)pg * 8 + (size_t)(cnt - 7 + e)] = dummy;
+        }
+      }
+      if (hw != kListOverflow) {
+        if (ka) { const int pos = __popc(ba & lt); if (pos < 7) srec[o * 8 + 1 + pos] = sa; else pool[(size_t)pg * 8 + (size_t)(pos - 7)] = sa; }
+        if (kb) { const int pos = __popc(ba) + __popc(bb & lt); if (pos < 7) srec[o * 8 + 1 + pos] = sb; else pool[(size_t)pg * 8 + (size_t)(pos - 7)] = sb; }
+      }
+      if (e == 0) srec[o * 8] = hw;
+    }
+    __syncwarp();
+    // lane l: word (l & 7) of octant (l >> 3), then of octant 4 + (l >> 3)
+    flists[rec_word(lane >> 3) + (unsigned int)(lane & 7)] = srec[lane];
+    flists[rec_word(4 + (lane >> 3)) + (unsigned int)(lane & 7)] = srec[lane + 32];
+    __syncwarp();
+  }
+  PFT_TRACE_MAX(1);
 }
 
 // second pass of the build: the cells queued by cand_build_kernel, one thread block each
 __global__ void __launch_bounds__(256) cand_build_far_kernel(const IndexHeader* __restrict__ hdr, const int* __restrict__ cs,
                                                              const float4* __restrict__ pts, double max_d2,
-                                                             unsigned short* __restrict__ flists, unsigned short* __restrict__ xlists,
+                                                             unsigned int* __restrict__ flists, unsigned short* __restrict__ xlists,
                                                              int* __restrict__ list_counters, const int* __restrict__ far_list) {
   __shared__ IndexHeader h;
   __shared__ int s_cnt, s_xi;
@@ -1164,61 +1419,7 @@ __global__ void __launch_bounds__(256) cand_build_far_kernel(const IndexHeader* 
     build_cell_direct(h, cs, pts, far_list[idx], leaf, margin, r_max, flists, xlists, list_counters, s_pref, s_start, &s_cnt, s_m2, s_ms, &s_xi, s_list);
     __syncthreads();
   }
-}
-
-// Query through the candidate lists; returns false when the row-table search has to be used instead.  One 16-byte
-// load brings the header of the cell's record and its first seven entries; longer lists continue in groups of eight.
-__device__ __forceinline__ bool nn_lookup(const IndexHeader& h, const unsigned short* __restrict__ flists,
-                                          const unsigned short* __restrict__ xlists, const float4* __restrict__ pts, float qx, float qy, float qz,
-                                          float lim2, NNResult& best) {
-  const float fx = floorf(qx * h.inv_leaf), fy = floorf(qy * h.inv_leaf), fz = floorf(qz * h.inv_leaf);
-  const float big = 1.0e9f;
-  const int ix = (int)fminf(fmaxf(fx, -big), big) - h.f_origin[0], iy = (int)fminf(fmaxf(fy, -big), big) - h.f_origin[1],
-            iz = (int)fminf(fmaxf(fz, -big), big) - h.f_origin[2];
-  if ((unsigned)ix >= (unsigned)h.f_dim[0] || (unsigned)iy >= (unsigned)h.f_dim[1] || (unsigned)iz >= (unsigned)h.f_dim[2]) return false;
-  const int cell = (iz * h.f_dim[1] + iy) * h.f_dim[0] + ix;
-  const uint4* l4 = reinterpret_cast<const uint4*>(flists + (size_t)cell * kListK);
-  uint4 v = l4[0];
-  int cnt = (int)(v.x & 0xffffu);
-  PFT_STAT(12, 1);
-  best = nn_none(lim2);
-  if (cnt >= (int)kListExtended) {
-    if (cnt == (int)kListOverflow) { PFT_STAT(13, 1); return false; }
-    // extended list (cells far from the surface): groups of eight from its own storage
-    const int xi = (int)(v.x >> 16) | ((int)(v.y & 0xffffu) << 16);
-    cnt = (int)(v.y >> 16);
-    PFT_STAT(14, cnt); PFT_STAT(3, 1);
-    const uint4* x4 = reinterpret_cast<const uint4*>(xlists + (size_t)xi * kListKX);
-    const int groups = (cnt + 7) >> 3;
-    for (int g = 0; g < groups; ++g) {
-      const uint4 cur = x4[g];
-      nn_eval(pts, (int)(cur.x & 0xffffu), qx, qy, qz, best); nn_eval(pts, (int)(cur.x >> 16), qx, qy, qz, best);
-      nn_eval(pts, (int)(cur.y & 0xffffu), qx, qy, qz, best); nn_eval(pts, (int)(cur.y >> 16), qx, qy, qz, best);
-      nn_eval(pts, (int)(cur.z & 0xffffu), qx, qy, qz, best); nn_eval(pts, (int)(cur.z >> 16), qx, qy, qz, best);
-      nn_eval(pts, (int)(cur.w & 0xffffu), qx, qy, qz, best); nn_eval(pts, (int)(cur.w >> 16), qx, qy, qz, best);
-    }
-    return true;
-  }
-  PFT_STAT(14, cnt);
-  PFT_STAT(0, cnt > 15 ? 1 : 0); PFT_STAT(1, cnt > 31 ? 1 : 0); PFT_STAT(2, cnt > 63 ? 1 : 0);
-  PFT_STAT(5, cnt == 0 ? 1 : 0);
-  if (cnt == 0) return true;
-  const int groups = (cnt + 8) >> 3;  // the header word + cnt entries, padded with the dummy slot to whole groups of 8
-  uint4 nxt = v;
-  if (groups > 1) nxt = l4[1];  // next group in flight while this one is evaluated
-  nn_eval(pts, (int)(v.x >> 16), qx, qy, qz, best);
-  nn_eval(pts, (int)(v.y & 0xffffu), qx, qy, qz, best); nn_eval(pts, (int)(v.y >> 16), qx, qy, qz, best);
-  nn_eval(pts, (int)(v.z & 0xffffu), qx, qy, qz, best); nn_eval(pts, (int)(v.z >> 16), qx, qy, qz, best);
-  nn_eval(pts, (int)(v.w & 0xffffu), qx, qy, qz, best); nn_eval(pts, (int)(v.w >> 16), qx, qy, qz, best);
-  for (int g = 1; g < groups; ++g) {
-    const uint4 cur = nxt;
-    if (g + 1 < groups) nxt = l4[g + 1];
-    nn_eval(pts, (int)(cur.x & 0xffffu), qx, qy, qz, best); nn_eval(pts, (int)(cur.x >> 16), qx, qy, qz, best);
-    nn_eval(pts, (int)(cur.y & 0xffffu), qx, qy, qz, best); nn_eval(pts, (int)(cur.y >> 16), qx, qy, qz, best);
-    nn_eval(pts, (int)(cur.z & 0xffffu), qx, qy, qz, best); nn_eval(pts, (int)(cur.z >> 16), qx, qy, qz, best);
-    nn_eval(pts, (int)(cur.w & 0xffffu), qx, qy, qz, best); nn_eval(pts, (int)(cur.w >> 16), qx, qy, qz, best);
-  }
-  return true;
+  PFT_TRACE_MAX(2);
 }
 
 struct WeightArgs {
@@ -1226,9 +1427,11 @@ struct WeightArgs {
   const IndexHeader* hdr;
   const int* cell_start;      // [n_cells + 1]
   const float4* pts;          // {x, y, z, input index} in cell order
+  const float4* pts2;         // {x, y, z, packed HSV} in cell order (what weight_lists_kernel stages)
   const unsigned int* hsv;    // packed HSV of every slot
   const RowEntry* table;      // kRows entries sorted by lb2
-  const unsigned short* flists;  // candidate lists (see cand_build_kernel): one record of kListK 16-bit words per fine cell
+  const unsigned int* flists;    // candidate lists (see cand_build_kernel): one record of 8 words per octant of the fine lattice
+  const unsigned int* pool;      // groups of eight entries for octant lists longer than seven
   const unsigned short* xlists;  // extended lists
   const float4* model;        // {x,y,z,hsv} in tile order
   const int* model_perm;      // tile order -> order of the reference cloud as given
@@ -1240,6 +1443,7 @@ struct WeightArgs {
   CoherenceParams co;
   int dbg_k; int* dbg_idx; float* dbg_d2;
   int smem_bytes;             // dynamic shared memory available for staging the index
+  int lists_kernel_ran;       // weight_lists_kernel precedes weight_kernel in the stream: whichever does not apply returns at once
 };
 
 // One (particle, model chunk) item by one warp: transform, nearest neighbour, coherence, warp reduction.
@@ -1253,7 +1457,6 @@ __device__ __forceinline__ void weight_items(const WeightArgs& a, const IndexHea
   const int lane = threadIdx.x & 31;
   // maximum_distance_^2 as the float just above it: every point with (double)d2 < max_d2 has d2 <= lim2
   const float lim2 = a.co.max_d2 >= 3.0e38 ? FLT_MAX : __double2float_ru(a.co.max_d2);
-  const bool use_lists = lists_on(h);
   // Large particle sets (many items per warp): items are handed out dynamically, one atomic per item with the next
   // one requested before the current one is worked on -- query cost varies with the list lengths (measured -4 % on
   // 100k particles).  Small sets (~4 items per warp): static interleaved assignment; there the atomic's latency costs
@@ -1286,7 +1489,7 @@ __device__ __forceinline__ void weight_items(const WeightArgs& a, const IndexHea
       xform(m, mp.x, mp.y, mp.z, qx, qy, qz);
       NNResult nn = nn_none(lim2);
       if (h.n_cropped > 0) {
-        if (!(use_lists && nn_lookup(h, a.flists, a.xlists, pts, qx, qy, qz, lim2, nn))) nn = nn_search<CS>(cs, pts, h, table, qx, qy, qz, lim2);
+        nn = nn_search<CS>(cs, pts, h, table, qx, qy, qz, lim2);
       }
       if (i < a.dbg_k) {
         const size_t o = (size_t)i * a.M + a.model_perm[j];
@@ -1318,7 +1521,7 @@ __device__ __forceinline__ void weight_items(const WeightArgs& a, const IndexHea
           const float diff2 = h_diff + s_diff + v_diff;
           den *= 1.0 + a.co.hsv_w * (double)diff2;
         }
-        val += 1.0 / den;
+        val += rcp_f64(den);
       }
     }
     val = warp_sum(val);
@@ -1339,7 +1542,11 @@ __global__ void __launch_bounds__(THREADS, 1) weight_kernel(const WeightArgs a) 
   __shared__ IndexHeader h;
   __shared__ float lut_h[256], lut_s[256];
   __shared__ RowEntry s_table[kRows];
+  PFT_TRACE_MIN(9);
   if (threadIdx.x == 0) h = *a.hdr;
+  __syncthreads();
+  PFT_TRACE_MAX(10);
+  if (a.lists_kernel_ran && lists_on(h)) return;  // this weight() was evaluated by weight_lists_kernel
   for (int i = threadIdx.x; i < kRows; i += blockDim.x) s_table[i] = a.table[i];
   if (USE_HSV) {
     for (int i = threadIdx.x; i < 256; i += blockDim.x) { lut_h[i] = (float)i / 180.0f; lut_s[i] = (float)i / 255.0f; }
@@ -1358,7 +1565,7 @@ __global__ void __launch_bounds__(THREADS, 1) weight_kernel(const WeightArgs a) 
   const bool hsv_staged = USE_HSV && pts_staged && need_pts + need_hsv <= (long long)a.smem_bytes;
 #endif
   const long long used = need_pts + (hsv_staged ? need_hsv : 0);
-  const bool cs_staged = pts_staged && !lists_on(h) && n_pts < 65536 && used + need_cs <= (long long)a.smem_bytes;
+  const bool cs_staged = pts_staged && n_pts < 65536 && used + need_cs <= (long long)a.smem_bytes;
   uint4* s_pts = dyn_smem;
   unsigned int* s_hsv = reinterpret_cast<unsigned int*>(dyn_smem + n_pts);
   if (pts_staged) {
@@ -1381,6 +1588,268 @@ __global__ void __launch_bounds__(THREADS, 1) weight_kernel(const WeightArgs a) 
     else weight_items<USE_HSV, DYN, int>(a, h, a.cell_start, reinterpret_cast<const float4*>(s_pts), a.hsv, s_table, lut_h, lut_s);
   } else {
     weight_items<USE_HSV, DYN, int>(a, h, a.cell_start, a.pts, a.hsv, s_table, lut_h, lut_s);
+  }
+}
+
+// ------------------------------------------------------------------ K3, list path: weight_lists_kernel
+// The product path of weight() whenever the candidate lists are on.  Persistent, one CTA per SM; the indexed points
+// {x, y, z, packed HSV} travel into shared memory as ONE bulk asynchronous copy (cp.async.bulk + mbarrier, issued by
+// one thread while the others set up), each warp takes (particle, model chunk) items, a lane = one model point:
+//   transform -> octant of the fine lattice -> ONE 16-byte load (header + seven slots) -> seven candidates from shared
+//   memory, straight-line (dx, dy as packed FADD2 / FMUL2; the list is in input-index order, so strict < resolves
+//   ties) -> coherence in fp64 -> warp-shuffle sum.
+// The few queries whose octant has no short list (extended lists far from the surface, cells without a list) are
+// answered one at a time by the whole warp (nn_slow_warp), bit-identical to the brute-force search.
+struct SlowNN { float d2; int slot; };
+
+// One query by a whole warp: every lane scans a 32nd of the candidates (an extended list, or every indexed point),
+// lexicographic (distance, input index) minimum across the lanes.  Returns the winner to all lanes (slot -1: none
+// nearer than lim2).
+__device__ __noinline__ SlowNN nn_slow_warp(const float4* __restrict__ pts /* {x,y,z,input index}, global */, const unsigned short* __restrict__ xl,
+                                            int n, float qx, float qy, float qz, float lim2) {
+  const int lane = threadIdx.x & 31;
+  float bd = lim2;
+  int bo = 0x7fffffff, bs = -1;
+  for (int t = lane; t < n; t += 32) {
+    const int slot = xl ? (int)xl[t] : t;
+    const float4 p = pts[slot];
+    const float dx = qx - p.x, dy = qy - p.y, dz = qz - p.z;
+    const float d2 = (dx * dx + dy * dy) + dz * dz;
+    const int orig = __float_as_int(p.w);
+    if (d2 < bd || (d2 == bd && bs >= 0 && orig < bo)) { bd = d2; bo = orig; bs = slot; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float od = __shfl_xor_sync(kFull, bd, o);
+    const int oo = __shfl_xor_sync(kFull, bo, o), os = __shfl_xor_sync(kFull, bs, o);
+    if (os >= 0 && (od < bd || (od == bd && (bs < 0 || oo < bo)))) { bd = od; bo = oo; bs = os; }
+  }
+  return SlowNN{bd, bs};
+}
+
+#ifndef PFT_LIST_PIPE
+#define PFT_LIST_PIPE 1
+#endif
+// one 32-byte record (header + seven entries, or a pool group of eight entries) as ONE 256-bit load
+struct Rec8 { unsigned int w[8]; };
+__device__ __forceinline__ Rec8 load_rec8(const unsigned int* __restrict__ p) {
+  Rec8 r;
+  asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]), "=r"(r.w[7])
+               : "l"(p));
+  return r;
+}
+
+// one candidate: OFF = byte offset of the point in the staged array.  d2 follows the arithmetic contract
+// ((dx*dx + dy*dy) + dz*dz, every operation rounded on its own); dx, dy as one packed FADD2 / FMUL2 pair.
+#define PFT_CAND(OFF)                                                                          \
+  {                                                                                            \
+    const unsigned int of_ = (OFF);                                                            \
+    const float4 p_ = *reinterpret_cast<const float4*>(sbase + of_);                           \
+    const float2 d_ = sub2_rn(qxy, make_float2(p_.x, p_.y));                                   \
+    const float dz_ = q.z - p_.z;                                                              \
+    const float2 dd_ = mul2_rn(d_, d_);                                                        \
+    const float d2_ = (dd_.x + dd_.y) + dz_ * dz_;                                             \
+    if (d2_ < best) { best = d2_; boff = of_; }                                                \
+  }
+
+// a query on its way: the transformed model point, its packed HSV, the octant record
+struct ListQuery { float x, y, z; unsigned int hsv; Rec8 r; };
+
+template <bool USE_HSV, bool DYN>
+__device__ __forceinline__ void weight_list_items(const WeightArgs& a, const IndexHeader& h, const unsigned char* __restrict__ sbase,
+                                                  const float* __restrict__ lut_h, const float* __restrict__ lut_s) {
+  const int n = a.st->particle_num;
+  const int n_local = n > a.rank_id ? (n - a.rank_id + a.nranks - 1) / a.nranks : 0;
+  const int items = n_local * a.chunks;
+  const int lane = threadIdx.x & 31;
+  // maximum_distance_^2 as the float just above it: (double)d2 < max_d2  <=>  d2 < lim2
+  const float lim2 = a.co.max_d2 >= 3.0e38 ? FLT_MAX : __double2float_ru(a.co.max_d2);
+  const float inv2 = h.inv_leaf * 2.0f;  // octant lattice: floor(q * 2 / resolution); (q * inv_leaf) * 2 == q * (inv_leaf * 2) exactly
+  const int o2x = 2 * h.f_origin[0], o2y = 2 * h.f_origin[1], o2z = 2 * h.f_origin[2];
+  const unsigned int d2x = 2u * (unsigned int)h.f_dim[0], d2y = 2u * (unsigned int)h.f_dim[1], d2z = 2u * (unsigned int)h.f_dim[2];
+  const bool any_pts = h.n_cropped > 0;
+  const bool use_v = a.co.v_w != 0.f;
+  const int total_warps = gridDim.x * (blockDim.x >> 5);
+  unsigned long long sum_um64 = 0ull;  // distance statistics: per lane, flushed once at the end
+  unsigned int matched = 0;
+  int next = (threadIdx.x >> 5) * gridDim.x + blockIdx.x;  // static: blocks interleaved so that consecutive items spread over the SMs
+  if (DYN) {
+    if (lane == 0) next = (int)atomicAdd(&a.st->work_counter, 1u);
+    next = __shfl_sync(kFull, next, 0);
+  }
+  while (next < items) {
+    const int item = next;
+#ifdef PFT_TRACE
+    const unsigned long long t_item0 = trace_now();
+#endif
+    if (!DYN) next = item + total_warps;
+    else if (lane == 0) next = (int)atomicAdd(&a.st->work_counter, 1u);
+    const int il = item / a.chunks, c = item - il * a.chunks;
+    const int i = a.rank_id + il * a.nranks;
+    float m[12];
+    {
+      const float4* mp = reinterpret_cast<const float4*>(a.mats) + (size_t)i * 3;
+      const float4 r0 = mp[0], r1 = mp[1], r2 = mp[2];
+      m[0] = r0.x; m[1] = r0.y; m[2] = r0.z; m[3] = r0.w; m[4] = r1.x; m[5] = r1.y; m[6] = r1.z; m[7] = r1.w;
+      m[8] = r2.x; m[9] = r2.y; m[10] = r2.z; m[11] = r2.w;
+    }
+    const int j0 = c * a.chunk_len, j1 = min(a.M, j0 + a.chunk_len);
+    // transform + octant + record load of the model point of round jb (inactive lanes repeat the last point)
+    auto fetch = [&](int jb) {
+      ListQuery q;
+      const float4 mp = a.model[min(jb + lane, j1 - 1)];
+      xform(m, mp.x, mp.y, mp.z, q.x, q.y, q.z);
+      q.hsv = __float_as_uint(mp.w);
+      // (cvt.rmi saturates: a far-away or non-finite query fails the range test)
+      const int ix = __float2int_rd(q.x * inv2) - o2x, iy = __float2int_rd(q.y * inv2) - o2y, iz = __float2int_rd(q.z * inv2) - o2z;
+      q.r.w[0] = kListOverflow;
+      if ((unsigned int)ix < d2x && (unsigned int)iy < d2y && (unsigned int)iz < d2z)
+        q.r = load_rec8(a.flists + (size_t)(((unsigned int)iz * d2y + (unsigned int)iy) * d2x + (unsigned int)ix) * 8);
+      return q;
+    };
+    double val = 0.0;
+    unsigned int sum_um = 0;  // (<= chunk_len / 32 x 1e8 per lane: no overflow for chunks below ~1300 points)
+    auto eval = [&](const ListQuery& q, int jb) {
+      const bool act = jb + lane < j1;
+      const float2 qxy = make_float2(q.x, q.y);
+      float best = lim2;
+      unsigned int boff = 0xffffffffu;
+      const unsigned int hw = q.r.w[0];
+      if (hw < kListExtended) {
+        PFT_CAND(q.r.w[1]) PFT_CAND(q.r.w[2]) PFT_CAND(q.r.w[3]) PFT_CAND(q.r.w[4]) PFT_CAND(q.r.w[5]) PFT_CAND(q.r.w[6]) PFT_CAND(q.r.w[7])
+        const int cnt = (int)(hw & 0xffu);
+        PFT_STAT(12, act ? 1 : 0); PFT_STAT(5, act ? cnt : 0);
+        if (cnt > 7) {
+          PFT_STAT(3, act ? 1 : 0); PFT_STAT(6, act ? cnt : 0);
+          const unsigned int* pg = a.pool + (size_t)(hw >> 8) * 8;
+          for (int g = 0; g < ((cnt - 7 + 7) >> 3); ++g) {
+            const Rec8 w = load_rec8(pg + g * 8);
+            PFT_CAND(w.w[0]) PFT_CAND(w.w[1]) PFT_CAND(w.w[2]) PFT_CAND(w.w[3]) PFT_CAND(w.w[4]) PFT_CAND(w.w[5]) PFT_CAND(w.w[6]) PFT_CAND(w.w[7])
+          }
+        }
+      }
+      // queries without a short list: one at a time, by the whole warp
+      unsigned int slow = __ballot_sync(kFull, act && any_pts && hw >= kListExtended);
+      while (slow) {
+        const int src = __ffs(slow) - 1;
+        slow &= slow - 1u;
+        const float sx = __shfl_sync(kFull, q.x, src), sy = __shfl_sync(kFull, q.y, src), sz = __shfl_sync(kFull, q.z, src);
+        const unsigned int shw = __shfl_sync(kFull, hw, src), s1 = __shfl_sync(kFull, q.r.w[1], src), s2 = __shfl_sync(kFull, q.r.w[2], src);
+        const unsigned short* xl = nullptr;
+        int nx = h.n_cropped;
+        if (shw == kListExtended) { xl = a.xlists + (size_t)s1 * kListKX; nx = (int)s2; }
+        PFT_STAT(13, lane == 0 ? 1 : 0); PFT_STAT(14, lane == 0 ? nx : 0); PFT_STAT(4, lane == 0 && !xl ? 1 : 0);
+        const SlowNN r = nn_slow_warp(a.pts, xl, nx, sx, sy, sz, lim2);
+        if (lane == src && r.slot >= 0) { best = r.d2; boff = (unsigned int)r.slot << 4; }
+      }
+      const bool hit = act && boff != 0xffffffffu;
+      if (i < a.dbg_k && act) {
+        const size_t o = (size_t)i * a.M + a.model_perm[min(jb + lane, j1 - 1)];
+        a.dbg_idx[o] = hit ? __float_as_int(a.pts[boff >> 4].w) : -1;
+        a.dbg_d2[o] = hit ? best : FLT_MAX;
+      }
+      if (hit) {
+        // DistanceCoherence x HSVColorCoherence: 1/(1+d^2 w_d) * 1/(1+w_h diff) evaluated as one fp64 reciprocal of
+        // the product of the denominators (differs from the product of reciprocals by ~1 ulp of fp64)
+        double den = 1.0;
+        const float df = sqrtf(best);
+        sum_um += (unsigned int)fminf(df * 1.0e6f, 1.0e8f);
+        ++matched;
+        if (a.co.use_dist) {
+          const double d = (double)df;
+          den = 1.0 + d * d * a.co.dist_w;
+        }
+        if (USE_HSV) {
+          const unsigned int sb = q.hsv, tb = *reinterpret_cast<const unsigned int*>(sbase + boff + 12);
+          const float sh = lut_h[sb & 0xff], ss = lut_s[(sb >> 8) & 0xff];
+          const float th = lut_h[tb & 0xff], ts = lut_s[(tb >> 8) & 0xff];
+          const float hd = fabsf(sh - th);
+          float hd2;
+          if (sh < th) hd2 = fabsf(1.0f + sh - th); else hd2 = fabsf(1.0f + th - sh);
+          float h_diff;
+          if (hd < hd2) h_diff = a.co.h_w * hd * hd; else h_diff = a.co.h_w * hd2 * hd2;
+          const float s_diff = a.co.s_w * (ss - ts) * (ss - ts);
+          float v_diff = 0.f;  // (v_w == 0, the upstream default: the term is +0 whatever the values)
+          if (use_v) { const float sv = lut_s[(sb >> 16) & 0xff], tv = lut_s[(tb >> 16) & 0xff]; v_diff = a.co.v_w * (sv - tv) * (sv - tv); }
+          const float diff2 = h_diff + s_diff + v_diff;
+          den *= 1.0 + a.co.hsv_w * (double)diff2;
+        }
+        val += rcp_f64(den);
+      }
+    };
+#if PFT_LIST_PIPE
+    // two rounds in flight (ping-pong, so that no query is copied between registers): the record of the next round
+    // is on its way while the current one is evaluated
+    ListQuery qa = fetch(j0), qb;
+    for (int jb = j0; jb < j1; jb += 64) {
+      const bool second = jb + 32 < j1;
+      if (second) qb = fetch(jb + 32);
+      eval(qa, jb);
+      if (second) {
+        if (jb + 64 < j1) qa = fetch(jb + 64);
+        eval(qb, jb + 32);
+      }
+    }
+#else
+    for (int jb = j0; jb < j1; jb += 32) eval(fetch(jb), jb);
+#endif
+    val = warp_sum(val);
+    sum_um64 += sum_um;
+    if (lane == 0) a.partial[(size_t)c * a.n_max + i] = val;
+    if (DYN) next = __shfl_sync(kFull, next, 0);
+#ifdef PFT_TRACE
+    if (lane == 0) {
+      const unsigned long long dt = trace_now() - t_item0;
+      const unsigned long long old = atomicMax(&g_trace[12], dt);
+      if (dt > old) g_trace[13] = (unsigned long long)item;
+      if (dt > 8000ull) atomicAdd(&g_trace[14], 1ull);
+      if (dt > 16000ull) atomicAdd(&g_trace[15], 1ull);
+      atomicAdd(&g_trace[16], dt);
+      atomicAdd(&g_trace[17], 1ull);
+    }
+#endif
+  }
+  // nearest-neighbour distance statistics (they steer the cell size of the next index build): integer sums, so the
+  // totals do not depend on the order the atomics land in
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum_um64 += __shfl_xor_sync(kFull, sum_um64, o);
+  matched = (unsigned int)warp_sum((int)matched);
+  if (lane == 0 && matched) { atomicAdd(&a.st->nn_sum_um, sum_um64); atomicAdd(&a.st->nn_count, (unsigned long long)matched); }
+}
+#undef PFT_CAND
+
+template <bool USE_HSV, int THREADS, bool DYN>
+__global__ void __launch_bounds__(THREADS, 1) weight_lists_kernel(const WeightArgs a) {
+  extern __shared__ uint4 dyn_smem[];
+  __shared__ IndexHeader h;
+  __shared__ float lut_h[256], lut_s[256];
+  __shared__ __align__(8) unsigned long long s_bar;
+  PFT_TRACE_MIN(3); PFT_TRACE_MAX(4);
+  if (threadIdx.x == 0) h = *a.hdr;
+  __syncthreads();
+  if (!lists_on(h)) return;  // weight_kernel (row-table search) evaluates this weight()
+  PFT_TRACE_MAX(5);
+  const int n_pts = h.n_cropped + 1;  // + the dummy point that pads the lists
+  const bool staged = 16ll * n_pts <= (long long)a.smem_bytes;
+  if (staged && threadIdx.x == 0) {
+    mbar_init(&s_bar, 1);
+    const uint32_t bytes = 16u * (uint32_t)n_pts;
+    mbar_expect_tx(&s_bar, bytes);
+    for (uint32_t off = 0; off < bytes; off += 65536u)
+      bulk_g2s(reinterpret_cast<unsigned char*>(dyn_smem) + off, reinterpret_cast<const unsigned char*>(a.pts2) + off, min(65536u, bytes - off), &s_bar);
+  }
+  if (USE_HSV) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) { lut_h[i] = (float)i / 180.0f; lut_s[i] = (float)i / 255.0f; }
+  }
+  __syncthreads();  // (the barrier is initialised, the tables are written)
+  if (staged) {
+    mbar_wait(&s_bar, 0);
+    PFT_TRACE_MAX(6);
+    weight_list_items<USE_HSV, DYN>(a, h, reinterpret_cast<const unsigned char*>(dyn_smem), lut_h, lut_s);
+    PFT_TRACE_MIN(7); PFT_TRACE_MAX(8);
+  } else {
+    weight_list_items<USE_HSV, DYN>(a, h, reinterpret_cast<const unsigned char*>(a.pts2), lut_h, lut_s);
   }
 }
 
@@ -1697,6 +2166,7 @@ normalize_kernel(TrackerState* st, DevParticle* parts, const float* raw, double 
                  int chunks, int n_max, float* raw_out, int fuse_update /* compute(): update() follows every weight(), do it in the same launch */) {
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned int crank = cluster.block_rank();
+  PFT_TRACE_MIN(11);
   __shared__ double red[32];
   __shared__ double s_part[3];  // this CTA's partial min, max, sum (read by the other CTAs of the cluster)
   __shared__ double s_upd[6];   // fused update(): this CTA's partial weighted state
