@@ -245,9 +245,16 @@ constexpr int kClusterMinParticles = 4096;  // above this capacity the O(N) repl
 constexpr int kWeightThreads = PFT_WEIGHT_THREADS;  // CTA size of the persistent weight kernel (one CTA per SM), large particle sets
 constexpr int kWeightThreadsSmall = 768;            // small sets (static item split): 85 registers per thread instead of 64 (measured -6 %)
 #ifndef PFT_LIST_THREADS
-#define PFT_LIST_THREADS 512
+#define PFT_LIST_THREADS 640
 #endif
-constexpr int kListThreads = PFT_LIST_THREADS;      // CTA size of weight_lists_kernel (one CTA per SM)
+#ifndef PFT_LIST_THREADS_BIG
+#define PFT_LIST_THREADS_BIG 896
+#endif
+// CTA size of weight_lists_kernel (one CTA per SM): 96 registers per thread, no spills; large query sets (measured on 100 000
+// particles: -4 %) trade 72 registers and a few spilled values for 28 warps per SM
+constexpr int kListThreads = PFT_LIST_THREADS;
+constexpr int kListThreadsBig = PFT_LIST_THREADS_BIG;
+constexpr long long kListBigQueries = 48ll << 20;   // (particle, model point) pairs per weight() from which the large variant runs
 
 // Row table of the nearest-neighbour search: the (dy,dz) offsets within kRT cells sorted by the lower bound
 // gap(dy)^2 + gap(dz)^2 of their distance (gap(d) = max(|d|-1, 0)), nearer rows first.
@@ -287,6 +294,8 @@ int upload_row_table(pft_tracker* t) {
   PFT_CUDA_TRY(cudaFuncSetAttribute(weight_lists_kernel<true, kListThreads, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_l));
   PFT_CUDA_TRY(cudaFuncSetAttribute(weight_lists_kernel<false, kListThreads, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_l));
   PFT_CUDA_TRY(cudaFuncSetAttribute(weight_lists_kernel<false, kListThreads, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_l));
+  PFT_CUDA_TRY(cudaFuncSetAttribute(weight_lists_kernel<true, kListThreadsBig, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_l));
+  PFT_CUDA_TRY(cudaFuncSetAttribute(weight_lists_kernel<false, kListThreadsBig, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_l));
   t->lists_smem = dyn_l;
   if (t->list_max_cells / 8 + 64 > max_optin - 2048) t->list_max_cells = (max_optin - 4096) * 8;  // the mark kernel keeps one bit per fine cell in shared memory
   PFT_CUDA_TRY(cudaFuncSetAttribute(cand_mark_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, t->list_max_cells / 8 + 64));
@@ -325,7 +334,7 @@ int ensure_particle_buffers(pft_tracker* t) {
       // blocks of 2x2x2 fine cells: at most ceil(d/2)^3 <= (d+1)^3/8, bounded generously by cells/2 + 4096
       if ((rc = t->fneeded_list.reserve(((size_t)t->list_max_cells / 2 + 4096) * sizeof(int)))) return rc;
       if ((rc = t->ffar_list.reserve(((size_t)t->list_max_cells + 16) * sizeof(int)))) return rc;
-      if ((rc = t->xlists.reserve((size_t)kListXCells * kListKX * sizeof(unsigned short)))) return rc;
+      if ((rc = t->xlists.reserve((size_t)kListXCells * kListKX * sizeof(unsigned int)))) return rc;
       if ((rc = t->xcount.reserve(64))) return rc;
     }
   }
@@ -667,25 +676,26 @@ int weight_phase_eval(pft_tracker* t, bool force_raw = false) {
     PFT_LAUNCH_CHECK();
     stage_mark(t, "cand_collect_kernel");
     cand_build_kernel<<<sm * 8, 256, 0, s>>>(hdr, t->cell_start.as<int>(), t->ipts.as<float4>(), t->max_dist * t->max_dist, t->flists.as<unsigned int>(),
-                                            t->fneeded.as<unsigned int>(), t->fneeded_list.as<int>(), t->xlists.as<unsigned short>(),
-                                            t->xcount.as<int>(), t->ffar_list.as<int>(), t->fcell_items.as<int2>(), t->fl1_slots.as<unsigned short>());
+                                            t->fneeded.as<unsigned int>(), t->fneeded_list.as<int>(), t->xcount.as<int>(), t->ffar_list.as<int>(),
+                                            t->fcell_items.as<int2>(), t->fl1_slots.as<unsigned short>());
     PFT_LAUNCH_CHECK();
     stage_mark(t, "cand_build_kernel");
+    // cells far from the surface (long lists): pairwise pruning, one thread block each; most of them join the octant pass
+    cand_build_far_kernel<<<sm * 4, 256, 0, s>>>(hdr, t->cell_start.as<int>(), t->ipts.as<float4>(), t->max_dist * t->max_dist,
+                                                t->flists.as<unsigned int>(), t->xlists.as<unsigned int>(), t->xcount.as<int>(), t->ffar_list.as<int>(),
+                                                t->fneeded.as<unsigned int>(), t->fcell_items.as<int2>(), t->fl1_slots.as<unsigned short>());
+    PFT_LAUNCH_CHECK();
+    stage_mark(t, "cand_build_far_kernel");
     cand_octant_kernel<<<sm * 8, 256, 0, s>>>(hdr, t->ipts.as<float4>(), t->max_dist * t->max_dist, t->flists.as<unsigned int>(), t->fpool.as<unsigned int>(),
                                              t->xcount.as<int>(), t->fcell_items.as<int2>(), t->fl1_slots.as<unsigned short>());
     PFT_LAUNCH_CHECK();
     stage_mark(t, "cand_octant_kernel");
-    cand_build_far_kernel<<<sm * 8, 256, 0, s>>>(hdr, t->cell_start.as<int>(), t->ipts.as<float4>(), t->max_dist * t->max_dist,
-                                                t->flists.as<unsigned int>(), t->xlists.as<unsigned short>(),
-                                                t->xcount.as<int>(), t->ffar_list.as<int>());
-    PFT_LAUNCH_CHECK();
-    stage_mark(t, "cand_build_far_kernel");
   }
   const bool lists_built = t->list_max_cells > 0 && t->list_mode && t->nn_mode == PFT_NN_EXACT;
   if (t->nn_mode == PFT_NN_PCL_APPROX) return weight_eval_pcl_approx(t, force_raw);
   WeightArgs a;
   a.st = st; a.hdr = hdr; a.pts2 = t->ipts2.as<float4>(); a.lists_kernel_ran = lists_built ? 1 : 0;
-  a.flists = t->flists.as<unsigned int>(); a.pool = t->fpool.as<unsigned int>(); a.xlists = t->xlists.as<unsigned short>();
+  a.flists = t->flists.as<unsigned int>(); a.pool = t->fpool.as<unsigned int>(); a.xlists = t->xlists.as<unsigned int>();
   a.cell_start = t->cell_start.as<int>(); a.pts = t->ipts.as<float4>();
   a.hsv = t->ihsv.as<unsigned int>(); a.table = t->row_table.as<RowEntry>(); a.smem_bytes = t->weight_smem;
   a.model = t->model.as<float4>(); a.model_perm = t->model_perm.as<int>(); a.M = t->M;
@@ -706,8 +716,12 @@ int weight_phase_eval(pft_tracker* t, bool force_raw = false) {
   if (lists_built) {
     // the product path: candidate lists (returns at once when the index header says they are off for this crop)
     a.smem_bytes = t->lists_smem;
-    const bool dyn_l = (long long)std::max(1, (t->particle_num > 0 ? t->particle_num : t->n_cap) / t->nranks) * t->chunks >= dyn_per_warp * sm * (kListThreads / 32);
-    if (t->use_hsv) {
+    const long long n_local = std::max(1, (t->particle_num > 0 ? t->particle_num : t->n_cap) / t->nranks);
+    const bool dyn_l = n_local * t->chunks >= dyn_per_warp * sm * (kListThreads / 32);
+    if (n_local * t->M >= kListBigQueries) {
+      if (t->use_hsv) weight_lists_kernel<true, kListThreadsBig, true><<<wgrid, kListThreadsBig, t->lists_smem, s>>>(a);
+      else weight_lists_kernel<false, kListThreadsBig, true><<<wgrid, kListThreadsBig, t->lists_smem, s>>>(a);
+    } else if (t->use_hsv) {
       if (dyn_l) weight_lists_kernel<true, kListThreads, true><<<wgrid, kListThreads, t->lists_smem, s>>>(a);
       else weight_lists_kernel<true, kListThreads, false><<<wgrid, kListThreads, t->lists_smem, s>>>(a);
     } else {

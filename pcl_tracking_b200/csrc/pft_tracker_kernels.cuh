@@ -637,8 +637,8 @@ __device__ __forceinline__ NNResult nn_search(const CS* __restrict__ cs, const f
 // Octant record = 8 words of 32 bits (one 32-byte sector, read by ONE 256-bit load):
 //   word 0      header: 0..7 = entry count | count (8..71) + (g << 8) = entries beyond the seventh are in pool groups
 //               g, g+1, .. (eight entries each) | kListExtended = word 1 holds the index of an extended list (cells far
-//               from the surface: up to kListKX slots, not sorted), word 2 its length | kListOverflow = no list (the
-//               query is answered by brute force)
+//               from the surface whose list pairwise pruning cannot shorten: up to kListKX entries in input-index order),
+//               word 2 its length | kListOverflow = no list (the query is answered by brute force)
 //   words 1..7  entries as BYTE offsets of the points in the staged array (slot << 4), padded with the dummy slot
 constexpr int kL1Cap = 64;                         // a cell's own list is split into octants up to this length; longer ones become extended lists
 constexpr int kListKX = 1024;                      // entries of an extended list (cells far from the surface)
@@ -646,7 +646,7 @@ constexpr int kListXCells = 8192;                  // extended lists available p
 constexpr int kPoolGroups = 1 << 18;               // groups of eight entries for octant lists longer than seven
 constexpr unsigned int kListOverflow = 0xffffffffu;  // no list
 constexpr unsigned int kListExtended = 0xfffffffeu;  // extended list
-// extended-list entries are 16-bit slots: larger crops use the row-table search only
+// the build passes carry 16-bit slots: larger crops use the row-table search only
 __device__ __forceinline__ bool lists_on(const IndexHeader& h) { return h.use_lists && h.n_cropped < 65535; }
 
 __device__ __forceinline__ float box_mindist2(const float* lo, const float* hi, const float4& p) {
@@ -857,14 +857,33 @@ __device__ __forceinline__ void block_points_of_rows(int nrows, int* s_pref /* [
   }
 }
 
+// ascending bitonic sort of m2 (a power of two) 64-bit keys in shared memory by the whole thread block
+__device__ __forceinline__ void block_bitonic_sort(unsigned long long* keys, int m2) {
+  for (int k = 2; k <= m2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = threadIdx.x; t < m2; t += blockDim.x) {
+        const int u = t ^ j;
+        if (u > t) {
+          const unsigned long long x = keys[t], y = keys[u];
+          if (((t & k) == 0) == (x > y)) { keys[t] = y; keys[u] = x; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
 // One thread BLOCK builds the list of ONE fine cell straight from the grid (no shared-memory superset): used for the
 // cells of blocks whose superset does not fit, i.e. far from the surface, where lists are long (extended lists up to
 // kListKX) and a single warp would walk ~1000 points on its own while the rest of the GPU waits.
 __device__ __forceinline__ void build_cell_direct(const IndexHeader& h, const int* __restrict__ cs, const float4* __restrict__ pts, int cell,
                                                   float leaf, float margin, float r_max,
-                                                  unsigned int* __restrict__ flists, unsigned short* __restrict__ xlists,
+                                                  unsigned int* __restrict__ flists, unsigned int* __restrict__ xlists,
                                                   int* __restrict__ list_counters, int* pref, int* start, int* s_cnt, float* s_m2, int* s_ms, int* s_xi,
-                                                  unsigned short* s_list /* [kListKX] shared */) {
+                                                  unsigned short* s_list /* [kListKX] shared */, float4* s_pt4 /* [kListKX] shared */,
+                                                  unsigned long long* s_key /* [kListKX] shared */, unsigned long long* s_key2 /* [kListKX] shared */,
+                                                  const unsigned int* __restrict__ needed,
+                                                  int2* __restrict__ cell_items, unsigned short* __restrict__ l1_slots) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int fdx = h.f_dim[0], fdy = h.f_dim[1];
   const float cell_m = h.cell;
@@ -959,16 +978,77 @@ __device__ __forceinline__ void build_cell_direct(const IndexHeader& h, const in
         }
       });
   const int n = *s_cnt;
-  // cells far from the surface: one extended list (not sorted; the weight kernel scans it with a whole warp and
-  // resolves ties by input index), shared by the eight octants
-  if (threadIdx.x == 0) *s_xi = n <= kListKX ? atomicAdd(&list_counters[0], 1) : -1;
+  if (n > kListKX) { if (threadIdx.x < 32) write_octant_codes(h, flists, fx, fy, fz, kListOverflow, 0, 0); return; }
+  // ---- (3) pairwise pruning.  Far from the surface the two tests above keep hundreds of points (they only compare
+  // with ONE competitor, p0); nearly all of them are beaten everywhere in the cell by some other candidate (a point
+  // of the same face that lies nearer to the cell).  Every thread scans the competitors of its candidate and stops at
+  // the first that dominates it (domination is transitive: whatever dominated the dominator dominates the candidate
+  // too, so testing against every candidate, kept or not, is valid); the survivors are the cell's list.
+  const float ch = 0.5f * (hi[0] - lo[0]) + 1.0e-6f;  // half extent of the (cubic) cell box
+  // candidates in ascending order of their distance from the cell centre: only a nearer candidate can dominate, and the
+  // dominators of a far candidate are found within a few steps, so every scan is short
+  int n2 = 1;
+  while (n2 < n) n2 <<= 1;
+  for (int t = threadIdx.x; t < n2; t += blockDim.x) {
+    unsigned long long key = ~0ull;
+    if (t < n) {
+      const float4 p = pts[s_list[t]];
+      const float x = p.x - bc[0], y = p.y - bc[1], z = p.z - bc[2];
+      s_pt4[t] = make_float4(x, y, z, p.w);
+      key = ((unsigned long long)__float_as_uint((x * x + y * y) + z * z) << 32) | (unsigned long long)t;
+    }
+    s_key[t] = key;
+  }
+  if (threadIdx.x == 0) *s_cnt = 0;
+  __syncthreads();
+  block_bitonic_sort(s_key, n2);
+  for (int r0 = 0; r0 < n; r0 += blockDim.x) {
+    const int r = r0 + threadIdx.x;
+    if (r < n) {
+      const int t = (int)(s_key[r] & 0xffffffffull);
+      const float4 p = s_pt4[t];
+      const float pn = (p.x * p.x + p.y * p.y) + p.z * p.z;
+      bool alive = true;
+      for (int k = 0; k < r; ++k) {
+        const float4 c = s_pt4[(int)(s_key[k] & 0xffffffffull)];
+        const float cn = (c.x * c.x + c.y * c.y) + c.z * c.z;
+        // min over the cube of |q-p|^2 - |q-c|^2: positive (beyond the rounding slack) = c is nearer everywhere
+        const float fmin = (pn - cn) - 2.0f * (ch * ((fabsf(p.x - c.x) + fabsf(p.y - c.y)) + fabsf(p.z - c.z)));
+        if (fmin > 1.0e-6f * (pn + cn) + 1.0e-9f) { alive = false; break; }
+      }
+      // key = input index (upper half: the order of the extended list) | position in s_list
+      if (alive) s_key2[atomicAdd(s_cnt, 1)] = ((unsigned long long)(unsigned int)__float_as_int(p.w) << 32) | (unsigned long long)t;
+    }
+  }
+  __syncthreads();
+  const int m = *s_cnt;
+  PFT_STAT(11, threadIdx.x == 0 ? 1 : 0);
+  if (m <= kL1Cap) {
+    // a normal cell after all: its list goes to cand_octant_kernel like those of cand_build_kernel
+    if ((int)threadIdx.x < m) l1_slots[(size_t)cell * kL1Cap + threadIdx.x] = s_list[(int)(s_key2[threadIdx.x] & 0xffffffffull)];
+    if (threadIdx.x == 0) {
+      const int item = cell | (m << 24) | (needed[cell] < kCoarseBelow ? (int)0x80000000 : 0);
+      const int xyz = (fx < 1024 && fy < 1024 && fz < 1024) ? (fx | (fy << 10) | (fz << 20)) : -1;
+      cell_items[atomicAdd(&list_counters[4], 1)] = make_int2(item, xyz);
+    }
+    return;
+  }
+  // still long: an extended list in ascending order of the input index, scanned entry by entry by the queries of the cell
+  int m2 = 1;
+  while (m2 < m) m2 <<= 1;
+  for (int t = m + threadIdx.x; t < m2; t += blockDim.x) s_key2[t] = ~0ull;
+  __syncthreads();
+  block_bitonic_sort(s_key2, m2);
+  s_key = s_key2;
+  if (threadIdx.x == 0) *s_xi = atomicAdd(&list_counters[0], 1);
   __syncthreads();
   const int xi = *s_xi;
-  if (xi < 0 || xi >= kListXCells) { if (threadIdx.x < 32) write_octant_codes(h, flists, fx, fy, fz, kListOverflow, 0, 0); return; }
-  unsigned short* dst = xlists + (size_t)xi * kListKX;
-  PFT_STAT(11, threadIdx.x == 0 ? 1 : 0);
-  for (int t = threadIdx.x; t < n; t += blockDim.x) dst[t] = s_list[t];
-  if (threadIdx.x < 32) write_octant_codes(h, flists, fx, fy, fz, kListExtended, xi, n);
+  if (xi >= kListXCells) { if (threadIdx.x < 32) write_octant_codes(h, flists, fx, fy, fz, kListOverflow, 0, 0); return; }
+  unsigned int* dst = xlists + (size_t)xi * kListKX;
+  const unsigned int dummy = (unsigned int)h.n_cropped << 4;
+  const int m4 = (m + 3) & ~3;  // the lookup reads four entries at a time
+  for (int t = threadIdx.x; t < m4; t += blockDim.x) dst[t] = t < m ? ((unsigned int)s_list[(int)(s_key[t] & 0xffffffffull)] << 4) : dummy;
+  if (threadIdx.x < 32) write_octant_codes(h, flists, fx, fy, fz, kListExtended, xi, m);
   PFT_STAT(15, threadIdx.x == 0 ? 1 : 0);
 }
 
@@ -979,7 +1059,7 @@ __global__ void __launch_bounds__(256) cand_build_kernel(const IndexHeader* __re
                                                          const float4* __restrict__ pts, double max_d2,
                                                          unsigned int* __restrict__ flists,
                                                          const unsigned int* __restrict__ needed, const int* __restrict__ needed_list,
-                                                         unsigned short* __restrict__ xlists, int* __restrict__ list_counters,
+                                                         int* __restrict__ list_counters,
                                                          int* __restrict__ far_list, int2* __restrict__ cell_items,
                                                          unsigned short* __restrict__ l1_slots) {
   __shared__ IndexHeader h;
@@ -1163,23 +1243,8 @@ __global__ void __launch_bounds__(256) cand_build_kernel(const IndexHeader* __re
         }
       }
       if (n > kL1Cap) {
-        // long list (far from the surface): an extended list shared by the eight octants, scanned by a whole warp per query
-        int xi = -1;
-        if (n <= kListKX) {
-          if (lane == 0) xi = atomicAdd(&list_counters[0], 1);
-          xi = __shfl_sync(kFull, xi, 0);
-        }
-        if (xi < 0 || xi >= kListXCells) { write_octant_codes(h, flists, fx, fy, fz, kListOverflow, 0, 0); continue; }
-        unsigned short* dst = xlists + (size_t)xi * kListKX;
-        int w = 0;
-#pragma unroll
-        for (int q = 0; q < kSuperCap / 32; ++q) {
-          const unsigned int bal = keep_bal[q];
-          if ((bal >> lane) & 1u) dst[w + __popc(bal & ((1u << lane) - 1u))] = sslot[q * 32 + lane];
-          w += __popc(bal);
-        }
-        write_octant_codes(h, flists, fx, fy, fz, kListExtended, xi, n);
-        PFT_STAT(15, lane == 0 ? 1 : 0);
+        // long list (far from the surface): the far pass prunes it pairwise
+        if (lane == 0) { far_list[atomicAdd(&list_counters[2], 1)] = cell; PFT_STAT(10, 1); }
         continue;
       }
       // ---- (4) hand the cell's list to cand_octant_kernel (slots in superset order; the octant pass sorts them)
@@ -1266,12 +1331,13 @@ __global__ void __launch_bounds__(256) cand_octant_kernel(const IndexHeader* __r
   };
   for (int it = warp; it < n_items; it += nwarps) {
     const int2 item = cell_items[it];
-    const int cell = item.x & 0xffffff, n = (item.x >> 24) & 0x7f;
+    const int cell = item.x & 0xffffff;
+    int n = (item.x >> 24) & 0x7f;
     const bool coarse = item.x < 0;
     int fx, fy, fz;
     if (item.y >= 0) { fx = item.y & 1023; fy = (item.y >> 10) & 1023; fz = item.y >> 20; }
     else { fz = cell / (fdx * fdy); const int r2 = cell - fz * fdx * fdy; fy = r2 / fdx; fx = r2 - fy * fdx; }
-    const bool two = n > 32;
+    bool two = n > 32;
     // ---- the list in ascending order of the input index (rank = how many keys are smaller; keys are distinct)
     {
       const unsigned short* src = l1_slots + (size_t)cell * kL1Cap;
@@ -1294,6 +1360,35 @@ __global__ void __launch_bounds__(256) cand_octant_kernel(const IndexHeader* __r
     }
     srec[lane] = dummy; srec[lane + 32] = dummy;
     __syncwarp();
+    // ---- lists longer than one record: pairwise pruning at the cell level first -- an entry that another entry beats
+    // everywhere in the cell never wins (domination is transitive, so testing against every entry, kept or not, is
+    // valid); typically 10 entries become 6-7
+    if (n > 7) {
+      const float chh = 0.5f * leaf + margin + 1.0e-6f;
+      const float ccx = (float)(2 * (h.f_origin[0] + fx) + 1) * (0.5f * leaf), ccy = (float)(2 * (h.f_origin[1] + fy) + 1) * (0.5f * leaf),
+                  ccz = (float)(2 * (h.f_origin[2] + fz) + 1) * (0.5f * leaf);
+      const bool ia = lane < n, ib = two && lane + 32 < n;
+      const float4 ea = spt[ia ? lane : 0], eb = spt[ib ? lane + 32 : 0];
+      const unsigned int oa = soff[ia ? lane : 0], ob = soff[ib ? lane + 32 : 0];
+      const float ax = ea.x - ccx, ay = ea.y - ccy, az = ea.z - ccz, bx = eb.x - ccx, by = eb.y - ccy, bz = eb.z - ccz;
+      const float an = (ax * ax + ay * ay) + az * az, bn = (bx * bx + by * by) + bz * bz;
+      bool la = ia, lb = ib;
+      for (int c = 0; c < n; ++c) {
+        const float4 pc = spt[c];
+        const float cx = pc.x - ccx, cy = pc.y - ccy, cz = pc.z - ccz;
+        const float cn = (cx * cx + cy * cy) + cz * cz;
+        // min over the cube of |q-p|^2 - |q-c|^2: positive (beyond the rounding slack) = c is nearer everywhere
+        if ((an - cn) - 2.0f * (chh * ((fabsf(ax - cx) + fabsf(ay - cy)) + fabsf(az - cz))) > 1.0e-6f * (an + cn) + 1.0e-9f) la = false;
+        if (two && (bn - cn) - 2.0f * (chh * ((fabsf(bx - cx) + fabsf(by - cy)) + fabsf(bz - cz))) > 1.0e-6f * (bn + cn) + 1.0e-9f) lb = false;
+      }
+      const unsigned int ka = __ballot_sync(kFull, la), kb = __ballot_sync(kFull, lb);
+      __syncwarp();
+      if (la) { const int pos = __popc(ka & lt); spt[pos] = ea; soff[pos] = oa; }
+      if (lb) { const int pos = __popc(ka) + __popc(kb & lt); spt[pos] = eb; soff[pos] = ob; }
+      n = __popc(ka) + __popc(kb);
+      two = n > 32;
+      __syncwarp();
+    }
     // records of octant o: word index of its first word (the octants form one dense lattice, x fastest)
     auto rec_word = [&](int o) { return (((unsigned int)(2 * fz + (o >> 2)) * d2y + (unsigned int)(2 * fy + ((o >> 1) & 1))) * d2x + (unsigned int)(2 * fx + (o & 1))) * 8u; };
     if (coarse) {
@@ -1401,13 +1496,17 @@ __global__ void __launch_bounds__(256) cand_octant_kernel(const IndexHeader* __r
 // second pass of the build: the cells queued by cand_build_kernel, one thread block each
 __global__ void __launch_bounds__(256) cand_build_far_kernel(const IndexHeader* __restrict__ hdr, const int* __restrict__ cs,
                                                              const float4* __restrict__ pts, double max_d2,
-                                                             unsigned int* __restrict__ flists, unsigned short* __restrict__ xlists,
-                                                             int* __restrict__ list_counters, const int* __restrict__ far_list) {
+                                                             unsigned int* __restrict__ flists, unsigned int* __restrict__ xlists,
+                                                             int* __restrict__ list_counters, const int* __restrict__ far_list,
+                                                             const unsigned int* __restrict__ needed, int2* __restrict__ cell_items,
+                                                             unsigned short* __restrict__ l1_slots) {
   __shared__ IndexHeader h;
   __shared__ int s_cnt, s_xi;
   __shared__ int s_pref[34], s_start[32], s_ms[8];
   __shared__ float s_m2[8];
   __shared__ unsigned short s_list[kListKX];
+  __shared__ float4 s_pt4[kListKX];
+  __shared__ unsigned long long s_key[kListKX], s_key2[kListKX];
   if (threadIdx.x == 0) { h = *hdr; s_pref[32] = 0x7fffffff; }
   __syncthreads();
   if (!h.valid || !lists_on(h)) return;
@@ -1416,7 +1515,8 @@ __global__ void __launch_bounds__(256) cand_build_far_kernel(const IndexHeader* 
   const float margin = 1.0e-5f + 4.0e-6f * leaf * (float)(abs(h.f_origin[0]) + abs(h.f_origin[1]) + abs(h.f_origin[2]) + h.f_dim[0] + h.f_dim[1] + h.f_dim[2]);
   const float r_max = max_d2 >= 1.0e30 ? 1.0e15f : (float)sqrt(max_d2) * 1.00001f;
   for (int idx = blockIdx.x; idx < n_far; idx += gridDim.x) {
-    build_cell_direct(h, cs, pts, far_list[idx], leaf, margin, r_max, flists, xlists, list_counters, s_pref, s_start, &s_cnt, s_m2, s_ms, &s_xi, s_list);
+    build_cell_direct(h, cs, pts, far_list[idx], leaf, margin, r_max, flists, xlists, list_counters, s_pref, s_start, &s_cnt, s_m2, s_ms, &s_xi, s_list, s_pt4, s_key, s_key2,
+                      needed, cell_items, l1_slots);
     __syncthreads();
   }
   PFT_TRACE_MAX(2);
@@ -1432,7 +1532,7 @@ struct WeightArgs {
   const RowEntry* table;      // kRows entries sorted by lb2
   const unsigned int* flists;    // candidate lists (see cand_build_kernel): one record of 8 words per octant of the fine lattice
   const unsigned int* pool;      // groups of eight entries for octant lists longer than seven
-  const unsigned short* xlists;  // extended lists
+  const unsigned int* xlists;    // extended lists (byte offsets, ascending input index, padded to a multiple of four)
   const float4* model;        // {x,y,z,hsv} in tile order
   const int* model_perm;      // tile order -> order of the reference cloud as given
   int M;
@@ -1602,16 +1702,14 @@ __global__ void __launch_bounds__(THREADS, 1) weight_kernel(const WeightArgs a) 
 // answered one at a time by the whole warp (nn_slow_warp), bit-identical to the brute-force search.
 struct SlowNN { float d2; int slot; };
 
-// One query by a whole warp: every lane scans a 32nd of the candidates (an extended list, or every indexed point),
-// lexicographic (distance, input index) minimum across the lanes.  Returns the winner to all lanes (slot -1: none
+// One query by a whole warp, brute force: every lane scans a 32nd of the indexed points, lexicographic (distance,
+// input index) minimum across the lanes.  Returns the winner to all lanes (slot -1: none
 // nearer than lim2).
-__device__ __noinline__ SlowNN nn_slow_warp(const float4* __restrict__ pts /* {x,y,z,input index}, global */, const unsigned short* __restrict__ xl,
-                                            int n, float qx, float qy, float qz, float lim2) {
+__device__ __noinline__ SlowNN nn_slow_warp(const float4* __restrict__ pts /* {x,y,z,input index}, global */, int n, float qx, float qy, float qz, float lim2) {
   const int lane = threadIdx.x & 31;
   float bd = lim2;
   int bo = 0x7fffffff, bs = -1;
-  for (int t = lane; t < n; t += 32) {
-    const int slot = xl ? (int)xl[t] : t;
+  for (int slot = lane; slot < n; slot += 32) {
     const float4 p = pts[slot];
     const float dx = qx - p.x, dy = qy - p.y, dz = qz - p.z;
     const float d2 = (dx * dx + dy * dy) + dz * dz;
@@ -1628,7 +1726,7 @@ __device__ __noinline__ SlowNN nn_slow_warp(const float4* __restrict__ pts /* {x
 }
 
 #ifndef PFT_LIST_PIPE
-#define PFT_LIST_PIPE 1
+#define PFT_LIST_PIPE 0  // 1: two rounds of a warp in flight (measured: the registers are better spent on more warps)
 #endif
 // one 32-byte record (header + seven entries, or a pool group of eight entries) as ONE 256-bit load
 struct Rec8 { unsigned int w[8]; };
@@ -1716,7 +1814,16 @@ __device__ __forceinline__ void weight_list_items(const WeightArgs& a, const Ind
       float best = lim2;
       unsigned int boff = 0xffffffffu;
       const unsigned int hw = q.r.w[0];
-      if (hw < kListExtended) {
+      if (hw == kListExtended) {
+        // far from the surface (and not prunable to a short list): the lane scans its cell's extended list
+        const uint4* xl = reinterpret_cast<const uint4*>(a.xlists + (size_t)q.r.w[1] * kListKX);
+        const int n4 = ((int)q.r.w[2] + 3) >> 2;
+        PFT_STAT(13, act ? 1 : 0); PFT_STAT(14, act ? (int)q.r.w[2] : 0);
+        for (int g = 0; g < n4; ++g) {
+          const uint4 w = xl[g];
+          PFT_CAND(w.x) PFT_CAND(w.y) PFT_CAND(w.z) PFT_CAND(w.w)
+        }
+      } else if (hw < kListExtended) {
         PFT_CAND(q.r.w[1]) PFT_CAND(q.r.w[2]) PFT_CAND(q.r.w[3]) PFT_CAND(q.r.w[4]) PFT_CAND(q.r.w[5]) PFT_CAND(q.r.w[6]) PFT_CAND(q.r.w[7])
         const int cnt = (int)(hw & 0xffu);
         PFT_STAT(12, act ? 1 : 0); PFT_STAT(5, act ? cnt : 0);
@@ -1729,18 +1836,14 @@ __device__ __forceinline__ void weight_list_items(const WeightArgs& a, const Ind
           }
         }
       }
-      // queries without a short list: one at a time, by the whole warp
-      unsigned int slow = __ballot_sync(kFull, act && any_pts && hw >= kListExtended);
+      // queries whose cell has no list at all (the build gave up: extremely rare): brute force, one at a time, by the whole warp
+      unsigned int slow = __ballot_sync(kFull, act && any_pts && hw == kListOverflow);
       while (slow) {
         const int src = __ffs(slow) - 1;
         slow &= slow - 1u;
         const float sx = __shfl_sync(kFull, q.x, src), sy = __shfl_sync(kFull, q.y, src), sz = __shfl_sync(kFull, q.z, src);
-        const unsigned int shw = __shfl_sync(kFull, hw, src), s1 = __shfl_sync(kFull, q.r.w[1], src), s2 = __shfl_sync(kFull, q.r.w[2], src);
-        const unsigned short* xl = nullptr;
-        int nx = h.n_cropped;
-        if (shw == kListExtended) { xl = a.xlists + (size_t)s1 * kListKX; nx = (int)s2; }
-        PFT_STAT(13, lane == 0 ? 1 : 0); PFT_STAT(14, lane == 0 ? nx : 0); PFT_STAT(4, lane == 0 && !xl ? 1 : 0);
-        const SlowNN r = nn_slow_warp(a.pts, xl, nx, sx, sy, sz, lim2);
+        PFT_STAT(4, lane == 0 ? 1 : 0);
+        const SlowNN r = nn_slow_warp(a.pts, h.n_cropped, sx, sy, sz, lim2);
         if (lane == src && r.slot >= 0) { best = r.d2; boff = (unsigned int)r.slot << 4; }
       }
       const bool hit = act && boff != 0xffffffffu;
