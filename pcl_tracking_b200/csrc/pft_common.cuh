@@ -65,6 +65,21 @@ struct IndexHeader {
   int f_dim[3];
   int f_cells;        // f_dim[0] * f_dim[1] * f_dim[2]
   int use_lists;      // lists are built and used by this weight() (enough queries to amortise the build)
+  // One index per frame: with the lists on, the index covers the crop box DILATED by a margin (`built`), so that the
+  // later weight() calls of the same compute() -- whose crop boxes differ by the step noise of one resample -- find
+  // their points in it and only build the lists of the cells their queries newly reach.  Exactness: a nearest
+  // neighbour found among the points of `built` that lies inside the crop box IS the nearest neighbour among the
+  // cropped points.  The list build keeps that true for every query: cells whose lists can only depend on points well
+  // inside the crop box are built from all points and reused; cells near the faces are built from the cropped points
+  // only and rebuilt by the next weight().  (Safety net: a winner outside the crop box -- flag in bit 31 of the staged
+  // point's fourth word -- would send the query to the brute-force search over the cropped points.)
+  float built[6];     // box the indexed points were taken from (= aabb when the lists are off)
+  float core[6];      // hull of the crop boxes of the frame so far, each shrunk by `dilate`: the lists marked reusable only
+                      // depend on points inside it, so a later crop box must contain it (and lie inside `built`)
+  float dilate;       // the margin (0: the index holds the crop box only and nothing is reused)
+  int reuse;          // this weight() reuses the index of an earlier weight() of the frame (its crop box lies in `built`)
+  int n_in_crop;      // indexed points inside the crop box of THIS weight() (what cropInputPointCloud would return)
+  unsigned int epoch; // weight() calls so far (diagnostics)
 };
 
 // ------------------------------------------------------------------ device helpers

@@ -154,12 +154,13 @@ struct pft_tracker {
   int graph_nodes[2] = {0, 0};
   // device buffers
   DevBuf st, parts[2], mats, slot_aabb, model, model_perm, model_tmp, sort_keys, sort_idx, bbox, raw, partial, cdf, cdf_total, ancestors, bin_keys, tbl_rep,
-      tbl_min, slot_of, klb, d_usel, d_normals, d_umot, idx_hdr, cell_start, ipts, ipts2, ihsv, icount, dbg_idx, dbg_d2, d_trans, row_table, flists, fpool, fcell_items, fl1_slots, fneeded, fneeded_list, ffar_list, xlists, xcount, result_box, alias_a, alias_q, alias_hl, oct_hdr, oct_nodes, oct_next, cd_hdr, cd_nodes, cd_out;
+      tbl_min, slot_of, klb, d_usel, d_normals, d_umot, idx_hdr, idx_hdr_prev, fbuilt_bits, cell_start, ipts, ipts2, ihsv, icount, dbg_idx, dbg_d2, d_trans, row_table, flists, fpool, fcell_items, fl1_slots, fneeded, fneeded_list, ffar_list, xlists, xcount, result_box, alias_a, alias_q, alias_hl, oct_hdr, oct_nodes, oct_next, cd_hdr, cd_nodes, cd_out;
   int oct_node_cap = 0;
   // change detector (PCL ctor defaults, off in the reference): host-driven, one read-back per test
   bool use_cd = false;
   int cd_interval = 10, cd_filter = 10, change_counter = 0, cd_tests = 0, cd_last_found = -1, cd_node_cap = 0, cd_resets = 0;
   double cd_res = 0.01;
+  int lists_hint = -1;  // TrackerState::lists_on as last read back (-1: not yet): 1 = the row-table kernel is not launched behind weight_lists_kernel
   int weight_smem = 0;  // dynamic shared memory of the weight kernel (bytes)
   int lists_smem = 0;   // ... of weight_lists_kernel
   int tbl_size = 0;
@@ -195,7 +196,7 @@ void stage_mark(pft_tracker* t, const char* name) {
 void release_all(pft_tracker* t) {
   DevBuf* bufs[] = {&t->st, &t->parts[0], &t->parts[1], &t->mats, &t->slot_aabb, &t->model, &t->model_perm, &t->model_tmp, &t->sort_keys, &t->sort_idx,
                     &t->bbox, &t->raw, &t->partial, &t->cdf, &t->cdf_total, &t->ancestors, &t->bin_keys, &t->tbl_rep, &t->tbl_min, &t->slot_of, &t->klb,
-                    &t->d_usel, &t->d_normals, &t->d_umot, &t->idx_hdr, &t->cell_start, &t->ipts, &t->ipts2, &t->ihsv, &t->icount, &t->dbg_idx,
+                    &t->d_usel, &t->d_normals, &t->d_umot, &t->idx_hdr, &t->idx_hdr_prev, &t->fbuilt_bits, &t->cell_start, &t->ipts, &t->ipts2, &t->ihsv, &t->icount, &t->dbg_idx,
                     &t->dbg_d2, &t->d_trans, &t->row_table, &t->flists, &t->fpool, &t->fcell_items, &t->fl1_slots, &t->fneeded, &t->fneeded_list, &t->ffar_list, &t->xlists, &t->xcount, &t->result_box, &t->alias_a, &t->alias_q, &t->alias_hl, &t->oct_hdr, &t->oct_nodes, &t->oct_next, &t->cd_hdr, &t->cd_nodes, &t->cd_out};
   for (auto* b : bufs) b->release();
 }
@@ -299,6 +300,7 @@ int upload_row_table(pft_tracker* t) {
   t->lists_smem = dyn_l;
   if (t->list_max_cells / 8 + 64 > max_optin - 2048) t->list_max_cells = (max_optin - 4096) * 8;  // the mark kernel keeps one bit per fine cell in shared memory
   PFT_CUDA_TRY(cudaFuncSetAttribute(cand_mark_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, t->list_max_cells / 8 + 64));
+  PFT_CUDA_TRY(cudaFuncSetAttribute(cand_mark_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, t->list_max_cells / 8 + 64));
   return PFT_OK;
 }
 
@@ -321,6 +323,10 @@ int ensure_particle_buffers(pft_tracker* t) {
     PFT_CUDA_TRY(cudaStreamSynchronize(s));
     if ((rc = t->cdf_total.reserve(sizeof(unsigned long long)))) return rc;
     if ((rc = t->idx_hdr.reserve(sizeof(IndexHeader)))) return rc;
+    if ((rc = t->idx_hdr_prev.reserve(sizeof(IndexHeader)))) return rc;
+    PFT_CUDA_TRY(cudaMemsetAsync(t->idx_hdr.p, 0, sizeof(IndexHeader), s));
+    PFT_CUDA_TRY(cudaMemsetAsync(t->idx_hdr_prev.p, 0, sizeof(IndexHeader), s));
+    PFT_CUDA_TRY(cudaStreamSynchronize(s));
     if ((rc = t->d_trans.reserve(12 * sizeof(float)))) return rc;
     if ((rc = t->cell_start.reserve(((size_t)t->max_cells + 16) * sizeof(int)))) return rc;
     if ((rc = t->icount.reserve(((size_t)t->max_cells + 16) * sizeof(int)))) return rc;
@@ -331,6 +337,7 @@ int ensure_particle_buffers(pft_tracker* t) {
       if ((rc = t->fcell_items.reserve(((size_t)t->list_max_cells + 16) * sizeof(int2)))) return rc;
       if ((rc = t->fl1_slots.reserve(((size_t)t->list_max_cells + 1) * kL1Cap * sizeof(unsigned short)))) return rc;
       if ((rc = t->fneeded.reserve(((size_t)t->list_max_cells + 16) * sizeof(unsigned int)))) return rc;
+      if ((rc = t->fbuilt_bits.reserve(((size_t)t->list_max_cells / 32 + 16) * sizeof(unsigned int)))) return rc;
       // blocks of 2x2x2 fine cells: at most ceil(d/2)^3 <= (d+1)^3/8, bounded generously by cells/2 + 4096
       if ((rc = t->fneeded_list.reserve(((size_t)t->list_max_cells / 2 + 4096) * sizeof(int)))) return rc;
       if ((rc = t->ffar_list.reserve(((size_t)t->list_max_cells + 16) * sizeof(int)))) return rc;
@@ -630,19 +637,23 @@ int weight_eval_pcl_approx(pft_tracker* t, bool force_raw) {
 }
 
 // crop box -> index header (also what in_crop() reads) + reset of the per-weight() counters
-int launch_index_begin(pft_tracker* t) {
+int launch_index_begin(pft_tracker* t, bool reuse_allowed = false) {
   const int sm = t->ctx->sm_count;
   const float inv_leaf = 1.0f / (float)t->search_res;
+  // one index per frame (see IndexHeader): with the lists on, the crop box is dilated by this margin; the later weight()
+  // calls of a compute() reuse the index when their crop box fits
+  static const float dilate = [] { const char* e = getenv("PFT_INDEX_DILATE"); return e ? (float)atof(e) : 0.03f; }();
   index_begin_kernel<<<sm, 256, 0, t->run_stream()>>>(t->st.as<TrackerState>(), t->idx_hdr.as<IndexHeader>(), t->icount.as<int>(), inv_leaf, t->index_level,
                                                       t->max_cells, t->list_mode ? t->list_max_cells : 0, t->list_mode == 2 ? 0 : t->M, t->nranks, t->rank,
-                                                      t->fneeded.as<unsigned int>(), t->xcount.as<int>());
+                                                      t->fneeded.as<unsigned int>(), t->xcount.as<int>(), t->fbuilt_bits.as<unsigned int>(),
+                                                      reuse_allowed ? 1 : 0, t->iteration_num > 1 ? dilate : 0.f, t->idx_hdr_prev.as<IndexHeader>());
   PFT_LAUNCH_CHECK();
   stage_mark(t, "index_begin_kernel");
   return PFT_OK;
 }
 
 // weight(), part 2: cropInputPointCloud + search index rebuild (K2), coherence of this rank's particles (K3)
-int weight_phase_eval(pft_tracker* t, bool force_raw = false) {
+int weight_phase_eval(pft_tracker* t, bool force_raw = false, bool reuse_allowed = false) {
   int rc = check_weight_ready(t);
   if (rc) return rc;
   cudaStream_t s = t->run_stream();
@@ -653,11 +664,11 @@ int weight_phase_eval(pft_tracker* t, bool force_raw = false) {
   IndexHeader* hdr = t->idx_hdr.as<IndexHeader>();
   const float inv_leaf = 1.0f / (float)t->search_res;
   const int gscene = blocks_for(ncap_scene, 256, sm * 4);
-  if ((rc = launch_index_begin(t))) return rc;
-  index_count_kernel<<<gscene, 256, 0, s>>>(in->d_pts(), in->d_hdr(), hdr, t->icount.as<int>());
+  if ((rc = launch_index_begin(t, reuse_allowed && t->list_max_cells > 0 && t->list_mode && t->nn_mode == PFT_NN_EXACT))) return rc;
+  index_count_kernel<<<gscene, 256, 0, s>>>(in->d_pts(), in->d_hdr(), hdr, t->icount.as<int>(), t->ipts2.as<float4>());
   PFT_LAUNCH_CHECK();
   stage_mark(t, "index_count_kernel");
-  index_scan_kernel<<<1, 1024, 0, s>>>(hdr, t->icount.as<int>(), t->cell_start.as<int>(), st, t->ipts.as<float4>(), t->ipts2.as<float4>());
+  index_scan_kernel<<<1, 1024, 0, s>>>(hdr, t->icount.as<int>(), t->cell_start.as<int>(), st, t->ipts.as<float4>(), t->ipts2.as<float4>(), t->idx_hdr_prev.as<IndexHeader>());
   PFT_LAUNCH_CHECK();
   stage_mark(t, "index_scan_kernel");
   index_scatter_kernel<<<gscene, 256, 0, s>>>(in->d_pts(), in->d_hdr(), hdr, t->cell_start.as<int>(), t->icount.as<int>(), t->ipts.as<float4>(),
@@ -668,8 +679,9 @@ int weight_phase_eval(pft_tracker* t, bool force_raw = false) {
     // dynamic shared memory: one bit per fine cell the lists are sized for
     // small query sets: exact query counts per cell (cells with few queries get one list instead of eight octant lists)
     const long long n_queries = (long long)std::max(1, (t->particle_num > 0 ? t->particle_num : t->n_cap) / t->nranks) * t->M;
-    if (n_queries <= kMarkCountMaxQueries) cand_mark_kernel<true><<<sm * 3, 256, 0, s>>>(st, hdr, t->model.as<float4>(), t->M, t->mats.as<float>(), t->fneeded.as<unsigned int>(), t->nranks, t->rank);
-    else cand_mark_kernel<false><<<sm * 3, 256, (size_t)(t->list_max_cells / 8 + 64), s>>>(st, hdr, t->model.as<float4>(), t->M, t->mats.as<float>(), t->fneeded.as<unsigned int>(), t->nranks, t->rank);
+    const size_t mark_smem = (size_t)(t->list_max_cells / 8 + 64);
+    if (n_queries <= kMarkCountMaxQueries) cand_mark_kernel<true><<<sm * 3, 256, mark_smem, s>>>(st, hdr, t->model.as<float4>(), t->M, t->mats.as<float>(), t->fneeded.as<unsigned int>(), t->nranks, t->rank, t->fbuilt_bits.as<unsigned int>());
+    else cand_mark_kernel<false><<<sm * 3, 256, mark_smem, s>>>(st, hdr, t->model.as<float4>(), t->M, t->mats.as<float>(), t->fneeded.as<unsigned int>(), t->nranks, t->rank, t->fbuilt_bits.as<unsigned int>());
     PFT_LAUNCH_CHECK();
     stage_mark(t, "cand_mark_kernel");
     cand_collect_kernel<<<sm * 2, 256, 0, s>>>(hdr, t->fneeded.as<unsigned int>(), t->fneeded_list.as<int>(), t->xcount.as<int>());
@@ -677,13 +689,13 @@ int weight_phase_eval(pft_tracker* t, bool force_raw = false) {
     stage_mark(t, "cand_collect_kernel");
     cand_build_kernel<<<sm * 8, 256, 0, s>>>(hdr, t->cell_start.as<int>(), t->ipts.as<float4>(), t->max_dist * t->max_dist, t->flists.as<unsigned int>(),
                                             t->fneeded.as<unsigned int>(), t->fneeded_list.as<int>(), t->xcount.as<int>(), t->ffar_list.as<int>(),
-                                            t->fcell_items.as<int2>(), t->fl1_slots.as<unsigned short>());
+                                            t->fcell_items.as<int2>(), t->fl1_slots.as<unsigned short>(), t->fbuilt_bits.as<unsigned int>());
     PFT_LAUNCH_CHECK();
     stage_mark(t, "cand_build_kernel");
     // cells far from the surface (long lists): pairwise pruning, one thread block each; most of them join the octant pass
     cand_build_far_kernel<<<sm * 4, 256, 0, s>>>(hdr, t->cell_start.as<int>(), t->ipts.as<float4>(), t->max_dist * t->max_dist,
                                                 t->flists.as<unsigned int>(), t->xlists.as<unsigned int>(), t->xcount.as<int>(), t->ffar_list.as<int>(),
-                                                t->fneeded.as<unsigned int>(), t->fcell_items.as<int2>(), t->fl1_slots.as<unsigned short>());
+                                                t->fneeded.as<unsigned int>(), t->fcell_items.as<int2>(), t->fl1_slots.as<unsigned short>(), t->fbuilt_bits.as<unsigned int>());
     PFT_LAUNCH_CHECK();
     stage_mark(t, "cand_build_far_kernel");
     cand_octant_kernel<<<sm * 8, 256, 0, s>>>(hdr, t->ipts.as<float4>(), t->max_dist * t->max_dist, t->flists.as<unsigned int>(), t->fpool.as<unsigned int>(),
@@ -694,7 +706,9 @@ int weight_phase_eval(pft_tracker* t, bool force_raw = false) {
   const bool lists_built = t->list_max_cells > 0 && t->list_mode && t->nn_mode == PFT_NN_EXACT;
   if (t->nn_mode == PFT_NN_PCL_APPROX) return weight_eval_pcl_approx(t, force_raw);
   WeightArgs a;
-  a.st = st; a.hdr = hdr; a.pts2 = t->ipts2.as<float4>(); a.lists_kernel_ran = lists_built ? 1 : 0;
+  // the row-table kernel runs behind weight_lists_kernel unless the last state read-back says the lists are on
+  const bool fallback_kernel = !lists_built || t->lists_hint != 1;
+  a.st = st; a.hdr = hdr; a.pts2 = t->ipts2.as<float4>(); a.lists_kernel_ran = lists_built ? 1 : 0; a.fallback_follows = fallback_kernel ? 1 : 0;
   a.flists = t->flists.as<unsigned int>(); a.pool = t->fpool.as<unsigned int>(); a.xlists = t->xlists.as<unsigned int>();
   a.cell_start = t->cell_start.as<int>(); a.pts = t->ipts.as<float4>();
   a.hsv = t->ihsv.as<unsigned int>(); a.table = t->row_table.as<RowEntry>(); a.smem_bytes = t->weight_smem;
@@ -735,15 +749,17 @@ int weight_phase_eval(pft_tracker* t, bool force_raw = false) {
     a.smem_bytes = t->weight_smem;
   }
   // row-table search over the grid: crops the lists do not cover (returns at once otherwise)
-  if (t->use_hsv) {
-    if (dyn) weight_kernel<true, kWeightThreads, true><<<wgrid, kWeightThreads, t->weight_smem, s>>>(a);
-    else weight_kernel<true, kWeightThreadsSmall, false><<<wgrid, kWeightThreadsSmall, t->weight_smem, s>>>(a);
-  } else {
-    if (dyn) weight_kernel<false, kWeightThreads, true><<<wgrid, kWeightThreads, t->weight_smem, s>>>(a);
-    else weight_kernel<false, kWeightThreadsSmall, false><<<wgrid, kWeightThreadsSmall, t->weight_smem, s>>>(a);
+  if (fallback_kernel) {
+    if (t->use_hsv) {
+      if (dyn) weight_kernel<true, kWeightThreads, true><<<wgrid, kWeightThreads, t->weight_smem, s>>>(a);
+      else weight_kernel<true, kWeightThreadsSmall, false><<<wgrid, kWeightThreadsSmall, t->weight_smem, s>>>(a);
+    } else {
+      if (dyn) weight_kernel<false, kWeightThreads, true><<<wgrid, kWeightThreads, t->weight_smem, s>>>(a);
+      else weight_kernel<false, kWeightThreadsSmall, false><<<wgrid, kWeightThreadsSmall, t->weight_smem, s>>>(a);
+    }
+    PFT_LAUNCH_CHECK();
+    stage_mark(t, "weight_kernel");
   }
-  PFT_LAUNCH_CHECK();
-  stage_mark(t, "weight_kernel");
   if (t->timing && !lists_built) { PFT_CUDA_TRY(cudaEventRecord(t->ev_w[2 * t->n_ev_used + 1], s)); t->n_ev_used++; }
   if (t->nranks > 1 || force_raw) {  // (single rank: normalize_kernel sums the per-chunk partials itself)
     raw_weights_kernel<<<blocks_for(local_cap, 256, sm * 4), 256, 0, s>>>(st, t->partial.as<double>(), t->chunks, t->n_cap, t->raw.as<float>(), local_cap,
@@ -822,7 +838,7 @@ int weight_phase_renormalize(pft_tracker* t) {
   return PFT_OK;
 }
 
-int stage_weight(pft_tracker* t, bool fuse_update = false) {
+int stage_weight(pft_tracker* t, bool fuse_update = false, bool reuse_allowed = false) {
   int rc;
   if ((rc = weight_phase_box(t))) return rc;
   if ((rc = weight_comm_box(t))) return rc;
@@ -838,7 +854,7 @@ int stage_weight(pft_tracker* t, bool fuse_update = false) {
       --t->change_counter;
     }
   }
-  if ((rc = weight_phase_eval(t))) return rc;
+  if ((rc = weight_phase_eval(t, false, reuse_allowed))) return rc;
   if ((rc = weight_comm_raw(t))) return rc;
   return weight_phase_normalize(t, fuse_update);
 }
@@ -858,7 +874,9 @@ int enqueue_tracking(pft_tracker* t) {
     if (t->changed && (rc = stage_resample(t, it))) return rc;
     // upstream: update() runs when changed_, which every weight() sets (the change detector is off): it is fused into
     // the normalise launch
-    if ((rc = stage_weight(t, true))) return rc;
+    // the first weight() of a compute() builds the scene index of the frame; the later ones reuse it when their crop
+    // box fits the (dilated) box it was built from (decided on the device, see index_begin_kernel)
+    if ((rc = stage_weight(t, true, it > 0 && !t->use_cd))) return rc;
   }
   return PFT_OK;
 }
@@ -1239,6 +1257,10 @@ static int read_state(pft_tracker* t, TrackerState* host) {
   cudaStream_t s = t->run_stream();
   PFT_CUDA_TRY(cudaMemcpyAsync(t->ctx->pinned, t->st.p, sizeof(TrackerState), cudaMemcpyDeviceToHost, s));
   PFT_CUDA_TRY(cudaStreamSynchronize(s));
+  {
+    const int seen = reinterpret_cast<const TrackerState*>(t->ctx->pinned)->lists_on ? 1 : 0;
+    if (t->M > 0 && seen != t->lists_hint) { t->lists_hint = seen; invalidate_graph(t); }  // (the launch sequence of weight() changes)
+  }
   memcpy(host, t->ctx->pinned, sizeof(TrackerState));
   if (host->peer_error) { set_last_error("NVLink peer exchange timed out: a peer rank did not reach the same weight()"); return PFT_ERR_COMM; }
   return PFT_OK;
@@ -1470,7 +1492,7 @@ int pft_tracker_get_cropped_count(pft_tracker* t, size_t* n) {
   cudaStream_t s = t->run_stream();
   PFT_CUDA_TRY(cudaMemcpyAsync(t->ctx->pinned, t->idx_hdr.p, sizeof(IndexHeader), cudaMemcpyDeviceToHost, s));
   PFT_CUDA_TRY(cudaStreamSynchronize(s));
-  *n = (size_t)reinterpret_cast<IndexHeader*>(t->ctx->pinned)->n_cropped;
+  *n = (size_t)reinterpret_cast<IndexHeader*>(t->ctx->pinned)->n_in_crop;
   return PFT_OK;
 }
 
@@ -1483,7 +1505,7 @@ int pft_tracker_get_index_info(pft_tracker* t, int* info8) {
   PFT_CUDA_TRY(cudaStreamSynchronize(s));
   const IndexHeader* h = reinterpret_cast<IndexHeader*>(t->ctx->pinned);
   info8[0] = h->dim[0]; info8[1] = h->dim[1]; info8[2] = h->dim[2]; info8[3] = h->level;
-  info8[4] = h->n_cropped; info8[5] = h->n_cells; info8[6] = h->use_lists; info8[7] = h->f_cells;
+  info8[4] = h->n_in_crop; info8[5] = h->n_cells; info8[6] = h->use_lists; info8[7] = h->f_cells;
   return PFT_OK;
 }
 

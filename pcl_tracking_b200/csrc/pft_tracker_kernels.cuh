@@ -47,6 +47,7 @@ struct TrackerState {
   int resample_n_old;            // particle count the running resample draws FROM (cdf_kernel publishes the new count for fixed-N trackers)
   unsigned int work_counter;     // next (particle, model chunk) item of the running weight kernel (reset by index_begin_kernel)
   unsigned long long evals;      // likelihood evaluations so far: sum over weight() calls of particles x model points (whole job)
+  int lists_on;                  // the last weight() ran on the candidate lists (read back with the state: the host then stops launching the row-table kernel behind weight_lists_kernel)
 };
 
 // ------------------------------------------------------------------ NVLink peer exchange (one process per GPU)
@@ -350,12 +351,14 @@ __global__ void __launch_bounds__(WARPS * 32) aabb_kernel(TrackerState* st, cons
 // of the points of cell c (cells x-fastest, so the points of any x-window of a row are ONE contiguous slot range).
 // It replaces pcl::search::Octree::setInputCloud (a pointer octree rebuilt by every weight()); the cell
 // edge is an internal choice (base resolution x 2^level) that never changes results: the search below is exact.
-__device__ inline void compute_index_header(const float* aabb, float inv_leaf, int base_level, int max_cells, IndexHeader& h) {
+__device__ inline void compute_index_header(const float* crop, const float* aabb /* box to index: the crop box, possibly dilated */, float inv_leaf,
+                                            int base_level, int max_cells, IndexHeader& h) {
 #pragma unroll
-  for (int d = 0; d < 6; ++d) h.aabb[d] = aabb[d];
+  for (int d = 0; d < 6; ++d) { h.aabb[d] = crop[d]; h.built[d] = aabb[d]; h.core[d] = crop[d]; }
+  h.reuse = 0; h.n_in_crop = 0; h.dilate = 0.f;
   h.inv_leaf = inv_leaf;
   h.n_cropped = 0;
-  h.valid = (aabb[0] <= aabb[3] && aabb[1] <= aabb[4] && aabb[2] <= aabb[5]) ? 1 : 0;
+  h.valid = (crop[0] <= crop[3] && crop[1] <= crop[4] && crop[2] <= crop[5]) ? 1 : 0;
   h.level = base_level; h.level_scale = 1.0f; h.n_cells = 0;
   h.dim[0] = h.dim[1] = h.dim[2] = 0; h.origin[0] = h.origin[1] = h.origin[2] = 0;
   h.cell = 1.0f / inv_leaf;
@@ -401,35 +404,96 @@ __device__ inline void compute_index_header(const float* aabb, float inv_leaf, i
 // that is d away from the surface walks ~pi (d/cell + 1)^2 rows and ~(d + cell)^2 candidates: cell ~ d balances them)
 __global__ void index_begin_kernel(TrackerState* st, IndexHeader* hdr, int* cell_count, float inv_leaf, int base_level,
                                    int max_cells, int list_max_cells, int M, int nranks, int rank, unsigned int* needed_words,
-                                   int* list_counters /* [0] extended lists handed out, [1] needed blocks, [2] cells queued for the far pass, [3] pool groups handed out, [4] cells queued for the octant pass */) {
+                                   int* list_counters /* [0] extended lists handed out, [1] needed blocks, [2] cells queued for the far pass, [3] pool groups handed out, [4] cells queued for the octant pass */,
+                                   unsigned int* built_bits /* one bit per fine cell: its lists exist (this frame) */, int reuse_allowed, float dilate,
+                                   const IndexHeader* __restrict__ hdr_prev /* header of the previous weight() (snapshot taken by index_scan_kernel:
+                                                                               nothing writes it while this kernel runs, so every block derives the same header) */) {
   __shared__ IndexHeader h;
   PFT_TRACE_MIN(0);
   if (threadIdx.x == 0) {
-    if (base_level < 0) {
-      base_level = 1;
-      if (st->nn_count > 0) {
-        const float mean_d = (float)((double)st->nn_sum_um / (double)st->nn_count) * 1.0e-6f;
-        const float want = mean_d * 1.15f * inv_leaf;  // cell edge in units of the resolution
-        base_level = want <= 1.5f ? 1 : (want <= 3.0f ? 1 : (want <= 6.0f ? 2 : (want <= 12.0f ? 3 : 4)));
+    const IndexHeader old = *hdr_prev;
+    bool reuse = reuse_allowed && old.valid && old.use_lists && old.n_cropped < 65535;
+    if (reuse) {
+      // the new crop box must lie inside the box the index was built from (an empty crop box reuses nothing)
+      reuse = st->aabb[0] <= st->aabb[3] && st->aabb[1] <= st->aabb[4] && st->aabb[2] <= st->aabb[5];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) reuse = reuse && st->aabb[d] >= old.built[d] && st->aabb[3 + d] <= old.built[3 + d];
+      // ... and contain the core the reusable lists depend on (an inverted core = nothing was reusable: no constraint)
+      if (old.core[0] <= old.core[3] && old.core[1] <= old.core[4] && old.core[2] <= old.core[5]) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) reuse = reuse && st->aabb[d] <= old.core[d] && st->aabb[3 + d] >= old.core[3 + d];
       }
     }
-    compute_index_header(st->aabb, inv_leaf, base_level, max_cells, h);
-    // candidate lists pay off when this rank's queries outnumber the fine cells they are built for
-    const int n = st->particle_num;
-    const long long n_local = n > rank ? (n - rank + nranks - 1) / nranks : 0;
-    // (M == 0: the caller forces the lists on)
-    h.use_lists = (h.valid && h.f_cells > 0 && h.f_cells <= list_max_cells && (M == 0 || n_local * (long long)M >= 2ll * h.f_cells)) ? 1 : 0;
+    if (reuse) {
+      h = old;
+#pragma unroll
+      for (int d = 0; d < 6; ++d) h.aabb[d] = st->aabb[d];
+      h.reuse = 1; h.n_in_crop = 0; h.epoch = old.epoch + 1u;
+#pragma unroll
+      for (int d = 0; d < 3; ++d) { h.core[d] = fminf(old.core[d], st->aabb[d] + old.dilate); h.core[3 + d] = fmaxf(old.core[3 + d], st->aabb[3 + d] - old.dilate); }
+    } else {
+      if (base_level < 0) {
+        base_level = 1;
+        if (st->nn_count > 0) {
+          const float mean_d = (float)((double)st->nn_sum_um / (double)st->nn_count) * 1.0e-6f;
+          const float want = mean_d * 1.15f * inv_leaf;  // cell edge in units of the resolution
+          base_level = want <= 1.5f ? 1 : (want <= 3.0f ? 1 : (want <= 6.0f ? 2 : (want <= 12.0f ? 3 : 4)));
+        }
+      }
+      // candidate lists pay off when this rank's queries outnumber the fine cells they are built for
+      const int n = st->particle_num;
+      const long long n_local = n > rank ? (n - rank + nranks - 1) / nranks : 0;
+      float box[6];
+#pragma unroll
+      for (int d = 0; d < 6; ++d) box[d] = st->aabb[d];
+      compute_index_header(st->aabb, box, inv_leaf, base_level, max_cells, h);
+      // (M == 0: the caller forces the lists on)
+      bool lists = h.valid && h.f_cells > 0 && h.f_cells <= list_max_cells && (M == 0 || n_local * (long long)M >= 2ll * h.f_cells);
+      if (lists && dilate > 0.f) {
+        // lists on: index the dilated box, so that the next weight() of the frame can reuse the index (when the dilated
+        // box does not fit the list tables, the plain crop box is indexed and the next weight() rebuilds)
+        IndexHeader hd;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) { box[d] = st->aabb[d] - dilate; box[3 + d] = st->aabb[3 + d] + dilate; }
+        compute_index_header(st->aabb, box, inv_leaf, base_level, max_cells, hd);
+        if (hd.f_cells > 0 && hd.f_cells <= list_max_cells) {
+          h = hd;
+          h.dilate = dilate;
+#pragma unroll
+          for (int d = 0; d < 3; ++d) { h.core[d] = st->aabb[d] + dilate; h.core[3 + d] = st->aabb[3 + d] - dilate; }
+        }
+      }
+      h.use_lists = lists ? 1 : 0;
+      h.epoch = old.epoch + 1u;
+    }
     if (blockIdx.x == 0) *hdr = h;
   }
   __syncthreads();
-  const int nc = h.n_cells + 1;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nc; i += gridDim.x * blockDim.x) cell_count[i] = 0;
+  if (!h.reuse) {
+    const int nc = h.n_cells + 1;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nc; i += gridDim.x * blockDim.x) cell_count[i] = 0;
+  }
   if (h.use_lists) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < h.f_cells; i += gridDim.x * blockDim.x) needed_words[i] = 0u;
+    if (!h.reuse) {
+      const int words = (h.f_cells + 31) >> 5;
+      for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < words; i += gridDim.x * blockDim.x) built_bits[i] = 0u;
+    }
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) { list_counters[0] = 0; list_counters[1] = 0; list_counters[2] = 0; list_counters[3] = 0; list_counters[4] = 0; st->work_counter = 0u; }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    // (a reusing weight() keeps handing out extended lists and pool groups where the earlier ones stopped)
+    if (!h.reuse) { list_counters[0] = 0; list_counters[3] = 0; }
+    list_counters[1] = 0; list_counters[2] = 0; list_counters[4] = 0;
+    st->work_counter = 0u;
+  }
 }
 
+// the points the index holds: finite and inside the box it was built from (the crop box, or the crop box dilated)
+__device__ __forceinline__ bool in_built(const float4& p, const IndexHeader& h) {
+  return isfinite(p.x) && isfinite(p.y) && isfinite(p.z) && p.x >= h.built[0] && p.x <= h.built[3] && p.y >= h.built[1] &&
+         p.y <= h.built[4] && p.z >= h.built[2] && p.z <= h.built[5];
+}
+constexpr unsigned int kInCropBit = 0x80000000u;  // fourth word of a staged point: packed HSV | this bit when the point lies in the crop box of the running weight()
 __device__ __forceinline__ bool in_crop(const float4& p, const IndexHeader& h) {
   // three inclusive PassThrough passes (x, y, z) on finite points
   return isfinite(p.x) && isfinite(p.y) && isfinite(p.z) && p.x >= h.aabb[0] && p.x <= h.aabb[3] && p.y >= h.aabb[1] &&
@@ -442,29 +506,51 @@ __device__ __forceinline__ int cell_of(const float4& p, const IndexHeader& h) {
   return (cz * h.dim[1] + cy) * h.dim[0] + cx;
 }
 
-__global__ void index_count_kernel(const float4* __restrict__ scene, const CloudHeader* __restrict__ scene_hdr, IndexHeader* hdr, int* cell_count) {
+__global__ void index_count_kernel(const float4* __restrict__ scene, const CloudHeader* __restrict__ scene_hdr, IndexHeader* hdr, int* cell_count,
+                                   float4* __restrict__ pts2) {
   __shared__ IndexHeader h;
   if (threadIdx.x == 0) h = *hdr;
   __syncthreads();
   if (!h.valid) return;
+  if (h.reuse) {
+    // the index stays: only the crop box has changed -- refresh the in-crop flag of every indexed point and count them
+    int local = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < h.n_cropped; i += gridDim.x * blockDim.x) {
+      float4 p = pts2[i];
+      const bool in = in_crop(p, h);
+      const unsigned int w = (__float_as_uint(p.w) & ~kInCropBit) | (in ? kInCropBit : 0u);
+      if (w != __float_as_uint(p.w)) pts2[i].w = __uint_as_float(w);
+      local += in ? 1 : 0;
+    }
+    local = warp_sum(local);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(&hdr->n_in_crop, local);
+    return;
+  }
   const int ns = scene_hdr->n;
-  int local = 0;
+  int local = 0, local_in = 0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ns; i += gridDim.x * blockDim.x) {
     const float4 p = scene[i];
-    if (!in_crop(p, h)) continue;
+    if (!in_built(p, h)) continue;
     atomicAdd(&cell_count[cell_of(p, h)], 1);
     ++local;
+    local_in += in_crop(p, h) ? 1 : 0;
   }
   local = warp_sum(local);
-  if ((threadIdx.x & 31) == 0 && local) atomicAdd(&hdr->n_cropped, local);
+  local_in = warp_sum(local_in);
+  if ((threadIdx.x & 31) == 0 && local) { atomicAdd(&hdr->n_cropped, local); atomicAdd(&hdr->n_in_crop, local_in); }
 }
 
 // exclusive prefix of the cell counts -> cell_start; the counters are cleared again (they become the fill cursors)
 __global__ void __launch_bounds__(1024) index_scan_kernel(const IndexHeader* __restrict__ hdr, int* cell_count, int* __restrict__ cell_start,
-                                                          TrackerState* st, float4* __restrict__ pts, float4* __restrict__ pts2) {
+                                                          TrackerState* st, float4* __restrict__ pts, float4* __restrict__ pts2, IndexHeader* hdr_prev) {
   __shared__ int smem[34];
   const int nc = hdr->n_cells;
-  if (threadIdx.x == 0) { st->nn_sum_um = 0ull; st->nn_count = 0ull; }  // consumed by index_begin; refilled by the weight kernel
+  if (threadIdx.x == 0) {
+    st->nn_sum_um = 0ull; st->nn_count = 0ull;  // consumed by index_begin; refilled by the weight kernel
+    *hdr_prev = *hdr;  // what the next weight() of the frame tests its crop box against (the point counts are final by now)
+    st->lists_on = (hdr->use_lists && hdr->n_cropped < 65535) ? 1 : 0;  // (= lists_on(*hdr))
+  }
+  if (hdr->reuse) return;
   const int total = block_exclusive_scan<int>(
       nc, [&](int i) { return cell_count[i]; }, [&](int i, int ex) { cell_start[i] = ex; cell_count[i] = 0; }, smem);
   if (threadIdx.x == 0) {
@@ -481,17 +567,17 @@ __global__ void index_scatter_kernel(const float4* __restrict__ scene, const Clo
   __shared__ IndexHeader h;
   if (threadIdx.x == 0) h = *hdr;
   __syncthreads();
-  if (!h.valid) return;
+  if (!h.valid || h.reuse) return;
   const int ns = scene_hdr->n;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ns; i += gridDim.x * blockDim.x) {
     const float4 p = scene[i];
-    if (!in_crop(p, h)) continue;
+    if (!in_built(p, h)) continue;
     const int c = cell_of(p, h);
     const int pos = cell_start[c] + atomicAdd(&cell_count[c], 1);
     pts[pos] = make_float4(p.x, p.y, p.z, __int_as_float(i));  // .w = index in the input cloud (tie-break key)
     const unsigned int packed = rgba_to_hsv_packed(__float_as_uint(p.w));
     hsv[pos] = packed;
-    pts2[pos] = make_float4(p.x, p.y, p.z, __uint_as_float(packed));
+    pts2[pos] = make_float4(p.x, p.y, p.z, __uint_as_float(packed | (in_crop(p, h) ? kInCropBit : 0u)));
   }
 }
 
@@ -525,8 +611,10 @@ struct NNResult {
 };
 __device__ __forceinline__ NNResult nn_none(float lim2) { return NNResult{lim2, (int)0x80000000, -1}; }  // only d2 < lim2 can beat it
 
-__device__ __forceinline__ void nn_eval(const float4* __restrict__ pts, int slot, float qx, float qy, float qz, NNResult& best) {
+__device__ __forceinline__ void nn_eval(const IndexHeader& h, const float4* __restrict__ pts, int slot, float qx, float qy, float qz, NNResult& best) {
   const float4 p = pts[slot];
+  // (the index may hold points beyond the crop box of this weight(), see IndexHeader::built: they are not candidates)
+  if (!(p.x >= h.aabb[0] && p.x <= h.aabb[3] && p.y >= h.aabb[1] && p.y <= h.aabb[4] && p.z >= h.aabb[2] && p.z <= h.aabb[5])) return;
   const float dx = qx - p.x, dy = qy - p.y, dz = qz - p.z;
   const float d2 = (dx * dx + dy * dy) + dz * dz;
   const int orig = __float_as_int(p.w);
@@ -571,7 +659,7 @@ __device__ __noinline__ NNResult nn_search_shells(const CS* __restrict__ cs, con
           xa = max(xa, 0); xb = min(xb, h.dim[0] - 1);
           if (xa > xb) continue;
           const int s1 = (int)cs[base + xb + 1];
-          for (int s = (int)cs[base + xa]; s < s1; ++s) nn_eval(pts, s, qx, qy, qz, best);
+          for (int s = (int)cs[base + xa]; s < s1; ++s) nn_eval(h, pts, s, qx, qy, qz, best);
         }
       }
     }
@@ -615,7 +703,7 @@ __device__ __forceinline__ NNResult nn_search(const CS* __restrict__ cs, const f
     PFT_STAT(8, 1);
     const int base = (z * dimy + y) * dimx;
     const int s1 = (int)cs[base + xb + 1];
-    for (int s = (int)cs[base + xa]; s < s1; ++s) { PFT_STAT(9, 1); nn_eval(pts, s, qx, qy, qz, best); }
+    for (int s = (int)cs[base + xa]; s < s1; ++s) { PFT_STAT(9, 1); nn_eval(h, pts, s, qx, qy, qz, best); }
   }
   // rows outside the table start at a distance of kRT cells: only then can the search have missed something
   if (best.d2() > (float)(kRT * kRT) * cell2 * 0.99f) best = nn_search_shells<CS>(cs, pts, h, qx, qy, qz, cx, cy, cz, tx, ty, tz, lim2, best);
@@ -672,18 +760,25 @@ __device__ __forceinline__ float box_maxdist2(const float* lo, const float* hi, 
 // remembers the cells it has flagged in a bitmap of the fine grid in shared memory (f_cells bits, dynamic): every
 // block stores every cell at most once.
 constexpr int kMarkUnroll = 4;
-constexpr unsigned int kCoarseBelow = 24u;  // queries of a cell below which its list is not split into octants
+#ifndef PFT_COARSE_BELOW
+#define PFT_COARSE_BELOW 24
+#endif
+constexpr unsigned int kCoarseBelow = PFT_COARSE_BELOW;  // queries of a cell below which its list is not split into octants
 template <bool COUNT>
 __global__ void __launch_bounds__(256) cand_mark_kernel(const TrackerState* __restrict__ st, const IndexHeader* __restrict__ hdr, const float4* __restrict__ model, int M,
-                                                        const float* __restrict__ mats, unsigned int* __restrict__ needed, int nranks, int rank) {
+                                                        const float* __restrict__ mats, unsigned int* __restrict__ needed, int nranks, int rank,
+                                                        const unsigned int* __restrict__ built_bits) {
   extern __shared__ unsigned int s_bits[];  // (f_cells + 31) / 32 words
   __shared__ IndexHeader h;
   if (threadIdx.x == 0) h = *hdr;
   __syncthreads();
   if (!h.valid || !lists_on(h)) return;
-  if (!COUNT) {
+  // one bit per fine cell: "nothing to do for this cell" -- its lists exist already (a weight() that reuses the index of
+  // the frame), or (flag mode) this block has flagged it
+  const bool use_bits = !COUNT || h.reuse;
+  if (use_bits) {
     const int words = (h.f_cells + 31) >> 5;
-    for (int i = threadIdx.x; i < words; i += blockDim.x) s_bits[i] = 0u;
+    for (int i = threadIdx.x; i < words; i += blockDim.x) s_bits[i] = h.reuse ? built_bits[i] : 0u;
     __syncthreads();
   }
   const int n = st->particle_num;
@@ -716,7 +811,7 @@ __global__ void __launch_bounds__(256) cand_mark_kernel(const TrackerState* __re
           if ((unsigned)ix < (unsigned)fdx && (unsigned)iy < (unsigned)fdy && (unsigned)iz < (unsigned)fdz) {
             const int c = (iz * fdy + iy) * fdx + ix;
             if (COUNT) {
-              atomicAdd(&needed[c], 1u);  // (no return value: a reduction at the L2, nothing comes back)
+              if (!use_bits || !((s_bits[c >> 5] >> (c & 31)) & 1u)) atomicAdd(&needed[c], 1u);  // (no return value: a reduction at the L2, nothing comes back)
             } else {
               const unsigned int bit = 1u << (c & 31);
               if (!(s_bits[c >> 5] & bit)) {  // (cheap pre-test; the atomic decides)
@@ -750,7 +845,10 @@ __global__ void __launch_bounds__(256) cand_collect_kernel(const IndexHeader* __
 #pragma unroll
       for (int sub = 0; sub < 8; ++sub) {
         const int fx = 2 * bx + (sub & 1), fy = 2 * by + ((sub >> 1) & 1), fz = 2 * bz + (sub >> 2);
-        if (fx < fdx && fy < fdy && fz < fdz && needed[(fz * fdy + fy) * fdx + fx] != 0u) any = true;
+        if (fx < fdx && fy < fdy && fz < fdz) {
+          const int c = (fz * fdy + fy) * fdx + fx;
+          if (needed[c] != 0u) any = true;
+        }
       }
     }
     const unsigned int bal = __ballot_sync(kFull, any);
@@ -883,7 +981,7 @@ __device__ __forceinline__ void build_cell_direct(const IndexHeader& h, const in
                                                   unsigned short* s_list /* [kListKX] shared */, float4* s_pt4 /* [kListKX] shared */,
                                                   unsigned long long* s_key /* [kListKX] shared */, unsigned long long* s_key2 /* [kListKX] shared */,
                                                   const unsigned int* __restrict__ needed,
-                                                  int2* __restrict__ cell_items, unsigned short* __restrict__ l1_slots) {
+                                                  int2* __restrict__ cell_items, unsigned short* __restrict__ l1_slots, unsigned int* __restrict__ built_bits) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int fdx = h.f_dim[0], fdy = h.f_dim[1];
   const float cell_m = h.cell;
@@ -900,6 +998,11 @@ __device__ __forceinline__ void build_cell_direct(const IndexHeader& h, const in
     a = max((int)floorf(((lo[d] - r) * h.inv_leaf) * h.level_scale) - h.origin[d], 0);
     b = min((int)floorf(((hi[d] + r) * h.inv_leaf) * h.level_scale) - h.origin[d], h.dim[d] - 1);
   };
+  // (one index per frame: see cand_build_kernel) far from the faces of the crop box the list is built from all points
+  // and serves every weight() of the frame; near them it is built from the cropped points, for this weight() only
+  const bool dilated = h.dilate > 0.f;
+  bool crop_only = false, indep = true;
+retry:
   // ---- (1) U: probe the box dilated by a growing radius until it holds a point
   float U2 = 3.0e38f;
   int p0_slot = -1;
@@ -915,7 +1018,7 @@ __device__ __forceinline__ void build_cell_direct(const IndexHeader& h, const in
       block_points_of_rows(
           ny * (z1 - z0 + 1), pref, start,
           [&](int r) { const int zz = r / ny; const int base = ((z0 + zz) * dimy + (y0 + r - zz * ny)) * dimx; const int a = cs[base + x0]; return RowSpan{a, cs[base + x1 + 1] - a}; },
-          [&](int s) { const float v = box_maxdist2(lo, hi, pts[s]); if (v < m2 || (v == m2 && s > ms)) { m2 = v; ms = s; } });
+          [&](int s) { const float4 p = pts[s]; if (crop_only && !in_crop(p, h)) return; const float v = box_maxdist2(lo, hi, p); if (v < m2 || (v == m2 && s > ms)) { m2 = v; ms = s; } });
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
         const float om = __shfl_xor_sync(kFull, m2, o);
@@ -935,10 +1038,17 @@ __device__ __forceinline__ void build_cell_direct(const IndexHeader& h, const in
     // provably no point within maximum_distance_ of any query of the cell (empty lists), or the probe gave up (the
     // queries of this cell are answered by brute force)
     if (threadIdx.x < 32) write_octant_codes(h, flists, fx, fy, fz, no_match ? 0u : kListOverflow, 0, 0);
+    if (!crop_only && threadIdx.x == 0) atomicOr(&built_bits[cell >> 5], 1u << (cell & 31));  // (found among all points: holds for every crop box)
     return;
   }
   U2 = fminf(U2, r_max * r_max);
   const float reach = sqrtf(U2) * 1.00001f;
+  if (dilated && !crop_only) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+      indep = indep && lo[d] - reach >= h.aabb[d] + h.dilate && hi[d] + reach <= h.aabb[3 + d] - h.dilate;
+    if (!indep) { crop_only = true; __syncthreads(); goto retry; }
+  }
   // Second, sharper filter: the nearest neighbour p* of a query q of the cell satisfies |q - p*| <= |q - p0| for the
   // reference point p0 found above, i.e. q lies on p*'s side of the bisector plane of (p*, p0) (see can_win).
   float bc[3], bh[3];
@@ -972,6 +1082,7 @@ __device__ __forceinline__ void build_cell_direct(const IndexHeader& h, const in
       },
       [&](int s) {
         const float4 p = pts[s];
+        if (crop_only && !in_crop(p, h)) return;
         if (box_mindist2(lo, hi, p) <= U2 && can_win(p, p0, bc, bh)) {
           const int pos = atomicAdd(s_cnt, 1);
           if (pos < kListKX) s_list[pos] = (unsigned short)s;
@@ -1001,31 +1112,46 @@ __device__ __forceinline__ void build_cell_direct(const IndexHeader& h, const in
   }
   if (threadIdx.x == 0) *s_cnt = 0;
   __syncthreads();
-  block_bitonic_sort(s_key, n2);
+  unsigned long long* s_sorted = s_key;   // the keys in ascending order
+  unsigned long long* s_out = s_key2;     // the survivors' keys
+  if (n <= 512) {
+    // rank by counting (the keys are distinct): no barrier per step, cheaper than the bitonic network at these sizes
+    for (int t = threadIdx.x; t < n; t += blockDim.x) {
+      const unsigned long long my = s_key[t];
+      int r = 0;
+      for (int k = 0; k < n; ++k) r += s_key[k] < my ? 1 : 0;
+      s_key2[r] = my;
+    }
+    __syncthreads();
+    s_sorted = s_key2; s_out = s_key;
+  } else {
+    block_bitonic_sort(s_key, n2);
+  }
   for (int r0 = 0; r0 < n; r0 += blockDim.x) {
     const int r = r0 + threadIdx.x;
     if (r < n) {
-      const int t = (int)(s_key[r] & 0xffffffffull);
+      const int t = (int)(s_sorted[r] & 0xffffffffull);
       const float4 p = s_pt4[t];
       const float pn = (p.x * p.x + p.y * p.y) + p.z * p.z;
       bool alive = true;
       for (int k = 0; k < r; ++k) {
-        const float4 c = s_pt4[(int)(s_key[k] & 0xffffffffull)];
+        const float4 c = s_pt4[(int)(s_sorted[k] & 0xffffffffull)];
         const float cn = (c.x * c.x + c.y * c.y) + c.z * c.z;
         // min over the cube of |q-p|^2 - |q-c|^2: positive (beyond the rounding slack) = c is nearer everywhere
         const float fmin = (pn - cn) - 2.0f * (ch * ((fabsf(p.x - c.x) + fabsf(p.y - c.y)) + fabsf(p.z - c.z)));
         if (fmin > 1.0e-6f * (pn + cn) + 1.0e-9f) { alive = false; break; }
       }
       // key = input index (upper half: the order of the extended list) | position in s_list
-      if (alive) s_key2[atomicAdd(s_cnt, 1)] = ((unsigned long long)(unsigned int)__float_as_int(p.w) << 32) | (unsigned long long)t;
+      if (alive) s_out[atomicAdd(s_cnt, 1)] = ((unsigned long long)(unsigned int)__float_as_int(p.w) << 32) | (unsigned long long)t;
     }
   }
   __syncthreads();
   const int m = *s_cnt;
   PFT_STAT(11, threadIdx.x == 0 ? 1 : 0);
+  if (indep && threadIdx.x == 0) atomicOr(&built_bits[cell >> 5], 1u << (cell & 31));  // (the next weight() of the frame need not build it again)
   if (m <= kL1Cap) {
     // a normal cell after all: its list goes to cand_octant_kernel like those of cand_build_kernel
-    if ((int)threadIdx.x < m) l1_slots[(size_t)cell * kL1Cap + threadIdx.x] = s_list[(int)(s_key2[threadIdx.x] & 0xffffffffull)];
+    if ((int)threadIdx.x < m) l1_slots[(size_t)cell * kL1Cap + threadIdx.x] = s_list[(int)(s_out[threadIdx.x] & 0xffffffffull)];
     if (threadIdx.x == 0) {
       const int item = cell | (m << 24) | (needed[cell] < kCoarseBelow ? (int)0x80000000 : 0);
       const int xyz = (fx < 1024 && fy < 1024 && fz < 1024) ? (fx | (fy << 10) | (fz << 20)) : -1;
@@ -1036,10 +1162,10 @@ __device__ __forceinline__ void build_cell_direct(const IndexHeader& h, const in
   // still long: an extended list in ascending order of the input index, scanned entry by entry by the queries of the cell
   int m2 = 1;
   while (m2 < m) m2 <<= 1;
-  for (int t = m + threadIdx.x; t < m2; t += blockDim.x) s_key2[t] = ~0ull;
+  for (int t = m + threadIdx.x; t < m2; t += blockDim.x) s_out[t] = ~0ull;
   __syncthreads();
-  block_bitonic_sort(s_key2, m2);
-  s_key = s_key2;
+  block_bitonic_sort(s_out, m2);
+  s_key = s_out;
   if (threadIdx.x == 0) *s_xi = atomicAdd(&list_counters[0], 1);
   __syncthreads();
   const int xi = *s_xi;
@@ -1061,7 +1187,7 @@ __global__ void __launch_bounds__(256) cand_build_kernel(const IndexHeader* __re
                                                          const unsigned int* __restrict__ needed, const int* __restrict__ needed_list,
                                                          int* __restrict__ list_counters,
                                                          int* __restrict__ far_list, int2* __restrict__ cell_items,
-                                                         unsigned short* __restrict__ l1_slots) {
+                                                         unsigned short* __restrict__ l1_slots, unsigned int* __restrict__ built_bits) {
   __shared__ IndexHeader h;
   __shared__ int s_cnt[8];
   __shared__ int s_pref[8][33], s_start[8][32];
@@ -1094,13 +1220,16 @@ __global__ void __launch_bounds__(256) cand_build_kernel(const IndexHeader* __re
     lo[1] = (float)(h.f_origin[1] + 2 * by) * leaf - margin; hi[1] = (float)(h.f_origin[1] + 2 * by + 2) * leaf + margin;
     lo[2] = (float)(h.f_origin[2] + 2 * bz) * leaf - margin; hi[2] = (float)(h.f_origin[2] + 2 * bz + 2) * leaf + margin;
     // every fine cell of the block gets `value` (used when the whole block is decided at once)
-    auto set_all = [&](unsigned int value) {
+    auto set_all = [&](unsigned int value, bool reusable) {
       for (int sub = 0; sub < 8; ++sub) {
         const int fx = 2 * bx + (sub & 1), fy = 2 * by + ((sub >> 1) & 1), fz = 2 * bz + (sub >> 2);
         if (fx < fdx && fy < fdy && fz < fdz) {
           const int c = (fz * fdy + fy) * fdx + fx;
           // every octant: header + dummy slots (value 0 = empty list: nothing within maximum_distance_)
-          if (needed[c]) write_octant_codes(h, flists, fx, fy, fz, value, 0, 0);
+          if (needed[c]) {
+            write_octant_codes(h, flists, fx, fy, fz, value, 0, 0);
+            if (reusable && lane == 0) atomicOr(&built_bits[c >> 5], 1u << (c & 31));
+          }
         }
       }
     };
@@ -1110,6 +1239,13 @@ __global__ void __launch_bounds__(256) cand_build_kernel(const IndexHeader* __re
       a = max((int)floorf(((lo[d] - r) * h.inv_leaf) * h.level_scale) - h.origin[d], 0);
       b = min((int)floorf(((hi[d] + r) * h.inv_leaf) * h.level_scale) - h.origin[d], h.dim[d] - 1);
     };
+    // One index per frame (IndexHeader::built): when the index holds more than the crop box, a block whose lists cannot
+    // depend on where the faces of the crop box are -- every point that matters lies well inside it -- is built from all
+    // points and marked as built for the later weight() calls of the frame; a block near the faces is built from the
+    // cropped points only (exact for THIS weight(), rebuilt by the next).
+    const bool dilated = h.dilate > 0.f;
+    bool crop_only = false, indep = true;
+  retry:
     // ---- (1) U_B = min over points of maxdist(block, p): probe the block dilated by a growing radius until it holds a point
     float U2 = 3.0e38f;
     int p0_slot = -1;
@@ -1125,7 +1261,7 @@ __global__ void __launch_bounds__(256) cand_build_kernel(const IndexHeader* __re
         warp_points_of_rows(
             ny * (z1 - z0 + 1), pref, start,
             [&](int r) { const int zz = r / ny; const int base = ((z0 + zz) * dimy + (y0 + r - zz * ny)) * dimx; const int a = cs[base + x0]; return RowSpan{a, cs[base + x1 + 1] - a}; },
-            [&](int s) { const float v = box_maxdist2(lo, hi, pts[s]); if (v < m2) { m2 = v; ms = s; } });
+            [&](int s) { const float4 p = pts[s]; if (crop_only && !in_crop(p, h)) return; const float v = box_maxdist2(lo, hi, p); if (v < m2) { m2 = v; ms = s; } });
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
           const float om = __shfl_xor_sync(kFull, m2, o);
@@ -1138,12 +1274,20 @@ __global__ void __launch_bounds__(256) cand_build_kernel(const IndexHeader* __re
     }
     if (U2 >= 3.0e38f) {
       // provably no point within maximum_distance_ of any query of the block (empty lists), or the probe gave up
-      // (the queries of the block use the row-table search)
-      set_all(no_match ? 0u : kListOverflow);
+      // (the queries of the block are answered by brute force).  Found among ALL points, it holds for every crop box.
+      set_all(no_match ? 0u : kListOverflow, !crop_only);
       continue;
     }
     U2 = fminf(U2, r_max * r_max);
     const float reach = sqrtf(U2) * 1.00001f;
+    if (dilated && !crop_only) {
+      // every point the lists of this block can depend on lies within `reach` of it: inside the crop box shrunk by the
+      // dilation margin on every side, they are the same whatever the next crop box of the frame is
+#pragma unroll
+      for (int d = 0; d < 3; ++d)
+        indep = indep && lo[d] - reach >= h.aabb[d] + h.dilate && hi[d] + reach <= h.aabb[3 + d] - h.dilate;
+      if (!indep) { crop_only = true; goto retry; }
+    }
     float bc[3], bh[3];
 #pragma unroll
     for (int d = 0; d < 3; ++d) { bc[d] = 0.5f * (lo[d] + hi[d]); bh[d] = 0.5f * (hi[d] - lo[d]); }
@@ -1174,6 +1318,7 @@ __global__ void __launch_bounds__(256) cand_build_kernel(const IndexHeader* __re
         },
         [&](int s) {
           const float4 p = pts[s];
+          if (crop_only && !in_crop(p, h)) return;
           if (box_mindist2(lo, hi, p) <= U2 && can_win(p, p0, bc, bh)) {
             const int pos = atomicAdd(&s_cnt[wib], 1);
             if (pos < kSuperCap) { spt[pos] = p; sslot[pos] = (unsigned short)s; }
@@ -1263,6 +1408,7 @@ __global__ void __launch_bounds__(256) cand_build_kernel(const IndexHeader* __re
         my_item = cell | (n << 24) | (needed[cell] < kCoarseBelow ? (int)0x80000000 : 0);
         my_xyz = (fx < 1024 && fy < 1024 && fz < 1024) ? (fx | (fy << 10) | (fz << 20)) : -1;
         my_valid = true;
+        if (indep) atomicOr(&built_bits[cell >> 5], 1u << (cell & 31));  // (the next weight() of the frame need not build it again)
       }
       PFT_STAT(15, lane == 0 ? 1 : 0);
     }
@@ -1499,7 +1645,7 @@ __global__ void __launch_bounds__(256) cand_build_far_kernel(const IndexHeader* 
                                                              unsigned int* __restrict__ flists, unsigned int* __restrict__ xlists,
                                                              int* __restrict__ list_counters, const int* __restrict__ far_list,
                                                              const unsigned int* __restrict__ needed, int2* __restrict__ cell_items,
-                                                             unsigned short* __restrict__ l1_slots) {
+                                                             unsigned short* __restrict__ l1_slots, unsigned int* __restrict__ built_bits) {
   __shared__ IndexHeader h;
   __shared__ int s_cnt, s_xi;
   __shared__ int s_pref[34], s_start[32], s_ms[8];
@@ -1516,7 +1662,7 @@ __global__ void __launch_bounds__(256) cand_build_far_kernel(const IndexHeader* 
   const float r_max = max_d2 >= 1.0e30 ? 1.0e15f : (float)sqrt(max_d2) * 1.00001f;
   for (int idx = blockIdx.x; idx < n_far; idx += gridDim.x) {
     build_cell_direct(h, cs, pts, far_list[idx], leaf, margin, r_max, flists, xlists, list_counters, s_pref, s_start, &s_cnt, s_m2, s_ms, &s_xi, s_list, s_pt4, s_key, s_key2,
-                      needed, cell_items, l1_slots);
+                      needed, cell_items, l1_slots, built_bits);
     __syncthreads();
   }
   PFT_TRACE_MAX(2);
@@ -1544,6 +1690,9 @@ struct WeightArgs {
   int dbg_k; int* dbg_idx; float* dbg_d2;
   int smem_bytes;             // dynamic shared memory available for staging the index
   int lists_kernel_ran;       // weight_lists_kernel precedes weight_kernel in the stream: whichever does not apply returns at once
+  int fallback_follows;       // weight_kernel follows weight_lists_kernel (0: the host expects the lists to be on and launches weight_lists_kernel
+                              // alone -- should they be off after all, it answers every query by brute force: slow, exact, and the host learns it
+                              // with the next state read-back)
 };
 
 // One (particle, model chunk) item by one warp: transform, nearest neighbour, coherence, warp reduction.
@@ -1702,20 +1851,23 @@ __global__ void __launch_bounds__(THREADS, 1) weight_kernel(const WeightArgs a) 
 // answered one at a time by the whole warp (nn_slow_warp), bit-identical to the brute-force search.
 struct SlowNN { float d2; int slot; };
 
-// One query by a whole warp, brute force: every lane scans a 32nd of the indexed points, lexicographic (distance,
-// input index) minimum across the lanes.  Returns the winner to all lanes (slot -1: none
-// nearer than lim2).
-__device__ __noinline__ SlowNN nn_slow_warp(const float4* __restrict__ pts /* {x,y,z,input index}, global */, int n, float qx, float qy, float qz, float lim2) {
+// One query by a whole warp, brute force: every lane scans a 32nd of the indexed points that lie inside the crop box
+// (the staged copy carries the flag), lexicographic (distance, input index) minimum across the lanes; the input index
+// of a point is only fetched (from the global copy) to settle a tie or to compare the lanes' winners.
+__device__ __noinline__ SlowNN nn_slow_warp(const unsigned char* __restrict__ sbase /* staged points {x,y,z,HSV|flag} */,
+                                            const float4* __restrict__ pts /* {x,y,z,input index}, global */, int n, float qx, float qy, float qz, float lim2) {
   const int lane = threadIdx.x & 31;
   float bd = lim2;
-  int bo = 0x7fffffff, bs = -1;
+  int bs = -1;
   for (int slot = lane; slot < n; slot += 32) {
-    const float4 p = pts[slot];
+    const float4 p = *reinterpret_cast<const float4*>(sbase + ((size_t)slot << 4));
+    if (!(__float_as_uint(p.w) & kInCropBit)) continue;
     const float dx = qx - p.x, dy = qy - p.y, dz = qz - p.z;
     const float d2 = (dx * dx + dy * dy) + dz * dz;
-    const int orig = __float_as_int(p.w);
-    if (d2 < bd || (d2 == bd && bs >= 0 && orig < bo)) { bd = d2; bo = orig; bs = slot; }
+    if (d2 < bd) { bd = d2; bs = slot; }
+    else if (d2 == bd && bs >= 0 && __float_as_int(pts[slot].w) < __float_as_int(pts[bs].w)) bs = slot;
   }
+  int bo = bs >= 0 ? __float_as_int(pts[bs].w) : 0x7fffffff;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     const float od = __shfl_xor_sync(kFull, bd, o);
@@ -1756,7 +1908,7 @@ struct ListQuery { float x, y, z; unsigned int hsv; Rec8 r; };
 
 template <bool USE_HSV, bool DYN>
 __device__ __forceinline__ void weight_list_items(const WeightArgs& a, const IndexHeader& h, const unsigned char* __restrict__ sbase,
-                                                  const float* __restrict__ lut_h, const float* __restrict__ lut_s) {
+                                                  const float* __restrict__ lut_h, const float* __restrict__ lut_s, bool brute) {
   const int n = a.st->particle_num;
   const int n_local = n > a.rank_id ? (n - a.rank_id + a.nranks - 1) / a.nranks : 0;
   const int items = n_local * a.chunks;
@@ -1802,7 +1954,7 @@ __device__ __forceinline__ void weight_list_items(const WeightArgs& a, const Ind
       // (cvt.rmi saturates: a far-away or non-finite query fails the range test)
       const int ix = __float2int_rd(q.x * inv2) - o2x, iy = __float2int_rd(q.y * inv2) - o2y, iz = __float2int_rd(q.z * inv2) - o2z;
       q.r.w[0] = kListOverflow;
-      if ((unsigned int)ix < d2x && (unsigned int)iy < d2y && (unsigned int)iz < d2z)
+      if (!brute && (unsigned int)ix < d2x && (unsigned int)iy < d2y && (unsigned int)iz < d2z)
         q.r = load_rec8(a.flists + (size_t)(((unsigned int)iz * d2y + (unsigned int)iy) * d2x + (unsigned int)ix) * 8);
       return q;
     };
@@ -1836,15 +1988,23 @@ __device__ __forceinline__ void weight_list_items(const WeightArgs& a, const Ind
           }
         }
       }
-      // queries whose cell has no list at all (the build gave up: extremely rare): brute force, one at a time, by the whole warp
-      unsigned int slow = __ballot_sync(kFull, act && any_pts && hw == kListOverflow);
+      // fourth word of the winner: packed HSV | in-crop flag.  The index may hold points beyond the crop box of this
+      // weight() (one index per frame): a winner inside the box is the nearest CROPPED point; one outside is not an answer
+      unsigned int tb = kInCropBit;
+      if (boff != 0xffffffffu) tb = *reinterpret_cast<const unsigned int*>(sbase + boff + 12);
+      // queries whose winner lies outside the crop box (near its faces), or whose cell has no list at all (the build gave
+      // up: extremely rare): brute force over the cropped points, one query at a time, by the whole warp
+      unsigned int slow = __ballot_sync(kFull, act && any_pts && (hw == kListOverflow || !(tb & kInCropBit)));
       while (slow) {
         const int src = __ffs(slow) - 1;
         slow &= slow - 1u;
         const float sx = __shfl_sync(kFull, q.x, src), sy = __shfl_sync(kFull, q.y, src), sz = __shfl_sync(kFull, q.z, src);
         PFT_STAT(4, lane == 0 ? 1 : 0);
-        const SlowNN r = nn_slow_warp(a.pts, h.n_cropped, sx, sy, sz, lim2);
-        if (lane == src && r.slot >= 0) { best = r.d2; boff = (unsigned int)r.slot << 4; }
+        const SlowNN r = nn_slow_warp(sbase, a.pts, h.n_cropped, sx, sy, sz, lim2);
+        if (lane == src) {
+          best = r.d2; boff = r.slot >= 0 ? (unsigned int)r.slot << 4 : 0xffffffffu;
+          if (r.slot >= 0) tb = *reinterpret_cast<const unsigned int*>(sbase + boff + 12);
+        }
       }
       const bool hit = act && boff != 0xffffffffu;
       if (i < a.dbg_k && act) {
@@ -1864,7 +2024,7 @@ __device__ __forceinline__ void weight_list_items(const WeightArgs& a, const Ind
           den = 1.0 + d * d * a.co.dist_w;
         }
         if (USE_HSV) {
-          const unsigned int sb = q.hsv, tb = *reinterpret_cast<const unsigned int*>(sbase + boff + 12);
+          const unsigned int sb = q.hsv;
           const float sh = lut_h[sb & 0xff], ss = lut_s[(sb >> 8) & 0xff];
           const float th = lut_h[tb & 0xff], ts = lut_s[(tb >> 8) & 0xff];
           const float hd = fabsf(sh - th);
@@ -1931,7 +2091,8 @@ __global__ void __launch_bounds__(THREADS, 1) weight_lists_kernel(const WeightAr
   PFT_TRACE_MIN(3); PFT_TRACE_MAX(4);
   if (threadIdx.x == 0) h = *a.hdr;
   __syncthreads();
-  if (!lists_on(h)) return;  // weight_kernel (row-table search) evaluates this weight()
+  const bool brute = !lists_on(h);
+  if (brute && a.fallback_follows) return;  // weight_kernel (row-table search) evaluates this weight()
   PFT_TRACE_MAX(5);
   const int n_pts = h.n_cropped + 1;  // + the dummy point that pads the lists
   const bool staged = 16ll * n_pts <= (long long)a.smem_bytes;
@@ -1949,10 +2110,10 @@ __global__ void __launch_bounds__(THREADS, 1) weight_lists_kernel(const WeightAr
   if (staged) {
     mbar_wait(&s_bar, 0);
     PFT_TRACE_MAX(6);
-    weight_list_items<USE_HSV, DYN>(a, h, reinterpret_cast<const unsigned char*>(dyn_smem), lut_h, lut_s);
+    weight_list_items<USE_HSV, DYN>(a, h, reinterpret_cast<const unsigned char*>(dyn_smem), lut_h, lut_s, brute);
     PFT_TRACE_MIN(7); PFT_TRACE_MAX(8);
   } else {
-    weight_list_items<USE_HSV, DYN>(a, h, reinterpret_cast<const unsigned char*>(a.pts2), lut_h, lut_s);
+    weight_list_items<USE_HSV, DYN>(a, h, reinterpret_cast<const unsigned char*>(a.pts2), lut_h, lut_s, brute);
   }
 }
 

@@ -26,6 +26,6 @@ for k in range(12):
     v = list(out)
     if k in (1, 5, 11):
         print("frame %d (2 x weight()): list lookups %d, mean count %.2f; with pool groups %d (%.3f%%, mean count %.1f); warp-scanned queries %d (%.3f%% of all), "
-              "of which brute force %d, mean scan length %.0f" % (k, v[12], v[5] / max(v[12], 1), v[3], 100.0 * v[3] / max(v[12], 1), v[6] / max(v[3], 1),
+              "brute-force queries %d, mean extended scan length %.0f" % (k, v[12], v[5] / max(v[12], 1), v[3], 100.0 * v[3] / max(v[12], 1), v[6] / max(v[3], 1),
                                                                    v[13], 100.0 * v[13] / max(v[12] + v[13], 1), v[4], v[14] / max(v[13], 1)))
         print("   build: octant lists %d, mean length %.2f, longer than seven %d; cells built %d, far cells %d (extended %d)" % (v[2], v[1] / max(v[2], 1), v[0], v[15], v[10], v[11]))
