@@ -693,6 +693,8 @@ int weight_phase_eval(pft_tracker* t, bool force_raw = false, bool reuse_allowed
     PFT_LAUNCH_CHECK();
     stage_mark(t, "cand_build_kernel");
     // cells far from the surface (long lists): pairwise pruning, one thread block each; most of them join the octant pass
+    // (measured and dropped: the far pass on a second stream beside the octant pass of the other cells -- it then takes
+    // longer than the octant pass it competes with, and the frame does not get shorter)
     cand_build_far_kernel<<<sm * 4, 256, 0, s>>>(hdr, t->cell_start.as<int>(), t->ipts.as<float4>(), t->max_dist * t->max_dist,
                                                 t->flists.as<unsigned int>(), t->xlists.as<unsigned int>(), t->xcount.as<int>(), t->ffar_list.as<int>(),
                                                 t->fneeded.as<unsigned int>(), t->fcell_items.as<int2>(), t->fl1_slots.as<unsigned short>(), t->fbuilt_bits.as<unsigned int>());

@@ -764,6 +764,7 @@ constexpr int kMarkUnroll = 4;
 #define PFT_COARSE_BELOW 24
 #endif
 constexpr unsigned int kCoarseBelow = PFT_COARSE_BELOW;  // queries of a cell below which its list is not split into octants
+constexpr unsigned int kLightBelow = 256u;               // ... below which a list that fits one record is not split either
 template <bool COUNT>
 __global__ void __launch_bounds__(256) cand_mark_kernel(const TrackerState* __restrict__ st, const IndexHeader* __restrict__ hdr, const float4* __restrict__ model, int M,
                                                         const float* __restrict__ mats, unsigned int* __restrict__ needed, int nranks, int rank,
@@ -1154,7 +1155,7 @@ retry:
     if ((int)threadIdx.x < m) l1_slots[(size_t)cell * kL1Cap + threadIdx.x] = s_list[(int)(s_out[threadIdx.x] & 0xffffffffull)];
     if (threadIdx.x == 0) {
       const int item = cell | (m << 24) | (needed[cell] < kCoarseBelow ? (int)0x80000000 : 0);
-      const int xyz = (fx < 1024 && fy < 1024 && fz < 1024) ? (fx | (fy << 10) | (fz << 20)) : -1;
+      const int xyz = (fx < 1024 && fy < 1024 && fz < 1024) ? (fx | (fy << 10) | (fz << 20) | (needed[cell] < kLightBelow ? (1 << 30) : 0)) : -1;
       cell_items[atomicAdd(&list_counters[4], 1)] = make_int2(item, xyz);
     }
     return;
@@ -1406,7 +1407,7 @@ __global__ void __launch_bounds__(256) cand_build_kernel(const IndexHeader* __re
       if (lane == sub) {
         // item = cell | list length << 24 | (few queries: one list for the whole cell) << 31, and the cell's coordinates
         my_item = cell | (n << 24) | (needed[cell] < kCoarseBelow ? (int)0x80000000 : 0);
-        my_xyz = (fx < 1024 && fy < 1024 && fz < 1024) ? (fx | (fy << 10) | (fz << 20)) : -1;
+        my_xyz = (fx < 1024 && fy < 1024 && fz < 1024) ? (fx | (fy << 10) | (fz << 20) | (needed[cell] < kLightBelow ? (1 << 30) : 0)) : -1;
         my_valid = true;
         if (indep) atomicOr(&built_bits[cell >> 5], 1u << (cell & 31));  // (the next weight() of the frame need not build it again)
       }
@@ -1481,7 +1482,8 @@ __global__ void __launch_bounds__(256) cand_octant_kernel(const IndexHeader* __r
     int n = (item.x >> 24) & 0x7f;
     const bool coarse = item.x < 0;
     int fx, fy, fz;
-    if (item.y >= 0) { fx = item.y & 1023; fy = (item.y >> 10) & 1023; fz = item.y >> 20; }
+    const bool light = item.y >= 0 && ((item.y >> 30) & 1);
+    if (item.y >= 0) { fx = item.y & 1023; fy = (item.y >> 10) & 1023; fz = (item.y >> 20) & 1023; }
     else { fz = cell / (fdx * fdy); const int r2 = cell - fz * fdx * fdy; fy = r2 / fdx; fx = r2 - fy * fdx; }
     bool two = n > 32;
     // ---- the list in ascending order of the input index (rank = how many keys are smaller; keys are distinct)
@@ -1537,8 +1539,10 @@ __global__ void __launch_bounds__(256) cand_octant_kernel(const IndexHeader* __r
     }
     // records of octant o: word index of its first word (the octants form one dense lattice, x fastest)
     auto rec_word = [&](int o) { return (((unsigned int)(2 * fz + (o >> 2)) * d2y + (unsigned int)(2 * fy + ((o >> 1) & 1))) * d2x + (unsigned int)(2 * fx + (o & 1))) * 8u; };
-    if (coarse) {
-      // few queries: the cell's own list in every octant record (entries beyond the seventh in ONE run of pool groups)
+    if (coarse || (light && n <= 7)) {
+      // the cell's own list in every octant record: the cell has few queries (entries beyond the seventh in ONE run of pool
+      // groups), or not many and the list fits one record anyway (a lookup evaluates seven slots whatever the length;
+      // busy cells are still split: shorter lists mean fewer shared-memory wavefronts per lookup)
       unsigned int hw = (unsigned int)n;
       int pg = 0;
       if (n > 7) {

@@ -26,5 +26,9 @@ for r in rows[2:]:
         k += 1
         key = "%s#%d" % (name, k)
     res[key] = {"%s [%s]" % (h, u): v for h, u, v in zip(hdr, units, r) if "__" in h}
+import os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench  # noqa: E402
+res["_source_hash"] = bench.source_hash()  # bench.py only reports the DRAM traffic of a capture taken on the sources it runs
 json.dump(res, open(sys.argv[2], "w"), indent=1)
-print("\n".join("%-40s %s us" % (k, v.get("gpu__time_duration.sum [us]")) for k, v in res.items()))
+print("\n".join("%-40s %s us" % (k, v.get("gpu__time_duration.sum [us]")) for k, v in res.items() if isinstance(v, dict)))
