@@ -20,6 +20,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <fstream>
 #include <memory>
 #include <sstream>
@@ -29,7 +30,27 @@
 
 #include "pft.h"
 
+// Smart pointers: PCL 1.8 hands clouds, coherences and trackers around as boost::shared_ptr, and so does the reference
+// (ref: src/auto_tracking.cpp:199-254).  Define PFT_SHIM_USE_BOOST before including this header to make every Ptr of
+// the shim a boost::shared_ptr (needs <boost/shared_ptr.hpp>); the default is std::shared_ptr.
+#ifdef PFT_SHIM_USE_BOOST
+#include <boost/make_shared.hpp>
+#include <boost/pointer_cast.hpp>
+#include <boost/shared_ptr.hpp>
+#define PFT_SHIM_PTR_NS boost
+#else
+#define PFT_SHIM_PTR_NS std
+#endif
+// Eigen: define PFT_SHIM_USE_EIGEN (with <Eigen/Geometry> included first) to get Eigen::Affine3f from toEigenMatrix();
+// setTrans() takes any affine type with operator()(row, col) either way (Eigen::Affine3f, pft::Affine3f).
+
 namespace pft {
+namespace sp {
+using PFT_SHIM_PTR_NS::shared_ptr;
+using PFT_SHIM_PTR_NS::make_shared;
+using PFT_SHIM_PTR_NS::static_pointer_cast;
+using PFT_SHIM_PTR_NS::dynamic_pointer_cast;
+}  // namespace sp
 
 struct Error : std::runtime_error {
   int code;
@@ -48,7 +69,13 @@ struct Affine3f {
   void translation(float x, float y, float z) { m[12] = x; m[13] = y; m[14] = z; }
   const float* data() const { return m; }
   float* data() { return m; }
+  const Affine3f& matrix() const { return *this; }  // (Eigen: t.matrix().data() is the column-major 4x4)
 };
+#ifdef PFT_SHIM_USE_EIGEN
+typedef Eigen::Affine3f AffineResult;
+#else
+typedef Affine3f AffineResult;
+#endif
 
 // One context (device + stream) per process by default, like the implicit global state of a CPU library.
 class Context {
@@ -86,8 +113,8 @@ static_assert(sizeof(PointXYZRGBA) == 32, "PointXYZRGBA must be the 32-byte PCL 
 template <typename PointT>
 class PointCloud {
  public:
-  typedef std::shared_ptr<PointCloud<PointT>> Ptr;
-  typedef std::shared_ptr<const PointCloud<PointT>> ConstPtr;
+  typedef pft::sp::shared_ptr<PointCloud<PointT>> Ptr;
+  typedef pft::sp::shared_ptr<const PointCloud<PointT>> ConstPtr;
   std::vector<PointT> points;
   uint32_t width = 0, height = 1;
   bool is_dense = true;
@@ -343,9 +370,26 @@ class EuclideanClusterExtraction {
   int min_ = 1, max_ = 2147483647;
 };
 
+// pcl::getTime (pcl/common/time.h; ref: src/auto_tracking.cpp:552, :559): seconds, wall clock
+inline double getTime() {
+  struct timespec ts;
+  clock_gettime(CLOCK_REALTIME, &ts);
+  return (double)ts.tv_sec + 1.0e-9 * (double)ts.tv_nsec;
+}
+
 namespace search {
 // pcl::search::Octree(resolution) (ref :250): the cell size of the uniform-grid index
-template <typename PointT> struct Octree { explicit Octree(double r) : resolution(r) {} double resolution; };
+template <typename PointT> struct Octree {
+  typedef pft::sp::shared_ptr<Octree<PointT>> Ptr;
+  explicit Octree(double r) : resolution(r) {}
+  double resolution;
+};
+// pcl::search::KdTree (ref :155-156, :183): only constructed by the reference (normals are off, ref :233)
+template <typename PointT> struct KdTree {
+  typedef pft::sp::shared_ptr<KdTree<PointT>> Ptr;
+  explicit KdTree(bool sorted = true) : sorted_results(sorted) {}
+  bool sorted_results;
+};
 }  // namespace search
 
 namespace tracking {
@@ -354,55 +398,77 @@ namespace tracking {
 struct ParticleXYZRPY {
   float x = 0.f, y = 0.f, z = 0.f, one = 1.f, roll = 0.f, pitch = 0.f, yaw = 0.f, weight = 0.f;
   // ParticleXYZRPY::toEigenMatrix (ref :310), evaluated by the same device routine weight() uses
-  pft::Affine3f toEigenMatrix() const {
+  pft::AffineResult toEigenMatrix() const {
     float m12[12];
     pft::check(pft_particle_to_matrix(pft::Context::Default()->get(), reinterpret_cast<const pft_particle*>(this), m12));
-    pft::Affine3f a;
+    pft::AffineResult a = pft::AffineResult::Identity();
     for (int r = 0; r < 3; ++r) for (int c = 0; c < 4; ++c) a(r, c) = m12[r * 4 + c];
     return a;
   }
 };
 static_assert(sizeof(ParticleXYZRPY) == sizeof(pft_particle), "particle layout");
 
-template <typename PointT> struct PointCoherence { virtual ~PointCoherence() {} };
+template <typename PointT> struct PointCoherence {
+  typedef pft::sp::shared_ptr<PointCoherence<PointT>> Ptr;
+  virtual ~PointCoherence() {}
+};
 // pcl::tracking::DistanceCoherence (ref :240-242)
 template <typename PointT> struct DistanceCoherence : PointCoherence<PointT> {
+  typedef pft::sp::shared_ptr<DistanceCoherence<PointT>> Ptr;
   void setWeight(double w) { weight = w; }
   double weight = 1.0;
 };
 // pcl::tracking::HSVColorCoherence (ref :244-247)
 template <typename PointT> struct HSVColorCoherence : PointCoherence<PointT> {
+  typedef pft::sp::shared_ptr<HSVColorCoherence<PointT>> Ptr;
   void setWeight(double w) { weight = w; }
   void setHWeight(double w) { h_weight = w; }
   void setSWeight(double w) { s_weight = w; }
   void setVWeight(double w) { v_weight = w; }
   double weight = 1.0, h_weight = 1.0, s_weight = 1.0, v_weight = 0.0;
 };
-// pcl::tracking::NearestPairPointCloudCoherence / ApproxNearestPairPointCloudCoherence (ref :235-238)
-template <typename PointT> struct NearestPairPointCloudCoherence {
-  typedef std::shared_ptr<NearestPairPointCloudCoherence<PointT>> Ptr;
-  void addPointCoherence(const std::shared_ptr<PointCoherence<PointT>>& c) { point_coherences.push_back(c); }
-  void setSearchMethod(const std::shared_ptr<pcl::search::Octree<PointT>>& s) { resolution = s->resolution; }
-  void setMaximumDistance(double d) { maximum_distance = d; }
-  std::vector<std::shared_ptr<PointCoherence<PointT>>> point_coherences;
+// pcl::tracking::PointCloudCoherence: what ParticleFilterTracker::setCloudCoherence takes (CoherencePtr, ref :154, :254)
+template <typename PointT> struct PointCloudCoherence {
+  typedef pft::sp::shared_ptr<PointCloudCoherence<PointT>> Ptr;
+  typedef typename PointCoherence<PointT>::Ptr PointCoherencePtr;
+  virtual ~PointCloudCoherence() {}
+  void addPointCoherence(const PointCoherencePtr& c) { point_coherences.push_back(c); }          // ref :242, :247
+  std::vector<PointCoherencePtr> point_coherences;
   double resolution = 0.01, maximum_distance = 1.79769313486231570815e308;
   bool pcl_approximate_search = false;
+};
+// pcl::tracking::NearestPairPointCloudCoherence / ApproxNearestPairPointCloudCoherence (ref :235-238)
+template <typename PointT> struct NearestPairPointCloudCoherence : PointCloudCoherence<PointT> {
+  typedef pft::sp::shared_ptr<NearestPairPointCloudCoherence<PointT>> Ptr;
+  void setSearchMethod(const typename pcl::search::Octree<PointT>::Ptr& s) { this->resolution = s->resolution; }  // ref :252
+  void setMaximumDistance(double d) { this->maximum_distance = d; }                                              // ref :253
 };
 // Both classes run the exact search unless setPclApproximateSearch(true) asks for the parity mode that reproduces
 // upstream's greedy approxNearestSearch (PFT_NN_PCL_APPROX: same misses as PCL, far slower).
 template <typename PointT> struct ApproxNearestPairPointCloudCoherence : NearestPairPointCloudCoherence<PointT> {
+  typedef pft::sp::shared_ptr<ApproxNearestPairPointCloudCoherence<PointT>> Ptr;
   void setPclApproximateSearch(bool on) { this->pcl_approximate_search = on; }
 };
 
-// pcl::tracking::ParticleFilterOMPTracker (ref :201-206)
+// pcl::tracking::ParticleFilterTracker: the type the reference declares its trackers with
+// (`typedef ParticleFilterTracker<RefPointType, ParticleT> ParticleFilter`, `boost::shared_ptr<ParticleFilter> tracker_`,
+// ref: src/auto_tracking.cpp:153, :199) -- everything it calls through that pointer lives here (ref :225-254, :673-693,
+// :270, :309).  Constructed directly it is the fixed-size tracker (as upstream's base class is).
 template <typename PointT, typename StateT>
-class ParticleFilterOMPTracker {
+class ParticleFilterTracker {
  public:
-  typedef std::shared_ptr<PointCloud<StateT>> PointCloudStatePtr;
-  explicit ParticleFilterOMPTracker(unsigned int nr_threads = 0) : ParticleFilterOMPTracker(nr_threads, 0) {}
-  virtual ~ParticleFilterOMPTracker() { pft_tracker_destroy(h_); }
-  void setNumberOfThreads(unsigned int n) { si(PFT_THREADS, (int)n); }
-  void setTrans(const pft::Affine3f& t) {  // ref :225, :674
+  typedef typename PointCloud<PointT>::Ptr PointCloudInPtr;
+  typedef typename PointCloud<PointT>::ConstPtr PointCloudInConstPtr;
+  typedef pft::sp::shared_ptr<PointCloud<StateT>> PointCloudStatePtr;
+  typedef PointCloudCoherence<PointT> CloudCoherence;
+  typedef typename CloudCoherence::Ptr CloudCoherencePtr;
+  typedef CloudCoherencePtr CoherencePtr;                                                         // ref :154
+  ParticleFilterTracker() : ParticleFilterTracker(0, 0) {}
+  virtual ~ParticleFilterTracker() { pft_tracker_destroy(h_); }
+  ParticleFilterTracker(const ParticleFilterTracker&) = delete;
+  ParticleFilterTracker& operator=(const ParticleFilterTracker&) = delete;
+  // any affine type with operator()(row, col): Eigen::Affine3f (ref :225, :674), pft::Affine3f
+  template <typename AffineT> void setTrans(const AffineT& t) {
     float m12[12];
     for (int r = 0; r < 3; ++r) for (int c = 0; c < 4; ++c) m12[r * 4 + c] = t(r, c);
     pft::check(pft_tracker_set_trans(h_, m12));
@@ -422,7 +488,7 @@ class ParticleFilterOMPTracker {
   void setResolutionOfChangeDetection(double r) { sd(PFT_CHANGE_DETECTOR_RESOLUTION, r); }
   void setAlpha(double a) { sd(PFT_ALPHA, a); }
   void setMotionRatio(double r) { sd(PFT_MOTION_RATIO, r); }
-  void setCloudCoherence(const typename NearestPairPointCloudCoherence<PointT>::Ptr& c) {         // ref :254
+  void setCloudCoherence(const CloudCoherencePtr& c) {                                            // ref :254
     int use_d = 0, use_h = 0;
     for (auto& pc : c->point_coherences) {
       if (auto* d = dynamic_cast<DistanceCoherence<PointT>*>(pc.get())) { use_d = 1; sd(PFT_DIST_WEIGHT, d->weight); }
@@ -434,15 +500,13 @@ class ParticleFilterOMPTracker {
     sd(PFT_MAX_DIST, c->maximum_distance); sd(PFT_SEARCH_RESOLUTION, c->resolution);
     coherence_ = c;
   }
-  template <typename CoherenceT> void setCloudCoherence(const std::shared_ptr<CoherenceT>& c) {
-    setCloudCoherence(std::static_pointer_cast<NearestPairPointCloudCoherence<PointT>>(c));
-  }
-  void setReferenceCloud(const typename PointCloud<PointT>::ConstPtr& c) {                        // ref :673
+  CloudCoherencePtr getCloudCoherence() const { return coherence_; }
+  void setReferenceCloud(const PointCloudInConstPtr& c) {                                         // ref :673
     ref_ = c;
     pft::check(pft_tracker_set_reference_cloud(h_, c->device()));
   }
-  typename PointCloud<PointT>::ConstPtr getReferenceCloud() const { return ref_; }
-  void setInputCloud(const typename PointCloud<PointT>::ConstPtr& c) {                            // ref :691
+  PointCloudInConstPtr getReferenceCloud() const { return ref_; }
+  void setInputCloud(const PointCloudInConstPtr& c) {                                             // ref :691
     input_ = c;
     pft::check(pft_tracker_set_input_cloud(h_, c ? c->device() : nullptr));
   }
@@ -453,7 +517,7 @@ class ParticleFilterOMPTracker {
     return s;
   }
   PointCloudStatePtr getParticles() const {                                                       // ref :270
-    auto out = std::make_shared<PointCloud<StateT>>();
+    PointCloudStatePtr out = pft::sp::make_shared<PointCloud<StateT>>();
     size_t n = 0;
     int rc = pft_tracker_get_particles(h_, nullptr, 0, &n);
     if (rc != PFT_OK && rc != PFT_ERR_CAPACITY) pft::check(rc);
@@ -461,6 +525,7 @@ class ParticleFilterOMPTracker {
     if (n) pft::check(pft_tracker_get_particles(h_, reinterpret_cast<pft_particle*>(out->points.data()), n, &n));
     return out;
   }
+  pft::AffineResult toEigenMatrix(const StateT& particle) { return particle.toEigenMatrix(); }    // ref :310
   // what viz_cb derives from getResult() per object (ref :309-316, :432-466, :481-515): published centroid + PCA box
   pft_result_box getResultBox(float z_offset = -0.005f) const {
     pft_result_box b;
@@ -472,7 +537,7 @@ class ParticleFilterOMPTracker {
   pft_tracker* handle() const { return h_; }
 
  protected:
-  ParticleFilterOMPTracker(unsigned int nr_threads, int kld) {
+  ParticleFilterTracker(unsigned int nr_threads, int kld) {
     pft::check(pft_tracker_create(pft::Context::Default()->get(), kld, &h_));
     si(PFT_THREADS, (int)nr_threads);
   }
@@ -483,24 +548,57 @@ class ParticleFilterOMPTracker {
     pft::check(pft_tracker_set_vec6(h_, k, v.data()));
   }
   pft_tracker* h_ = nullptr;
-  typename PointCloud<PointT>::ConstPtr ref_, input_;
-  typename NearestPairPointCloudCoherence<PointT>::Ptr coherence_;
+  PointCloudInConstPtr ref_, input_;
+  CloudCoherencePtr coherence_;
 };
 
-// pcl::tracking::KLDAdaptiveParticleFilterOMPTracker (ref :209-222)
+// pcl::tracking::ParticleFilterOMPTracker (ref :201-206)
 template <typename PointT, typename StateT>
-class KLDAdaptiveParticleFilterOMPTracker : public ParticleFilterOMPTracker<PointT, StateT> {
+class ParticleFilterOMPTracker : public ParticleFilterTracker<PointT, StateT> {
  public:
-  explicit KLDAdaptiveParticleFilterOMPTracker(unsigned int nr_threads = 0) : ParticleFilterOMPTracker<PointT, StateT>(nr_threads, 1) {}
+  explicit ParticleFilterOMPTracker(unsigned int nr_threads = 0) : ParticleFilterTracker<PointT, StateT>(nr_threads, 0) {}
+  void setNumberOfThreads(unsigned int n) { this->si(PFT_THREADS, (int)n); }
+
+ protected:
+  ParticleFilterOMPTracker(unsigned int nr_threads, int kld) : ParticleFilterTracker<PointT, StateT>(nr_threads, kld) {}
+};
+
+// pcl::tracking::KLDAdaptiveParticleFilterTracker / KLDAdaptiveParticleFilterOMPTracker (ref :209-222; :150-151 commented)
+template <typename PointT, typename StateT>
+class KLDAdaptiveParticleFilterTracker : public ParticleFilterTracker<PointT, StateT> {
+ public:
+  KLDAdaptiveParticleFilterTracker() : ParticleFilterTracker<PointT, StateT>(0, 1) {}
   void setMaximumParticleNum(unsigned int n) { this->si(PFT_MAX_PARTICLE_NUM, (int)n); }          // ref :211
   void setDelta(double d) { this->sd(PFT_DELTA, d); }                                            // ref :212
   void setEpsilon(double e) { this->sd(PFT_EPSILON, e); }                                        // ref :213
   void setBinSize(const StateT& b) {                                                              // ref :214-221
     this->sv(PFT_BIN_SIZE, {b.x, b.y, b.z, b.roll, b.pitch, b.yaw});
   }
+
+ protected:
+  explicit KLDAdaptiveParticleFilterTracker(unsigned int nr_threads) : ParticleFilterTracker<PointT, StateT>(nr_threads, 1) {}
+};
+template <typename PointT, typename StateT>
+class KLDAdaptiveParticleFilterOMPTracker : public KLDAdaptiveParticleFilterTracker<PointT, StateT> {
+ public:
+  explicit KLDAdaptiveParticleFilterOMPTracker(unsigned int nr_threads = 0) : KLDAdaptiveParticleFilterTracker<PointT, StateT>(nr_threads) {}
+  void setNumberOfThreads(unsigned int n) { this->si(PFT_THREADS, (int)n); }
 };
 
 }  // namespace tracking
+
+// pcl::NormalEstimationOMP (ref :168, :183-185): constructed and configured by the reference, never run (setUseNormal(false), ref :233)
+template <typename PointInT, typename PointOutT>
+class NormalEstimationOMP {
+ public:
+  explicit NormalEstimationOMP(unsigned int nr_threads = 0) : threads_(nr_threads) {}
+  template <typename TreePtr> void setSearchMethod(const TreePtr&) {}
+  void setRadiusSearch(double r) { radius_ = r; }
+ private:
+  unsigned int threads_;
+  double radius_ = 0.0;
+};
+struct Normal { float normal_x = 0.f, normal_y = 0.f, normal_z = 0.f, curvature = 0.f; };
 }  // namespace pcl
 #endif  // PFT_SHIM_USE_PCL_TYPES
 

@@ -78,6 +78,7 @@ def lib():
             "orc_get_motion": (None, [vp, vp]),
             "orc_set_motion": (None, [vp, vp]),
             "orc_set_changed": (None, [vp, i]),
+            "orc_reset_tracking": (None, [vp]),
             "orc_get_changed": (i, [vp]),
             "orc_change_detector_info": (None, [vp, vp]),
             "orc_change_detector_sequence": (i, [vp, vp, i, d, i, vp]),
@@ -418,6 +419,10 @@ class Tracker:
     def set_input(self, pts):
         pts = as_points(pts)
         lib().orc_set_input(self._h, _p(pts), len(pts))
+
+    def reset(self):
+        """ParticleFilterTracker::resetTracking: clears the particle set, nothing else."""
+        lib().orc_reset_tracking(self._h)
 
     def set_particles(self, parts):
         parts = np.ascontiguousarray(parts, dtype=PARTICLE)

@@ -1300,6 +1300,10 @@ void orc_get_result(orc_tracker* t, orc_particle* out) { *out = t->T.rep; }
 void orc_set_result(orc_tracker* t, const orc_particle* in) { t->T.rep = *in; }
 void orc_get_motion(orc_tracker* t, orc_particle* out) { *out = t->T.motion; }
 void orc_set_motion(orc_tracker* t, const orc_particle* in) { t->T.motion = *in; }
+// ParticleFilterTracker::resetTracking [tracking/particle_filter.h]: `if (particles_) particles_->points.clear ();` -- nothing else:
+// particle_num_ keeps the count of the last (KLD) resample and changed_ stays as it is, so the compute() that follows re-draws
+// that many particles (initParticles) and, when an earlier weight() had set changed_, resamples them in its first iteration
+void orc_reset_tracking(orc_tracker* t) { t->T.particles.clear(); }
 void orc_set_changed(orc_tracker* t, int c) { t->T.changed = c != 0; }
 int orc_get_changed(orc_tracker* t) { return t->T.changed ? 1 : 0; }
 // out[4] = {change_counter_, tests run so far, point indices reported by the last test (-1: none yet), changed_}

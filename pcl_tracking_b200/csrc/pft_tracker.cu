@@ -1357,6 +1357,13 @@ int pft_tracker_get_result_box(pft_tracker* t, float z_offset, pft_result_box* o
 int pft_tracker_reset(pft_tracker* t) {
   if (!t) { set_last_error("null tracker"); return PFT_ERR_INVALID; }
   // resetTracking: particles are re-drawn around trans_ on the next compute()
+  if (t->kld && t->st.p && t->has_particles) {
+    // upstream's particle_num_ is whatever the last KLD resample left: that many particles are re-drawn
+    TrackerState hs;
+    int rc = read_state(t, &hs);
+    if (rc) return rc;
+    if (hs.particle_num > 0) t->particle_num = hs.particle_num;
+  }
   t->has_particles = false;
   // (changed_ is left as it is: upstream's resetTracking() only clears the particle vector, so the compute() that
   // follows re-draws the particles and, when an earlier weight() had set changed_, resamples them in the same frame)
@@ -1365,12 +1372,9 @@ int pft_tracker_reset(pft_tracker* t) {
     PFT_CUDA_TRY(cudaSetDevice(t->ctx->device));
     cudaStream_t s = t->run_stream();
     PFT_CUDA_TRY(cudaMemsetAsync(&t->st.as<TrackerState>()->has_particles, 0, sizeof(int), s));
-    if (t->slot_aabb.p && t->n_cap > 0) {
-      std::vector<float> init((size_t)t->n_cap * 6);
-      for (int i = 0; i < t->n_cap; ++i) { for (int d = 0; d < 3; ++d) { init[6 * i + d] = FLT_MAX; init[6 * i + 3 + d] = -FLT_MAX; } }
-      PFT_CUDA_TRY(cudaMemcpyAsync(t->slot_aabb.p, init.data(), init.size() * sizeof(float), cudaMemcpyHostToDevice, s));
-      PFT_CUDA_TRY(cudaStreamSynchronize(s));
-    }
+    // (the per-slot boxes of the transformed model stay: upstream keeps transed_reference_vector_ across resetTracking(),
+    // so stale slots go on widening the crop box)
+    PFT_CUDA_TRY(cudaStreamSynchronize(s));
   }
   return PFT_OK;
 }

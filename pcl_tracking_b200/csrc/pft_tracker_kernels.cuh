@@ -250,7 +250,8 @@ __global__ void init_particles_kernel(TrackerState* st, DevParticle* parts, int 
   rep.weight = 1.0f / (float)n;
   if (i == 0) {
     st->rep = rep;
-    st->motion = DevParticle{0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 0.f};
+    // (motion_ is NOT touched: upstream's initParticles leaves it alone, so after resetTracking() the next resample
+    // still applies the motion of the frames before; it starts as zero with the tracker)
     st->particle_num = n;
     st->has_particles = 1;
     st->draw_call += 1ull;

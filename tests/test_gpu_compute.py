@@ -44,6 +44,74 @@ def test_first_compute_matches_oracle_control_flow():
         assert abs(float(gr[k]) - float(orr[k])) < 2e-3
 
 
+def _cdf_after_first_iteration(scene, model, centre, draws, n, nmax):
+    """Cumulative selection table the resample of iteration 1 draws from, from the oracle run stage by stage
+    (initParticles, weight, update: what iteration 0 of compute() does)."""
+    _, o = util.make_pair(kld=True, particle_num=n, max_particle_num=nmax, use_hsv=True, oracle_nn=oracle.NN_EXACT_GRID)
+    m = np.eye(4, dtype=np.float32); m[:3, 3] = centre
+    o.set_trans(m[:3])
+    o.inject_draws(*draws)
+    o.set_reference(model); o.set_input(scene)
+    o.init_particles(); o.weight(); o.update()
+    w = o.get_particles()["weight"].astype(np.float64)
+    return np.cumsum(w) / w.sum()
+
+
+def test_first_compute_ancestor_mismatches_are_cdf_boundary_flips():
+    """Whole compute() against the oracle: wherever the two disagree on an ancestor, the selection uniform of that
+    candidate lies within 2e-6 of the boundary between the two (adjacent) ancestors in the cumulative table --
+    i.e. the only source of divergence is an ulp-level difference of the weights moving a CDF boundary across a draw."""
+    scene, model, centre = util.small_case(8, n_scene=5000, n_model=300)
+    n, nmax = 100, 220
+    d = synth.draws(2, nmax, seed=21)
+    g, o = util.make_pair(kld=True, particle_num=n, max_particle_num=nmax, use_hsv=True, oracle_nn=oracle.NN_EXACT_GRID)
+    util.set_trans_both(g, o, centre)
+    g.injectDraws(*d); o.inject_draws(*d)
+    g.setReferenceCloud(model); g.setInputCloud(pcl.PointCloud(scene)); g.compute()
+    o.set_reference(model); o.set_input(scene); o.compute()
+    cdf = _cdf_after_first_iteration(scene, model, centre, d, n, nmax)
+    ga, oa = g.ancestors(), o.ancestors()
+    assert len(ga) == len(oa)
+    usel = d[0][1]                                   # iteration 1 draws from slot 1
+    for i in np.nonzero(ga != oa)[0]:
+        lo, hi = sorted((int(ga[i]), int(oa[i])))
+        assert np.all(np.diff(cdf[lo:hi]) < 1e-9) or hi - lo == 1, "not neighbours in the table"
+        assert abs(float(usel[i]) - cdf[lo]) < 2e-6, (i, usel[i], cdf[lo])
+
+
+def test_first_compute_exact_when_draws_avoid_cdf_boundaries():
+    """The same whole compute() with the selection uniforms nudged away from every boundary of the cumulative table
+    (by 1e-4, far above the ulp-level differences of the weights): every ancestor agrees, and the particle set and
+    the pose hold the north-star tolerance, 1e-4 m / 1e-4 rad."""
+    scene, model, centre = util.small_case(8, n_scene=5000, n_model=300)
+    n, nmax = 100, 220
+    usel, normals, umot = synth.draws(2, nmax, seed=21)
+    cdf = _cdf_after_first_iteration(scene, model, centre, (usel, normals, umot), n, nmax)
+    u = usel[1].astype(np.float64)
+    k = np.clip(np.searchsorted(cdf, u), 0, len(cdf) - 1)
+    near_hi = np.abs(cdf[k] - u) < 1e-4
+    near_lo = (k > 0) & (np.abs(cdf[np.maximum(k - 1, 0)] - u) < 1e-4)
+    u[near_hi] -= 2e-4
+    u[near_lo] += 2e-4
+    usel = usel.copy()
+    usel[1] = np.clip(u, 0.0, 1.0 - 2.0 ** -24).astype(np.float32)
+    d = (usel, normals, umot)
+    g, o = util.make_pair(kld=True, particle_num=n, max_particle_num=nmax, use_hsv=True, oracle_nn=oracle.NN_EXACT_GRID)
+    util.set_trans_both(g, o, centre)
+    g.injectDraws(*d); o.inject_draws(*d)
+    g.setReferenceCloud(model); g.setInputCloud(pcl.PointCloud(scene)); g.compute()
+    o.set_reference(model); o.set_input(scene); o.compute()
+    assert np.array_equal(g.ancestors(), o.ancestors())
+    gp, op = g.getParticles(), o.get_particles()
+    assert len(gp) == len(op)
+    for key in ("x", "y", "z", "roll", "pitch", "yaw"):
+        np.testing.assert_allclose(gp[key], op[key], atol=1e-4)
+    np.testing.assert_allclose(gp["weight"], op["weight"], rtol=2e-4, atol=1e-9)
+    gr, orr = g.getResult(), o.get_result()
+    for key in ("x", "y", "z", "roll", "pitch", "yaw"):
+        assert abs(float(gr[key]) - float(orr[key])) < 1e-4, key
+
+
 def test_tracking_follows_moving_object_and_graph_replays():
     objs = synth.default_objects(1)
     frames = [synth.render(f, objs)[0] for f in range(5)]
@@ -239,3 +307,82 @@ def test_cluster_models_feed_the_trackers():
         want = obj_pts[clusters[k]]
         centre = np.array([want["x"].mean(), want["y"].mean(), want["z"].mean()])
         assert np.linalg.norm(box["centroid"] - centre) < 0.03   # every tracker stays on its own cluster
+
+
+def test_multi_object_batch_one_object_vs_oracle():
+    """C5 against the oracle: the first compute() of a batch of 8 trackers (one shared scene), with injected draws; one
+    object of the batch is compared with the CPU oracle's compute() on the same inputs (control flow, particle count,
+    ancestors up to CDF-boundary flips, matched states 1e-4)."""
+    objs = synth.default_objects(8)
+    pts, oid = synth.render(0, objs)
+    vg = pcl.ApproximateVoxelGrid()
+    vg.setLeafSize(0.01)
+    vg.setPassThrough("z", 0.0, 10.0)
+    vg.setInputCloud(pcl.PointCloud(pts))
+    ds = vg.filter()
+    scene = ds.to_numpy()
+    n, nmax, pick = 120, 260, 3
+    trackers, o_pick, model_pick = [], None, None
+    for k in range(8):
+        model_cloud, c = pcl.prepare_model(pcl.PointCloud(synth.model_points(pts, oid, k)), 0.01)
+        g, o = util.make_pair(kld=True, particle_num=n, max_particle_num=nmax, use_hsv=True, oracle_nn=oracle.NN_EXACT_GRID)
+        util.set_trans_both(g, o, c)
+        d = synth.draws(2, nmax, seed=300 + k)
+        g.injectDraws(*d)
+        g.setReferenceCloud(model_cloud); g.setInputCloud(ds)
+        trackers.append(g)
+        if k == pick:
+            o.inject_draws(*d)
+            o.set_reference(model_cloud.to_numpy()); o.set_input(scene)
+            o_pick = o
+    pcl.compute_batch(trackers)
+    o_pick.compute()
+    g = trackers[pick]
+    gp, op = g.getParticles(), o_pick.get_particles()
+    assert len(gp) == len(op) and len(gp) != n
+    same = g.ancestors() == o_pick.ancestors()
+    assert same.mean() > 0.97
+    for key in ("x", "y", "z", "roll", "pitch", "yaw"):
+        np.testing.assert_allclose(gp[key][same], op[key][same], atol=1e-4)
+
+
+def test_raising_maximum_particle_number_between_computes_keeps_the_kld_stop_rule():
+    """setMaximumParticleNum(larger) after the first compute() re-sizes the particle buffers; the table of KLD bounds
+    must follow (it is read up to the new capacity).  The resample after the change is compared with the oracle."""
+    scene, model, centre = util.small_case(14, n_scene=3000, n_model=200)
+    g, o = util.make_pair(kld=True, particle_num=100, max_particle_num=150, use_hsv=False, epsilon=0.02, bin_size=0.02, oracle_nn=oracle.NN_EXACT_GRID)
+    util.set_trans_both(g, o, centre)
+    cloud = pcl.PointCloud(scene)
+    g.setReferenceCloud(model); g.setInputCloud(cloud)
+    o.set_reference(model); o.set_input(scene)
+    d = synth.draws(2, 600, seed=31)
+    g.injectDraws(*d); o.inject_draws(*d)
+    g.compute(); o.compute()
+    assert len(g.getParticles()) == len(o.get_particles()) <= 150
+    g.setMaximumParticleNum(600); o.set_i(oracle.MAX_PARTICLE_NUM, 600)
+    # identical state on both sides, then one resample under the new cap
+    o.set_particles(g.getParticles()); o.set_result(g.getResult()); o.set_motion(g.getMotion())
+    g.resample(1); o.resample(1)
+    assert np.array_equal(g.ancestors(), o.ancestors())
+    assert len(g.getParticles()) == len(o.get_particles()) > 150
+
+
+def test_reset_tracking_then_compute_resamples_in_the_same_frame():
+    """resetTracking() only clears the particle set (upstream leaves changed_ as it is): the compute() that follows
+    re-draws the particles AND resamples them in its first iteration, because an earlier weight() had set changed_."""
+    scene, model, centre = util.small_case(15, n_scene=3000, n_model=200)
+    g, o = util.make_pair(kld=True, particle_num=80, max_particle_num=200, use_hsv=False, oracle_nn=oracle.NN_EXACT_GRID)
+    util.set_trans_both(g, o, centre)
+    g.setReferenceCloud(model); g.setInputCloud(pcl.PointCloud(scene))
+    o.set_reference(model); o.set_input(scene)
+    d = synth.draws(2, 200, seed=33)
+    g.injectDraws(*d); o.inject_draws(*d)
+    g.compute(); o.compute()
+    g.resetTracking(); o.reset()
+    g.compute(); o.compute()
+    gp, op = g.getParticles(), o.get_particles()
+    assert len(gp) == len(op)
+    same = g.ancestors() == o.ancestors()
+    assert same.mean() > 0.97
+    for key in ("x", "y", "z"):
+        np.testing.assert_allclose(gp[key][same], op[key][same], atol=1e-4)

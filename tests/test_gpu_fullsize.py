@@ -142,3 +142,62 @@ def test_c4_100k_particles_properties():
     o.set_crop_box(g.aabb())
     o.weight()
     np.testing.assert_allclose(raw[:64], o.raw_weights(), rtol=1e-5)
+
+
+def test_c3_kld_resample_and_weight_10k_vs_oracle():
+    """configs[2] against the oracle at full size: ONE KLD resample with a cap of 10 000 candidates (fine bins, small
+    epsilon: ~10 000 survive) followed by weight() of all of them on the c2 scene -- ~20 M likelihood evaluations,
+    seconds on the CPU in exact-grid mode.  Ancestors and particle count bit-exact, states 1e-6, crop box bit-exact,
+    raw weights 1e-5."""
+    ds, model_cloud, c = _c2_inputs()
+    scene, model = ds.to_numpy(), model_cloud.to_numpy()
+    n0, nmax = 400, 10_000
+    g, o = util.make_pair(kld=True, particle_num=n0, max_particle_num=nmax, use_hsv=True, oracle_nn=oracle.NN_EXACT_GRID, epsilon=0.02, bin_size=0.02)
+    parts = _step_noise_particles(c, n0, seed=11)
+    rng = np.random.default_rng(12)
+    parts["weight"] = (rng.random(n0) ** 3).astype(np.float32)
+    parts["weight"] /= parts["weight"].sum(dtype=np.float64)
+    d = synth.draws(2, nmax, seed=13)
+    g.injectDraws(*d); o.inject_draws(*d)
+    g.setReferenceCloud(model_cloud); g.setInputCloud(ds); g.setParticles(parts)
+    o.set_reference(model); o.set_input(scene); o.set_particles(parts)
+    rep, mot = parts[0].copy(), parts[1].copy()
+    mot["x"], mot["y"], mot["z"], mot["roll"], mot["pitch"], mot["yaw"] = 0.004, -0.006, 0.002, 0.01, -0.01, 0.02
+    g.setResult(rep, mot); o.set_result(rep); o.set_motion(mot)
+    g.resample(1); o.resample(1)
+    assert np.array_equal(g.ancestors(), o.ancestors())
+    gp, op = g.getParticles(), o.get_particles()
+    assert len(gp) == len(op) and len(gp) > 5000
+    util.assert_particles_close(gp, op, 1e-6, 2e-6, None)
+    o.set_particles(gp)                      # identical inputs for the weight stage
+    g.setDebugNN(4)
+    g.weight(); o.weight(keep_nn=True)
+    np.testing.assert_array_equal(g.aabb(), o.aabb())
+    cidx, _ = o.cropped()
+    assert g.croppedCount() == len(cidx)
+    for p in range(4):
+        gi, gd = g.nn(p, len(model))
+        oi, od = o.nn(p, len(model))
+        m = od.astype(np.float64) < 0.1 * 0.1
+        np.testing.assert_array_equal(gi[m], cidx[oi[m]])
+        np.testing.assert_array_equal(gd[m], od[m])
+    np.testing.assert_allclose(g.rawWeights(), o.raw_weights(), rtol=1e-5)
+
+
+def test_c4_1000_random_particles_of_100k_vs_oracle():
+    """configs[3]: 1 024 particles drawn at random from the 100 000 (not a prefix) against the oracle given the GPU's
+    crop box; raw weights 1e-5."""
+    ds, model_cloud, c = _c2_inputs()
+    n = 100_000
+    parts = _step_noise_particles(c, n, seed=6)
+    g, _ = util.make_pair(kld=False, particle_num=n, use_hsv=True)
+    g.setReferenceCloud(model_cloud); g.setInputCloud(ds); g.setParticles(parts)
+    g.weight()
+    raw = g.rawWeights()
+    pick = np.sort(np.random.default_rng(8).choice(n, 1024, replace=False))
+    o = oracle.Tracker(kld=False)
+    oracle.configure_like_reference(o, particle_num=len(pick), use_hsv=True, nn_mode=oracle.NN_EXACT_GRID)
+    o.set_reference(model_cloud.to_numpy()); o.set_input(ds.to_numpy()); o.set_particles(parts[pick].copy())
+    o.set_crop_box(g.aabb())
+    o.weight()
+    np.testing.assert_allclose(raw[pick], o.raw_weights(), rtol=1e-5)
