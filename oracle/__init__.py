@@ -79,6 +79,7 @@ def lib():
             "orc_set_motion": (None, [vp, vp]),
             "orc_set_changed": (None, [vp, i]),
             "orc_reset_tracking": (None, [vp]),
+            "orc_alias_table": (None, [vp, vp, vp]),
             "orc_get_changed": (i, [vp]),
             "orc_change_detector_info": (None, [vp, vp]),
             "orc_change_detector_sequence": (i, [vp, vp, i, d, i, vp]),
@@ -419,6 +420,13 @@ class Tracker:
     def set_input(self, pts):
         pts = as_points(pts)
         lib().orc_set_input(self._h, _p(pts), len(pts))
+
+    def alias_table(self):
+        """genAliasTable (Walker) of the current particle set: (a[int32], q[float64])."""
+        n = lib().orc_get_particles(self._h, None, 0)
+        a, q = np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.float64)
+        lib().orc_alias_table(self._h, _p(a), _p(q))
+        return a, q
 
     def reset(self):
         """ParticleFilterTracker::resetTracking: clears the particle set, nothing else."""

@@ -1304,6 +1304,13 @@ void orc_set_motion(orc_tracker* t, const orc_particle* in) { t->T.motion = *in;
 // particle_num_ keeps the count of the last (KLD) resample and changed_ stays as it is, so the compute() that follows re-draws
 // that many particles (initParticles) and, when an earlier weight() had set changed_, resamples them in its first iteration
 void orc_reset_tracking(orc_tracker* t) { t->T.particles.clear(); }
+// genAliasTable of the current particle set (out arrays hold one entry per particle)
+void orc_alias_table(orc_tracker* t, int* a_out, double* q_out) {
+  std::vector<int> a; std::vector<double> q;
+  gen_alias_table(t->T.particles, a, q);
+  std::copy(a.begin(), a.end(), a_out);
+  std::copy(q.begin(), q.end(), q_out);
+}
 void orc_set_changed(orc_tracker* t, int c) { t->T.changed = c != 0; }
 int orc_get_changed(orc_tracker* t) { return t->T.changed ? 1 : 0; }
 // out[4] = {change_counter_, tests run so far, point indices reported by the last test (-1: none yet), changed_}

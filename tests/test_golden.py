@@ -146,3 +146,82 @@ def test_cuda_parity_modes_match_committed_fixture():
         i = c.changeDetectorInfo()
         assert [i["counter"], i["tests"], i["last_found"], int(i["changed"])] == want["cd_info"][k].tolist()
         np.testing.assert_allclose(c.getParticles()["weight"], want["cd_weights"][k], rtol=1e-5, atol=1e-12)
+
+
+PCL_GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pcl_small_case.npz")
+
+
+@pytest.mark.skipif(not os.path.exists(PCL_GOLDEN), reason="tests/golden/pcl_small_case.npz is produced by tests/golden/make_pcl_golden.cpp on a "
+                                                           "machine with PCL 1.8.0 (not installable in this image): until it is committed the oracle is "
+                                                           "unpinned against PCL binaries")
+def test_oracle_matches_pcl_golden_when_present():
+    """Pins the oracle to REAL PCL 1.8.0: what make_pcl_golden.cpp computed with pcl::tracking / pcl::filters / pcl::search on the
+    inputs of oracle_small_case.npz against what the restatement computes on the same inputs."""
+    import oracle
+    pclg = np.load(PCL_GOLDEN)
+    inp = np.load(GOLDEN)
+    scene, model, parts = inp["scene"], inp["model"], inp["particles"]
+
+    def tracker(nn_mode):
+        t = oracle.Tracker(kld=True)
+        oracle.configure_like_reference(t, particle_num=len(parts), max_particle_num=96, use_hsv=True, nn_mode=nn_mode)
+        t.set_reference(model); t.set_input(scene); t.set_particles(parts)
+        return t
+
+    # exact coherence: crop box and count bit-exact, raw / normalised weights 1e-5, update() 1e-5
+    t = tracker(oracle.NN_EXACT_BRUTE)
+    t.weight(keep_nn=True)
+    np.testing.assert_array_equal(t.aabb(), pclg["aabb"])
+    cidx, _ = t.cropped()
+    assert len(cidx) == int(pclg["cropped_count"][0])
+    np.testing.assert_allclose(t.raw_weights(), pclg["raw"], rtol=1e-5)
+    np.testing.assert_allclose(t.get_particles()["weight"], pclg["weights"], rtol=1e-5, atol=1e-12)
+    t.update()
+    r = t.get_result()
+    for i, k in enumerate(("x", "y", "z", "one", "roll", "pitch", "yaw")):
+        if k != "one":
+            assert abs(float(r[k]) - float(pclg["result"][i])) < 1e-5, k
+    # the reference's own (approximate) coherence: the greedy octree search, pair by pair, then the weights
+    a = tracker(oracle.NN_PCL_APPROX)
+    a.weight(keep_nn=True)
+    for p in range(pclg["approx_nn_idx"].shape[0]):
+        oi, od = a.nn(p, len(model))
+        np.testing.assert_array_equal(oi, pclg["approx_nn_idx"][p])
+        np.testing.assert_array_equal(od, pclg["approx_nn_d2"][p])
+    np.testing.assert_allclose(a.raw_weights(), pclg["approx_raw"], rtol=1e-5)
+    # filters: PassThrough order-preserving and bit-exact; ApproximateVoxelGrid bit-exact incl. duplicates and flush order;
+    # VoxelGrid as a set of centroids (std::sort is unstable: the fp32 sums of a voxel may differ in the last bits)
+    passed = oracle.passthrough(scene, 2, 0.0, 10.0)
+    assert passed.tobytes() == pclg["passthrough"].tobytes()
+    assert oracle.approx_voxel_grid_pcl(passed, 0.02).tobytes() == pclg["approx_voxel_grid"].tobytes()
+    vg, want = oracle.voxel_grid_pcl(passed, 0.02), pclg["voxel_grid"]
+    assert len(vg) == len(want)
+    for k in ("x", "y", "z"):
+        np.testing.assert_allclose(vg[k], want[k], atol=1e-6)
+    # scalars: calcKLBound, Walker's alias table of the normalised weights
+    np.testing.assert_allclose([oracle.kl_bound(k, 0.99, 0.2) for k in range(2, 201)], pclg["kl_bound"], rtol=1e-12)
+    w = parts.copy()
+    w["weight"] = pclg["weights"]
+    t.set_particles(w)
+    aa, qq = t.alias_table()
+    np.testing.assert_array_equal(aa, pclg["alias_a"])
+    np.testing.assert_allclose(qq, pclg["alias_q"], rtol=1e-12)
+
+
+def test_pcl_golden_writer_emits_loadable_npy(tmp_path):
+    """make_pcl_golden.cpp cannot be built here (no PCL), but its .npy writer can be checked: the same function compiled on
+    its own writes files numpy loads with the declared dtype and shape."""
+    import re
+    import subprocess
+    src = open(os.path.join(os.path.dirname(PCL_GOLDEN), "make_pcl_golden.cpp")).read()
+    body = re.search(r"(// minimal \.npy \(v1\.0\) writer.*?\n}\n)", src, re.S).group(1)
+    prog = tmp_path / "w.cpp"
+    prog.write_text("#include <fstream>\n#include <string>\n#include <vector>\n" + body +
+                    'int main(int, char** v) { float a[6] = {0, 1, 2, 3, 4, 5}; int b[3] = {7, 8, 9};\n'
+                    ' write_npy(std::string(v[1]) + "/a.npy", "<f4", {2, 3}, a, 24); write_npy(std::string(v[1]) + "/b.npy", "<i4", {3}, b, 12); return 0; }\n')
+    exe = tmp_path / "w"
+    subprocess.check_call(["g++", "-std=c++11", "-O1", "-o", str(exe), str(prog)])
+    subprocess.check_call([str(exe), str(tmp_path)])
+    a, b = np.load(tmp_path / "a.npy"), np.load(tmp_path / "b.npy")
+    assert a.dtype == np.float32 and a.shape == (2, 3) and a.tolist() == [[0, 1, 2], [3, 4, 5]]
+    assert b.dtype == np.int32 and b.tolist() == [7, 8, 9]
