@@ -583,14 +583,14 @@ def run_workload(rig, workload, steps, warmup, with_pipelined=True):
         peak, peak_src = float(mp["hbm_gbs"]), "measured (MEASURED_PEAKS.json, burst copy)"
     except Exception:
         pass
-    kernel = "weight_lists_kernel" if info["use_lists"] else "weight_kernel"
+    kernel = "weight_lists_kernel" if info["use_lists"] else "weight_lists_kernel(row-table path: lists off for this crop)"
     # DRAM traffic of that kernel per launch: from the committed `ncu --set full` capture of this workload, and only when the
     # capture was taken on the very sources this library was built from (a stale figure is never reported)
     traffic, traffic_src = None, None
     try:
         km = json.load(open(os.path.join(ROOT, "profiles", "r02_kernel_metrics_%s.json" % workload)))
         if km.get("_source_hash") == source_hash() and world == 1:
-            wk = [v for k, v in km.items() if k.startswith(kernel)][0]
+            wk = [v for k, v in km.items() if k.startswith("weight_lists_kernel")][0]
             scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
             traffic = 0.0
             for key, val in wk.items():
@@ -611,7 +611,7 @@ def run_workload(rig, workload, steps, warmup, with_pipelined=True):
         "e2e": e2e, "e2e_packed16": e2e16, "e2e_pipelined": e2e_pipe,
         "gpu_launches": int(launches), "graph_replays": int(graph_replays), "clocks": sampler.summary(),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
-                     "kernel": kernel + ("<HSV>" if True else ""), "peak_source": peak_src,
+                     "kernel": kernel + "<HSV>", "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": bytes_per_launch, "ms_per_launch": w_ms_per_launch,
                      "evals_per_s_in_kernel": evals_per_launch / (w_ms_per_launch * 1e-3),
                      "particles_per_launch": n_local,

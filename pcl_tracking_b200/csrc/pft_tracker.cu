@@ -160,7 +160,6 @@ struct pft_tracker {
   bool use_cd = false;
   int cd_interval = 10, cd_filter = 10, change_counter = 0, cd_tests = 0, cd_last_found = -1, cd_node_cap = 0, cd_resets = 0;
   double cd_res = 0.01;
-  int lists_hint = -1;  // TrackerState::lists_on as last read back (-1: not yet): 1 = the row-table kernel is not launched behind weight_lists_kernel
   int weight_smem = 0;  // dynamic shared memory of the weight kernel (bytes)
   int lists_smem = 0;   // ... of weight_lists_kernel
   int tbl_size = 0;
@@ -168,6 +167,8 @@ struct pft_tracker {
   int chunks = 1, chunk_len = 0;
 
   // pft_compute_batch: every tracker of a batch runs on a stream of its own, forked from / joined to the context stream
+  cudaStream_t aux_stream = nullptr;  // mark + collect run beside the point index build
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaStream_t batch_stream = nullptr;
   cudaEvent_t batch_done = nullptr;
   bool batch_active = false;
@@ -643,10 +644,11 @@ int launch_index_begin(pft_tracker* t, bool reuse_allowed = false) {
   // one index per frame (see IndexHeader): with the lists on, the crop box is dilated by this margin; the later weight()
   // calls of a compute() reuse the index when their crop box fits
   static const float dilate = [] { const char* e = getenv("PFT_INDEX_DILATE"); return e ? (float)atof(e) : 0.03f; }();
+  static const int list_ratio = [] { const char* e = getenv("PFT_LIST_RATIO"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 2; }();  // tuning knob
   index_begin_kernel<<<sm, 256, 0, t->run_stream()>>>(t->st.as<TrackerState>(), t->idx_hdr.as<IndexHeader>(), t->icount.as<int>(), inv_leaf, t->index_level,
                                                       t->max_cells, t->list_mode ? t->list_max_cells : 0, t->list_mode == 2 ? 0 : t->M, t->nranks, t->rank,
                                                       t->fneeded.as<unsigned int>(), t->xcount.as<int>(), t->fbuilt_bits.as<unsigned int>(),
-                                                      reuse_allowed ? 1 : 0, t->iteration_num > 1 ? dilate : 0.f, t->idx_hdr_prev.as<IndexHeader>());
+                                                      reuse_allowed ? 1 : 0, t->iteration_num > 1 ? dilate : 0.f, list_ratio, t->idx_hdr_prev.as<IndexHeader>());
   PFT_LAUNCH_CHECK();
   stage_mark(t, "index_begin_kernel");
   return PFT_OK;
@@ -665,6 +667,28 @@ int weight_phase_eval(pft_tracker* t, bool force_raw = false, bool reuse_allowed
   const float inv_leaf = 1.0f / (float)t->search_res;
   const int gscene = blocks_for(ncap_scene, 256, sm * 4);
   if ((rc = launch_index_begin(t, reuse_allowed && t->list_max_cells > 0 && t->list_mode && t->nn_mode == PFT_NN_EXACT))) return rc;
+  const bool build_lists = t->list_max_cells > 0 && t->list_mode && t->nn_mode == PFT_NN_EXACT;
+  if (build_lists) {
+    // which fine cells the queries fall into (mark + collect) does not depend on the point index being built (count +
+    // scan + scatter): the two chains of small kernels run side by side on two streams and join before the list build
+    if (!t->aux_stream) {
+      PFT_CUDA_TRY(cudaStreamCreateWithFlags(&t->aux_stream, cudaStreamNonBlocking));
+      PFT_CUDA_TRY(cudaEventCreateWithFlags(&t->ev_fork, cudaEventDisableTiming));
+      PFT_CUDA_TRY(cudaEventCreateWithFlags(&t->ev_join, cudaEventDisableTiming));
+    }
+    cudaStream_t sa = t->aux_stream;
+    PFT_CUDA_TRY(cudaEventRecord(t->ev_fork, s));
+    PFT_CUDA_TRY(cudaStreamWaitEvent(sa, t->ev_fork, 0));
+    // small query sets: exact query counts per cell (cells with few queries get one list instead of eight octant lists)
+    const long long n_queries = (long long)std::max(1, (t->particle_num > 0 ? t->particle_num : t->n_cap) / t->nranks) * t->M;
+    const size_t mark_smem = (size_t)(t->list_max_cells / 8 + 64);
+    if (n_queries <= kMarkCountMaxQueries) cand_mark_kernel<true><<<sm * 3, 256, mark_smem, sa>>>(st, hdr, t->model.as<float4>(), t->M, t->mats.as<float>(), t->fneeded.as<unsigned int>(), t->nranks, t->rank, t->fbuilt_bits.as<unsigned int>());
+    else cand_mark_kernel<false><<<sm * 3, 256, mark_smem, sa>>>(st, hdr, t->model.as<float4>(), t->M, t->mats.as<float>(), t->fneeded.as<unsigned int>(), t->nranks, t->rank, t->fbuilt_bits.as<unsigned int>());
+    PFT_LAUNCH_CHECK();
+    cand_collect_kernel<<<sm * 2, 256, 0, sa>>>(hdr, t->fneeded.as<unsigned int>(), t->fneeded_list.as<int>(), t->xcount.as<int>());
+    PFT_LAUNCH_CHECK();
+    PFT_CUDA_TRY(cudaEventRecord(t->ev_join, sa));
+  }
   index_count_kernel<<<gscene, 256, 0, s>>>(in->d_pts(), in->d_hdr(), hdr, t->icount.as<int>(), t->ipts2.as<float4>());
   PFT_LAUNCH_CHECK();
   stage_mark(t, "index_count_kernel");
@@ -675,18 +699,9 @@ int weight_phase_eval(pft_tracker* t, bool force_raw = false, bool reuse_allowed
                                               t->ihsv.as<unsigned int>(), t->ipts2.as<float4>());
   PFT_LAUNCH_CHECK();
   stage_mark(t, "index_scatter_kernel");
-  if (t->list_max_cells > 0 && t->list_mode && t->nn_mode == PFT_NN_EXACT) {
-    // dynamic shared memory: one bit per fine cell the lists are sized for
-    // small query sets: exact query counts per cell (cells with few queries get one list instead of eight octant lists)
-    const long long n_queries = (long long)std::max(1, (t->particle_num > 0 ? t->particle_num : t->n_cap) / t->nranks) * t->M;
-    const size_t mark_smem = (size_t)(t->list_max_cells / 8 + 64);
-    if (n_queries <= kMarkCountMaxQueries) cand_mark_kernel<true><<<sm * 3, 256, mark_smem, s>>>(st, hdr, t->model.as<float4>(), t->M, t->mats.as<float>(), t->fneeded.as<unsigned int>(), t->nranks, t->rank, t->fbuilt_bits.as<unsigned int>());
-    else cand_mark_kernel<false><<<sm * 3, 256, mark_smem, s>>>(st, hdr, t->model.as<float4>(), t->M, t->mats.as<float>(), t->fneeded.as<unsigned int>(), t->nranks, t->rank, t->fbuilt_bits.as<unsigned int>());
-    PFT_LAUNCH_CHECK();
-    stage_mark(t, "cand_mark_kernel");
-    cand_collect_kernel<<<sm * 2, 256, 0, s>>>(hdr, t->fneeded.as<unsigned int>(), t->fneeded_list.as<int>(), t->xcount.as<int>());
-    PFT_LAUNCH_CHECK();
-    stage_mark(t, "cand_collect_kernel");
+  if (build_lists) {
+    PFT_CUDA_TRY(cudaStreamWaitEvent(s, t->ev_join, 0));
+    stage_mark(t, "cand_mark+collect (beside the index)");
     cand_build_kernel<<<sm * 8, 256, 0, s>>>(hdr, t->cell_start.as<int>(), t->ipts.as<float4>(), t->max_dist * t->max_dist, t->flists.as<unsigned int>(),
                                             t->fneeded.as<unsigned int>(), t->fneeded_list.as<int>(), t->xcount.as<int>(), t->ffar_list.as<int>(),
                                             t->fcell_items.as<int2>(), t->fl1_slots.as<unsigned short>(), t->fbuilt_bits.as<unsigned int>());
@@ -708,9 +723,8 @@ int weight_phase_eval(pft_tracker* t, bool force_raw = false, bool reuse_allowed
   const bool lists_built = t->list_max_cells > 0 && t->list_mode && t->nn_mode == PFT_NN_EXACT;
   if (t->nn_mode == PFT_NN_PCL_APPROX) return weight_eval_pcl_approx(t, force_raw);
   WeightArgs a;
-  // the row-table kernel runs behind weight_lists_kernel unless the last state read-back says the lists are on
-  const bool fallback_kernel = !lists_built || t->lists_hint != 1;
-  a.st = st; a.hdr = hdr; a.pts2 = t->ipts2.as<float4>(); a.lists_kernel_ran = lists_built ? 1 : 0; a.fallback_follows = fallback_kernel ? 1 : 0;
+  const bool fallback_kernel = !lists_built;  // (weight_lists_kernel runs the row-table search itself when the index header says the lists are off)
+  a.st = st; a.hdr = hdr; a.pts2 = t->ipts2.as<float4>();
   a.flists = t->flists.as<unsigned int>(); a.pool = t->fpool.as<unsigned int>(); a.xlists = t->xlists.as<unsigned int>();
   a.cell_start = t->cell_start.as<int>(); a.pts = t->ipts.as<float4>();
   a.hsv = t->ihsv.as<unsigned int>(); a.table = t->row_table.as<RowEntry>(); a.smem_bytes = t->weight_smem;
@@ -730,7 +744,7 @@ int weight_phase_eval(pft_tracker* t, bool force_raw = false, bool reuse_allowed
     PFT_CUDA_TRY(cudaEventRecord(t->ev_w[2 * t->n_ev_used], s));
   }
   if (lists_built) {
-    // the product path: candidate lists (returns at once when the index header says they are off for this crop)
+    // the product path: candidate lists (the same launch runs the row-table search when the index header says they are off for this crop)
     a.smem_bytes = t->lists_smem;
     const long long n_local = std::max(1, (t->particle_num > 0 ? t->particle_num : t->n_cap) / t->nranks);
     const bool dyn_l = n_local * t->chunks >= dyn_per_warp * sm * (kListThreads / 32);
@@ -972,6 +986,7 @@ void pft_tracker_destroy(pft_tracker* t) {
   if (t->ev_c1) cudaEventDestroy(t->ev_c1);
   pft_tracker_peer_detach(t);
   if (t->batch_stream) cudaStreamDestroy(t->batch_stream);
+  if (t->aux_stream) { cudaStreamDestroy(t->aux_stream); cudaEventDestroy(t->ev_fork); cudaEventDestroy(t->ev_join); }
   if (t->batch_done) cudaEventDestroy(t->batch_done);
   release_all(t);
   delete t;
@@ -1259,10 +1274,6 @@ static int read_state(pft_tracker* t, TrackerState* host) {
   cudaStream_t s = t->run_stream();
   PFT_CUDA_TRY(cudaMemcpyAsync(t->ctx->pinned, t->st.p, sizeof(TrackerState), cudaMemcpyDeviceToHost, s));
   PFT_CUDA_TRY(cudaStreamSynchronize(s));
-  {
-    const int seen = reinterpret_cast<const TrackerState*>(t->ctx->pinned)->lists_on ? 1 : 0;
-    if (t->M > 0 && seen != t->lists_hint) { t->lists_hint = seen; invalidate_graph(t); }  // (the launch sequence of weight() changes)
-  }
   memcpy(host, t->ctx->pinned, sizeof(TrackerState));
   if (host->peer_error) { set_last_error("NVLink peer exchange timed out: a peer rank did not reach the same weight()"); return PFT_ERR_COMM; }
   return PFT_OK;

@@ -407,6 +407,7 @@ __global__ void index_begin_kernel(TrackerState* st, IndexHeader* hdr, int* cell
                                    int max_cells, int list_max_cells, int M, int nranks, int rank, unsigned int* needed_words,
                                    int* list_counters /* [0] extended lists handed out, [1] needed blocks, [2] cells queued for the far pass, [3] pool groups handed out, [4] cells queued for the octant pass */,
                                    unsigned int* built_bits /* one bit per fine cell: its lists exist (this frame) */, int reuse_allowed, float dilate,
+                                   int list_ratio /* the lists are built when this rank's queries outnumber the fine cells of the crop box by this factor */,
                                    const IndexHeader* __restrict__ hdr_prev /* header of the previous weight() (snapshot taken by index_scan_kernel:
                                                                                nothing writes it while this kernel runs, so every block derives the same header) */) {
   __shared__ IndexHeader h;
@@ -449,7 +450,7 @@ __global__ void index_begin_kernel(TrackerState* st, IndexHeader* hdr, int* cell
       for (int d = 0; d < 6; ++d) box[d] = st->aabb[d];
       compute_index_header(st->aabb, box, inv_leaf, base_level, max_cells, h);
       // (M == 0: the caller forces the lists on)
-      bool lists = h.valid && h.f_cells > 0 && h.f_cells <= list_max_cells && (M == 0 || n_local * (long long)M >= 2ll * h.f_cells);
+      bool lists = h.valid && h.f_cells > 0 && h.f_cells <= list_max_cells && (M == 0 || n_local * (long long)M >= (long long)list_ratio * h.f_cells);
       if (lists && dilate > 0.f) {
         // lists on: index the dilated box, so that the next weight() of the frame can reuse the index (when the dilated
         // box does not fit the list tables, the plain crop box is indexed and the next weight() rebuilds)
@@ -774,7 +775,7 @@ __global__ void __launch_bounds__(256) cand_mark_kernel(const TrackerState* __re
   __shared__ IndexHeader h;
   if (threadIdx.x == 0) h = *hdr;
   __syncthreads();
-  if (!h.valid || !lists_on(h)) return;
+  if (!h.valid || !h.use_lists) return;  // (not lists_on(): the indexed points are being counted beside this kernel)
   // one bit per fine cell: "nothing to do for this cell" -- its lists exist already (a weight() that reuses the index of
   // the frame), or (flag mode) this block has flagged it
   const bool use_bits = !COUNT || h.reuse;
@@ -834,7 +835,7 @@ __global__ void __launch_bounds__(256) cand_collect_kernel(const IndexHeader* __
   __shared__ IndexHeader h;
   if (threadIdx.x == 0) h = *hdr;
   __syncthreads();
-  if (!h.valid || !lists_on(h)) return;
+  if (!h.valid || !h.use_lists) return;
   const int fdx = h.f_dim[0], fdy = h.f_dim[1], fdz = h.f_dim[2];
   const int bdx = (fdx + 1) >> 1, bdy = (fdy + 1) >> 1, bdz = (fdz + 1) >> 1;
   const int nb = bdx * bdy * bdz;
@@ -1696,10 +1697,6 @@ struct WeightArgs {
   CoherenceParams co;
   int dbg_k; int* dbg_idx; float* dbg_d2;
   int smem_bytes;             // dynamic shared memory available for staging the index
-  int lists_kernel_ran;       // weight_lists_kernel precedes weight_kernel in the stream: whichever does not apply returns at once
-  int fallback_follows;       // weight_kernel follows weight_lists_kernel (0: the host expects the lists to be on and launches weight_lists_kernel
-                              // alone -- should they be off after all, it answers every query by brute force: slow, exact, and the host learns it
-                              // with the next state read-back)
 };
 
 // One (particle, model chunk) item by one warp: transform, nearest neighbour, coherence, warp reduction.
@@ -1792,17 +1789,12 @@ __device__ __forceinline__ void weight_items(const WeightArgs& a, const IndexHea
 }
 
 // Persistent launch: one CTA per SM, each warp works through (particle, model chunk) items.
-template <bool USE_HSV, int THREADS, bool DYN>
-__global__ void __launch_bounds__(THREADS, 1) weight_kernel(const WeightArgs a) {
+// The whole weight() of one CTA through the row-table search (crops the candidate lists do not cover).  h, the two
+// look-up tables and s_table live in the caller's shared memory; the tables are filled here.
+template <bool USE_HSV, bool DYN>
+__device__ __noinline__ void weight_rowtable_body(const WeightArgs a /* by value: a reference would pull the caller's kernel parameters into local memory */,
+                                                  const IndexHeader& h, float* lut_h, float* lut_s, RowEntry* s_table) {
   extern __shared__ uint4 dyn_smem[];
-  __shared__ IndexHeader h;
-  __shared__ float lut_h[256], lut_s[256];
-  __shared__ RowEntry s_table[kRows];
-  PFT_TRACE_MIN(9);
-  if (threadIdx.x == 0) h = *a.hdr;
-  __syncthreads();
-  PFT_TRACE_MAX(10);
-  if (a.lists_kernel_ran && lists_on(h)) return;  // this weight() was evaluated by weight_lists_kernel
   for (int i = threadIdx.x; i < kRows; i += blockDim.x) s_table[i] = a.table[i];
   if (USE_HSV) {
     for (int i = threadIdx.x; i < 256; i += blockDim.x) { lut_h[i] = (float)i / 180.0f; lut_s[i] = (float)i / 255.0f; }
@@ -1845,6 +1837,17 @@ __global__ void __launch_bounds__(THREADS, 1) weight_kernel(const WeightArgs a) 
   } else {
     weight_items<USE_HSV, DYN, int>(a, h, a.cell_start, a.pts, a.hsv, s_table, lut_h, lut_s);
   }
+}
+
+// Persistent launch of the row-table search alone (the host knows that no lists are built: PFT_CANDIDATE_LISTS = 0)
+template <bool USE_HSV, int THREADS, bool DYN>
+__global__ void __launch_bounds__(THREADS, 1) weight_kernel(const WeightArgs a) {
+  __shared__ IndexHeader h;
+  __shared__ float lut_h[256], lut_s[256];
+  __shared__ RowEntry s_table[kRows];
+  if (threadIdx.x == 0) h = *a.hdr;
+  __syncthreads();
+  weight_rowtable_body<USE_HSV, DYN>(a, h, lut_h, lut_s, s_table);
 }
 
 // ------------------------------------------------------------------ K3, list path: weight_lists_kernel
@@ -2095,11 +2098,18 @@ __global__ void __launch_bounds__(THREADS, 1) weight_lists_kernel(const WeightAr
   __shared__ IndexHeader h;
   __shared__ float lut_h[256], lut_s[256];
   __shared__ __align__(8) unsigned long long s_bar;
+  __shared__ RowEntry s_table[kRows];
   PFT_TRACE_MIN(3); PFT_TRACE_MAX(4);
   if (threadIdx.x == 0) h = *a.hdr;
   __syncthreads();
-  const bool brute = !lists_on(h);
-  if (brute && a.fallback_follows) return;  // weight_kernel (row-table search) evaluates this weight()
+  if (!lists_on(h)) {
+    // the index header says the lists are off for this crop (too few queries for the fine cells of the box, or a crop
+    // too large for the tables): the same launch runs the row-table search instead -- one kernel either way, the
+    // host never has to know
+    weight_rowtable_body<USE_HSV, DYN>(a, h, lut_h, lut_s, s_table);
+    return;
+  }
+  const bool brute = false;
   PFT_TRACE_MAX(5);
   const int n_pts = h.n_cropped + 1;  // + the dummy point that pads the lists
   const bool staged = 16ll * n_pts <= (long long)a.smem_bytes;
