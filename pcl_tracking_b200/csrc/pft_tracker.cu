@@ -141,6 +141,7 @@ struct pft_tracker {
   int nranks = 1, rank = 0;
   // NVLink peer exchange (pft_tracker_peer_*): the local window + the peers' windows mapped with CUDA IPC
   bool peer_mode = false;
+  bool peer_fused = false;  // inside compute(): the box exchange rides on aabb_kernel, the raw-weight push on normalize_kernel (the phase API keeps the separate kernels)
   void* peer_local = nullptr;
   size_t peer_bytes = 0;
   PeerSet peers{};
@@ -575,10 +576,10 @@ int weight_phase_box(pft_tracker* t) {
   stage_mark(t, "matrices_kernel");
   if (t->n_slots <= sm * 32) {
     aabb_kernel<4><<<std::min(t->n_slots, sm * 16), 128, 0, s>>>(st, t->model.as<float4>(), t->M, t->mats.as<float>(), t->slot_aabb.as<float>(), t->n_slots,
-                                                                t->nranks, t->rank);
+                                                                t->nranks, t->rank, t->peers, t->peer_fused ? 1 : 0);
   } else {
     aabb_kernel<1><<<std::min(t->n_slots, sm * 64), 32, 0, s>>>(st, t->model.as<float4>(), t->M, t->mats.as<float>(), t->slot_aabb.as<float>(), t->n_slots,
-                                                               t->nranks, t->rank);
+                                                               t->nranks, t->rank, t->peers, t->peer_fused ? 1 : 0);
   }
   PFT_LAUNCH_CHECK();
   stage_mark(t, "aabb_kernel");
@@ -589,6 +590,7 @@ int weight_phase_box(pft_tracker* t) {
 int weight_comm_box(pft_tracker* t) {
   cudaStream_t s = t->run_stream();
   TrackerState* st = t->st.as<TrackerState>();
+  if (t->peer_mode && t->peer_fused) return PFT_OK;  // (exchanged by the last block of aabb_kernel)
   if (t->peer_mode) {
     peer_box_exchange_kernel<<<1, 32, 0, s>>>(st, t->peers);
     PFT_LAUNCH_CHECK();
@@ -777,7 +779,7 @@ int weight_phase_eval(pft_tracker* t, bool force_raw = false, bool reuse_allowed
     stage_mark(t, "weight_kernel");
   }
   if (t->timing && !lists_built) { PFT_CUDA_TRY(cudaEventRecord(t->ev_w[2 * t->n_ev_used + 1], s)); t->n_ev_used++; }
-  if (t->nranks > 1 || force_raw) {  // (single rank: normalize_kernel sums the per-chunk partials itself)
+  if ((t->nranks > 1 || force_raw) && !(t->peer_mode && t->peer_fused && !force_raw)) {  // (single rank, or peer mode inside compute(): normalize_kernel sums the per-chunk partials itself)
     raw_weights_kernel<<<blocks_for(local_cap, 256, sm * 4), 256, 0, s>>>(st, t->partial.as<double>(), t->chunks, t->n_cap, t->raw.as<float>(), local_cap,
                                                                          t->nranks, t->rank, t->peers, t->peer_mode ? 1 : 0);
     PFT_LAUNCH_CHECK();
@@ -799,12 +801,15 @@ int weight_comm_raw(pft_tracker* t) {
 int weight_phase_normalize(pft_tracker* t, bool fuse_update = false) {
   int rc = check_weight_ready(t);
   if (rc) return rc;
+  const bool push = t->peer_mode && t->peer_fused && t->nn_mode == PFT_NN_EXACT;  // (the launch pushes this rank's raw weights to the peers itself)
   if (t->n_cap > kClusterMinParticles) normalize_kernel<kClusterCtas><<<kClusterCtas, 1024, 0, t->run_stream()>>>(t->st.as<TrackerState>(), t->parts[t->cur].as<DevParticle>(), t->raw.as<float>(), t->alpha, t->nranks,
                                                    t->slice_cap(), t->input->d_hdr(), t->peer_mode ? reinterpret_cast<PeerWindow*>(t->peer_local) : nullptr, t->M,
-                                                   t->nranks == 1 ? t->partial.as<double>() : nullptr, t->chunks, t->n_cap, t->raw.as<float>(), fuse_update ? 1 : 0);
+                                                   t->nranks == 1 ? t->partial.as<double>() : nullptr, t->chunks, t->n_cap, t->raw.as<float>(), fuse_update ? 1 : 0,
+                                                   t->peers, push ? t->partial.as<double>() : nullptr, t->rank);
   else normalize_kernel<1><<<1, 1024, 0, t->run_stream()>>>(t->st.as<TrackerState>(), t->parts[t->cur].as<DevParticle>(), t->raw.as<float>(), t->alpha, t->nranks,
                                                    t->slice_cap(), t->input->d_hdr(), t->peer_mode ? reinterpret_cast<PeerWindow*>(t->peer_local) : nullptr, t->M,
-                                                   t->nranks == 1 ? t->partial.as<double>() : nullptr, t->chunks, t->n_cap, t->raw.as<float>(), fuse_update ? 1 : 0);
+                                                   t->nranks == 1 ? t->partial.as<double>() : nullptr, t->chunks, t->n_cap, t->raw.as<float>(), fuse_update ? 1 : 0,
+                                                   t->peers, push ? t->partial.as<double>() : nullptr, t->rank);
   PFT_LAUNCH_CHECK();
   stage_mark(t, "normalize_kernel");
   t->changed = true;  // change detector is off upstream => changed_ = true after every weight()
@@ -845,9 +850,9 @@ int weight_phase_renormalize(pft_tracker* t) {
   PFT_LAUNCH_CHECK();
   stage_mark(t, "weights_to_raw_kernel");
   if (t->n_cap > kClusterMinParticles) normalize_kernel<kClusterCtas><<<kClusterCtas, 1024, 0, s>>>(st, parts, t->raw.as<float>(), t->alpha, t->nranks, t->slice_cap(), t->input->d_hdr(),
-                                                   nullptr, 0, nullptr, t->chunks, t->n_cap, t->raw.as<float>(), 0);
+                                                   nullptr, 0, nullptr, t->chunks, t->n_cap, t->raw.as<float>(), 0, t->peers, nullptr, t->rank);
   else normalize_kernel<1><<<1, 1024, 0, s>>>(st, parts, t->raw.as<float>(), t->alpha, t->nranks, t->slice_cap(), t->input->d_hdr(),
-                                              nullptr, 0, nullptr, t->chunks, t->n_cap, t->raw.as<float>(), 0);
+                                              nullptr, 0, nullptr, t->chunks, t->n_cap, t->raw.as<float>(), 0, t->peers, nullptr, t->rank);
   PFT_LAUNCH_CHECK();
   stage_mark(t, "normalize_kernel");
   t->changed = false;
@@ -856,6 +861,10 @@ int weight_phase_renormalize(pft_tracker* t) {
 
 int stage_weight(pft_tracker* t, bool fuse_update = false, bool reuse_allowed = false) {
   int rc;
+  // NVLink peer mode: weight() as a whole fuses the two exchanges into aabb_kernel / normalize_kernel; the phase API
+  // (pft_tracker_weight_phase: tests that emulate several ranks on one GPU) keeps the separate exchange kernels
+  struct Fused { pft_tracker* t; ~Fused() { t->peer_fused = false; } } fused{t};
+  t->peer_fused = t->peer_mode && t->nn_mode == PFT_NN_EXACT;
   if ((rc = weight_phase_box(t))) return rc;
   if ((rc = weight_comm_box(t))) return rc;
   if (t->use_cd && t->nranks > 1) { set_last_error("the change detector is not supported on a sharded tracker"); return PFT_ERR_STATE; }

@@ -47,6 +47,7 @@ struct TrackerState {
   int resample_n_old;            // particle count the running resample draws FROM (cdf_kernel publishes the new count for fixed-N trackers)
   unsigned int work_counter;     // next (particle, model chunk) item of the running weight kernel (reset by index_begin_kernel)
   unsigned long long evals;      // likelihood evaluations so far: sum over weight() calls of particles x model points (whole job)
+  unsigned int aabb_blocks_done; // blocks of the running aabb_kernel that have added their boxes (peer mode: the last one exchanges the box)
   int lists_on;                  // the last weight() ran on the candidate lists (read back with the state: the host then stops launching the row-table kernel behind weight_lists_kernel)
 };
 
@@ -82,8 +83,10 @@ __device__ __forceinline__ bool peer_wait(volatile unsigned int* flag, unsigned 
 }
 
 // crop box all-reduce over NVLink: one warp.  Runs right after aabb_kernel.
-__global__ void peer_box_exchange_kernel(TrackerState* st, PeerSet ps) {
-  const int lane = threadIdx.x;
+// Crop-box exchange by one warp: every rank stores its six values into slot [rank] of every window, raises every rank's
+// flag, waits for its own to show all ranks of this epoch, reduces locally (an all-reduce(min/max) without a collective).
+__device__ __forceinline__ void peer_box_exchange(TrackerState* st, const PeerSet& ps) {
+  const int lane = threadIdx.x & 31;
   PeerWindow* me = ps.win[ps.rank];
   unsigned int e = 0;
   if (lane == 0) { e = st->peer_epoch + 1u; st->peer_epoch = e; st->peer_blocks_done = 0u; }
@@ -92,7 +95,7 @@ __global__ void peer_box_exchange_kernel(TrackerState* st, PeerSet ps) {
   // lane = (destination rank, component): 8 floats to each of up to 4 ranks per pass
   for (int r0 = 0; r0 < ps.nranks; r0 += 4) {
     const int r = r0 + (lane >> 3), d = lane & 7;
-    if (r < ps.nranks && d < 6) ps.win[r]->box[cur][ps.rank][d] = st->aabb[d];
+    if (r < ps.nranks && d < 6) ps.win[r]->box[cur][ps.rank][d] = __ldcg(&st->aabb[d]);  // (L2: the other blocks of aabb_kernel wrote it with atomics)
   }
   // (the pattern NCCL's primitives use: the writers synchronise, ONE thread issues the system-scope fence -- it is
   //  cumulative over what the barrier ordered before it -- and only then are the flags raised)
@@ -113,6 +116,7 @@ __global__ void peer_box_exchange_kernel(TrackerState* st, PeerSet ps) {
     st->aabb[lane] = v;
   }
 }
+__global__ void peer_box_exchange_kernel(TrackerState* st, PeerSet ps) { peer_box_exchange(st, ps); }
 
 struct NoiseParams {      // host-precomputed square roots (IEEE, identical to the oracle's)
   double mean[6];
@@ -290,7 +294,8 @@ __global__ void matrices_kernel(TrackerState* st, const DevParticle* __restrict_
 // 1 for large ones (no block barrier).
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) aabb_kernel(TrackerState* st, const float4* __restrict__ model, int M, const float* __restrict__ mats,
-                                                          float* __restrict__ slot_aabb, int n_slots, int nranks, int rank) {
+                                                          float* __restrict__ slot_aabb, int n_slots, int nranks, int rank,
+                                                          PeerSet ps, int peer_exchange /* NVLink peer mode: the last block to finish exchanges the box with the other ranks */) {
   __shared__ float s_red[WARPS][6];
   const int n = st->particle_num;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -344,6 +349,18 @@ __global__ void __launch_bounds__(WARPS * 32) aabb_kernel(TrackerState* st, cons
   if (wid == 0 && un[0] <= ux[0]) {
     if (lane < 3) atomic_min_float(&st->aabb[lane], un[lane]);
     else if (lane < 6) atomic_max_float(&st->aabb[lane], ux[lane - 3]);
+  }
+  if (peer_exchange && wid == 0) {
+    // the block that finishes last holds this rank's complete box: its first warp runs the exchange (no extra launch)
+    unsigned int done = 0;
+    __syncwarp();
+    if (lane == 0) { __threadfence(); done = atomicAdd(&st->aabb_blocks_done, 1u) + 1u; }
+    done = __shfl_sync(kFull, done, 0);
+    if (done == gridDim.x) {
+      if (lane == 0) { st->aabb_blocks_done = 0u; __threadfence(); }
+      __syncwarp();
+      peer_box_exchange(st, ps);
+    }
   }
 }
 
@@ -2446,7 +2463,11 @@ normalize_kernel(TrackerState* st, DevParticle* parts, const float* raw, double 
                  const CloudHeader* __restrict__ scene_hdr, PeerWindow* peer_window /* non-null: wait for the peers' raw weights */, int M,
                  const double* __restrict__ partial /* non-null (single rank): the raw weights are summed here from the weight kernel's
                                                        per-chunk partials instead of by raw_weights_kernel */,
-                 int chunks, int n_max, float* raw_out, int fuse_update /* compute(): update() follows every weight(), do it in the same launch */) {
+                 int chunks, int n_max, float* raw_out, int fuse_update /* compute(): update() follows every weight(), do it in the same launch */,
+                 PeerSet ps, const double* __restrict__ push_partial /* non-null (NVLink peer mode): this rank's raw weights are summed from these
+                                                                       per-chunk partials and stored straight into EVERY rank's window first -- this
+                                                                       launch is the all-gather, no raw_weights_kernel in between */,
+                 int rank) {
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned int crank = cluster.block_rank();
   PFT_TRACE_MIN(11);
@@ -2454,6 +2475,21 @@ normalize_kernel(TrackerState* st, DevParticle* parts, const float* raw, double 
   __shared__ double s_part[3];  // this CTA's partial min, max, sum (read by the other CTAs of the cluster)
   __shared__ double s_upd[6];   // fused update(): this CTA's partial weighted state
   __shared__ double red6[192];
+  if (peer_window && push_partial) {
+    const int np = st->particle_num;
+    for (int l = crank * blockDim.x + threadIdx.x; rank + l * nranks < np; l += CTAS * blockDim.x) {
+      const int i = rank + l * nranks;
+      double v = 0.0;
+      for (int c = 0; c < chunks; ++c) v += push_partial[(size_t)c * n_max + i];
+      const float w = -(float)v;
+      for (int r = 0; r < nranks; ++r) ps.win[r]->raw[rank * slice_cap + l] = w;
+    }
+    cluster.sync();  // every store of this rank is issued ...
+    if (crank == 0 && threadIdx.x == 0) {
+      __threadfence_system();  // ... and ordered (cumulatively) before the flags
+      for (int r = 0; r < nranks; ++r) atomicAdd_system(&ps.win[r]->flag_raw, 1u);
+    }
+  }
   if (peer_window) {
     if (crank == 0 && threadIdx.x == 0) peer_wait(&peer_window->flag_raw, st->peer_epoch * (unsigned int)nranks, &st->peer_error);
     cluster.sync();

@@ -222,3 +222,23 @@ def test_pcl_approx_mode_differs_from_exact_and_tracks():
     gr, orr = g.getResult(), o.get_result()
     for k in ("x", "y", "z"):
         assert abs(float(gr[k]) - float(orr[k])) < 2e-3
+
+
+def test_lists_switch_off_and_on_again_on_one_tracker():
+    """The candidate lists are a per-weight() decision taken on the device (enough queries for the fine cells of the crop
+    box): one tracker goes through many particles (lists), a handful (row-table search inside the same kernel launch) and
+    many again, against the oracle driven through the same sequence (stale slots of the crop box included)."""
+    scene, model, centre = util.small_case(21, n_scene=6000, n_model=400)
+    g, o = util.make_pair(kld=True, particle_num=600, max_particle_num=600, use_hsv=True, oracle_nn=oracle.NN_EXACT_GRID)
+    g.setReferenceCloud(model); g.setInputCloud(pcl.PointCloud(scene))
+    o.set_reference(model); o.set_input(scene)
+    seen = []
+    for n, seed in ((600, 3), (8, 4), (600, 5), (12, 6)):
+        p = util.particles_around(centre, n, seed=seed)
+        g.setParticles(p); o.set_particles(p)
+        g.weight(); o.weight()
+        seen.append(g.indexInfo()["use_lists"])
+        np.testing.assert_array_equal(g.aabb(), o.aabb())
+        np.testing.assert_allclose(g.rawWeights(), o.raw_weights(), rtol=1e-5)
+        np.testing.assert_allclose(g.getParticles()["weight"], o.get_particles()["weight"], rtol=1e-5, atol=1e-12)
+    assert seen == [1, 0, 1, 0]
