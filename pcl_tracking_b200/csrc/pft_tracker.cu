@@ -1846,8 +1846,8 @@ __attribute__((visibility("default"))) int pft_debug_trace(unsigned long long* o
 // tuning builds only (not declared in pft.h): read and clear the search statistics
 __attribute__((visibility("default"))) int pft_debug_stats(unsigned long long* out16) {
   cudaDeviceSynchronize();
-  if (cudaMemcpyFromSymbol(out16, g_stats, sizeof(unsigned long long) * 16) != cudaSuccess) return -1;
-  unsigned long long z[16] = {0};
+  if (cudaMemcpyFromSymbol(out16, g_stats, sizeof(unsigned long long) * 48) != cudaSuccess) return -1;
+  unsigned long long z[48] = {0};
   cudaMemcpyToSymbol(g_stats, z, sizeof(z));
   return 0;
 }

@@ -611,7 +611,7 @@ __global__ void index_scatter_kernel(const float4* __restrict__ scene, const Clo
 // The index of a typical crop (a few thousand points: ~100 KB of points + ~50 KB of cell starts) is staged into
 // shared memory once per CTA by a persistent one-CTA-per-SM launch; larger indices are read through L1/L2.
 #ifdef PFT_STATS
-__device__ unsigned long long g_stats[16];
+__device__ unsigned long long g_stats[48];
 #define PFT_STAT(i, v) atomicAdd(&g_stats[i], (unsigned long long)(v))
 #else
 #define PFT_STAT(i, v)
@@ -868,10 +868,14 @@ __global__ void __launch_bounds__(256) cand_collect_kernel(const IndexHeader* __
         if (fx < fdx && fy < fdy && fz < fdz) {
           const int c = (fz * fdy + fy) * fdx + fx;
           if (needed[c] != 0u) any = true;
+#ifdef PFT_STATS
+          { const unsigned int q = needed[c]; if (q) { const int b = min(31 - __clz(q), 9); PFT_STAT(16 + b, 1); PFT_STAT(26 + b, q); } }
+#endif
         }
       }
     }
     const unsigned int bal = __ballot_sync(kFull, any);
+    PFT_STAT(36, any ? 1 : 0);
     if (bal) {
       int base = 0;
       if (lane == 0) base = atomicAdd(&list_counters[1], __popc(bal));

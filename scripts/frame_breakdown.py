@@ -69,6 +69,7 @@ def main():
     graph_ms = e0.elapsed_time(e1) / n_frames
     tracker.enableTiming(True)
     agg = collections.OrderedDict()
+    by_occ = collections.OrderedDict()  # (kernel, n-th launch of it in the frame): the iterations of a frame differ (index reuse)
     k1_ms = 0.0
     total = 0.0
     for k in range(n_frames):
@@ -87,6 +88,10 @@ def main():
             e[0] += 1
             e[1] += ms
             total += ms
+            occ[name] += 1
+            o = by_occ.setdefault((name, occ[name]), [0, 0.0])
+            o[0] += 1
+            o[1] += ms
     out = {"workload": workload, "particles": n_particles, "model_points": M, "frames": n_frames,
            "frame_ms_graph_replay": graph_ms, "frame_ms_stream_launched_sum": (total + k1_ms) / n_frames,
            "k1_downsample_ms_per_frame": k1_ms / n_frames, "index": tracker.indexInfo(), "kernels": {}}
@@ -100,6 +105,8 @@ def main():
         print("  %-28s %5.1f launches/frame  %8.2f us/launch  %8.2f us/frame  %5.1f%%"
               % (name, cnt / n_frames, 1e3 * ms / cnt, 1e3 * ms / n_frames, 100.0 * ms / (total + k1_ms)))
         out["kernels"][name] = {"launches_per_frame": cnt / n_frames, "us_per_launch": 1e3 * ms / cnt, "us_per_frame": 1e3 * ms / n_frames}
+    print("  launch order (us per launch, by occurrence in the frame):")
+    print("   " + "  ".join("%s#%d %.1f" % (name.replace("_kernel", ""), k, 1e3 * ms / cnt) for (name, k), (cnt, ms) in by_occ.items()))
     print(json.dumps(out))
     if world > 1:
         dist.barrier()

@@ -17,7 +17,7 @@ vg = pcl.ApproximateVoxelGrid(ctx=ctx); vg.setLeafSize(0.01); vg.setPassThrough(
 ds = pcl.PointCloud(ctx=ctx)
 dev = [pcl.PointCloud(f, ctx=ctx) for f in frames]
 lib = _capi.load()
-out = (C.c_ulonglong * 16)()
+out = (C.c_ulonglong * 48)()
 for k in range(12):
     vg.setInputCloud(dev[bench.frame_order(k, 6)]); vg.filter(ds)
     t.setInputCloud(ds); t.compute()
@@ -29,3 +29,4 @@ for k in range(12):
               "brute-force queries %d, mean extended scan length %.0f" % (k, v[12], v[5] / max(v[12], 1), v[3], 100.0 * v[3] / max(v[12], 1), v[6] / max(v[3], 1),
                                                                    v[13], 100.0 * v[13] / max(v[12] + v[13], 1), v[4], v[14] / max(v[13], 1)))
         print("   build: octant lists %d, mean length %.2f, longer than seven %d; cells built %d, far cells %d (extended %d)" % (v[2], v[1] / max(v[2], 1), v[0], v[15], v[10], v[11]))
+        print("   marked cells by queries per cell [1, 2-3, 4-7, ... >=512]: cells %s  queries %s; blocks %d" % (v[16:26], v[26:36], v[36]))
