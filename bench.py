@@ -389,7 +389,7 @@ def run_workload(rig, workload, steps, warmup, with_pipelined=True):
     frames, oid0 = rig.frames(n_objects, sensor)
     n_pts = len(frames[0])
     n_particles = {"c2": PARTICLES_PER_GPU * world, "c4": C4_PARTICLES, "c3": C3_MAX_PARTICLES, "c5": PARTICLES_PER_GPU, "qhd": 400}[workload]
-    scene_mode = args.scene or ("replicate" if args.exchange == "peer" else "broadcast")
+    scene_mode = args.scene or ("peer" if args.exchange == "peer" else "broadcast")
     owns_frames = rank == 0 or scene_mode == "replicate"
 
     trackers, M = [], 0
@@ -469,12 +469,21 @@ def run_workload(rig, workload, steps, warmup, with_pipelined=True):
     vg.setLeafSize(LEAF, LEAF, LEAF)
     vg.setPassThrough("z", 0.0, 10.0)
 
+    if world > 1 and scene_mode == "peer":
+        # the downsampled scene of every rank is mapped by rank 0 (CUDA IPC handles shipped by torch.distributed)
+        handles = [None] * world
+        dist.all_gather_object(handles, ds.peerExport(n_pts))
+        ds.peerAttach(handles, rank)
+        dist.barrier()
+
     def track(cloud):
         if owns_frames:
             vg.setInputCloud(cloud)
             vg.filter(ds)
         if world > 1 and scene_mode == "broadcast":
             ds.broadcast(n_pts, 0)
+        elif world > 1 and scene_mode == "peer":
+            ds.peerBroadcast(0)
         for t in trackers:
             t.setInputCloud(ds)
         compute_all()
@@ -665,9 +674,11 @@ def main():
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N>1: how the crop box and the raw weights travel between the GPUs: 'peer' = stores over NVLink from the "
                          "producing kernels into CUDA-IPC windows (no collective call per frame), 'nccl' = ncclAllReduce/ncclAllGather")
-    ap.add_argument("--scene", default=None, choices=["replicate", "broadcast"],
-                    help="N>1: every rank downsamples the frame itself (default with --exchange peer) or rank 0 does and "
-                         "broadcasts the result over NCCL (default with --exchange nccl)")
+    ap.add_argument("--scene", default=None, choices=["peer", "replicate", "broadcast"],
+                    help="N>1: how the downsampled scene reaches every GPU: 'peer' = rank 0 owns the sensor (one upload + downsample per "
+                         "frame for the whole job) and its push kernel stores the result into every rank's cloud over NVLink (default "
+                         "with --exchange peer); 'broadcast' = the same with ncclBroadcast (default with --exchange nccl); 'replicate' = "
+                         "every rank uploads and downsamples the frame itself")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -695,7 +706,7 @@ def main():
     from pcl_tracking_b200 import pcl
 
     ctx = pcl.Context(local_rank)
-    scene_mode = args.scene or ("replicate" if args.exchange == "peer" else "broadcast")
+    scene_mode = args.scene or ("peer" if args.exchange == "peer" else "broadcast")
     use_nccl = world > 1 and (args.exchange == "nccl" or scene_mode == "broadcast")
     uid = None
     if use_nccl:

@@ -330,6 +330,21 @@ PFT_API int pft_tracker_peer_export(pft_tracker* t, void* handle64);
 PFT_API int pft_tracker_peer_attach(pft_tracker* t, const void* handles /* nranks x PFT_PEER_HANDLE_BYTES */);
 PFT_API int pft_tracker_peer_detach(pft_tracker* t);
 
+/* Scene distribution by peer stores: ONE rank owns the sensor.  It uploads and downsamples the frame; its
+ * push kernel stores the downsampled cloud (points + header) straight into the same cloud of every other
+ * rank over NVLink and raises a flag there; the other ranks' streams wait on their flag.  One host->device
+ * copy per frame for the whole job, no collective call.  Call order on every rank: pft_cloud_peer_export
+ * (the same `capacity` everywhere; fixes the cloud's storage) -> the host framework all-gathers the
+ * PFT_CLOUD_PEER_HANDLE_BYTES handles in rank order -> pft_cloud_peer_attach -> per frame the root fills
+ * the cloud and EVERY rank calls pft_cloud_peer_broadcast (stream ordered).  The root must not refill the
+ * cloud before its peers have finished with the previous scene: a peer-mode tracker loop implies that
+ * (the last raw-weight exchange of a frame follows every rank's last read of the scene). */
+#define PFT_CLOUD_PEER_HANDLE_BYTES 192
+PFT_API int pft_cloud_peer_export(pft_cloud* cloud, size_t capacity, void* handles192);
+PFT_API int pft_cloud_peer_attach(pft_cloud* cloud, const void* handles /* nranks x PFT_CLOUD_PEER_HANDLE_BYTES */, int nranks, int rank);
+PFT_API int pft_cloud_peer_broadcast(pft_cloud* cloud, int root);
+PFT_API int pft_cloud_peer_detach(pft_cloud* cloud);
+
 #ifdef __cplusplus
 }
 #endif

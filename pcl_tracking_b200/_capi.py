@@ -32,6 +32,7 @@ USE_CHANGE_DETECTOR, CHANGE_DETECTOR_INTERVAL, CHANGE_DETECTOR_MIN_POINTS = 13, 
 CHANGE_DETECTOR_RESOLUTION = 32
 NN_EXACT, NN_PCL_APPROX = 0, 1
 PEER_HANDLE_BYTES = 64
+CLOUD_PEER_HANDLE_BYTES = 192
 SAMPLER_ALIAS_PCL, SAMPLER_CDF, SAMPLER_CDF_VDC = 0, 1, 2
 
 
@@ -124,6 +125,10 @@ SIGNATURES = {
     "pft_cloud_broadcast": (_i, [_vp, _sz, _i]),
     "pft_tracker_comm_init": (_i, [_vp, _i, _i, _vp]),
     "pft_tracker_comm_destroy": (_i, [_vp]),
+    "pft_cloud_peer_export": (_i, [_vp, _sz, _vp]),
+    "pft_cloud_peer_attach": (_i, [_vp, _vp, _i, _i]),
+    "pft_cloud_peer_broadcast": (_i, [_vp, _i]),
+    "pft_cloud_peer_detach": (_i, [_vp]),
     "pft_tracker_peer_export": (_i, [_vp, _vp]),
     "pft_tracker_peer_attach": (_i, [_vp, _vp]),
     "pft_tracker_peer_detach": (_i, [_vp]),

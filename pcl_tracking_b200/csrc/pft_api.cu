@@ -49,6 +49,10 @@ void DevBuf::release() {
 int pft_cloud::ensure(size_t cap) {
   int rc = hdr.reserve(sizeof(pft::CloudHeader));
   if (rc) return rc;
+  if (peer_exported && cap * sizeof(float4) > pts.bytes) {
+    pft::set_last_error("the cloud is mapped by its peers with room for %zu points; %zu do not fit (export it with a larger capacity)", peer_capacity, cap);
+    return PFT_ERR_CAPACITY;
+  }
   if (cap > capacity || !pts.p) {
     rc = pts.reserve((cap ? cap : 1) * sizeof(float4));
     if (rc) return rc;
@@ -211,6 +215,7 @@ void pft_cloud_destroy(pft_cloud* c) {
   cudaSetDevice(c->ctx->device);
   cudaStreamSynchronize(c->ctx->stream);
   if (c->ready) { cudaEventSynchronize(c->ready); cudaEventDestroy(c->ready); }
+  pft_cloud_peer_detach(c);
   c->pts.release();
   c->hdr.release();
   c->raw_staging.release();

@@ -61,6 +61,14 @@ struct pft_cloud {
   cudaEvent_t ready = nullptr;
   mutable bool upload_pending = false;
   int join_upload() const;
+  // scene distribution by peer stores (pft_cloud_peer_*): once exported the storage never moves
+  bool peer_exported = false, peer_attached = false;
+  size_t peer_capacity = 0;
+  int peer_nranks = 0, peer_rank = 0;
+  pft::DevBuf peer_sync;         // {flag, blocks done}
+  void* peer_pts[16] = {nullptr}; void* peer_hdr[16] = {nullptr}; void* peer_flag[16] = {nullptr};
+  unsigned int* peer_error = nullptr;  // host-mapped
+  unsigned int peer_epoch = 0;
   float4* d_pts() const { return pts.as<float4>(); }
   pft::CloudHeader* d_hdr() const { return hdr.as<pft::CloudHeader>(); }
   int ensure(size_t cap);

@@ -1833,6 +1833,126 @@ int pft_tracker_peer_detach(pft_tracker* t) {
   return PFT_OK;
 }
 
+// ------------------------------------------------------------------ scene distribution by peer stores
+// Call order on every rank: pft_cloud_peer_export (same capacity everywhere) -> the host framework all-gathers the
+// PFT_CLOUD_PEER_HANDLE_BYTES handles in rank order -> pft_cloud_peer_attach -> per frame: the root fills the cloud
+// (upload + downsample), every rank calls pft_cloud_peer_broadcast.  The root must not refill the cloud before every
+// peer has finished reading the previous scene: inside a peer-mode tracker loop that is implied (the root's last
+// normalize of a frame waits for every rank's raw weights, which a rank pushes after its last read of the scene);
+// elsewhere the caller orders it.
+int pft_cloud_peer_export(pft_cloud* c, size_t capacity, void* handles) {
+  if (!c || !handles) { set_last_error("null argument"); return PFT_ERR_INVALID; }
+  if (c->peer_attached) { set_last_error("the cloud's peer mappings are already attached"); return PFT_ERR_STATE; }
+  static_assert(3 * sizeof(cudaIpcMemHandle_t) == PFT_CLOUD_PEER_HANDLE_BYTES, "handle size");
+  PFT_CUDA_TRY(cudaSetDevice(c->ctx->device));
+  PFT_CUDA_TRY(cudaStreamSynchronize(c->ctx->stream));
+  if (!c->peer_exported) {
+    const size_t keep = c->capacity;
+    int rc = c->ensure(std::max(capacity, c->capacity));
+    if (rc) return rc;
+    c->capacity = keep;  // (ensure() records its argument as the point bound: the contents did not change)
+    if ((rc = c->peer_sync.reserve(2 * sizeof(unsigned int)))) return rc;
+    PFT_CUDA_TRY(cudaMemset(c->peer_sync.p, 0, 2 * sizeof(unsigned int)));
+    if (!c->peer_error) {
+      PFT_CUDA_TRY(cudaHostAlloc((void**)&c->peer_error, sizeof(unsigned int), cudaHostAllocMapped));
+      *c->peer_error = 0u;
+    }
+    PFT_CUDA_TRY(cudaDeviceSynchronize());
+    c->peer_capacity = c->pts.bytes / sizeof(float4);
+    c->peer_exported = true;
+  } else if (capacity > c->peer_capacity) {
+    set_last_error("the cloud was exported with room for %zu points", c->peer_capacity);
+    return PFT_ERR_CAPACITY;
+  }
+  cudaIpcMemHandle_t h[3];
+  PFT_CUDA_TRY(cudaIpcGetMemHandle(&h[0], c->pts.p));
+  PFT_CUDA_TRY(cudaIpcGetMemHandle(&h[1], c->hdr.p));
+  PFT_CUDA_TRY(cudaIpcGetMemHandle(&h[2], c->peer_sync.p));
+  memcpy(handles, h, sizeof(h));
+  return PFT_OK;
+}
+
+int pft_cloud_peer_attach(pft_cloud* c, const void* handles, int nranks, int rank) {
+  if (!c || !handles) { set_last_error("null argument"); return PFT_ERR_INVALID; }
+  if (!c->peer_exported) { set_last_error("pft_cloud_peer_export must precede pft_cloud_peer_attach"); return PFT_ERR_STATE; }
+  if (c->peer_attached) { set_last_error("the cloud's peer mappings are already attached"); return PFT_ERR_STATE; }
+  if (nranks < 2 || nranks > kMaxPeers || rank < 0 || rank >= nranks) { set_last_error("bad rank %d of %d (at most %d ranks)", rank, nranks, kMaxPeers); return PFT_ERR_INVALID; }
+  PFT_CUDA_TRY(cudaSetDevice(c->ctx->device));
+  void** maps[3] = {c->peer_pts, c->peer_hdr, c->peer_flag};
+  void* local[3] = {c->pts.p, c->hdr.p, c->peer_sync.p};
+  for (int r = 0; r < nranks; ++r) {
+    for (int k = 0; k < 3; ++k) {
+      if (r == rank) { maps[k][r] = local[k]; continue; }
+      cudaIpcMemHandle_t h;
+      memcpy(&h, (const char*)handles + (size_t)r * PFT_CLOUD_PEER_HANDLE_BYTES + (size_t)k * sizeof(h), sizeof(h));
+      void* p = nullptr;
+      cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) {
+        set_last_error("cudaIpcOpenMemHandle(rank %d) -> %s (scene distribution by peer stores needs NVLink/P2P between the GPUs of one node)", r, cudaGetErrorString(e));
+        cudaGetLastError();
+        c->peer_nranks = nranks; c->peer_rank = rank; c->peer_attached = true;
+        pft_cloud_peer_detach(c);  // closes what was opened so far
+        return PFT_ERR_COMM;
+      }
+      maps[k][r] = p;
+    }
+  }
+  c->peer_nranks = nranks; c->peer_rank = rank; c->peer_attached = true;
+  return PFT_OK;
+}
+
+int pft_cloud_peer_broadcast(pft_cloud* c, int root) {
+  if (!c) { set_last_error("null cloud"); return PFT_ERR_INVALID; }
+  if (!c->peer_attached) { set_last_error("pft_cloud_peer_attach must precede pft_cloud_peer_broadcast"); return PFT_ERR_STATE; }
+  if (root < 0 || root >= c->peer_nranks) { set_last_error("bad root %d", root); return PFT_ERR_INVALID; }
+  if (*(volatile unsigned int*)c->peer_error) {
+    *c->peer_error = 0u;
+    set_last_error(c->peer_rank == root ? "an earlier scene held more points than the peers' clouds have room for (%zu)" : "an earlier scene did not arrive within the time limit (rank %d gone?)",
+                   c->peer_rank == root ? c->peer_capacity : (size_t)root);
+    return c->peer_rank == root ? PFT_ERR_CAPACITY : PFT_ERR_COMM;
+  }
+  PFT_CUDA_TRY(cudaSetDevice(c->ctx->device));
+  cudaStream_t s = c->ctx->stream;
+  const unsigned int epoch = ++c->peer_epoch;
+  unsigned int* d_err = nullptr;
+  PFT_CUDA_TRY(cudaHostGetDevicePointer((void**)&d_err, c->peer_error, 0));
+  if (c->peer_rank == root) {
+    int jrc = c->join_upload();
+    if (jrc) return jrc;
+    CloudPeerSet ps{};
+    ps.nranks = c->peer_nranks; ps.rank = c->peer_rank;
+    for (int r = 0; r < c->peer_nranks; ++r) {
+      ps.pts[r] = reinterpret_cast<float4*>(c->peer_pts[r]); ps.hdr[r] = reinterpret_cast<CloudHeader*>(c->peer_hdr[r]);
+      ps.sync[r] = reinterpret_cast<unsigned int*>(c->peer_flag[r]);
+    }
+    const int grid = std::max(1, std::min(c->ctx->sm_count, (int)((std::max<size_t>(c->capacity, 1) + 255) / 256)));
+    cloud_push_kernel<<<grid, 256, 0, s>>>(c->d_pts(), c->d_hdr(), ps, epoch, (int)std::min<size_t>(c->peer_capacity, 0x7fffffff), d_err);
+    PFT_LAUNCH_CHECK();
+  } else {
+    cloud_wait_kernel<<<1, 1, 0, s>>>(c->peer_sync.as<unsigned int>(), epoch, d_err);
+    PFT_LAUNCH_CHECK();
+    c->host_n = -1;
+    c->capacity = c->peer_capacity;  // (the point count stays on the device: this is the host's bound)
+  }
+  return PFT_OK;
+}
+
+int pft_cloud_peer_detach(pft_cloud* c) {
+  if (!c) { set_last_error("null cloud"); return PFT_ERR_INVALID; }
+  if (!c->peer_exported && !c->peer_attached) return PFT_OK;
+  cudaSetDevice(c->ctx->device);
+  cudaStreamSynchronize(c->ctx->stream);
+  if (c->peer_attached) {
+    void** maps[3] = {c->peer_pts, c->peer_hdr, c->peer_flag};
+    for (int r = 0; r < c->peer_nranks; ++r)
+      for (int k = 0; k < 3; ++k) { if (r != c->peer_rank && maps[k][r]) cudaIpcCloseMemHandle(maps[k][r]); maps[k][r] = nullptr; }
+  }
+  c->peer_sync.release();
+  if (c->peer_error) { cudaFreeHost(c->peer_error); c->peer_error = nullptr; }
+  c->peer_exported = false; c->peer_attached = false; c->peer_nranks = 0; c->peer_epoch = 0;
+  return PFT_OK;
+}
+
 #ifdef PFT_TRACE
 // tuning builds only (not declared in pft.h): read and re-arm the stamps (even entries of a pair are minima, see the macros)
 __attribute__((visibility("default"))) int pft_debug_trace(unsigned long long* out64, const unsigned long long* init64) {

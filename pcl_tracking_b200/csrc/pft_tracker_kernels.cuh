@@ -118,6 +118,40 @@ __device__ __forceinline__ void peer_box_exchange(TrackerState* st, const PeerSe
 }
 __global__ void peer_box_exchange_kernel(TrackerState* st, PeerSet ps) { peer_box_exchange(st, ps); }
 
+// ---- scene distribution by peer stores: ONE rank owns the sensor (upload + downsample), its kernel stores the
+// downsampled cloud straight into the cloud of every other rank over NVLink (CUDA IPC mappings) and raises their
+// flags; the other ranks' streams wait on the flag.  No collective, no host round trip, one H2D copy per frame for
+// the whole job.
+struct CloudPeerSet {
+  float4* pts[kMaxPeers];
+  CloudHeader* hdr[kMaxPeers];
+  unsigned int* sync[kMaxPeers];  // [0] flag = number of the last scene that has fully arrived, [1] blocks done (root only)
+  int nranks, rank;
+};
+__global__ void __launch_bounds__(256) cloud_push_kernel(const float4* __restrict__ src, const CloudHeader* __restrict__ src_hdr, CloudPeerSet ps,
+                                                         unsigned int epoch, int capacity, unsigned int* error /* host-mapped */) {
+  int n = src_hdr->n;
+  if (n > capacity) { if (blockIdx.x == 0 && threadIdx.x == 0) *error = 1u; n = 0; }  // (loud on the host at the next call; the peers see an empty scene)
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 p = src[i];
+    for (int r = 0; r < ps.nranks; ++r) if (r != ps.rank) ps.pts[r][i] = p;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < ps.nranks && (int)threadIdx.x != ps.rank) { CloudHeader h = *src_hdr; h.n = n; *ps.hdr[threadIdx.x] = h; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();  // one system-scope fence per block, after the barrier (cumulative over the block's stores)
+    unsigned int* mine = ps.sync[ps.rank];
+    if (atomicAdd(&mine[1], 1u) + 1u == gridDim.x) {  // every block has pushed its part
+      mine[1] = 0u;
+      __threadfence_system();
+      for (int r = 0; r < ps.nranks; ++r) if (r != ps.rank) atomicExch_system(&ps.sync[r][0], epoch);
+    }
+  }
+}
+__global__ void cloud_wait_kernel(unsigned int* sync, unsigned int epoch, unsigned int* error /* host-mapped */) {
+  peer_wait(&sync[0], epoch, error);
+}
+
 struct NoiseParams {      // host-precomputed square roots (IEEE, identical to the oracle's)
   double mean[6];
   double sigma[6];        // sqrt(cov[d])

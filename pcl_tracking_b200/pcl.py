@@ -156,6 +156,28 @@ class PointCloud:
         check(capi.load().pft_cloud_broadcast(self._h, int(capacity), int(root)))
         return self
 
+    # scene distribution by peer stores: one rank owns the sensor, its kernel stores the cloud into every rank's copy
+    def peerExport(self, capacity):
+        """Fixes this cloud's storage at `capacity` points (the same on every rank) and returns its CUDA IPC handles (bytes)."""
+        buf = C.create_string_buffer(capi.CLOUD_PEER_HANDLE_BYTES)
+        check(capi.load().pft_cloud_peer_export(self._h, int(capacity), buf))
+        return bytes(buf.raw)
+
+    def peerAttach(self, handles, rank):
+        """`handles`: the peerExport() results of all ranks in rank order (e.g. dist.all_gather_object)."""
+        blob = b"".join(bytes(h) for h in handles)
+        buf = C.create_string_buffer(blob, len(blob))
+        check(capi.load().pft_cloud_peer_attach(self._h, buf, len(handles), int(rank)))
+        return self
+
+    def peerBroadcast(self, root=0):
+        """Stream ordered; every rank calls it once per scene: the root pushes its contents over NVLink, the others wait for them."""
+        check(capi.load().pft_cloud_peer_broadcast(self._h, int(root)))
+        return self
+
+    def peerDetach(self):
+        check(capi.load().pft_cloud_peer_detach(self._h))
+
     def size(self):
         n = C.c_size_t()
         check(capi.load().pft_cloud_size(self._h, C.byref(n)))
