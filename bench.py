@@ -321,6 +321,7 @@ class Rig:
 
     def __init__(self, args, torch, dist, ctx, stream, rank, world, local_rank, uid):
         self.args, self.torch, self.dist, self.ctx, self.stream = args, torch, dist, ctx, stream
+        self.devices = [int(d) for d in args.devices.split(",")] if getattr(args, "devices", None) else None
         self.rank, self.world, self.local_rank, self.uid = rank, world, local_rank, uid
         self.flush_buf = None if args.no_flush else torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
         self._frames = {}
@@ -388,7 +389,7 @@ def run_workload(rig, workload, steps, warmup, with_pipelined=True):
     n_objects = C5_OBJECTS if workload == "c5" else 1
     frames, oid0 = rig.frames(n_objects, sensor)
     n_pts = len(frames[0])
-    n_particles = {"c2": PARTICLES_PER_GPU * world, "c4": C4_PARTICLES, "c3": C3_MAX_PARTICLES, "c5": PARTICLES_PER_GPU, "qhd": 400}[workload]
+    n_particles = {"c2": PARTICLES_PER_GPU * world * (len(rig.devices) if rig.devices else 1), "c4": C4_PARTICLES, "c3": C3_MAX_PARTICLES, "c5": PARTICLES_PER_GPU, "qhd": 400}[workload]
     scene_mode = args.scene or ("peer" if args.exchange == "peer" else "broadcast")
     owns_frames = rank == 0 or scene_mode == "replicate"
 
@@ -412,7 +413,7 @@ def run_workload(rig, workload, steps, warmup, with_pipelined=True):
         model_cloud, centroid = pcl.prepare_model(raw_model_cloud, LEAF, ctx=ctx)
         M += model_cloud.size()
         if workload in ("c3", "qhd"):
-            tracker = pcl.KLDAdaptiveParticleFilterOMPTracker(16, ctx=ctx)
+            tracker = pcl.KLDAdaptiveParticleFilterOMPTracker(16, ctx=ctx, devices=rig.devices)
             if workload == "c3":
                 pcl.configure_like_reference(tracker, particle_num=n_particles, max_particle_num=n_particles, use_hsv=True, iteration_num=ITERATIONS)
                 tracker.setEpsilon(args.kld_epsilon)
@@ -420,7 +421,7 @@ def run_workload(rig, workload, steps, warmup, with_pipelined=True):
             else:  # the reference's literal configuration (ref: src/auto_tracking.cpp:211-231, :775)
                 pcl.configure_like_reference(tracker, particle_num=400, max_particle_num=500, use_hsv=True, iteration_num=ITERATIONS)
         else:
-            tracker = pcl.ParticleFilterOMPTracker(16, ctx=ctx)
+            tracker = pcl.ParticleFilterOMPTracker(16, ctx=ctx, devices=rig.devices)
             pcl.configure_like_reference(tracker, particle_num=n_particles, use_hsv=True, iteration_num=ITERATIONS)
         m = np.eye(4, dtype=np.float32)
         m[:3, 3] = centroid
@@ -577,7 +578,7 @@ def run_workload(rig, workload, steps, warmup, with_pipelined=True):
             w_ms += a
             c_ms += b
             n_w += ITERATIONS
-    evals_per_launch = float(eval_count() - evals0) / max(n_w, 1) / world  # this rank's share of every weight()
+    evals_per_launch = float(eval_count() - evals0) / max(n_w, 1) / (world * (len(rig.devices) if rig.devices else 1))  # this rank's share of every weight()
     for t in trackers:
         t.enableTiming(False)
     info = tracker.indexInfo()
@@ -653,8 +654,9 @@ def workload_config(args, workload, M, n_particles, n_pts=217088, scene_mode="re
     return {
         "workload": names[workload],
         "scene_points": n_pts, "model_points": M, "particles_total": n_particles, "iterations_per_frame": ITERATIONS,
-        "leaf_m": LEAF, "max_distance_m": 0.1, "l2": "flushed between timed steps (256 MiB write)", "parallelism": "particle-shard x%d" % args.gpus + ("" if args.gpus == 1 else
-                                                                 ", %s exchange, scene %s" % (args.exchange, scene_mode)),
+        "leaf_m": LEAF, "max_distance_m": 0.1, "l2": "flushed between timed steps (256 MiB write)", "parallelism": ("particle-shard x%d, ONE process driving devices %s (pft_tracker_set_devices: windows mapped directly, scene by peer copy)"
+                                                                                               % (len(args.devices.split(",")), args.devices)) if getattr(args, "devices", None) else
+                       "particle-shard x%d" % args.gpus + ("" if args.gpus == 1 else ", %s exchange, scene %s" % (args.exchange, scene_mode)),
     }
 
 
@@ -674,6 +676,9 @@ def main():
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N>1: how the crop box and the raw weights travel between the GPUs: 'peer' = stores over NVLink from the "
                          "producing kernels into CUDA-IPC windows (no collective call per frame), 'nccl' = ncclAllReduce/ncclAllGather")
+    ap.add_argument("--devices", default=None, help="single-process multi-device mode (not the driver's launch): ONE process, ONE tracker object "
+                                                   "per tracked object, driving these GPUs (e.g. 0,1; first = this process's device) through "
+                                                   "pft_tracker_set_devices; the workload is sharded as with --gpus N under torchrun")
     ap.add_argument("--scene", default=None, choices=["peer", "replicate", "broadcast"],
                     help="N>1: how the downsampled scene reaches every GPU: 'peer' = rank 0 owns the sensor (one upload + downsample per "
                          "frame for the whole job) and its push kernel stores the result into every rank's cloud over NVLink (default "
@@ -723,7 +728,7 @@ def main():
     head = run_workload(rig, args.workload, args.steps, args.warmup)
     line = None
     if rank == 0:
-        line = {"metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": head["warmup"],
+        line = {"metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": world * (len(args.devices.split(",")) if args.devices else 1), "steps": args.steps, "warmup": head["warmup"],
                 "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": head["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic"}
         line.update({k: v for k, v in head.items() if k not in line})
     # ---- the other BASELINE configs, in the same line (each with its own value / e2e / roofline / clocks)

@@ -95,6 +95,25 @@ class Context {
   pft_context* h_ = nullptr;
 };
 
+// GPUs driven by every tracker constructed afterwards (single-process multi-device mode, pft_tracker_set_devices)
+inline std::vector<int>& trackerDevices() {
+  static std::vector<int> devs = [] {
+    std::vector<int> v;
+    if (const char* e = std::getenv("PFT_DEVICES")) {
+      for (const char* p = e; *p;) {
+        char* end = nullptr;
+        const long d = std::strtol(p, &end, 10);
+        if (end == p) break;
+        v.push_back((int)d);
+        p = (*end == ',') ? end + 1 : end;
+      }
+    }
+    return v;
+  }();
+  return devs;
+}
+inline void setTrackerDevices(const std::vector<int>& devices) { trackerDevices() = devices; }
+
 }  // namespace pft
 
 #ifndef PFT_SHIM_USE_PCL_TYPES
@@ -539,6 +558,10 @@ class ParticleFilterTracker {
  protected:
   ParticleFilterTracker(unsigned int nr_threads, int kld) {
     pft::check(pft_tracker_create(pft::Context::Default()->get(), kld, &h_));
+    // single-process multi-device mode: the reference's constructor call (ref :201, :215) cannot name GPUs, so the
+    // list comes from pft::setTrackerDevices({0, 1, ...}) or the environment (PFT_DEVICES=0,1,...); first = device 0
+    const std::vector<int>& devs = pft::trackerDevices();
+    if (devs.size() > 1) pft::check(pft_tracker_set_devices(h_, (int)devs.size(), devs.data()));
     si(PFT_THREADS, (int)nr_threads);
   }
   void si(int k, int v) { pft::check(pft_tracker_set_i(h_, k, v)); }

@@ -345,6 +345,17 @@ PFT_API int pft_cloud_peer_attach(pft_cloud* cloud, const void* handles /* nrank
 PFT_API int pft_cloud_peer_broadcast(pft_cloud* cloud, int root);
 PFT_API int pft_cloud_peer_detach(pft_cloud* cloud);
 
+/* Single-process multi-device mode: ONE tracker object drives n GPUs of the node (the reference is one process:
+ * ref src/auto_tracking.cpp).  The tracker becomes rank 0 on devices[0] (= the device of its context); the
+ * library creates a follower tracker per further device, shards the particles over them (particle i on rank
+ * i % n), maps the exchange windows of weight() directly (cudaDeviceEnablePeerAccess; no IPC, no second
+ * process) and copies the model and every frame's scene to the other devices itself.  Must be the first call
+ * on a new tracker; the setters called afterwards are forwarded.  compute() enqueues one frame on every
+ * device; results are bit-identical to the single-GPU run.  The stage-by-stage API is not forwarded. */
+PFT_API int pft_tracker_set_devices(pft_tracker* t, int n, const int* devices);
+/* the library-owned tracker of rank 1 .. n-1 (borrowed handle, for the getters: every rank holds the same replicated state) */
+PFT_API int pft_tracker_get_follower(pft_tracker* t, int rank, pft_tracker** out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -129,6 +129,8 @@ SIGNATURES = {
     "pft_cloud_peer_attach": (_i, [_vp, _vp, _i, _i]),
     "pft_cloud_peer_broadcast": (_i, [_vp, _i]),
     "pft_cloud_peer_detach": (_i, [_vp]),
+    "pft_tracker_set_devices": (_i, [_vp, _i, _vp]),
+    "pft_tracker_get_follower": (_i, [_vp, _i, _vp]),
     "pft_tracker_peer_export": (_i, [_vp, _vp]),
     "pft_tracker_peer_attach": (_i, [_vp, _vp]),
     "pft_tracker_peer_detach": (_i, [_vp]),

@@ -141,6 +141,11 @@ struct pft_tracker {
   int nranks = 1, rank = 0;
   // NVLink peer exchange (pft_tracker_peer_*): the local window + the peers' windows mapped with CUDA IPC
   bool peer_mode = false;
+  bool peer_ipc = true;       // the peers' windows were opened with CUDA IPC (false: same process, mapped directly)
+  // single-process multi-device mode (pft_tracker_set_devices): this tracker is rank 0; one follower per further device
+  struct Follower { pft_context* ctx = nullptr; pft_tracker* t = nullptr; pft_cloud* scene = nullptr; pft_cloud* model = nullptr; cudaEvent_t scene_ready = nullptr, scene_free = nullptr; bool free_recorded = false; };
+  std::vector<Follower> followers;
+  bool md_attached = false, md_prepared = false;
   bool peer_fused = false;  // inside compute(): the box exchange rides on aabb_kernel, the raw-weight push on normalize_kernel (the phase API keeps the separate kernels)
   void* peer_local = nullptr;
   size_t peer_bytes = 0;
@@ -968,6 +973,21 @@ bool is_noop(const pft_tracker* t) {
 
 // ------------------------------------------------------------------ C ABI
 extern "C" {
+static int copy_cloud_to_device(const pft_cloud* src, pft_cloud* dst, cudaEvent_t ready, cudaEvent_t dst_free);
+static int compute_multi_device(pft_tracker* t);
+static void destroy_followers(pft_tracker* t) {
+  for (auto& f : t->followers) {
+    if (f.t) pft_tracker_destroy(f.t);
+    if (f.scene) pft_cloud_destroy(f.scene);
+    if (f.model) pft_cloud_destroy(f.model);
+    if (f.scene_ready) cudaEventDestroy(f.scene_ready);
+    if (f.scene_free) cudaEventDestroy(f.scene_free);
+    if (f.ctx) pft_context_destroy(f.ctx);
+  }
+  t->followers.clear();
+  t->md_attached = false;
+}
+
 
 int pft_tracker_create(pft_context* ctx, int kld, pft_tracker** out) {
   if (!ctx || !out) { set_last_error("pft_tracker_create: null argument"); return PFT_ERR_INVALID; }
@@ -986,6 +1006,9 @@ int pft_tracker_create(pft_context* ctx, int kld, pft_tracker** out) {
 
 void pft_tracker_destroy(pft_tracker* t) {
   if (!t) return;
+  // multi-device mode: the followers go first -- they read this tracker's window until their streams are idle
+  for (auto& f : t->followers) if (f.t) { cudaSetDevice(f.ctx->device); cudaStreamSynchronize(f.t->run_stream()); }
+  destroy_followers(t);
   cudaSetDevice(t->ctx->device);
   cudaStreamSynchronize(t->run_stream());
   for (int g = 0; g < 2; ++g) if (t->graph_exec[g]) cudaGraphExecDestroy(t->graph_exec[g]);
@@ -1002,6 +1025,7 @@ void pft_tracker_destroy(pft_tracker* t) {
 }
 
 int pft_tracker_set_i(pft_tracker* t, int key, int v) {
+  if (t) for (auto& f_ : t->followers) { int rc_ = pft_tracker_set_i(f_.t, key, v); if (rc_) return rc_; }
   if (!t) { set_last_error("null tracker"); return PFT_ERR_INVALID; }
   switch (key) {
     case PFT_THREADS: t->threads = v; break;  // OpenMP thread count of the CPU tracker: meaningless here
@@ -1046,6 +1070,7 @@ int pft_tracker_set_i(pft_tracker* t, int key, int v) {
 }
 
 int pft_tracker_set_d(pft_tracker* t, int key, double v) {
+  if (t) for (auto& f_ : t->followers) { int rc_ = pft_tracker_set_d(f_.t, key, v); if (rc_) return rc_; }
   if (!t) { set_last_error("null tracker"); return PFT_ERR_INVALID; }
   switch (key) {
     case PFT_DELTA: t->delta = v; break;
@@ -1077,6 +1102,7 @@ int pft_tracker_set_d(pft_tracker* t, int key, double v) {
 }
 
 int pft_tracker_set_vec6(pft_tracker* t, int key, const double* v) {
+  if (t) for (auto& f_ : t->followers) { int rc_ = pft_tracker_set_vec6(f_.t, key, v); if (rc_) return rc_; }
   if (!t || !v) { set_last_error("null argument"); return PFT_ERR_INVALID; }
   switch (key) {
     case PFT_STEP_NOISE_COV: memcpy(t->step_cov, v, sizeof(t->step_cov)); break;
@@ -1090,6 +1116,7 @@ int pft_tracker_set_vec6(pft_tracker* t, int key, const double* v) {
 }
 
 int pft_tracker_set_trans(pft_tracker* t, const float* m12) {
+  if (t) for (auto& f_ : t->followers) { int rc_ = pft_tracker_set_trans(f_.t, m12); if (rc_) return rc_; }
   if (!t || !m12) { set_last_error("null argument"); return PFT_ERR_INVALID; }
   memcpy(t->trans, m12, sizeof(t->trans));
   return PFT_OK;
@@ -1126,6 +1153,11 @@ static int set_reference_device(pft_tracker* t, const float4* d_pts, int n) {
 int pft_tracker_set_reference_cloud(pft_tracker* t, const pft_cloud* cloud) {
   if (!t || !cloud) { set_last_error("null argument"); return PFT_ERR_INVALID; }
   if (cloud->ctx != t->ctx) { set_last_error("cloud belongs to another context"); return PFT_ERR_INVALID; }
+  for (auto& f_ : t->followers) {  // multi-device: every device gets its own copy of the model
+    int rc_ = copy_cloud_to_device(cloud, f_.model, nullptr, nullptr);
+    if (!rc_) rc_ = pft_tracker_set_reference_cloud(f_.t, f_.model);
+    if (rc_) return rc_;
+  }
   PFT_CUDA_TRY(cudaSetDevice(t->ctx->device));
   size_t n = 0;
   int rc = pft_cloud_size(const_cast<pft_cloud*>(cloud), &n);
@@ -1134,6 +1166,7 @@ int pft_tracker_set_reference_cloud(pft_tracker* t, const pft_cloud* cloud) {
 }
 
 int pft_tracker_set_reference_points(pft_tracker* t, const void* host_points, size_t n, int layout) {
+  if (t) for (auto& f_ : t->followers) { int rc_ = pft_tracker_set_reference_points(f_.t, host_points, n, layout); if (rc_) return rc_; }
   if (!t || (n && !host_points)) { set_last_error("null argument"); return PFT_ERR_INVALID; }
   PFT_CUDA_TRY(cudaSetDevice(t->ctx->device));
   pft_cloud tmp;
@@ -1149,6 +1182,7 @@ int pft_tracker_set_reference_points(pft_tracker* t, const void* host_points, si
 int pft_tracker_set_input_cloud(pft_tracker* t, const pft_cloud* cloud) {
   if (!t) { set_last_error("null tracker"); return PFT_ERR_INVALID; }
   if (cloud && cloud->ctx != t->ctx) { set_last_error("cloud belongs to another context"); return PFT_ERR_INVALID; }
+  for (auto& f_ : t->followers) f_.t->input = cloud ? f_.scene : nullptr;  // (the mirror is refilled by every compute())
   t->input = cloud;
   return PFT_OK;
 }
@@ -1227,8 +1261,156 @@ static int compute_one(pft_tracker* t) {
   return PFT_OK;
 }
 
+// ---- single-process multi-device mode
+// Copies a cloud (header + its host-known capacity of points) into a cloud of another context / device, ordered on the
+// two context streams by events: the source stream waits until the destination's earlier readers are done
+// (`dst_free`, if recorded), copies, and the destination stream waits for the copy (`ready`).
+static int copy_cloud_to_device(const pft_cloud* src, pft_cloud* dst, cudaEvent_t ready, cudaEvent_t dst_free) {
+  PFT_CUDA_TRY(cudaSetDevice(dst->ctx->device));
+  int rc = dst->ensure(std::max<size_t>(src->capacity, 1));
+  if (rc) return rc;
+  PFT_CUDA_TRY(cudaSetDevice(src->ctx->device));
+  if ((rc = src->join_upload())) return rc;
+  cudaStream_t ss = src->ctx->stream;
+  if (dst_free) PFT_CUDA_TRY(cudaStreamWaitEvent(ss, dst_free, 0));
+  PFT_CUDA_TRY(cudaMemcpyPeerAsync(dst->hdr.p, dst->ctx->device, src->hdr.p, src->ctx->device, sizeof(CloudHeader), ss));
+  if (src->capacity) PFT_CUDA_TRY(cudaMemcpyPeerAsync(dst->pts.p, dst->ctx->device, src->pts.p, src->ctx->device, src->capacity * sizeof(float4), ss));
+  dst->host_n = src->host_n;
+  dst->capacity = src->capacity;
+  if (ready) {
+    PFT_CUDA_TRY(cudaEventRecord(ready, ss));
+    PFT_CUDA_TRY(cudaSetDevice(dst->ctx->device));
+    PFT_CUDA_TRY(cudaStreamWaitEvent(dst->ctx->stream, ready, 0));
+  } else {
+    PFT_CUDA_TRY(cudaStreamSynchronize(ss));
+  }
+  return PFT_OK;
+}
+
+static int alloc_peer_window(pft_tracker* t);
+// Loads every kernel of the tracker path on the current device (CUDA loads kernels lazily, on first launch, and that
+// load may synchronise the context: with several ranks in one process a rank whose kernel spins on a peer flag must
+// never be waited for by the host -- see compute_multi_device).
+static int preload_kernels() {
+  static const void* const kernels[] = {
+      (const void*)aabb_kernel<1>,
+      (const void*)aabb_kernel<4>,
+      (const void*)alias_table_kernel,
+      (const void*)bitonic_sort_kernel,
+      (const void*)cand_build_far_kernel,
+      (const void*)cand_build_kernel,
+      (const void*)cand_collect_kernel,
+      (const void*)cand_mark_kernel<false>,
+      (const void*)cand_mark_kernel<true>,
+      (const void*)cand_octant_kernel,
+      (const void*)cdf_kernel<1>,
+      (const void*)cdf_kernel<kClusterCtas>,
+      (const void*)change_detect_kernel,
+      (const void*)cloud_push_kernel,
+      (const void*)cloud_wait_kernel,
+      (const void*)draws_kernel,
+      (const void*)index_begin_kernel,
+      (const void*)index_count_kernel,
+      (const void*)index_scan_kernel,
+      (const void*)index_scatter_kernel,
+      (const void*)init_particles_kernel,
+      (const void*)kld_insert_kernel,
+      (const void*)kld_stop_kernel,
+      (const void*)matrices_kernel,
+      (const void*)model_bbox_kernel,
+      (const void*)model_gather_kernel,
+      (const void*)model_keys_kernel,
+      (const void*)normalize_kernel<1>,
+      (const void*)normalize_kernel<kClusterCtas>,
+      (const void*)octree_build_kernel,
+      (const void*)peer_box_exchange_kernel,
+      (const void*)raw_weights_kernel,
+      (const void*)resample_kernel,
+      (const void*)result_box_kernel,
+      (const void*)single_matrix_kernel,
+      (const void*)update_kernel<1>,
+      (const void*)update_kernel<kClusterCtas>,
+      (const void*)weight_approx_kernel,
+      (const void*)weight_kernel<false, kWeightThreads, true>,
+      (const void*)weight_kernel<false, kWeightThreadsSmall, false>,
+      (const void*)weight_kernel<true, kWeightThreads, true>,
+      (const void*)weight_kernel<true, kWeightThreadsSmall, false>,
+      (const void*)weight_lists_kernel<false, kListThreads, false>,
+      (const void*)weight_lists_kernel<false, kListThreads, true>,
+      (const void*)weight_lists_kernel<false, kListThreadsBig, true>,
+      (const void*)weight_lists_kernel<true, kListThreads, false>,
+      (const void*)weight_lists_kernel<true, kListThreads, true>,
+      (const void*)weight_lists_kernel<true, kListThreadsBig, true>,
+      (const void*)weights_to_raw_kernel};
+  for (const void* k : kernels) {
+    cudaFuncAttributes a;
+    PFT_CUDA_TRY(cudaFuncGetAttributes(&a, k));
+  }
+  return PFT_OK;
+}
+
+// One process, several GPUs: the follower trackers are ordinary sharded trackers whose exchange windows are mapped
+// directly (peer access, no IPC).  Per frame: the scene travels to every device (peer copy, event ordered), then one
+// frame is enqueued on every device -- nothing here blocks the host, the kernels of the ranks meet through the
+// windows exactly as separate processes do.
+static int compute_multi_device(pft_tracker* t) {
+  if (is_noop(t)) return PFT_OK;
+  const int n = (int)t->followers.size() + 1;
+  int rc;
+  if (!t->md_attached) {
+    std::vector<pft_tracker*> all{t};
+    for (auto& f : t->followers) all.push_back(f.t);
+    for (pft_tracker* x : all) {
+      PFT_CUDA_TRY(cudaSetDevice(x->ctx->device));
+      if ((rc = alloc_peer_window(x))) return rc;
+    }
+    for (int r = 0; r < n; ++r) {
+      PeerSet ps{};
+      ps.nranks = n; ps.rank = r;
+      for (int q = 0; q < n; ++q) ps.win[q] = reinterpret_cast<PeerWindow*>(all[q]->peer_local);
+      all[r]->peers = ps; all[r]->peer_mode = true; all[r]->peer_ipc = false;
+      invalidate_graph(all[r]);
+    }
+    t->md_attached = true;
+  }
+  for (auto& f : t->followers) {
+    if ((rc = copy_cloud_to_device(t->input, f.scene, f.scene_ready, f.free_recorded ? f.scene_free : nullptr))) return rc;
+    f.t->input = f.scene;
+  }
+  // Everything that may allocate, free or load code happens for EVERY rank before the first frame is enqueued: once a
+  // rank's frame is in flight its kernels spin on peer flags until the other ranks' frames arrive, and a host call that
+  // waits for the device (cudaFree, a lazy kernel load) in between would stall until their time limit.
+  {
+    std::vector<pft_tracker*> all{t};
+    for (auto& f : t->followers) all.push_back(f.t);
+    for (pft_tracker* x : all) {
+      PFT_CUDA_TRY(cudaSetDevice(x->ctx->device));
+      if (!x->md_prepared) { if ((rc = preload_kernels())) return rc; }
+      if ((rc = prepare_compute(x))) return rc;
+      if (x->inj_stride == 0) {
+        const int count = x->kld ? x->max_particle_num : x->n_cap;
+        if (x->draw_cap < count) { if ((rc = ensure_draw_buffers(x, 1, count))) return rc; x->draw_cap = count; }
+      }
+      if (!x->aux_stream) {
+        PFT_CUDA_TRY(cudaStreamCreateWithFlags(&x->aux_stream, cudaStreamNonBlocking));
+        PFT_CUDA_TRY(cudaEventCreateWithFlags(&x->ev_fork, cudaEventDisableTiming));
+        PFT_CUDA_TRY(cudaEventCreateWithFlags(&x->ev_join, cudaEventDisableTiming));
+      }
+      x->md_prepared = true;
+    }
+  }
+  for (auto& f : t->followers) {
+    if ((rc = compute_one(f.t))) return rc;
+    PFT_CUDA_TRY(cudaSetDevice(f.ctx->device));
+    PFT_CUDA_TRY(cudaEventRecord(f.scene_free, f.ctx->stream));
+    f.free_recorded = true;
+  }
+  return compute_one(t);
+}
+
 int pft_tracker_compute(pft_tracker* t) {
   if (!t) { set_last_error("null tracker"); return PFT_ERR_INVALID; }
+  if (!t->followers.empty()) return compute_multi_device(t);
   return compute_one(t);
 }
 
@@ -1243,10 +1425,10 @@ int pft_compute_batch(pft_tracker** ts, int n) {
   }
   bool concurrent = n > 1;
   for (int i = 1; i < n && concurrent; ++i) concurrent = ts[i]->ctx == ts[0]->ctx;
-  for (int i = 0; i < n && concurrent; ++i) concurrent = !ts[i]->timing && !ts[i]->comm && !ts[i]->peer_mode;
+  for (int i = 0; i < n && concurrent; ++i) concurrent = !ts[i]->timing && !ts[i]->comm && !ts[i]->peer_mode && ts[i]->followers.empty();
   if (!concurrent) {
     for (int i = 0; i < n; ++i) {
-      int rc = compute_one(ts[i]);
+      int rc = pft_tracker_compute(ts[i]);
       if (rc) return rc;
     }
     return PFT_OK;
@@ -1375,6 +1557,7 @@ int pft_tracker_get_result_box(pft_tracker* t, float z_offset, pft_result_box* o
 }
 
 int pft_tracker_reset(pft_tracker* t) {
+  if (t) for (auto& f_ : t->followers) { int rc_ = pft_tracker_reset(f_.t); if (rc_) return rc_; }
   if (!t) { set_last_error("null tracker"); return PFT_ERR_INVALID; }
   // resetTracking: particles are re-drawn around trans_ on the next compute()
   if (t->kld && t->st.p && t->has_particles) {
@@ -1401,6 +1584,7 @@ int pft_tracker_reset(pft_tracker* t) {
 
 // ------------------------------------------------------------------ reproducibility / parity hooks
 int pft_tracker_set_particles(pft_tracker* t, const pft_particle* p, size_t n) {
+  if (t) for (auto& f_ : t->followers) { int rc_ = pft_tracker_set_particles(f_.t, p, n); if (rc_) return rc_; }
   if (!t || (n && !p)) { set_last_error("null argument"); return PFT_ERR_INVALID; }
   if (n == 0 || n > 0x7fffffffull) { set_last_error("bad particle count %zu", n); return PFT_ERR_INVALID; }
   PFT_CUDA_TRY(cudaSetDevice(t->ctx->device));
@@ -1420,6 +1604,7 @@ int pft_tracker_set_particles(pft_tracker* t, const pft_particle* p, size_t n) {
 }
 
 int pft_tracker_set_result(pft_tracker* t, const pft_particle* rep, const pft_particle* motion) {
+  if (t) for (auto& f_ : t->followers) { int rc_ = pft_tracker_set_result(f_.t, rep, motion); if (rc_) return rc_; }
   if (!t) { set_last_error("null tracker"); return PFT_ERR_INVALID; }
   PFT_CUDA_TRY(cudaSetDevice(t->ctx->device));
   int rc = ensure_particle_buffers(t);
@@ -1432,6 +1617,7 @@ int pft_tracker_set_result(pft_tracker* t, const pft_particle* rep, const pft_pa
 }
 
 int pft_tracker_inject_draws(pft_tracker* t, const float* usel, const float* normals6, const float* umot, int slots, int stride) {
+  if (t) for (auto& f_ : t->followers) { int rc_ = pft_tracker_inject_draws(f_.t, usel, normals6, umot, slots, stride); if (rc_) return rc_; }
   if (!t) { set_last_error("null tracker"); return PFT_ERR_INVALID; }
   PFT_CUDA_TRY(cudaSetDevice(t->ctx->device));
   invalidate_graph(t);
@@ -1454,6 +1640,7 @@ int pft_tracker_inject_draws(pft_tracker* t, const float* usel, const float* nor
 }
 
 int pft_tracker_seed(pft_tracker* t, uint64_t seed) {
+  if (t) for (auto& f_ : t->followers) { int rc_ = pft_tracker_seed(f_.t, seed); if (rc_) return rc_; }
   if (!t) { set_last_error("null tracker"); return PFT_ERR_INVALID; }
   t->seed = seed;
   invalidate_graph(t);
@@ -1495,6 +1682,7 @@ int pft_tracker_update(pft_tracker* t) {
   return stage_update(t);
 }
 int pft_tracker_set_changed(pft_tracker* t, int changed) {
+  if (t) for (auto& f_ : t->followers) { int rc_ = pft_tracker_set_changed(f_.t, changed); if (rc_) return rc_; }
   if (!t) { set_last_error("null tracker"); return PFT_ERR_INVALID; }
   t->changed = changed != 0;
   return PFT_OK;
@@ -1770,12 +1958,7 @@ int pft_tracker_set_shard(pft_tracker* t, int nranks, int rank) {
 // that every rank maps with CUDA IPC (see PeerWindow in pft_tracker_kernels.cuh).  Call order on every rank:
 //   set_shard / comm_init (rank layout) -> particle numbers -> peer_export -> [host framework all-gathers the
 //   64-byte handles] -> peer_attach -> compute ...
-int pft_tracker_peer_export(pft_tracker* t, void* handle64) {
-  if (!t || !handle64) { set_last_error("null argument"); return PFT_ERR_INVALID; }
-  if (t->nranks < 2) { set_last_error("peer exchange needs a rank layout: call pft_tracker_set_shard / pft_tracker_comm_init first"); return PFT_ERR_STATE; }
-  if (t->nranks > kMaxPeers) { set_last_error("peer exchange supports up to %d ranks", kMaxPeers); return PFT_ERR_INVALID; }
-  static_assert(sizeof(cudaIpcMemHandle_t) == PFT_PEER_HANDLE_BYTES, "handle size");
-  PFT_CUDA_TRY(cudaSetDevice(t->ctx->device));
+static int alloc_peer_window(pft_tracker* t) {
   int rc = ensure_particle_buffers(t);
   if (rc) return rc;
   if (!t->peer_local) {
@@ -1785,6 +1968,17 @@ int pft_tracker_peer_export(pft_tracker* t, void* handle64) {
     PFT_CUDA_TRY(cudaDeviceSynchronize());
     t->peer_bytes = bytes;
   }
+  return PFT_OK;
+}
+
+int pft_tracker_peer_export(pft_tracker* t, void* handle64) {
+  if (!t || !handle64) { set_last_error("null argument"); return PFT_ERR_INVALID; }
+  if (t->nranks < 2) { set_last_error("peer exchange needs a rank layout: call pft_tracker_set_shard / pft_tracker_comm_init first"); return PFT_ERR_STATE; }
+  if (t->nranks > kMaxPeers) { set_last_error("peer exchange supports up to %d ranks", kMaxPeers); return PFT_ERR_INVALID; }
+  static_assert(sizeof(cudaIpcMemHandle_t) == PFT_PEER_HANDLE_BYTES, "handle size");
+  PFT_CUDA_TRY(cudaSetDevice(t->ctx->device));
+  int rc = alloc_peer_window(t);
+  if (rc) return rc;
   cudaIpcMemHandle_t h;
   PFT_CUDA_TRY(cudaIpcGetMemHandle(&h, t->peer_local));
   memcpy(handle64, &h, sizeof(h));
@@ -1823,9 +2017,10 @@ int pft_tracker_peer_detach(pft_tracker* t) {
   if (!t->peer_local && !t->peer_mode) return PFT_OK;
   cudaSetDevice(t->ctx->device);
   cudaStreamSynchronize(t->run_stream());
-  if (t->peer_mode) {
+  if (t->peer_mode && t->peer_ipc) {
     for (int r = 0; r < t->peers.nranks; ++r) if (r != t->peers.rank && t->peers.win[r]) cudaIpcCloseMemHandle(t->peers.win[r]);
   }
+  t->peer_ipc = true;
   if (t->peer_local) cudaFree(t->peer_local);
   t->peer_local = nullptr; t->peer_bytes = 0; t->peer_mode = false;
   t->peers = PeerSet{};
@@ -1950,6 +2145,66 @@ int pft_cloud_peer_detach(pft_cloud* c) {
   c->peer_sync.release();
   if (c->peer_error) { cudaFreeHost(c->peer_error); c->peer_error = nullptr; }
   c->peer_exported = false; c->peer_attached = false; c->peer_nranks = 0; c->peer_epoch = 0;
+  return PFT_OK;
+}
+
+// ------------------------------------------------------------------ single-process multi-device mode
+// The reference is ONE process (ref: src/auto_tracking.cpp: one node, one tracker object).  pft_tracker_set_devices lets
+// that one tracker object drive n GPUs: rank 0 is the tracker itself (on devices[0] = its context's device), every
+// further device gets a follower tracker in a context of its own; the particle set is sharded as in the multi-process
+// mode (particle i on rank i % n), the exchange windows of weight() are mapped directly (cudaDeviceEnablePeerAccess),
+// the scene and the model are copied to every device by the library.  Call it right after pft_tracker_create: the
+// setters called afterwards are forwarded to the followers.  compute() and the getters work as before (the replicated
+// state is read from rank 0); the stage-by-stage debugging API (resample / weight / update) is not forwarded.
+int pft_tracker_set_devices(pft_tracker* t, int n, const int* devices) {
+  if (!t || n < 1 || !devices) { set_last_error("pft_tracker_set_devices: bad arguments"); return PFT_ERR_INVALID; }
+  if (n > kMaxPeers) { set_last_error("at most %d devices", kMaxPeers); return PFT_ERR_INVALID; }
+  if (t->n_cap > 0 || t->comm || t->nranks > 1 || !t->followers.empty()) { set_last_error("pft_tracker_set_devices must be the first call on a new tracker"); return PFT_ERR_STATE; }
+  if (devices[0] != t->ctx->device) { set_last_error("devices[0] must be the device of the tracker's context (%d)", t->ctx->device); return PFT_ERR_INVALID; }
+  if (n == 1) return PFT_OK;
+  int count = 0;
+  PFT_CUDA_TRY(cudaGetDeviceCount(&count));
+  for (int r = 0; r < n; ++r) if (devices[r] < 0 || devices[r] >= count) { set_last_error("device %d out of range [0,%d)", devices[r], count); return PFT_ERR_INVALID; }
+  for (int a = 0; a < n; ++a) {
+    for (int b = 0; b < n; ++b) {
+      if (devices[a] == devices[b]) continue;
+      int can = 0;
+      PFT_CUDA_TRY(cudaDeviceCanAccessPeer(&can, devices[a], devices[b]));
+      if (!can) { set_last_error("device %d cannot map the memory of device %d (needs NVLink/P2P)", devices[a], devices[b]); return PFT_ERR_COMM; }
+      PFT_CUDA_TRY(cudaSetDevice(devices[a]));
+      cudaError_t e = cudaDeviceEnablePeerAccess(devices[b], 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { set_last_error("cudaDeviceEnablePeerAccess(%d -> %d) -> %s", devices[a], devices[b], cudaGetErrorString(e)); cudaGetLastError(); return PFT_ERR_COMM; }
+      cudaGetLastError();
+    }
+  }
+  int rc = PFT_OK;
+  for (int r = 1; r < n && !rc; ++r) {
+    pft_tracker::Follower f;
+    if ((rc = pft_context_create(devices[r], &f.ctx))) break;
+    if (!rc) rc = pft_tracker_create(f.ctx, t->kld ? 1 : 0, &f.t);
+    if (!rc) rc = pft_cloud_create(f.ctx, &f.scene);
+    if (!rc) rc = pft_cloud_create(f.ctx, &f.model);
+    if (!rc) {
+      cudaSetDevice(t->ctx->device);
+      if (cudaEventCreateWithFlags(&f.scene_ready, cudaEventDisableTiming) != cudaSuccess) rc = PFT_ERR_CUDA;
+      cudaSetDevice(devices[r]);
+      if (cudaEventCreateWithFlags(&f.scene_free, cudaEventDisableTiming) != cudaSuccess) rc = PFT_ERR_CUDA;
+    }
+    if (!rc) { f.t->nranks = n; f.t->rank = r; f.t->graph_enabled = t->graph_enabled; }
+    t->followers.push_back(f);  // (also on failure: destroy_followers releases what exists)
+  }
+  if (rc) { destroy_followers(t); return rc; }
+  t->nranks = n; t->rank = 0;
+  invalidate_graph(t);
+  PFT_CUDA_TRY(cudaSetDevice(t->ctx->device));
+  return PFT_OK;
+}
+
+/* the follower tracker of rank `rank` (1 .. n-1) in multi-device mode: for inspection (getters) only */
+int pft_tracker_get_follower(pft_tracker* t, int rank, pft_tracker** out) {
+  if (!t || !out) { set_last_error("null argument"); return PFT_ERR_INVALID; }
+  if (rank < 1 || rank > (int)t->followers.size()) { set_last_error("no follower of rank %d", rank); return PFT_ERR_INVALID; }
+  *out = t->followers[rank - 1].t;
   return PFT_OK;
 }
 

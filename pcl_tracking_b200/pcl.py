@@ -458,11 +458,15 @@ class ParticleFilterOMPTracker:
 
     _KLD = 0
 
-    def __init__(self, nr_threads=0, ctx=None):
+    def __init__(self, nr_threads=0, ctx=None, devices=None):
+        """devices: single-process multi-device mode -- this one tracker object drives these GPUs (devices[0] = the device
+        of `ctx`), see setDevices."""
         self.ctx = ctx or Context.default()
         self._h = C.c_void_p()
         check(capi.load().pft_tracker_create(self.ctx._h, self._KLD, C.byref(self._h)))
         self._input = None
+        if devices is not None and len(devices) > 1:
+            self.setDevices(devices)
         self._si(capi.THREADS, nr_threads)
 
     # -- plumbing
@@ -766,6 +770,20 @@ class ParticleFilterOMPTracker:
     def commDestroy(self):
         check(capi.load().pft_tracker_comm_destroy(self._h))
 
+    def setDevices(self, devices):
+        """Single-process multi-device mode: this one tracker object drives the GPUs `devices` (devices[0] = the device of
+        its context).  Must be the first call on a new tracker; everything else stays as with one GPU."""
+        arr = (C.c_int * len(devices))(*[int(d) for d in devices])
+        check(capi.load().pft_tracker_set_devices(self._h, len(devices), arr))
+
+    def follower(self, rank):
+        """Multi-device mode: a borrowed view of the library-owned tracker of `rank` (1 .. n-1), for the getters."""
+        v = object.__new__(type(self))
+        v.ctx, v._input, v._h = self.ctx, None, C.c_void_p()
+        check(capi.load().pft_tracker_get_follower(self._h, int(rank), C.byref(v._h)))
+        v._borrowed = True
+        return v
+
     # NVLink peer exchange: the collectives of weight() as peer stores from the producing kernels
     def peerExport(self):
         """Allocates this rank's exchange window and returns its CUDA IPC handle (bytes).  Needs the rank
@@ -785,7 +803,7 @@ class ParticleFilterOMPTracker:
 
     def __del__(self):
         try:
-            if self._h:
+            if self._h and not getattr(self, "_borrowed", False):
                 capi.load().pft_tracker_destroy(self._h)
                 self._h = C.c_void_p()
         except Exception:

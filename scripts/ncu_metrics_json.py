@@ -13,7 +13,13 @@ METRICS = ["gpu__time_duration.sum", "smsp__inst_executed.sum", "smsp__issue_act
            "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
            "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
            "sm__cycles_active.avg", "sm__cycles_elapsed.max", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
-           "dram__throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed"]
+           "dram__throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+           "sass__inst_executed_local_loads", "sass__inst_executed_local_stores",  # executed LDL / STL (spills that actually run)
+           "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+           "smsp__inst_executed_op_shared_ld.sum", "smsp__inst_executed_op_global_ld.sum",
+           "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
+           "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
+           "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio"]
 out = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv", "--metrics", ",".join(METRICS)], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hdr, units = rows[0], rows[1]
@@ -26,6 +32,7 @@ for r in rows[2:]:
         k += 1
         key = "%s#%d" % (name, k)
     res[key] = {"%s [%s]" % (h, u): v for h, u, v in zip(hdr, units, r) if "__" in h}
+    res[key]["launch"] = "grid %s block %s" % (r[hdr.index("Grid Size")], r[hdr.index("Block Size")])
 import os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench  # noqa: E402

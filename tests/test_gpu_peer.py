@@ -240,3 +240,56 @@ def test_exported_cloud_refuses_to_grow():
     c.peerDetach()
     c.upload(_scene_frame(0)[:2000])
     assert c.size() == 2000
+
+
+# ---------------------------------------------------------------- single-process multi-device mode (pft_tracker_set_devices)
+def _multi_device_tracker(kld, devices):
+    from pcl_tracking_b200 import pcl
+    from tests import util
+    ctx = pcl.Context(devices[0])
+    scene, model, centre = util.small_case(77, n_scene=4000, n_model=260)
+    g = (pcl.KLDAdaptiveParticleFilterOMPTracker if kld else pcl.ParticleFilterOMPTracker)(16, ctx=ctx)
+    g.setDevices(devices)  # first call on the new tracker: the setters below reach every device
+    pcl.configure_like_reference(g, coherence_cls=pcl.NearestPairPointCloudCoherence, particle_num=N_PART, max_particle_num=N_MAX,
+                                 use_hsv=True, iteration_num=2)
+    if kld:
+        g.setEpsilon(0.2)
+        g.setBinSize([0.1] * 6)
+    m = np.eye(4, dtype=np.float32)
+    m[:3, 3] = centre
+    g.setTrans(m)
+    g.seed(99)
+    g.setReferenceCloud(model)
+    cloud = pcl.PointCloud(scene, ctx=ctx)
+    g.setInputCloud(cloud)
+    return ctx, g, cloud
+
+
+@pytest.mark.parametrize("kld,n_dev", [(False, 2), (True, 3)])
+def test_one_tracker_object_drives_several_devices(kld, n_dev):
+    """One process, one tracker object, n ranks: bit-identical to the plain single-GPU tracker over several frames (graph
+    replays included).  With fewer GPUs than ranks the ranks share GPU 0 (two contexts of this process on one device)."""
+    import torch
+    have = torch.cuda.device_count()
+    devices = list(range(n_dev)) if have >= n_dev else [0] * n_dev
+    ctx, g, cloud = _multi_device_tracker(kld, devices)
+    got = _run(g)
+    assert g.graphReplays() >= 1
+    ctx1, g1, cloud1 = _tracker(kld)
+    want = _run(g1)
+    for f in range(FRAMES):
+        for j, name in enumerate(("particles", "raw weights", "result")):
+            assert np.array_equal(got[f][j].view(np.uint32), want[f][j].view(np.uint32)), "%s differ: frame %d" % (name, f)
+    # the library-owned trackers of the other ranks hold the same replicated state
+    for r in range(1, n_dev):
+        fr = g.follower(r)
+        assert np.array_equal(fr.getParticles().view(np.uint32), want[-1][0].view(np.uint32)), "rank %d differs" % r
+        assert np.array_equal(fr.rawWeights().view(np.uint32), want[-1][1].view(np.uint32)), "rank %d differs" % r
+
+
+def test_set_devices_must_come_first():
+    from pcl_tracking_b200 import pcl
+    ctx, g, cloud = _tracker(False)
+    g.compute()
+    with pytest.raises(pcl.PftError):
+        g.setDevices([0, 0])

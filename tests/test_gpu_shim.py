@@ -26,6 +26,14 @@ def test_offline_driver_matches_python_path(tmp_path):
     out = subprocess.run([exe, str(tmp_path / "model.raw"), "4242"] + names, capture_output=True, text=True, check=True).stdout
     lines = [l.split() for l in out.strip().splitlines()]
     assert len(lines) == 3
+    # single-process multi-device mode through the shim (PFT_DEVICES; the ranks share GPU 0 when there is only one):
+    # the same one tracker object, the same poses
+    import os
+    import torch
+    devs = "0,1" if torch.cuda.device_count() >= 2 else "0,0"
+    out_md = subprocess.run([exe, str(tmp_path / "model.raw"), "4242"] + names, capture_output=True, text=True, check=True,
+                            env=dict(os.environ, PFT_DEVICES=devs)).stdout
+    assert out_md == out
     # the same pipeline through the Python mirror
     model, c = pcl.prepare_model(pcl.PointCloud(raw_model), 0.01)
     t = pcl.KLDAdaptiveParticleFilterOMPTracker(16)
