@@ -1147,6 +1147,10 @@ retry:
         }
       });
   const int n = *s_cnt;
+  __syncthreads();  // every thread holds the count before thread 0 reuses the counter for the survivors below (without
+                    // this barrier a warp that is scheduled late -- other kernels share the SM when several trackers
+                    // run side by side -- read 0 and left the block's barriers out of step: an intermittent fault of
+                    // the multi-object batch)
   if (n > kListKX) { if (threadIdx.x < 32) write_octant_codes(h, flists, fx, fy, fz, kListOverflow, 0, 0); return; }
   // ---- (3) pairwise pruning.  Far from the surface the two tests above keep hundreds of points (they only compare
   // with ONE competitor, p0); nearly all of them are beaten everywhere in the cell by some other candidate (a point
