@@ -28,8 +28,14 @@ def main():
             n_particles *= world
     ctx = pcl.Context(local_rank)
     stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
-    frames, oid0 = bench.make_frames(bench.N_FRAMES)
-    model_cloud, centroid = pcl.prepare_model(pcl.PointCloud(bench.raw_model(frames, oid0), ctx=ctx), bench.LEAF, ctx=ctx)
+    # c5:<k> = object k of the eight-object scene of bench.py's c5 workload, tracked alone (one of the batch's trackers)
+    obj_k = int(workload.split(":")[1]) if workload.startswith("c5") and ":" in workload else 0
+    if workload.startswith("c5"):
+        frames, oid0 = bench.make_frames(bench.N_FRAMES, bench.C5_OBJECTS)
+        workload = "c2"
+    else:
+        frames, oid0 = bench.make_frames(bench.N_FRAMES)
+    model_cloud, centroid = pcl.prepare_model(pcl.PointCloud(bench.raw_model(frames, oid0, obj_k), ctx=ctx), bench.LEAF, ctx=ctx)
     M = model_cloud.size()
     tracker = pcl.ParticleFilterOMPTracker(16, ctx=ctx)
     pcl.configure_like_reference(tracker, particle_num=n_particles, use_hsv=True, iteration_num=bench.ITERATIONS)

@@ -201,3 +201,40 @@ def test_c4_1000_random_particles_of_100k_vs_oracle():
     o.set_crop_box(g.aabb())
     o.weight()
     np.testing.assert_allclose(raw[pick], o.raw_weights(), rtol=1e-5)
+
+
+def test_c5_batch_equals_one_tracker_at_a_time_at_bench_size():
+    """C5 at bench.py's size (8 objects in the 217 088-pt scene, 1000 particles each, 2 iterations per frame, six moving
+    frames): pft_compute_batch -- every tracker's frame on a stream of its own, their kernels sharing the SMs -- must give
+    every tracker bit for bit what it computes alone.  (Guards the far pass of the list build: its shared counter was once
+    reused without a barrier, which only went wrong when other trackers' kernels delayed a warp.)"""
+    objs = synth.default_objects(8, seed=3)
+    frames = [synth.render(f, objs) for f in range(6)]
+    pts0, oid0 = frames[0]
+    vg = pcl.ApproximateVoxelGrid()
+    vg.setLeafSize(0.01)
+    vg.setPassThrough("z", 0.0, 10.0)
+    ds = pcl.PointCloud()
+    batch, alone = [], []
+    for k in range(8):
+        model, c = pcl.prepare_model(pcl.PointCloud(synth.model_points(pts0, oid0, k)), 0.01)
+        for lst in (batch, alone):
+            t = pcl.ParticleFilterOMPTracker(16)
+            pcl.configure_like_reference(t, particle_num=1000, use_hsv=True, iteration_num=2)
+            m = np.eye(4, dtype=np.float32)
+            m[:3, 3] = c
+            t.setTrans(m)
+            t.seed(500 + k)
+            t.setReferenceCloud(model)
+            lst.append(t)
+    for f, (pts, _) in enumerate(frames):
+        vg.setInputCloud(pcl.PointCloud(pts))
+        vg.filter(ds)
+        for t in batch + alone:
+            t.setInputCloud(ds)
+        pcl.compute_batch(batch)
+        for t in alone:
+            t.compute()
+        for k, (a, b) in enumerate(zip(batch, alone)):
+            assert np.array_equal(a.getParticles().view(np.uint32), b.getParticles().view(np.uint32)), "object %d, frame %d" % (k, f)
+    assert all(t.graphReplays() >= 1 for t in batch)
