@@ -237,4 +237,5 @@ def test_c5_batch_equals_one_tracker_at_a_time_at_bench_size():
             t.compute()
         for k, (a, b) in enumerate(zip(batch, alone)):
             assert np.array_equal(a.getParticles().view(np.uint32), b.getParticles().view(np.uint32)), "object %d, frame %d" % (k, f)
-    assert all(t.graphReplays() >= 1 for t in batch)
+    import os
+    assert os.environ.get("PFT_NO_GRAPH") == "1" or all(t.graphReplays() >= 1 for t in batch)
